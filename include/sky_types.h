@@ -1,0 +1,289 @@
+/*
+ * sky_types.h -- plain-old-data contract shared by the C-ABI library (libskyb200.so),
+ * the host library (libskyhost.so) and the CPU oracle (oracle/liboracle.so).
+ *
+ * Every struct here is the byte-for-byte std140 uniform block the reference host fills and
+ * the reference shaders read.  Keeping them verbatim is what makes the CUDA path a drop-in:
+ * a maintainer hands the very same bytes to sky_* that they hand to glNamedBufferSubData.
+ * Matrices are column-major (glm), m[c*4+r].
+ *
+ * Reference citations are relative to /root/reference.
+ */
+#ifndef SKY_TYPES_H
+#define SKY_TYPES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/SkyRendering/Atmosphere.cpp:21-47, shaders/SkyRendering/Atmosphere.glsl:6-32 (128 B) */
+typedef struct SkyAtmosphereBufferData {
+    float solar_illuminance[3];
+    float sun_angular_radius;
+    float rayleigh_scattering[3];
+    float inv_rayleigh_exponential_distribution;
+    float mie_scattering[3];
+    float inv_mie_exponential_distribution;
+    float mie_absorption[3];
+    float ozone_center_altitude;
+    float ozone_absorption[3];
+    float inv_ozone_width;
+    float ground_albedo[3];
+    float mie_phase_g;
+    float _atmosphere_padding[3];
+    float multiscattering_mask;
+    float bottom_radius;
+    float top_radius;
+    float transmittance_steps;
+    float multiscattering_steps;
+} SkyAtmosphereBufferData;
+
+/* src/SkyRendering/AtmosphereRenderer.cpp:25-50, shaders/SkyRendering/AtmosphereRenderer.glsl:25-50 (320 B) */
+typedef struct SkyAtmosphereRenderBufferData {
+    float sun_direction[3];
+    float star_luminance_scale;
+    float earth_center[3];
+    float camera_earth_center_distance;
+    float camera_position[3];
+    float raymarching_steps;
+    float up_direction[3];
+    float sky_view_lut_steps;
+    float right_direction[3];
+    float aerial_perspective_lut_steps;
+    float front_direction[3];
+    float aerial_perspective_lut_max_distance;
+    float moon_position[3];
+    float moon_radius;
+    float inv_view_projection[16];
+    float light_view_projection[16];
+    float padding00;
+    float uInvShadowFroxelMaxDistance;
+    float blocker_kernel_size_k;
+    float pcss_size_k;
+    float uCloudShadowMapMat[16];
+} SkyAtmosphereRenderBufferData;
+
+/* src/SkyRendering/VolumetricCloud.cpp:11-33, shaders/SkyRendering/VolumetricCloudCommon.glsl:6-28 (384 B) */
+typedef struct SkyCloudCommonBufferData {
+    float uInvMVP[16];
+    float uReprojectMat[16];
+    float uLightVP[16];
+    float uInvLightVP[16];
+    float uShadowMapReprojectMat[16];
+    float uCameraPos[3];
+    uint32_t uBaseShadingIndex;
+    float uLinearDepthParam[2];
+    float uBottomAltitude;
+    float uTopAltitude;
+    float uSunDirection[3];
+    float uFrameID;
+    float uInvShadowFroxelMaxDistance;
+    float uAerialPerspectiveLutMaxDistance;
+    float uShadowFroxelMaxDistance;
+    float uEarthRadius;
+} SkyCloudCommonBufferData;
+
+/* src/SkyRendering/VolumetricCloud.cpp:35-50, shaders/SkyRendering/VolumetricCloudRender.comp:17-32 (64 B) */
+typedef struct SkyCloudBufferData {
+    float uSunIlluminanceScale;
+    float uMaxRaymarchDistance;
+    float uMaxRaymarchSteps;
+    float uMaxVisibleDistance;
+    float uEnvColorScale[3];
+    float uShadowSteps;
+    float uSunMultiscatteringSigmaScale;
+    float uEnvMultiscatteringSigmaScale;
+    float uShadowDistance;
+    float uEnvBottomVisibility;
+    float padding_[3];
+    float uEnvSunHeightCurveExp;
+} SkyCloudBufferData;
+
+/* src/SkyRendering/VolumetricCloudDefaultMaterial.cpp:9-22 (64 B) */
+typedef struct SkySampleInfo {
+    float bias[2];
+    float frequency;
+    float k_lod;
+} SkySampleInfo;
+
+typedef struct SkyMaterialCommonBufferData {
+    SkySampleInfo uCloudMapSampleInfo;
+    SkySampleInfo uDetailSampleInfo;
+    SkySampleInfo uDisplacementSampleInfo;
+    float padding0[2];
+    float uLodBias;
+    float uDensity;
+} SkyMaterialCommonBufferData;
+
+/* src/SkyRendering/VolumetricCloudDefaultMaterial.cpp:183-187 (16 B) */
+typedef struct SkyMaterial0BufferData {
+    float uDetailParam[2];
+    float uDisplacementScale;
+    float padding1;
+} SkyMaterial0BufferData;
+
+/* src/SkyRendering/VolumetricCloudDefaultMaterial.cpp:228-237 (32 B) */
+typedef struct SkyMaterial1BufferData {
+    float uBaseDensityThreshold;
+    float uBaseHeightHardness;
+    float uBaseEdgeHardness;
+    float uDetailBase;
+    float uDetailScale;
+    float uHeightCut;
+    float uEdgeCur;
+    float padding1;
+} SkyMaterial1BufferData;
+
+/* src/SkyRendering/VolumetricCloudVoxelMaterial.cpp:17-24 (32 B) */
+typedef struct SkyMaterialVoxelBufferData {
+    float uSampleFrequency[2];
+    float uLodBias;
+    float uDensity;
+    float uSampleBias[2];
+    float uSampleLodK;
+    float voxel_material_padding;
+} SkyMaterialVoxelBufferData;
+
+/* src/SkyRendering/VolumetricCloudMinimalMaterial.cpp:5-8 (16 B) */
+typedef struct SkyMaterialMinimalBufferData {
+    float padding[3];
+    float uDensity;
+} SkyMaterialMinimalBufferData;
+
+/* One tagged block that carries whichever material the scene uses.
+ * The reference binds the common block at UBO 3 and the specific one at UBO 4
+ * (VolumetricCloudDefaultMaterial.cpp:104-117,214-217); Voxel/Minimal bind theirs at UBO 3. */
+enum SkyMaterialType {
+    SKY_MATERIAL_DEFAULT0 = 0, /* VolumetricCloudDefaultMaterial0.glsl */
+    SKY_MATERIAL_DEFAULT1 = 1, /* VolumetricCloudDefaultMaterial1.glsl */
+    SKY_MATERIAL_MINIMAL = 2,  /* VolumetricCloudMaterialMinimal.glsl  */
+    SKY_MATERIAL_VOXEL = 3     /* VolumetricCloudMaterialVoxel.glsl    */
+};
+
+typedef struct SkyMaterialBlock {
+    int32_t type; /* SkyMaterialType */
+    int32_t _pad[3];
+    SkyMaterialCommonBufferData common; /* DEFAULT0 / DEFAULT1 */
+    union {
+        SkyMaterial0BufferData m0;
+        SkyMaterial1BufferData m1;
+        SkyMaterialVoxelBufferData voxel;
+        SkyMaterialMinimalBufferData minimal;
+    } u;
+} SkyMaterialBlock;
+
+/* src/SkyRendering/VolumetricCloudDefaultMaterial.h:57-61, shaders/SkyRendering/NoiseGen.comp:5-10 (16 B).
+ * Stored as int on the C++ side, read as uint by the shader. */
+typedef struct SkyNoiseCreateInfo {
+    uint32_t seed;
+    uint32_t base_frequency;
+    float remap_min;
+    float remap_max;
+} SkyNoiseCreateInfo;
+
+enum SkyNoiseKind {
+    SKY_NOISE_CLOUD_MAP = 0,    /* CLOUD_MAP_GEN:    RG8 512x512,   info[0]=uDensity info[1]=uHeight */
+    SKY_NOISE_DETAIL = 1,       /* DETAIL_MAP_GEN:   R8 128^3,      info[0]=uPerlin  info[1]=uWorley */
+    SKY_NOISE_DISPLACEMENT = 2  /* DISPLACEMENT_GEN: RGBA8 128x128, info[0]=uPerlin                  */
+};
+
+/* Compile-time permutation flags of AtmosphereRenderer (AtmosphereRenderer.h:44-66,
+ * AtmosphereRenderer.cpp:91-107) plus the LUT sizes the reference hard-codes (:15-23). */
+typedef struct SkyLutConfig {
+    int32_t sky_view_width;   /* reference: 128 (AtmosphereRenderer.cpp:15) */
+    int32_t sky_view_height;  /* reference: 128 */
+    int32_t aerial_perspective_depth; /* aerial_perspective_lut_depth; width/height are 32 */
+    int32_t environment_size; /* reference: 128 (AtmosphereRenderer.cpp:23) */
+    int32_t use_sky_view_lut;
+    int32_t use_aerial_perspective_lut;
+    int32_t sky_view_dither;            /* sky_view_lut_dither_sample_point_enable            */
+    int32_t aerial_perspective_dither;  /* aerial_perspective_lut_dither_sample_point_enable  */
+    int32_t raymarching_dither;         /* raymarching_dither_sample_point_enable             */
+    int32_t _pad[3];
+} SkyLutConfig;
+
+/* VolumetricCloud::PathTracing::InitParam (VolumetricCloud.h:158-168) plus the compile-time
+ * constants its constructor bakes into the shader text (VolumetricCloud.cpp:505-519). */
+enum SkyPrng { SKY_PRNG_WANG = 0, SKY_PRNG_PCG = 1 };
+enum SkyEnvLight {
+    SKY_ENV_OFF = 0,
+    SKY_ENV_CONST_ENVIRONMENT_MAP = 1,
+    SKY_ENV_GROUND_SINGLE_BOUNCE = 2,
+    SKY_ENV_GROUND_MULTI_BOUNCE = 3
+};
+
+typedef struct SkyPathTracingInit {
+    int32_t sqrt_tile_count;
+    int32_t max_bounces;
+    float region_box_half_width;
+    int32_t importance_sampling;
+    float forward_phase_g;
+    float back_phase_g;
+    float forward_scattering_ratio;
+    int32_t prng;                 /* SkyPrng */
+    int32_t environment_lighting; /* SkyEnvLight */
+    float sigma_t_max;            /* material->GetSigmaTMax() */
+    float model_matrix3[9];       /* column-major upper 3x3 of VolumetricCloud::model_ */
+    int32_t _pad;
+} SkyPathTracingInit;
+
+/* Identifiers for sky_get_resource / sky_read_resource.  Layouts are row-major, x fastest,
+ * origin = GL texel (0,0); channel counts and element types as the reference allocates them. */
+enum SkyResource {
+    SKY_RES_TRANSMITTANCE = 0,        /* float4 [64][256]          Atmosphere.cpp:9-15          */
+    SKY_RES_MULTISCATTERING = 1,      /* float4 [32][32]           Atmosphere.cpp:17-19         */
+    SKY_RES_SKY_VIEW_LUMINANCE = 2,   /* float4 [H][W]             AtmosphereRenderer.cpp:15-17 */
+    SKY_RES_SKY_VIEW_TRANSMITTANCE = 3,
+    SKY_RES_AERIAL_LUMINANCE = 4,     /* float4 [D][32][32]        AtmosphereRenderer.cpp:19-21 */
+    SKY_RES_AERIAL_TRANSMITTANCE = 5,
+    SKY_RES_ENVIRONMENT = 6,          /* half4  [6][S][S]          AtmosphereRenderer.cpp:154   */
+    SKY_RES_CLOUD_MAP = 7,            /* u8x2   [512][512] mip 0   VolumetricCloudDefaultMaterial.cpp:32-43 */
+    SKY_RES_DETAIL = 8,               /* u8     [128][128][128]    :46-57 */
+    SKY_RES_DISPLACEMENT = 9,         /* u8x4   [128][128]         :60-71 */
+    SKY_RES_SHADOW_MAP_RAW = 10,      /* float2 [512][512]  shadow_maps_[0] after K11 */
+    SKY_RES_SHADOW_MAP = 11,          /* float2 [512][512]  shadow_maps_[2] after K12 */
+    SKY_RES_SHADOW_FROXEL = 12,       /* u16    [128][H/12][W/12]  VolumetricCloud.cpp:134-135  */
+    SKY_RES_CHECKERBOARD_DEPTH = 13,  /* float  [H/2][W/2]         :121-122 */
+    SKY_RES_INDEX_LINEAR_DEPTH = 14,  /* float2 [H/4][W/4]         :123-124 */
+    SKY_RES_CLOUD_RENDER = 15,        /* half4  [H/4][W/4]         :125-126 */
+    SKY_RES_CLOUD_DISTANCE = 16,      /* float  [H/4][W/4]         :127-128 */
+    SKY_RES_RECONSTRUCT = 17,         /* half4  [H/2][W/2]  newest reconstruct_texture_ */
+    SKY_RES_PT_ACCUM = 18,            /* float4 [H][W]             :498-501 */
+    SKY_RES_PT_MASK = 19,             /* u8     [H][W]             :502-503 */
+    SKY_RES_VOXEL = 20,               /* u8     [dz][dy][dx] mip 0 VolumetricCloudVoxelMaterial.cpp:72-74 */
+    SKY_RES_CLOUD_MAP_MIPS = 21,      /* all mips >= 1, concatenated, same element type */
+    SKY_RES_DETAIL_MIPS = 22,
+    SKY_RES_DISPLACEMENT_MIPS = 23,
+    SKY_RES_VOXEL_MIPS = 24,
+    SKY_RES_COUNTERS = 25,            /* uint64 [8]: work counters, see sky_counters */
+    SKY_RES_COUNT_
+};
+
+enum SkyFormat {
+    SKY_FMT_F32 = 0, SKY_FMT_F16 = 1, SKY_FMT_U8 = 2, SKY_FMT_U16 = 3, SKY_FMT_U64 = 4
+};
+
+typedef struct SkyResourceDesc {
+    void* ptr;          /* borrowed; device pointer for libskyb200, host pointer for the oracle */
+    int32_t width, height, depth, channels;
+    int32_t format;     /* SkyFormat */
+    int32_t _pad;
+    uint64_t bytes;
+} SkyResourceDesc;
+
+/* Slots of SKY_RES_COUNTERS (incremented only when counting is enabled). */
+enum SkyCounter {
+    SKY_CNT_RENDER_SIGMA_EVALS = 0,  /* SampleSigmaT calls made by K16                */
+    SKY_CNT_RENDER_TEX_FETCHES = 1,  /* texture fetches those calls issued            */
+    SKY_CNT_PT_PATHS = 2,            /* pixel-samples traced by K19                   */
+    SKY_CNT_PT_LOOKUPS = 3,          /* SampleSigmaT calls made by K19                */
+    SKY_CNT_PT_COLLISIONS = 4,       /* tentative collisions incl. the provably-empty */
+    SKY_CNT_SHADOW_SIGMA_EVALS = 5   /* SampleSigmaT calls made by K11                */
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKY_TYPES_H */

@@ -1,0 +1,135 @@
+/*
+ * skyb200.h -- C ABI of the B200-native SkyRendering hot path (libskyb200.so).
+ *
+ * The reference has no FFI; its seam is the C++ class API of the render subsystems plus the
+ * std140 blocks they upload.  Each entry point below replaces one
+ * host call (+ the GLSL programs it dispatches); the citation names that call.
+ *
+ * The same declarations are compiled a second time with the prefix orc_ by the CPU oracle
+ * (oracle/oracle_api.cpp) so that a test drives both through one binding; the oracle is test
+ * infrastructure only and is never linked into or called from this library.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; sky_last_error() gives the text
+ *     (the reference throws std::runtime_error, e.g. VolumetricCloud.cpp:169-170).
+ *   - one context per GPU, externally synchronised, all work on the stream given at creation;
+ *     no hidden host synchronisation except in sky_read_resource / *_host entry points.
+ *   - "dev" pointers are device pointers (host pointers for the oracle build).
+ *   - images: row-major, x fastest, row 0 = GL texel row 0 (bottom of the screen).
+ */
+#ifndef SKYB200_H
+#define SKYB200_H
+
+#include "sky_types.h"
+
+#ifndef SKY_FN
+#define SKY_FN(name) sky_##name
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SkyContext SkyContext;
+
+/* Context = the GL context + every GLTexture/GLBuffer the subsystems own
+ * (Atmosphere.h:84-91, AtmosphereRenderer.h:118-128, VolumetricCloud.h:99-128). */
+int SKY_FN(ctx_create)(int device, void* cuda_stream, SkyContext** out);
+void SKY_FN(ctx_destroy)(SkyContext* ctx);
+const char* SKY_FN(last_error)(SkyContext* ctx);
+/* Block until all work queued on the context's stream has finished. */
+int SKY_FN(sync)(SkyContext* ctx);
+
+/* Textures::Textures blue-noise upload (src/Base/src/Textures.cpp:19-26): 64x64 R16, rows already
+ * in GL order (i.e. the PNG flipped vertically, StbImage.cpp:12-17). */
+int SKY_FN(set_blue_noise)(SkyContext* ctx, const uint16_t* host_texels_64x64);
+
+/* VolumetricCloud::SetViewport (VolumetricCloud.cpp:115-136): (re)allocates the per-viewport
+ * targets and zero-fills the temporal histories. */
+int SKY_FN(set_viewport)(SkyContext* ctx, int width, int height);
+
+/* Atmosphere::UpdateLuts (Atmosphere.cpp:101-124): K1 transmittance + K2 multiscattering. */
+int SKY_FN(atmosphere_bake)(SkyContext* ctx, const SkyAtmosphereBufferData* atmosphere);
+
+/* AtmosphereRenderer::Render up to the environment cube (AtmosphereRenderer.cpp:164-242):
+ * K3 sky-view, K4 aerial perspective, K5 environment luminance. */
+int SKY_FN(atmosphere_luts)(SkyContext* ctx, const SkyAtmosphereRenderBufferData* render,
+                            const SkyLutConfig* config);
+
+/* AtmosphereRenderer::Render full-screen pass (AtmosphereRenderer.cpp:246-250, K6), sky / aerial
+ * perspective / sun-disc branches.  depth_dev: float[H][W] in [0,1]; hdr_dev: half4[H][W] (written).
+ * Ground/object pixels receive the atmosphere in-scatter only and alpha = 0 marks them
+ * (object shading is outside the hot path). */
+int SKY_FN(composite)(SkyContext* ctx, const float* depth_dev, void* hdr_dev, int width, int height);
+
+/* DynamicTexture::Generate (VolumetricCloudDefaultMaterial.h:39-49): K8/K9/K10 + mip chain. */
+int SKY_FN(noise_generate)(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info);
+
+/* VolumetricCloudVoxelMaterial ctor upload (VolumetricCloudVoxelMaterial.cpp:72-75): R8 grid
+ * [dz][dy][dx] (dx = vdb x, dy = vdb z, dz = vdb y) + mip chain. */
+int SKY_FN(voxel_upload)(SkyContext* ctx, const uint8_t* host_voxels, int dx, int dy, int dz);
+
+/* IVolumetricCloudMaterial::Update/Bind (IVolumetricCloudMaterial.h:17-19): material uniforms. */
+int SKY_FN(set_material)(SkyContext* ctx, const SkyMaterialBlock* material);
+
+/* VolumetricCloud::RenderShadow (VolumetricCloud.cpp:282-325): K11 -> K12 x2 -> K13. */
+int SKY_FN(cloud_shadow)(SkyContext* ctx, const SkyCloudCommonBufferData* common);
+
+/* VolumetricCloud::Render (VolumetricCloud.cpp:327-423): K14 -> K15 -> K16 -> K17 -> K18.
+ * depth_dev float[H][W]; hdr_dev half4[H][W] read-modify-write. */
+int SKY_FN(cloud_frame)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
+                        const SkyCloudBufferData* cloud, const float* depth_dev, void* hdr_dev);
+
+/* The same frame split at the one exchange point a tile-sharded run needs:
+ * _begin runs K14, K15 and K16 for quarter-res rows r with (r / band_rows) % band_count == band_index;
+ * _end runs K17, K18 once every row of SKY_RES_CLOUD_RENDER / SKY_RES_CLOUD_DISTANCE is present. */
+int SKY_FN(cloud_frame_begin)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
+                              const SkyCloudBufferData* cloud, const float* depth_dev,
+                              int band_rows, int band_index, int band_count);
+int SKY_FN(cloud_frame_end)(SkyContext* ctx, const float* depth_dev, void* hdr_dev);
+
+/* cloud_frame with HOST buffers: copies depth and hdr in, runs the frame, copies hdr out and
+ * synchronises -- the call a host application without device pointers makes. */
+int SKY_FN(cloud_frame_host)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
+                             const SkyCloudBufferData* cloud, const float* depth_host, void* hdr_host);
+
+/* VolumetricCloud::PathTracing ctor (VolumetricCloud.cpp:495-531): allocates + clears accumulators. */
+int SKY_FN(pt_begin)(SkyContext* ctx, const SkyPathTracingInit* init);
+
+/* PathTracing::Render render pass (VolumetricCloud.cpp:533-560, K19) for kFrameId in
+ * [frame_begin, frame_begin+count) over kRenderRegion = {x0,y0,x1,y1}. */
+int SKY_FN(pt_samples)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
+                       uint32_t frame_begin, uint32_t count, const int32_t region[4]);
+
+/* PathTracing::Render display pass (VolumetricCloud.cpp:562-565, K20): hdr = hdr*avg.a + avg.rgb,
+ * avg = accum / frame_count. */
+int SKY_FN(pt_resolve)(SkyContext* ctx, uint32_t frame_count, void* hdr_dev);
+
+/* pt_samples + host read-back of the accumulation buffer (float4[H][W]). */
+int SKY_FN(pt_samples_host)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
+                            uint32_t frame_begin, uint32_t count, const int32_t region[4],
+                            float* accum_host);
+
+/* Texture getters (Atmosphere.h:76-82, AtmosphereRenderer.h:96-108, VolumetricCloud.h:59-73). */
+int SKY_FN(get_resource)(SkyContext* ctx, int resource, SkyResourceDesc* out);
+int SKY_FN(read_resource)(SkyContext* ctx, int resource, void* host_dst, uint64_t bytes);
+/* Overwrite a resource from host memory (used to inject LUTs / histories in tests and to
+ * install the result of a collective). */
+int SKY_FN(write_resource)(SkyContext* ctx, int resource, const void* host_src, uint64_t bytes);
+
+/* Work counters for the roofline: enable != 0 switches kernels to their counting
+ * variants; counters live in SKY_RES_COUNTERS and are reset here. */
+int SKY_FN(counters_enable)(SkyContext* ctx, int enable);
+
+/* Which filtering the material textures use: 0 = exact fp32 software filtering on gathered
+ * texels (default; matches the oracle), 1 = hardware linear filtering (8-bit weights). */
+int SKY_FN(set_hw_filtering)(SkyContext* ctx, int enable);
+
+/* Microbenchmark for the texture-pipe roofline: launches `iters` dependent-free trilinear R8
+ * fetches per thread over the detail volume and returns texel-quads per second. */
+int SKY_FN(tex_peak)(SkyContext* ctx, int mode, double* fetches_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYB200_H */

@@ -1,0 +1,72 @@
+/*
+ * skyhost.h -- C ABI of the host-side parameter surface (libskyhost.so, plain C++17, no CUDA).
+ *
+ * It mirrors the reference host classes that turn a scene JSON + camera into the uniform blocks
+ * of sky_types.h; the blocks are then handed to libskyb200.so (skyb200.h).  Citations are
+ * relative to /root/reference.  All functions return 0 on success; skyhost_last_error() has
+ * the message otherwise (the reference throws std::runtime_error / R_ASSERT).
+ */
+#ifndef SKYHOST_H
+#define SKYHOST_H
+
+#include "sky_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SkyScene SkyScene;
+
+const char* skyhost_last_error(void);
+
+/* AppWindow::Init (src/SkyRendering/AppWindow.cpp:30-53): parse (comments and trailing commas
+ * allowed) and deserialise; keys that are absent keep their C++ defaults and are listed by
+ * skyhost_scene_log. */
+int skyhost_scene_load(const char* json_text, SkyScene** out);
+void skyhost_scene_destroy(SkyScene* scene);
+const char* skyhost_scene_log(SkyScene* scene);
+/* AppWindow::SaveConfig (AppWindow.cpp:128-137).  Returns the required size (including NUL) when
+ * buf is NULL or too small, 0 on success. */
+int64_t skyhost_scene_save(SkyScene* scene, char* buf, int64_t capacity);
+
+/* Earth::Update -> AssignBufferData (src/SkyRendering/Atmosphere.cpp:49-70). */
+int skyhost_atmosphere_buffer(SkyScene* scene, SkyAtmosphereBufferData* out);
+/* AtmosphereRenderInitParameters -> shader permutation flags (AtmosphereRenderer.cpp:91-107). */
+int skyhost_lut_config(SkyScene* scene, SkyLutConfig* out);
+/* AtmosphereRenderer::Render's AssignBufferData (AtmosphereRenderer.cpp:52-83,168-174); also
+ * records sun_direction() / aerial_perspective_lut().max_distance for the next cloud update. */
+int skyhost_atmosphere_render_buffer(SkyScene* scene, SkyAtmosphereRenderBufferData* out);
+
+/* VolumetricCloud::SetViewport (VolumetricCloud.cpp:115-118); also sets camera aspect like
+ * AppWindow::HandleReshapeEvent (AppWindow.cpp:559-566). */
+int skyhost_set_viewport(SkyScene* scene, int width, int height);
+/* VolumetricCloud::Update (VolumetricCloud.cpp:168-280) incl. material->Update; delta_time is
+ * ImGui::GetIO().DeltaTime in the reference. */
+int skyhost_cloud_update(SkyScene* scene, float delta_time, SkyCloudCommonBufferData* common,
+                         SkyCloudBufferData* cloud, SkyMaterialBlock* material);
+/* Noise parameters of the scene's material (VolumetricCloudDefaultMaterial.h:63-84); returns 1
+ * in *has when the material owns that texture. */
+int skyhost_noise_info(SkyScene* scene, int kind, SkyNoiseCreateInfo out[2], int* has);
+/* Voxel material: level-0 grid size (VolumetricCloudVoxelMaterial.cpp:53). */
+int skyhost_set_voxel_dim(SkyScene* scene, int dx, int dy, int dz);
+int skyhost_material_type(SkyScene* scene, int* type);
+
+/* PathTracing ctor constants + tile schedule (VolumetricCloud.cpp:495-519,571-581). */
+int skyhost_pt_params(SkyScene* scene, int sqrt_tile_count, int max_bounces, float region_box_half_width,
+                      int importance_sampling, int prng, int environment_lighting);
+int skyhost_pt_init(SkyScene* scene, SkyPathTracingInit* out);
+int skyhost_pt_region(SkyScene* scene, int tile_index, int32_t region[4]);
+
+/* Camera (src/Base/include/Camera.h): pose access for moving-camera tests. */
+int skyhost_camera_get(SkyScene* scene, float position[3], float front[3], float* fovy, float* z_near, float* z_far);
+int skyhost_camera_move(SkyScene* scene, const float delta_position[3], float d_pitch, float d_yaw);
+int skyhost_view_projection(SkyScene* scene, float view_projection[16]);
+
+/* Synthetic depth input: what the ground pass (shaders/SkyRendering/EarthRender.frag:40-52) writes
+ * into the D24 depth buffer, 1.0 elsewhere. */
+int skyhost_ground_depth(SkyScene* scene, float* depth, int width, int height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYHOST_H */

@@ -1,0 +1,323 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see glsl.h).
+//
+// oracle_api.cpp: exposes the CPU restatement behind the very same C ABI as libskyb200.so, with
+// the prefix orc_ (include/skyb200.h compiled with SKY_FN(name) = orc_##name), so that one ctypes
+// binding drives either side on identical inputs.  "dev" pointers are host pointers here.
+#define SKY_FN(name) orc_##name
+#include "../include/skyb200.h"
+
+#include <cstdio>
+#include <string>
+
+#include "cloud.h"
+
+using namespace orc;
+
+struct SkyContext {
+    CloudScene scene;
+    std::string error;
+    std::vector<uint8_t> scratch;   // packed copies handed out by get_resource
+    std::vector<uint64_t> counter_copy;
+};
+
+namespace {
+int fail(SkyContext* ctx, const char* msg) { if (ctx) ctx->error = msg; return 1; }
+
+template <int C>
+void pack_unorm(const Image<C>& img, int bits, std::vector<uint8_t>& out) {
+    size_t n = img.data.size();
+    float m = float((1u << bits) - 1u);
+    if (bits == 8) {
+        out.resize(n);
+        for (size_t i = 0; i < n; ++i) out[i] = uint8_t(std::nearbyint(img.data[i] * m));
+    } else {
+        out.resize(n * 2);
+        uint16_t* p = reinterpret_cast<uint16_t*>(out.data());
+        for (size_t i = 0; i < n; ++i) p[i] = uint16_t(std::nearbyint(img.data[i] * m));
+    }
+}
+template <int C>
+void pack_half(const Image<C>& img, std::vector<uint8_t>& out) {
+    size_t n = img.data.size();
+    out.resize(n * 2);
+    uint16_t* p = reinterpret_cast<uint16_t*>(out.data());
+    for (size_t i = 0; i < n; ++i) p[i] = float_to_half_bits(img.data[i]);
+}
+template <int C>
+void pack_mips(const MipTexture<C>& t, std::vector<uint8_t>& out) {
+    out.clear();
+    for (size_t l = 1; l < t.levels.size(); ++l) {
+        std::vector<uint8_t> tmp;
+        pack_unorm(t.levels[l], 8, tmp);
+        out.insert(out.end(), tmp.begin(), tmp.end());
+    }
+}
+template <int C>
+void set_desc_f32(SkyResourceDesc* d, Image<C>& img) {
+    d->ptr = img.data.data(); d->width = img.w; d->height = img.h; d->depth = img.d; d->channels = C;
+    d->format = SKY_FMT_F32; d->bytes = img.data.size() * 4;
+}
+}  // namespace
+
+extern "C" {
+
+int orc_ctx_create(int, void*, SkyContext** out) {
+    *out = new SkyContext();
+    (*out)->scene.blue_noise.resize(64, 64);
+    (*out)->scene.transmittance.resize(256, 64);    // Atmosphere.cpp:11-12
+    (*out)->scene.multiscattering.resize(32, 32);   // Atmosphere.cpp:17-18
+    return 0;
+}
+void orc_ctx_destroy(SkyContext* ctx) { delete ctx; }
+const char* orc_last_error(SkyContext* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+int orc_sync(SkyContext*) { return 0; }
+
+int orc_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
+    for (int i = 0; i < 64 * 64; ++i) ctx->scene.blue_noise.data[i] = float(texels[i]) / 65535.0f;
+    return 0;
+}
+
+int orc_set_viewport(SkyContext* ctx, int w, int h) {
+    if (w < 12 || h < 12) return fail(ctx, "viewport too small");
+    ctx->scene.SetViewport(w, h);
+    return 0;
+}
+
+int orc_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
+    ctx->scene.atm.u = *a;
+    ctx->scene.atm.BakeTransmittance(ctx->scene.transmittance);
+    ctx->scene.atm.BakeMultiscattering(ctx->scene.transmittance, ctx->scene.multiscattering);
+    return 0;
+}
+
+int orc_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg) {
+    CloudScene& s = ctx->scene;
+    s.render_u = *r;
+    s.lut_cfg = *cfg;
+    s.sky_lum.resize(cfg->sky_view_width, cfg->sky_view_height);
+    s.sky_trans.resize(cfg->sky_view_width, cfg->sky_view_height);
+    s.ap_lum.resize(32, 32, cfg->aerial_perspective_depth);  // AtmosphereRenderer.cpp:19-20
+    s.ap_trans.resize(32, 32, cfg->aerial_perspective_depth);
+    s.env.resize(cfg->environment_size, cfg->environment_size, 6);
+    AtmosphereRenderer ar{s.atm, *r, *cfg, s.transmittance, s.multiscattering, &s.blue_noise};
+    ar.BakeSkyView(s.sky_lum, s.sky_trans);
+    ar.BakeAerialPerspective(s.ap_lum, s.ap_trans);
+    ar.BakeEnvironment(s.sky_lum, s.sky_trans, s.env);
+    return 0;
+}
+
+int orc_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
+    CloudScene& s = ctx->scene;
+    AtmosphereRenderer ar{s.atm, s.render_u, s.lut_cfg, s.transmittance, s.multiscattering, &s.blue_noise};
+    const Image<1>* froxel = (s.shadow_froxel.w > 0) ? &s.shadow_froxel : nullptr;
+    ar.Composite(s.sky_lum, s.sky_trans, s.ap_lum, s.ap_trans, froxel, depth, width, height, static_cast<uint16_t*>(hdr));
+    return 0;
+}
+
+int orc_noise_generate(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info) {
+    switch (kind) {
+        case SKY_NOISE_CLOUD_MAP: GenerateCloudMap(info, ctx->scene.cloud_map); return 0;
+        case SKY_NOISE_DETAIL: GenerateDetail(info, ctx->scene.detail); return 0;
+        case SKY_NOISE_DISPLACEMENT: GenerateDisplacement(info, ctx->scene.displacement); return 0;
+    }
+    return fail(ctx, "unknown noise kind");
+}
+
+int orc_voxel_upload(SkyContext* ctx, const uint8_t* v, int dx, int dy, int dz) {
+    MipTexture<1>& t = ctx->scene.voxel;
+    t.bits = 8;
+    t.levels.resize(1);
+    t.levels[0].resize(dx, dy, dz);
+    for (size_t i = 0; i < t.levels[0].data.size(); ++i) t.levels[0].data[i] = float(v[i]) / 255.0f;
+    t.build_mips();
+    return 0;
+}
+
+int orc_set_material(SkyContext* ctx, const SkyMaterialBlock* m) { ctx->scene.material = *m; return 0; }
+
+int orc_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
+    CloudScene& s = ctx->scene;
+    if (s.width == 0) return fail(ctx, "Volumetric cloud viewport is undefined");  // VolumetricCloud.cpp:169-170
+    s.c = *common;
+    s.ShadowMap();
+    s.ShadowBlur();
+    s.ShadowFroxel();
+    return 0;
+}
+
+int orc_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
+                          const float* depth, int band_rows, int band_index, int band_count) {
+    CloudScene& s = ctx->scene;
+    if (s.width == 0) return fail(ctx, "Volumetric cloud viewport is undefined");
+    s.c = *common;
+    s.b = *cloud;
+    s.CheckerboardGen(depth);
+    s.IndexGen();
+    s.Render(band_rows, band_index, band_count);
+    return 0;
+}
+
+int orc_cloud_frame_end(SkyContext* ctx, const float* depth, void* hdr) {
+    CloudScene& s = ctx->scene;
+    s.Reconstruct();
+    s.Upscale(depth, static_cast<uint16_t*>(hdr));
+    std::swap(s.reconstruct[0], s.reconstruct[1]);  // VolumetricCloud.cpp:421-422
+    return 0;
+}
+
+int orc_cloud_frame(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
+                    const float* depth, void* hdr) {
+    if (int e = orc_cloud_frame_begin(ctx, common, cloud, depth, 0, 0, 1)) return e;
+    return orc_cloud_frame_end(ctx, depth, hdr);
+}
+
+int orc_cloud_frame_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
+                         const float* depth, void* hdr) {
+    return orc_cloud_frame(ctx, common, cloud, depth, hdr);
+}
+
+int orc_pt_begin(SkyContext* ctx, const SkyPathTracingInit* init) {
+    if (ctx->scene.width == 0) return fail(ctx, "Volumetric cloud viewport is undefined");
+    ctx->scene.PathTraceBegin(*init);
+    return 0;
+}
+
+int orc_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
+                   const int32_t region[4]) {
+    if (ctx->scene.pt_accum.w == 0) return fail(ctx, "pt_begin was not called");
+    ctx->scene.c = *common;
+    ctx->scene.PathTraceSamples(frame_begin, count, region);
+    return 0;
+}
+
+int orc_pt_resolve(SkyContext* ctx, uint32_t frame_count, void* hdr) {
+    ctx->scene.PathTraceResolve(frame_count, static_cast<uint16_t*>(hdr));
+    return 0;
+}
+
+int orc_pt_samples_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
+                        const int32_t region[4], float* accum_host) {
+    if (int e = orc_pt_samples(ctx, common, frame_begin, count, region)) return e;
+    std::memcpy(accum_host, ctx->scene.pt_accum.data.data(), ctx->scene.pt_accum.data.size() * 4);
+    return 0;
+}
+
+int orc_get_resource(SkyContext* ctx, int resource, SkyResourceDesc* d) {
+    CloudScene& s = ctx->scene;
+    std::memset(d, 0, sizeof(*d));
+    auto packed = [&](int w, int h, int dep, int ch, int fmt) {
+        d->ptr = ctx->scratch.data(); d->width = w; d->height = h; d->depth = dep; d->channels = ch; d->format = fmt;
+        d->bytes = ctx->scratch.size();
+    };
+    switch (resource) {
+        case SKY_RES_TRANSMITTANCE: set_desc_f32(d, s.transmittance); return 0;
+        case SKY_RES_MULTISCATTERING: set_desc_f32(d, s.multiscattering); return 0;
+        case SKY_RES_SKY_VIEW_LUMINANCE: set_desc_f32(d, s.sky_lum); return 0;
+        case SKY_RES_SKY_VIEW_TRANSMITTANCE: set_desc_f32(d, s.sky_trans); return 0;
+        case SKY_RES_AERIAL_LUMINANCE: set_desc_f32(d, s.ap_lum); return 0;
+        case SKY_RES_AERIAL_TRANSMITTANCE: set_desc_f32(d, s.ap_trans); return 0;
+        case SKY_RES_ENVIRONMENT: pack_half(s.env, ctx->scratch); packed(s.env.w, s.env.h, 6, 4, SKY_FMT_F16); return 0;
+        case SKY_RES_CLOUD_MAP:
+            if (s.cloud_map.levels.empty()) return fail(ctx, "cloud map not generated");
+            pack_unorm(s.cloud_map.levels[0], 8, ctx->scratch); packed(s.cloud_map.levels[0].w, s.cloud_map.levels[0].h, 1, 2, SKY_FMT_U8); return 0;
+        case SKY_RES_DETAIL:
+            if (s.detail.levels.empty()) return fail(ctx, "detail not generated");
+            pack_unorm(s.detail.levels[0], 8, ctx->scratch); packed(s.detail.levels[0].w, s.detail.levels[0].h, s.detail.levels[0].d, 1, SKY_FMT_U8); return 0;
+        case SKY_RES_DISPLACEMENT:
+            if (s.displacement.levels.empty()) return fail(ctx, "displacement not generated");
+            pack_unorm(s.displacement.levels[0], 8, ctx->scratch); packed(s.displacement.levels[0].w, s.displacement.levels[0].h, 1, 4, SKY_FMT_U8); return 0;
+        case SKY_RES_VOXEL:
+            if (s.voxel.levels.empty()) return fail(ctx, "voxel grid not uploaded");
+            pack_unorm(s.voxel.levels[0], 8, ctx->scratch); packed(s.voxel.levels[0].w, s.voxel.levels[0].h, s.voxel.levels[0].d, 1, SKY_FMT_U8); return 0;
+        case SKY_RES_CLOUD_MAP_MIPS: pack_mips(s.cloud_map, ctx->scratch); packed(int(ctx->scratch.size()), 1, 1, 1, SKY_FMT_U8); return 0;
+        case SKY_RES_DETAIL_MIPS: pack_mips(s.detail, ctx->scratch); packed(int(ctx->scratch.size()), 1, 1, 1, SKY_FMT_U8); return 0;
+        case SKY_RES_DISPLACEMENT_MIPS: pack_mips(s.displacement, ctx->scratch); packed(int(ctx->scratch.size()), 1, 1, 1, SKY_FMT_U8); return 0;
+        case SKY_RES_VOXEL_MIPS: pack_mips(s.voxel, ctx->scratch); packed(int(ctx->scratch.size()), 1, 1, 1, SKY_FMT_U8); return 0;
+        case SKY_RES_SHADOW_MAP_RAW: set_desc_f32(d, s.shadow_maps[0]); return 0;
+        case SKY_RES_SHADOW_MAP: set_desc_f32(d, s.shadow_maps[2]); return 0;
+        case SKY_RES_SHADOW_FROXEL: pack_unorm(s.shadow_froxel, 16, ctx->scratch); packed(s.shadow_froxel.w, s.shadow_froxel.h, s.shadow_froxel.d, 1, SKY_FMT_U16); return 0;
+        case SKY_RES_CHECKERBOARD_DEPTH: set_desc_f32(d, s.checkerboard_depth); return 0;
+        case SKY_RES_INDEX_LINEAR_DEPTH: set_desc_f32(d, s.index_linear_depth); return 0;
+        case SKY_RES_CLOUD_RENDER: pack_half(s.render_texture, ctx->scratch); packed(s.render_texture.w, s.render_texture.h, 1, 4, SKY_FMT_F16); return 0;
+        case SKY_RES_CLOUD_DISTANCE: set_desc_f32(d, s.cloud_distance); return 0;
+        case SKY_RES_RECONSTRUCT: pack_half(s.reconstruct[1], ctx->scratch); packed(s.reconstruct[1].w, s.reconstruct[1].h, 1, 4, SKY_FMT_F16); return 0;
+        case SKY_RES_PT_ACCUM: set_desc_f32(d, s.pt_accum); return 0;
+        case SKY_RES_PT_MASK:
+            d->ptr = s.pt_mask.data(); d->width = s.width; d->height = s.height; d->depth = 1; d->channels = 1; d->format = SKY_FMT_U8;
+            d->bytes = s.pt_mask.size(); return 0;
+        case SKY_RES_COUNTERS:
+            ctx->counter_copy.resize(8);
+            for (int i = 0; i < 8; ++i) ctx->counter_copy[i] = s.counters[i].load();
+            d->ptr = ctx->counter_copy.data(); d->width = 8; d->height = 1; d->depth = 1; d->channels = 1; d->format = SKY_FMT_U64;
+            d->bytes = 64; return 0;
+    }
+    return fail(ctx, "unknown resource");
+}
+
+int orc_read_resource(SkyContext* ctx, int resource, void* dst, uint64_t bytes) {
+    SkyResourceDesc d;
+    if (int e = orc_get_resource(ctx, resource, &d)) return e;
+    if (bytes != d.bytes) { ctx->error = "read_resource: size mismatch, expected " + std::to_string(d.bytes); return 1; }
+    std::memcpy(dst, d.ptr, bytes);
+    return 0;
+}
+
+int orc_write_resource(SkyContext* ctx, int resource, const void* src, uint64_t bytes) {
+    CloudScene& s = ctx->scene;
+    auto put_f32 = [&](std::vector<float>& v) { if (bytes != v.size() * 4) return fail(ctx, "write_resource: size mismatch"); std::memcpy(v.data(), src, bytes); return 0; };
+    auto put_half = [&](std::vector<float>& v) {
+        if (bytes != v.size() * 2) return fail(ctx, "write_resource: size mismatch");
+        const uint16_t* p = static_cast<const uint16_t*>(src);
+        for (size_t i = 0; i < v.size(); ++i) v[i] = half_bits_to_float(p[i]);
+        return 0;
+    };
+    switch (resource) {
+        case SKY_RES_TRANSMITTANCE: return put_f32(s.transmittance.data);
+        case SKY_RES_MULTISCATTERING: return put_f32(s.multiscattering.data);
+        case SKY_RES_SKY_VIEW_LUMINANCE: return put_f32(s.sky_lum.data);
+        case SKY_RES_SKY_VIEW_TRANSMITTANCE: return put_f32(s.sky_trans.data);
+        case SKY_RES_AERIAL_LUMINANCE: return put_f32(s.ap_lum.data);
+        case SKY_RES_AERIAL_TRANSMITTANCE: return put_f32(s.ap_trans.data);
+        case SKY_RES_ENVIRONMENT: return put_half(s.env.data);
+        case SKY_RES_SHADOW_MAP_RAW: return put_f32(s.shadow_maps[0].data);
+        case SKY_RES_SHADOW_MAP: return put_f32(s.shadow_maps[2].data);
+        case SKY_RES_CHECKERBOARD_DEPTH: return put_f32(s.checkerboard_depth.data);
+        case SKY_RES_INDEX_LINEAR_DEPTH: return put_f32(s.index_linear_depth.data);
+        case SKY_RES_CLOUD_RENDER: return put_half(s.render_texture.data);
+        case SKY_RES_CLOUD_DISTANCE: return put_f32(s.cloud_distance.data);
+        case SKY_RES_RECONSTRUCT: return put_half(s.reconstruct[1].data);
+        case SKY_RES_PT_ACCUM: return put_f32(s.pt_accum.data);
+        case SKY_RES_SHADOW_FROXEL: {
+            if (bytes != s.shadow_froxel.data.size() * 2) return fail(ctx, "write_resource: size mismatch");
+            const uint16_t* p = static_cast<const uint16_t*>(src);
+            for (size_t i = 0; i < s.shadow_froxel.data.size(); ++i) s.shadow_froxel.data[i] = float(p[i]) / 65535.0f;
+            return 0;
+        }
+        case SKY_RES_CLOUD_MAP: case SKY_RES_DETAIL: case SKY_RES_DISPLACEMENT: {
+            // install level 0 codes and rebuild the chain
+            const uint8_t* p = static_cast<const uint8_t*>(src);
+            auto put = [&](auto& tex) {
+                if (tex.levels.empty() || bytes != tex.levels[0].data.size()) return fail(ctx, "write_resource: size mismatch");
+                for (size_t i = 0; i < bytes; ++i) tex.levels[0].data[i] = float(p[i]) / 255.0f;
+                tex.build_mips();
+                return 0;
+            };
+            if (resource == SKY_RES_CLOUD_MAP) { if (s.cloud_map.levels.empty()) { s.cloud_map.levels.resize(1); s.cloud_map.levels[0].resize(512, 512); } return put(s.cloud_map); }
+            if (resource == SKY_RES_DETAIL) { if (s.detail.levels.empty()) { s.detail.levels.resize(1); s.detail.levels[0].resize(128, 128, 128); } return put(s.detail); }
+            if (s.displacement.levels.empty()) { s.displacement.levels.resize(1); s.displacement.levels[0].resize(128, 128); }
+            return put(s.displacement);
+        }
+    }
+    return fail(ctx, "write_resource: resource is not writable");
+}
+
+int orc_counters_enable(SkyContext* ctx, int enable) {
+    ctx->scene.counting = enable != 0;
+    for (auto& c : ctx->scene.counters) c = 0;
+    return 0;
+}
+
+int orc_set_hw_filtering(SkyContext*, int) { return 0; }
+int orc_tex_peak(SkyContext* ctx, int, double*) { return fail(ctx, "tex_peak is a GPU microbenchmark"); }
+
+}  // extern "C"

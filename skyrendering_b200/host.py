@@ -1,0 +1,171 @@
+"""ctypes binding of libskyhost.so (include/skyhost.h): the reference's parameter surface
+(scene JSON, camera, per-frame uniform maths) re-hosted in C++."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import (AtmosphereBufferData, AtmosphereRenderBufferData, CloudBufferData, CloudCommonBufferData, I,
+                  LutConfig, MaterialBlock, NoiseCreateInfo, PathTracingInit, SkyError)
+
+_lib = None
+
+
+def _host():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(abi.HOST_LIB_PATH):
+            raise SkyError(f"{abi.HOST_LIB_PATH} is missing: run __graft_entry__.build()")
+        L = C.CDLL(abi.HOST_LIB_PATH)
+        V = C.c_void_p
+        P = C.POINTER
+        sig = {
+            "skyhost_last_error": ([], C.c_char_p),
+            "skyhost_scene_load": ([C.c_char_p, P(V)], I),
+            "skyhost_scene_destroy": ([V], None),
+            "skyhost_scene_log": ([V], C.c_char_p),
+            "skyhost_scene_save": ([V, C.c_char_p, C.c_int64], C.c_int64),
+            "skyhost_atmosphere_buffer": ([V, P(AtmosphereBufferData)], I),
+            "skyhost_lut_config": ([V, P(LutConfig)], I),
+            "skyhost_atmosphere_render_buffer": ([V, P(AtmosphereRenderBufferData)], I),
+            "skyhost_set_viewport": ([V, I, I], I),
+            "skyhost_cloud_update": ([V, C.c_float, P(CloudCommonBufferData), P(CloudBufferData), P(MaterialBlock)], I),
+            "skyhost_noise_info": ([V, I, P(NoiseCreateInfo), P(I)], I),
+            "skyhost_set_voxel_dim": ([V, I, I, I], I),
+            "skyhost_material_type": ([V, P(I)], I),
+            "skyhost_pt_params": ([V, I, I, C.c_float, I, I, I], I),
+            "skyhost_pt_init": ([V, P(PathTracingInit)], I),
+            "skyhost_pt_region": ([V, I, P(I * 4)], I),
+            "skyhost_camera_get": ([V, P(C.c_float * 3), P(C.c_float * 3), P(C.c_float), P(C.c_float), P(C.c_float)], I),
+            "skyhost_camera_move": ([V, P(C.c_float * 3), C.c_float, C.c_float], I),
+            "skyhost_view_projection": ([V, P(C.c_float * 16)], I),
+            "skyhost_ground_depth": ([V, C.c_void_p, I, I], I),
+        }
+        for name, (args, res) in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, res
+        _lib = L
+    return _lib
+
+
+HOST_SYMBOLS = [
+    "skyhost_last_error", "skyhost_scene_load", "skyhost_scene_destroy", "skyhost_scene_log", "skyhost_scene_save",
+    "skyhost_atmosphere_buffer", "skyhost_lut_config", "skyhost_atmosphere_render_buffer", "skyhost_set_viewport",
+    "skyhost_cloud_update", "skyhost_noise_info", "skyhost_set_voxel_dim", "skyhost_material_type", "skyhost_pt_params",
+    "skyhost_pt_init", "skyhost_pt_region", "skyhost_camera_get", "skyhost_camera_move", "skyhost_view_projection",
+    "skyhost_ground_depth",
+]
+
+
+class Scene:
+    """AppWindow's serialised state (earth_, camera_, volumetric_cloud_, atmosphere_render_*)."""
+
+    def __init__(self, json_text):
+        L = _host()
+        h = C.c_void_p()
+        if L.skyhost_scene_load(json_text.encode(), C.byref(h)) != 0:
+            raise SkyError(L.skyhost_last_error().decode())
+        self.h = h
+
+    @classmethod
+    def from_file(cls, path):
+        with open(path) as f:
+            return cls(f.read())
+
+    def __del__(self):
+        try:
+            if self.h:
+                _host().skyhost_scene_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SkyError(_host().skyhost_last_error().decode())
+
+    @property
+    def log(self):
+        return _host().skyhost_scene_log(self.h).decode()
+
+    def save(self):
+        L = _host()
+        need = L.skyhost_scene_save(self.h, None, 0)
+        if need < 0:
+            raise SkyError(L.skyhost_last_error().decode())
+        buf = C.create_string_buffer(need)
+        L.skyhost_scene_save(self.h, buf, need)
+        return buf.value.decode()
+
+    def atmosphere_buffer(self):
+        out = AtmosphereBufferData()
+        self._check(_host().skyhost_atmosphere_buffer(self.h, C.byref(out)))
+        return out
+
+    def lut_config(self):
+        out = LutConfig()
+        self._check(_host().skyhost_lut_config(self.h, C.byref(out)))
+        return out
+
+    def atmosphere_render_buffer(self):
+        out = AtmosphereRenderBufferData()
+        self._check(_host().skyhost_atmosphere_render_buffer(self.h, C.byref(out)))
+        return out
+
+    def set_viewport(self, w, h):
+        self._check(_host().skyhost_set_viewport(self.h, w, h))
+
+    def cloud_update(self, delta_time=0.0):
+        common, cloud, mat = CloudCommonBufferData(), CloudBufferData(), MaterialBlock()
+        self._check(_host().skyhost_cloud_update(self.h, delta_time, C.byref(common), C.byref(cloud), C.byref(mat)))
+        return common, cloud, mat
+
+    def noise_info(self, kind):
+        out = (NoiseCreateInfo * 2)()
+        has = I()
+        self._check(_host().skyhost_noise_info(self.h, kind, out, C.byref(has)))
+        return (out[0].copy(), out[1].copy()) if has.value else None
+
+    def set_voxel_dim(self, dx, dy, dz):
+        self._check(_host().skyhost_set_voxel_dim(self.h, dx, dy, dz))
+
+    def material_type(self):
+        t = I()
+        self._check(_host().skyhost_material_type(self.h, C.byref(t)))
+        return t.value
+
+    def pt_params(self, sqrt_tile_count=1, max_bounces=128, region_box_half_width=100.0, importance_sampling=True,
+                  prng=abi.PRNG_PCG, environment_lighting=abi.ENV_GROUND_MULTI_BOUNCE):
+        self._check(_host().skyhost_pt_params(self.h, sqrt_tile_count, max_bounces, region_box_half_width,
+                                               int(importance_sampling), prng, environment_lighting))
+
+    def pt_init(self):
+        out = PathTracingInit()
+        self._check(_host().skyhost_pt_init(self.h, C.byref(out)))
+        return out
+
+    def pt_region(self, tile_index):
+        r = (I * 4)()
+        self._check(_host().skyhost_pt_region(self.h, tile_index, C.byref(r)))
+        return list(r)
+
+    def camera(self):
+        pos, front = (C.c_float * 3)(), (C.c_float * 3)()
+        fovy, zn, zf = C.c_float(), C.c_float(), C.c_float()
+        self._check(_host().skyhost_camera_get(self.h, C.byref(pos), C.byref(front), C.byref(fovy), C.byref(zn), C.byref(zf)))
+        return {"position": list(pos), "front": list(front), "fovy": fovy.value, "zNear": zn.value, "zFar": zf.value}
+
+    def camera_move(self, delta=(0.0, 0.0, 0.0), d_pitch=0.0, d_yaw=0.0):
+        d = (C.c_float * 3)(*delta)
+        self._check(_host().skyhost_camera_move(self.h, C.byref(d), d_pitch, d_yaw))
+
+    def view_projection(self):
+        m = (C.c_float * 16)()
+        self._check(_host().skyhost_view_projection(self.h, C.byref(m)))
+        return np.array(m, np.float32).reshape(4, 4).T  # row-major numpy view of the column-major matrix
+
+    def ground_depth(self, w, h):
+        out = np.empty((h, w), np.float32)
+        self._check(_host().skyhost_ground_depth(self.h, out.ctypes.data, w, h))
+        return out

@@ -1,0 +1,143 @@
+"""Frame driver: replays the reference's per-frame call order (AppWindow::HandleDisplayEvent /
+Render, src/SkyRendering/AppWindow.cpp:139-181) on top of the two C ABIs.
+
+    Earth::Update                 -> Context.atmosphere_bake           (K1, K2)
+    VolumetricCloud::Update       -> Scene.cloud_update (+ noise regeneration when parameters change)
+    VolumetricCloud::RenderShadow -> Context.cloud_shadow              (K11-K13)
+    AtmosphereRenderer::Render    -> Context.atmosphere_luts/composite (K3-K6)
+    VolumetricCloud::Render       -> Context.cloud_frame               (K14-K18)  or the path tracer (K19/K20)
+
+The kernel library is the CUDA one unless a test hands in the oracle binding explicitly; nothing in
+this module imports or falls back to the oracle.
+"""
+import os
+
+import numpy as np
+
+from . import abi
+from .host import Scene
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+SCENES_DIR = os.path.join(abi.REPO_ROOT, "scenes")
+SCENE_FILES = {
+    "c1": "c1_earth_lut_bake.json",
+    "c2": "c2_sunset_composite.json",
+    "c3": "c3_clouds_godrays.json",
+    "c5": "c5_voxel_pathtrace.json",
+}
+
+
+def load_blue_noise():
+    """64x64 R16 blue noise in GL texel order (Textures.cpp:19-26 after StbImage.cpp:12-17's flip)."""
+    return np.fromfile(os.path.join(_DATA, "blue_noise_64x64.u16"), dtype="<u2").reshape(64, 64)
+
+
+def scene_path(name):
+    return os.path.join(SCENES_DIR, SCENE_FILES.get(name, name))
+
+
+def synthetic_voxel_grid(dx=126, dy=154, dz=86, seed=0, blobs=64):
+    """Deterministic sparse R8 density grid at the wdas_cloud_sixteenth bounds (126 x 86 x 154 voxels
+    in vdb xyz; stored [dz][dy][dx] with y/z swapped like VolumetricCloudVoxelMaterial.cpp:53-69).
+    Sum of Gaussian blobs, thresholded so that about a quarter of the voxels are non-zero, like the
+    real asset (415 642 / 1 668 744 active).  The Disney data set is not available offline."""
+    rng = np.random.RandomState(seed)
+    z, y, x = np.meshgrid(np.linspace(0, 1, dz, dtype=np.float32), np.linspace(0, 1, dy, dtype=np.float32),
+                          np.linspace(0, 1, dx, dtype=np.float32), indexing="ij")
+    field = np.zeros((dz, dy, dx), np.float32)
+    centres = rng.uniform(0.2, 0.8, size=(blobs, 3)).astype(np.float32)
+    radii = rng.uniform(0.06, 0.16, size=blobs).astype(np.float32)
+    for (cx, cy, cz), r in zip(centres, radii):
+        field += np.exp(-((x - cx) ** 2 + (y - cy) ** 2 + ((z - cz * 0.6 - 0.1) * 1.4) ** 2) / (r * r))
+    # high-frequency erosion so the interior is not smooth
+    ripple = (np.sin(37.0 * x + 11.0 * z) * np.sin(29.0 * y + 5.0 * x) * np.sin(23.0 * z + 17.0 * y)).astype(np.float32)
+    field = field * (1.0 + 0.35 * ripple)
+    thresh = np.quantile(field, 0.75)
+    dens = np.clip((field - thresh) / max(float(field.max() - thresh), 1e-6), 0.0, 1.0)
+    return np.round(np.sqrt(dens) * 255.0).astype(np.uint8)
+
+
+class Renderer:
+    def __init__(self, scene, width, height, library=None, device=0, stream=0, blue_noise=None):
+        self.scene = scene if isinstance(scene, Scene) else Scene.from_file(scene_path(scene))
+        self.width, self.height = width, height
+        self.lib = library if library is not None else abi.cuda_library()
+        self.ctx = abi.Context(self.lib, device, stream)
+        self.ctx.set_blue_noise(load_blue_noise() if blue_noise is None else blue_noise)
+        self.ctx.set_viewport(width, height)
+        self.scene.set_viewport(width, height)
+        self._noise_cache = {}
+        self._pt_frame_cnt = 0
+        self._pt_tile = 0
+        self.last_uniforms = None
+
+    # ---- pieces -------------------------------------------------------------------------------------
+    def earth_update(self):
+        """Earth::Update (Earth.cpp:42-44)."""
+        self.atmosphere = self.scene.atmosphere_buffer()
+        self.ctx.atmosphere_bake(self.atmosphere)
+
+    def atmosphere_render_luts(self):
+        """AtmosphereRenderer::Render up to the environment cube (AtmosphereRenderer.cpp:164-242)."""
+        self.render_buffer = self.scene.atmosphere_render_buffer()
+        self.lut_config = self.scene.lut_config()
+        self.ctx.atmosphere_luts(self.render_buffer, self.lut_config)
+
+    def upload_voxels(self, grid):
+        dz, dy, dx = grid.shape
+        self.scene.set_voxel_dim(dx, dy, dz)
+        self.ctx.voxel_upload(grid)
+
+    def _material_update(self, common_cloud_material):
+        """DynamicTexture::GenerateIfParameterChanged (VolumetricCloudDefaultMaterial.h:32-37)."""
+        for kind in (abi.NOISE_CLOUD_MAP, abi.NOISE_DETAIL, abi.NOISE_DISPLACEMENT):
+            info = self.scene.noise_info(kind)
+            if info is None:
+                continue
+            key = tuple((i.seed, i.base_frequency, i.remap_min, i.remap_max) for i in info)
+            if self._noise_cache.get(kind) != key:
+                self.ctx.noise_generate(kind, info)
+                self._noise_cache[kind] = key
+        self.ctx.set_material(common_cloud_material[2])
+
+    def cloud_update(self, delta_time=0.0):
+        """VolumetricCloud::Update (VolumetricCloud.cpp:168-280)."""
+        u = self.scene.cloud_update(delta_time)
+        self._material_update(u)
+        self.last_uniforms = u
+        return u
+
+    def prime(self):
+        """Frame-0 state: the reference's first cloud update sees a zero sun
+        direction because AtmosphereRenderer::Render has not run yet; run the atmosphere once first."""
+        self.earth_update()
+        self.atmosphere_render_luts()
+
+    # ---- whole frames ---------------------------------------------------------------------------------
+    def frame(self, depth, hdr, delta_time=0.0, composite=True, clouds=True):
+        """One HandleDisplayEvent: depth float[H][W], hdr half4[H][W] (both in the library's memory space)."""
+        self.earth_update()
+        common, cloud, _ = self.cloud_update(delta_time)
+        self.ctx.cloud_shadow(common)
+        self.atmosphere_render_luts()
+        if composite:
+            self.ctx.composite(depth, hdr, self.width, self.height)
+        if clouds:
+            self.ctx.cloud_frame(common, cloud, depth, hdr)
+        return common, cloud
+
+    def path_trace_begin(self, **params):
+        """StartPathTracing button (VolumetricCloud.cpp:426-428)."""
+        if params:
+            self.scene.pt_params(**params)
+        self.pt_init = self.scene.pt_init()
+        self.ctx.pt_begin(self.pt_init)
+        self._pt_frame_cnt = 0
+        self._pt_tile = 0
+
+    def path_trace_frames(self, common, count, frame_begin=None):
+        """`count` full-screen PathTracing::Render calls with sqrt_tile_count == 1."""
+        begin = self._pt_frame_cnt + 1 if frame_begin is None else frame_begin
+        self.ctx.pt_samples(common, begin, count, [0, 0, self.width, self.height])
+        self._pt_frame_cnt = begin + count - 1
+        return self._pt_frame_cnt
