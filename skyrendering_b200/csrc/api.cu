@@ -1,0 +1,344 @@
+// C ABI of libskyb200.so (include/skyb200.h).  Plain pointers and PODs only; no exceptions and no
+// torch types cross this boundary.  There is no CPU fallback anywhere in this library: without a
+// CUDA device sky_ctx_create fails.
+#include "../../include/skyb200.h"
+
+#include <cstring>
+
+#include "context.h"
+
+int sky_fail(SkyContext* ctx, const std::string& msg) {
+    if (ctx) ctx->error = msg;
+    return 1;
+}
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+void free_lut(Lut<T>& l) {
+    if (l.p) cudaFree(l.p);
+    l = Lut<T>{};
+}
+void free_mip(MipTextureDev& t) {
+    if (t.view.tex_linear) cudaDestroyTextureObject(t.view.tex_linear);
+    if (t.view.tex_point) cudaDestroyTextureObject(t.view.tex_point);
+    if (t.array) cudaFreeMipmappedArray(t.array);
+    if (t.data) cudaFree(t.data);
+    t = MipTextureDev{};
+}
+
+struct ResView {
+    void* ptr = nullptr;
+    int w = 0, h = 0, d = 1, ch = 1, fmt = SKY_FMT_F32;
+    size_t bytes = 0;
+};
+
+template <class T>
+ResView view_of(const Lut<T>& l, int ch, int fmt) {
+    ResView v;
+    v.ptr = l.p; v.w = l.w; v.h = l.h; v.d = l.d; v.ch = ch; v.fmt = fmt; v.bytes = l.bytes();
+    return v;
+}
+ResView mip0_of(const MipTextureDev& t) {
+    ResView v;
+    if (!t.valid) return v;
+    v.ptr = t.data; v.w = t.view.w[0]; v.h = t.view.h[0]; v.d = t.view.d[0]; v.ch = t.view.channels; v.fmt = SKY_FMT_U8;
+    v.bytes = size_t(v.w) * v.h * v.d * v.ch;
+    return v;
+}
+ResView mips_of(const MipTextureDev& t) {
+    ResView v;
+    if (!t.valid) return v;
+    size_t first = size_t(t.view.off[1]) * t.view.channels;
+    v.ptr = t.data + first; v.bytes = t.bytes - first; v.w = int(v.bytes); v.h = 1; v.d = 1; v.ch = 1; v.fmt = SKY_FMT_U8;
+    return v;
+}
+
+bool resolve(SkyContext* ctx, int resource, ResView& v) {
+    switch (resource) {
+        case SKY_RES_TRANSMITTANCE: v = view_of(ctx->transmittance, 4, SKY_FMT_F32); return true;
+        case SKY_RES_MULTISCATTERING: v = view_of(ctx->multiscattering, 4, SKY_FMT_F32); return true;
+        case SKY_RES_SKY_VIEW_LUMINANCE: v = view_of(ctx->sky_lum, 4, SKY_FMT_F32); return true;
+        case SKY_RES_SKY_VIEW_TRANSMITTANCE: v = view_of(ctx->sky_trans, 4, SKY_FMT_F32); return true;
+        case SKY_RES_AERIAL_LUMINANCE: v = view_of(ctx->ap_lum, 4, SKY_FMT_F32); return true;
+        case SKY_RES_AERIAL_TRANSMITTANCE: v = view_of(ctx->ap_trans, 4, SKY_FMT_F32); return true;
+        case SKY_RES_ENVIRONMENT: v = view_of(ctx->env, 4, SKY_FMT_F16); return true;
+        case SKY_RES_CLOUD_MAP: v = mip0_of(ctx->cloud_map); return true;
+        case SKY_RES_DETAIL: v = mip0_of(ctx->detail); return true;
+        case SKY_RES_DISPLACEMENT: v = mip0_of(ctx->displacement); return true;
+        case SKY_RES_VOXEL: v = mip0_of(ctx->voxel); return true;
+        case SKY_RES_CLOUD_MAP_MIPS: v = mips_of(ctx->cloud_map); return true;
+        case SKY_RES_DETAIL_MIPS: v = mips_of(ctx->detail); return true;
+        case SKY_RES_DISPLACEMENT_MIPS: v = mips_of(ctx->displacement); return true;
+        case SKY_RES_VOXEL_MIPS: v = mips_of(ctx->voxel); return true;
+        case SKY_RES_SHADOW_MAP_RAW: v = view_of(ctx->shadow_maps[0], 2, SKY_FMT_F32); return true;
+        case SKY_RES_SHADOW_MAP: v = view_of(ctx->shadow_maps[2], 2, SKY_FMT_F32); return true;
+        case SKY_RES_SHADOW_FROXEL: v = view_of(ctx->shadow_froxel, 1, SKY_FMT_U16); return true;
+        case SKY_RES_CHECKERBOARD_DEPTH: v = view_of(ctx->checkerboard_depth, 1, SKY_FMT_F32); return true;
+        case SKY_RES_INDEX_LINEAR_DEPTH: v = view_of(ctx->index_linear_depth, 2, SKY_FMT_F32); return true;
+        case SKY_RES_CLOUD_RENDER: v = view_of(ctx->render_texture, 4, SKY_FMT_F16); return true;
+        case SKY_RES_CLOUD_DISTANCE: v = view_of(ctx->cloud_distance, 1, SKY_FMT_F32); return true;
+        case SKY_RES_RECONSTRUCT: v = view_of(ctx->reconstruct[1], 4, SKY_FMT_F16); return true;  // newest after the swap
+        case SKY_RES_PT_ACCUM: v = view_of(ctx->pt_accum, 4, SKY_FMT_F32); return true;
+        case SKY_RES_PT_MASK: v = view_of(ctx->pt_mask, 1, SKY_FMT_U8); return true;
+        case SKY_RES_COUNTERS:
+            v.ptr = ctx->counters; v.w = 8; v.h = 1; v.d = 1; v.ch = 1; v.fmt = SKY_FMT_U64; v.bytes = 64;
+            return true;
+    }
+    return false;
+}
+
+int ensure_stage(SkyContext* ctx) {
+    size_t px = size_t(ctx->width) * ctx->height;
+    if (ctx->stage_pixels == px && ctx->stage_depth) return 0;
+    if (ctx->stage_depth) cudaFree(ctx->stage_depth);
+    if (ctx->stage_hdr) cudaFree(ctx->stage_hdr);
+    ctx->stage_depth = nullptr; ctx->stage_hdr = nullptr; ctx->stage_pixels = 0;
+    SKY_CUDA(ctx, cudaMalloc(&ctx->stage_depth, px * sizeof(float)));
+    SKY_CUDA(ctx, cudaMalloc(&ctx->stage_hdr, px * sizeof(half4)));
+    ctx->stage_pixels = px;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        return 1;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    SkyContext* ctx = new SkyContext();
+    ctx->device = device;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    int rc = 0;
+    rc |= sky_alloc(ctx, ctx->transmittance, 256, 64);   // Atmosphere.cpp:11-12
+    rc |= sky_alloc(ctx, ctx->multiscattering, 32, 32);  // Atmosphere.cpp:17-18
+    for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);  // VolumetricCloud.cpp:52,102-105
+    if (cudaMalloc(&ctx->blue_noise, 64 * 64 * sizeof(uint16_t)) != cudaSuccess) rc = 1;
+    if (cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) rc = 1;
+    if (!rc) {
+        cudaMemsetAsync(ctx->blue_noise, 0, 64 * 64 * sizeof(uint16_t), ctx->stream);
+        cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream);
+    }
+    if (rc) {
+        g_create_error = ctx->error.empty() ? "device allocation failed" : ctx->error;
+        delete ctx;
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void sky_ctx_destroy(SkyContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_lut(ctx->transmittance); free_lut(ctx->multiscattering); free_lut(ctx->sky_lum); free_lut(ctx->sky_trans);
+    free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
+    for (auto& m : ctx->shadow_maps) free_lut(m);
+    free_lut(ctx->shadow_froxel); free_lut(ctx->checkerboard_depth); free_lut(ctx->cloud_distance);
+    free_lut(ctx->index_linear_depth); free_lut(ctx->render_texture); free_lut(ctx->reconstruct[0]); free_lut(ctx->reconstruct[1]);
+    free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
+    free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
+    if (ctx->blue_noise) cudaFree(ctx->blue_noise);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->stage_depth) cudaFree(ctx->stage_depth);
+    if (ctx->stage_hdr) cudaFree(ctx->stage_hdr);
+    delete ctx;
+}
+
+const char* sky_last_error(SkyContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int sky_sync(SkyContext* ctx) {
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int sky_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
+    SKY_CUDA(ctx, cudaMemcpyAsync(ctx->blue_noise, texels, 64 * 64 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer may be a temporary
+    return 0;
+}
+
+int sky_set_viewport(SkyContext* ctx, int w, int h) {
+    if (w < 12 || h < 12) return sky_fail(ctx, "viewport too small");
+    ctx->width = w; ctx->height = h;
+    int rc = 0;  // VolumetricCloud.cpp:120-136; histories zero-filled
+    rc |= sky_alloc(ctx, ctx->checkerboard_depth, w / 2, h / 2);
+    rc |= sky_alloc(ctx, ctx->index_linear_depth, w / 4, h / 4);
+    rc |= sky_alloc(ctx, ctx->render_texture, w / 4, h / 4);
+    rc |= sky_alloc(ctx, ctx->cloud_distance, w / 4, h / 4);
+    rc |= sky_alloc(ctx, ctx->reconstruct[0], w / 2, h / 2);
+    rc |= sky_alloc(ctx, ctx->reconstruct[1], w / 2, h / 2);
+    rc |= sky_alloc(ctx, ctx->shadow_froxel, w / 12, h / 12, 128);
+    for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);
+    free_lut(ctx->pt_accum);
+    free_lut(ctx->pt_mask);
+    return rc;
+}
+
+int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
+    ctx->atm = *a;
+    return launch_atmosphere_bake(ctx);
+}
+
+int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg) {
+    if (cfg->sky_view_width < 2 || cfg->sky_view_height < 2 || cfg->aerial_perspective_depth < 2 || cfg->environment_size < 1)
+        return sky_fail(ctx, "bad LUT sizes");
+    ctx->render = *r;
+    ctx->lut_cfg = *cfg;
+    int rc = 0;
+    rc |= sky_alloc(ctx, ctx->sky_lum, cfg->sky_view_width, cfg->sky_view_height, 1, false);
+    rc |= sky_alloc(ctx, ctx->sky_trans, cfg->sky_view_width, cfg->sky_view_height, 1, false);
+    rc |= sky_alloc(ctx, ctx->ap_lum, 32, 32, cfg->aerial_perspective_depth, false);  // AtmosphereRenderer.cpp:19-20
+    rc |= sky_alloc(ctx, ctx->ap_trans, 32, 32, cfg->aerial_perspective_depth, false);
+    rc |= sky_alloc(ctx, ctx->env, cfg->environment_size, cfg->environment_size, 6, false);
+    if (rc) return rc;
+    return launch_atmosphere_luts(ctx);
+}
+
+int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
+    if (!ctx->sky_lum.p) return sky_fail(ctx, "atmosphere LUTs have not been baked");
+    return launch_composite(ctx, depth, static_cast<half4*>(hdr), width, height);
+}
+
+int sky_noise_generate(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info) { return launch_noise(ctx, kind, info); }
+
+int sky_voxel_upload(SkyContext* ctx, const uint8_t* host_voxels, int dx, int dy, int dz) {
+    if (dx < 1 || dy < 1 || dz < 1 || dx > 4096 || dy > 4096 || dz > 4096) return sky_fail(ctx, "voxel grid dimensions out of range");
+    ctx->voxel.valid = false;
+    if (int e = build_mip_texture(ctx, ctx->voxel, dx, dy, dz, 1, true)) return e;
+    SKY_CUDA(ctx, cudaMemcpyAsync(ctx->voxel.data, host_voxels, size_t(dx) * dy * dz, cudaMemcpyHostToDevice, ctx->stream));
+    if (int e = launch_mip_chain(ctx, ctx->voxel)) return e;
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int sky_set_material(SkyContext* ctx, const SkyMaterialBlock* m) {
+    if (m->type < SKY_MATERIAL_DEFAULT0 || m->type > SKY_MATERIAL_VOXEL) return sky_fail(ctx, "unknown material type");
+    ctx->material = *m;
+    return 0;
+}
+
+int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
+    if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");  // VolumetricCloud.cpp:169-170
+    return launch_cloud_shadow(ctx, *common);
+}
+
+int sky_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
+                          const float* depth, int band_rows, int band_index, int band_count) {
+    if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
+    if (band_count < 1 || band_index < 0 || band_index >= band_count || band_rows < 0) return sky_fail(ctx, "bad band arguments");
+    ctx->last_common = *common;  // cloud_frame_end runs K17/K18 with the same uniforms
+    return launch_cloud_begin(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
+}
+
+int sky_cloud_frame(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
+                    const float* depth, void* hdr) {
+    if (int e = sky_cloud_frame_begin(ctx, common, cloud, depth, 0, 0, 1)) return e;
+    return launch_cloud_end(ctx, *common, depth, static_cast<half4*>(hdr));
+}
+
+int sky_cloud_frame_end(SkyContext* ctx, const float* depth, void* hdr) {
+    if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
+    return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr));
+}
+
+int sky_cloud_frame_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
+                         const float* depth_host, void* hdr_host) {
+    if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
+    if (int e = ensure_stage(ctx)) return e;
+    size_t px = ctx->stage_pixels;
+    SKY_CUDA(ctx, cudaMemcpyAsync(ctx->stage_depth, depth_host, px * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SKY_CUDA(ctx, cudaMemcpyAsync(ctx->stage_hdr, hdr_host, px * sizeof(half4), cudaMemcpyHostToDevice, ctx->stream));
+    if (int e = sky_cloud_frame(ctx, common, cloud, ctx->stage_depth, ctx->stage_hdr)) return e;
+    SKY_CUDA(ctx, cudaMemcpyAsync(hdr_host, ctx->stage_hdr, px * sizeof(half4), cudaMemcpyDeviceToHost, ctx->stream));
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int sky_pt_begin(SkyContext* ctx, const SkyPathTracingInit* init) {
+    if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
+    if (init->prng != SKY_PRNG_WANG && init->prng != SKY_PRNG_PCG) return sky_fail(ctx, "unknown PRNG");
+    if (init->environment_lighting < SKY_ENV_OFF || init->environment_lighting > SKY_ENV_GROUND_MULTI_BOUNCE) return sky_fail(ctx, "unknown environment lighting mode");
+    ctx->pt = *init;
+    int rc = sky_alloc(ctx, ctx->pt_accum, ctx->width, ctx->height);  // glClearTexImage, VolumetricCloud.cpp:498-501
+    rc |= sky_alloc(ctx, ctx->pt_mask, ctx->width, ctx->height);
+    return rc;
+}
+
+int sky_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
+                   const int32_t region[4]) {
+    return launch_pt_samples(ctx, *common, frame_begin, count, region);
+}
+
+int sky_pt_resolve(SkyContext* ctx, uint32_t frame_count, void* hdr) { return launch_pt_resolve(ctx, frame_count, static_cast<half4*>(hdr)); }
+
+int sky_pt_samples_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
+                        const int32_t region[4], float* accum_host) {
+    if (int e = launch_pt_samples(ctx, *common, frame_begin, count, region)) return e;
+    SKY_CUDA(ctx, cudaMemcpyAsync(accum_host, ctx->pt_accum.p, ctx->pt_accum.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int sky_get_resource(SkyContext* ctx, int resource, SkyResourceDesc* out) {
+    std::memset(out, 0, sizeof(*out));
+    ResView v;
+    if (!resolve(ctx, resource, v)) return sky_fail(ctx, "unknown resource");
+    if (!v.ptr) return sky_fail(ctx, "resource " + std::to_string(resource) + " has not been created yet");
+    out->ptr = v.ptr; out->width = v.w; out->height = v.h; out->depth = v.d; out->channels = v.ch; out->format = v.fmt; out->bytes = v.bytes;
+    return 0;
+}
+
+int sky_read_resource(SkyContext* ctx, int resource, void* host_dst, uint64_t bytes) {
+    SkyResourceDesc d;
+    if (int e = sky_get_resource(ctx, resource, &d)) return e;
+    if (bytes != d.bytes) return sky_fail(ctx, "read_resource: size mismatch, expected " + std::to_string(d.bytes));
+    SKY_CUDA(ctx, cudaMemcpyAsync(host_dst, d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint64_t bytes) {
+    switch (resource) {
+        case SKY_RES_CLOUD_MAP: if (int e = build_mip_texture(ctx, ctx->cloud_map, 512, 512, 1, 2, false)) return e; break;
+        case SKY_RES_DETAIL: if (int e = build_mip_texture(ctx, ctx->detail, 128, 128, 128, 1, false)) return e; break;
+        case SKY_RES_DISPLACEMENT: if (int e = build_mip_texture(ctx, ctx->displacement, 128, 128, 1, 4, false)) return e; break;
+        case SKY_RES_CLOUD_MAP_MIPS: case SKY_RES_DETAIL_MIPS: case SKY_RES_DISPLACEMENT_MIPS: case SKY_RES_VOXEL_MIPS:
+        case SKY_RES_VOXEL: case SKY_RES_COUNTERS: case SKY_RES_PT_MASK:
+            return sky_fail(ctx, "write_resource: resource is not writable");
+    }
+    SkyResourceDesc d;
+    if (int e = sky_get_resource(ctx, resource, &d)) return e;
+    if (bytes != d.bytes) return sky_fail(ctx, "write_resource: size mismatch, expected " + std::to_string(d.bytes));
+    SKY_CUDA(ctx, cudaMemcpyAsync(d.ptr, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (resource == SKY_RES_CLOUD_MAP) { if (int e = launch_mip_chain(ctx, ctx->cloud_map)) return e; }
+    if (resource == SKY_RES_DETAIL) { if (int e = launch_mip_chain(ctx, ctx->detail)) return e; }
+    if (resource == SKY_RES_DISPLACEMENT) { if (int e = launch_mip_chain(ctx, ctx->displacement)) return e; }
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int sky_counters_enable(SkyContext* ctx, int enable) {
+    ctx->counting = enable != 0;
+    SKY_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+int sky_set_hw_filtering(SkyContext* ctx, int enable) {
+    ctx->hw_filtering = enable != 0;
+    return 0;
+}
+
+int sky_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) { return launch_tex_peak(ctx, mode, fetches_per_second); }
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+// K1-K6: atmosphere LUT bake and the sky / aerial-perspective composite, sm_100a.
+// Follows shaders/SkyRendering/Atmosphere.glsl and AtmosphereRenderer.glsl (line references on
+// each function).  Compiled with -fmad=false: these kernels are microsecond-scale and
+// latency-bound, and the altitude r_i - bottom_radius (Atmosphere.glsl:258-260) cancels ~7 digits,
+// so keeping the reference's unfused fp32 operation order is worth more than the FMAs.
+#include "atmosphere_dev.cuh"
+#include "context.h"
+
+namespace {
+
+struct BakeParams {
+    AtmosphereModel atm;
+    LutView transmittance;
+    float4* transmittance_out;
+    float4* multiscattering_out;
+    int ms_w, ms_h;
+};
+
+// Atmosphere.glsl:119-132
+SKY_D float3 GetExtinction(const SkyAtmosphereBufferData& u, float altitude) {
+    float3 rayleigh_extinction = f3(u.rayleigh_scattering) * clampf(expf(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+    float3 mie_extinction = (f3(u.mie_scattering) + f3(u.mie_absorption)) *
+                            clampf(expf(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+    float3 ozone_extinction = f3(u.ozone_absorption) *
+                              fmaxf(0.0f, altitude < u.ozone_center_altitude ? 1.0f + (altitude - u.ozone_center_altitude) * u.inv_ozone_width
+                                                                            : 1.0f - (altitude - u.ozone_center_altitude) * u.inv_ozone_width);
+    return rayleigh_extinction + mie_extinction + ozone_extinction;
+}
+
+// Atmosphere.glsl:220-295.  MS = MULTISCATTERING_COMPUTE_PROGRAM permutation.
+template <bool MS>
+SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture,
+                                       const LutView& multiscattering_texture, float start_i, float3 earth_center,
+                                       float3 start_position, float3 view_direction, float3 sun_direction,
+                                       float marching_distance, float steps, float3& transmittance, float3& L_f) {
+    const SkyAtmosphereBufferData& u = atm.u;
+    float r = length(start_position - earth_center);
+    float3 up_direction = normalize(start_position - earth_center);
+    float mu = dot(view_direction, up_direction);
+    float cos_sun_view = dot(view_direction, sun_direction);
+    const float SAMPLE_COUNT = steps;
+    float dx = marching_distance / SAMPLE_COUNT;
+
+    transmittance = f3(1.0f);
+    float3 luminance = f3(0.0f);
+    float rayleigh_phase, mie_phase;
+    if (MS) {
+        L_f = f3(0.0f);
+        start_i = 0.5f;
+        rayleigh_phase = mie_phase = 1.0f / (4.0f * kPi);  // IsotropicPhaseFunction, :134-136
+    } else {
+        // RayleighPhaseFunction / MiePhaseFunction, :138-154
+        rayleigh_phase = (3.0f / (16.0f * kPi)) * (1.0f + cos_sun_view * cos_sun_view);
+        float g = u.mie_phase_g;
+        float k = 3.0f / (8.0f * kPi) * (1.0f - g * g) / (2.0f + g * g);
+        mie_phase = k * (1.0f + cos_sun_view * cos_sun_view) / powf(1.0f + g * g - 2.0f * g * cos_sun_view, 1.5f);
+    }
+    for (float i = start_i; i < SAMPLE_COUNT; ++i) {
+        float d_i = i * dx;
+        float r_i = sqrtf(d_i * d_i + 2.0f * r * mu * d_i + r * r);
+        float3 position_i = start_position + view_direction * d_i;
+        float altitude_i = r_i - u.bottom_radius;
+
+        // GetScattering, :156-159
+        float3 rayleigh_scattering_i = f3(u.rayleigh_scattering) * clampf(expf(-altitude_i * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+        float3 mie_scattering_i = f3(u.mie_scattering) * clampf(expf(-altitude_i * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+        float3 scattering_i = rayleigh_scattering_i + mie_scattering_i;
+        float3 scattering_with_phase_i = rayleigh_scattering_i * rayleigh_phase + mie_scattering_i * mie_phase;
+
+        float3 extinction_i = GetExtinction(u, altitude_i);
+        float3 transmittance_i = exp3(-extinction_i * dx);
+        float3 up_direction_i = normalize(position_i - earth_center);
+        float mu_s_i = dot(sun_direction, up_direction_i);
+        float3 luminance_i = scattering_with_phase_i * atm.GetSunVisibility(transmittance_texture, r_i, mu_s_i);
+        if (!MS) {
+            // GetMultiscatteringContribution, :169-178
+            float x_mu_s = mu_s_i * 0.5f + 0.5f;
+            float x_r = (r_i - u.bottom_radius) / (u.top_radius - u.bottom_radius);
+            float uu = 0.5f / float(multiscattering_texture.w) + x_mu_s * (1.0f - 1.0f / float(multiscattering_texture.w));
+            float vv = 0.5f / float(multiscattering_texture.h) + x_r * (1.0f - 1.0f / float(multiscattering_texture.h));
+            float3 multiscattering_contribution = xyz(sample_lut2d(multiscattering_texture, uu, vv));
+            luminance_i += u.multiscattering_mask * multiscattering_contribution * scattering_i;
+            luminance_i *= f3(u.solar_illuminance);
+        }
+        luminance += transmittance * (luminance_i - luminance_i * transmittance_i) / extinction_i;
+        if (MS) L_f += transmittance * (scattering_i - scattering_i * transmittance_i) / extinction_i;
+        transmittance *= transmittance_i;
+    }
+    return luminance;
+}
+
+// Atmosphere.glsl:297-306
+template <bool MS>
+SKY_D float3 ComputeGroundLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture, float3 earth_center,
+                                    float3 position, float3 sun_direction) {
+    float3 up_direction = normalize(position - earth_center);
+    float mu_s = dot(sun_direction, up_direction);
+    float3 solar_illuminance_at_ground = atm.GetSunVisibility(transmittance_texture, atm.u.bottom_radius, mu_s);
+    if (!MS) solar_illuminance_at_ground *= atm.solar_illuminance();
+    float3 normal = normalize(position - earth_center);
+    return kInvPi * clampf(dot(normal, sun_direction), 0.0f, 1.0f) * atm.ground_albedo() * solar_illuminance_at_ground;
+}
+
+// ------------------------------------------------------------------------------------------------- K1
+// Atmosphere.glsl:311-337 (+ GetRMuFromTransmittanceTextureIndex :71-88); one thread per texel.
+__global__ void __launch_bounds__(128) k1_transmittance(const __grid_constant__ BakeParams P) {
+    const SkyAtmosphereBufferData& u = P.atm.u;
+    const int W = P.transmittance.w, Hh = P.transmittance.h;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W || y >= Hh) return;
+    float x_mu = float(x) / float(W - 1), x_r = float(y) / float(Hh - 1);
+    float H = sqrtf(u.top_radius * u.top_radius - u.bottom_radius * u.bottom_radius);
+    float rho = H * x_r;
+    float r = sqrtf(rho * rho + u.bottom_radius * u.bottom_radius);
+    float d_min = u.top_radius - r;
+    float d_max = rho + H;
+    float d = d_min + x_mu * (d_max - d_min);
+    float mu = d == 0.0f ? 1.0f : (H * H - rho * rho - d * d) / (2.0f * r * d);
+    mu = clampf(mu, -1.0f, 1.0f);
+
+    const float SAMPLE_COUNT = u.transmittance_steps;
+    float dx = P.atm.DistanceToTopAtmosphereBoundary(r, mu) / SAMPLE_COUNT;
+    float3 optical_length = f3(0.0f);
+    for (float i = 0.5f; i < SAMPLE_COUNT; ++i) {
+        float d_i = i * dx;
+        float r_i = sqrtf(d_i * d_i + 2.0f * r * mu * d_i + r * r);
+        float altitude_i = r_i - u.bottom_radius;
+        optical_length += GetExtinction(u, altitude_i) * dx;
+    }
+    P.transmittance_out[y * W + x] = f4(exp3(-optical_length), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------- K2
+// Atmosphere.glsl:344-438: one 64-thread block per texel, one sphere direction per thread, pairwise
+// tree (i, i+32) ... (i, i+1) kept in the reference's order (:392-425) via smem + shuffles.
+__global__ void __launch_bounds__(64) k2_multiscattering(const __grid_constant__ BakeParams P) {
+    const SkyAtmosphereBufferData& u = P.atm.u;
+    const int gx = blockIdx.x, gy = blockIdx.y;
+    const int local_index = threadIdx.x;
+    // GetAltitudeMuSFromMultiscatteringTextureIndex, :161-167
+    float x_mu_s = float(gx) / float(P.ms_w - 1), x_altitude = float(gy) / float(P.ms_h - 1);
+    float altitude = x_altitude * (u.top_radius - u.bottom_radius);
+    float mu_s = x_mu_s * 2.0f - 1.0f;
+    float3 earth_center = f3(0.0f, -u.bottom_radius, 0.0f);
+    float3 start_position = f3(0.0f, altitude, 0.0f);
+    float3 sun_direction = f3(0.0f, mu_s, sqrtf(1 - mu_s * mu_s));
+    // GetDirectionFromLocalIndex, :344-355
+    float unit_theta = (0.5f + float(local_index / 8)) / 8.0f;
+    float unit_phi = (0.5f + float(local_index % 8)) / 8.0f;
+    float cos_theta = 1.0f - 2.0f * unit_theta;
+    float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
+    float phi = 2 * kPi * unit_phi;
+    float3 view_direction = f3(cosf(phi) * sin_theta, cos_theta, sinf(phi) * sin_theta);
+
+    float r = altitude + u.bottom_radius;
+    float mu = view_direction.y;
+    bool intersect_bottom = P.atm.RayIntersectsGround(r, mu);
+    float marching_distance = intersect_bottom ? P.atm.DistanceToBottomAtmosphereBoundary(r, mu) : P.atm.DistanceToTopAtmosphereBoundary(r, mu);
+    float3 transmittance, L_f;
+    float3 luminance = ComputeScatteredLuminance<true>(P.atm, P.transmittance, P.transmittance, 0.5f, earth_center, start_position,
+                                                       view_direction, sun_direction, marching_distance, u.multiscattering_steps,
+                                                       transmittance, L_f);
+    if (intersect_bottom) {
+        float3 ground_position = start_position + view_direction * marching_distance;
+        luminance += transmittance * ComputeGroundLuminance<true>(P.atm, P.transmittance, earth_center, ground_position, sun_direction);
+    }
+    __shared__ float sh[32][6];
+    if (local_index >= 32) {
+        float* s = sh[local_index - 32];
+        s[0] = luminance.x; s[1] = luminance.y; s[2] = luminance.z; s[3] = L_f.x; s[4] = L_f.y; s[5] = L_f.z;
+    }
+    __syncthreads();
+    if (local_index >= 32) return;
+    float v[6] = {luminance.x, luminance.y, luminance.z, L_f.x, L_f.y, L_f.z};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] += sh[local_index][k];
+#pragma unroll
+    for (int stride = 16; stride >= 1; stride >>= 1)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] += __shfl_down_sync(0xffffffffu, v[k], stride);
+    if (local_index == 0) {
+        float3 L_2nd_order = f3(v[0], v[1], v[2]) / 64.0f;
+        float3 f_ms = f3(v[3], v[4], v[5]) / 64.0f;
+        float3 F_ms = 1.0f / (f3(1.0f) - f_ms);
+        P.multiscattering_out[gy * P.ms_w + gx] = f4(L_2nd_order * F_ms, 1.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K3 / K4 / K5 / K6
+struct RenderParams {
+    AtmosphereModel atm;
+    SkyAtmosphereRenderBufferData r;  // AtmosphereRenderer.glsl:25-50
+    SkyLutConfig cfg;
+    LutView transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
+    FroxelView froxel;  // p == nullptr: no cloud shadow froxel yet (visibility 1)
+    const uint16_t* blue_noise;
+    float4 *sky_lum_out, *sky_trans_out, *ap_lum_out, *ap_trans_out;
+    half4* env_out;
+    const float* depth;
+    half4* hdr;
+    int width, height;
+};
+
+// AtmosphereRenderer.glsl:56-72
+SKY_D float3 ComputeRaymarchingStartPositionAndChangeDistance(const RenderParams& P, float3 view_direction, float& marching_distance) {
+    float3 start_position = f3(P.r.camera_position);
+    bool in_space = P.r.camera_earth_center_distance > P.atm.u.top_radius;
+    if (in_space) {
+        float r = P.r.camera_earth_center_distance;
+        float mu = dot(view_direction, f3(P.r.up_direction));
+        float near_distance;
+        if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu, near_distance)) {
+            start_position += near_distance * view_direction;
+            marching_distance -= near_distance;
+        } else {
+            marching_distance = 0;
+        }
+    }
+    return start_position;
+}
+// AtmosphereRenderer.glsl:74-78
+SKY_D float GetHorizonDownAngleFromR(const RenderParams& P, float r) {
+    float tangent_point_distance = sqrtf(r * r - P.atm.u.bottom_radius * P.atm.u.bottom_radius);
+    return acosf(tangent_point_distance / r);
+}
+// AtmosphereRenderer.glsl:113-132.  acos/sqrt arguments are clamped into their domains: GLSL leaves
+// them undefined a few ulp outside, which rounding in dot()/normalize() does produce.
+SKY_D float2 GetSkyViewTextureUvFromCosLatLon(const RenderParams& P, float r, float cos_lat, float cos_lon) {
+    float horizon_down_angle = GetHorizonDownAngleFromR(P, r);
+    float horizon_up_angle = kPi - horizon_down_angle;
+    float lat = acosf(clampf(cos_lat, -1.0f, 1.0f));
+    float x_cos_lat;
+    if (lat < horizon_up_angle) {
+        float coord = lat / horizon_up_angle;
+        coord = sqrtf(fmaxf(1 - coord, 0.0f));
+        x_cos_lat = 0.5f - 0.5f * coord;
+    } else {
+        float coord = (lat - horizon_up_angle) / horizon_down_angle;
+        coord = sqrtf(fmaxf(coord, 0.0f));
+        x_cos_lat = coord * 0.5f + 0.5f;
+    }
+    float x_cos_lon = sqrtf(fmaxf(0.5f - 0.5f * cos_lon, 0.0f));
+    float w = float(P.cfg.sky_view_width), h = float(P.cfg.sky_view_height);
+    return f2(0.5f / w + x_cos_lon * (1.0f - 1.0f / w), 0.5f / h + x_cos_lat * (1.0f - 1.0f / h));
+}
+// AtmosphereRenderer.glsl:134-145
+SKY_D void GetCosLatLonFromViewDirection(const RenderParams& P, float3 view_direction, float& cos_lat, float& cos_lon) {
+    float3 up = f3(P.r.up_direction);
+    cos_lat = dot(up, view_direction);
+    float3 lon_direction = view_direction - up * cos_lat;
+    float lon_direction_length2 = dot(lon_direction, lon_direction);
+    if (lon_direction_length2 == 0) {
+        cos_lon = 1;
+    } else {
+        lon_direction *= (1.0f / sqrtf(lon_direction_length2));
+        cos_lon = dot(lon_direction, f3(P.r.front_direction));
+    }
+}
+SKY_D float DitherStart(const RenderParams& P, int enable, int x, int y) {
+    if (enable) return float(__ldg(P.blue_noise + (y & 0x3f) * 64 + (x & 0x3f))) / 65535.0f;
+    return 0.5f;
+}
+
+// K3 -- AtmosphereRenderer.glsl:153-186 (+ :81-111)
+__global__ void __launch_bounds__(64) k3_sky_view(const __grid_constant__ RenderParams P) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int W = P.cfg.sky_view_width, H = P.cfg.sky_view_height;
+    if (x >= W || y >= H) return;
+    float r = P.r.camera_earth_center_distance;
+    // GetCosLatLonFromSkyViewTextureIndex
+    float x_cos_lon = float(x) / float(W - 1), x_cos_lat = float(y) / float(H - 1);
+    float horizon_down_angle = GetHorizonDownAngleFromR(P, r);
+    float horizon_up_angle = kPi - horizon_down_angle;
+    float lat;
+    if (x_cos_lat < 0.5f) {
+        float coord = 1.0f - 2.0f * x_cos_lat;
+        coord = 1.0f - coord * coord;
+        lat = horizon_up_angle * coord;
+    } else {
+        float coord = x_cos_lat * 2.0f - 1.0f;
+        coord *= coord;
+        lat = horizon_up_angle + horizon_down_angle * coord;
+    }
+    float cos_lat = cosf(lat);
+    float cos_lon = -(x_cos_lon * x_cos_lon * 2.0f - 1.0f);
+    // GetViewDirectionFromCosLatLon
+    float sin_lat = clampf(sqrtf(1 - cos_lat * cos_lat), 0.0f, 1.0f);
+    float sin_lon = clampf(sqrtf(1 - cos_lon * cos_lon), 0.0f, 1.0f);
+    float3 view_direction = f3(P.r.up_direction) * cos_lat + f3(P.r.front_direction) * (sin_lat * cos_lon) +
+                            f3(P.r.right_direction) * (sin_lat * sin_lon);
+    float mu = cos_lat;
+    bool intersect_bottom = P.atm.RayIntersectsGround(r, mu);
+    float marching_distance = intersect_bottom ? P.atm.DistanceToBottomAtmosphereBoundary(r, mu) : P.atm.DistanceToTopAtmosphereBoundary(r, mu);
+    float3 start_position = ComputeRaymarchingStartPositionAndChangeDistance(P, view_direction, marching_distance);
+    float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
+    if (marching_distance > 0) {
+        float start_i = DitherStart(P, P.cfg.sky_view_dither, x, y);
+        luminance = ComputeScatteredLuminance<false>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                     view_direction, f3(P.r.sun_direction), marching_distance, P.r.sky_view_lut_steps,
+                                                     transmittance, unused);
+    }
+    P.sky_lum_out[y * W + x] = f4(luminance, 0.0f);
+    P.sky_trans_out[y * W + x] = f4(transmittance, 0.0f);
+}
+
+// K4 -- AtmosphereRenderer.glsl:191-243
+__global__ void __launch_bounds__(64) k4_aerial_perspective(const __grid_constant__ RenderParams P) {
+    const int W = P.ap_lum.w, H = P.ap_lum.h, D = P.ap_lum.d;
+    int x = threadIdx.x % W, y = blockIdx.x * (blockDim.x / W) + threadIdx.x / W, z = blockIdx.y;
+    if (y >= H || z >= D) return;
+    float3 uvw = f3(float(x) / float(W - 1), float(y) / float(H - 1), float(z) / float(D - 1));
+    float3 position = projective_mul(P.r.inv_view_projection, f3(uvw.x * 2.0f - 1.0f, uvw.y * 2.0f - 1.0f, 0.0f));
+    float3 view_direction = normalize(position - f3(P.r.camera_position));
+    float marching_distance = uvw.z * uvw.z * P.r.aerial_perspective_lut_max_distance;
+
+    float r = P.r.camera_earth_center_distance;
+    float mu = dot(view_direction, f3(P.r.up_direction));
+    bool intersect_bottom = P.atm.RayIntersectsGround(r, mu);
+    float max_marching_distance = intersect_bottom ? marching_distance : P.atm.DistanceToTopAtmosphereBoundary(r, mu);
+    float3 start_position = ComputeRaymarchingStartPositionAndChangeDistance(P, view_direction, max_marching_distance);
+    marching_distance = fminf(marching_distance, max_marching_distance);
+    float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
+    if (marching_distance > 0) {
+        float start_i = DitherStart(P, P.cfg.aerial_perspective_dither, x, y);
+        luminance = ComputeScatteredLuminance<false>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                     view_direction, f3(P.r.sun_direction), marching_distance,
+                                                     P.r.aerial_perspective_lut_steps, transmittance, unused);
+    }
+    size_t o = (size_t(z) * H + y) * W + x;
+    P.ap_lum_out[o] = f4(luminance, 0.0f);
+    P.ap_trans_out[o] = f4(transmittance, 0.0f);
+}
+
+// shaders/Base/Common.glsl:13-30
+SKY_D float3 ConvertCubUvToDir(int index, float u, float v) {
+    float uc = 2.0f * u - 1.0f, vc = 2.0f * v - 1.0f;
+    float3 dir = f3(0.0f);
+    switch (index) {
+        case 0: dir = f3(1.0f, vc, -uc); break;
+        case 1: dir = f3(-1.0f, vc, uc); break;
+        case 2: dir = f3(uc, 1.0f, -vc); break;
+        case 3: dir = f3(uc, -1.0f, vc); break;
+        case 4: dir = f3(uc, vc, 1.0f); break;
+        case 5: dir = f3(-uc, vc, -1.0f); break;
+    }
+    return normalize(dir);
+}
+
+// K5 -- AtmosphereRenderer.glsl:253-273
+__global__ void __launch_bounds__(128) k5_environment(const __grid_constant__ RenderParams P) {
+    const int S = P.cfg.environment_size;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, index = blockIdx.z;
+    if (x >= S) return;
+    float fu = (float(x) + 0.5f) / float(S), fv = (float(y) + 0.5f) / float(S);
+    fv = 1.0f - fv;
+    float3 view_direction = ConvertCubUvToDir(index, fu, fv);
+    float cos_lat, cos_lon;
+    GetCosLatLonFromViewDirection(P, view_direction, cos_lat, cos_lon);
+    float r = P.r.camera_earth_center_distance;
+    float2 uv = GetSkyViewTextureUvFromCosLatLon(P, r, cos_lat, cos_lon);
+    float3 luminance = xyz(sample_lut2d(P.sky_lum, uv.x, uv.y));
+    float3 transmittance = xyz(sample_lut2d(P.sky_trans, uv.x, uv.y));
+    float mu = cos_lat;
+    if (P.atm.RayIntersectsGround(r, mu)) {
+        float marching_distance = P.atm.DistanceToBottomAtmosphereBoundary(r, mu);
+        float3 ground_position = f3(P.r.camera_position) + view_direction * marching_distance;
+        luminance += ComputeGroundLuminance<false>(P.atm, P.transmittance, f3(P.r.earth_center), ground_position, f3(P.r.sun_direction)) * transmittance;
+    }
+    P.env_out[(size_t(index) * S + y) * S + x] = to_half4(f4(luminance, 0.0f));
+}
+
+// K6 -- AtmosphereRenderer.glsl:345-432: sky-view LUT / aerial-perspective LUT / per-pixel raymarch,
+// x cloud-shadow froxel, + sun disc with limb darkening.  Object pixels (depth != 1) get the
+// in-scatter only and alpha = 0 (ComputeObjectLuminance needs the G-buffer + IBL chain);
+// the star-map term of sky pixels (:427-429) is in the same "next" row.
+// HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
+__global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ RenderParams P) {
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    if (px >= P.width) return;
+    float2 vTexCoord = f2((float(px) + 0.5f) / float(P.width), (float(py) + 0.5f) / float(P.height));
+    float depth = __ldg(P.depth + size_t(py) * P.width + px);
+    float3 camera_position = f3(P.r.camera_position);
+    float3 fragment_position = projective_mul(P.r.inv_view_projection, f3(vTexCoord.x * 2.0f - 1.0f, vTexCoord.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
+    float3 view_direction = normalize(fragment_position - camera_position);
+    float r = P.r.camera_earth_center_distance;
+    float mu = dot(view_direction, f3(P.r.up_direction));
+    float marching_distance = P.atm.RayIntersectsGround(r, mu) ? P.atm.DistanceToBottomAtmosphereBoundary(r, mu) : P.atm.DistanceToTopAtmosphereBoundary(r, mu);
+    bool intersect_object = false;
+    if (depth != 1.0f) {
+        float object_distance = length(fragment_position - camera_position);
+        intersect_object = true;
+        marching_distance = fminf(marching_distance, object_distance);
+    }
+    float3 start_position = ComputeRaymarchingStartPositionAndChangeDistance(P, view_direction, marching_distance);
+    float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
+    float3 sun_direction = f3(P.r.sun_direction);
+    if (marching_distance > 0) {
+        if (P.cfg.use_sky_view_lut && !intersect_object) {
+            float cos_lat, cos_lon;
+            GetCosLatLonFromViewDirection(P, view_direction, cos_lat, cos_lon);
+            float2 uv = GetSkyViewTextureUvFromCosLatLon(P, r, cos_lat, cos_lon);
+            luminance = xyz(sample_lut2d(P.sky_lum, uv.x, uv.y));
+            transmittance = xyz(sample_lut2d(P.sky_trans, uv.x, uv.y));
+        } else if (P.cfg.use_aerial_perspective_lut && intersect_object) {
+            float3 uvw = aerial_perspective_uvw(vTexCoord, marching_distance, P.r.aerial_perspective_lut_max_distance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
+            luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
+            transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
+        } else {
+            float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
+            luminance = ComputeScatteredLuminance<false>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                         view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused);
+        }
+    }
+    if (P.froxel.p) luminance *= SampleRayScatterVisibility(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);
+
+    float alpha = 1.0f;
+    if (intersect_object) {
+        alpha = 0.0f;
+    } else if (dot(view_direction, sun_direction) >= cosf(P.atm.u.sun_angular_radius)) {
+        const float3 a = f3(0.397f, 0.503f, 0.652f);
+        float cos_view_sun = dot(view_direction, sun_direction);
+        float sin_view_sun = sqrtf(1.0f - cos_view_sun * cos_view_sun);
+        float center_to_edge = clampf(sin_view_sun / sinf(P.atm.u.sun_angular_radius), 0.0f, 1.0f);
+        float mu2 = sqrtf(1.0f - center_to_edge * center_to_edge);
+        float3 factor = f3(1.0f) - f3(1.0f) * (f3(1.0f) - f3(powf(mu2, a.x), powf(mu2, a.y), powf(mu2, a.z)));
+        float3 solar_illuminance_at_eye = P.atm.solar_illuminance() * transmittance;
+        luminance += solar_illuminance_at_eye / (kPi * P.atm.u.sun_angular_radius * P.atm.u.sun_angular_radius) * factor;
+    }
+    P.hdr[size_t(py) * P.width + px] = to_half4(f4(luminance, alpha));
+}
+
+RenderParams make_render_params(SkyContext* ctx) {
+    RenderParams P{};
+    P.atm.u = ctx->atm;
+    P.r = ctx->render;
+    P.cfg = ctx->lut_cfg;
+    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
+    P.multiscattering = LutView{ctx->multiscattering.p, ctx->multiscattering.w, ctx->multiscattering.h, 1};
+    P.sky_lum = LutView{ctx->sky_lum.p, ctx->sky_lum.w, ctx->sky_lum.h, 1};
+    P.sky_trans = LutView{ctx->sky_trans.p, ctx->sky_trans.w, ctx->sky_trans.h, 1};
+    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d};
+    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d};
+    P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
+    P.blue_noise = ctx->blue_noise;
+    P.sky_lum_out = ctx->sky_lum.p; P.sky_trans_out = ctx->sky_trans.p;
+    P.ap_lum_out = ctx->ap_lum.p; P.ap_trans_out = ctx->ap_trans.p;
+    P.env_out = ctx->env.p;
+    return P;
+}
+
+}  // namespace
+
+int launch_atmosphere_bake(SkyContext* ctx) {
+    BakeParams P{};
+    P.atm.u = ctx->atm;
+    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
+    P.transmittance_out = ctx->transmittance.p;
+    P.multiscattering_out = ctx->multiscattering.p;
+    P.ms_w = ctx->multiscattering.w; P.ms_h = ctx->multiscattering.h;
+    k1_transmittance<<<dim3(ceil_div(P.transmittance.w, 128), P.transmittance.h), 128, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    k2_multiscattering<<<dim3(P.ms_w, P.ms_h), 64, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_atmosphere_luts(SkyContext* ctx) {
+    RenderParams P = make_render_params(ctx);
+    k3_sky_view<<<dim3(ceil_div(P.cfg.sky_view_width, 64), P.cfg.sky_view_height), 64, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    // 64 threads = two rows of the 32-wide froxel slice
+    k4_aerial_perspective<<<dim3(ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), P.ap_lum.d), 64, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    k5_environment<<<dim3(ceil_div(P.cfg.environment_size, 128), P.cfg.environment_size, 6), 128, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h) {
+    RenderParams P = make_render_params(ctx);
+    P.depth = depth; P.hdr = hdr; P.width = w; P.height = h;
+    k6_composite<<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}

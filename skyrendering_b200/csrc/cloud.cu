@@ -1,0 +1,743 @@
+// K11-K18: cloud shadow chain and the real-time quarter-resolution cloud raymarch with temporal
+// reconstruction and depth-aware upscale, sm_100a.  Follows shaders/SkyRendering/
+// VolumetricCloud{ShadowMap,ShadowMapBlur,ShadowFroxel,IndexGen,Render,Reconstruct,Upscale}.comp,
+// CheckerboardGen.comp and VolumetricCloud{Common,ShadowInterface}.glsl.
+//
+// Bounds: the reference dispatches ceil-div groups with no in-shader bounds checks and relies on GL
+// dropping out-of-range image stores (GLReloadableProgram.h:55-59); every kernel here guards explicitly.
+#include "atmosphere_dev.cuh"
+#include "context.h"
+#include "material_dev.cuh"
+
+namespace {
+
+constexpr float kMinTransmittance = 0.01f;  // VolumetricCloudCommon.glsl:30
+
+struct CloudParams {
+    SkyCloudCommonBufferData c;  // VolumetricCloudCommon.glsl:6-28
+    SkyCloudBufferData b;        // VolumetricCloudRender.comp:17-32
+    AtmosphereModel atm;
+    MaterialParams mat;
+    LutView transmittance, ap_lum, ap_trans;
+    FroxelView froxel;
+    const uint16_t* blue_noise;
+    unsigned long long* counters;
+    // shadow chain
+    const float2* shadow_prev;  // pre_raw_cloud_shadow_map
+    float2* shadow_out;
+    const float2* shadow_blurred;
+    uint16_t* froxel_out;
+    int shadow_w, shadow_h;
+    // viewport chain
+    int width, height;         // full resolution
+    const float* depth;        // full-res depth
+    float* checkerboard;       // W/2 x H/2
+    float2* index_linear;      // W/4 x H/4
+    half4* render;             // W/4 x H/4
+    float* cloud_distance;     // W/4 x H/4
+    const half4* reconstruct_prev;
+    half4* reconstruct_out;    // W/2 x H/2
+    half4* hdr;
+    int band_rows, band_index, band_count;
+};
+
+SKY_D float DepthToLinearDepth(const SkyCloudCommonBufferData& c, float depth) {  // VolumetricCloudCommon.glsl:32-34
+    return 1.0f / (c.uLinearDepthParam[0] - c.uLinearDepthParam[1] * depth);
+}
+SKY_D float CalHeight01(const SkyCloudCommonBufferData& c, float3 pos) {  // VolumetricCloudCommon.glsl:36-39
+    float altitude = length(f3(pos.x, pos.y, pos.z + c.uEarthRadius)) - c.uEarthRadius;
+    return clampf((altitude - c.uBottomAltitude) / (c.uTopAltitude - c.uBottomAltitude), 0.0f, 1.0f);
+}
+SKY_D int2 IndexToOffset(uint32_t index) {  // VolumetricCloudCommon.glsl:42-52
+    return make_int2(int(((index + 1) >> 1) & 1), int(((index + 2) >> 1) & 1));
+}
+SKY_D float HenyeyGreenstein(float cos_theta, float g) {  // VolumetricCloudCommon.glsl:58-63
+    float a = 1.0f - g * g;
+    float b = 1.0f + g * g - 2.0f * g * cos_theta;
+    b *= sqrtf(b);
+    return (0.25f * kInvPi) * a / b;
+}
+SKY_D float blue_noise_at(const uint16_t* bn, int x, int y) { return float(__ldg(bn + (y & 0x3f) * 64 + (x & 0x3f))) / 65535.0f; }
+
+// GL_LINEAR + CLAMP_TO_BORDER(1e10, 1) on the RG32F cloud shadow map (VolumetricCloud.cpp:106-112)
+SKY_D float2 sample_shadow_map(const float2* p, int w, int h, float u, float v) {
+    float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    // keep the int conversion defined for far-away points
+    int i0 = int(fminf(fmaxf(fx, -2.0f), float(w) + 1.0f)), j0 = int(fminf(fmaxf(fy, -2.0f), float(h) + 1.0f));
+    auto fetch = [&](int i, int j) {
+        if (i < 0 || i >= w || j < 0 || j >= h) return f2(1e10f, 1.0f);
+        return __ldg(p + j * w + i);
+    };
+    float2 t00 = fetch(i0, j0), t10 = fetch(i0 + 1, j0), t01 = fetch(i0, j0 + 1), t11 = fetch(i0 + 1, j0 + 1);
+    return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+}
+// VolumetricCloudShadowInterface.glsl:4-8
+SKY_D float SampleCloudShadowTransmittance(const float2* map, int w, int h, float3 light_ndc) {
+    const float kInvTransitionDepth = 1.0f / 0.5f;
+    float2 dt = sample_shadow_map(map, w, h, light_ndc.x * 0.5f + 0.5f, light_ndc.y * 0.5f + 0.5f);
+    return mixf(dt.y, 1.0f, clampf((dt.x - light_ndc.z) * kInvTransitionDepth, 0.0f, 1.0f));
+}
+
+// ------------------------------------------------------------------------------------------------ K11
+// VolumetricCloudShadowMap.comp:37-75: ortho light-space march through the cloud shell, blue-noise +
+// golden-ratio jitter, temporal blend 0.2 with the reprojected previous raw map.
+template <int MAT, bool HW, bool COUNT>
+__global__ void __launch_bounds__(128) k11_shadow_map(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    int gx = blockIdx.x * 16 + (threadIdx.x & 15), gy = blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (gx >= P.shadow_w || gy >= P.shadow_h) return;
+    float2 image_size = f2(float(P.shadow_w), float(P.shadow_h));
+    float2 uv = f2((float(gx) + 0.5f) / image_size.x, (float(gy) + 0.5f) / image_size.y);
+    float3 origin = projective_mul(c.uInvLightVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 0.0f));
+    float3 dir = -f3(c.uSunDirection);
+    float3 up = f3(origin.x, origin.y, origin.z + c.uEarthRadius);
+    float r = length(up);
+    up /= r;
+    float mu = dot(up, dir);
+    // LineShellFirstIntersect, :18-35
+    float t1 = 0.0f, t2 = 0.0f;
+    {
+        float bottom_radius = c.uEarthRadius + c.uBottomAltitude;
+        float top_radius = c.uEarthRadius + c.uTopAltitude;
+        float discriminant_top = r * r * (mu * mu - 1.0f) + top_radius * top_radius;
+        if (discriminant_top > 0) {
+            float discriminant_bottom = r * r * (mu * mu - 1.0f) + bottom_radius * bottom_radius;
+            float sqrt_discriminant_top = sqrtf(discriminant_top);
+            float sqrt_discriminant_bottom = sqrtf(discriminant_bottom);
+            t1 = -r * mu - sqrt_discriminant_top;
+            t2 = -r * mu + (discriminant_bottom >= 0 ? -sqrt_discriminant_bottom : sqrt_discriminant_top);
+        }
+    }
+    float dist = fmaxf(t2 - t1, 0.0f);
+    dist = fminf(dist, 1.0f / cosf(85.0f * 0.01745329251994329576923690768489f) * (c.uTopAltitude - c.uBottomAltitude));
+    float optical_depth = 0.0f;
+    int evals = 0;
+    if (dist > 0.0f) {
+        float steps = mixf(12.0f, 6.0f, fabsf(dir.z));
+        float step_size = dist / steps;
+        float noise = blue_noise_at(P.blue_noise, gx, gy);
+        float t = t1 + step_size * fractf(noise + c.uFrameID * 0.61803398875f);
+        for (uint32_t cnt = uint32_t(steps); cnt != 0; cnt--, t += step_size) {
+            float3 pos = origin + t * dir;
+            float height01 = CalHeight01(c, pos);
+            float sigma_t = SampleSigmaT<MAT, HW>(P.mat, pos, height01);
+            optical_depth += sigma_t * step_size;
+            if (COUNT) ++evals;
+        }
+    }
+    float transmittance = expf(-optical_depth);
+    float depth = mixf(t1, t2, 0.5f);
+    float2 res = f2(depth, transmittance);
+    float3 pre = projective_mul(c.uShadowMapReprojectMat, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 0.0f));
+    float2 pre_uv = f2(pre.x * 0.5f + 0.5f, pre.y * 0.5f + 0.5f);
+    float2 lo = f2(0.5f / image_size.x, 0.5f / image_size.y);
+    float2 hi = f2((image_size.x - 0.5f) / image_size.x, (image_size.y - 0.5f) / image_size.y);
+    if (clampf(pre_uv.x, lo.x, hi.x) == pre_uv.x && clampf(pre_uv.y, lo.y, hi.y) == pre_uv.y) {
+        float2 pre_res = sample_shadow_map(P.shadow_prev, P.shadow_w, P.shadow_h, pre_uv.x, pre_uv.y);
+        res = mix2(pre_res, res, 0.2f);
+    }
+    P.shadow_out[gy * P.shadow_w + gx] = res;
+    if (COUNT && evals) atomicAdd(P.counters + SKY_CNT_SHADOW_SIGMA_EVALS, (unsigned long long)evals);
+}
+
+// ------------------------------------------------------------------------------------------------ K12
+// VolumetricCloudShadowMapBlur.comp:14-42: separable 9-tap Gaussian, clamp to edge.
+template <bool HORIZONTAL>
+__global__ void __launch_bounds__(128) k12_blur(const float2* __restrict__ in, float2* __restrict__ out, int w, int h) {
+    const float weight[5] = {0.227027f, 0.1945946f, 0.1216216f, 0.054054f, 0.016216f};
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    float2 res = __ldg(in + y * w + x) * weight[0];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        int x1 = x, y1 = y, x2 = x, y2 = y;
+        if (HORIZONTAL) { x1 = max(x - i, 0); x2 = min(x + i, w - 1); }
+        else { y1 = max(y - i, 0); y2 = min(y + i, h - 1); }
+        res += __ldg(in + y1 * w + x1) * weight[i];
+        res += __ldg(in + y2 * w + x2) * weight[i];
+    }
+    out[y * w + x] = res;
+}
+
+// ------------------------------------------------------------------------------------------------ K13
+// VolumetricCloudShadowFroxel.comp:10-27: running mean of cloud-shadow transmittance along each view
+// ray.  The sum stays sequential per column (reference order); the shadow-map taps do not depend on
+// it, so the loop is unrolled to keep 8 taps in flight.
+__global__ void __launch_bounds__(64) k13_shadow_froxel(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const int FW = P.froxel.w, FH = P.froxel.h, FD = P.froxel.d;
+    int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
+    if (gx >= FW || gy >= FH) return;
+    float2 uv = f2((float(gx) + 0.5f) / float(FW), (float(gy) + 0.5f) / float(FH));
+    float3 camera = f3(c.uCameraPos);
+    float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 0.0f));
+    float step_size = c.uShadowFroxelMaxDistance / float(FD);
+    float3 dir = normalize(frag_pos - camera);
+    float t = 0.5f * step_size;
+    float transmittance_sum = 0.0f;
+    for (int z0 = 0; z0 < FD; z0 += 8) {
+        float tap[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float3 pos = camera + t * dir;
+            t += step_size;
+            float3 light_ndc = projective_mul(c.uLightVP, pos);
+            tap[k] = (z0 + k < FD) ? SampleCloudShadowTransmittance(P.shadow_blurred, P.shadow_w, P.shadow_h, light_ndc) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int z = z0 + k;
+            if (z < FD) {
+                transmittance_sum += tap[k];
+                float ray_scatter_visibility = transmittance_sum / float(z + 1);
+                P.froxel_out[(size_t(z) * FH + gy) * FW + gx] = uint16_t(__float2int_rn(clampf(ray_scatter_visibility, 0.0f, 1.0f) * 65535.0f));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K14
+// CheckerboardGen.comp:7-14: max / min of each 2x2 depth block in a checkerboard pattern.
+__global__ void __launch_bounds__(256) k14_checkerboard(const __grid_constant__ CloudParams P) {
+    const int HW_ = P.width / 2, HH = P.height / 2;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= HW_) return;
+    int x0 = min(2 * x, P.width - 1), x1 = min(2 * x + 1, P.width - 1), y0 = min(2 * y, P.height - 1), y1 = min(2 * y + 1, P.height - 1);
+    float v0 = __ldg(P.depth + size_t(y1) * P.width + x0), v1 = __ldg(P.depth + size_t(y1) * P.width + x1);
+    float v2 = __ldg(P.depth + size_t(y0) * P.width + x1), v3 = __ldg(P.depth + size_t(y0) * P.width + x0);
+    bool bmax = ((x & 1) == (y & 1));
+    float d = bmax ? fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) : fminf(fminf(v0, v1), fminf(v2, v3));
+    P.checkerboard[size_t(y) * HW_ + x] = d;
+    (void)HH;
+}
+
+SKY_D float checker_clamped(const CloudParams& P, int x, int y) {
+    const int w = P.width / 2, h = P.height / 2;
+    return __ldg(P.checkerboard + size_t(clampi(y, 0, h - 1)) * w + clampi(x, 0, w - 1));
+}
+
+// ------------------------------------------------------------------------------------------------ K15
+// VolumetricCloudIndexGen.comp:13-42.  Out-of-range neighbour fetches (the reference leans on robust
+// texelFetch) are clamped to the edge, as the oracle defines.
+__global__ void __launch_bounds__(128) k15_index_gen(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const int QW = P.width / 4, QH = P.height / 4;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= QW || y >= QH) return;
+    float depth_tile[4] = {checker_clamped(P, 2 * x, 2 * y + 1), checker_clamped(P, 2 * x + 1, 2 * y + 1),
+                           checker_clamped(P, 2 * x + 1, 2 * y), checker_clamped(P, 2 * x, 2 * y)};
+    uint32_t nearest_index = 0, farthest_index = 0;
+#pragma unroll
+    for (uint32_t i = 1; i < 4; ++i) {
+        nearest_index = depth_tile[i] < depth_tile[nearest_index] ? i : nearest_index;
+        farthest_index = depth_tile[i] > depth_tile[farthest_index] ? i : farthest_index;
+    }
+    float nearest_linear_depth = DepthToLinearDepth(c, depth_tile[nearest_index]);
+    float farthest_linear_depth = DepthToLinearDepth(c, depth_tile[farthest_index]);
+    uint32_t close_to_nearest_count = 0, close_to_farthest_count = 0;
+    const int ox[8] = {0, 1, 1, 1, 0, -1, -1, -1}, oy[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int tx = x + ox[i], ty = y + oy[i];
+        uint32_t idx = (c.uBaseShadingIndex + uint32_t((tx + ty) & 1)) & 3u;  // PosToIndex, :9-11
+        int2 off = IndexToOffset(idx);
+        float depth = checker_clamped(P, (tx << 1) + off.x, (ty << 1) + off.y);
+        float linear_depth = DepthToLinearDepth(c, depth);
+        float max_delta_allowed = linear_depth * 0.25f;
+        if (fabsf(linear_depth - nearest_linear_depth) < max_delta_allowed) ++close_to_nearest_count;
+        if (fabsf(linear_depth - farthest_linear_depth) < max_delta_allowed) ++close_to_farthest_count;
+    }
+    uint32_t own = (c.uBaseShadingIndex + uint32_t((x + y) & 1)) & 3u;
+    uint32_t index = close_to_nearest_count == 0 ? nearest_index : close_to_farthest_count == 0 ? farthest_index : own;
+    P.index_linear[size_t(y) * QW + x] = f2(float(index), DepthToLinearDepth(c, depth_tile[index]));
+}
+
+// ------------------------------------------------------------------------------------------------ K16
+// VolumetricCloudRender.comp:139-210, one thread per quarter-res ray, 16x8 tiles (screen-coherent
+// rays share texture cache lines).  Tex-pipe / L1 bound; see DESIGN.md for the roofline.
+struct RayMarchContext {
+    float t;
+    float3 pos;
+    float height01;
+    float step_size;
+    float transmittance;
+    float transmittance_sum;
+    float weighted_t_sum;
+    float2 sun_env;
+    float cos_sun_view;
+};
+
+template <int MAT, bool HW, bool COUNT>
+SKY_D float SampleShadow(const CloudParams& P, float3 pos, int& evals, int& fetches) {  // :98-114
+    float optical_depth = 0.0f;
+    float inv_shadow_steps = 1.0f / P.b.uShadowSteps;
+    float3 sample_vector = P.b.uShadowDistance * f3(P.c.uSunDirection);
+    float previous_t = 0.0f;
+    for (float t = inv_shadow_steps; t <= 1.0f; t += inv_shadow_steps) {
+        float current_t = t * t;
+        float delta_t = current_t - previous_t;
+        float3 sample_pos = pos + sample_vector * (previous_t + 0.5f * delta_t);
+        float sample_height01 = CalHeight01(P.c, sample_pos);
+        optical_depth += SampleSigmaT<MAT, HW>(P.mat, sample_pos, sample_height01, COUNT ? &fetches : nullptr) * P.b.uShadowDistance * delta_t;
+        if (COUNT) ++evals;
+        previous_t = current_t;
+    }
+    return expf(-optical_depth);
+}
+
+template <int MAT, bool HW, bool COUNT>
+SKY_D void RayMarchStep(const CloudParams& P, RayMarchContext& ctx, int& evals, int& fetches) {  // :116-137
+    float sigma_t = SampleSigmaT<MAT, HW>(P.mat, ctx.pos, ctx.height01, COUNT ? &fetches : nullptr);
+    if (COUNT) ++evals;
+    if (sigma_t < 1e-5f) return;
+    float tr = expf(-ctx.step_size * sigma_t);
+    float transmittance_to_sun = SampleShadow<MAT, HW, COUNT>(P, ctx.pos, evals, fetches);
+    float phase = mixf(HenyeyGreenstein(ctx.cos_sun_view, -0.15f) * 2.16f, HenyeyGreenstein(ctx.cos_sun_view, 0.85f),
+                       expf(-P.b.uSunMultiscatteringSigmaScale * sigma_t));
+    float2 sun_env;
+    sun_env.x = transmittance_to_sun * phase;
+    sun_env.y = mixf(P.b.uEnvBottomVisibility, 1.0f, ctx.height01);
+    sun_env.y = sun_env.y - sun_env.y * expf(-P.b.uEnvMultiscatteringSigmaScale * sigma_t);
+    sun_env = sun_env - sun_env * tr;
+    ctx.sun_env += ctx.transmittance * sun_env;
+    ctx.transmittance_sum += ctx.transmittance;
+    ctx.weighted_t_sum += ctx.t * ctx.transmittance;
+    ctx.transmittance *= tr;
+}
+
+template <int MAT, bool HW, bool COUNT>
+__global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const SkyCloudBufferData& b = P.b;
+    const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
+    int px = blockIdx.x * 16 + (threadIdx.x & 15);
+    int row_in_band = blockIdx.y * 8 + (threadIdx.x >> 4);
+    int py = row_in_band;
+    if (P.band_rows > 0) {
+        // rows owned by this rank: ((py / band_rows) % band_count) == band_index
+        int local_band = row_in_band / P.band_rows;
+        py = (local_band * P.band_count + P.band_index) * P.band_rows + row_in_band % P.band_rows;
+    }
+    if (px >= QW || py >= QH) return;
+    uint32_t index = uint32_t(__ldg(P.index_linear + size_t(py) * QW + px).x);
+    int2 off = IndexToOffset(index);
+    int cx = px * 2 + off.x, cy = py * 2 + off.y;
+    float2 uv = f2((float(cx) + 0.5f) / float(HW_), (float(cy) + 0.5f) / float(HH));
+    float depth = checker_clamped(P, cx, cy);
+    float3 camera = f3(c.uCameraPos);
+    float3 sun = f3(c.uSunDirection);
+    float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
+    float3 view_dir = normalize(frag_pos - camera);
+
+    float r = c.uCameraPos[2] + c.uEarthRadius;
+    float mu = view_dir.z;
+    // RayShellIntersect, :39-71
+    float i0t1 = 0.0f, i0t2 = 0.0f, i1t1 = 0.0f, i1t2 = 0.0f;
+    {
+        float bottom_radius = c.uEarthRadius + c.uBottomAltitude;
+        float top_radius = c.uEarthRadius + c.uTopAltitude;
+        float discriminant_bottom = r * r * (mu * mu - 1.0f) + bottom_radius * bottom_radius;
+        float discriminant_top = r * r * (mu * mu - 1.0f) + top_radius * top_radius;
+        float sqrt_discriminant_bottom = sqrtf(discriminant_bottom);
+        float sqrt_discriminant_top = sqrtf(discriminant_top);
+        if (c.uCameraPos[2] < c.uBottomAltitude) {
+            i0t1 = -r * mu + sqrt_discriminant_bottom;
+            i0t2 = -r * mu + sqrt_discriminant_top;
+        } else if (c.uCameraPos[2] < c.uTopAltitude) {
+            if (discriminant_bottom >= 0.0f && mu < 0.0f) {
+                i0t2 = -r * mu - sqrt_discriminant_bottom;
+                i1t1 = -r * mu + sqrt_discriminant_bottom;
+                i1t2 = -r * mu + sqrt_discriminant_top;
+            } else {
+                i0t2 = -r * mu + sqrt_discriminant_top;
+            }
+        } else {
+            if (discriminant_bottom >= 0.0f && mu < 0.0f) {
+                i0t1 = -r * mu - sqrt_discriminant_top;
+                i0t2 = -r * mu - sqrt_discriminant_bottom;
+                i1t1 = -r * mu + sqrt_discriminant_bottom;
+                i1t2 = -r * mu + sqrt_discriminant_top;
+            } else if (discriminant_top >= 0.0f && mu < 0.0f) {
+                i0t1 = -r * mu - sqrt_discriminant_top;
+                i0t2 = -r * mu + sqrt_discriminant_top;
+            }
+        }
+    }
+    float frag_dist = distance(frag_pos, camera);
+    float limit = fminf(frag_dist, b.uMaxVisibleDistance);
+    i0t2 = fminf(fmaxf(limit, i0t1), i0t2);  // clamp(x, minVal, maxVal) = min(max(x, minVal), maxVal)
+    i1t2 = fminf(fmaxf(limit, i1t1), i1t2);
+
+    int evals = 0, fetches = 0;
+    RayMarchContext ctx;
+    ctx.cos_sun_view = dot(sun, view_dir);
+    float dist = i0t2 - i0t1;
+    dist = fminf(dist, b.uMaxRaymarchDistance);
+    uint32_t num_steps = uint32_t(fmaxf(b.uMaxRaymarchSteps * (dist / b.uMaxRaymarchDistance), 1.0f));
+    ctx.step_size = dist / float(num_steps);
+    ctx.transmittance = 1.0f;
+    ctx.transmittance_sum = 0.0f;
+    ctx.weighted_t_sum = 0.0f;
+    ctx.sun_env = f2(0.0f, 0.0f);
+    float noise = blue_noise_at(P.blue_noise, px, py);
+    float jitter = fractf(noise + c.uFrameID * 0.61803398875f);
+    ctx.t = i0t1 + ctx.step_size * jitter;
+    for (uint32_t cnt = num_steps; cnt != 0; cnt--, ctx.t += ctx.step_size) {
+        ctx.pos = camera + view_dir * ctx.t;  // UpdateContext, :90-93
+        ctx.height01 = CalHeight01(c, ctx.pos);
+        RayMarchStep<MAT, HW, COUNT>(P, ctx, evals, fetches);
+        if (ctx.transmittance < kMinTransmittance) break;
+    }
+    float dist1 = i1t2 - i1t1;
+    if (dist1 > 0) {
+        dist1 = fminf(dist1, b.uMaxRaymarchDistance);
+        uint32_t num_steps1 = uint32_t(fmaxf(b.uMaxRaymarchSteps * (dist1 / b.uMaxRaymarchDistance), 1.0f));
+        ctx.step_size = dist1 / float(num_steps1);
+        ctx.t = i1t1 + ctx.step_size * jitter;
+        for (uint32_t cnt = num_steps1; cnt != 0; cnt--, ctx.t += ctx.step_size) {
+            ctx.pos = camera + view_dir * ctx.t;
+            ctx.height01 = CalHeight01(c, ctx.pos);
+            RayMarchStep<MAT, HW, COUNT>(P, ctx, evals, fetches);
+            if (ctx.transmittance < kMinTransmittance) break;
+        }
+    }
+    float average_t = ctx.weighted_t_sum == 0 ? frag_dist : ctx.weighted_t_sum / ctx.transmittance_sum;
+    P.cloud_distance[size_t(py) * QW + px] = average_t;
+    float3 average_pos = camera + view_dir * average_t;
+    // GetSunVisibility(pos), VolumetricCloudCommon.glsl:73-79
+    float3 up_dir = f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius);
+    float up_len = length(up_dir);
+    up_dir /= up_len;
+    float mu_s = dot(sun, up_dir);
+    float3 sun_visibility = P.atm.GetSunVisibility(P.transmittance, up_len, mu_s);
+    float sun_cos_theta = clampf(dot(normalize(f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius)), sun), 0.0f, 1.0f);  // SunCosTheta :85-88
+    float3 luminance = ctx.sun_env.x * b.uSunIlluminanceScale * sun_visibility * P.atm.solar_illuminance() +
+                       ctx.sun_env.y * powf(sun_cos_theta, b.uEnvSunHeightCurveExp) * f3(b.uEnvColorScale);
+    // GetAerialPerspective, VolumetricCloudCommon.glsl:81-97
+    float ap_t = average_t;
+    if (r > P.atm.u.top_radius) {
+        float near_distance;
+        if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu, near_distance)) ap_t -= near_distance;
+        else ap_t = 0;
+    }
+    float3 uvw = aerial_perspective_uvw(uv, ap_t, c.uAerialPerspectiveLutMaxDistance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
+    float3 atmosphere_transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
+    float3 atmosphere_luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
+    atmosphere_luminance *= SampleRayScatterVisibility(P.froxel, uv, average_t, c.uInvShadowFroxelMaxDistance);
+    luminance = luminance * atmosphere_transmittance + atmosphere_luminance * (1 - ctx.transmittance);
+
+    luminance /= fmaxf(1e-5f, (1 - ctx.transmittance));
+    float fade = smoothstepf(b.uMaxVisibleDistance * 0.75f, b.uMaxVisibleDistance, i0t1);
+    ctx.transmittance = mixf(ctx.transmittance, 1.0f, fade);
+    luminance *= 1 - ctx.transmittance;
+    P.render[size_t(py) * QW + px] = to_half4(f4(luminance, ctx.transmittance));
+
+    if (COUNT) {  // counting variant is never the timed one
+        atomicAdd(P.counters + SKY_CNT_RENDER_SIGMA_EVALS, (unsigned long long)evals);
+        atomicAdd(P.counters + SKY_CNT_RENDER_TEX_FETCHES, (unsigned long long)fetches);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K17
+// VolumetricCloudReconstruct.comp:28-110: reproject last frame's half-res image through the cloud
+// distance, clamp to the depth-aware 3x3 neighbourhood AABB in Reinhard space, blend 0.2.
+SKY_D float4 Reinhard(float4 v) { return f4(v.x / (1.0f + v.x), v.y / (1.0f + v.y), v.z / (1.0f + v.z), v.w); }
+SKY_D float4 InverseReinhard(float4 v) { return f4(v.x / (1.0f - v.x), v.y / (1.0f - v.y), v.z / (1.0f - v.z), v.w); }
+
+SKY_D float4 sample_half4_linear_clamp(const half4* p, int w, int h, float u, float v) {
+    float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = int(fminf(fmaxf(fx, -2.0f), float(w) + 1.0f)), j0 = int(fminf(fmaxf(fy, -2.0f), float(h) + 1.0f));
+    int i1 = clampi(i0 + 1, 0, w - 1), j1 = clampi(j0 + 1, 0, h - 1);
+    i0 = clampi(i0, 0, w - 1); j0 = clampi(j0, 0, h - 1);
+    float4 t00 = load_half4(p + size_t(j0) * w + i0), t10 = load_half4(p + size_t(j0) * w + i1);
+    float4 t01 = load_half4(p + size_t(j1) * w + i0), t11 = load_half4(p + size_t(j1) * w + i1);
+    return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+}
+
+__global__ void __launch_bounds__(128) k17_reconstruct(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
+    int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (x >= HW_ || y >= HH) return;
+    int qx = x >> 1, qy = y >> 1;
+    float2 uv = f2((float(x) + 0.5f) / float(HW_), (float(y) + 0.5f) / float(HH));
+    float depth = __ldg(P.checkerboard + size_t(y) * HW_ + x);
+    float linear_depth = DepthToLinearDepth(c, depth);
+    // kOffsets, :35
+    const int ox[9] = {0, 0, 1, 1, 1, 0, -1, -1, -1}, oy[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1};
+    float rendered_linear_depths[9], delta_linear_depths[9];
+    float min_delta_linear_depth = 1e10f;
+    int nearest_i = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        // the two textureGathers + two texelFetchClamps of :37-49 read exactly these clamped texels
+        int tx = clampi(qx + ox[i], 0, QW - 1), ty = clampi(qy + oy[i], 0, QH - 1);
+        rendered_linear_depths[i] = __ldg(P.index_linear + size_t(ty) * QW + tx).y;
+        delta_linear_depths[i] = fabsf(rendered_linear_depths[i] - linear_depth);
+        if (delta_linear_depths[i] < min_delta_linear_depth) {
+            min_delta_linear_depth = delta_linear_depths[i];
+            nearest_i = i;
+        }
+    }
+    float4 taps[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        int tx = clampi(qx + ox[i], 0, QW - 1), ty = clampi(qy + oy[i], 0, QH - 1);
+        taps[i] = Reinhard(load_half4(P.render + size_t(ty) * QW + tx));
+    }
+    float4 rendered_nearest = taps[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) if (i == nearest_i) rendered_nearest = taps[i];
+    float4 aabb_min = rendered_nearest, aabb_max = rendered_nearest;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        float4 rendered = taps[i];
+        if (delta_linear_depths[i] < rendered_linear_depths[i] * 0.3f ||
+            fabsf(rendered.w - rendered_nearest.w) / fmaxf(1e-6f, 1 - fmaxf(rendered.w, rendered_nearest.w)) < 0.2f) {
+            aabb_min = min4(aabb_min, rendered);
+            aabb_max = max4(aabb_max, rendered);
+        }
+    }
+    float4 rendered = taps[0];
+    float3 camera = f3(c.uCameraPos);
+    float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
+    float3 view_dir = normalize(frag_pos - camera);
+    int cqx = clampi(qx, 0, QW - 1), cqy = clampi(qy, 0, QH - 1);
+    float rendered_distance = __ldg(P.cloud_distance + size_t(cqy) * QW + cqx);
+    float3 cloud_pos = camera + view_dir * rendered_distance;
+    float3 pre = projective_mul(c.uReprojectMat, cloud_pos);
+    float2 pre_uv = f2(pre.x * 0.5f + 0.5f, pre.y * 0.5f + 0.5f);
+    float4 pre_frame = Reinhard(sample_half4_linear_clamp(P.reconstruct_prev, HW_, HH, pre_uv.x, pre_uv.y));
+    pre_frame = min4(max4(pre_frame, aabb_min), aabb_max);
+
+    bool is_pre_out_of_screen = fmaxf(fabsf(pre.x), fabsf(pre.y)) > 1.0f;
+    int rendered_index = int(__ldg(P.index_linear + size_t(cqy) * QW + cqx).x);
+    int2 roff = IndexToOffset(uint32_t(rendered_index));
+    bool is_rendered = ((x & 1) == roff.x) && ((y & 1) == roff.y);
+    float rendered_weight = is_pre_out_of_screen ? 1.0f : is_rendered ? 0.2f : 0.0f;
+    float4 reconstructed = InverseReinhard(mix4(pre_frame, rendered, rendered_weight));
+    P.reconstruct_out[size_t(y) * HW_ + x] = to_half4(reconstructed);
+}
+
+// ------------------------------------------------------------------------------------------------ K18
+// VolumetricCloudUpscale.comp:11-55: depth-aware 4-tap upscale and composite over the HDR target.
+// HBM-bound: 4 B depth + 8 B hdr read + 8 B hdr write per full-res pixel.
+__global__ void __launch_bounds__(256) k18_upscale(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const int HW_ = P.width / 2, HH = P.height / 2;
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.width || y >= P.height) return;
+    float depth = __ldg(P.depth + size_t(y) * P.width + x);
+    float linear_depth = DepthToLinearDepth(c, depth);
+    const int ox[4] = {-1, 1, 1, -1}, oy[4] = {1, 1, -1, -1};  // same order as textureGather
+    int bx = (x - 1) >> 1, by = (y - 1) >> 1;
+    float neighbor_depths[4] = {checker_clamped(P, bx, by + 1), checker_clamped(P, bx + 1, by + 1),
+                                checker_clamped(P, bx + 1, by), checker_clamped(P, bx, by)};
+    float4 reconstructed_neighbors[4];
+    float min_delta_linear_depth = 1e10f;
+    int nearest_i = 0;
+    bool is_edge = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int hx = clampi((x + ox[i]) >> 1, 0, HW_ - 1), hy = clampi((y + oy[i]) >> 1, 0, HH - 1);
+        reconstructed_neighbors[i] = load_half4(P.reconstruct_out + size_t(hy) * HW_ + hx);
+        float neighbor_linear_depth = DepthToLinearDepth(c, neighbor_depths[i]);
+        float delta_linear_depth = fabsf(linear_depth - neighbor_linear_depth);
+        if (delta_linear_depth < min_delta_linear_depth) {
+            nearest_i = i;
+            min_delta_linear_depth = delta_linear_depth;
+        }
+        if (delta_linear_depth > linear_depth * 0.1f) is_edge = true;
+    }
+    float max_a = fmaxf(fmaxf(reconstructed_neighbors[0].w, reconstructed_neighbors[1].w), fmaxf(reconstructed_neighbors[2].w, reconstructed_neighbors[3].w));
+    float min_a = fminf(fminf(reconstructed_neighbors[0].w, reconstructed_neighbors[1].w), fminf(reconstructed_neighbors[2].w, reconstructed_neighbors[3].w));
+    float4 upscaled;
+    if (is_edge && (max_a - min_a) / fmaxf(1e-6f, 1 - min_a) > 0.2f) {
+        upscaled = reconstructed_neighbors[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) if (i == nearest_i) upscaled = reconstructed_neighbors[i];
+    } else {
+        upscaled = ((reconstructed_neighbors[0] + reconstructed_neighbors[1]) + (reconstructed_neighbors[2] + reconstructed_neighbors[3])) * 0.25f;
+    }
+    float transmittance = upscaled.w;
+    half4* dst = P.hdr + size_t(y) * P.width + x;
+    float4 color = load_half4(dst);
+    float k = transmittance <= kMinTransmittance ? 0.0f : transmittance;
+    color.x = color.x * k + upscaled.x;
+    color.y = color.y * k + upscaled.y;
+    color.z = color.z * k + upscaled.z;
+    *dst = to_half4(color);
+}
+
+// ------------------------------------------------------------------------------------------------ tex peak
+// Texture-pipe roofline microbenchmark: every thread issues `iters` independent trilinear R8 fetches
+// over the (L1/L2-resident) detail volume; mode 0 = coherent (neighbouring threads, neighbouring
+// texels), mode 1 = incoherent (hashed coordinates).
+__global__ void __launch_bounds__(256) k_tex_peak(cudaTextureObject_t tex, int iters, int mode, float* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.0f;
+    float u = float(tid & 127) * (1.0f / 128.0f), v = float((tid >> 7) & 127) * (1.0f / 128.0f), w = float((tid >> 14) & 127) * (1.0f / 128.0f);
+    uint32_t s = tid * 747796405u + 2891336453u;
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (mode == 0) {
+                u += 0.00390625f; w += 0.0009765625f;
+            } else {
+                s = s * 1664525u + 1013904223u;
+                u = float(s >> 8) * (1.0f / 16777216.0f);
+                v = float((s * 2654435761u) >> 8) * (1.0f / 16777216.0f);
+                w = float((s * 40503u) >> 8) * (1.0f / 16777216.0f);
+            }
+            acc += tex3DLod<float>(tex, u, v, w, 0.0f);
+        }
+    }
+    if (acc == -1.0f) sink[tid] = acc;
+}
+
+CloudParams make_cloud_params(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
+    CloudParams P{};
+    P.c = c;
+    P.atm.u = ctx->atm;
+    make_material_params(ctx, c.uCameraPos, P.mat);
+    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
+    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d};
+    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d};
+    P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
+    P.blue_noise = ctx->blue_noise;
+    P.counters = ctx->counters;
+    P.shadow_w = ctx->shadow_maps[0].w; P.shadow_h = ctx->shadow_maps[0].h;
+    P.width = ctx->width; P.height = ctx->height;
+    P.checkerboard = ctx->checkerboard_depth.p;
+    P.index_linear = ctx->index_linear_depth.p;
+    P.render = ctx->render_texture.p;
+    P.cloud_distance = ctx->cloud_distance.p;
+    return P;
+}
+
+}  // namespace
+
+int make_material_params(SkyContext* ctx, const float* camera_pos, MaterialParams& M) {
+    M.m = ctx->material;
+    M.cloud_map = ctx->cloud_map.view;
+    M.detail = ctx->detail.view;
+    M.displacement = ctx->displacement.view;
+    M.voxel = ctx->voxel.view;
+    M.camera_pos = f3(camera_pos);
+    return 0;
+}
+
+static int check_material_ready(SkyContext* ctx) {
+    switch (ctx->material.type) {
+        case SKY_MATERIAL_DEFAULT0:
+            if (!ctx->displacement.valid) return sky_fail(ctx, "displacement texture has not been generated");
+            // fall through
+        case SKY_MATERIAL_DEFAULT1:
+            if (!ctx->cloud_map.valid || !ctx->detail.valid) return sky_fail(ctx, "cloud map / detail texture has not been generated");
+            return 0;
+        case SKY_MATERIAL_MINIMAL: return 0;
+        case SKY_MATERIAL_VOXEL:
+            if (!ctx->voxel.valid) return sky_fail(ctx, "voxel grid has not been uploaded");
+            return 0;
+    }
+    return sky_fail(ctx, "set_material has not been called with a known material type");
+}
+
+int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
+    if (int e = check_material_ready(ctx)) return e;
+    std::swap(ctx->shadow_maps[0], ctx->shadow_maps[1]);  // VolumetricCloud.cpp:284
+    CloudParams P = make_cloud_params(ctx, c);
+    P.shadow_prev = ctx->shadow_maps[1].p;
+    P.shadow_out = ctx->shadow_maps[0].p;
+    P.shadow_blurred = ctx->shadow_maps[2].p;
+    P.froxel_out = ctx->shadow_froxel.p;
+    const bool count = ctx->counting;
+    dim3 grid(ceil_div(P.shadow_w, 16), ceil_div(P.shadow_h, 8));
+    int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
+        if (count) k11_shadow_map<MAT, HW, true><<<grid, 128, 0, ctx->stream>>>(P);
+        else k11_shadow_map<MAT, HW, false><<<grid, 128, 0, ctx->stream>>>(P);
+        return 0;
+    });
+    if (rc) return sky_fail(ctx, "unknown material");
+    SKY_LAUNCH_CHECK(ctx);
+    dim3 bgrid(ceil_div(P.shadow_w, 128), P.shadow_h);
+    k12_blur<true><<<bgrid, 128, 0, ctx->stream>>>(ctx->shadow_maps[0].p, ctx->shadow_maps[1].p, P.shadow_w, P.shadow_h);
+    SKY_LAUNCH_CHECK(ctx);
+    k12_blur<false><<<bgrid, 128, 0, ctx->stream>>>(ctx->shadow_maps[1].p, ctx->shadow_maps[2].p, P.shadow_w, P.shadow_h);
+    SKY_LAUNCH_CHECK(ctx);
+    k13_shadow_froxel<<<dim3(ceil_div(P.froxel.w, 64), P.froxel.h), 64, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const SkyCloudBufferData& b, const float* depth,
+                       int band_rows, int band_index, int band_count) {
+    if (int e = check_material_ready(ctx)) return e;
+    if (!ctx->ap_lum.p || !ctx->transmittance.p) return sky_fail(ctx, "atmosphere LUTs have not been baked");
+    CloudParams P = make_cloud_params(ctx, c);
+    P.b = b;
+    P.depth = depth;
+    const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
+    k14_checkerboard<<<dim3(ceil_div(HW_, 256), HH), 256, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    k15_index_gen<<<dim3(ceil_div(QW, 128), QH), 128, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    int rows = QH;
+    if (band_rows > 0 && band_count > 1) {
+        P.band_rows = band_rows; P.band_index = band_index; P.band_count = band_count;
+        int bands_total = ceil_div(QH, band_rows);
+        int my_bands = (bands_total - band_index + band_count - 1) / band_count;
+        rows = my_bands * band_rows;
+    }
+    dim3 grid(ceil_div(QW, 16), ceil_div(rows, 8));
+    const bool count = ctx->counting;
+    int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
+        if (count) k16_render<MAT, HW, true><<<grid, 128, 0, ctx->stream>>>(P);
+        else k16_render<MAT, HW, false><<<grid, 128, 0, ctx->stream>>>(P);
+        return 0;
+    });
+    if (rc) return sky_fail(ctx, "unknown material");
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr) {
+    CloudParams P = make_cloud_params(ctx, c);
+    P.depth = depth;
+    P.hdr = hdr;
+    P.reconstruct_out = ctx->reconstruct[0].p;
+    P.reconstruct_prev = ctx->reconstruct[1].p;
+    const int HW_ = P.width / 2, HH = P.height / 2;
+    k17_reconstruct<<<dim3(ceil_div(HW_, 16), ceil_div(HH, 8)), 128, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(P.height, 8)), 256, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    std::swap(ctx->reconstruct[0], ctx->reconstruct[1]);  // VolumetricCloud.cpp:421-422
+    return 0;
+}
+
+int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
+    if (!ctx->detail.valid) return sky_fail(ctx, "tex_peak needs the detail volume (noise_generate(SKY_NOISE_DETAIL))");
+    const int iters = 1024, blocks = 148 * 16, threads = 256;
+    cudaEvent_t e0, e1;
+    SKY_CUDA(ctx, cudaEventCreate(&e0));
+    SKY_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        SKY_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        k_tex_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->detail.view.tex_linear, iters, mode, nullptr);
+        SKY_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        SKY_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        SKY_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *fetches_per_second = double(blocks) * threads * iters / (double(best) * 1e-3);
+    return 0;
+}

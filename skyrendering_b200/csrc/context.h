@@ -1,0 +1,124 @@
+// SkyContext: everything one GL context owned in the reference (Atmosphere.h:84-91,
+// AtmosphereRenderer.h:118-128, VolumetricCloud.h:99-128), as device allocations on one GPU.
+#pragma once
+#include <string>
+
+#include "common.cuh"
+
+constexpr int kMaxMipLevels = 13;  // up to 4096 texels per axis
+
+// A UNORM8 texture with its full mip chain, kept twice: as linear device memory (exact fp32
+// software filtering, the default) and as a CUDA mip-mapped array behind two texture objects
+// (hardware filtering, opt-in; 8-bit interpolation weights).
+struct MipView {
+    const uint8_t* base;            // all levels, level l at base + off[l]*channels
+    unsigned long long off[kMaxMipLevels];
+    int w[kMaxMipLevels], h[kMaxMipLevels], d[kMaxMipLevels];
+    int levels;
+    int channels;
+    cudaTextureObject_t tex_linear;  // LINEAR, level 0 (magnification)
+    cudaTextureObject_t tex_point;   // POINT over the mip chain (NEAREST_MIPMAP_NEAREST)
+};
+
+struct MipTextureDev {
+    MipView view{};
+    uint8_t* data = nullptr;
+    size_t bytes = 0;
+    cudaMipmappedArray_t array = nullptr;
+    bool is3d = false;
+    bool border = false;  // CLAMP_TO_BORDER(0) instead of REPEAT
+    bool valid = false;
+};
+
+template <class T>
+struct Lut {  // plain row-major image in device memory
+    T* p = nullptr;
+    int w = 0, h = 0, d = 1;
+    size_t bytes() const { return size_t(w) * h * d * sizeof(T); }
+};
+
+struct SkyContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    bool hw_filtering = false;
+    bool counting = false;
+
+    // uniforms last seen
+    SkyAtmosphereBufferData atm{};
+    SkyAtmosphereRenderBufferData render{};
+    SkyLutConfig lut_cfg{};
+    SkyMaterialBlock material{};
+    SkyPathTracingInit pt{};
+    SkyCloudCommonBufferData last_common{};  // uniforms of the frame opened by cloud_frame_begin
+
+    // K1-K5
+    Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
+    Lut<half4> env;  // [6][S][S]
+    uint16_t* blue_noise = nullptr;  // 64x64 u16
+
+    // materials
+    MipTextureDev cloud_map, detail, displacement, voxel;
+
+    // shadow chain
+    Lut<float2> shadow_maps[3];
+    Lut<uint16_t> shadow_froxel;
+
+    // viewport
+    int width = 0, height = 0;
+    Lut<float> checkerboard_depth, cloud_distance;
+    Lut<float2> index_linear_depth;
+    Lut<half4> render_texture, reconstruct[2];
+
+    // path tracer
+    Lut<float4> pt_accum;
+    Lut<uint8_t> pt_mask;
+
+    unsigned long long* counters = nullptr;  // SkyCounter slots
+
+    // staging for *_host entry points
+    float* stage_depth = nullptr;
+    half4* stage_hdr = nullptr;
+    size_t stage_pixels = 0;
+};
+
+// error plumbing ------------------------------------------------------------------------------------------
+int sky_fail(SkyContext* ctx, const std::string& msg);
+#define SKY_CUDA(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return sky_fail(ctx, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+#define SKY_LAUNCH_CHECK(ctx) SKY_CUDA(ctx, cudaGetLastError())
+
+template <class T>
+int sky_alloc(SkyContext* ctx, Lut<T>& l, int w, int h, int d = 1, bool zero = true) {
+    if (l.p && l.w == w && l.h == h && l.d == d) {
+        if (zero) SKY_CUDA(ctx, cudaMemsetAsync(l.p, 0, l.bytes(), ctx->stream));
+        return 0;
+    }
+    if (l.p) SKY_CUDA(ctx, cudaFree(l.p));
+    l.p = nullptr;
+    l.w = w; l.h = h; l.d = d;
+    if (l.bytes() == 0) return 0;
+    SKY_CUDA(ctx, cudaMalloc(&l.p, l.bytes()));
+    if (zero) SKY_CUDA(ctx, cudaMemsetAsync(l.p, 0, l.bytes(), ctx->stream));
+    return 0;
+}
+
+// per-subsystem launchers (defined in the .cu files) -----------------------------------------------------------
+int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
+int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5
+int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6
+int launch_noise(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info);   // noise.cu       K8-K10
+int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, int channels, bool border);
+int launch_mip_chain(SkyContext* ctx, MipTextureDev& t);                       // noise.cu       glGenerateTextureMipmap
+int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c);   // cloud.cu       K11-K13
+int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const SkyCloudBufferData& b, const float* depth,
+                       int band_rows, int band_index, int band_count);         // cloud.cu       K14-K16
+int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr);  // K17,K18
+int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32_t frame_begin, uint32_t count,
+                      const int32_t region[4]);                                // pathtrace.cu   K19
+int launch_pt_resolve(SkyContext* ctx, uint32_t frame_count, half4* hdr);      // pathtrace.cu   K20
+int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second);    // cloud.cu
