@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SkyRendering hot path on B200 (contract in the task brief).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores (oracle port)
+
+BASELINE.json's metric has two halves; one JSON line carries both:
+  * headline `value`: path-traced samples/s (Gsamples/s) of the voxel-cloud path tracer (scene c5,
+    1280x720, reference defaults: 128 bounces, +-100 km box, PCG, ground multi-bounce) on the synthetic
+    126x154x86 grid.  One step = `--spp` samples per pixel of that image, split across the N ranks by
+    kFrameId range and summed with ONE all-reduce -- the partition a 1024-spp job uses (strong scaling).
+  * `frame_4k`: the 3840x2160 cloud frame (scene c3), milliseconds per frame, with the tex-pipe / HBM
+    roofline of K16 and of K17/K18; at N > 1 the K16 rows are tile-sharded with an all-gather.
+Both are timed with CUDA events on the launching stream, L2 flushed between timed iterations, max over
+ranks.  `e2e` repeats the headline through the C-ABI entry point that takes HOST buffers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PT_W, PT_H = 1280, 720          # reference default window (main.cpp:14)
+FRAME_W, FRAME_H = 3840, 2160
+CPU_PT_W, CPU_PT_H, CPU_PT_SPP = 160, 90, 8   # bounded CPU sample of the same workload
+CPU_FRAME_W, CPU_FRAME_H = 480, 270
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own algorithm on the host cores: the oracle port (the GLSL cannot run here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.parity import oracle_library
+    from skyrendering_b200 import abi
+    from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
+    orc = oracle_library()
+    cores = os.cpu_count()
+    r = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
+    r.upload_voxels(synthetic_voxel_grid())
+    r.prime()
+    common, cloud, _ = r.cloud_update(0.0)
+    r.ctx.cloud_shadow(common)
+    r.atmosphere_render_luts()
+    r.path_trace_begin()
+    times = []
+    for i in range(args.warmup + args.steps):
+        r.path_trace_begin()
+        t0 = time.perf_counter()
+        r.ctx.pt_samples(common, 1, CPU_PT_SPP, [0, 0, CPU_PT_W, CPU_PT_H])
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = CPU_PT_W * CPU_PT_H * CPU_PT_SPP / (ms * 1e-3) / 1e9
+    sample = f"{CPU_PT_W}x{CPU_PT_H} x {CPU_PT_SPP} spp per step of the same scene/grid/parameters (oracle port, OpenMP)"
+    line = {
+        "impl": "reference", "metric": "path_traced_gsamples_per_s", "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, reference=True),
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, reference=False):
+    return {
+        "workload": "c5 voxel-cloud path tracer 1280x720 (bin/config_voxel.json, synthetic 126x154x86 R8 grid at the wdas_cloud_sixteenth bounds), "
+                    f"{args.spp} spp per step of a 1024-spp job, kFrameId ranges split across ranks + one all-reduce",
+        "pt": {"width": PT_W, "height": PT_H, "spp_per_step": args.spp, "max_bounces": 128, "region_box_half_width_km": 100.0,
+               "prng": "PCGHash", "environment_lighting": "GROUND_MULTI_BOUNCE", "mode": "reference RNG streams (stream-exact)"},
+        "frame_4k": {"scene": "c3 (bin/config3.json) 3840x2160, quarter-res raymarch 960x540, static camera"},
+        "filtering": "hardware" if args.hw_filtering else "exact-fp32",
+        "l2": "flushed between timed iterations (256 MiB write)",
+        "cpu_sample": f"{CPU_PT_W}x{CPU_PT_H}x{CPU_PT_SPP}spp" if reference else None,
+    }
+
+
+# ------------------------------------------------------------------------------------------------- CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--spp", type=int, default=8, help="samples per pixel per step (whole job, all ranks)")
+    ap.add_argument("--hw-filtering", action="store_true", help="texture-unit filtering (8-bit weights) instead of exact fp32")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-frame", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from skyrendering_b200 import abi
+    from skyrendering_b200.distributed import ShardedCloudFrame, ShardedPathTracer, frame_ranges
+    from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cuda = abi.cuda_library()  # fails loudly if the extension is missing
+    peaks, peak_kind = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def timed_steps(step_fn, steps, warmup):
+        """W untimed + exactly K timed steps, each bracketed by CUDA events on the launching stream,
+        barrier + synchronize on both sides, max over ranks."""
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        total_ms = 0.0
+        for _ in range(steps):
+            flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            e0.record()
+            step_fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    def kernel_ms(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        best = []
+        for _ in range(reps):
+            flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            best.append(e0.elapsed_time(e1))
+        return float(np.mean(best))
+
+    # ---- path tracer ----------------------------------------------------------------------------------
+    rp = Renderer("c5", PT_W, PT_H, library=cuda, device=local_rank)
+    rp.ctx.set_hw_filtering(args.hw_filtering)
+    rp.upload_voxels(synthetic_voxel_grid())
+    rp.prime()
+    common_pt, _, _ = rp.cloud_update(0.0)
+    rp.ctx.cloud_shadow(common_pt)
+    rp.atmosphere_render_luts()
+    rp.path_trace_begin()
+    spt = ShardedPathTracer(rp, rank, world)
+    my_begin, my_count = frame_ranges(args.spp, world)[rank]
+    region = [0, 0, PT_W, PT_H]
+
+    def pt_step():
+        rp.ctx.pt_begin(rp.pt_init)      # each step is an independent spp-sample job: clear, trace, reduce
+        spt.render(common_pt, args.spp)
+        spt.reduce()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    pt_ms = timed_steps(pt_step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    pt_value = PT_W * PT_H * args.spp / (pt_ms * 1e-3) / 1e9
+
+    # end to end through the C-ABI call with HOST buffers (pinned), per rank its share + host-side sum on rank 0
+    accum_host = torch.empty((PT_H, PT_W, 4), dtype=torch.float32).pin_memory()
+
+    def pt_step_host():
+        rp.ctx.pt_begin(rp.pt_init)
+        if my_count > 0:
+            rp.ctx.pt_samples_host(common_pt, my_begin, my_count, region, accum_host.numpy())
+        if world > 1:
+            spt.reduce()
+
+    e2e_ms = timed_steps(pt_step_host, max(1, args.steps), 1)
+    e2e_value = PT_W * PT_H * args.spp / (e2e_ms * 1e-3) / 1e9
+    h2d = 384 + 16 + 16  # common block + region + frame ids: the only inputs of a step
+    d2h = PT_W * PT_H * 16
+
+    # dominant kernel K19 on this rank: duration, work counters, roofline
+    k19_ms = kernel_ms(lambda: rp.ctx.pt_samples(common_pt, my_begin, max(my_count, 1), region), reps=2)
+    rp.ctx.counters_enable(True)
+    rp.ctx.pt_samples(common_pt, my_begin, max(my_count, 1), region)
+    rp.ctx.sync()
+    cnt = rp.ctx.counters()
+    rp.ctx.counters_enable(False)
+    # the detail volume for the tex-pipe microbenchmark lives in a default-material context
+    rf = Renderer("c3", FRAME_W, FRAME_H, library=cuda, device=local_rank)
+    rf.ctx.set_hw_filtering(args.hw_filtering)
+    rf.prime()
+    rf.cloud_update(0.0)
+    tex_peak = rf.ctx.tex_peak(0)
+    lookups, collisions = int(cnt[abi.CNT_PT_LOOKUPS]), int(cnt[abi.CNT_PT_COLLISIONS])
+    lookups_per_s = lookups / (k19_ms * 1e-3)
+    pt_roofline = {
+        "kernel": "k19_path_trace", "bound": "tex", "achieved": lookups_per_s / 1e9, "peak": tex_peak / 1e9, "unit": "Gfetch/s",
+        "frac": lookups_per_s / tex_peak, "traffic": None,
+        "note": "grid (1.7 MB + mips) is L2-resident: trilinear-lookup rate vs the same-run tex-pipe microbenchmark; "
+                "the kernel is bound by the sequential RNG/log chain of null collisions, see DESIGN.md",
+        "hbm": {"achieved": lookups * 8 / (k19_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": lookups * 8 / (k19_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind},
+        "lookups_per_launch": lookups, "tentative_collisions_per_launch": collisions, "paths_per_launch": int(cnt[abi.CNT_PT_PATHS]),
+        "ms_per_launch": k19_ms,
+    }
+
+    # ---- 4K cloud frame ---------------------------------------------------------------------------------
+    frame = None
+    if not args.skip_frame:
+        depth_np = rf.scene.ground_depth(FRAME_W, FRAME_H)
+        depth = torch.from_numpy(depth_np).cuda()
+        hdr = torch.zeros((FRAME_H, FRAME_W, 4), dtype=torch.float16, device="cuda")
+        scf = ShardedCloudFrame(rf, rank, world, band_rows=8)
+        state = {}
+
+        def frame_step():
+            rf.earth_update()
+            common, cloud, _ = rf.cloud_update(0.0)
+            rf.ctx.cloud_shadow(common)
+            rf.atmosphere_render_luts()
+            rf.ctx.composite(depth, hdr, FRAME_W, FRAME_H)
+            scf.frame(common, cloud, depth, hdr)
+            state["u"] = (common, cloud)
+
+        frame_ms = timed_steps(frame_step, max(args.steps, 5), max(args.warmup, 8))
+        common, cloud = state["u"]
+        parts = {
+            "bake_K1_K2": kernel_ms(rf.earth_update), "luts_K3_K5": kernel_ms(rf.atmosphere_render_luts),
+            "shadow_K11_K13": kernel_ms(lambda: rf.ctx.cloud_shadow(common)),
+            "composite_K6": kernel_ms(lambda: rf.ctx.composite(depth, hdr, FRAME_W, FRAME_H)),
+            "K14_K16": kernel_ms(lambda: rf.ctx.cloud_frame_begin(common, cloud, depth)),
+            "K17_K18": kernel_ms(lambda: rf.ctx.cloud_frame_end(depth, hdr)),
+        }
+        rf.ctx.counters_enable(True)
+        rf.ctx.cloud_frame_begin(common, cloud, depth)
+        rf.ctx.sync()
+        fc = rf.ctx.counters()
+        rf.ctx.counters_enable(False)
+        evals, fetches = int(fc[abi.CNT_RENDER_SIGMA_EVALS]), int(fc[abi.CNT_RENDER_TEX_FETCHES])
+        k16_s = parts["K14_K16"] * 1e-3
+        hbm_bytes = FRAME_W * FRAME_H * (4 + 8 + 8) + (FRAME_W // 2) * (FRAME_H // 2) * (8 + 8 + 4)  # K17+K18 algorithmic
+        hdr_host = torch.zeros((FRAME_H, FRAME_W, 4), dtype=torch.float16).pin_memory()
+        depth_host = torch.from_numpy(depth_np).pin_memory()
+        e2e_frame_ms = timed_steps(lambda: rf.ctx.cloud_frame_host(common, cloud, depth_host.numpy(), hdr_host.numpy()), 3, 1) if world == 1 else None
+        frame = {
+            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "unit": "ms", "higher_is_better": False,
+            "frame_definition": "one AppWindow::HandleDisplayEvent: K1,K2 bake, K11-K13 shadow chain, K3-K5 LUTs, K6 composite, K14-K18 cloud chain",
+            "parts_ms": parts, "gpu_launches": 15,
+            "sigma_evals_per_frame": evals, "tex_fetches_per_frame": fetches,
+            "roofline": {"kernel": "k16_render (+K14,K15)", "bound": "tex", "achieved": fetches / k16_s / 1e9, "peak": tex_peak / 1e9,
+                         "unit": "Gfetch/s", "frac": fetches / k16_s / tex_peak, "traffic": None,
+                         "peak_source": "same-run microbenchmark: coherent trilinear R8 fetches over the L2-resident 128^3 volume"},
+            "roofline_K17_K18": {"bound": "hbm", "achieved": hbm_bytes / (parts["K17_K18"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": hbm_bytes / (parts["K17_K18"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind},
+            "e2e_host_buffers_ms": e2e_frame_ms,
+            "e2e_h2d_bytes": FRAME_W * FRAME_H * 12, "e2e_d2h_bytes": FRAME_W * FRAME_H * 8,
+        }
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample ------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        from tests.parity import oracle_library
+        orc = oracle_library()
+        ro = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
+        ro.upload_voxels(synthetic_voxel_grid())
+        ro.prime()
+        c, _, _ = ro.cloud_update(0.0)
+        ro.ctx.cloud_shadow(c)
+        ro.atmosphere_render_luts()
+        ro.path_trace_begin()
+        t0 = time.perf_counter()
+        ro.ctx.pt_samples(c, 1, CPU_PT_SPP, [0, 0, CPU_PT_W, CPU_PT_H])
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": CPU_PT_W * CPU_PT_H * CPU_PT_SPP / dt / 1e9, "unit": "Gsamples/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{CPU_PT_W}x{CPU_PT_H} x {CPU_PT_SPP} spp of the same scene, grid and parameters ({dt:.1f} s of OpenMP oracle)"}
+        if frame is not None:
+            from tests.parity import run_cloud_frames
+            t0 = time.perf_counter()
+            run_cloud_frames("c3", CPU_FRAME_W, CPU_FRAME_H, orc, frames=1, device="cpu")
+            dtf = time.perf_counter() - t0
+            frame["cpu_baseline"] = {"value": dtf * 1e3, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                                     "sample": f"one {CPU_FRAME_W}x{CPU_FRAME_H} frame (1/64 of the 4K pixels) incl. LUT bake and noise generation"}
+
+    if rank == 0:
+        line = {
+            "metric": "path_traced_gsamples_per_s", "value": pt_value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": pt_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": args.steps * 1,
+            "roofline": pt_roofline, "cpu_baseline": cpu_baseline, "frame_4k": frame,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -106,7 +106,7 @@ void AtmosphereRenderer::BakeAerialPerspective(Image<4>& luminance_image, Image<
                 bool intersect_bottom = atm.RayIntersectsGround(r, mu);
                 float max_marching_distance = intersect_bottom ? marching_distance : atm.DistanceToTopAtmosphereBoundary(r, mu);
                 vec3 start_position = ComputeRaymarchingStartPositionAndChangeDistance(view_direction, max_marching_distance);
-                marching_distance = std::min(marching_distance, max_marching_distance);
+                marching_distance = min(marching_distance, max_marching_distance);
                 vec3 transmittance(1.0f), luminance(0.0f);
                 if (marching_distance > 0) {
                     float start_i = DitherStart(cfg.aerial_perspective_dither != 0, x, y);
@@ -196,7 +196,7 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
             if (depth != 1.0f) {
                 float object_distance = length(fragment_position - camera_position());
                 intersect_object = true;
-                marching_distance = std::min(marching_distance, object_distance);
+                marching_distance = min(marching_distance, object_distance);
             }
             vec3 start_position = ComputeRaymarchingStartPositionAndChangeDistance(view_direction, marching_distance);
             vec3 transmittance(1.0f), luminance(0.0f);

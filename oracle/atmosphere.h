@@ -33,8 +33,8 @@ struct Atmosphere {
 
     // Atmosphere.glsl:37-51
     static float ClampCosine(float mu) { return clamp(mu, -1.0f, 1.0f); }
-    static float ClampDistance(float d) { return std::max(d, 0.0f); }
-    static float SafeSqrt(float a) { return std::sqrt(std::max(a, 0.0f)); }
+    static float ClampDistance(float d) { return max(d, 0.0f); }
+    static float SafeSqrt(float a) { return std::sqrt(max(a, 0.0f)); }
 
     // Atmosphere.glsl:53-55
     static vec2 GetTextureCoordFromUnitRange(vec2 xy, ivec2 size) {
@@ -106,7 +106,7 @@ struct Atmosphere {
     // Atmosphere.glsl:110-117
     vec3 GetSunVisibility(const Image<4>& tex, float r, float mu_s) const {
         float sin_theta_h = u.bottom_radius / r;
-        float cos_theta_h = -std::sqrt(std::max(1.0f - sin_theta_h * sin_theta_h, 0.0f));
+        float cos_theta_h = -std::sqrt(max(1.0f - sin_theta_h * sin_theta_h, 0.0f));
         return GetTransmittanceToTopAtmosphereBoundary(tex, r, mu_s) *
                smoothstep(-sin_theta_h * u.sun_angular_radius, sin_theta_h * u.sun_angular_radius, mu_s - cos_theta_h);
     }
@@ -118,7 +118,7 @@ struct Atmosphere {
         vec3 mie_extinction = (mie_scattering() + mie_absorption()) *
                               clamp(std::exp(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
         vec3 ozone_extinction =
-            ozone_absorption() * std::max(0.0f, altitude < u.ozone_center_altitude
+            ozone_absorption() * max(0.0f, altitude < u.ozone_center_altitude
                                                    ? 1.0f + (altitude - u.ozone_center_altitude) * u.inv_ozone_width
                                                    : 1.0f - (altitude - u.ozone_center_altitude) * u.inv_ozone_width);
         return rayleigh_extinction + mie_extinction + ozone_extinction;
@@ -324,14 +324,14 @@ struct AtmosphereRenderer {
         float x_cos_lat;
         if (lat < horizon_up_angle) {
             float coord = lat / horizon_up_angle;
-            coord = std::sqrt(std::max(1 - coord, 0.0f));
+            coord = std::sqrt(max(1 - coord, 0.0f));
             x_cos_lat = 0.5f - 0.5f * coord;
         } else {
             float coord = (lat - horizon_up_angle) / horizon_down_angle;
-            coord = std::sqrt(std::max(coord, 0.0f));
+            coord = std::sqrt(max(coord, 0.0f));
             x_cos_lat = coord * 0.5f + 0.5f;
         }
-        float x_cos_lon = std::sqrt(std::max(0.5f - 0.5f * cos_lon, 0.0f));
+        float x_cos_lon = std::sqrt(max(0.5f - 0.5f * cos_lon, 0.0f));
         return Atmosphere::GetTextureCoordFromUnitRange(vec2(x_cos_lon, x_cos_lat), sky_size());
     }
     // AtmosphereRenderer.glsl:134-145

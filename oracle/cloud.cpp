@@ -71,7 +71,7 @@ float CloudScene::SampleSigmaT(vec3 pos, float height01, int slot) {
             float det = detail.texture_lod(uvwlod.xyz(), uvwlod.w, kRepeat).x;
             fetches = 2;
             det = (det + m.uDetailBase) * m.uDetailScale;
-            det *= std::max(clamp(height01 - m.uHeightCut, 0.0f, 1.0f), clamp(m.uEdgeCur - cloud_type.x, 0.0f, 1.0f));
+            det *= max(clamp(height01 - m.uHeightCut, 0.0f, 1.0f), clamp(m.uEdgeCur - cloud_type.x, 0.0f, 1.0f));
             result = clamp(density - det, 0.0f, 1.0f) * mc.uDensity * height01;
             break;
         }
@@ -147,8 +147,8 @@ void CloudScene::ShadowMap() {
                     t2 = -r * mu + (discriminant_bottom >= 0 ? -sqrt_discriminant_bottom : sqrt_discriminant_top);
                 }
             }
-            float dist = std::max(t2 - t1, 0.0f);
-            dist = std::min(dist, 1.0f / std::cos(radians(85.0f)) * (c.uTopAltitude - c.uBottomAltitude));
+            float dist = max(t2 - t1, 0.0f);
+            dist = min(dist, 1.0f / std::cos(radians(85.0f)) * (c.uTopAltitude - c.uBottomAltitude));
 
             float optical_depth = 0.0f;
             if (dist > 0.0f) {
@@ -189,8 +189,8 @@ void CloudScene::ShadowBlur() {
                 vec2 res = vec2(in.at(x, y)[0], in.at(x, y)[1]) * weight[0];
                 for (int i = 1; i < 5; ++i) {
                     int x1 = x, y1 = y, x2 = x, y2 = y;
-                    if (horizontal) { x1 = std::max(x - i, 0); x2 = std::min(x + i, in.w - 1); }
-                    else { y1 = std::max(y - i, 0); y2 = std::min(y + i, in.h - 1); }
+                    if (horizontal) { x1 = max(x - i, 0); x2 = min(x + i, in.w - 1); }
+                    else { y1 = max(y - i, 0); y2 = min(y + i, in.h - 1); }
                     res += vec2(in.at(x1, y1)[0], in.at(x1, y1)[1]) * weight[i];
                     res += vec2(in.at(x2, y2)[0], in.at(x2, y2)[1]) * weight[i];
                 }
@@ -236,7 +236,7 @@ void CloudScene::CheckerboardGen(const float* depth) {
             // textureGather at ((index+0.5)/half_size) = the 2x2 block (2x, 2y)
             float v0 = D(2 * x, 2 * y + 1), v1 = D(2 * x + 1, 2 * y + 1), v2 = D(2 * x + 1, 2 * y), v3 = D(2 * x, 2 * y);
             bool bmax = ((x & 1) == (y & 1));
-            float d = bmax ? std::max(std::max(v0, v1), std::max(v2, v3)) : std::min(std::min(v0, v1), std::min(v2, v3));
+            float d = bmax ? max(max(v0, v1), max(v2, v3)) : min(min(v0, v1), min(v2, v3));
             out.at(x, y)[0] = d;
         }
 }
@@ -381,13 +381,13 @@ void CloudScene::Render(int band_rows, int band_index, int band_count) {
             RayShellIntersect(r, mu, intersect);
             float frag_dist = distance(frag_pos, uCameraPos());
             for (int i = 0; i < 2; ++i)
-                intersect[i].t2 = clamp(std::min(frag_dist, b.uMaxVisibleDistance), intersect[i].t1, intersect[i].t2);
+                intersect[i].t2 = clamp(min(frag_dist, b.uMaxVisibleDistance), intersect[i].t1, intersect[i].t2);
 
             RayMarchContext ctx;
             ctx.cos_sun_view = dot(uSunDirection(), view_dir);
             float dist = intersect[0].t2 - intersect[0].t1;
-            dist = std::min(dist, b.uMaxRaymarchDistance);
-            uint num_steps = uint(std::max(b.uMaxRaymarchSteps * (dist / b.uMaxRaymarchDistance), 1.0f));
+            dist = min(dist, b.uMaxRaymarchDistance);
+            uint num_steps = uint(max(b.uMaxRaymarchSteps * (dist / b.uMaxRaymarchDistance), 1.0f));
             ctx.step_size = dist / float(num_steps);
             ctx.transmittance = 1.0f;
             ctx.transmittance_sum = 0.0f;
@@ -403,8 +403,8 @@ void CloudScene::Render(int band_rows, int band_index, int band_count) {
             }
             float dist1 = intersect[1].t2 - intersect[1].t1;
             if (dist1 > 0) {
-                dist1 = std::min(dist1, b.uMaxRaymarchDistance);
-                uint num_steps1 = uint(std::max(b.uMaxRaymarchSteps * (dist1 / b.uMaxRaymarchDistance), 1.0f));
+                dist1 = min(dist1, b.uMaxRaymarchDistance);
+                uint num_steps1 = uint(max(b.uMaxRaymarchSteps * (dist1 / b.uMaxRaymarchDistance), 1.0f));
                 ctx.step_size = dist1 / float(num_steps1);
                 ctx.t = intersect[1].t1 + ctx.step_size * fract(noise + c.uFrameID * 0.61803398875f);
                 for (uint cnt = num_steps1; cnt != 0; cnt--, ctx.t += ctx.step_size) {
@@ -427,7 +427,7 @@ void CloudScene::Render(int band_rows, int band_index, int band_count) {
             atmosphere_luminance *= SampleRayScatterVisibility(shadow_froxel, uv, average_t, c.uInvShadowFroxelMaxDistance);
             luminance = luminance * atmosphere_transmittance + atmosphere_luminance * (1 - ctx.transmittance);
 
-            luminance /= std::max(1e-5f, (1 - ctx.transmittance));
+            luminance /= max(1e-5f, (1 - ctx.transmittance));
             float fade = smoothstep(b.uMaxVisibleDistance * 0.75f, b.uMaxVisibleDistance, intersect[0].t1);
             ctx.transmittance = mix(ctx.transmittance, 1.0f, fade);
             luminance *= 1 - ctx.transmittance;
@@ -481,7 +481,7 @@ void CloudScene::Reconstruct() {
                 vec4 rendered = texel_fetch_clamp(render_texture, q + kOffsets[i]);
                 Reinhard(rendered);
                 if (delta_linear_depths[i] < rendered_linear_depths[i] * 0.3f ||
-                    std::fabs(rendered.w - rendered_nearest.w) / std::max(1e-6f, 1 - std::max(rendered.w, rendered_nearest.w)) < 0.2f) {
+                    std::fabs(rendered.w - rendered_nearest.w) / max(1e-6f, 1 - max(rendered.w, rendered_nearest.w)) < 0.2f) {
                     aabb_min = min(aabb_min, rendered);
                     aabb_max = max(aabb_max, rendered);
                 }
@@ -498,7 +498,7 @@ void CloudScene::Reconstruct() {
             Reinhard(pre_frame);
             pre_frame = clamp(pre_frame, aabb_min, aabb_max);
 
-            bool is_pre_out_of_screen = std::max(std::fabs(pre_ndc.x), std::fabs(pre_ndc.y)) > 1.0f;
+            bool is_pre_out_of_screen = max(std::fabs(pre_ndc.x), std::fabs(pre_ndc.y)) > 1.0f;
             int rendered_index = int(texel_fetch_clamp(index_linear_depth, q).x);
             bool is_rendered = (pos & 1) == IndexToOffset(uint(rendered_index));
             float rendered_weight = is_pre_out_of_screen ? 1.0f : is_rendered ? 0.2f : 0.0f;
@@ -537,11 +537,11 @@ void CloudScene::Upscale(const float* depth_img, uint16_t* hdr) {
                 if (delta_linear_depth > linear_depth * 0.1f) is_edge = true;
             }
             vec4 upscaled;
-            float max_a = std::max(std::max(reconstructed_neighbors[0].w, reconstructed_neighbors[1].w),
-                                   std::max(reconstructed_neighbors[2].w, reconstructed_neighbors[3].w));
-            float min_a = std::min(std::min(reconstructed_neighbors[0].w, reconstructed_neighbors[1].w),
-                                   std::min(reconstructed_neighbors[2].w, reconstructed_neighbors[3].w));
-            if (is_edge && (max_a - min_a) / std::max(1e-6f, 1 - min_a) > 0.2f) {
+            float max_a = max(max(reconstructed_neighbors[0].w, reconstructed_neighbors[1].w),
+                                   max(reconstructed_neighbors[2].w, reconstructed_neighbors[3].w));
+            float min_a = min(min(reconstructed_neighbors[0].w, reconstructed_neighbors[1].w),
+                                   min(reconstructed_neighbors[2].w, reconstructed_neighbors[3].w));
+            if (is_edge && (max_a - min_a) / max(1e-6f, 1 - min_a) > 0.2f) {
                 upscaled = reconstructed_neighbors[nearest_i];
             } else {
                 upscaled = ((reconstructed_neighbors[0] + reconstructed_neighbors[1]) +

@@ -79,8 +79,16 @@ inline bool operator==(ivec2 a, ivec2 b) { return a.x == b.x && a.y == b.y; }
 inline vec2 tovec2(ivec2 a) { return vec2(float(a.x), float(a.y)); }
 inline vec3 tovec3(ivec3 a) { return vec3(float(a.x), float(a.y), float(a.z)); }
 
-inline float clamp(float x, float lo, float hi) { return std::min(std::max(x, lo), hi); }
-inline int clamp(int x, int lo, int hi) { return std::min(std::max(x, lo), hi); }
+// GLSL leaves min/max/clamp of NaN undefined; GPUs implement them with the IEEE-754 minNum/maxNum
+// instruction (NVIDIA FMNMX), which returns the non-NaN operand.  The oracle does the same, so e.g.
+// clamp(0.0/0.0, 0, 1) == 0 exactly as in the shaders' RemapTo01 with remap_min == remap_max
+// (bin/config.json detail_.buffer.uPerlin).
+inline float max(float a, float b) { return std::fmax(a, b); }
+inline float min(float a, float b) { return std::fmin(a, b); }
+inline int max(int a, int b) { return a < b ? b : a; }
+inline int min(int a, int b) { return b < a ? b : a; }
+inline float clamp(float x, float lo, float hi) { return std::fmin(std::fmax(x, lo), hi); }
+inline int clamp(int x, int lo, int hi) { return min(max(x, lo), hi); }
 inline float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 inline float fract(float x) { return x - std::floor(x); }
 inline float radians(float d) { return d * 0.01745329251994329576923690768489f; }
@@ -98,8 +106,8 @@ inline float inversesqrt(float x) { return 1.0f / std::sqrt(x); }
     GLSL_MAP1(T, N, abs, std::fabs(v))                       \
     GLSL_MAP1(T, N, floor, std::floor(v))                    \
     GLSL_MAP1(T, N, fract, v - std::floor(v))                \
-    inline T min(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = std::min(a[i], b[i]); return r; } \
-    inline T max(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = std::max(a[i], b[i]); return r; } \
+    inline T min(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = std::fmin(a[i], b[i]); return r; } \
+    inline T max(T a, T b) { T r; for (int i = 0; i < N; ++i) r[i] = std::fmax(a[i], b[i]); return r; } \
     inline T clamp(T a, T lo, T hi) { return min(max(a, lo), hi); }                                    \
     inline T clamp(T a, float lo, float hi) { T r; for (int i = 0; i < N; ++i) r[i] = clamp(a[i], lo, hi); return r; } \
     inline T mix(T a, T b, float t) { return a * (1.0f - t) + b * t; }                                 \

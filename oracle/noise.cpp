@@ -70,7 +70,7 @@ float WorleyNoise2(vec2 p, uint freq, uint seed) {
             uint rnd0 = WangHash(seed + WangHash(sx + WangHash(sy)));
             uint rnd1 = WangHash(seed + WangHash(sx + WangHash(sy + 1)));
             vec2 g = vec2(float(gx), float(gy)) + vec2(float(rnd0), float(rnd1)) / 4294967296.0f;
-            min_dist = std::min(min_dist, distance(p, g));
+            min_dist = min(min_dist, distance(p, g));
         }
     return min_dist;
 }
@@ -90,7 +90,7 @@ float WorleyNoise3(vec3 p, uint freq, uint seed) {
                 uint rnd1 = WangHash(seed + WangHash(sx + WangHash(sy + WangHash(sz + 1))));
                 uint rnd2 = WangHash(seed + WangHash(sx + WangHash(sy + WangHash(sz + 2))));
                 vec3 g = vec3(float(gx), float(gy), float(gz)) + vec3(float(rnd0), float(rnd1), float(rnd2)) / 4294967296.0f;
-                min_dist = std::min(min_dist, distance(p, g));
+                min_dist = min(min_dist, distance(p, g));
             }
     return min_dist;
 }

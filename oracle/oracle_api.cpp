@@ -320,4 +320,27 @@ int orc_counters_enable(SkyContext* ctx, int enable) {
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
 int orc_tex_peak(SkyContext* ctx, int, double*) { return fail(ctx, "tex_peak is a GPU microbenchmark"); }
 
+// ---- test hooks (not part of skyb200.h): expose the leaf functions to the known-answer tests ------
+uint32_t orc_test_wang_hash(uint32_t x) { return WangHash(x); }
+uint32_t orc_test_pcg_hash(uint32_t x) { return PCGHash(x); }
+float orc_test_perlin(float x, float y, float z, uint32_t freq, uint32_t seed) { return PerlinNoise(vec3(x, y, z), freq, seed); }
+float orc_test_worley(float x, float y, float z, uint32_t freq, uint32_t seed) { return WorleyNoise3(vec3(x, y, z), freq, seed); }
+float orc_test_worley2(float x, float y, uint32_t freq, uint32_t seed) { return WorleyNoise2(vec2(x, y), freq, seed); }
+// R8 volume [d][h][w] sampled like the material textures (mag LINEAR, min NEAREST_MIPMAP_NEAREST)
+float orc_test_sample_r8(const uint8_t* texels, int w, int h, int d, float u, float v, float s, float lod, int wrap) {
+    MipTexture<1> t;
+    t.levels.resize(1);
+    t.levels[0].resize(w, h, d);
+    for (size_t i = 0; i < t.levels[0].data.size(); ++i) t.levels[0].data[i] = float(texels[i]) / 255.0f;
+    t.build_mips();
+    Sampler smp;
+    smp.wrap = Wrap(wrap);
+    return d > 1 ? t.texture_lod(vec3(u, v, s), lod, smp).x : t.texture_lod(vec2(u, v), lod, smp).x;
+}
+// density of the current material at a local-frame position (uses the uniforms of the last pass)
+float orc_test_sigma_t(SkyContext* ctx, float x, float y, float z) {
+    vec3 p(x, y, z);
+    return ctx->scene.SampleSigmaT(p, ctx->scene.CalHeight01(p), 7);
+}
+
 }  // extern "C"

@@ -65,10 +65,10 @@ struct Tracer {
         for (int i = 0; i < 3; ++i) {
             float t1 = (kCloudAABBMin[i] - ray.o[i]) / ray.d[i];
             float t2 = (kCloudAABBMax[i] - ray.o[i]) / ray.d[i];
-            float tmin = std::min(t1, t2);  // GLSL min/max: NaN handling is undefined; std::min keeps the first
-            float tmax = std::max(t1, t2);
-            t.x = std::max(t.x, tmin);
-            t.y = std::min(t.y, tmax);
+            float tmin = min(t1, t2);  // minNum/maxNum semantics, see glsl.h
+            float tmax = max(t1, t2);
+            t.x = max(t.x, tmin);
+            t.y = min(t.y, tmax);
         }
         return t;
     }
@@ -118,7 +118,7 @@ struct Tracer {
             t += InfiniteTransmittanceIS(ctx.sigma_t_max, Random01(ctx));
             if (t > inter_t.y) break;
             float sigma_t = SampleSigmaT(ray.o + ray.d * t);
-            transmittance *= 1.0f - std::max(0.0f, sigma_t / ctx.sigma_t_max);
+            transmittance *= 1.0f - max(0.0f, sigma_t / ctx.sigma_t_max);
             if (S.counting) S.counters[SKY_CNT_PT_COLLISIONS].fetch_add(1, std::memory_order_relaxed);
         }
         return clamp(transmittance, 0.0f, 1.0f);
@@ -159,7 +159,7 @@ struct Tracer {
 
         ctx.ray.o += camera_inter_t.x * ctx.ray.d;
         int istep = 0;
-        while (istep < P.max_bounces && std::max(throughput.x, std::max(throughput.y, throughput.z)) > 0.0f) {
+        while (istep < P.max_bounces && max(throughput.x, max(throughput.y, throughput.z)) > 0.0f) {
             vec2 inter_t = CloudRegionIntersect(ctx.ray);
             if (inter_t.x >= inter_t.y) break;
             float t_max = inter_t.y;
@@ -230,8 +230,8 @@ void CloudScene::PathTraceSamples(uint32_t frame_begin, uint32_t count, const in
     for (uint32_t f = 0; f < count; ++f) {
         const uint kFrameId = frame_begin + f;
 #pragma omp parallel for schedule(dynamic)
-        for (int py = region[1]; py < std::min(region[3], height); ++py)
-            for (int px = region[0]; px < std::min(region[2], width); ++px) {
+        for (int py = region[1]; py < min(region[3], height); ++py)
+            for (int px = region[0]; px < min(region[2], width); ++px) {
                 Context ctx;
                 ctx.seed = T.PRNG(T.PRNG(T.PRNG(uint(px)) + uint(py)) + kFrameId);
                 ctx.sigma_t_max = pt.sigma_t_max;

@@ -138,7 +138,7 @@ struct MipTexture {
             const Image<C>& src = levels.back();
             if (src.w == 1 && src.h == 1 && src.d == 1) break;
             Image<C> dst;
-            dst.resize(std::max(src.w / 2, 1), std::max(src.h / 2, 1), std::max(src.d / 2, 1));
+            dst.resize(max(src.w / 2, 1), max(src.h / 2, 1), max(src.d / 2, 1));
             float m = float((1u << bits) - 1u);
             for (int z = 0; z < dst.d; ++z)
                 for (int y = 0; y < dst.h; ++y)
@@ -149,8 +149,8 @@ struct MipTexture {
                             for (int dz = 0; dz < (src.d > 1 ? 2 : 1); ++dz)
                                 for (int dy = 0; dy < (src.h > 1 ? 2 : 1); ++dy)
                                     for (int dx = 0; dx < (src.w > 1 ? 2 : 1); ++dx) {
-                                        int sx = std::min(2 * x + dx, src.w - 1), sy = std::min(2 * y + dy, src.h - 1),
-                                            sz = std::min(2 * z + dz, src.d - 1);
+                                        int sx = min(2 * x + dx, src.w - 1), sy = min(2 * y + dy, src.h - 1),
+                                            sz = min(2 * z + dz, src.d - 1);
                                         sum += int(std::nearbyint(src.at(sx, sy, sz)[c] * m));
                                         ++n;
                                     }

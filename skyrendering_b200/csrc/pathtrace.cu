@@ -79,7 +79,7 @@ SKY_D void CreateOrthonormalBasis(float3 N, float3& t0, float3& t1) {  // shader
 }
 
 // :57-75.  IEEE division keeps the reference's inf/NaN behaviour for zero direction components;
-// fminf/fmaxf drop NaNs the way std::min/std::max(t, nan) do in the oracle for the second operand.
+// min/max are the hardware FMNMX (minNum/maxNum), which is what GLSL min/max compile to.
 SKY_D float2 CloudRegionIntersect(const PtParams& P, const Ray& ray) {
     const float hw = P.pt.region_box_half_width;
     const float bmin[3] = {-hw, -hw, P.c.uBottomAltitude}, bmax[3] = {hw, hw, P.c.uTopAltitude};
@@ -89,10 +89,10 @@ SKY_D float2 CloudRegionIntersect(const PtParams& P, const Ray& ray) {
     for (int i = 0; i < 3; ++i) {
         float t1 = (bmin[i] - o[i]) / d[i];
         float t2 = (bmax[i] - o[i]) / d[i];
-        float tmin = t2 < t1 ? t2 : t1;  // std::min(t1, t2)
-        float tmax = t1 < t2 ? t2 : t1;  // std::max(t1, t2)
-        t.x = t.x < tmin ? tmin : t.x;   // std::max(t.x, tmin)
-        t.y = tmax < t.y ? tmax : t.y;   // std::min(t.y, tmax)
+        float tmin = fminf(t1, t2);
+        float tmax = fmaxf(t1, t2);
+        t.x = fmaxf(t.x, tmin);
+        t.y = fminf(t.y, tmax);
     }
     return t;
 }
