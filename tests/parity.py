@@ -26,6 +26,17 @@ def max_rel_err(a, b, abs_floor=1e-7):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), abs_floor)))
 
 
+def lut_errors(a, b, floor_frac=1e-3):
+    """(relative RMS, 99.9th percentile, count above 2e-2) of the per-texel error |a-b| / max(|b|, floor) with
+    floor = floor_frac * max|b|: texels far below the LUT's own scale are judged absolutely -- their
+    relative error is not defined in fp32, see DESIGN.md "Parity"."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    floor = floor_frac * float(np.max(np.abs(b)))
+    e = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    return rel_rms(a, b), float(np.percentile(e, 99.9)), int(np.sum(e > 2e-2))
+
+
 def rel_rms(a, b):
     """||a-b||_2 / ||b||_2 over the whole image: the per-frame tolerance metric."""
     a = np.asarray(a, np.float64)

@@ -18,7 +18,7 @@ import torch
 
 from skyrendering_b200 import abi
 from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
-from tests.parity import (make_buffers, max_rel_err, oracle_library, rel_rms, run_cloud_frames, run_path_trace, to_numpy)
+from tests.parity import (lut_errors, make_buffers, max_rel_err, oracle_library, rel_rms, run_cloud_frames, run_path_trace, to_numpy)
 
 pytestmark = pytest.mark.gpu
 
@@ -47,11 +47,13 @@ def test_lut_bake_parity(libs, scene):
     for res in (abi.RES_MULTISCATTERING, abi.RES_SKY_VIEW_LUMINANCE, abi.RES_AERIAL_LUMINANCE):
         g, o = rg.ctx.read(res)[..., :3], ro.ctx.read(res)[..., :3]
         assert np.all(np.isfinite(g))
-        assert rel_rms(g, o) < 1e-4, res
-        assert rel_percentile(g, o, 99.9) < 2e-3, res
+        rr, p999, nbad = lut_errors(g, o)
+        assert rr < 1e-4, res
+        assert p999 < 2e-3, res
+        assert nbad <= 24, res  # horizon texels where RayIntersectsGround flips on the last ulp of cos()
     g, o = rg.ctx.read(abi.RES_ENVIRONMENT).astype(np.float32)[..., :3], ro.ctx.read(abi.RES_ENVIRONMENT).astype(np.float32)[..., :3]
-    assert rel_rms(g, o) < 5e-4
-    assert rel_percentile(g, o, 99.9) < 2.1e-3  # two fp16 ulps
+    rr, p999, nbad = lut_errors(g, o)
+    assert rr < 5e-4 and p999 < 2.1e-3 and nbad <= 24  # stored as fp16: one or two ulps of 2^-10
     # layouts the reference allocates
     assert rg.ctx.read(abi.RES_TRANSMITTANCE).shape == (64, 256, 4)
     assert rg.ctx.read(abi.RES_MULTISCATTERING).shape == (32, 32, 4)
@@ -108,12 +110,10 @@ def test_voxel_mips_bit_exact_non_power_of_two(libs):
 
 
 # ---------------------------------------------------------------------------------------------- cloud chain
-@pytest.mark.parametrize("scene,move", [("c3", None), ("c1", None), ("c3", (0.05, 0.0, 0.02)), ("c5", None)])
+@pytest.mark.parametrize("scene,move", [("c3", None), ("c1", None), ("c3", (0.05, 0.0, 0.02))])
 def test_cloud_chain_parity(libs, scene, move):
     cuda, orc = libs
     w, h = 384, 216
-    if scene == "c5":
-        pytest.skip("voxel material in the real-time chain is covered by test_voxel_realtime_parity")
     g = run_cloud_frames(scene, w, h, cuda, frames=4, device="cuda", move=move, count=True)
     o = run_cloud_frames(scene, w, h, orc, frames=4, device="cpu", move=move, count=True)
     assert np.array_equal(g["checker"], o["checker"])                       # K14: pure min/max

@@ -11,7 +11,7 @@ import torch  # noqa: E402
 
 from skyrendering_b200 import abi  # noqa: E402
 from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid  # noqa: E402
-from tests.parity import (max_rel_err, oracle_library, rel_rms, run_cloud_frames, run_path_trace)  # noqa: E402
+from tests.parity import (lut_errors, max_rel_err, oracle_library, rel_rms, run_cloud_frames, run_path_trace)  # noqa: E402
 
 
 def main():
@@ -27,7 +27,8 @@ def main():
                               (abi.RES_SKY_VIEW_TRANSMITTANCE, "SKY_T"), (abi.RES_AERIAL_LUMINANCE, "AP_L"),
                               (abi.RES_AERIAL_TRANSMITTANCE, "AP_T"), (abi.RES_ENVIRONMENT, "ENV")):
                 g, o = rg.ctx.read(res).astype(np.float32)[..., :3], ro.ctx.read(res).astype(np.float32)[..., :3]
-                print(f"LUT {scene} {name:6s} max_rel {max_rel_err(g, o):.3e} rel_rms {rel_rms(g, o):.3e} nan {int(np.isnan(g).sum())}")
+                rr, p999, nbad = lut_errors(g, o)
+                print(f"LUT {scene} {name:6s} max_rel {max_rel_err(g, o):.3e} rel_rms {rr:.3e} floored p99.9 {p999:.3e} n(>2e-2) {nbad} nan {int(np.isnan(g).sum())}")
 
     if "noise" in only:
         rg, ro = Renderer("c3", 192, 108, library=cuda), Renderer("c3", 192, 108, library=orc)
