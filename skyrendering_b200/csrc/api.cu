@@ -26,6 +26,7 @@ void free_mip(MipTextureDev& t) {
     if (t.view.tex_point) cudaDestroyTextureObject(t.view.tex_point);
     if (t.array) cudaFreeMipmappedArray(t.array);
     if (t.data) cudaFree(t.data);
+    if (t.cells) cudaFree(t.cells);
     t = MipTextureDev{};
 }
 
@@ -152,6 +153,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->stage_depth) cudaFree(ctx->stage_depth);
     if (ctx->stage_hdr) cudaFree(ctx->stage_hdr);
+    if (ctx->pt_samples) cudaFree(ctx->pt_samples);
+    if (ctx->pt_job_counter) cudaFree(ctx->pt_job_counter);
     delete ctx;
 }
 

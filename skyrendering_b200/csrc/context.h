@@ -18,12 +18,21 @@ struct MipView {
     int channels;
     cudaTextureObject_t tex_linear;  // LINEAR, level 0 (magnification)
     cudaTextureObject_t tex_point;   // POINT over the mip chain (NEAREST_MIPMAP_NEAREST)
+    // Corner-packed copy of level 0 for the exact LINEAR path: cell (i,j[,k]) holds the 4 (2-D) or 8 (3-D)
+    // texels a bilinear / trilinear tap at base texel (i,j,k) needs, wrap or border already applied, so
+    // one aligned 8- or 16-byte load replaces 4-8 scattered byte loads.  HBM is cheap on this part
+    // (8x the level-0 bytes), load slots are not.  REPEAT: cell_w = w; BORDER: cell_w = w + 1 and cell
+    // index = base texel + 1 (base texel -1 .. w-1).
+    const void* cells;
+    int cell_w, cell_h, cell_d;
 };
 
 struct MipTextureDev {
     MipView view{};
     uint8_t* data = nullptr;
     size_t bytes = 0;
+    void* cells = nullptr;  // corner-packed level 0, see MipView
+    size_t cell_bytes = 0;
     cudaMipmappedArray_t array = nullptr;
     bool is3d = false;
     bool border = false;  // CLAMP_TO_BORDER(0) instead of REPEAT
@@ -73,6 +82,9 @@ struct SkyContext {
     // path tracer
     Lut<float4> pt_accum;
     Lut<uint8_t> pt_mask;
+    void* pt_samples = nullptr;           // per-job sample slots of K19, float4[frames][region pixels]
+    size_t pt_samples_bytes = 0;
+    unsigned int* pt_job_counter = nullptr;
 
     unsigned long long* counters = nullptr;  // SkyCounter slots
 

@@ -42,6 +42,8 @@ SKY_D void load_texel(const MipView& t, int level, int x, int y, int z, float* o
     }
 }
 
+SKY_D float byte_of(uint32_t word, int n) { return float((word >> (8 * n)) & 0xffu) * (1.0f / 255.0f); }
+
 template <int C>
 SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, float lod, float* out) {
     int level = select_mip_level(lod, t.levels);
@@ -51,13 +53,19 @@ SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, float lod, 
         float fx = floorf(x), fy = floorf(y);
         float a = x - fx, b = y - fy;
         int i0 = int(fx) & (w - 1), j0 = int(fy) & (h - 1);
-        int i1 = (i0 + 1) & (w - 1), j1 = (j0 + 1) & (h - 1);
-        float t00[C], t10[C], t01[C], t11[C];
-        load_texel<C>(t, 0, i0, j0, 0, t00); load_texel<C>(t, 0, i1, j0, 0, t10);
-        load_texel<C>(t, 0, i0, j1, 0, t01); load_texel<C>(t, 0, i1, j1, 0, t11);
         float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+        // one load brings the four corners: C == 2 -> 8 bytes {c00 c10 c01 c11} x {r,g}; C == 4 -> 16 bytes
+        if (C == 2) {
+            uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + size_t(j0) * w + i0);
 #pragma unroll
-        for (int c = 0; c < C; ++c) out[c] = w00 * t00[c] + w10 * t10[c] + w01 * t01[c] + w11 * t11[c];
+            for (int c = 0; c < 2; ++c)
+                out[c] = w00 * byte_of(cell.x, c) + w10 * byte_of(cell.x, 2 + c) + w01 * byte_of(cell.y, c) + w11 * byte_of(cell.y, 2 + c);
+        } else {
+            uint4 cell = __ldg(reinterpret_cast<const uint4*>(t.cells) + size_t(j0) * w + i0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                out[c] = w00 * byte_of(cell.x, c) + w10 * byte_of(cell.y, c) + w01 * byte_of(cell.z, c) + w11 * byte_of(cell.w, c);
+        }
     } else {
         int w = t.w[level], h = t.h[level];
         int i = int(floorf(u * float(w))) & (w - 1), j = int(floorf(v * float(h))) & (h - 1);
@@ -73,10 +81,9 @@ SKY_D float sample3d_repeat_exact(const MipView& t, float u, float v, float w_, 
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
         float fx = floorf(x), fy = floorf(y), fz = floorf(z);
         float a = x - fx, b = y - fy, c = z - fz;
-        int i[2], j[2], k[2];
-        i[0] = int(fx) & (w - 1); i[1] = (i[0] + 1) & (w - 1);
-        j[0] = int(fy) & (h - 1); j[1] = (j[0] + 1) & (h - 1);
-        k[0] = int(fz) & (d - 1); k[1] = (k[0] + 1) & (d - 1);
+        int i0 = int(fx) & (w - 1), j0 = int(fy) & (h - 1), k0 = int(fz) & (d - 1);
+        // 8 corners in one 8-byte load: byte n = di + 2*dj + 4*dk
+        uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(k0) * h + j0) * w + i0);
         float r = 0.0f;
 #pragma unroll
         for (int dk = 0; dk < 2; ++dk)
@@ -85,9 +92,7 @@ SKY_D float sample3d_repeat_exact(const MipView& t, float u, float v, float w_, 
 #pragma unroll
                 for (int di = 0; di < 2; ++di) {
                     float wt = (di ? a : 1.0f - a) * (dj ? b : 1.0f - b) * (dk ? c : 1.0f - c);
-                    float tx;
-                    load_texel<1>(t, 0, i[di], j[dj], k[dk], &tx);
-                    r += wt * tx;
+                    r += wt * byte_of(dk ? cell.y : cell.x, di + 2 * dj);
                 }
         out = r;
     } else {
@@ -106,7 +111,10 @@ SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, 
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
         float fx = floorf(x), fy = floorf(y), fz = floorf(z);
         float a = x - fx, b = y - fy, c = z - fz;
-        int i0 = int(fx), j0 = int(fy), k0 = int(fz);
+        // cell index = base texel + 1; outside [0, w] x [0, h] x [0, d] every corner is the border
+        float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
+        if (!(cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d))) return 0.0f;
+        uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(int(cz)) * t.cell_h + int(cy)) * t.cell_w + int(cx));
         float r = 0.0f;
 #pragma unroll
         for (int dk = 0; dk < 2; ++dk)
@@ -115,10 +123,7 @@ SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, 
 #pragma unroll
                 for (int di = 0; di < 2; ++di) {
                     float wt = (di ? a : 1.0f - a) * (dj ? b : 1.0f - b) * (dk ? c : 1.0f - c);
-                    int xi = i0 + di, yj = j0 + dj, zk = k0 + dk;
-                    float tx = 0.0f;
-                    if (xi >= 0 && xi < w && yj >= 0 && yj < h && zk >= 0 && zk < d) load_texel<1>(t, 0, xi, yj, zk, &tx);
-                    r += wt * tx;
+                    r += wt * byte_of(dk ? cell.y : cell.x, di + 2 * dj);
                 }
         return r;
     }

@@ -174,6 +174,36 @@ __global__ void __launch_bounds__(256) k_mip_level(const __grid_constant__ MipPa
     P.dst[idx] = uint8_t((2 * sum + n) / (2 * n));
 }
 
+// Corner packing of level 0 (see MipView::cells).  One thread per cell.
+struct PackParams {
+    const uint8_t* src;
+    uint8_t* dst;
+    int w, h, d, channels, border, cw, ch, cd;
+};
+__global__ void __launch_bounds__(256) k_pack_cells(const __grid_constant__ PackParams P) {
+    size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    size_t total = size_t(P.cw) * P.ch * P.cd;
+    if (idx >= total) return;
+    int ci = int(idx % P.cw);
+    size_t t = idx / P.cw;
+    int cj = int(t % P.ch), ck = int(t / P.ch);
+    const bool is3d = P.d > 1;
+    const int corners = is3d ? 8 : 4;
+    uint8_t* out = P.dst + idx * size_t(corners) * P.channels;
+    for (int n = 0; n < corners; ++n) {
+        int x = ci + (n & 1), y = cj + ((n >> 1) & 1), z = ck + ((n >> 2) & 1);
+        bool inside = true;
+        if (P.border) {
+            x -= 1; y -= 1; if (is3d) z -= 1;  // cell index = base texel + 1
+            inside = x >= 0 && x < P.w && y >= 0 && y < P.h && z >= 0 && z < P.d;
+        } else {
+            x %= P.w; y %= P.h; z %= P.d;
+        }
+        for (int c = 0; c < P.channels; ++c)
+            out[n * P.channels + c] = inside ? P.src[((size_t(z) * P.h + y) * P.w + x) * P.channels + c] : uint8_t(0);
+    }
+}
+
 }  // namespace
 
 int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, int channels, bool border) {
@@ -182,6 +212,7 @@ int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, in
     if (t.view.tex_point) cudaDestroyTextureObject(t.view.tex_point);
     if (t.array) cudaFreeMipmappedArray(t.array);
     if (t.data) cudaFree(t.data);
+    if (t.cells) cudaFree(t.cells);
     t = MipTextureDev{};
     t.is3d = d > 1;
     t.border = border;
@@ -200,6 +231,12 @@ int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, in
     t.bytes = off * channels;
     SKY_CUDA(ctx, cudaMalloc(&t.data, t.bytes));
     v.base = t.data;
+    v.cell_w = border ? w + 1 : w;
+    v.cell_h = border ? h + 1 : h;
+    v.cell_d = t.is3d ? (border ? d + 1 : d) : 1;
+    t.cell_bytes = size_t(v.cell_w) * v.cell_h * v.cell_d * (t.is3d ? 8 : 4) * channels;
+    SKY_CUDA(ctx, cudaMalloc(&t.cells, t.cell_bytes));
+    v.cells = t.cells;
 
     cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, channels >= 2 ? 8 : 0, channels >= 3 ? 8 : 0, channels >= 4 ? 8 : 0,
                                                        cudaChannelFormatKindUnsigned);
@@ -227,6 +264,12 @@ int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, in
 // level 0 is in t.data already: build levels 1.. and mirror every level into the CUDA array
 int launch_mip_chain(SkyContext* ctx, MipTextureDev& t) {
     MipView& v = t.view;
+    {
+        PackParams P{t.data, static_cast<uint8_t*>(t.cells), v.w[0], v.h[0], v.d[0], v.channels, t.border ? 1 : 0, v.cell_w, v.cell_h, v.cell_d};
+        size_t total = size_t(v.cell_w) * v.cell_h * v.cell_d;
+        k_pack_cells<<<unsigned((total + 255) / 256), 256, 0, ctx->stream>>>(P);
+        SKY_LAUNCH_CHECK(ctx);
+    }
     for (int l = 1; l < v.levels; ++l) {
         MipParams P{t.data + v.off[l - 1] * v.channels, t.data + v.off[l] * v.channels,
                     v.w[l - 1], v.h[l - 1], v.d[l - 1], v.w[l], v.h[l], v.d[l], v.channels};

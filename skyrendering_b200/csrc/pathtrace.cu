@@ -8,6 +8,17 @@
 // liberty taken is exact: tentative collisions that provably land on zero density (outside the voxel
 // footprint, where CLAMP_TO_BORDER returns 0 at every mip level) skip the texture fetch but still
 // consume their random numbers.
+//
+// Execution model (why this is not the shader's loop nest).  A path is ~5e3 tentative collisions, with
+// the count varying by 1000x between neighbouring pixels, split between the free-flight loop (:182-196)
+// and the shadow-ray loop (:142-149) of up to 128 bounces.  Run as written, lanes of a warp sit in
+// different loops and ncu shows 2 of 32 lanes active.  Here every lane is a small state machine inside ONE
+// loop whose hot block -- a single tentative collision, shared by free-flight and shadow tracking --
+// is executed convergently by all tracking lanes; the rare transitions (scatter, shadow end, ground
+// hit, path end) are side blocks.  Lanes are persistent and pull (pixel, frame) jobs from a global
+// counter, so a finished path never idles its lane.  Each job writes its sample to its own slot and
+// a second kernel adds the slots to the RGBA32F accumulator in kFrameId order, which keeps the
+// reference's order of fp32 additions and makes the result independent of scheduling.
 #include "atmosphere_dev.cuh"
 #include "context.h"
 #include "material_dev.cuh"
@@ -26,6 +37,8 @@ struct PtParams {
     float4* accum;
     uint8_t* mask;
     half4* hdr;
+    float4* samples;             // [frame_count][region pixels]
+    unsigned int* job_counter;
     unsigned long long* counters;
     int width, height;
     int x0, y0, x1, y1;  // kRenderRegion
@@ -48,11 +61,9 @@ SKY_D uint32_t PCGHash(uint32_t seed) {  // shaders/Base/Noise.glsl:11-15
 template <int PRNG_KIND>
 SKY_D uint32_t PRNG(uint32_t x) { return PRNG_KIND == SKY_PRNG_WANG ? WangHash(x) : PCGHash(x); }
 
-struct Ray { float3 o, d; };
-
 template <int PRNG_KIND>
 SKY_D float Random01(uint32_t& seed) {  // :44-48 (returns, then advances; can round to 1.0)
-    float res = float(seed) / 4294967296.0f;
+    float res = float(seed) * (1.0f / 4294967296.0f);  // exact: power-of-two scale
     seed = PRNG<PRNG_KIND>(seed);
     return res;
 }
@@ -80,10 +91,10 @@ SKY_D void CreateOrthonormalBasis(float3 N, float3& t0, float3& t1) {  // shader
 
 // :57-75.  IEEE division keeps the reference's inf/NaN behaviour for zero direction components;
 // min/max are the hardware FMNMX (minNum/maxNum), which is what GLSL min/max compile to.
-SKY_D float2 CloudRegionIntersect(const PtParams& P, const Ray& ray) {
+SKY_D float2 CloudRegionIntersect(const PtParams& P, float3 ro, float3 rd) {
     const float hw = P.pt.region_box_half_width;
     const float bmin[3] = {-hw, -hw, P.c.uBottomAltitude}, bmax[3] = {hw, hw, P.c.uTopAltitude};
-    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
+    const float o[3] = {ro.x, ro.y, ro.z}, d[3] = {rd.x, rd.y, rd.z};
     float2 t = f2(0.0f, 1e7f);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -96,8 +107,6 @@ SKY_D float2 CloudRegionIntersect(const PtParams& P, const Ray& ray) {
     }
     return t;
 }
-
-SKY_D float InfiniteTransmittanceIS(float sigma_t, float zeta) { return -logf(1.0f - zeta) / sigma_t; }  // :82-84
 
 template <int MAT, bool HW, bool COUNT>
 SKY_D float SampleSigmaTAt(const PtParams& P, float3 pos, int& lookups) {  // :89-91
@@ -146,170 +155,264 @@ SKY_D float3 GetSunIlluminance(const PtParams& P, float3 pos) {  // :131-133 + V
     return P.atm.GetSunVisibility(P.transmittance, r, mu_s) * P.atm.solar_illuminance();
 }
 
-// :135-151; `seed` is a COPY of the path's stream
-template <int MAT, bool HW, int PRNG_KIND, bool COUNT>
-SKY_D float TransmittanceEstimation(const PtParams& P, uint32_t seed, const Ray& ray, int& lookups, int& collisions) {
-    float transmittance = 1.0f;
-    float2 inter_t = CloudRegionIntersect(P, ray);
-    if (inter_t.x >= inter_t.y) return transmittance;
-    const float sigma_t_max = P.pt.sigma_t_max;
-    float t = inter_t.x;
-    while (true) {
-        t += InfiniteTransmittanceIS(sigma_t_max, Random01<PRNG_KIND>(seed));
-        if (t > inter_t.y) break;
-        float sigma_t = SampleSigmaTAt<MAT, HW, COUNT>(P, ray.o + ray.d * t, lookups);
-        transmittance *= 1.0f - fmaxf(0.0f, sigma_t / sigma_t_max);
-        if (COUNT) ++collisions;
-    }
-    return clampf(transmittance, 0.0f, 1.0f);
-}
+// lane states
+enum : int {
+    ST_FETCH = 0,     // needs a (pixel, frame) job
+    ST_SEGMENT,       // top of `while (istep < kMaxBounces && throughput > 0)`, :172
+    ST_TRACK,         // inside a tracking loop (free flight :182-196 or shadow ray :142-149)
+    ST_EXIT_PRIMARY,  // free flight left the box without a collision, :198-230
+    ST_SCATTER,       // real collision, :231-243
+    ST_SHADOW_END,    // shadow ray finished: add the light sample, then sample the next direction
+    ST_FINISH,        // path complete: aerial perspective, write the sample
+    ST_IDLE           // no jobs left
+};
 
+// K19 -- :160-284 as a per-lane state machine; see the header of this file.
 template <int MAT, bool HW, int PRNG_KIND, bool COUNT>
-SKY_D float3 SampleLuminanceFromLight(const PtParams& P, uint32_t seed, float3 pos, float3 bsdf_with_cosine, int& lookups, int& collisions) {  // :153-158
-    float3 light_luminance = GetSunIlluminance(P, pos);
-    Ray ray{pos, f3(P.c.uSunDirection)};
-    return TransmittanceEstimation<MAT, HW, PRNG_KIND, COUNT>(P, seed, ray, lookups, collisions) * light_luminance * bsdf_with_cosine;
-}
-
-// :160-249
-template <int MAT, bool HW, int PRNG_KIND, bool COUNT>
-SKY_D float4 Trace(const PtParams& P, uint32_t& seed, float3 view_dir, bool& has_scattered, float& scattered_t, int& lookups, int& collisions) {
-    float3 L = f3(0.0f);
-    float3 throughput = f3(1.0f);
-    has_scattered = false;
+__global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__ PtParams P) {
+    const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
+    const int tiles_x = (rw + 7) >> 3, tiles_y = (rh + 3) >> 2;  // jobs walk the region in 8x4 pixel tiles so a warp starts on one tile
+    const unsigned int npix = (unsigned int)rw * (unsigned int)rh;                  // sample-slot stride per frame
+    const unsigned int npix_padded = (unsigned int)tiles_x * (unsigned int)tiles_y * 32u;  // job stride per frame
+    const unsigned int njobs = npix_padded * P.frame_count;
     const float3 camera = f3(P.c.uCameraPos);
     const float3 sun = f3(P.c.uSunDirection);
     const float sigma_t_max = P.pt.sigma_t_max;
-    Ray ray{camera, view_dir};
-    float2 camera_inter_t = CloudRegionIntersect(P, ray);
-    if (camera_inter_t.x >= camera_inter_t.y) return f4(L, throughput.x);
+    const unsigned int lane = threadIdx.x & 31u;
 
-    ray.o += camera_inter_t.x * ray.d;
+    int state = ST_FETCH;
+    unsigned int job = 0;
+    int px = 0, py = 0;
+    uint32_t seed = 0, saved_seed = 0;
+    float3 ro = f3(0.0f), rd = f3(0.0f, 0.0f, 1.0f);  // ctx.ray
+    float3 L = f3(0.0f), throughput = f3(1.0f), light = f3(0.0f), bsdf = f3(0.0f);
+    float t = 0.0f, t_max = 0.0f, transmittance = 1.0f, scattered_t = 0.0f;
     int istep = 0;
-    while (istep < P.pt.max_bounces && fmaxf(throughput.x, fmaxf(throughput.y, throughput.z)) > 0.0f) {
-        float2 inter_t = CloudRegionIntersect(P, ray);
-        if (inter_t.x >= inter_t.y) break;
-        float t_max = inter_t.y;
-        float t = inter_t.x;
-        bool event_scatter = false;
-        while (true) {
-            if (sigma_t_max <= 0) break;
-            t += InfiniteTransmittanceIS(sigma_t_max, Random01<PRNG_KIND>(seed));
-            if (t > t_max) break;
-            float3 Pp = ray.o + ray.d * t;
-            float sigma_t = SampleSigmaTAt<MAT, HW, COUNT>(P, Pp, lookups);
-            if (COUNT) ++collisions;
-            float xi = Random01<PRNG_KIND>(seed);
-            if (xi < sigma_t / sigma_t_max) { event_scatter = true; break; }
+    bool has_scattered = false, in_shadow = false, after_ground = false;
+    int lookups = 0, collisions = 0, paths = 0;
+
+    for (;;) {
+        // ---------------------------------------------------------------- job fetch (warp-aggregated)
+        {
+            unsigned int need = __ballot_sync(0xffffffffu, state == ST_FETCH);
+            if (need) {
+                unsigned int base = 0;
+                int leader = __ffs(need) - 1;
+                if (lane == (unsigned int)leader) base = atomicAdd(P.job_counter, (unsigned int)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (state == ST_FETCH) {
+                    job = base + __popc(need & ((1u << lane) - 1u));
+                    if (job >= njobs) {
+                        state = ST_IDLE;
+                    } else {
+                        unsigned int frame_index = job / npix_padded, p = job - frame_index * npix_padded;
+                        // 8x4 tile order inside the region
+                        unsigned int tile = p >> 5, in_tile = p & 31u;
+                        int tx = int(tile % (unsigned int)tiles_x), ty = int(tile / (unsigned int)tiles_x);
+                        px = P.x0 + tx * 8 + int(in_tile & 7u);
+                        py = P.y0 + ty * 4 + int(in_tile >> 3);
+                        if (px >= P.x1 || py >= P.y1) {
+                            state = ST_FETCH;  // padding of the tile grid: take another job next round
+                        } else {
+                            seed = PRNG<PRNG_KIND>(PRNG<PRNG_KIND>(PRNG<PRNG_KIND>(uint32_t(px)) + uint32_t(py)) + (P.frame_begin + frame_index));  // :260
+                            float2 uv = f2((float(px) + 0.5f) / float(P.width), (float(py) + 0.5f) / float(P.height));
+                            float3 frag_pos = projective_mul(P.c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 1.0f));
+                            rd = normalize(frag_pos - camera);
+                            ro = camera;
+                            L = f3(0.0f); throughput = f3(1.0f);
+                            has_scattered = false; in_shadow = false; istep = 0; scattered_t = 0.0f;
+                            if (COUNT) ++paths;
+                            float2 camera_inter_t = CloudRegionIntersect(P, ro, rd);  // :166-170
+                            if (camera_inter_t.x >= camera_inter_t.y) {
+                                state = ST_FINISH;
+                            } else {
+                                ro += camera_inter_t.x * rd;
+                                state = ST_SEGMENT;
+                            }
+                        }
+                    }
+                }
+            }
         }
-        if (!event_scatter) {
-            if (P.pt.environment_lighting == SKY_ENV_OFF) break;
-            if (!has_scattered) break;
-            const float* mm = P.pt.model_matrix3;
-            float3 world_dir = f3(mm[0] * ray.d.x + mm[3] * ray.d.y + mm[6] * ray.d.z, mm[1] * ray.d.x + mm[4] * ray.d.y + mm[7] * ray.d.z,
-                                  mm[2] * ray.d.x + mm[5] * ray.d.y + mm[8] * ray.d.z);
-            if (P.pt.environment_lighting == SKY_ENV_CONST_ENVIRONMENT_MAP) {
-                L += throughput * SampleEnvironment(P, world_dir);
-                break;
+        if (__all_sync(0xffffffffu, state == ST_IDLE)) break;
+
+        // ---------------------------------------------------------------- :172-181
+        if (state == ST_SEGMENT) {
+            if (!(istep < P.pt.max_bounces && fmaxf(throughput.x, fmaxf(throughput.y, throughput.z)) > 0.0f)) {
+                state = ST_FINISH;
+            } else {
+                float2 inter_t = CloudRegionIntersect(P, ro, rd);
+                if (inter_t.x >= inter_t.y) {
+                    state = ST_FINISH;
+                } else {
+                    t = inter_t.x; t_max = inter_t.y;
+                    in_shadow = false;
+                    state = sigma_t_max <= 0 ? ST_EXIT_PRIMARY : ST_TRACK;  // :183
+                }
             }
-            float3 up_dir = f3(ray.o.x, ray.o.y, ray.o.z + P.c.uEarthRadius);
-            float r = length(up_dir);
-            up_dir /= r;
-            float mu = dot(ray.d, up_dir);
-            if (!P.atm.RayIntersectsGround(r, mu)) {
-                L += throughput * SampleEnvironment(P, world_dir);
-                break;
+        }
+
+        // ---------------------------------------------------------------- hot block: one tentative collision
+        if (state == ST_TRACK) {
+            const float3 dir = in_shadow ? sun : rd;
+            t += -logf(1.0f - Random01<PRNG_KIND>(seed)) / sigma_t_max;  // InfiniteTransmittanceIS, :82-84
+            if (t > t_max) {
+                state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
+            } else {
+                float sigma_t = SampleSigmaTAt<MAT, HW, COUNT>(P, ro + dir * t, lookups);
+                if (COUNT) ++collisions;
+                if (in_shadow) {
+                    transmittance *= 1.0f - fmaxf(0.0f, sigma_t / sigma_t_max);  // :148
+                } else {
+                    float xi = Random01<PRNG_KIND>(seed);
+                    if (xi < sigma_t / sigma_t_max) state = ST_SCATTER;  // :191-195
+                }
             }
-            ray.o += ray.d * P.atm.DistanceToBottomAtmosphereBoundary(r, mu);
-            float3 ground_normal = normalize(f3(ray.o.x, ray.o.y, ray.o.z + P.c.uEarthRadius));
-            float3 light_bsdf = kInvPi * P.atm.ground_albedo();
-            float NdotL = dot(ground_normal, sun);
-            L += throughput * SampleLuminanceFromLight<MAT, HW, PRNG_KIND, COUNT>(P, seed, ray.o, light_bsdf * NdotL, lookups, collisions);
-            if (P.pt.environment_lighting == SKY_ENV_GROUND_SINGLE_BOUNCE) break;
-            // GenerateLambertSample, :119-129
-            float sin_theta = sqrtf(Random01<PRNG_KIND>(seed));
-            float cos_theta = sqrtf(clampf(1.0f - sin_theta * sin_theta, 0.0f, 1.0f));
-            float3 t0, t1;
-            CreateOrthonormalBasis(ground_normal, t0, t1);
-            float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
-            ray.d = sin_theta * sinf(phi) * t0 + sin_theta * cosf(phi) * t1 + cos_theta * ground_normal;
-            throughput *= P.atm.ground_albedo();
-        } else {
-            if (!has_scattered) scattered_t = distance(camera, ray.o);
+        }
+
+        // ---------------------------------------------------------------- :198-230
+        if (state == ST_EXIT_PRIMARY) {
+            state = ST_FINISH;
+            if (P.pt.environment_lighting != SKY_ENV_OFF && has_scattered) {
+                const float* mm = P.pt.model_matrix3;
+                float3 world_dir = f3(mm[0] * rd.x + mm[3] * rd.y + mm[6] * rd.z, mm[1] * rd.x + mm[4] * rd.y + mm[7] * rd.z,
+                                      mm[2] * rd.x + mm[5] * rd.y + mm[8] * rd.z);
+                if (P.pt.environment_lighting == SKY_ENV_CONST_ENVIRONMENT_MAP) {
+                    L += throughput * SampleEnvironment(P, world_dir);
+                } else {
+                    float3 up_dir = f3(ro.x, ro.y, ro.z + P.c.uEarthRadius);
+                    float r = length(up_dir);
+                    up_dir /= r;
+                    float mu = dot(rd, up_dir);
+                    if (!P.atm.RayIntersectsGround(r, mu)) {
+                        L += throughput * SampleEnvironment(P, world_dir);
+                    } else {
+                        ro += rd * P.atm.DistanceToBottomAtmosphereBoundary(r, mu);
+                        float3 ground_normal = normalize(f3(ro.x, ro.y, ro.z + P.c.uEarthRadius));
+                        float NdotL = dot(ground_normal, sun);
+                        light = GetSunIlluminance(P, ro);                     // :131-133
+                        bsdf = (kInvPi * P.atm.ground_albedo()) * NdotL;       // :220-222
+                        after_ground = true;
+                        // TransmittanceEstimation(ctx BY VALUE, ray(pos, sun)), :135-141
+                        saved_seed = seed;
+                        transmittance = 1.0f;
+                        float2 st = CloudRegionIntersect(P, ro, sun);
+                        if (st.x >= st.y) {
+                            state = ST_SHADOW_END;
+                        } else {
+                            t = st.x; t_max = st.y; in_shadow = true;
+                            state = ST_TRACK;
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---------------------------------------------------------------- :231-238
+        if (state == ST_SCATTER) {
+            if (!has_scattered) scattered_t = distance(camera, ro);
             has_scattered = true;
-            ray.o += ray.d * t;
-            float light_bsdf = GetPhase(P, dot(ray.d, sun));
-            L += throughput * SampleLuminanceFromLight<MAT, HW, PRNG_KIND, COUNT>(P, seed, ray.o, f3(light_bsdf), lookups, collisions);
-            // GenerateHGSample, :98-117
-            if (P.pt.importance_sampling) {
+            ro += rd * t;
+            light = GetSunIlluminance(P, ro);
+            bsdf = f3(GetPhase(P, dot(rd, sun)));  // :237
+            after_ground = false;
+            saved_seed = seed;
+            transmittance = 1.0f;
+            float2 st = CloudRegionIntersect(P, ro, sun);
+            if (st.x >= st.y) {
+                state = ST_SHADOW_END;
+            } else {
+                t = st.x; t_max = st.y; in_shadow = true;
+                state = ST_TRACK;
+            }
+        }
+
+        // ---------------------------------------------------------------- :150, :157, then :224-230 or :240-242
+        if (state == ST_SHADOW_END) {
+            seed = saved_seed;  // the shadow ray consumed a copy of the stream
+            in_shadow = false;
+            L += throughput * (clampf(transmittance, 0.0f, 1.0f) * light * bsdf);  // :157, same association as the shader
+            state = ST_SEGMENT;
+            if (after_ground) {
+                if (P.pt.environment_lighting == SKY_ENV_GROUND_SINGLE_BOUNCE) {
+                    state = ST_FINISH;
+                } else {
+                    // GenerateLambertSample, :119-129
+                    float3 ground_normal = normalize(f3(ro.x, ro.y, ro.z + P.c.uEarthRadius));
+                    float sin_theta = sqrtf(Random01<PRNG_KIND>(seed));
+                    float cos_theta = sqrtf(clampf(1.0f - sin_theta * sin_theta, 0.0f, 1.0f));
+                    float3 t0, t1;
+                    CreateOrthonormalBasis(ground_normal, t0, t1);
+                    float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
+                    rd = sin_theta * sinf(phi) * t0 + sin_theta * cosf(phi) * t1 + cos_theta * ground_normal;
+                    throughput *= P.atm.ground_albedo();
+                }
+            } else if (P.pt.importance_sampling) {
+                // GenerateHGSample, :98-111
                 float g = Random01<PRNG_KIND>(seed) < P.pt.forward_scattering_ratio ? P.pt.forward_phase_g : P.pt.back_phase_g;
                 float cos_theta = HenyeyGreensteinInvertcdf(Random01<PRNG_KIND>(seed), g);
                 float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
                 float3 t0, t1;
-                CreateOrthonormalBasis(ray.d, t0, t1);
+                CreateOrthonormalBasis(rd, t0, t1);
                 float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
-                ray.d = sin_theta * sinf(phi) * t0 + sin_theta * cosf(phi) * t1 + cos_theta * ray.d;
+                rd = sin_theta * sinf(phi) * t0 + sin_theta * cosf(phi) * t1 + cos_theta * rd;
             } else {
-                // UniformSphereSample, :50-55
+                // UniformSphereSample, :50-55, :112-115
                 float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
                 float cos_theta = 1.0f - 2.0f * Random01<PRNG_KIND>(seed);
                 float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
                 float3 direction = f3(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta);
-                float value = GetPhase(P, dot(ray.d, direction));
-                ray.d = direction;
+                float value = GetPhase(P, dot(rd, direction));
+                rd = direction;
                 throughput *= value / (1.0f / (4.0f * kPi));
             }
+            ++istep;
         }
-        ++istep;
-    }
-    return f4(L, has_scattered ? 0.0f : 1.0f);
-}
 
-// K19 -- :255-284.  One thread per pixel of kRenderRegion; the thread walks kFrameId =
-// frame_begin .. frame_begin+frame_count-1 and adds each sample to the accumulator in frame order
-// (the reference's order of fp32 additions), with one read-modify-write of the RGBA32F texel.
-template <int MAT, bool HW, int PRNG_KIND, bool COUNT>
-__global__ void __launch_bounds__(128) k19_path_trace(const __grid_constant__ PtParams P) {
-    int px = P.x0 + blockIdx.x * 16 + (threadIdx.x & 15), py = P.y0 + blockIdx.y * 8 + (threadIdx.x >> 4);
-    if (px >= P.x1 || py >= P.y1 || px >= P.width || py >= P.height) return;
-    const size_t pix = size_t(py) * P.width + px;
-    float2 uv = f2((float(px) + 0.5f) / float(P.width), (float(py) + 0.5f) / float(P.height));
-    const float3 camera = f3(P.c.uCameraPos);
-    float3 frag_pos = projective_mul(P.c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 1.0f));
-    float3 view_dir = normalize(frag_pos - camera);
-    const uint32_t pixel_seed = PRNG<PRNG_KIND>(PRNG<PRNG_KIND>(uint32_t(px)) + uint32_t(py));
-    float4 accumulated = P.accum[pix];
-    int lookups = 0, collisions = 0;
-    for (uint32_t f = 0; f < P.frame_count; ++f) {
-        uint32_t seed = PRNG<PRNG_KIND>(pixel_seed + (P.frame_begin + f));
-        bool has_scattered;
-        float scattered_t = 0.0f;
-        float4 this_res = Trace<MAT, HW, PRNG_KIND, COUNT>(P, seed, view_dir, has_scattered, scattered_t, lookups, collisions);
-        if (has_scattered) {
-            float r = P.c.uCameraPos[2] + P.c.uEarthRadius;
-            float mu = view_dir.z;
-            float ap_t = scattered_t;
-            if (r > P.atm.u.top_radius) {  // GetAerialPerspective, VolumetricCloudCommon.glsl:81-97
-                float near_distance;
-                if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu, near_distance)) ap_t -= near_distance;
-                else ap_t = 0;
+        // ---------------------------------------------------------------- :248, :263-283
+        if (state == ST_FINISH) {
+            float4 this_res = f4(L, has_scattered ? 0.0f : 1.0f);
+            if (has_scattered) {
+                float2 uv = f2((float(px) + 0.5f) / float(P.width), (float(py) + 0.5f) / float(P.height));
+                float3 frag_pos = projective_mul(P.c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 1.0f));
+                float3 view_dir = normalize(frag_pos - camera);
+                float r = P.c.uCameraPos[2] + P.c.uEarthRadius;
+                float mu = view_dir.z;
+                float ap_t = scattered_t;
+                if (r > P.atm.u.top_radius) {  // GetAerialPerspective, VolumetricCloudCommon.glsl:81-97
+                    float near_distance;
+                    if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu, near_distance)) ap_t -= near_distance;
+                    else ap_t = 0;
+                }
+                float3 uvw = aerial_perspective_uvw(uv, ap_t, P.c.uAerialPerspectiveLutMaxDistance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
+                float3 atmosphere_transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
+                float3 atmosphere_luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
+                atmosphere_luminance *= SampleRayScatterVisibility(P.froxel, uv, scattered_t, P.c.uInvShadowFroxelMaxDistance);
+                this_res = f4(xyz(this_res) * atmosphere_transmittance + atmosphere_luminance, this_res.w);
             }
-            float3 uvw = aerial_perspective_uvw(uv, ap_t, P.c.uAerialPerspectiveLutMaxDistance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
-            float3 atmosphere_transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
-            float3 atmosphere_luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
-            atmosphere_luminance *= SampleRayScatterVisibility(P.froxel, uv, scattered_t, P.c.uInvShadowFroxelMaxDistance);
-            float3 rgb = xyz(this_res) * atmosphere_transmittance + atmosphere_luminance;
-            this_res = f4(rgb, this_res.w);
+            unsigned int frame_index = job / npix_padded;
+            P.samples[size_t(frame_index) * npix + size_t(py - P.y0) * rw + (px - P.x0)] = this_res;
+            state = ST_FETCH;
         }
-        accumulated = accumulated + this_res;
     }
-    P.accum[pix] = accumulated;
-    P.mask[pix] = 1;
     if (COUNT) {
-        atomicAdd(P.counters + SKY_CNT_PT_PATHS, (unsigned long long)P.frame_count);
+        atomicAdd(P.counters + SKY_CNT_PT_PATHS, (unsigned long long)paths);
         atomicAdd(P.counters + SKY_CNT_PT_LOOKUPS, (unsigned long long)lookups);
         atomicAdd(P.counters + SKY_CNT_PT_COLLISIONS, (unsigned long long)collisions);
     }
+}
+
+// second half of K19 (:281-283): accumulated += this_res, one sample per kFrameId, in frame order.
+__global__ void __launch_bounds__(256) k19_accumulate(const __grid_constant__ PtParams P) {
+    const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= rw || y >= rh) return;
+    const size_t npix = size_t(rw) * rh, local = size_t(y) * rw + x;
+    const size_t pix = size_t(P.y0 + y) * P.width + (P.x0 + x);
+    float4 accumulated = P.accum[pix];
+    for (uint32_t f = 0; f < P.frame_count; ++f) accumulated = accumulated + __ldcs(P.samples + size_t(f) * npix + local);
+    P.accum[pix] = accumulated;
+    P.mask[pix] = 1;
 }
 
 // K20 -- :288-296
@@ -357,25 +460,58 @@ int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32
         return sky_fail(ctx, "cloud map / detail texture has not been generated");
     if (count == 0) return 0;
     PtParams P = make_pt_params(ctx, c);
-    P.x0 = region[0]; P.y0 = region[1]; P.x1 = region[2]; P.y1 = region[3];
-    P.frame_begin = frame_begin; P.frame_count = count;
-    int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
+    P.x0 = std::max(region[0], 0); P.y0 = std::max(region[1], 0);
+    P.x1 = std::min(region[2], ctx->width); P.y1 = std::min(region[3], ctx->height);
+    const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
     if (rw <= 0 || rh <= 0) return 0;
-    dim3 grid(ceil_div(rw, 16), ceil_div(rh, 8));
+    // tile-padded job space: ceil(rw/8) x ceil(rh/4) tiles of 32 pixels
+    const size_t padded = size_t((rw + 7) / 8) * size_t((rh + 3) / 4) * 32;
+    // sample slots: at most ~1 GiB per launch, so long jobs run in chunks of frames
+    uint32_t frames_per_launch = uint32_t(std::max<size_t>(1, std::min<size_t>(count, (size_t(1) << 26) / padded)));
+    if (padded * frames_per_launch >= (size_t(1) << 32)) return sky_fail(ctx, "region too large for one launch");
+    const size_t need = padded * frames_per_launch * sizeof(float4);
+    if (ctx->pt_samples_bytes < need) {
+        if (ctx->pt_samples) SKY_CUDA(ctx, cudaFree(ctx->pt_samples));
+        ctx->pt_samples = nullptr; ctx->pt_samples_bytes = 0;
+        SKY_CUDA(ctx, cudaMalloc(&ctx->pt_samples, need));
+        ctx->pt_samples_bytes = need;
+    }
+    if (!ctx->pt_job_counter) SKY_CUDA(ctx, cudaMalloc(&ctx->pt_job_counter, sizeof(unsigned int)));
+    P.samples = static_cast<float4*>(ctx->pt_samples);
+    P.job_counter = ctx->pt_job_counter;
+
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
     const bool count_on = ctx->counting;
     const int prng = ctx->pt.prng;
-    int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
-        if (prng == SKY_PRNG_WANG) {
-            if (count_on) k19_path_trace<MAT, HW, SKY_PRNG_WANG, true><<<grid, 128, 0, ctx->stream>>>(P);
-            else k19_path_trace<MAT, HW, SKY_PRNG_WANG, false><<<grid, 128, 0, ctx->stream>>>(P);
-        } else {
-            if (count_on) k19_path_trace<MAT, HW, SKY_PRNG_PCG, true><<<grid, 128, 0, ctx->stream>>>(P);
-            else k19_path_trace<MAT, HW, SKY_PRNG_PCG, false><<<grid, 128, 0, ctx->stream>>>(P);
-        }
-        return 0;
-    });
-    if (rc) return sky_fail(ctx, "unknown material");
-    SKY_LAUNCH_CHECK(ctx);
+    for (uint32_t done = 0; done < count; done += frames_per_launch) {
+        P.frame_begin = frame_begin + done;
+        P.frame_count = std::min(frames_per_launch, count - done);
+        SKY_CUDA(ctx, cudaMemsetAsync(ctx->pt_job_counter, 0, sizeof(unsigned int), ctx->stream));
+        // NOTE: the job space is the tile-padded pixel count, the slots are indexed by real pixels
+        PtParams Q = P;
+        int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
+            auto launch = [&](auto kernel) {
+                int per_sm = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+                size_t jobs = padded * Q.frame_count;
+                unsigned blocks = unsigned(std::min<size_t>(size_t(sm_count) * std::max(per_sm, 1), (jobs + 127) / 128));
+                kernel<<<blocks, 128, 0, ctx->stream>>>(Q);
+            };
+            if (prng == SKY_PRNG_WANG) {
+                if (count_on) launch(k19_path_trace<MAT, HW, SKY_PRNG_WANG, true>);
+                else launch(k19_path_trace<MAT, HW, SKY_PRNG_WANG, false>);
+            } else {
+                if (count_on) launch(k19_path_trace<MAT, HW, SKY_PRNG_PCG, true>);
+                else launch(k19_path_trace<MAT, HW, SKY_PRNG_PCG, false>);
+            }
+            return 0;
+        });
+        if (rc) return sky_fail(ctx, "unknown material");
+        SKY_LAUNCH_CHECK(ctx);
+        k19_accumulate<<<dim3(ceil_div(rw, 256), rh), 256, 0, ctx->stream>>>(Q);
+        SKY_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 
