@@ -1,0 +1,120 @@
+/*
+ * sky_detmath.h -- deterministic fp32 elementary functions for the atmosphere LUT bake.
+ *
+ * GLSL leaves the accuracy of exp/sin/cos/acos to the driver, and the LUT arithmetic amplifies a
+ * one-ulp difference without bound.  These versions are written with plain IEEE
+ * fp32 +, -, *, /, sqrt only, in a fixed order, so that a CPU build with -ffp-contract=off and a CUDA
+ * build with -fmad=false return bit-identical results: the LUT kernels and the oracle can then be
+ * compared bit for bit.  Accuracy is the usual 1-2 ulp of a minimax polynomial after Cody-Waite
+ * range reduction (checked against double precision in tests/test_oracle_kat.py).
+ * This header is neutral infrastructure: it contains no part of the rendering algorithm.
+ */
+#ifndef SKY_DETMATH_H
+#define SKY_DETMATH_H
+
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define SKY_DM __host__ __device__ __forceinline__
+#else
+#define SKY_DM inline
+#include <math.h>
+#endif
+
+SKY_DM float sky_bits_to_float(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+SKY_DM uint32_t sky_float_to_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+
+/* exp(x): k = round(x / ln2), r = x - k ln2 in two pieces, Pade-style kernel, scale by 2^k. */
+SKY_DM float sky_det_expf(float x) {
+    if (x != x) return x;
+    if (x > 88.72f) return sky_bits_to_float(0x7f800000u);
+    if (x < -103.9f) return 0.0f;
+    const float ln2hi = 6.9314575195e-01f, ln2lo = 1.4286067653e-06f, invln2 = 1.4426950216e+00f;
+    const float P1 = 1.6666625440e-01f, P2 = -2.7667332906e-03f;
+    int k = (int)(invln2 * x + (x < 0.0f ? -0.5f : 0.5f));
+    float fk = (float)k;
+    float hi = x - fk * ln2hi;
+    float lo = fk * ln2lo;
+    float r = hi - lo;
+    float rr = r * r;
+    float c = r - rr * (P1 + rr * P2);
+    float y = 1.0f + (r * c / (2.0f - c) - lo + hi);
+    if (k >= -125) return y * sky_bits_to_float((uint32_t)(k + 127) << 23);
+    /* subnormal results: two-step scaling */
+    return y * sky_bits_to_float((uint32_t)(k + 64 + 127) << 23) * sky_bits_to_float((uint32_t)(127 - 64) << 23);
+}
+
+/* sin and cos together: quadrant n = round(x * 2/pi), r = x - n pi/2 (two-piece), kernels on [-pi/4, pi/4].
+ * Meant for the angles of the bake (|x| up to a few pi). */
+SKY_DM void sky_det_sincosf(float x, float* s_out, float* c_out) {
+    const float two_over_pi = 6.3661977237e-01f, pio2_1 = 1.5707855225e+00f, pio2_1t = 1.0804334124e-05f;
+    int n = (int)(x * two_over_pi + (x < 0.0f ? -0.5f : 0.5f));
+    float fn = (float)n;
+    float r = (x - fn * pio2_1) - fn * pio2_1t;
+    float z = r * r;
+    const float S1 = -1.6666667163e-01f, S2 = 8.3333337680e-03f, S3 = -1.9841270114e-04f, S4 = 2.7557314297e-06f, S5 = -2.5050759689e-08f;
+    const float C1 = 4.1666667908e-02f, C2 = -1.3888889225e-03f, C3 = 2.4801587642e-05f, C4 = -2.7557314297e-07f, C5 = 2.0875723372e-09f;
+    float s = r + r * z * (S1 + z * (S2 + z * (S3 + z * (S4 + z * S5))));
+    float c = 1.0f - (0.5f * z - z * z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * C5)))));
+    switch (n & 3) {
+        case 0: *s_out = s; *c_out = c; break;
+        case 1: *s_out = c; *c_out = -s; break;
+        case 2: *s_out = -s; *c_out = -c; break;
+        default: *s_out = -c; *c_out = s; break;
+    }
+}
+SKY_DM float sky_det_sinf(float x) { float s, c; sky_det_sincosf(x, &s, &c); return s; }
+SKY_DM float sky_det_cosf(float x) { float s, c; sky_det_sincosf(x, &s, &c); return c; }
+
+/* acos(x), |x| <= 1 (callers clamp): rational kernel R(z) on z = x^2 or (1 -+ x)/2, as in the classic
+ * Sun libm split into |x| < 0.5, x < -0.5, x > 0.5. */
+SKY_DM float sky_det_acos_r(float z) {
+    const float pS0 = 1.6666586697e-01f, pS1 = -4.2743422091e-02f, pS2 = -8.6563630030e-03f, qS1 = -7.0662963390e-01f;
+    float p = z * (pS0 + z * (pS1 + z * pS2));
+    float q = 1.0f + z * qS1;
+    return p / q;
+}
+SKY_DM float sky_det_acosf(float x) {
+    const float pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f;
+    if (x >= 1.0f) return 0.0f;
+    if (x <= -1.0f) return 2.0f * pio2_hi;
+    float ax = x < 0.0f ? -x : x;
+    if (ax < 0.5f) {
+        if (ax < 3.7252903e-09f) return pio2_hi;
+        return pio2_hi - (x - (pio2_lo - x * sky_det_acos_r(x * x)));
+    }
+    if (x < 0.0f) {
+        float z = (1.0f + x) * 0.5f;
+        float s = sqrtf(z);
+        float w = sky_det_acos_r(z) * s - pio2_lo;
+        return 2.0f * (pio2_hi - (s + w));
+    }
+    float z = (1.0f - x) * 0.5f;
+    float s = sqrtf(z);
+    float df = sky_bits_to_float(sky_float_to_bits(s) & 0xfffff000u);
+    float c = (z - df * df) / (s + df);
+    float w = sky_det_acos_r(z) * s + c;
+    return 2.0f * (df + w);
+}
+
+/* x^1.5 for x >= 0 (MiePhaseFunction, Atmosphere.glsl:150): x * sqrt(x) */
+SKY_DM float sky_det_pow15f(float x) { return x * sqrtf(x); }
+
+#endif /* SKY_DETMATH_H */

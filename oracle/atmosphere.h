@@ -8,9 +8,14 @@
 // restatement is pinned by derived known-answer tests in tests/test_oracle_kat.py instead.
 #pragma once
 #include "../include/sky_types.h"
+#include "../include/sky_detmath.h"
 #include "sampler.h"
 
 namespace orc {
+
+// The LUT bake (K1-K5) evaluates exp / sin / cos / acos / x^1.5 with the deterministic fp32 versions of
+// include/sky_detmath.h, so that it can be compared bit for bit with the CUDA kernels.
+inline vec3 lut_exp3(vec3 v) { return vec3(sky_det_expf(v.x), sky_det_expf(v.y), sky_det_expf(v.z)); }
 
 constexpr float PI = 3.1415926535897932384626433832795f;  // shaders/Base/Common.glsl:4
 constexpr float INV_PI = 1.0f / PI;
@@ -114,9 +119,9 @@ struct Atmosphere {
     // Atmosphere.glsl:119-132
     vec3 GetExtinction(float altitude) const {
         vec3 rayleigh_extinction =
-            rayleigh_scattering() * clamp(std::exp(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+            rayleigh_scattering() * clamp(sky_det_expf(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
         vec3 mie_extinction = (mie_scattering() + mie_absorption()) *
-                              clamp(std::exp(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+                              clamp(sky_det_expf(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
         vec3 ozone_extinction =
             ozone_absorption() * max(0.0f, altitude < u.ozone_center_altitude
                                                    ? 1.0f + (altitude - u.ozone_center_altitude) * u.inv_ozone_width
@@ -136,13 +141,13 @@ struct Atmosphere {
     static float MiePhaseFunction(float g, float cos_theta) {
         if (MS) return IsotropicPhaseFunction();
         float k = 3.0f / (8.0f * PI) * (1.0f - g * g) / (2.0f + g * g);
-        return k * (1.0f + cos_theta * cos_theta) / std::pow(1.0f + g * g - 2.0f * g * cos_theta, 1.5f);
+        return k * (1.0f + cos_theta * cos_theta) / sky_det_pow15f(1.0f + g * g - 2.0f * g * cos_theta);
     }
 
     // Atmosphere.glsl:156-159
     void GetScattering(float altitude, vec3& rayleigh, vec3& mie) const {
-        rayleigh = rayleigh_scattering() * clamp(std::exp(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
-        mie = mie_scattering() * clamp(std::exp(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+        rayleigh = rayleigh_scattering() * clamp(sky_det_expf(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+        mie = mie_scattering() * clamp(sky_det_expf(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
     }
 
     // Atmosphere.glsl:161-167
@@ -191,7 +196,7 @@ struct Atmosphere {
             vec3 scattering_with_phase_i = rayleigh_scattering_i * rayleigh_phase + mie_scattering_i * mie_phase;
 
             vec3 extinction_i = GetExtinction(altitude_i);
-            vec3 transmittance_i = exp(-extinction_i * dx);
+            vec3 transmittance_i = lut_exp3(-extinction_i * dx);
             vec3 up_direction_i = normalize(position_i - earth_center);
             float mu_s_i = dot(sun_direction, up_direction_i);
             vec3 luminance_i = scattering_with_phase_i * GetSunVisibility(transmittance_texture, r_i, mu_s_i);
@@ -230,7 +235,7 @@ struct Atmosphere {
             float altitude_i = r_i - u.bottom_radius;
             optical_length += GetExtinction(altitude_i) * dx;
         }
-        return exp(-optical_length);
+        return lut_exp3(-optical_length);
     }
 
     // Atmosphere.glsl:344-355
@@ -240,7 +245,7 @@ struct Atmosphere {
         float cos_theta = 1.0f - 2.0f * unit_theta;
         float sin_theta = std::sqrt(clamp(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
         float phi = 2 * PI * unit_phi;
-        return vec3(std::cos(phi) * sin_theta, cos_theta, std::sin(phi) * sin_theta);
+        return vec3(sky_det_cosf(phi) * sin_theta, cos_theta, sky_det_sinf(phi) * sin_theta);
     }
 
     // K1: Atmosphere.glsl:332-337 over 256x64 (Atmosphere.cpp:9-15)
@@ -287,7 +292,7 @@ struct AtmosphereRenderer {
     float GetHorizonDownAngleFromR(float r) const {
         float tangent_point_distance = std::sqrt(r * r - atm.u.bottom_radius * atm.u.bottom_radius);
         float cos_horizon_down = tangent_point_distance / r;
-        return std::acos(cos_horizon_down);
+        return sky_det_acosf(cos_horizon_down);
     }
     // AtmosphereRenderer.glsl:81-102
     void GetCosLatLonFromSkyViewTextureIndex(ivec2 index, float r, float& cos_lat, float& cos_lon) const {
@@ -305,7 +310,7 @@ struct AtmosphereRenderer {
             coord *= coord;
             lat = horizon_up_angle + horizon_down_angle * coord;
         }
-        cos_lat = std::cos(lat);
+        cos_lat = sky_det_cosf(lat);
         cos_lon = -(x_cos_lon * x_cos_lon * 2.0f - 1.0f);
     }
     // AtmosphereRenderer.glsl:104-111
@@ -320,7 +325,7 @@ struct AtmosphereRenderer {
         float horizon_up_angle = PI - horizon_down_angle;
         // GLSL leaves acos(|x|>1) and sqrt(x<0) undefined; rounding in dot()/normalize() can push the
         // arguments a few ulp outside, so the oracle (and the CUDA kernels) clamp them.
-        float lat = std::acos(clamp(cos_lat, -1.0f, 1.0f));
+        float lat = sky_det_acosf(clamp(cos_lat, -1.0f, 1.0f));
         float x_cos_lat;
         if (lat < horizon_up_angle) {
             float coord = lat / horizon_up_angle;

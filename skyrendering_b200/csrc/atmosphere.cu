@@ -3,10 +3,27 @@
 // each function).  Compiled with -fmad=false: these kernels are microsecond-scale and
 // latency-bound, and the altitude r_i - bottom_radius (Atmosphere.glsl:258-260) cancels ~7 digits,
 // so keeping the reference's unfused fp32 operation order is worth more than the FMAs.
+#include "../../include/sky_detmath.h"
 #include "atmosphere_dev.cuh"
 #include "context.h"
 
+// The LUT kernels use the deterministic fp32 elementary functions shared with the oracle (bit-for-bit
+// comparable results); the composite translation unit uses the hardware intrinsics.
+#ifdef SKY_COMPOSITE_TU
+#define LUT_EXP(x) __expf(x)
+#define LUT_COS(x) __cosf(x)
+#define LUT_SIN(x) __sinf(x)
+#define LUT_ACOS(x) acosf(x)
+#else
+#define LUT_EXP(x) sky_det_expf(x)
+#define LUT_COS(x) sky_det_cosf(x)
+#define LUT_SIN(x) sky_det_sinf(x)
+#define LUT_ACOS(x) sky_det_acosf(x)
+#endif
+
 namespace {
+
+SKY_D float3 lut_exp3(float3 a) { return f3(LUT_EXP(a.x), LUT_EXP(a.y), LUT_EXP(a.z)); }
 
 struct BakeParams {
     AtmosphereModel atm;
@@ -18,9 +35,9 @@ struct BakeParams {
 
 // Atmosphere.glsl:119-132
 SKY_D float3 GetExtinction(const SkyAtmosphereBufferData& u, float altitude) {
-    float3 rayleigh_extinction = f3(u.rayleigh_scattering) * clampf(expf(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+    float3 rayleigh_extinction = f3(u.rayleigh_scattering) * clampf(LUT_EXP(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
     float3 mie_extinction = (f3(u.mie_scattering) + f3(u.mie_absorption)) *
-                            clampf(expf(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+                            clampf(LUT_EXP(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
     float3 ozone_extinction = f3(u.ozone_absorption) *
                               fmaxf(0.0f, altitude < u.ozone_center_altitude ? 1.0f + (altitude - u.ozone_center_altitude) * u.inv_ozone_width
                                                                             : 1.0f - (altitude - u.ozone_center_altitude) * u.inv_ozone_width);
@@ -53,7 +70,7 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
         rayleigh_phase = (3.0f / (16.0f * kPi)) * (1.0f + cos_sun_view * cos_sun_view);
         float g = u.mie_phase_g;
         float k = 3.0f / (8.0f * kPi) * (1.0f - g * g) / (2.0f + g * g);
-        mie_phase = k * (1.0f + cos_sun_view * cos_sun_view) / powf(1.0f + g * g - 2.0f * g * cos_sun_view, 1.5f);
+        mie_phase = k * (1.0f + cos_sun_view * cos_sun_view) / sky_det_pow15f(1.0f + g * g - 2.0f * g * cos_sun_view);
     }
     for (float i = start_i; i < SAMPLE_COUNT; ++i) {
         float d_i = i * dx;
@@ -62,13 +79,13 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
         float altitude_i = r_i - u.bottom_radius;
 
         // GetScattering, :156-159
-        float3 rayleigh_scattering_i = f3(u.rayleigh_scattering) * clampf(expf(-altitude_i * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
-        float3 mie_scattering_i = f3(u.mie_scattering) * clampf(expf(-altitude_i * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+        float3 rayleigh_scattering_i = f3(u.rayleigh_scattering) * clampf(LUT_EXP(-altitude_i * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+        float3 mie_scattering_i = f3(u.mie_scattering) * clampf(LUT_EXP(-altitude_i * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
         float3 scattering_i = rayleigh_scattering_i + mie_scattering_i;
         float3 scattering_with_phase_i = rayleigh_scattering_i * rayleigh_phase + mie_scattering_i * mie_phase;
 
         float3 extinction_i = GetExtinction(u, altitude_i);
-        float3 transmittance_i = exp3(-extinction_i * dx);
+        float3 transmittance_i = lut_exp3(-extinction_i * dx);
         float3 up_direction_i = normalize(position_i - earth_center);
         float mu_s_i = dot(sun_direction, up_direction_i);
         float3 luminance_i = scattering_with_phase_i * atm.GetSunVisibility(transmittance_texture, r_i, mu_s_i);
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(128) k1_transmittance(const __grid_constant__ 
         float altitude_i = r_i - u.bottom_radius;
         optical_length += GetExtinction(u, altitude_i) * dx;
     }
-    P.transmittance_out[y * W + x] = f4(exp3(-optical_length), 1.0f);
+    P.transmittance_out[y * W + x] = f4(lut_exp3(-optical_length), 1.0f);
 }
 
 // ------------------------------------------------------------------------------------------------- K2
@@ -151,7 +168,7 @@ __global__ void __launch_bounds__(64) k2_multiscattering(const __grid_constant__
     float cos_theta = 1.0f - 2.0f * unit_theta;
     float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
     float phi = 2 * kPi * unit_phi;
-    float3 view_direction = f3(cosf(phi) * sin_theta, cos_theta, sinf(phi) * sin_theta);
+    float3 view_direction = f3(LUT_COS(phi) * sin_theta, cos_theta, LUT_SIN(phi) * sin_theta);
 
     float r = altitude + u.bottom_radius;
     float mu = view_direction.y;
@@ -222,14 +239,14 @@ SKY_D float3 ComputeRaymarchingStartPositionAndChangeDistance(const RenderParams
 // AtmosphereRenderer.glsl:74-78
 SKY_D float GetHorizonDownAngleFromR(const RenderParams& P, float r) {
     float tangent_point_distance = sqrtf(r * r - P.atm.u.bottom_radius * P.atm.u.bottom_radius);
-    return acosf(tangent_point_distance / r);
+    return LUT_ACOS(tangent_point_distance / r);
 }
 // AtmosphereRenderer.glsl:113-132.  acos/sqrt arguments are clamped into their domains: GLSL leaves
 // them undefined a few ulp outside, which rounding in dot()/normalize() does produce.
 SKY_D float2 GetSkyViewTextureUvFromCosLatLon(const RenderParams& P, float r, float cos_lat, float cos_lon) {
     float horizon_down_angle = GetHorizonDownAngleFromR(P, r);
     float horizon_up_angle = kPi - horizon_down_angle;
-    float lat = acosf(clampf(cos_lat, -1.0f, 1.0f));
+    float lat = LUT_ACOS(clampf(cos_lat, -1.0f, 1.0f));
     float x_cos_lat;
     if (lat < horizon_up_angle) {
         float coord = lat / horizon_up_angle;
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(64) k3_sky_view(const __grid_constant__ Render
         coord *= coord;
         lat = horizon_up_angle + horizon_down_angle * coord;
     }
-    float cos_lat = cosf(lat);
+    float cos_lat = LUT_COS(lat);
     float cos_lon = -(x_cos_lon * x_cos_lon * 2.0f - 1.0f);
     // GetViewDirectionFromCosLatLon
     float sin_lat = clampf(sqrtf(1 - cos_lat * cos_lat), 0.0f, 1.0f);
