@@ -39,14 +39,16 @@ struct CloudParams {
     half4* reconstruct_out;    // W/2 x H/2
     half4* hdr;
     int band_rows, band_index, band_count;
+    float inv_thickness;  // 1 / (uTopAltitude - uBottomAltitude)
 };
 
 SKY_D float DepthToLinearDepth(const SkyCloudCommonBufferData& c, float depth) {  // VolumetricCloudCommon.glsl:32-34
     return 1.0f / (c.uLinearDepthParam[0] - c.uLinearDepthParam[1] * depth);
 }
-SKY_D float CalHeight01(const SkyCloudCommonBufferData& c, float3 pos) {  // VolumetricCloudCommon.glsl:36-39
+SKY_D float CalHeight01(const CloudParams& P, float3 pos) {  // VolumetricCloudCommon.glsl:36-39
+    const SkyCloudCommonBufferData& c = P.c;
     float altitude = length(f3(pos.x, pos.y, pos.z + c.uEarthRadius)) - c.uEarthRadius;
-    return clampf((altitude - c.uBottomAltitude) / (c.uTopAltitude - c.uBottomAltitude), 0.0f, 1.0f);
+    return clampf((altitude - c.uBottomAltitude) * P.inv_thickness, 0.0f, 1.0f);  // the divisor is a uniform
 }
 SKY_D int2 IndexToOffset(uint32_t index) {  // VolumetricCloudCommon.glsl:42-52
     return make_int2(int(((index + 1) >> 1) & 1), int(((index + 2) >> 1) & 1));
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(128) k11_shadow_map(const __grid_constant__ Cl
         float t = t1 + step_size * fractf(noise + c.uFrameID * 0.61803398875f);
         for (uint32_t cnt = uint32_t(steps); cnt != 0; cnt--, t += step_size) {
             float3 pos = origin + t * dir;
-            float height01 = CalHeight01(c, pos);
+            float height01 = CalHeight01(P, pos);
             float sigma_t = SampleSigmaT<MAT, HW>(P.mat, pos, height01);
             optical_depth += sigma_t * step_size;
             if (COUNT) ++evals;
@@ -279,7 +281,7 @@ SKY_D float SampleShadow(const CloudParams& P, float3 pos, int& evals, int& fetc
         float current_t = t * t;
         float delta_t = current_t - previous_t;
         float3 sample_pos = pos + sample_vector * (previous_t + 0.5f * delta_t);
-        float sample_height01 = CalHeight01(P.c, sample_pos);
+        float sample_height01 = CalHeight01(P, sample_pos);
         optical_depth += SampleSigmaT<MAT, HW>(P.mat, sample_pos, sample_height01, COUNT ? &fetches : nullptr) * P.b.uShadowDistance * delta_t;
         if (COUNT) ++evals;
         previous_t = current_t;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudP
     ctx.t = i0t1 + ctx.step_size * jitter;
     for (uint32_t cnt = num_steps; cnt != 0; cnt--, ctx.t += ctx.step_size) {
         ctx.pos = camera + view_dir * ctx.t;  // UpdateContext, :90-93
-        ctx.height01 = CalHeight01(c, ctx.pos);
+        ctx.height01 = CalHeight01(P, ctx.pos);
         RayMarchStep<MAT, HW, COUNT>(P, ctx, evals, fetches);
         if (ctx.transmittance < kMinTransmittance) break;
     }
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudP
         ctx.t = i1t1 + ctx.step_size * jitter;
         for (uint32_t cnt = num_steps1; cnt != 0; cnt--, ctx.t += ctx.step_size) {
             ctx.pos = camera + view_dir * ctx.t;
-            ctx.height01 = CalHeight01(c, ctx.pos);
+            ctx.height01 = CalHeight01(P, ctx.pos);
             RayMarchStep<MAT, HW, COUNT>(P, ctx, evals, fetches);
             if (ctx.transmittance < kMinTransmittance) break;
         }
@@ -602,6 +604,7 @@ __global__ void __launch_bounds__(256) k_tex_peak(cudaTextureObject_t tex, int i
 CloudParams make_cloud_params(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
     CloudParams P{};
     P.c = c;
+    P.inv_thickness = 1.0f / (c.uTopAltitude - c.uBottomAltitude);
     P.atm.u = ctx->atm;
     make_material_params(ctx, c.uCameraPos, P.mat);
     P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
@@ -628,6 +631,17 @@ int make_material_params(SkyContext* ctx, const float* camera_pos, MaterialParam
     M.displacement = ctx->displacement.view;
     M.voxel = ctx->voxel.view;
     M.camera_pos = f3(camera_pos);
+    // lambda <= 0.5  <=>  k_lod * dist <= 2^(0.5 - bias)
+    auto thr2 = [](float k_lod, float bias) {
+        if (!(k_lod > 0.0f)) return INFINITY;  // log2(0 * dist) = -inf: always magnified
+        float t = exp2f(0.5f - bias) / k_lod;
+        return t * t;
+    };
+    const SkyMaterialCommonBufferData& mc = M.m.common;
+    M.thr2_cloud_map = thr2(mc.uCloudMapSampleInfo.k_lod, mc.uLodBias);
+    M.thr2_detail = thr2(mc.uDetailSampleInfo.k_lod, mc.uLodBias);
+    M.thr2_displacement = thr2(mc.uDisplacementSampleInfo.k_lod, mc.uLodBias);
+    M.thr2_voxel = thr2(M.m.u.voxel.uSampleLodK, M.m.u.voxel.uLodBias);
     return 0;
 }
 

@@ -5,9 +5,11 @@
 // Sampler semantics (VolumetricCloudDefaultMaterial.cpp:111-116, VolumetricCloudVoxelMaterial.cpp:30-37):
 // mag = LINEAR, min = NEAREST_MIPMAP_NEAREST, explicit LOD.  GL 4.6 section 8.14.3: lambda <= 0.5 ->
 // LINEAR on level 0; otherwise NEAREST on level ceil(lambda + 0.5) - 1.
-//   HW == false: exact fp32 weights on texels read straight from linear device memory (L1/L2 hits);
-//                bit-compatible with the oracle's software sampler.
-//   HW == true : the texture unit filters (8-bit weights); one TEX per fetch instead of 4-8 loads.
+//   HW == false: exact fp32 weights on texels read from device memory: one 8/16-byte load of a
+//                corner-packed cell (MipView::cells) per LINEAR fetch, one texel load per NEAREST fetch.
+//   HW == true : the texture unit filters (8-bit weights); one TEX per fetch.
+// lambda = log2(k_lod * dist) + bias is only needed to pick the level: lambda <= 0.5 is decided by
+// comparing dist^2 against a per-texture threshold, so the common (magnified) case costs no log2 / sqrt.
 #pragma once
 #include "common.cuh"
 #include "context.h"
@@ -16,6 +18,8 @@ struct MaterialParams {
     SkyMaterialBlock m;
     MipView cloud_map, detail, displacement, voxel;
     float3 camera_pos;  // uCameraPos
+    // (2^(0.5 - lod_bias) / k_lod)^2 per texture: dist^2 <= thr2  <=>  lambda <= 0.5
+    float thr2_cloud_map, thr2_detail, thr2_displacement, thr2_voxel;
 };
 
 // spec 8.14.3 level selection; returns -1 for magnification
@@ -25,8 +29,15 @@ SKY_D int select_mip_level(float lod, int levels) {
     int d = (lod <= float(q) + 0.5f) ? int(ceilf(lod + 0.5f)) - 1 : q;
     return clampi(d, 0, q);
 }
+// level for lambda = log2(k_lod * sqrt(d2)) + bias (GetUVWLod, VolumetricCloudDefaultMaterialCommon.glsl:20-24)
+SKY_D int level_from_distance2(float d2, float k_lod, float lod_bias, float thr2, int levels) {
+    if (d2 <= thr2) return -1;
+    return select_mip_level(log2f(k_lod * sqrtf(d2)) + lod_bias, levels);
+}
 
-// ---- exact path: REPEAT textures have power-of-two sizes (512 / 128, fixed by the reference) --------
+// ---- exact path ---------------------------------------------------------------------------------------
+SKY_D float byte_to_float(uint32_t word, int n) { return float(uint8_t(word >> (8 * n))); }  // I2F.U8 with byte select
+
 template <int C>
 SKY_D void load_texel(const MipView& t, int level, int x, int y, int z, float* out) {
     const uint8_t* p = t.base + (t.off[level] + (size_t(z) * t.h[level] + y) * t.w[level] + x) * C;
@@ -42,29 +53,34 @@ SKY_D void load_texel(const MipView& t, int level, int x, int y, int z, float* o
     }
 }
 
-SKY_D float byte_of(uint32_t word, int n) { return float((word >> (8 * n)) & 0xffu) * (1.0f / 255.0f); }
-
+// REPEAT textures have power-of-two sizes (512 / 128, fixed by the reference)
 template <int C>
-SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, float lod, float* out) {
-    int level = select_mip_level(lod, t.levels);
+SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, int level, float* out) {
     if (level < 0) {
         int w = t.w[0], h = t.h[0];
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f;
         float fx = floorf(x), fy = floorf(y);
         float a = x - fx, b = y - fy;
         int i0 = int(fx) & (w - 1), j0 = int(fy) & (h - 1);
-        float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
         // one load brings the four corners: C == 2 -> 8 bytes {c00 c10 c01 c11} x {r,g}; C == 4 -> 16 bytes
         if (C == 2) {
             uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + size_t(j0) * w + i0);
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-                out[c] = w00 * byte_of(cell.x, c) + w10 * byte_of(cell.x, 2 + c) + w01 * byte_of(cell.y, c) + w11 * byte_of(cell.y, 2 + c);
+            for (int c = 0; c < 2; ++c) {
+                float t00 = byte_to_float(cell.x, c), t10 = byte_to_float(cell.x, 2 + c);
+                float t01 = byte_to_float(cell.y, c), t11 = byte_to_float(cell.y, 2 + c);
+                float r0 = t00 + a * (t10 - t00), r1 = t01 + a * (t11 - t01);
+                out[c] = (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
+            }
         } else {
             uint4 cell = __ldg(reinterpret_cast<const uint4*>(t.cells) + size_t(j0) * w + i0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                out[c] = w00 * byte_of(cell.x, c) + w10 * byte_of(cell.y, c) + w01 * byte_of(cell.z, c) + w11 * byte_of(cell.w, c);
+            for (int c = 0; c < 4; ++c) {
+                float t00 = byte_to_float(cell.x, c), t10 = byte_to_float(cell.y, c);
+                float t01 = byte_to_float(cell.z, c), t11 = byte_to_float(cell.w, c);
+                float r0 = t00 + a * (t10 - t00), r1 = t01 + a * (t11 - t01);
+                out[c] = (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
+            }
         }
     } else {
         int w = t.w[level], h = t.h[level];
@@ -73,59 +89,43 @@ SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, float lod, 
     }
 }
 
-SKY_D float sample3d_repeat_exact(const MipView& t, float u, float v, float w_, float lod) {
-    int level = select_mip_level(lod, t.levels);
-    float out;
+// trilinear blend of the 8 corner bytes of a packed cell (byte n = di + 2*dj + 4*dk), x first
+SKY_D float blend_cell(uint2 cell, float a, float b, float c) {
+    float t000 = byte_to_float(cell.x, 0), t100 = byte_to_float(cell.x, 1), t010 = byte_to_float(cell.x, 2), t110 = byte_to_float(cell.x, 3);
+    float t001 = byte_to_float(cell.y, 0), t101 = byte_to_float(cell.y, 1), t011 = byte_to_float(cell.y, 2), t111 = byte_to_float(cell.y, 3);
+    float x00 = t000 + a * (t100 - t000), x10 = t010 + a * (t110 - t010);
+    float x01 = t001 + a * (t101 - t001), x11 = t011 + a * (t111 - t011);
+    float y0 = x00 + b * (x10 - x00), y1 = x01 + b * (x11 - x01);
+    return (y0 + c * (y1 - y0)) * (1.0f / 255.0f);
+}
+
+SKY_D float sample3d_repeat_exact(const MipView& t, float u, float v, float w_, int level) {
     if (level < 0) {
         int w = t.w[0], h = t.h[0], d = t.d[0];
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
         float fx = floorf(x), fy = floorf(y), fz = floorf(z);
-        float a = x - fx, b = y - fy, c = z - fz;
         int i0 = int(fx) & (w - 1), j0 = int(fy) & (h - 1), k0 = int(fz) & (d - 1);
-        // 8 corners in one 8-byte load: byte n = di + 2*dj + 4*dk
         uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(k0) * h + j0) * w + i0);
-        float r = 0.0f;
-#pragma unroll
-        for (int dk = 0; dk < 2; ++dk)
-#pragma unroll
-            for (int dj = 0; dj < 2; ++dj)
-#pragma unroll
-                for (int di = 0; di < 2; ++di) {
-                    float wt = (di ? a : 1.0f - a) * (dj ? b : 1.0f - b) * (dk ? c : 1.0f - c);
-                    r += wt * byte_of(dk ? cell.y : cell.x, di + 2 * dj);
-                }
-        out = r;
-    } else {
-        int w = t.w[level], h = t.h[level], d = t.d[level];
-        int i = int(floorf(u * float(w))) & (w - 1), j = int(floorf(v * float(h))) & (h - 1), k = int(floorf(w_ * float(d))) & (d - 1);
-        load_texel<1>(t, level, i, j, k, &out);
+        return blend_cell(cell, x - fx, y - fy, z - fz);
     }
+    int w = t.w[level], h = t.h[level], d = t.d[level];
+    int i = int(floorf(u * float(w))) & (w - 1), j = int(floorf(v * float(h))) & (h - 1), k = int(floorf(w_ * float(d))) & (d - 1);
+    float out;
+    load_texel<1>(t, level, i, j, k, &out);
     return out;
 }
 
 // CLAMP_TO_BORDER with border colour 0, any size (voxel grid)
-SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, float lod) {
-    int level = select_mip_level(lod, t.levels);
+SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, int level) {
     if (level < 0) {
         int w = t.w[0], h = t.h[0], d = t.d[0];
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
         float fx = floorf(x), fy = floorf(y), fz = floorf(z);
-        float a = x - fx, b = y - fy, c = z - fz;
         // cell index = base texel + 1; outside [0, w] x [0, h] x [0, d] every corner is the border
         float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
         if (!(cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d))) return 0.0f;
         uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(int(cz)) * t.cell_h + int(cy)) * t.cell_w + int(cx));
-        float r = 0.0f;
-#pragma unroll
-        for (int dk = 0; dk < 2; ++dk)
-#pragma unroll
-            for (int dj = 0; dj < 2; ++dj)
-#pragma unroll
-                for (int di = 0; di < 2; ++di) {
-                    float wt = (di ? a : 1.0f - a) * (dj ? b : 1.0f - b) * (dk ? c : 1.0f - c);
-                    r += wt * byte_of(dk ? cell.y : cell.x, di + 2 * dj);
-                }
-        return r;
+        return blend_cell(cell, x - fx, y - fy, z - fz);
     }
     int w = t.w[level], h = t.h[level], d = t.d[level];
     int i = int(floorf(u * float(w))), j = int(floorf(v * float(h))), k = int(floorf(w_ * float(d)));
@@ -135,27 +135,21 @@ SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, 
 }
 
 // ---- hardware path ----------------------------------------------------------------------------------
-SKY_D float4 sample2d_hw(const MipView& t, float u, float v, float lod) {
-    int level = select_mip_level(lod, t.levels);
+SKY_D float4 sample2d_hw(const MipView& t, float u, float v, int level) {
     return level < 0 ? tex2DLod<float4>(t.tex_linear, u, v, 0.0f) : tex2DLod<float4>(t.tex_point, u, v, float(level));
 }
-SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, float lod) {
-    int level = select_mip_level(lod, t.levels);
+SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, int level) {
     return level < 0 ? tex3DLod<float>(t.tex_linear, u, v, w, 0.0f) : tex3DLod<float>(t.tex_point, u, v, w, float(level));
 }
 
 // ---- SampleSigmaT ------------------------------------------------------------------------------------
-// VolumetricCloudDefaultMaterialCommon.glsl:20-24
-SKY_D float4 GetUVWLod(float3 pos, const SkySampleInfo& info, float3 camera_pos, float lod_bias) {
-    float lod = log2f(info.k_lod * distance(pos, camera_pos)) + lod_bias;
-    return f4(pos.x * info.frequency + info.bias[0], pos.y * info.frequency + info.bias[1], pos.z * info.frequency, lod);
-}
 // VolumetricCloudDefaultMaterial0.glsl:9-16
 SKY_D float CalHeightMask(float cloud_type, float height01) {
     float height_in_type = clampf(height01 / cloud_type, 0.0f, 1.0f);
     return clampf(height_in_type * (height_in_type - 1.0f) * -4.0f, 0.0f, 1.0f);
 }
 SKY_D float Remap01(float x, float x0, float x1) { return clampf((x - x0) / (x1 - x0), 0.0f, 1.0f); }
+SKY_D float distance2(float3 a, float3 b) { float3 d = a - b; return dot(d, d); }
 
 // MAT: SkyMaterialType.  `fetches` (optional) receives the number of texture fetches issued.
 template <int MAT, bool HW>
@@ -163,50 +157,58 @@ SKY_D float SampleSigmaT(const MaterialParams& M, float3 pos, float height01, in
     if (MAT == SKY_MATERIAL_DEFAULT0) {  // VolumetricCloudDefaultMaterial0.glsl:18-32
         const SkyMaterialCommonBufferData& mc = M.m.common;
         const SkyMaterial0BufferData& m = M.m.u.m0;
-        float4 uvwlod = GetUVWLod(pos, mc.uCloudMapSampleInfo, M.camera_pos, mc.uLodBias);
+        // GetUVWLod (VolumetricCloudDefaultMaterialCommon.glsl:20-24) for the cloud map and the displacement map: same pos
+        float d2 = distance2(pos, M.camera_pos);
+        const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
+        const SkySampleInfo& di = mc.uDisplacementSampleInfo;
+        int lc = level_from_distance2(d2, ci.k_lod, mc.uLodBias, M.thr2_cloud_map, M.cloud_map.levels);
+        int ld = level_from_distance2(d2, di.k_lod, mc.uLodBias, M.thr2_displacement, M.displacement.levels);
+        float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
+        float du = pos.x * di.frequency + di.bias[0], dv = pos.y * di.frequency + di.bias[1], dw = pos.z * di.frequency;
         float cloud_type[2];
         float d0[4], d1[4];
         if (HW) {
-            float4 c = sample2d_hw(M.cloud_map, uvwlod.x, uvwlod.y, uvwlod.w);
+            float4 c = sample2d_hw(M.cloud_map, cu, cv, lc);
             cloud_type[0] = c.x; cloud_type[1] = c.y;
-        } else {
-            sample2d_repeat_exact<2>(M.cloud_map, uvwlod.x, uvwlod.y, uvwlod.w, cloud_type);
-        }
-        uvwlod = GetUVWLod(pos, mc.uDisplacementSampleInfo, M.camera_pos, mc.uLodBias);
-        if (HW) {
-            float4 a = sample2d_hw(M.displacement, uvwlod.x, uvwlod.y, uvwlod.w);
-            float4 b = sample2d_hw(M.displacement, uvwlod.x, uvwlod.z, uvwlod.w);
+            float4 a = sample2d_hw(M.displacement, du, dv, ld);
+            float4 b = sample2d_hw(M.displacement, du, dw, ld);
             d0[0] = a.x; d0[1] = a.y; d1[2] = b.z; d1[3] = b.w;
         } else {
-            sample2d_repeat_exact<4>(M.displacement, uvwlod.x, uvwlod.y, uvwlod.w, d0);
-            sample2d_repeat_exact<4>(M.displacement, uvwlod.x, uvwlod.z, uvwlod.w, d1);
+            sample2d_repeat_exact<2>(M.cloud_map, cu, cv, lc, cloud_type);
+            sample2d_repeat_exact<4>(M.displacement, du, dv, ld, d0);
+            sample2d_repeat_exact<4>(M.displacement, du, dw, ld, d1);
         }
         float3 displace_vector = f3(0.0f + d0[0] + d1[2], 0.0f + d0[1], 0.0f + d1[3]);
         pos = pos + m.uDisplacementScale * displace_vector;
-        uvwlod = GetUVWLod(pos, mc.uDetailSampleInfo, M.camera_pos, mc.uLodBias);
-        float detail = HW ? sample3d_hw(M.detail, uvwlod.x, uvwlod.y, uvwlod.z, uvwlod.w)
-                          : sample3d_repeat_exact(M.detail, uvwlod.x, uvwlod.y, uvwlod.z, uvwlod.w);
+        const SkySampleInfo& ti = mc.uDetailSampleInfo;
+        int lt = level_from_distance2(distance2(pos, M.camera_pos), ti.k_lod, mc.uLodBias, M.thr2_detail, M.detail.levels);
+        float tu = pos.x * ti.frequency + ti.bias[0], tv = pos.y * ti.frequency + ti.bias[1], tw = pos.z * ti.frequency;
+        float detail = HW ? sample3d_hw(M.detail, tu, tv, tw, lt) : sample3d_repeat_exact(M.detail, tu, tv, tw, lt);
         detail = detail * m.uDetailParam[0] + m.uDetailParam[1];
         if (fetches) *fetches += 4;
         return Remap01(cloud_type[0] * CalHeightMask(cloud_type[1], height01), detail, 1.0f) * height01 * mc.uDensity;
     } else if (MAT == SKY_MATERIAL_DEFAULT1) {  // VolumetricCloudDefaultMaterial1.glsl:14-29
         const SkyMaterialCommonBufferData& mc = M.m.common;
         const SkyMaterial1BufferData& m = M.m.u.m1;
-        float4 uvwlod = GetUVWLod(pos, mc.uCloudMapSampleInfo, M.camera_pos, mc.uLodBias);
+        float d2 = distance2(pos, M.camera_pos);
+        const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
+        int lc = level_from_distance2(d2, ci.k_lod, mc.uLodBias, M.thr2_cloud_map, M.cloud_map.levels);
+        float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
         float cloud_type[2];
         if (HW) {
-            float4 c = sample2d_hw(M.cloud_map, uvwlod.x, uvwlod.y, uvwlod.w);
+            float4 c = sample2d_hw(M.cloud_map, cu, cv, lc);
             cloud_type[0] = c.x; cloud_type[1] = c.y;
         } else {
-            sample2d_repeat_exact<2>(M.cloud_map, uvwlod.x, uvwlod.y, uvwlod.w, cloud_type);
+            sample2d_repeat_exact<2>(M.cloud_map, cu, cv, lc, cloud_type);
         }
         if (fetches) *fetches += 1;
         float density = clampf((cloud_type[0] - m.uBaseDensityThreshold) * m.uBaseEdgeHardness, 0.0f, 1.0f);
         density *= clampf((1 - height01) * m.uBaseHeightHardness, 0.0f, 1.0f);
         if (density == 0) return 0.0f;
-        uvwlod = GetUVWLod(pos, mc.uDetailSampleInfo, M.camera_pos, mc.uLodBias);
-        float detail = HW ? sample3d_hw(M.detail, uvwlod.x, uvwlod.y, uvwlod.z, uvwlod.w)
-                          : sample3d_repeat_exact(M.detail, uvwlod.x, uvwlod.y, uvwlod.z, uvwlod.w);
+        const SkySampleInfo& ti = mc.uDetailSampleInfo;
+        int lt = level_from_distance2(d2, ti.k_lod, mc.uLodBias, M.thr2_detail, M.detail.levels);
+        float tu = pos.x * ti.frequency + ti.bias[0], tv = pos.y * ti.frequency + ti.bias[1], tw = pos.z * ti.frequency;
+        float detail = HW ? sample3d_hw(M.detail, tu, tv, tw, lt) : sample3d_repeat_exact(M.detail, tu, tv, tw, lt);
         if (fetches) *fetches += 1;
         detail = (detail + m.uDetailBase) * m.uDetailScale;
         detail *= fmaxf(clampf(height01 - m.uHeightCut, 0.0f, 1.0f), clampf(m.uEdgeCur - cloud_type[0], 0.0f, 1.0f));
@@ -217,8 +219,8 @@ SKY_D float SampleSigmaT(const MaterialParams& M, float3 pos, float height01, in
         const SkyMaterialVoxelBufferData& m = M.m.u.voxel;
         float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
         float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
-        float lod = log2f(m.uSampleLodK * distance(pos, M.camera_pos)) + m.uLodBias;
-        float density = HW ? sample3d_hw(M.voxel, u, v, height01, lod) : sample3d_border_exact(M.voxel, u, v, height01, lod);
+        int level = level_from_distance2(distance2(pos, M.camera_pos), m.uSampleLodK, m.uLodBias, M.thr2_voxel, M.voxel.levels);
+        float density = HW ? sample3d_hw(M.voxel, u, v, height01, level) : sample3d_border_exact(M.voxel, u, v, height01, level);
         if (fetches) *fetches += 1;
         return density * m.uDensity;
     }

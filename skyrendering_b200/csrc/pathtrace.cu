@@ -109,8 +109,7 @@ SKY_D float2 CloudRegionIntersect(const PtParams& P, float3 ro, float3 rd) {
 }
 
 template <int MAT, bool HW, bool COUNT>
-SKY_D float SampleSigmaTAt(const PtParams& P, float3 pos, int& lookups) {  // :89-91
-    float height01 = clampf((pos.z - P.c.uBottomAltitude) / (P.c.uTopAltitude - P.c.uBottomAltitude), 0.0f, 1.0f);
+SKY_D float SampleSigmaTAt(const PtParams& P, float3 pos, float inv_thickness, int& lookups) {  // :89-91
     if (MAT == SKY_MATERIAL_VOXEL) {
         // exact empty-space skip: with CLAMP_TO_BORDER(0) every tap of every level is the border here
         const SkyMaterialVoxelBufferData& m = P.mat.m.u.voxel;
@@ -120,6 +119,7 @@ SKY_D float SampleSigmaTAt(const PtParams& P, float3 pos, int& lookups) {  // :8
         if (u < -hu || u > 1.0f + hu || v < -hv || v > 1.0f + hv) return 0.0f;
     }
     if (COUNT) ++lookups;
+    float height01 = clampf((pos.z - P.c.uBottomAltitude) * inv_thickness, 0.0f, 1.0f);
     return SampleSigmaT<MAT, HW>(P.mat, pos, height01);
 }
 
@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__
     const float3 camera = f3(P.c.uCameraPos);
     const float3 sun = f3(P.c.uSunDirection);
     const float sigma_t_max = P.pt.sigma_t_max;
+    const float inv_sigma_t_max = 1.0f / sigma_t_max;
+    const float inv_thickness = 1.0f / (P.c.uTopAltitude - P.c.uBottomAltitude);
     const unsigned int lane = threadIdx.x & 31u;
 
     int state = ST_FETCH;
@@ -254,18 +256,19 @@ __global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__
 
         // ---------------------------------------------------------------- hot block: one tentative collision
         if (state == ST_TRACK) {
+            // divisions by the constant majorant are multiplications by its reciprocal (what a GLSL compiler emits)
             const float3 dir = in_shadow ? sun : rd;
-            t += -logf(1.0f - Random01<PRNG_KIND>(seed)) / sigma_t_max;  // InfiniteTransmittanceIS, :82-84
+            t += -logf(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
             if (t > t_max) {
                 state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
             } else {
-                float sigma_t = SampleSigmaTAt<MAT, HW, COUNT>(P, ro + dir * t, lookups);
+                float sigma_t = SampleSigmaTAt<MAT, HW, COUNT>(P, ro + dir * t, inv_thickness, lookups);
                 if (COUNT) ++collisions;
                 if (in_shadow) {
-                    transmittance *= 1.0f - fmaxf(0.0f, sigma_t / sigma_t_max);  // :148
+                    transmittance *= 1.0f - fmaxf(0.0f, sigma_t * inv_sigma_t_max);  // :148
                 } else {
                     float xi = Random01<PRNG_KIND>(seed);
-                    if (xi < sigma_t / sigma_t_max) state = ST_SCATTER;  // :191-195
+                    if (xi < sigma_t * inv_sigma_t_max) state = ST_SCATTER;  // :191-195
                 }
             }
         }
