@@ -184,7 +184,7 @@ KERNEL_API = {
     "tex_peak": ([I, P(C.c_double)], I),
 }
 
-CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libskyb200.so")
+CUDA_LIB_PATH = os.environ.get("SKYB200_LIB", os.path.join(_HERE, "csrc", "libskyb200.so"))  # override: kernel A/B experiments
 HOST_LIB_PATH = os.path.join(_HERE, "host", "libskyhost.so")
 
 

@@ -13,6 +13,12 @@ namespace {
 
 constexpr float kMinTransmittance = 0.01f;  // VolumetricCloudCommon.glsl:30
 
+// K16: clear-air steps a lane may take per trip before the warp shades its pending dense steps
+#ifndef SKY_K16_MARCH_STEPS
+#define SKY_K16_MARCH_STEPS 4
+#endif
+constexpr int kMarchSteps = SKY_K16_MARCH_STEPS;
+
 struct CloudParams {
     SkyCloudCommonBufferData c;  // VolumetricCloudCommon.glsl:6-28
     SkyCloudBufferData b;        // VolumetricCloudRender.comp:17-32
@@ -290,10 +296,7 @@ SKY_D float SampleShadow(const CloudParams& P, float3 pos, int& evals, int& fetc
 }
 
 template <int MAT, bool HW, bool COUNT>
-SKY_D void RayMarchStep(const CloudParams& P, RayMarchContext& ctx, int& evals, int& fetches) {  // :116-137
-    float sigma_t = SampleSigmaT<MAT, HW>(P.mat, ctx.pos, ctx.height01, COUNT ? &fetches : nullptr);
-    if (COUNT) ++evals;
-    if (sigma_t < 1e-5f) return;
+SKY_D void ShadeDenseStep(const CloudParams& P, RayMarchContext& ctx, float sigma_t, int& evals, int& fetches) {  // :120-136
     float tr = expf(-ctx.step_size * sigma_t);
     float transmittance_to_sun = SampleShadow<MAT, HW, COUNT>(P, ctx.pos, evals, fetches);
     float phase = mixf(HenyeyGreenstein(ctx.cos_sun_view, -0.15f) * 2.16f, HenyeyGreenstein(ctx.cos_sun_view, 0.85f),
@@ -322,7 +325,11 @@ __global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudP
         int local_band = row_in_band / P.band_rows;
         py = (local_band * P.band_count + P.band_index) * P.band_rows + row_in_band % P.band_rows;
     }
-    if (px >= QW || py >= QH) return;
+    // lanes past the image edge march a clamped duplicate ray and skip the stores: every lane reaches the
+    // warp votes of the marching loop
+    const bool valid = px < QW && py < QH;
+    px = min(px, QW - 1);
+    py = min(py, QH - 1);
     uint32_t index = uint32_t(__ldg(P.index_linear + size_t(py) * QW + px).x);
     int2 off = IndexToOffset(index);
     int cx = px * 2 + off.x, cy = py * 2 + off.y;
@@ -386,25 +393,54 @@ __global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudP
     float noise = blue_noise_at(P.blue_noise, px, py);
     float jitter = fractf(noise + c.uFrameID * 0.61803398875f);
     ctx.t = i0t1 + ctx.step_size * jitter;
-    for (uint32_t cnt = num_steps; cnt != 0; cnt--, ctx.t += ctx.step_size) {
-        ctx.pos = camera + view_dir * ctx.t;  // UpdateContext, :90-93
-        ctx.height01 = CalHeight01(P, ctx.pos);
-        RayMarchStep<MAT, HW, COUNT>(P, ctx, evals, fetches);
-        if (ctx.transmittance < kMinTransmittance) break;
-    }
+    // The two step loops of :170-188, run as two convergent phases per trip: (A) up to kMarchSteps steps
+    // that find no cloud (one SampleSigmaT each), stopping at the first step with cloud in it; (B) the
+    // shading of that step (5-tap shadow march + phase functions).  A lane's own sequence of operations is
+    // exactly the shader's, but lanes crossing clear air no longer idle through their neighbours' shadow
+    // marches, and the shadow marches of a warp run together.
     float dist1 = i1t2 - i1t1;
-    if (dist1 > 0) {
-        dist1 = fminf(dist1, b.uMaxRaymarchDistance);
-        uint32_t num_steps1 = uint32_t(fmaxf(b.uMaxRaymarchSteps * (dist1 / b.uMaxRaymarchDistance), 1.0f));
-        ctx.step_size = dist1 / float(num_steps1);
-        ctx.t = i1t1 + ctx.step_size * jitter;
-        for (uint32_t cnt = num_steps1; cnt != 0; cnt--, ctx.t += ctx.step_size) {
-            ctx.pos = camera + view_dir * ctx.t;
-            ctx.height01 = CalHeight01(P, ctx.pos);
-            RayMarchStep<MAT, HW, COUNT>(P, ctx, evals, fetches);
-            if (ctx.transmittance < kMinTransmittance) break;
+    uint32_t cnt = num_steps;
+    int segment = 0;
+    bool marching = true, dense_pending = false;
+    float dense_sigma = 0.0f;
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, marching)) {
+        if (marching && !dense_pending) {
+#pragma unroll 1
+            for (int k = 0; k < kMarchSteps; ++k) {
+                if (cnt == 0) {  // the segment's for loop ended (count exhausted or `break`)
+                    if (segment == 0 && dist1 > 0) {
+                        segment = 1;
+                        float d1 = fminf(dist1, b.uMaxRaymarchDistance);
+                        cnt = uint32_t(fmaxf(b.uMaxRaymarchSteps * (d1 / b.uMaxRaymarchDistance), 1.0f));
+                        ctx.step_size = d1 / float(cnt);
+                        ctx.t = i1t1 + ctx.step_size * jitter;
+                    } else {
+                        marching = false;
+                        break;
+                    }
+                }
+                ctx.pos = camera + view_dir * ctx.t;  // UpdateContext, :90-93
+                ctx.height01 = CalHeight01(P, ctx.pos);
+                float sigma_t = SampleSigmaT<MAT, HW>(P.mat, ctx.pos, ctx.height01, COUNT ? &fetches : nullptr);  // :117
+                if (COUNT) ++evals;
+                if (!(sigma_t < 1e-5f)) {  // :118-119
+                    dense_pending = true;
+                    dense_sigma = sigma_t;
+                    break;
+                }
+                if (ctx.transmittance < kMinTransmittance) cnt = 0;  // :173 / :185 `break`
+                else { cnt--; ctx.t += ctx.step_size; }
+            }
+        }
+        if (marching && dense_pending) {
+            dense_pending = false;
+            ShadeDenseStep<MAT, HW, COUNT>(P, ctx, dense_sigma, evals, fetches);  // :120-136
+            if (ctx.transmittance < kMinTransmittance) cnt = 0;
+            else { cnt--; ctx.t += ctx.step_size; }
         }
     }
+    if (!valid) return;
     float average_t = ctx.weighted_t_sum == 0 ? frag_dist : ctx.weighted_t_sum / ctx.transmittance_sum;
     P.cloud_distance[size_t(py) * QW + px] = average_t;
     float3 average_pos = camera + view_dir * average_t;
@@ -601,6 +637,22 @@ __global__ void __launch_bounds__(256) k_tex_peak(cudaTextureObject_t tex, int i
     if (acc == -1.0f) sink[tid] = acc;
 }
 
+// mode 2: coherent bilinear fetches of the RG8 weather map (the 2-D fetches of the default materials)
+__global__ void __launch_bounds__(256) k_tex_peak2d(cudaTextureObject_t tex, int iters, float* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.0f;
+    float u = float(tid & 511) * (1.0f / 512.0f), v = float((tid >> 9) & 511) * (1.0f / 512.0f);
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u += 0.0009765625f; v += 0.000244140625f;
+            float4 t = tex2DLod<float4>(tex, u, v, 0.0f);
+            acc += t.x + t.y;
+        }
+    }
+    if (acc == -1.0f) sink[tid] = acc;
+}
+
 CloudParams make_cloud_params(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
     CloudParams P{};
     P.c = c;
@@ -743,7 +795,8 @@ int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
         SKY_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-        k_tex_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->detail.view.tex_linear, iters, mode, nullptr);
+        if (mode == 2) k_tex_peak2d<<<blocks, threads, 0, ctx->stream>>>(ctx->cloud_map.view.tex_linear, iters, nullptr);
+        else k_tex_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->detail.view.tex_linear, iters, mode, nullptr);
         SKY_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
         SKY_CUDA(ctx, cudaEventSynchronize(e1));
         float ms = 0.0f;

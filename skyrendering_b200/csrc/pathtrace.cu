@@ -108,17 +108,20 @@ SKY_D float2 CloudRegionIntersect(const PtParams& P, float3 ro, float3 rd) {
     return t;
 }
 
-template <int MAT, bool HW, bool COUNT>
-SKY_D float SampleSigmaTAt(const PtParams& P, float3 pos, float inv_thickness, int& lookups) {  // :89-91
-    if (MAT == SKY_MATERIAL_VOXEL) {
-        // exact empty-space skip: with CLAMP_TO_BORDER(0) every tap of every level is the border here
-        const SkyMaterialVoxelBufferData& m = P.mat.m.u.voxel;
-        float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
-        float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
-        float hu = 0.5f / float(P.mat.voxel.w[0]), hv = 0.5f / float(P.mat.voxel.h[0]);
-        if (u < -hu || u > 1.0f + hu || v < -hv || v > 1.0f + hv) return 0.0f;
-    }
-    if (COUNT) ++lookups;
+// Exact empty-space test: for the voxel material with CLAMP_TO_BORDER(0), every tap of every mip level is
+// the border when (u, v) is more than half a level-0 texel outside [0, 1], so sigma_t == 0 without a fetch.
+template <int MAT>
+SKY_D bool ProvablyEmpty(const PtParams& P, float3 pos) {
+    if (MAT != SKY_MATERIAL_VOXEL) return false;
+    const SkyMaterialVoxelBufferData& m = P.mat.m.u.voxel;
+    float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
+    float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
+    float hu = 0.5f / float(P.mat.voxel.w[0]), hv = 0.5f / float(P.mat.voxel.h[0]);
+    return u < -hu || u > 1.0f + hu || v < -hv || v > 1.0f + hv;
+}
+
+template <int MAT, bool HW>
+SKY_D float SampleSigmaTAt(const PtParams& P, float3 pos, float inv_thickness) {  // :89-91
     float height01 = clampf((pos.z - P.c.uBottomAltitude) * inv_thickness, 0.0f, 1.0f);
     return SampleSigmaT<MAT, HW>(P.mat, pos, height01);
 }
@@ -167,9 +170,22 @@ enum : int {
     ST_IDLE           // no jobs left
 };
 
+// tuning knobs of the tracking phases (measured on B200, see profiles/): rounds per trip around the state
+// machine, provably-empty collisions per round, resident blocks per SM the register budget is cut for
+#ifndef SKY_K19_TRACK_ROUNDS
+#define SKY_K19_TRACK_ROUNDS 8  // 1/1: 17.3, 4/4: 20.7, 8/4: 21.1, 8/8: 16.8, 4/16: 11.9 Msamples/s (720p, 8 spp)
+#endif
+#ifndef SKY_K19_EMPTY_STEPS
+#define SKY_K19_EMPTY_STEPS 4
+#endif
+#ifndef SKY_K19_OCC
+#define SKY_K19_OCC 6
+#endif
+constexpr int kTrackRounds = SKY_K19_TRACK_ROUNDS, kEmptySteps = SKY_K19_EMPTY_STEPS;
+
 // K19 -- :160-284 as a per-lane state machine; see the header of this file.
 template <int MAT, bool HW, int PRNG_KIND, bool COUNT>
-__global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__ PtParams P) {
+__global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_constant__ PtParams P) {
     const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
     const int tiles_x = (rw + 7) >> 3, tiles_y = (rh + 3) >> 2;  // jobs walk the region in 8x4 pixel tiles so a warp starts on one tile
     const unsigned int npix = (unsigned int)rw * (unsigned int)rh;                  // sample-slot stride per frame
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__
     float3 L = f3(0.0f), throughput = f3(1.0f), light = f3(0.0f), bsdf = f3(0.0f);
     float t = 0.0f, t_max = 0.0f, transmittance = 1.0f, scattered_t = 0.0f;
     int istep = 0;
-    bool has_scattered = false, in_shadow = false, after_ground = false;
+    bool has_scattered = false, in_shadow = false, after_ground = false, lookup_pending = false;
     int lookups = 0, collisions = 0, paths = 0;
 
     for (;;) {
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__
                             rd = normalize(frag_pos - camera);
                             ro = camera;
                             L = f3(0.0f); throughput = f3(1.0f);
-                            has_scattered = false; in_shadow = false; istep = 0; scattered_t = 0.0f;
+                            has_scattered = false; in_shadow = false; lookup_pending = false; istep = 0; scattered_t = 0.0f;
                             if (COUNT) ++paths;
                             float2 camera_inter_t = CloudRegionIntersect(P, ro, rd);  // :166-170
                             if (camera_inter_t.x >= camera_inter_t.y) {
@@ -254,16 +270,38 @@ __global__ void __launch_bounds__(128, 4) k19_path_trace(const __grid_constant__
             }
         }
 
-        // ---------------------------------------------------------------- hot block: one tentative collision
-        if (state == ST_TRACK) {
-            // divisions by the constant majorant are multiplications by its reciprocal (what a GLSL compiler emits)
+        // ---------------------------------------------------------------- hot block: tentative collisions
+        // kTrackRounds rounds of (A) up to kEmptySteps collisions that provably land on zero density -- they
+        // only advance t and the random stream -- and (B) one collision that needs a density lookup.  Both
+        // phases are short convergent loops, so the fetch / transition blocks around them are amortised over
+        // many collisions and empty-space lanes do not wait on the lookups of lanes inside the cloud.
+        // Divisions by the constant majorant are multiplications by its reciprocal (what a GLSL compiler emits).
+#pragma unroll 1
+        for (int round = 0; round < kTrackRounds; ++round) {
+            if (!__any_sync(0xffffffffu, state == ST_TRACK)) break;
             const float3 dir = in_shadow ? sun : rd;
-            t += -logf(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
-            if (t > t_max) {
-                state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
-            } else {
-                float sigma_t = SampleSigmaTAt<MAT, HW, COUNT>(P, ro + dir * t, inv_thickness, lookups);
-                if (COUNT) ++collisions;
+            if (state == ST_TRACK && !lookup_pending) {
+#pragma unroll 1
+                for (int e = 0; e < kEmptySteps; ++e) {
+                    t += -logf(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
+                    if (t > t_max) {
+                        state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
+                        break;
+                    }
+                    if (COUNT) ++collisions;
+                    if (!ProvablyEmpty<MAT>(P, ro + dir * t)) {
+                        lookup_pending = true;
+                        break;
+                    }
+                    // sigma_t == 0: the shadow ray multiplies by 1 (:148); the free flight draws xi and
+                    // compares it with 0 (:191-192), which never scatters
+                    if (!in_shadow) seed = PRNG<PRNG_KIND>(seed);
+                }
+            }
+            if (state == ST_TRACK && lookup_pending) {
+                lookup_pending = false;
+                float sigma_t = SampleSigmaTAt<MAT, HW>(P, ro + dir * t, inv_thickness);
+                if (COUNT) ++lookups;
                 if (in_shadow) {
                     transmittance *= 1.0f - fmaxf(0.0f, sigma_t * inv_sigma_t_max);  // :148
                 } else {

@@ -1,0 +1,17 @@
+"""Times K19 (1280x720, reference defaults) for the library named by SKYB200_LIB. Experiment helper."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from skyrendering_b200 import abi
+from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
+r = Renderer("c5", 1280, 720)
+r.ctx.set_hw_filtering(bool(int(os.environ.get("HW", "0"))))
+r.upload_voxels(synthetic_voxel_grid()); r.prime()
+common, cloud, _ = r.cloud_update(0.0)
+r.ctx.cloud_shadow(common); r.atmosphere_render_luts(); r.path_trace_begin()
+for spp in (2, 8):
+    r.ctx.pt_samples(common, 1, spp, [0, 0, 1280, 720]); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); r.ctx.pt_samples(common, 1, spp, [0, 0, 1280, 720]); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"{os.environ.get('SKYB200_LIB','default').split('/')[-1]} HW={os.environ.get('HW','0')} spp={spp}: {ms:.1f} ms  {1280*720*spp/ms/1e3:.2f} Msamples/s", flush=True)
