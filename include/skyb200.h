@@ -88,6 +88,23 @@ int SKY_FN(cloud_frame_begin)(SkyContext* ctx, const SkyCloudCommonBufferData* c
                               int band_rows, int band_index, int band_count);
 int SKY_FN(cloud_frame_end)(SkyContext* ctx, const float* depth_dev, void* hdr_dev);
 
+/* Tile-sharded K16 fused with its exchange over peer memory (NVLink / NVSwitch), one process per GPU.
+ * sky_peer_export fills the CUDA IPC handles of this context's K16 outputs and of its arrival flags;
+ * the host exchanges them (any transport) and hands all ranks' handles to sky_peer_attach.  From then
+ * on cloud_frame_begin with band_count == world stores every texel it renders into EVERY rank's
+ * SKY_RES_CLOUD_RENDER / SKY_RES_CLOUD_DISTANCE (plain stores to mapped peer pointers inside K16), and
+ * cloud_frame_end first publishes this rank's arrival flag to all peers and waits for theirs on the
+ * device -- no host synchronisation, no separate all-gather. */
+typedef struct SkyPeerHandles {
+    unsigned char render[64];    /* cudaIpcMemHandle_t of half4[H/4][W/4] */
+    unsigned char distance[64];  /* cudaIpcMemHandle_t of float[H/4][W/4] */
+    unsigned char flags[64];     /* cudaIpcMemHandle_t of unsigned int[SKY_MAX_PEERS] */
+} SkyPeerHandles;
+#define SKY_MAX_PEERS 8
+int SKY_FN(peer_export)(SkyContext* ctx, SkyPeerHandles* out);
+int SKY_FN(peer_attach)(SkyContext* ctx, int rank, int world_size, const SkyPeerHandles* all_ranks);
+int SKY_FN(peer_detach)(SkyContext* ctx);
+
 /* cloud_frame with HOST buffers: copies depth and hdr in, runs the frame, copies hdr out and
  * synchronises -- the call a host application without device pointers makes. */
 int SKY_FN(cloud_frame_host)(SkyContext* ctx, const SkyCloudCommonBufferData* common,

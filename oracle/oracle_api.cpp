@@ -317,6 +317,9 @@ int orc_counters_enable(SkyContext* ctx, int enable) {
     return 0;
 }
 
+int orc_peer_export(SkyContext* ctx, SkyPeerHandles*) { return fail(ctx, "peer memory is a CUDA feature"); }
+int orc_peer_attach(SkyContext* ctx, int, int, const SkyPeerHandles*) { return fail(ctx, "peer memory is a CUDA feature"); }
+int orc_peer_detach(SkyContext*) { return 0; }
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
 int orc_tex_peak(SkyContext* ctx, int, double*) { return fail(ctx, "tex_peak is a GPU microbenchmark"); }
 

@@ -172,6 +172,9 @@ KERNEL_API = {
     "cloud_frame_begin": ([P(CloudCommonBufferData), P(CloudBufferData), _VOIDP, I, I, I], I),
     "cloud_frame_end": ([_VOIDP, _VOIDP], I),
     "cloud_frame_host": ([P(CloudCommonBufferData), P(CloudBufferData), _VOIDP, _VOIDP], I),
+    "peer_export": ([_VOIDP], I),
+    "peer_attach": ([I, I, _VOIDP], I),
+    "peer_detach": ([], I),
     "pt_begin": ([P(PathTracingInit)], I),
     "pt_samples": ([P(CloudCommonBufferData), U, U, P(I * 4)], I),
     "pt_resolve": ([U, _VOIDP], I),
@@ -299,6 +302,18 @@ class Context:
 
     def cloud_frame_end(self, depth, hdr): self._call("cloud_frame_end", _ptr(depth), _ptr(hdr))
     def cloud_frame_host(self, common, cloud, depth, hdr): self._call("cloud_frame_host", C.byref(common), C.byref(cloud), _ptr(depth), _ptr(hdr))
+    def peer_export(self):
+        """192 bytes: the CUDA IPC handles of this context's K16 outputs and arrival flags (SkyPeerHandles)."""
+        buf = C.create_string_buffer(192)
+        self._call("peer_export", buf)
+        return buf.raw
+
+    def peer_attach(self, rank, world_size, all_handles):
+        blob = b"".join(all_handles)
+        assert len(blob) == 192 * world_size
+        self._call("peer_attach", rank, world_size, C.c_char_p(blob))
+
+    def peer_detach(self): self._call("peer_detach")
     def pt_begin(self, init): self._call("pt_begin", C.byref(init))
 
     def pt_samples(self, common, frame_begin, count, region):

@@ -155,6 +155,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     if (ctx->stage_hdr) cudaFree(ctx->stage_hdr);
     if (ctx->pt_samples) cudaFree(ctx->pt_samples);
     if (ctx->pt_job_counter) cudaFree(ctx->pt_job_counter);
+    sky_peer_detach(ctx);
+    if (ctx->my_flags) cudaFree(ctx->my_flags);
     delete ctx;
 }
 
@@ -173,6 +175,7 @@ int sky_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
 
 int sky_set_viewport(SkyContext* ctx, int w, int h) {
     if (w < 12 || h < 12) return sky_fail(ctx, "viewport too small");
+    sky_peer_detach(ctx);  // the exported buffers are about to be reallocated
     ctx->width = w; ctx->height = h;
     int rc = 0;  // VolumetricCloud.cpp:120-136; histories zero-filled
     rc |= sky_alloc(ctx, ctx->checkerboard_depth, w / 2, h / 2);
@@ -253,6 +256,64 @@ int sky_cloud_frame(SkyContext* ctx, const SkyCloudCommonBufferData* common, con
 int sky_cloud_frame_end(SkyContext* ctx, const float* depth, void* hdr) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr));
+}
+
+int sky_peer_detach(SkyContext* ctx) {
+    for (int k = 0; k < ctx->peer_world; ++k) {
+        if (k == ctx->peer_rank) continue;
+        if (ctx->peer_render[k]) cudaIpcCloseMemHandle(ctx->peer_render[k]);
+        if (ctx->peer_distance[k]) cudaIpcCloseMemHandle(ctx->peer_distance[k]);
+        if (ctx->peer_flags[k]) cudaIpcCloseMemHandle(ctx->peer_flags[k]);
+    }
+    for (int k = 0; k < SKY_MAX_PEERS; ++k) { ctx->peer_render[k] = nullptr; ctx->peer_distance[k] = nullptr; ctx->peer_flags[k] = nullptr; }
+    ctx->peer_rank = 0; ctx->peer_world = 1; ctx->peer_band_frame = false;
+    return 0;
+}
+
+int sky_peer_export(SkyContext* ctx, SkyPeerHandles* out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "SkyPeerHandles carries 64-byte IPC handles");
+    if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
+    if (!ctx->my_flags) {
+        // [0, 8): "rows arrived" epochs, [8, 16): "finished reading" epochs, one slot per peer
+        SKY_CUDA(ctx, cudaMalloc(&ctx->my_flags, 2 * SKY_MAX_PEERS * sizeof(unsigned int)));
+        SKY_CUDA(ctx, cudaMemset(ctx->my_flags, 0, 2 * SKY_MAX_PEERS * sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t h;
+    SKY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->render_texture.p));
+    std::memcpy(out->render, &h, 64);
+    SKY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->cloud_distance.p));
+    std::memcpy(out->distance, &h, 64);
+    SKY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->my_flags));
+    std::memcpy(out->flags, &h, 64);
+    return 0;
+}
+
+int sky_peer_attach(SkyContext* ctx, int rank, int world_size, const SkyPeerHandles* all) {
+    if (world_size < 1 || world_size > SKY_MAX_PEERS || rank < 0 || rank >= world_size) return sky_fail(ctx, "bad rank / world size");
+    if (!ctx->my_flags) return sky_fail(ctx, "peer_export must be called first");
+    sky_peer_detach(ctx);
+    ctx->peer_rank = rank; ctx->peer_world = world_size;
+    for (int k = 0; k < world_size; ++k) {
+        if (k == rank) {
+            ctx->peer_render[k] = ctx->render_texture.p;
+            ctx->peer_distance[k] = ctx->cloud_distance.p;
+            ctx->peer_flags[k] = ctx->my_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        void* p = nullptr;
+        std::memcpy(&h, all[k].render, 64);
+        SKY_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_render[k] = static_cast<half4*>(p);
+        std::memcpy(&h, all[k].distance, 64);
+        SKY_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_distance[k] = static_cast<float*>(p);
+        std::memcpy(&h, all[k].flags, 64);
+        SKY_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_flags[k] = static_cast<unsigned int*>(p);
+    }
+    // peer_epoch keeps counting across re-attachments: flags only ever grow
+    return 0;
 }
 
 int sky_cloud_frame_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,

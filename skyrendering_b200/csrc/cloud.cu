@@ -46,6 +46,10 @@ struct CloudParams {
     half4* hdr;
     int band_rows, band_index, band_count;
     float inv_thickness;  // 1 / (uTopAltitude - uBottomAltitude)
+    // K16 output replicas in peer memory (every rank's buffers, own included); peer_count == 0: local only
+    half4* peer_render[8];
+    float* peer_distance[8];
+    int peer_count;
 };
 
 SKY_D float DepthToLinearDepth(const SkyCloudCommonBufferData& c, float depth) {  // VolumetricCloudCommon.glsl:32-34
@@ -442,7 +446,6 @@ __global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudP
     }
     if (!valid) return;
     float average_t = ctx.weighted_t_sum == 0 ? frag_dist : ctx.weighted_t_sum / ctx.transmittance_sum;
-    P.cloud_distance[size_t(py) * QW + px] = average_t;
     float3 average_pos = camera + view_dir * average_t;
     // GetSunVisibility(pos), VolumetricCloudCommon.glsl:73-79
     float3 up_dir = f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius);
@@ -470,7 +473,20 @@ __global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudP
     float fade = smoothstepf(b.uMaxVisibleDistance * 0.75f, b.uMaxVisibleDistance, i0t1);
     ctx.transmittance = mixf(ctx.transmittance, 1.0f, fade);
     luminance *= 1 - ctx.transmittance;
-    P.render[size_t(py) * QW + px] = to_half4(f4(luminance, ctx.transmittance));
+    const half4 texel = to_half4(f4(luminance, ctx.transmittance));
+    const size_t at = size_t(py) * QW + px;
+    if (P.peer_count == 0) {
+        P.render[at] = texel;
+        P.cloud_distance[at] = average_t;
+    } else {
+        // the exchange step of a tile-sharded frame, fused into the producer: plain stores to every rank's
+        // copy over NVLink (12 B per ray and rank); k_peer_arrive_and_wait orders them before K17
+#pragma unroll 1
+        for (int k = 0; k < P.peer_count; ++k) {
+            P.peer_render[k][at] = texel;
+            P.peer_distance[k][at] = average_t;
+        }
+    }
 
     if (COUNT) {  // counting variant is never the timed one
         atomicAdd(P.counters + SKY_CNT_RENDER_SIGMA_EVALS, (unsigned long long)evals);
@@ -637,6 +653,35 @@ __global__ void __launch_bounds__(256) k_tex_peak(cudaTextureObject_t tex, int i
     if (acc == -1.0f) sink[tid] = acc;
 }
 
+// Cross-GPU arrival barrier of a tile-sharded frame.  Runs after K16 on the same stream: thread k tells rank
+// k "rank `rank` has stored all its rows of frame `epoch` into your buffers" and waits for rank k's own
+// message.  Epochs only grow, so a late reader never sees a stale match.
+// Two flag sets per rank: [0, 8) "rows of frame e arrived", [8, 16) "I finished reading frame e" -- the second
+// one keeps a fast rank from overwriting a slow rank's copy while its K17 is still reading it.
+struct PeerBarrierParams {
+    unsigned int* peer_flags[8];
+    unsigned int* my_flags;
+    int rank, world;
+    unsigned int epoch;
+    int offset;      // 0: arrival flags, 8: done flags
+    int signal, wait;
+};
+__global__ void __launch_bounds__(32) k_peer_flags(const __grid_constant__ PeerBarrierParams P) {
+    int k = threadIdx.x;
+    if (k < P.world) {
+        if (P.signal) {
+            __threadfence_system();  // this stream's earlier kernels (K16's peer stores / K17's reads) first
+            volatile unsigned int* theirs = P.peer_flags[k] + P.offset + P.rank;
+            *theirs = P.epoch;
+        }
+        if (P.wait) {
+            volatile unsigned int* mine = P.my_flags + P.offset + k;
+            while (*mine < P.epoch) __nanosleep(200);
+            __threadfence_system();
+        }
+    }
+}
+
 // mode 2: coherent bilinear fetches of the RG8 weather map (the 2-D fetches of the default materials)
 __global__ void __launch_bounds__(256) k_tex_peak2d(cudaTextureObject_t tex, int iters, float* sink) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -753,7 +798,24 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
     k15_index_gen<<<dim3(ceil_div(QW, 128), QH), 128, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     int rows = QH;
+    ctx->peer_band_frame = false;
     if (band_rows > 0 && band_count > 1) {
+        if (ctx->peer_world == band_count && ctx->peer_rank == band_index && ctx->my_flags) {
+            // peers attached: K16 stores its rows into every rank's copy (fused exchange)
+            P.peer_count = ctx->peer_world;
+            for (int k = 0; k < ctx->peer_world; ++k) { P.peer_render[k] = ctx->peer_render[k]; P.peer_distance[k] = ctx->peer_distance[k]; }
+            ctx->peer_band_frame = true;
+            if (ctx->peer_epoch > 0) {
+                // nobody may still be reading the previous frame's exchanged buffers when K16 overwrites them
+                PeerBarrierParams B{};
+                for (int k = 0; k < ctx->peer_world; ++k) B.peer_flags[k] = ctx->peer_flags[k];
+                B.my_flags = ctx->my_flags; B.rank = ctx->peer_rank; B.world = ctx->peer_world; B.epoch = ctx->peer_epoch;
+                B.offset = 8; B.signal = 0; B.wait = 1;
+                k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+                SKY_LAUNCH_CHECK(ctx);
+            }
+            ++ctx->peer_epoch;
+        }
         P.band_rows = band_rows; P.band_index = band_index; P.band_count = band_count;
         int bands_total = ceil_div(QH, band_rows);
         int my_bands = (bands_total - band_index + band_count - 1) / band_count;
@@ -778,7 +840,22 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
     P.reconstruct_out = ctx->reconstruct[0].p;
     P.reconstruct_prev = ctx->reconstruct[1].p;
     const int HW_ = P.width / 2, HH = P.height / 2;
+    const bool peer_frame = ctx->peer_band_frame;
+    PeerBarrierParams B{};
+    if (peer_frame) {
+        for (int k = 0; k < ctx->peer_world; ++k) B.peer_flags[k] = ctx->peer_flags[k];
+        B.my_flags = ctx->my_flags; B.rank = ctx->peer_rank; B.world = ctx->peer_world; B.epoch = ctx->peer_epoch;
+        B.offset = 0; B.signal = 1; B.wait = 1;  // my rows are everywhere; wait for everybody else's
+        k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+        SKY_LAUNCH_CHECK(ctx);
+        ctx->peer_band_frame = false;
+    }
     k17_reconstruct<<<dim3(ceil_div(HW_, 16), ceil_div(HH, 8)), 128, 0, ctx->stream>>>(P);
+    if (peer_frame) {
+        B.offset = 8; B.signal = 1; B.wait = 0;  // K17 was the last reader of the exchanged buffers
+        k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+        SKY_LAUNCH_CHECK(ctx);
+    }
     SKY_LAUNCH_CHECK(ctx);
     k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(P.height, 8)), 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);

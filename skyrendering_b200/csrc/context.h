@@ -88,6 +88,15 @@ struct SkyContext {
 
     unsigned long long* counters = nullptr;  // SkyCounter slots
 
+    // peer-memory exchange of the K16 outputs (sky_peer_attach)
+    int peer_rank = 0, peer_world = 1;
+    half4* peer_render[8] = {};      // [rank] -> that rank's render_texture (own entry = local pointer)
+    float* peer_distance[8] = {};
+    unsigned int* peer_flags[8] = {};  // [rank] -> that rank's arrival flags
+    unsigned int* my_flags = nullptr;  // unsigned int[8], written by peers
+    unsigned int peer_epoch = 0;
+    bool peer_band_frame = false;      // the open frame rendered bands into peer memory
+
     // staging for *_host entry points
     float* stage_depth = nullptr;
     half4* stage_hdr = nullptr;

@@ -30,9 +30,11 @@ SKY_D int select_mip_level(float lod, int levels) {
     return clampi(d, 0, q);
 }
 // level for lambda = log2(k_lod * sqrt(d2)) + bias (GetUVWLod, VolumetricCloudDefaultMaterialCommon.glsl:20-24)
+// Minified case: log2(k * sqrt(d2)) = 0.5 * log2(k^2 * d2), one MUFU.LG2 (2^-22 relative error moves a level
+// boundary by less than a millimetre of camera distance).
 SKY_D int level_from_distance2(float d2, float k_lod, float lod_bias, float thr2, int levels) {
     if (d2 <= thr2) return -1;
-    return select_mip_level(log2f(k_lod * sqrtf(d2)) + lod_bias, levels);
+    return select_mip_level(0.5f * __log2f(k_lod * k_lod * d2) + lod_bias, levels);
 }
 
 // ---- exact path ---------------------------------------------------------------------------------------
@@ -145,10 +147,10 @@ SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, int level) 
 // ---- SampleSigmaT ------------------------------------------------------------------------------------
 // VolumetricCloudDefaultMaterial0.glsl:9-16
 SKY_D float CalHeightMask(float cloud_type, float height01) {
-    float height_in_type = clampf(height01 / cloud_type, 0.0f, 1.0f);
+    float height_in_type = clampf(__fdividef(height01, cloud_type), 0.0f, 1.0f);  // same inf / NaN cases as '/'
     return clampf(height_in_type * (height_in_type - 1.0f) * -4.0f, 0.0f, 1.0f);
 }
-SKY_D float Remap01(float x, float x0, float x1) { return clampf((x - x0) / (x1 - x0), 0.0f, 1.0f); }
+SKY_D float Remap01(float x, float x0, float x1) { return clampf(__fdividef(x - x0, x1 - x0), 0.0f, 1.0f); }
 SKY_D float distance2(float3 a, float3 b) { float3 d = a - b; return dot(d, d); }
 
 // MAT: SkyMaterialType.  `fetches` (optional) receives the number of texture fetches issued.

@@ -94,11 +94,21 @@ class ShardedPathTracer:
 class ShardedCloudFrame:
     """Tile-sharded K16 with an all-gather of its two outputs; everything else replicated."""
 
-    def __init__(self, renderer, rank, world_size, band_rows=8, group=None):
+    def __init__(self, renderer, rank, world_size, band_rows=8, group=None, fused=None):
         self.r, self.rank, self.world, self.band_rows, self.group = renderer, rank, world_size, band_rows, group
         qh = renderer.height // 4
         self.rows = [band_rows_of_rank(qh, band_rows, k, world_size) for k in range(world_size)]
         self.max_rows = max(len(x) for x in self.rows)
+        # CUDA contexts exchange through peer memory inside K16 (stores over NVLink + a device-side arrival
+        # barrier); the collective path below is the portable fallback the CPU tests exercise.
+        self.fused = (renderer.ctx.L.prefix == "sky_" and world_size > 1) if fused is None else fused
+        if self.fused:
+            import torch.distributed as dist
+            mine = renderer.ctx.peer_export()
+            everyone = [None] * world_size
+            dist.all_gather_object(everyone, mine, group=group)
+            renderer.ctx.peer_attach(rank, world_size, everyone)
+            dist.barrier(group=group)
 
     def frame(self, common, cloud, depth, hdr):
         import torch
@@ -108,6 +118,9 @@ class ShardedCloudFrame:
             ctx.cloud_frame(common, cloud, depth, hdr)
             return
         ctx.cloud_frame_begin(common, cloud, depth, self.band_rows, self.rank, self.world)
+        if self.fused:
+            ctx.cloud_frame_end(depth, hdr)  # waits on the device for every rank's rows, then K17 / K18
+            return
         for res in (abi.RES_CLOUD_RENDER, abi.RES_CLOUD_DISTANCE):
             t, zc = resource_tensor(ctx, res)
             if zc:

@@ -1,0 +1,85 @@
+"""Two-GPU tests of the sharded paths over NCCL / peer memory (skipped on a single-GPU box; the same host
+logic runs over gloo in tests/test_distributed_cpu.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from skyrendering_b200 import abi
+    from skyrendering_b200.distributed import ShardedCloudFrame, ShardedPathTracer
+    from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cuda = abi.cuda_library()
+        # 4K-style frame at a smaller size: K16 bands stored into every rank's buffers over peer memory
+        w, h = 768, 432
+        r = Renderer("c3", w, h, library=cuda, device=rank)
+        r.prime()
+        depth = torch.from_numpy(r.scene.ground_depth(w, h)).cuda()
+        hdr = torch.zeros((h, w, 4), dtype=torch.float16, device="cuda")
+        scf = ShardedCloudFrame(r, rank, world, band_rows=8)
+        assert scf.fused
+        for _ in range(4):
+            hdr.zero_()
+            r.earth_update()
+            common, cloud, _ = r.cloud_update(0.0)
+            r.ctx.cloud_shadow(common)
+            r.atmosphere_render_luts()
+            r.ctx.composite(depth, hdr, w, h)
+            scf.frame(common, cloud, depth, hdr)
+        r.ctx.sync()
+        np.save(os.path.join(out_dir, f"hdr_{rank}.npy"), hdr.cpu().numpy())
+        np.save(os.path.join(out_dir, f"render_{rank}.npy"), r.ctx.read(abi.RES_CLOUD_RENDER))
+        dist.barrier()
+        # path tracer: split kFrameId range + one all-reduce
+        rp = Renderer("c5", 256, 144, library=cuda, device=rank)
+        rp.upload_voxels(synthetic_voxel_grid(63, 77, 43))
+        rp.prime()
+        common, _, _ = rp.cloud_update(0.0)
+        rp.ctx.cloud_shadow(common)
+        rp.atmosphere_render_luts()
+        rp.path_trace_begin(max_bounces=8, region_box_half_width=8.0)
+        spt = ShardedPathTracer(rp, rank, world)
+        spt.render(common, 8)
+        total = spt.reduce()
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, f"pt_{rank}.npy"), total.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_sharding_matches_single_gpu(tmp_path):
+    import torch.multiprocessing as mp
+    from skyrendering_b200 import abi
+    from tests.parity import run_cloud_frames, run_path_trace
+    from skyrendering_b200.renderer import synthetic_voxel_grid
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ref = run_cloud_frames("c3", 768, 432, abi.cuda_library(), frames=4, device="cuda")
+    for k in range(world):
+        assert np.array_equal(np.load(tmp_path / f"render_{k}.npy").astype(np.float32), ref["render"])  # rays are independent
+        assert np.array_equal(np.load(tmp_path / f"hdr_{k}.npy").astype(np.float32), ref["hdr"])
+    _, _, whole = run_path_trace("c5", 256, 144, abi.cuda_library(), 8, grid=synthetic_voxel_grid(63, 77, 43), max_bounces=8,
+                                 region_box_half_width=8.0)
+    pts = [np.load(tmp_path / f"pt_{k}.npy")[0] for k in range(world)]
+    assert np.array_equal(pts[0], pts[1])
+    assert np.allclose(pts[0], whole, rtol=1e-5, atol=1e-6)  # same streams; only the association of the fp32 sum differs
