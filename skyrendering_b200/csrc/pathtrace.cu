@@ -162,6 +162,7 @@ SKY_D float3 GetSunIlluminance(const PtParams& P, float3 pos) {  // :131-133 + V
 enum : int {
     ST_FETCH = 0,     // needs a (pixel, frame) job
     ST_SEGMENT,       // top of `while (istep < kMaxBounces && throughput > 0)`, :172
+    ST_BEGIN_TRACK,   // a tracking loop is about to start: bound the part of the ray that can see the voxel footprint
     ST_TRACK,         // inside a tracking loop (free flight :182-196 or shadow ray :142-149)
     ST_EXIT_PRIMARY,  // free flight left the box without a collision, :198-230
     ST_SCATTER,       // real collision, :231-243
@@ -182,6 +183,14 @@ enum : int {
 #define SKY_K19_OCC 6
 #endif
 constexpr int kTrackRounds = SKY_K19_TRACK_ROUNDS, kEmptySteps = SKY_K19_EMPTY_STEPS;
+// free-flight logarithm: logf (<= 1 ulp) or the MUFU.LG2-based __logf (what GLSL's log() compiles to on this hardware)
+// Measured: 20.8 -> 23.9 Msamples/s with __logf, parity against the oracle unchanged (relative RMS of the 16-spp
+// accumulator 2.16e-3 vs 2.13e-3, same 71 % bit-identical pixels): the default.
+#ifdef SKY_K19_PRECISE_LOG
+#define SKY_K19_LOG(x) logf(x)
+#else
+#define SKY_K19_LOG(x) __logf(x)
+#endif
 
 // K19 -- :160-284 as a per-lane state machine; see the header of this file.
 template <int MAT, bool HW, int PRNG_KIND, bool COUNT>
@@ -197,6 +206,18 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
     const float inv_sigma_t_max = 1.0f / sigma_t_max;
     const float inv_thickness = 1.0f / (P.c.uTopAltitude - P.c.uBottomAltitude);
     const unsigned int lane = threadIdx.x & 31u;
+    // voxel footprint in local x/y, enlarged (see ST_BEGIN_TRACK); other materials fill all of space
+    float fp_x_lo = -INFINITY, fp_x_hi = INFINITY, fp_y_lo = -INFINITY, fp_y_hi = INFINITY;
+    if (MAT == SKY_MATERIAL_VOXEL) {
+        const SkyMaterialVoxelBufferData& vm = P.mat.m.u.voxel;
+        const float margin = 1e-3f;
+        float hu = 0.5f / float(P.mat.voxel.w[0]) + margin, hv = 0.5f / float(P.mat.voxel.h[0]) + margin;
+        fp_x_lo = (-hu - vm.uSampleBias[0]) / vm.uSampleFrequency[0];
+        fp_x_hi = (1.0f + hu - vm.uSampleBias[0]) / vm.uSampleFrequency[0];
+        fp_y_lo = (-hv - vm.uSampleBias[1]) / vm.uSampleFrequency[1];
+        fp_y_hi = (1.0f + hv - vm.uSampleBias[1]) / vm.uSampleFrequency[1];
+    }
+    float t_in = -INFINITY, t_out = INFINITY;
 
     int state = ST_FETCH;
     unsigned int job = 0;
@@ -265,9 +286,25 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                 } else {
                     t = inter_t.x; t_max = inter_t.y;
                     in_shadow = false;
-                    state = sigma_t_max <= 0 ? ST_EXIT_PRIMARY : ST_TRACK;  // :183
+                    state = sigma_t_max <= 0 ? ST_EXIT_PRIMARY : ST_BEGIN_TRACK;  // :183
                 }
             }
+        }
+
+        // ---------------------------------------------------------------- footprint interval of the new tracking ray
+        // Conservative t-range in which (u, v) can lie inside the voxel footprint enlarged by 1e-3 (the exact test
+        // needs half a texel; fp32 error of the ray parameter is ~1e-6): outside it a collision is provably empty
+        // from two compares, without forming the position.
+        if (state == ST_BEGIN_TRACK) {
+            if (MAT == SKY_MATERIAL_VOXEL) {
+                const float3 d = in_shadow ? sun : rd;
+                float ix = 1.0f / d.x, iy = 1.0f / d.y;
+                float ta = (fp_x_lo - ro.x) * ix, tb = (fp_x_hi - ro.x) * ix;
+                float tc = (fp_y_lo - ro.y) * iy, td = (fp_y_hi - ro.y) * iy;
+                t_in = fmaxf(fminf(ta, tb), fminf(tc, td));
+                t_out = fminf(fmaxf(ta, tb), fmaxf(tc, td));
+            }
+            state = ST_TRACK;
         }
 
         // ---------------------------------------------------------------- hot block: tentative collisions
@@ -283,13 +320,13 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
             if (state == ST_TRACK && !lookup_pending) {
 #pragma unroll 1
                 for (int e = 0; e < kEmptySteps; ++e) {
-                    t += -logf(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
+                    t += -SKY_K19_LOG(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
                     if (t > t_max) {
                         state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
                         break;
                     }
                     if (COUNT) ++collisions;
-                    if (!ProvablyEmpty<MAT>(P, ro + dir * t)) {
+                    if (!(t < t_in || t > t_out) && !ProvablyEmpty<MAT>(P, ro + dir * t)) {
                         lookup_pending = true;
                         break;
                     }
@@ -342,7 +379,7 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                             state = ST_SHADOW_END;
                         } else {
                             t = st.x; t_max = st.y; in_shadow = true;
-                            state = ST_TRACK;
+                            state = ST_BEGIN_TRACK;
                         }
                     }
                 }
@@ -364,7 +401,7 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                 state = ST_SHADOW_END;
             } else {
                 t = st.x; t_max = st.y; in_shadow = true;
-                state = ST_TRACK;
+                state = ST_BEGIN_TRACK;
             }
         }
 
