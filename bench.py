@@ -312,6 +312,13 @@ def main():
         # Material0 issues three 2-D fetches and one 3-D fetch per evaluation: the peak for that mix is the
         # harmonic combination of the two measured rates
         mix_peak = 4.0 / (3.0 / tex_peak_2d + 1.0 / tex_peak)
+        # the opt-in hardware-filtered variant of the same kernels (texture unit, 8-bit weights; inside the frame tolerance)
+        hw_variant = None
+        if not args.hw_filtering:
+            rf.ctx.set_hw_filtering(True)
+            hw_ms = kernel_ms(lambda: rf.ctx.cloud_frame_begin(common, cloud, depth))
+            rf.ctx.set_hw_filtering(False)
+            hw_variant = {"K14_K16_ms": hw_ms, "achieved_gfetch_s": fetches / (hw_ms * 1e-3) / 1e9, "frac": fetches / (hw_ms * 1e-3) / mix_peak}
         hbm_bytes = FRAME_W * FRAME_H * (4 + 8 + 8) + (FRAME_W // 2) * (FRAME_H // 2) * (8 + 8 + 4)  # K17+K18 algorithmic
         hdr_host = torch.zeros((FRAME_H, FRAME_W, 4), dtype=torch.float16).pin_memory()
         depth_host = torch.from_numpy(depth_np).pin_memory()
@@ -328,6 +335,7 @@ def main():
                                         "combined for Material0's 3 x 2-D + 1 x 3-D fetches per SampleSigmaT"},
             "roofline_K17_K18": {"bound": "hbm", "achieved": hbm_bytes / (parts["K17_K18"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": hbm_bytes / (parts["K17_K18"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind},
+            "hardware_filtering_variant": hw_variant,
             "e2e_host_buffers_ms": e2e_frame_ms,
             "e2e_h2d_bytes": FRAME_W * FRAME_H * 12, "e2e_d2h_bytes": FRAME_W * FRAME_H * 8,
         }
