@@ -136,6 +136,31 @@ SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, 
     return out;
 }
 
+// Two-phase form of the level-0 LINEAR lookup above (same arithmetic): address and weights first, the
+// 8-byte load second, the blend third, so a caller can keep several independent lookups in flight per lane.
+struct VoxelTap {
+    long long cell;  // index into MipView::cells; kVoxelTapBorder: every corner is the border
+    float a, b, c;
+};
+constexpr long long kVoxelTapBorder = -1;
+SKY_D VoxelTap voxel_tap(const MipView& t, float u, float v, float w_) {
+    int w = t.w[0], h = t.h[0], d = t.d[0];
+    float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
+    VoxelTap tap;
+    tap.a = x - fx; tap.b = y - fy; tap.c = z - fz;
+    bool inside = cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d);
+    tap.cell = inside ? ((long long)(int(cz)) * t.cell_h + int(cy)) * t.cell_w + int(cx) : kVoxelTapBorder;
+    return tap;
+}
+SKY_D uint2 voxel_tap_load(const MipView& t, const VoxelTap& tap) {  // always a valid address: cell 0 stands in for the border
+    return __ldg(reinterpret_cast<const uint2*>(t.cells) + (tap.cell == kVoxelTapBorder ? 0ll : tap.cell));
+}
+SKY_D float voxel_tap_blend(const VoxelTap& tap, uint2 cell) {
+    return tap.cell == kVoxelTapBorder ? 0.0f : blend_cell(cell, tap.a, tap.b, tap.c);
+}
+
 // ---- hardware path ----------------------------------------------------------------------------------
 SKY_D float4 sample2d_hw(const MipView& t, float u, float v, int level) {
     return level < 0 ? tex2DLod<float4>(t.tex_linear, u, v, 0.0f) : tex2DLod<float4>(t.tex_point, u, v, float(level));

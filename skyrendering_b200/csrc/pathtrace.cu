@@ -171,18 +171,18 @@ enum : int {
     ST_IDLE           // no jobs left
 };
 
-// tuning knobs of the tracking phases (measured on B200, see profiles/): rounds per trip around the state
-// machine, provably-empty collisions per round, resident blocks per SM the register budget is cut for
+// tuning knobs of the tracking loop (measured on B200, see profiles/): batches per trip around the state machine,
+// collisions per batch, resident blocks per SM the register budget is cut for
 #ifndef SKY_K19_TRACK_ROUNDS
-#define SKY_K19_TRACK_ROUNDS 8  // 1/1: 17.3, 4/4: 20.7, 8/4: 21.1, 8/8: 16.8, 4/16: 11.9 Msamples/s (720p, 8 spp)
+#define SKY_K19_TRACK_ROUNDS 8
 #endif
-#ifndef SKY_K19_EMPTY_STEPS
-#define SKY_K19_EMPTY_STEPS 4
+#ifndef SKY_K19_BATCH
+#define SKY_K19_BATCH 4
 #endif
 #ifndef SKY_K19_OCC
-#define SKY_K19_OCC 6
+#define SKY_K19_OCC 5
 #endif
-constexpr int kTrackRounds = SKY_K19_TRACK_ROUNDS, kEmptySteps = SKY_K19_EMPTY_STEPS;
+constexpr int kTrackRounds = SKY_K19_TRACK_ROUNDS, kBatch = SKY_K19_BATCH;
 // free-flight logarithm: logf (<= 1 ulp) or the MUFU.LG2-based __logf (what GLSL's log() compiles to on this hardware)
 // Measured: 20.8 -> 23.9 Msamples/s with __logf, parity against the oracle unchanged (relative RMS of the 16-spp
 // accumulator 2.16e-3 vs 2.13e-3, same 71 % bit-identical pixels): the default.
@@ -227,8 +227,13 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
     float3 L = f3(0.0f), throughput = f3(1.0f), light = f3(0.0f), bsdf = f3(0.0f);
     float t = 0.0f, t_max = 0.0f, transmittance = 1.0f, scattered_t = 0.0f;
     int istep = 0;
-    bool has_scattered = false, in_shadow = false, after_ground = false, lookup_pending = false;
+    bool has_scattered = false, in_shadow = false, after_ground = false;
     int lookups = 0, collisions = 0, paths = 0;
+#ifdef SKY_K19_PROBE  // experiment build only: per-path collision / cycle maxima and the drain phase of the launch
+    unsigned long long probe_coll = 0, probe_t0 = 0;
+    auto probe_now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(P.counters + 5, (1ull << 62) - probe_now());
+#endif
 
     for (;;) {
         // ---------------------------------------------------------------- job fetch (warp-aggregated)
@@ -243,6 +248,9 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                     job = base + __popc(need & ((1u << lane) - 1u));
                     if (job >= njobs) {
                         state = ST_IDLE;
+#ifdef SKY_K19_PROBE
+                        atomicMax(P.counters + 0, (1ull << 62) - probe_now());
+#endif
                     } else {
                         unsigned int frame_index = job / npix_padded, p = job - frame_index * npix_padded;
                         // 8x4 tile order inside the region
@@ -259,8 +267,11 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                             rd = normalize(frag_pos - camera);
                             ro = camera;
                             L = f3(0.0f); throughput = f3(1.0f);
-                            has_scattered = false; in_shadow = false; lookup_pending = false; istep = 0; scattered_t = 0.0f;
+                            has_scattered = false; in_shadow = false; istep = 0; scattered_t = 0.0f;
                             if (COUNT) ++paths;
+#ifdef SKY_K19_PROBE
+                            probe_coll = 0; probe_t0 = probe_now();
+#endif
                             float2 camera_inter_t = CloudRegionIntersect(P, ro, rd);  // :166-170
                             if (camera_inter_t.x >= camera_inter_t.y) {
                                 state = ST_FINISH;
@@ -303,48 +314,118 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                 float tc = (fp_y_lo - ro.y) * iy, td = (fp_y_hi - ro.y) * iy;
                 t_in = fmaxf(fminf(ta, tb), fminf(tc, td));
                 t_out = fminf(fmaxf(ta, tb), fmaxf(tc, td));
+                // Dead-stream cut (exact): past t_out every remaining collision of this ray is a null collision, so
+                // the tail can only matter through the random numbers it consumes.  A shadow ray works on a COPY of
+                // the stream (:135) and its transmittance is final; a free flight that will leave the box towards the
+                // sky (or before any scattering) ends the path without drawing again (:198-216).  In both cases the
+                // first collision past t_out may end the ray.  Only a free flight that will reach the ground keeps its
+                // full chain: the Lambert bounce continues the stream.  The exit test reads the segment origin and
+                // direction only (:207-212), so it is known here.  The counting variant keeps every collision: its
+                // totals are the reference algorithm's.
+                if (!COUNT) {
+                    bool stream_is_dead = in_shadow;
+                    if (!in_shadow) {
+                        bool ground_bounce = false;
+                        if (P.pt.environment_lighting != SKY_ENV_OFF && P.pt.environment_lighting != SKY_ENV_CONST_ENVIRONMENT_MAP && has_scattered) {
+                            float3 up_dir = f3(ro.x, ro.y, ro.z + P.c.uEarthRadius);
+                            float r = length(up_dir);
+                            up_dir /= r;
+                            ground_bounce = P.atm.RayIntersectsGround(r, dot(rd, up_dir));
+                        }
+                        stream_is_dead = !ground_bounce;
+                    }
+                    if (stream_is_dead) t_max = fminf(t_max, t_out);  // NaN t_out (axis-parallel ray on a footprint edge) leaves t_max alone
+                }
             }
             state = ST_TRACK;
         }
 
         // ---------------------------------------------------------------- hot block: tentative collisions
-        // kTrackRounds rounds of (A) up to kEmptySteps collisions that provably land on zero density -- they
-        // only advance t and the random stream -- and (B) one collision that needs a density lookup.  Both
-        // phases are short convergent loops, so the fetch / transition blocks around them are amortised over
-        // many collisions and empty-space lanes do not wait on the lookups of lanes inside the cloud.
-        // Divisions by the constant majorant are multiplications by its reciprocal (what a GLSL compiler emits).
+        // kTrackRounds rounds of one BATCH of up to kBatch collisions per tracking lane, in three convergent phases:
+        //  (1) the collision distances.  They depend on the random stream only -- never on the density -- so the
+        //      batch is generated ahead of its lookups: a shadow ray never branches on sigma_t (:148), a free flight
+        //      only ends on a real collision (:191-195), and then the speculated rest of the batch is dropped and the
+        //      stream rewound to that collision;
+        //  (2) the density lookups of the batch, issued together (kBatch independent 8-byte loads in flight per lane
+        //      instead of a load -> blend -> compare -> next load chain; this is what bounds a lone long path);
+        //  (3) the in-order resolution: transmittance product (reference order) or the scatter test.
+        // Collisions that provably land on zero density (outside the footprint interval) resolve with sigma_t = 0
+        // without a lookup.  Divisions by the constant majorant are multiplications by its reciprocal.
 #pragma unroll 1
         for (int round = 0; round < kTrackRounds; ++round) {
             if (!__any_sync(0xffffffffu, state == ST_TRACK)) break;
-            const float3 dir = in_shadow ? sun : rd;
-            if (state == ST_TRACK && !lookup_pending) {
-#pragma unroll 1
-                for (int e = 0; e < kEmptySteps; ++e) {
-                    t += -SKY_K19_LOG(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
-                    if (t > t_max) {
-                        state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
-                        break;
+            if (state == ST_TRACK) {
+                const float3 dir = in_shadow ? sun : rd;
+                float tk[kBatch];
+                uint32_t sk[kBatch];  // stream position after the free-flight draw of collision k: xi_k = float(sk[k]) / 2^32
+                int n = 0;
+                bool exited = false;
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) {
+                    tk[k] = t; sk[k] = seed;
+                    if (!exited) {
+                        float tt = t + -SKY_K19_LOG(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
+                        if (tt > t_max) {
+                            exited = true;
+                        } else {
+                            t = tt; tk[k] = tt; sk[k] = seed; n = k + 1;
+                            if (!in_shadow) seed = PRNG<PRNG_KIND>(seed);  // the xi draw of :191
+                        }
                     }
-                    if (COUNT) ++collisions;
-                    if (!(t < t_in || t > t_out) && !ProvablyEmpty<MAT>(P, ro + dir * t)) {
-                        lookup_pending = true;
-                        break;
-                    }
-                    // sigma_t == 0: the shadow ray multiplies by 1 (:148); the free flight draws xi and
-                    // compares it with 0 (:191-192), which never scatters
-                    if (!in_shadow) seed = PRNG<PRNG_KIND>(seed);
                 }
-            }
-            if (state == ST_TRACK && lookup_pending) {
-                lookup_pending = false;
-                float sigma_t = SampleSigmaTAt<MAT, HW>(P, ro + dir * t, inv_thickness);
-                if (COUNT) ++lookups;
-                if (in_shadow) {
-                    transmittance *= 1.0f - fmaxf(0.0f, sigma_t * inv_sigma_t_max);  // :148
+                float sig[kBatch];
+                bool live[kBatch];
+                if (MAT == SKY_MATERIAL_VOXEL && !HW) {
+                    const SkyMaterialVoxelBufferData& vm = P.mat.m.u.voxel;
+                    VoxelTap tap[kBatch];
+                    float3 pos[kBatch];
+                    bool magnified = true;
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) {
+                        pos[k] = ro + dir * tk[k];
+                        live[k] = k < n && !(tk[k] < t_in || tk[k] > t_out) && !ProvablyEmpty<MAT>(P, pos[k]);
+                        float height01 = clampf((pos[k].z - P.c.uBottomAltitude) * inv_thickness, 0.0f, 1.0f);
+                        float u = pos[k].x * vm.uSampleFrequency[0] + vm.uSampleBias[0];
+                        float v = pos[k].y * vm.uSampleFrequency[1] + vm.uSampleBias[1];
+                        tap[k] = voxel_tap(P.mat.voxel, u, v, height01);
+                        if (!live[k]) tap[k].cell = kVoxelTapBorder;
+                        if (live[k] && !(distance2(pos[k], P.mat.camera_pos) <= P.mat.thr2_voxel)) magnified = false;
+                    }
+                    if (magnified) {
+                        uint2 cell[kBatch];
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k) cell[k] = voxel_tap_load(P.mat.voxel, tap[k]);
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k) sig[k] = voxel_tap_blend(tap[k], cell[k]) * vm.uDensity;
+                    } else {  // minified lookups (NEAREST on a mip level, far from the camera): the general sampler
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k) sig[k] = live[k] ? SampleSigmaTAt<MAT, HW>(P, pos[k], inv_thickness) : 0.0f;
+                    }
                 } else {
-                    float xi = Random01<PRNG_KIND>(seed);
-                    if (xi < sigma_t * inv_sigma_t_max) state = ST_SCATTER;  // :191-195
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) {
+                        float3 pos = ro + dir * tk[k];
+                        live[k] = k < n && !(tk[k] < t_in || tk[k] > t_out) && !ProvablyEmpty<MAT>(P, pos);
+                        sig[k] = live[k] ? SampleSigmaTAt<MAT, HW>(P, pos, inv_thickness) : 0.0f;
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) {
+                    if (k < n && state == ST_TRACK) {
+                        if (COUNT) { ++collisions; lookups += live[k] ? 1 : 0; }
+#ifdef SKY_K19_PROBE
+                        ++probe_coll;
+#endif
+                        if (in_shadow) {
+                            transmittance *= 1.0f - fmaxf(0.0f, sig[k] * inv_sigma_t_max);  // :148 (sigma_t == 0: times one, exactly)
+                        } else if (float(sk[k]) * (1.0f / 4294967296.0f) < sig[k] * inv_sigma_t_max) {  // :191-195
+                            state = ST_SCATTER;
+                            t = tk[k];
+                            seed = PRNG<PRNG_KIND>(sk[k]);
+                        }
+                    }
+                }
+                if (state == ST_TRACK && exited) state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
             }
         }
 
@@ -471,8 +552,21 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
             unsigned int frame_index = job / npix_padded;
             P.samples[size_t(frame_index) * npix + size_t(py - P.y0) * rw + (px - P.x0)] = this_res;
             state = ST_FETCH;
+#ifdef SKY_K19_PROBE
+            {
+                unsigned long long dur_us = (probe_now() - probe_t0) / 1000ull;
+                unsigned long long coll = probe_coll < (1ull << 28) ? probe_coll : (1ull << 28) - 1;
+                atomicMax(P.counters + 6, (dur_us << 40) | (coll << 12) | ((unsigned long long)(istep & 0xff) << 4));
+                atomicMax(P.counters + 7, (dur_us << 40) | ((unsigned long long)px << 20) | (unsigned long long)py);
+                atomicMax(P.counters + 2, (coll << 32) | ((unsigned long long)px << 16) | (unsigned long long)py);
+                atomicAdd(P.counters + 4, probe_coll);
+            }
+#endif
         }
     }
+#ifdef SKY_K19_PROBE
+    if (lane == 0) atomicMax(P.counters + 1, probe_now());
+#endif
     if (COUNT) {
         atomicAdd(P.counters + SKY_CNT_PT_PATHS, (unsigned long long)paths);
         atomicAdd(P.counters + SKY_CNT_PT_LOOKUPS, (unsigned long long)lookups);

@@ -296,6 +296,26 @@ def test_path_tracer_split_invariance(libs):
     assert np.array_equal(host, whole)
 
 
+@pytest.mark.parametrize("env", [abi.ENV_GROUND_MULTI_BOUNCE, abi.ENV_GROUND_SINGLE_BOUNCE, abi.ENV_CONST_ENVIRONMENT_MAP, abi.ENV_OFF])
+def test_path_tracer_dead_stream_cut_is_exact(libs, env):
+    """The timed kernel ends a tracking ray at the first collision past the voxel footprint when the rest of its
+    random stream cannot be observed; the counting variant walks every collision of the reference algorithm.
+    Same bits, fewer collisions."""
+    cuda, _ = libs
+    grid = synthetic_voxel_grid(63, 77, 43)
+    kw = dict(environment_lighting=env)  # reference defaults otherwise: 128 bounces, +-100 km box
+    r, common, cut = run_path_trace("c5", 160, 90, cuda, 4, grid=grid, **kw)
+    r.path_trace_begin(**kw)
+    r.ctx.counters_enable(True)
+    r.ctx.pt_samples(common, 1, 4, [0, 0, 160, 90])
+    r.ctx.sync()
+    full = r.ctx.read(abi.RES_PT_ACCUM)
+    cnt = r.ctx.counters()
+    r.ctx.counters_enable(False)
+    assert int(cnt[abi.CNT_PT_PATHS]) == 160 * 90 * 4
+    assert np.array_equal(cut, full)
+
+
 def test_path_tracer_statistical_self_consistency(libs):
     """Disjoint frame ranges are independent estimates of the same image: the difference of their means
     is within Monte-Carlo error."""
