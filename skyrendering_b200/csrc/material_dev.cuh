@@ -38,20 +38,36 @@ SKY_D int level_from_distance2(float d2, float k_lod, float lod_bias, float thr2
 }
 
 // ---- exact path ---------------------------------------------------------------------------------------
-SKY_D float byte_to_float(uint32_t word, int n) { return float(uint8_t(word >> (8 * n))); }  // I2F.U8 with byte select
+// Conversion-free arithmetic.  I2F / F2I / FRND run on the quarter-rate conversion pipe, and a software trilinear
+// fetch would need 14 of them (ncu: that pipe, not the FMA pipe, bounded K16 and K19).  Two exact replacements:
+//   floor: for |x| < 2^22, round-down(x + 1.5*2^23) = 1.5*2^23 + floor(x) exactly, and the low mantissa bits of
+//          that sum ARE floor(x) as an integer -> one FADD.RM, one FADD, one IADD;
+//   byte -> float: PRMT drops byte n of a word into the mantissa of 2^23: the float 2^23 + byte.  Differences of
+//          two such values are the exact byte differences, so a lerp needs one un-biasing FADD per pair.
+// Results are bit-identical to floorf() / float(uint8_t).
+constexpr float kFloorMagic = 12582912.0f;       // 1.5 * 2^23 = 0x4B400000
+constexpr float kByteBias = 8388608.0f;          // 2^23       = 0x4B000000
+SKY_D float floor_small(float x, int& i) {       // |x| < 2^22
+    float m = __fadd_rd(x, kFloorMagic);
+    i = __float_as_int(m) - 0x4B400000;
+    return m - kFloorMagic;
+}
+SKY_D float byte_biased(uint32_t word, int n) { return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + n)); }  // 2^23 + byte n
+SKY_D float lerp_biased(float t0b, float t1b, float a) { return (t0b - kByteBias) + a * (t1b - t0b); }  // t0 + a * (t1 - t0)
+SKY_D float byte_to_float(uint32_t word, int n) { return byte_biased(word, n) - kByteBias; }
 
 template <int C>
 SKY_D void load_texel(const MipView& t, int level, int x, int y, int z, float* out) {
     const uint8_t* p = t.base + (t.off[level] + (size_t(z) * t.h[level] + y) * t.w[level] + x) * C;
     if (C == 1) {
-        out[0] = float(__ldg(p)) * (1.0f / 255.0f);
+        out[0] = byte_to_float(__ldg(p), 0) * (1.0f / 255.0f);
     } else if (C == 2) {
-        uchar2 v = __ldg(reinterpret_cast<const uchar2*>(p));
-        out[0] = float(v.x) * (1.0f / 255.0f); out[1] = float(v.y) * (1.0f / 255.0f);
+        uint32_t v = __ldg(reinterpret_cast<const unsigned short*>(p));
+        out[0] = byte_to_float(v, 0) * (1.0f / 255.0f); out[1] = byte_to_float(v, 1) * (1.0f / 255.0f);
     } else {
-        uchar4 v = __ldg(reinterpret_cast<const uchar4*>(p));
-        out[0] = float(v.x) * (1.0f / 255.0f); out[1] = float(v.y) * (1.0f / 255.0f);
-        out[2] = float(v.z) * (1.0f / 255.0f); out[3] = float(v.w) * (1.0f / 255.0f);
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+        out[0] = byte_to_float(v, 0) * (1.0f / 255.0f); out[1] = byte_to_float(v, 1) * (1.0f / 255.0f);
+        out[2] = byte_to_float(v, 2) * (1.0f / 255.0f); out[3] = byte_to_float(v, 3) * (1.0f / 255.0f);
     }
 }
 
@@ -61,42 +77,40 @@ SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, int level, 
     if (level < 0) {
         int w = t.w[0], h = t.h[0];
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f;
-        float fx = floorf(x), fy = floorf(y);
+        int i0, j0;
+        float fx = floor_small(x, i0), fy = floor_small(y, j0);
         float a = x - fx, b = y - fy;
-        int i0 = int(fx) & (w - 1), j0 = int(fy) & (h - 1);
+        i0 &= w - 1; j0 &= h - 1;
         // one load brings the four corners: C == 2 -> 8 bytes {c00 c10 c01 c11} x {r,g}; C == 4 -> 16 bytes
         if (C == 2) {
             uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + size_t(j0) * w + i0);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                float t00 = byte_to_float(cell.x, c), t10 = byte_to_float(cell.x, 2 + c);
-                float t01 = byte_to_float(cell.y, c), t11 = byte_to_float(cell.y, 2 + c);
-                float r0 = t00 + a * (t10 - t00), r1 = t01 + a * (t11 - t01);
+                float r0 = lerp_biased(byte_biased(cell.x, c), byte_biased(cell.x, 2 + c), a);
+                float r1 = lerp_biased(byte_biased(cell.y, c), byte_biased(cell.y, 2 + c), a);
                 out[c] = (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
             }
         } else {
             uint4 cell = __ldg(reinterpret_cast<const uint4*>(t.cells) + size_t(j0) * w + i0);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                float t00 = byte_to_float(cell.x, c), t10 = byte_to_float(cell.y, c);
-                float t01 = byte_to_float(cell.z, c), t11 = byte_to_float(cell.w, c);
-                float r0 = t00 + a * (t10 - t00), r1 = t01 + a * (t11 - t01);
+                float r0 = lerp_biased(byte_biased(cell.x, c), byte_biased(cell.y, c), a);
+                float r1 = lerp_biased(byte_biased(cell.z, c), byte_biased(cell.w, c), a);
                 out[c] = (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
             }
         }
     } else {
         int w = t.w[level], h = t.h[level];
-        int i = int(floorf(u * float(w))) & (w - 1), j = int(floorf(v * float(h))) & (h - 1);
-        load_texel<C>(t, level, i, j, 0, out);
+        int i, j;
+        floor_small(u * float(w), i); floor_small(v * float(h), j);
+        load_texel<C>(t, level, i & (w - 1), j & (h - 1), 0, out);
     }
 }
 
 // trilinear blend of the 8 corner bytes of a packed cell (byte n = di + 2*dj + 4*dk), x first
 SKY_D float blend_cell(uint2 cell, float a, float b, float c) {
-    float t000 = byte_to_float(cell.x, 0), t100 = byte_to_float(cell.x, 1), t010 = byte_to_float(cell.x, 2), t110 = byte_to_float(cell.x, 3);
-    float t001 = byte_to_float(cell.y, 0), t101 = byte_to_float(cell.y, 1), t011 = byte_to_float(cell.y, 2), t111 = byte_to_float(cell.y, 3);
-    float x00 = t000 + a * (t100 - t000), x10 = t010 + a * (t110 - t010);
-    float x01 = t001 + a * (t101 - t001), x11 = t011 + a * (t111 - t011);
+    float x00 = lerp_biased(byte_biased(cell.x, 0), byte_biased(cell.x, 1), a), x10 = lerp_biased(byte_biased(cell.x, 2), byte_biased(cell.x, 3), a);
+    float x01 = lerp_biased(byte_biased(cell.y, 0), byte_biased(cell.y, 1), a), x11 = lerp_biased(byte_biased(cell.y, 2), byte_biased(cell.y, 3), a);
     float y0 = x00 + b * (x10 - x00), y1 = x01 + b * (x11 - x01);
     return (y0 + c * (y1 - y0)) * (1.0f / 255.0f);
 }
@@ -105,34 +119,42 @@ SKY_D float sample3d_repeat_exact(const MipView& t, float u, float v, float w_, 
     if (level < 0) {
         int w = t.w[0], h = t.h[0], d = t.d[0];
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
-        float fx = floorf(x), fy = floorf(y), fz = floorf(z);
-        int i0 = int(fx) & (w - 1), j0 = int(fy) & (h - 1), k0 = int(fz) & (d - 1);
+        int i0, j0, k0;
+        float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
+        i0 &= w - 1; j0 &= h - 1; k0 &= d - 1;
         uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(k0) * h + j0) * w + i0);
         return blend_cell(cell, x - fx, y - fy, z - fz);
     }
     int w = t.w[level], h = t.h[level], d = t.d[level];
-    int i = int(floorf(u * float(w))) & (w - 1), j = int(floorf(v * float(h))) & (h - 1), k = int(floorf(w_ * float(d))) & (d - 1);
+    int i, j, k;
+    floor_small(u * float(w), i); floor_small(v * float(h), j); floor_small(w_ * float(d), k);
     float out;
-    load_texel<1>(t, level, i, j, k, &out);
+    load_texel<1>(t, level, i & (w - 1), j & (h - 1), k & (d - 1), &out);
     return out;
 }
 
-// CLAMP_TO_BORDER with border colour 0, any size (voxel grid)
+// CLAMP_TO_BORDER with border colour 0, any size (voxel grid).  The border test runs on the float floor, which
+// stays far outside the grid for coordinates beyond the exact range of floor_small, so its integer is only used in range.
 SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, int level) {
     if (level < 0) {
         int w = t.w[0], h = t.h[0], d = t.d[0];
         float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
-        float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+        int i0, j0, k0;
+        float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
         // cell index = base texel + 1; outside [0, w] x [0, h] x [0, d] every corner is the border
         float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
         if (!(cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d))) return 0.0f;
-        uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(int(cz)) * t.cell_h + int(cy)) * t.cell_w + int(cx));
+        uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(k0 + 1) * t.cell_h + (j0 + 1)) * t.cell_w + (i0 + 1));
         return blend_cell(cell, x - fx, y - fy, z - fz);
     }
     int w = t.w[level], h = t.h[level], d = t.d[level];
-    int i = int(floorf(u * float(w))), j = int(floorf(v * float(h))), k = int(floorf(w_ * float(d)));
+    float fu = u * float(w), fv = v * float(h), fw = w_ * float(d);
     float out = 0.0f;
-    if (i >= 0 && i < w && j >= 0 && j < h && k >= 0 && k < d) load_texel<1>(t, level, i, j, k, &out);
+    if (fu >= 0.0f && fu < float(w) && fv >= 0.0f && fv < float(h) && fw >= 0.0f && fw < float(d)) {
+        int i, j, k;
+        floor_small(fu, i); floor_small(fv, j); floor_small(fw, k);
+        load_texel<1>(t, level, i, j, k, &out);
+    }
     return out;
 }
 
@@ -146,12 +168,13 @@ constexpr long long kVoxelTapBorder = -1;
 SKY_D VoxelTap voxel_tap(const MipView& t, float u, float v, float w_) {
     int w = t.w[0], h = t.h[0], d = t.d[0];
     float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
-    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    int i0, j0, k0;
+    float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
     float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
     VoxelTap tap;
     tap.a = x - fx; tap.b = y - fy; tap.c = z - fz;
     bool inside = cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d);
-    tap.cell = inside ? ((long long)(int(cz)) * t.cell_h + int(cy)) * t.cell_w + int(cx) : kVoxelTapBorder;
+    tap.cell = inside ? ((long long)(k0 + 1) * t.cell_h + (j0 + 1)) * t.cell_w + (i0 + 1) : kVoxelTapBorder;
     return tap;
 }
 SKY_D uint2 voxel_tap_load(const MipView& t, const VoxelTap& tap) {  // always a valid address: cell 0 stands in for the border

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
         fp_y_hi = (1.0f + hv - vm.uSampleBias[1]) / vm.uSampleFrequency[1];
     }
     float t_in = -INFINITY, t_out = INFINITY;
+    bool ray_magnified = false;  // every lookup of the current tracking ray is a level-0 LINEAR fetch (lambda <= 0.5)
 
     int state = ST_FETCH;
     unsigned int job = 0;
@@ -336,6 +337,11 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                     }
                     if (stream_is_dead) t_max = fminf(t_max, t_out);  // NaN t_out (axis-parallel ray on a footprint edge) leaves t_max alone
                 }
+                // lambda <= 0.5 <=> dist(pos, camera)^2 <= thr2; the distance to a point is convex along a ray, so the two
+                // ends of the part of the ray that can see the grid decide for all of it (0.01 % margin for rounding)
+                float ta_ = fmaxf(t, t_in), tb_ = fminf(t_max, t_out);
+                float thr2 = P.mat.thr2_voxel * 0.9999f;
+                ray_magnified = distance2(ro + d * ta_, P.mat.camera_pos) <= thr2 && distance2(ro + d * tb_, P.mat.camera_pos) <= thr2;
             }
             state = ST_TRACK;
         }
@@ -356,76 +362,72 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
             if (!__any_sync(0xffffffffu, state == ST_TRACK)) break;
             if (state == ST_TRACK) {
                 const float3 dir = in_shadow ? sun : rd;
+                // (1) branch-free: the next kBatch collision distances and stream positions.  Entries past the end of
+                //     the ray (tk > t_max) are computed and ignored.
                 float tk[kBatch];
                 uint32_t sk[kBatch];  // stream position after the free-flight draw of collision k: xi_k = float(sk[k]) / 2^32
-                int n = 0;
-                bool exited = false;
+                uint32_t s = seed;
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k) {
-                    tk[k] = t; sk[k] = seed;
-                    if (!exited) {
-                        float tt = t + -SKY_K19_LOG(1.0f - Random01<PRNG_KIND>(seed)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
-                        if (tt > t_max) {
-                            exited = true;
-                        } else {
-                            t = tt; tk[k] = tt; sk[k] = seed; n = k + 1;
-                            if (!in_shadow) seed = PRNG<PRNG_KIND>(seed);  // the xi draw of :191
-                        }
-                    }
+                    float step = -SKY_K19_LOG(1.0f - Random01<PRNG_KIND>(s)) * inv_sigma_t_max;  // InfiniteTransmittanceIS, :82-84
+                    tk[k] = (k ? tk[k - 1] : t) + step;
+                    sk[k] = s;
+                    if (!in_shadow) s = PRNG<PRNG_KIND>(s);  // the xi draw of :191
                 }
+                // (2) the lookups
                 float sig[kBatch];
                 bool live[kBatch];
-                if (MAT == SKY_MATERIAL_VOXEL && !HW) {
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) live[k] = !(tk[k] < t_in || tk[k] > t_out) && !(tk[k] > t_max);
+                if (MAT == SKY_MATERIAL_VOXEL && !HW && ray_magnified) {
                     const SkyMaterialVoxelBufferData& vm = P.mat.m.u.voxel;
                     VoxelTap tap[kBatch];
-                    float3 pos[kBatch];
-                    bool magnified = true;
-#pragma unroll
-                    for (int k = 0; k < kBatch; ++k) {
-                        pos[k] = ro + dir * tk[k];
-                        live[k] = k < n && !(tk[k] < t_in || tk[k] > t_out) && !ProvablyEmpty<MAT>(P, pos[k]);
-                        float height01 = clampf((pos[k].z - P.c.uBottomAltitude) * inv_thickness, 0.0f, 1.0f);
-                        float u = pos[k].x * vm.uSampleFrequency[0] + vm.uSampleBias[0];
-                        float v = pos[k].y * vm.uSampleFrequency[1] + vm.uSampleBias[1];
-                        tap[k] = voxel_tap(P.mat.voxel, u, v, height01);
-                        if (!live[k]) tap[k].cell = kVoxelTapBorder;
-                        if (live[k] && !(distance2(pos[k], P.mat.camera_pos) <= P.mat.thr2_voxel)) magnified = false;
-                    }
-                    if (magnified) {
-                        uint2 cell[kBatch];
-#pragma unroll
-                        for (int k = 0; k < kBatch; ++k) cell[k] = voxel_tap_load(P.mat.voxel, tap[k]);
-#pragma unroll
-                        for (int k = 0; k < kBatch; ++k) sig[k] = voxel_tap_blend(tap[k], cell[k]) * vm.uDensity;
-                    } else {  // minified lookups (NEAREST on a mip level, far from the camera): the general sampler
-#pragma unroll
-                        for (int k = 0; k < kBatch; ++k) sig[k] = live[k] ? SampleSigmaTAt<MAT, HW>(P, pos[k], inv_thickness) : 0.0f;
-                    }
-                } else {
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k) {
                         float3 pos = ro + dir * tk[k];
-                        live[k] = k < n && !(tk[k] < t_in || tk[k] > t_out) && !ProvablyEmpty<MAT>(P, pos);
+                        float height01 = clampf((pos.z - P.c.uBottomAltitude) * inv_thickness, 0.0f, 1.0f);
+                        float u = pos.x * vm.uSampleFrequency[0] + vm.uSampleBias[0];
+                        float v = pos.y * vm.uSampleFrequency[1] + vm.uSampleBias[1];
+                        tap[k] = voxel_tap(P.mat.voxel, u, v, height01);  // outside the grid: border, the exact empty-space test
+                        if (!live[k]) tap[k].cell = kVoxelTapBorder;
+                        live[k] = tap[k].cell != kVoxelTapBorder;
+                    }
+                    uint2 cell[kBatch];
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) cell[k] = voxel_tap_load(P.mat.voxel, tap[k]);
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) sig[k] = voxel_tap_blend(tap[k], cell[k]) * vm.uDensity;
+                } else {  // other materials, hardware filtering, rays reaching minified (NEAREST mip level) distances: the general sampler
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) {
+                        float3 pos = ro + dir * tk[k];
+                        live[k] = live[k] && !ProvablyEmpty<MAT>(P, pos);
                         sig[k] = live[k] ? SampleSigmaTAt<MAT, HW>(P, pos, inv_thickness) : 0.0f;
                     }
                 }
+                // (3) in-order resolution
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k) {
-                    if (k < n && state == ST_TRACK) {
-                        if (COUNT) { ++collisions; lookups += live[k] ? 1 : 0; }
+                    if (state == ST_TRACK) {
+                        if (tk[k] > t_max) {  // the ray left the box; the stream stands after this step's draw
+                            state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
+                            seed = sk[k];
+                        } else {
+                            if (COUNT) { ++collisions; lookups += live[k] ? 1 : 0; }
 #ifdef SKY_K19_PROBE
-                        ++probe_coll;
+                            ++probe_coll;
 #endif
-                        if (in_shadow) {
-                            transmittance *= 1.0f - fmaxf(0.0f, sig[k] * inv_sigma_t_max);  // :148 (sigma_t == 0: times one, exactly)
-                        } else if (float(sk[k]) * (1.0f / 4294967296.0f) < sig[k] * inv_sigma_t_max) {  // :191-195
-                            state = ST_SCATTER;
-                            t = tk[k];
-                            seed = PRNG<PRNG_KIND>(sk[k]);
+                            if (in_shadow) {
+                                transmittance *= 1.0f - fmaxf(0.0f, sig[k] * inv_sigma_t_max);  // :148 (sigma_t == 0: times one, exactly)
+                            } else if (float(sk[k]) * (1.0f / 4294967296.0f) < sig[k] * inv_sigma_t_max) {  // :191-195
+                                state = ST_SCATTER;
+                                t = tk[k];
+                                seed = PRNG<PRNG_KIND>(sk[k]);
+                            }
                         }
                     }
                 }
-                if (state == ST_TRACK && exited) state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
+                if (state == ST_TRACK) { t = tk[kBatch - 1]; seed = s; }
             }
         }
 
