@@ -151,6 +151,9 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
     if (ctx->blue_noise) cudaFree(ctx->blue_noise);
     if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->ray_setup) cudaFree(ctx->ray_setup);
+    if (ctx->ray_raw) cudaFree(ctx->ray_raw);
+    if (ctx->ray_job_counter) cudaFree(ctx->ray_job_counter);
     if (ctx->stage_depth) cudaFree(ctx->stage_depth);
     if (ctx->stage_hdr) cudaFree(ctx->stage_hdr);
     if (ctx->pt_samples) cudaFree(ctx->pt_samples);

@@ -18,6 +18,12 @@ constexpr float kMinTransmittance = 0.01f;  // VolumetricCloudCommon.glsl:30
 #define SKY_K16_MARCH_STEPS 4
 #endif
 constexpr int kMarchSteps = SKY_K16_MARCH_STEPS;
+#ifndef SKY_K16_OCC
+#define SKY_K16_OCC 5  // resident 128-thread blocks per SM the register budget is cut for
+#endif
+#ifndef SKY_K16_WARP_8X4
+#define SKY_K16_WARP_8X4 1  // a warp renders an 8x4 block of rays (more alike than a 16x2 strip)
+#endif
 
 struct CloudParams {
     SkyCloudCommonBufferData c;  // VolumetricCloudCommon.glsl:6-28
@@ -317,12 +323,17 @@ SKY_D void ShadeDenseStep(const CloudParams& P, RayMarchContext& ctx, float sigm
 }
 
 template <int MAT, bool HW, bool COUNT>
-__global__ void __launch_bounds__(128) k16_render(const __grid_constant__ CloudParams P) {
+__global__ void __launch_bounds__(128, SKY_K16_OCC) k16_render(const __grid_constant__ CloudParams P) {
     const SkyCloudCommonBufferData& c = P.c;
     const SkyCloudBufferData& b = P.b;
     const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
+#if SKY_K16_WARP_8X4
+    int px = blockIdx.x * 16 + int((threadIdx.x >> 5) & 1u) * 8 + int(threadIdx.x & 7u);
+    int row_in_band = blockIdx.y * 8 + int(threadIdx.x >> 6) * 4 + int((threadIdx.x >> 3) & 3u);
+#else
     int px = blockIdx.x * 16 + (threadIdx.x & 15);
     int row_in_band = blockIdx.y * 8 + (threadIdx.x >> 4);
+#endif
     int py = row_in_band;
     if (P.band_rows > 0) {
         // rows owned by this rank: ((py / band_rows) % band_count) == band_index
@@ -739,6 +750,14 @@ int make_material_params(SkyContext* ctx, const float* camera_pos, MaterialParam
     M.thr2_detail = thr2(mc.uDetailSampleInfo.k_lod, mc.uLodBias);
     M.thr2_displacement = thr2(mc.uDisplacementSampleInfo.k_lod, mc.uLodBias);
     M.thr2_voxel = thr2(M.m.u.voxel.uSampleLodK, M.m.u.voxel.uLodBias);
+    // 0.5 - (log2(k_lod) + bias): lambda <= 0.5  <=>  lod_h - 0.5 * log2(dist^2) >= 0
+    auto lod_h = [](float k_lod, float bias) { return k_lod > 0.0f ? 0.5f - (log2f(k_lod) + bias) : INFINITY; };
+    M.lod_h_cloud_map = lod_h(mc.uCloudMapSampleInfo.k_lod, mc.uLodBias);
+    M.lod_h_detail = lod_h(mc.uDetailSampleInfo.k_lod, mc.uLodBias);
+    M.lod_h_displacement = lod_h(mc.uDisplacementSampleInfo.k_lod, mc.uLodBias);
+    M.lod_h_voxel = lod_h(M.m.u.voxel.uSampleLodK, M.m.u.voxel.uLodBias);
+    const float* dp = M.m.u.m0.uDetailParam;
+    M.m0_zero_base_is_zero = M.m.type == SKY_MATERIAL_DEFAULT0 && dp[0] >= 0.0f && dp[1] >= 0.0f && dp[0] + dp[1] <= 1.0f;
     return 0;
 }
 

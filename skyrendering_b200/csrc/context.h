@@ -18,20 +18,24 @@ struct MipView {
     int channels;
     cudaTextureObject_t tex_linear;  // LINEAR, level 0 (magnification)
     cudaTextureObject_t tex_point;   // POINT over the mip chain (NEAREST_MIPMAP_NEAREST)
-    // Corner-packed copy of level 0 for the exact LINEAR path: cell (i,j[,k]) holds the 4 (2-D) or 8 (3-D)
-    // texels a bilinear / trilinear tap at base texel (i,j,k) needs, wrap or border already applied, so
-    // one aligned 8- or 16-byte load replaces 4-8 scattered byte loads.  HBM is cheap on this part
-    // (8x the level-0 bytes), load slots are not.  REPEAT: cell_w = w; BORDER: cell_w = w + 1 and cell
-    // index = base texel + 1 (base texel -1 .. w-1).
+    // Corner-packed copy of EVERY level for the exact path: cell (i,j[,k]) of level l holds the 4 (2-D) or 8 (3-D)
+    // texels a bilinear / trilinear tap at base texel (i,j,k) needs, wrap or border already applied, so any
+    // fetch -- LINEAR on level 0 or NEAREST on a mip level (corner 0 of the cell) -- is ONE aligned 8- or 16-byte
+    // load at a branch-free address.  HBM is cheap on this part (9x the texel bytes), load slots and divergence are not.
+    // REPEAT: cell dims = level dims, cell index = base texel.  BORDER: cell dims = (w+3, h+3, d+1) and cell
+    // index = base texel + (2, 2, 1): base texels -2..w in x/y (a tap up to a quarter texel outside the half-texel
+    // apron needs no range test) and -1..d-1 in z.
     const void* cells;
-    int cell_w, cell_h, cell_d;
+    unsigned long long cell_off[kMaxMipLevels];  // first cell of level l
+    int cell_w[kMaxMipLevels], cell_h[kMaxMipLevels], cell_d[kMaxMipLevels];
+    int pad_xy, pad_z;                            // BORDER: 2, 1; REPEAT: 0, 0
 };
 
 struct MipTextureDev {
     MipView view{};
     uint8_t* data = nullptr;
     size_t bytes = 0;
-    void* cells = nullptr;  // corner-packed level 0, see MipView
+    void* cells = nullptr;  // corner-packed levels, see MipView
     size_t cell_bytes = 0;
     cudaMipmappedArray_t array = nullptr;
     bool is3d = false;
@@ -78,6 +82,12 @@ struct SkyContext {
     Lut<float> checkerboard_depth, cloud_distance;
     Lut<float2> index_linear_depth;
     Lut<half4> render_texture, reconstruct[2];
+
+    // K16 wavefront: per-ray records between k16_setup / k16_march / k16_resolve, and the ray queue
+    void* ray_setup = nullptr;
+    void* ray_raw = nullptr;
+    size_t ray_records_bytes = 0;
+    unsigned int* ray_job_counter = nullptr;
 
     // path tracer
     Lut<float4> pt_accum;

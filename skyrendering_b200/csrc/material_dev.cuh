@@ -20,22 +20,11 @@ struct MaterialParams {
     float3 camera_pos;  // uCameraPos
     // (2^(0.5 - lod_bias) / k_lod)^2 per texture: dist^2 <= thr2  <=>  lambda <= 0.5
     float thr2_cloud_map, thr2_detail, thr2_displacement, thr2_voxel;
+    // 0.5 - (log2(k_lod) + lod_bias) per texture: lambda <= 0.5  <=>  lod_h - 0.5 * log2(dist^2) >= 0
+    float lod_h_cloud_map, lod_h_detail, lod_h_displacement, lod_h_voxel;
+    // DEFAULT0: 0 <= uDetailParam.x * detail + uDetailParam.y <= 1 for every texel value, see SigmaEval::advance
+    bool m0_zero_base_is_zero;
 };
-
-// spec 8.14.3 level selection; returns -1 for magnification
-SKY_D int select_mip_level(float lod, int levels) {
-    if (!(lod > 0.5f)) return -1;
-    int q = levels - 1;
-    int d = (lod <= float(q) + 0.5f) ? int(ceilf(lod + 0.5f)) - 1 : q;
-    return clampi(d, 0, q);
-}
-// level for lambda = log2(k_lod * sqrt(d2)) + bias (GetUVWLod, VolumetricCloudDefaultMaterialCommon.glsl:20-24)
-// Minified case: log2(k * sqrt(d2)) = 0.5 * log2(k^2 * d2), one MUFU.LG2 (2^-22 relative error moves a level
-// boundary by less than a millimetre of camera distance).
-SKY_D int level_from_distance2(float d2, float k_lod, float lod_bias, float thr2, int levels) {
-    if (d2 <= thr2) return -1;
-    return select_mip_level(0.5f * __log2f(k_lod * k_lod * d2) + lod_bias, levels);
-}
 
 // ---- exact path ---------------------------------------------------------------------------------------
 // Conversion-free arithmetic.  I2F / F2I / FRND run on the quarter-rate conversion pipe, and a software trilinear
@@ -56,57 +45,91 @@ SKY_D float byte_biased(uint32_t word, int n) { return __uint_as_float(__byte_pe
 SKY_D float lerp_biased(float t0b, float t1b, float a) { return (t0b - kByteBias) + a * (t1b - t0b); }  // t0 + a * (t1 - t0)
 SKY_D float byte_to_float(uint32_t word, int n) { return byte_biased(word, n) - kByteBias; }
 
-template <int C>
-SKY_D void load_texel(const MipView& t, int level, int x, int y, int z, float* out) {
-    const uint8_t* p = t.base + (t.off[level] + (size_t(z) * t.h[level] + y) * t.w[level] + x) * C;
-    if (C == 1) {
-        out[0] = byte_to_float(__ldg(p), 0) * (1.0f / 255.0f);
-    } else if (C == 2) {
-        uint32_t v = __ldg(reinterpret_cast<const unsigned short*>(p));
-        out[0] = byte_to_float(v, 0) * (1.0f / 255.0f); out[1] = byte_to_float(v, 1) * (1.0f / 255.0f);
-    } else {
-        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
-        out[0] = byte_to_float(v, 0) * (1.0f / 255.0f); out[1] = byte_to_float(v, 1) * (1.0f / 255.0f);
-        out[2] = byte_to_float(v, 2) * (1.0f / 255.0f); out[3] = byte_to_float(v, 3) * (1.0f / 255.0f);
-    }
+// GetUVWLod (VolumetricCloudDefaultMaterialCommon.glsl:20-24) + the GL level rule from L = log2(dist^2), which the
+// textures sampled at one position share: lambda = 0.5 * L + log2(k_lod) + bias.  x = 0.5 - lambda >= 0: LINEAR on
+// level 0 (-1); otherwise NEAREST on level min(ceil(lambda + 0.5) - 1, q) = min(ceil(-x), q) = min(-floor(x), q).
+// (The 2^-22 relative error of MUFU.LG2 moves a level boundary by less than a millimetre of camera distance.)
+SKY_D int level_from_log2(float log2_d2, float lod_h, int levels) {
+    float x = lod_h - 0.5f * log2_d2;
+    int d = 0x4B400000 - __float_as_int(__fadd_rd(x, kFloorMagic));  // -floor(x); garbage-but-large for |x| >= 2^22
+    return !(x < 0.0f) ? -1 : min(d, levels - 1);
 }
 
-// REPEAT textures have power-of-two sizes (512 / 128, fixed by the reference)
-template <int C>
-SKY_D void sample2d_repeat_exact(const MipView& t, float u, float v, int level, float* out) {
-    if (level < 0) {
-        int w = t.w[0], h = t.h[0];
-        float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f;
-        int i0, j0;
-        float fx = floor_small(x, i0), fy = floor_small(y, j0);
-        float a = x - fx, b = y - fy;
-        i0 &= w - 1; j0 &= h - 1;
-        // one load brings the four corners: C == 2 -> 8 bytes {c00 c10 c01 c11} x {r,g}; C == 4 -> 16 bytes
-        if (C == 2) {
-            uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + size_t(j0) * w + i0);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float r0 = lerp_biased(byte_biased(cell.x, c), byte_biased(cell.x, 2 + c), a);
-                float r1 = lerp_biased(byte_biased(cell.y, c), byte_biased(cell.y, 2 + c), a);
-                out[c] = (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
-            }
-        } else {
-            uint4 cell = __ldg(reinterpret_cast<const uint4*>(t.cells) + size_t(j0) * w + i0);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float r0 = lerp_biased(byte_biased(cell.x, c), byte_biased(cell.y, c), a);
-                float r1 = lerp_biased(byte_biased(cell.z, c), byte_biased(cell.w, c), a);
-                out[c] = (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
-            }
-        }
-    } else {
-        int w = t.w[level], h = t.h[level];
-        int i, j;
-        floor_small(u * float(w), i); floor_small(v * float(h), j);
-        load_texel<C>(t, level, i & (w - 1), j & (h - 1), 0, out);
-    }
+// ---- unified fetches ------------------------------------------------------------------------------------
+// One fetch = one tap: cell index + weights.  `level` < 0: LINEAR on level 0 (GL magnification); otherwise NEAREST
+// on that mip level, expressed as the same cell load with zero weights (corner 0 of cell (i,j,k) is texel (i,j,k)),
+// so lanes of a warp that sit on different sides of the LOD threshold run the same instructions.
+struct Tap2 { unsigned int cell; float a, b; };
+struct Tap3 { unsigned int cell; float a, b, c; };
+struct TapB { long long cell; float a, b, c; };  // BORDER volume (any size); cell < 0: every corner is the border
+
+// REPEAT textures have power-of-two sizes (512 / 128, fixed by the reference): level dims are shifts
+SKY_D Tap2 tap2_repeat(const MipView& t, float u, float v, int level) {
+    const bool mag = level < 0;
+    const int l = mag ? 0 : level;
+    const int w = max(t.w[0] >> l, 1), h = max(t.h[0] >> l, 1);
+    const float half = mag ? 0.5f : 0.0f;
+    float x = u * float(w) - half, y = v * float(h) - half;
+    int i0, j0;
+    float fx = floor_small(x, i0), fy = floor_small(y, j0);
+    Tap2 tap;
+    tap.a = mag ? x - fx : 0.0f;
+    tap.b = mag ? y - fy : 0.0f;
+    tap.cell = (unsigned int)t.cell_off[l] + (unsigned int)((j0 & (h - 1)) * w + (i0 & (w - 1)));
+    return tap;
+}
+SKY_D Tap3 tap3_repeat(const MipView& t, float u, float v, float w_, int level) {
+    const bool mag = level < 0;
+    const int l = mag ? 0 : level;
+    const int w = max(t.w[0] >> l, 1), h = max(t.h[0] >> l, 1), d = max(t.d[0] >> l, 1);
+    const float half = mag ? 0.5f : 0.0f;
+    float x = u * float(w) - half, y = v * float(h) - half, z = w_ * float(d) - half;
+    int i0, j0, k0;
+    float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
+    Tap3 tap;
+    tap.a = mag ? x - fx : 0.0f;
+    tap.b = mag ? y - fy : 0.0f;
+    tap.c = mag ? z - fz : 0.0f;
+    tap.cell = (unsigned int)t.cell_off[l] + (unsigned int)(((k0 & (d - 1)) * h + (j0 & (h - 1))) * w + (i0 & (w - 1)));
+    return tap;
+}
+// CLAMP_TO_BORDER with border colour 0, any size (voxel grid).  The range test runs on the float floor, which stays
+// far outside the grid for coordinates beyond the exact range of floor_small, so its integer is only used in range.
+SKY_D TapB tapb_border(const MipView& t, float u, float v, float w_, int level) {
+    const bool mag = level < 0;
+    const int l = mag ? 0 : level;
+    const int w = max(t.w[0] >> l, 1), h = max(t.h[0] >> l, 1), d = max(t.d[0] >> l, 1);
+    const float half = mag ? 0.5f : 0.0f;
+    float x = u * float(w) - half, y = v * float(h) - half, z = w_ * float(d) - half;
+    int i0, j0, k0;
+    float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
+    TapB tap;
+    tap.a = mag ? x - fx : 0.0f;
+    tap.b = mag ? y - fy : 0.0f;
+    tap.c = mag ? z - fz : 0.0f;
+    // LINEAR: base texel -1 .. size-1 touches the texture; NEAREST: texel 0 .. size-1
+    const float lo = mag ? -1.0f : 0.0f;
+    bool inside = fx >= lo && fx <= float(w - 1) && fy >= lo && fy <= float(h - 1) && fz >= lo && fz <= float(d - 1);
+    tap.cell = inside ? (long long)t.cell_off[l] + ((long long)(k0 + t.pad_z) * t.cell_h[l] + (j0 + t.pad_xy)) * t.cell_w[l] + (i0 + t.pad_xy) : -1ll;
+    return tap;
+}
+SKY_D uint2 load_cell8(const MipView& t, unsigned int cell) { return __ldg(reinterpret_cast<const uint2*>(t.cells) + cell); }
+SKY_D uint4 load_cell16(const MipView& t, unsigned int cell) { return __ldg(reinterpret_cast<const uint4*>(t.cells) + cell); }
+SKY_D uint2 load_cellb(const MipView& t, const TapB& tap) {  // always a valid address: cell 0 stands in for the border
+    return __ldg(reinterpret_cast<const uint2*>(t.cells) + (tap.cell < 0 ? 0ll : tap.cell));
 }
 
+// bilinear blend of channel c of an RG8 cell (8 bytes: {c00 c10 | c01 c11} x {r,g}) / an RGBA8 cell (16 bytes: one word per corner)
+SKY_D float blend_rg8(uint2 cell, int c, float a, float b) {
+    float r0 = lerp_biased(byte_biased(cell.x, c), byte_biased(cell.x, 2 + c), a);
+    float r1 = lerp_biased(byte_biased(cell.y, c), byte_biased(cell.y, 2 + c), a);
+    return (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
+}
+SKY_D float blend_rgba8(uint4 cell, int c, float a, float b) {
+    float r0 = lerp_biased(byte_biased(cell.x, c), byte_biased(cell.y, c), a);
+    float r1 = lerp_biased(byte_biased(cell.z, c), byte_biased(cell.w, c), a);
+    return (r0 + b * (r1 - r0)) * (1.0f / 255.0f);
+}
 // trilinear blend of the 8 corner bytes of a packed cell (byte n = di + 2*dj + 4*dk), x first
 SKY_D float blend_cell(uint2 cell, float a, float b, float c) {
     float x00 = lerp_biased(byte_biased(cell.x, 0), byte_biased(cell.x, 1), a), x10 = lerp_biased(byte_biased(cell.x, 2), byte_biased(cell.x, 3), a);
@@ -115,81 +138,43 @@ SKY_D float blend_cell(uint2 cell, float a, float b, float c) {
     return (y0 + c * (y1 - y0)) * (1.0f / 255.0f);
 }
 
-SKY_D float sample3d_repeat_exact(const MipView& t, float u, float v, float w_, int level) {
-    if (level < 0) {
-        int w = t.w[0], h = t.h[0], d = t.d[0];
-        float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
-        int i0, j0, k0;
-        float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
-        i0 &= w - 1; j0 &= h - 1; k0 &= d - 1;
-        uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(k0) * h + j0) * w + i0);
-        return blend_cell(cell, x - fx, y - fy, z - fz);
-    }
-    int w = t.w[level], h = t.h[level], d = t.d[level];
-    int i, j, k;
-    floor_small(u * float(w), i); floor_small(v * float(h), j); floor_small(w_ * float(d), k);
-    float out;
-    load_texel<1>(t, level, i & (w - 1), j & (h - 1), k & (d - 1), &out);
-    return out;
-}
-
-// CLAMP_TO_BORDER with border colour 0, any size (voxel grid).  The border test runs on the float floor, which
-// stays far outside the grid for coordinates beyond the exact range of floor_small, so its integer is only used in range.
-SKY_D float sample3d_border_exact(const MipView& t, float u, float v, float w_, int level) {
-    if (level < 0) {
-        int w = t.w[0], h = t.h[0], d = t.d[0];
-        float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
-        int i0, j0, k0;
-        float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
-        // cell index = base texel + 1; outside [0, w] x [0, h] x [0, d] every corner is the border
-        float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
-        if (!(cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d))) return 0.0f;
-        uint2 cell = __ldg(reinterpret_cast<const uint2*>(t.cells) + (size_t(k0 + 1) * t.cell_h + (j0 + 1)) * t.cell_w + (i0 + 1));
-        return blend_cell(cell, x - fx, y - fy, z - fz);
-    }
-    int w = t.w[level], h = t.h[level], d = t.d[level];
-    float fu = u * float(w), fv = v * float(h), fw = w_ * float(d);
-    float out = 0.0f;
-    if (fu >= 0.0f && fu < float(w) && fv >= 0.0f && fv < float(h) && fw >= 0.0f && fw < float(d)) {
-        int i, j, k;
-        floor_small(fu, i); floor_small(fv, j); floor_small(fw, k);
-        load_texel<1>(t, level, i, j, k, &out);
-    }
-    return out;
-}
-
-// Two-phase form of the level-0 LINEAR lookup above (same arithmetic): address and weights first, the
-// 8-byte load second, the blend third, so a caller can keep several independent lookups in flight per lane.
-struct VoxelTap {
-    long long cell;  // index into MipView::cells; kVoxelTapBorder: every corner is the border
-    float a, b, c;
-};
-constexpr long long kVoxelTapBorder = -1;
+// K19's fast path: level-0 LINEAR lookup of the voxel grid for a position the caller has already bounded to the
+// footprint apron (u, v at most a quarter texel outside [-1/2w, 1 + 1/2w], w_ in [0, 1]): the padded cell layout needs
+// no range test.  Same arithmetic as tapb_border.
+struct VoxelTap { unsigned int xy; int k; float a, b, c; };
 SKY_D VoxelTap voxel_tap(const MipView& t, float u, float v, float w_) {
-    int w = t.w[0], h = t.h[0], d = t.d[0];
-    float x = u * float(w) - 0.5f, y = v * float(h) - 0.5f, z = w_ * float(d) - 0.5f;
+    float x = u * float(t.w[0]) - 0.5f, y = v * float(t.h[0]) - 0.5f, z = w_ * float(t.d[0]) - 0.5f;
     int i0, j0, k0;
     float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
-    float cx = fx + 1.0f, cy = fy + 1.0f, cz = fz + 1.0f;
     VoxelTap tap;
     tap.a = x - fx; tap.b = y - fy; tap.c = z - fz;
-    bool inside = cx >= 0.0f && cx <= float(w) && cy >= 0.0f && cy <= float(h) && cz >= 0.0f && cz <= float(d);
-    tap.cell = inside ? ((long long)(k0 + 1) * t.cell_h + (j0 + 1)) * t.cell_w + (i0 + 1) : kVoxelTapBorder;
+    tap.xy = (unsigned int)((j0 + 2) * t.cell_w[0] + (i0 + 2));
+    tap.k = k0 + 1;
     return tap;
 }
-SKY_D uint2 voxel_tap_load(const MipView& t, const VoxelTap& tap) {  // always a valid address: cell 0 stands in for the border
-    return __ldg(reinterpret_cast<const uint2*>(t.cells) + (tap.cell == kVoxelTapBorder ? 0ll : tap.cell));
-}
-SKY_D float voxel_tap_blend(const VoxelTap& tap, uint2 cell) {
-    return tap.cell == kVoxelTapBorder ? 0.0f : blend_cell(cell, tap.a, tap.b, tap.c);
+SKY_D uint2 voxel_tap_load(const MipView& t, const VoxelTap& tap, bool live) {  // !live: any valid address
+    size_t cell = live ? size_t((unsigned int)tap.k) * (unsigned int)(t.cell_w[0] * t.cell_h[0]) + tap.xy : size_t(0);
+    return __ldg(reinterpret_cast<const uint2*>(t.cells) + cell);
 }
 
 // ---- hardware path ----------------------------------------------------------------------------------
+// LINEAR on level 0 and POINT over the mip chain are two texture objects (a CUDA texture object has one filter mode)
+#ifndef SKY_HW_HANDLE_SELECT
+#define SKY_HW_HANDLE_SELECT 0
+#endif
 SKY_D float4 sample2d_hw(const MipView& t, float u, float v, int level) {
+#if SKY_HW_HANDLE_SELECT  // one TEX with a per-lane handle
+    return tex2DLod<float4>(level < 0 ? t.tex_linear : t.tex_point, u, v, float(max(level, 0)));
+#else
     return level < 0 ? tex2DLod<float4>(t.tex_linear, u, v, 0.0f) : tex2DLod<float4>(t.tex_point, u, v, float(level));
+#endif
 }
 SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, int level) {
+#if SKY_HW_HANDLE_SELECT
+    return tex3DLod<float>(level < 0 ? t.tex_linear : t.tex_point, u, v, w, float(max(level, 0)));
+#else
     return level < 0 ? tex3DLod<float>(t.tex_linear, u, v, w, 0.0f) : tex3DLod<float>(t.tex_point, u, v, w, float(level));
+#endif
 }
 
 // ---- SampleSigmaT ------------------------------------------------------------------------------------
@@ -201,79 +186,158 @@ SKY_D float CalHeightMask(float cloud_type, float height01) {
 SKY_D float Remap01(float x, float x0, float x1) { return clampf(__fdividef(x - x0, x1 - x0), 0.0f, 1.0f); }
 SKY_D float distance2(float3 a, float3 b) { float3 d = a - b; return dot(d, d); }
 
-// MAT: SkyMaterialType.  `fetches` (optional) receives the number of texture fetches issued.
+// One SampleSigmaT(pos, height01) evaluation split at its texture fetches, so a caller can keep several evaluations
+// in flight: issue() starts the position-only fetches, advance() consumes them and starts the dependent fetch,
+// finish() returns sigma_t.  SampleSigmaT() below is the three in a row.  `fetches` counts texture
+// fetches as the reference issues them.
+//
+// Exact early-out of DEFAULT0: sigma_t = Remap01(base, detail', 1) * height01 * density with base = cloud_map.r *
+// CalHeightMask(cloud_map.g, height01).  Where the weather map leaves no cloud (base == 0) the result is
+// clamp(-detail' / (1 - detail'), 0, 1) = 0 for every detail' in [0, 1], i.e. for every texel when uDetailParam keeps
+// detail' in that range (checked on the host: MaterialParams::m0_zero_base_is_zero).  Such evaluations -- most of the
+// clear-air steps of a march -- end before the displacement blend and the detail (3-D) fetch.  DEFAULT1 has the same
+// early-out in the shader itself (:22).
+template <int MAT, bool HW>
+struct SigmaEval {
+    float3 pos;
+    float height01;
+    bool need;  // the dependent fetches are needed
+    // DEFAULT0 / DEFAULT1
+    Tap2 t_cm, t_d0, t_d1;
+    Tap3 t_dt;
+    uint2 c_cm, c_dt;
+    uint4 c_d0, c_d1;
+    float cloud_type[2], disp[4], detail, log2_d2, density;
+    // VOXEL
+    TapB t_vx;
+    uint2 c_vx;
+
+    SKY_D void issue(const MaterialParams& M, float3 p, float h01) {
+        pos = p; height01 = h01; need = true;
+        if (MAT == SKY_MATERIAL_DEFAULT0 || MAT == SKY_MATERIAL_DEFAULT1) {
+            const SkyMaterialCommonBufferData& mc = M.m.common;
+            log2_d2 = __log2f(distance2(pos, M.camera_pos));
+            const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
+            int lc = level_from_log2(log2_d2, M.lod_h_cloud_map, M.cloud_map.levels);
+            float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
+            if (HW) {
+                float4 c = sample2d_hw(M.cloud_map, cu, cv, lc);
+                cloud_type[0] = c.x; cloud_type[1] = c.y;
+            } else {
+                t_cm = tap2_repeat(M.cloud_map, cu, cv, lc);
+                c_cm = load_cell8(M.cloud_map, t_cm.cell);
+            }
+            if (MAT == SKY_MATERIAL_DEFAULT0) {
+                // the displacement fetches do not depend on the weather map: issued with it (one latency, not two),
+                // even though an evaluation that ends at the early-out below drops them
+                const SkySampleInfo& di = mc.uDisplacementSampleInfo;
+                int ld = level_from_log2(log2_d2, M.lod_h_displacement, M.displacement.levels);
+                float du = pos.x * di.frequency + di.bias[0], dv = pos.y * di.frequency + di.bias[1], dw = pos.z * di.frequency;
+                if (HW) {
+                    float4 a = sample2d_hw(M.displacement, du, dv, ld);
+                    float4 b = sample2d_hw(M.displacement, du, dw, ld);
+                    disp[0] = a.x; disp[1] = a.y; disp[2] = b.z; disp[3] = b.w;
+                } else {
+                    t_d0 = tap2_repeat(M.displacement, du, dv, ld);
+                    t_d1 = tap2_repeat(M.displacement, du, dw, ld);
+                    c_d0 = load_cell16(M.displacement, t_d0.cell);
+                    c_d1 = load_cell16(M.displacement, t_d1.cell);
+                }
+            }
+        } else if (MAT == SKY_MATERIAL_VOXEL) {
+            const SkyMaterialVoxelBufferData& m = M.m.u.voxel;
+            float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
+            float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
+            int level = level_from_log2(__log2f(distance2(pos, M.camera_pos)), M.lod_h_voxel, M.voxel.levels);
+            if (HW) {
+                detail = sample3d_hw(M.voxel, u, v, height01, level);
+            } else {
+                t_vx = tapb_border(M.voxel, u, v, height01, level);
+                c_vx = load_cellb(M.voxel, t_vx);
+            }
+        }
+    }
+
+    SKY_D void advance(const MaterialParams& M) {
+        if (MAT == SKY_MATERIAL_DEFAULT0) {  // VolumetricCloudDefaultMaterial0.glsl:18-32
+            const SkyMaterialCommonBufferData& mc = M.m.common;
+            const SkyMaterial0BufferData& m = M.m.u.m0;
+            if (!HW) { cloud_type[0] = blend_rg8(c_cm, 0, t_cm.a, t_cm.b); cloud_type[1] = blend_rg8(c_cm, 1, t_cm.a, t_cm.b); }
+            density = cloud_type[0] * CalHeightMask(cloud_type[1], height01);  // `base`
+            need = !(M.m0_zero_base_is_zero && density == 0.0f);
+            if (need) {
+                if (!HW) {
+                    disp[0] = blend_rgba8(c_d0, 0, t_d0.a, t_d0.b); disp[1] = blend_rgba8(c_d0, 1, t_d0.a, t_d0.b);
+                    disp[2] = blend_rgba8(c_d1, 2, t_d1.a, t_d1.b); disp[3] = blend_rgba8(c_d1, 3, t_d1.a, t_d1.b);
+                }
+                float3 displace_vector = f3(0.0f + disp[0] + disp[2], 0.0f + disp[1], 0.0f + disp[3]);
+                float3 p = pos + m.uDisplacementScale * displace_vector;
+                const SkySampleInfo& ti = mc.uDetailSampleInfo;
+                int lt = level_from_log2(__log2f(distance2(p, M.camera_pos)), M.lod_h_detail, M.detail.levels);
+                float tu = p.x * ti.frequency + ti.bias[0], tv = p.y * ti.frequency + ti.bias[1], tw = p.z * ti.frequency;
+                if (HW) {
+                    detail = sample3d_hw(M.detail, tu, tv, tw, lt);
+                } else {
+                    t_dt = tap3_repeat(M.detail, tu, tv, tw, lt);
+                    c_dt = load_cell8(M.detail, t_dt.cell);
+                }
+            }
+        } else if (MAT == SKY_MATERIAL_DEFAULT1) {  // VolumetricCloudDefaultMaterial1.glsl:14-29
+            const SkyMaterialCommonBufferData& mc = M.m.common;
+            const SkyMaterial1BufferData& m = M.m.u.m1;
+            if (!HW) { cloud_type[0] = blend_rg8(c_cm, 0, t_cm.a, t_cm.b); cloud_type[1] = blend_rg8(c_cm, 1, t_cm.a, t_cm.b); }
+            density = clampf((cloud_type[0] - m.uBaseDensityThreshold) * m.uBaseEdgeHardness, 0.0f, 1.0f);
+            density *= clampf((1 - height01) * m.uBaseHeightHardness, 0.0f, 1.0f);
+            need = !(density == 0);  // :22 returns before the detail fetch
+            if (need) {
+                const SkySampleInfo& ti = mc.uDetailSampleInfo;
+                int lt = level_from_log2(log2_d2, M.lod_h_detail, M.detail.levels);
+                float tu = pos.x * ti.frequency + ti.bias[0], tv = pos.y * ti.frequency + ti.bias[1], tw = pos.z * ti.frequency;
+                if (HW) {
+                    detail = sample3d_hw(M.detail, tu, tv, tw, lt);
+                } else {
+                    t_dt = tap3_repeat(M.detail, tu, tv, tw, lt);
+                    c_dt = load_cell8(M.detail, t_dt.cell);
+                }
+            }
+        }
+    }
+
+    SKY_D float finish(const MaterialParams& M, int* fetches = nullptr) {
+        if (MAT == SKY_MATERIAL_DEFAULT0) {
+            const SkyMaterialCommonBufferData& mc = M.m.common;
+            const SkyMaterial0BufferData& m = M.m.u.m0;
+            if (fetches) *fetches += 4;
+            if (!need) return 0.0f;
+            if (!HW) detail = blend_cell(c_dt, t_dt.a, t_dt.b, t_dt.c);
+            float dd = detail * m.uDetailParam[0] + m.uDetailParam[1];
+            return Remap01(density, dd, 1.0f) * height01 * mc.uDensity;
+        } else if (MAT == SKY_MATERIAL_DEFAULT1) {
+            const SkyMaterialCommonBufferData& mc = M.m.common;
+            const SkyMaterial1BufferData& m = M.m.u.m1;
+            if (fetches) *fetches += need ? 2 : 1;
+            if (!need) return 0.0f;
+            if (!HW) detail = blend_cell(c_dt, t_dt.a, t_dt.b, t_dt.c);
+            float dd = (detail + m.uDetailBase) * m.uDetailScale;
+            dd *= fmaxf(clampf(height01 - m.uHeightCut, 0.0f, 1.0f), clampf(m.uEdgeCur - cloud_type[0], 0.0f, 1.0f));
+            return clampf(density - dd, 0.0f, 1.0f) * mc.uDensity * height01;
+        } else if (MAT == SKY_MATERIAL_MINIMAL) {  // VolumetricCloudMaterialMinimal.glsl:6-8
+            return M.m.u.minimal.uDensity;
+        } else {  // VolumetricCloudMaterialVoxel.glsl:12-17
+            if (fetches) *fetches += 1;
+            if (!HW) detail = t_vx.cell < 0 ? 0.0f : blend_cell(c_vx, t_vx.a, t_vx.b, t_vx.c);
+            return detail * M.m.u.voxel.uDensity;
+        }
+    }
+};
+
+// MAT: SkyMaterialType.  `fetches` (optional) receives the number of texture fetches the reference issues.
 template <int MAT, bool HW>
 SKY_D float SampleSigmaT(const MaterialParams& M, float3 pos, float height01, int* fetches = nullptr) {
-    if (MAT == SKY_MATERIAL_DEFAULT0) {  // VolumetricCloudDefaultMaterial0.glsl:18-32
-        const SkyMaterialCommonBufferData& mc = M.m.common;
-        const SkyMaterial0BufferData& m = M.m.u.m0;
-        // GetUVWLod (VolumetricCloudDefaultMaterialCommon.glsl:20-24) for the cloud map and the displacement map: same pos
-        float d2 = distance2(pos, M.camera_pos);
-        const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
-        const SkySampleInfo& di = mc.uDisplacementSampleInfo;
-        int lc = level_from_distance2(d2, ci.k_lod, mc.uLodBias, M.thr2_cloud_map, M.cloud_map.levels);
-        int ld = level_from_distance2(d2, di.k_lod, mc.uLodBias, M.thr2_displacement, M.displacement.levels);
-        float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
-        float du = pos.x * di.frequency + di.bias[0], dv = pos.y * di.frequency + di.bias[1], dw = pos.z * di.frequency;
-        float cloud_type[2];
-        float d0[4], d1[4];
-        if (HW) {
-            float4 c = sample2d_hw(M.cloud_map, cu, cv, lc);
-            cloud_type[0] = c.x; cloud_type[1] = c.y;
-            float4 a = sample2d_hw(M.displacement, du, dv, ld);
-            float4 b = sample2d_hw(M.displacement, du, dw, ld);
-            d0[0] = a.x; d0[1] = a.y; d1[2] = b.z; d1[3] = b.w;
-        } else {
-            sample2d_repeat_exact<2>(M.cloud_map, cu, cv, lc, cloud_type);
-            sample2d_repeat_exact<4>(M.displacement, du, dv, ld, d0);
-            sample2d_repeat_exact<4>(M.displacement, du, dw, ld, d1);
-        }
-        float3 displace_vector = f3(0.0f + d0[0] + d1[2], 0.0f + d0[1], 0.0f + d1[3]);
-        pos = pos + m.uDisplacementScale * displace_vector;
-        const SkySampleInfo& ti = mc.uDetailSampleInfo;
-        int lt = level_from_distance2(distance2(pos, M.camera_pos), ti.k_lod, mc.uLodBias, M.thr2_detail, M.detail.levels);
-        float tu = pos.x * ti.frequency + ti.bias[0], tv = pos.y * ti.frequency + ti.bias[1], tw = pos.z * ti.frequency;
-        float detail = HW ? sample3d_hw(M.detail, tu, tv, tw, lt) : sample3d_repeat_exact(M.detail, tu, tv, tw, lt);
-        detail = detail * m.uDetailParam[0] + m.uDetailParam[1];
-        if (fetches) *fetches += 4;
-        return Remap01(cloud_type[0] * CalHeightMask(cloud_type[1], height01), detail, 1.0f) * height01 * mc.uDensity;
-    } else if (MAT == SKY_MATERIAL_DEFAULT1) {  // VolumetricCloudDefaultMaterial1.glsl:14-29
-        const SkyMaterialCommonBufferData& mc = M.m.common;
-        const SkyMaterial1BufferData& m = M.m.u.m1;
-        float d2 = distance2(pos, M.camera_pos);
-        const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
-        int lc = level_from_distance2(d2, ci.k_lod, mc.uLodBias, M.thr2_cloud_map, M.cloud_map.levels);
-        float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
-        float cloud_type[2];
-        if (HW) {
-            float4 c = sample2d_hw(M.cloud_map, cu, cv, lc);
-            cloud_type[0] = c.x; cloud_type[1] = c.y;
-        } else {
-            sample2d_repeat_exact<2>(M.cloud_map, cu, cv, lc, cloud_type);
-        }
-        if (fetches) *fetches += 1;
-        float density = clampf((cloud_type[0] - m.uBaseDensityThreshold) * m.uBaseEdgeHardness, 0.0f, 1.0f);
-        density *= clampf((1 - height01) * m.uBaseHeightHardness, 0.0f, 1.0f);
-        if (density == 0) return 0.0f;
-        const SkySampleInfo& ti = mc.uDetailSampleInfo;
-        int lt = level_from_distance2(d2, ti.k_lod, mc.uLodBias, M.thr2_detail, M.detail.levels);
-        float tu = pos.x * ti.frequency + ti.bias[0], tv = pos.y * ti.frequency + ti.bias[1], tw = pos.z * ti.frequency;
-        float detail = HW ? sample3d_hw(M.detail, tu, tv, tw, lt) : sample3d_repeat_exact(M.detail, tu, tv, tw, lt);
-        if (fetches) *fetches += 1;
-        detail = (detail + m.uDetailBase) * m.uDetailScale;
-        detail *= fmaxf(clampf(height01 - m.uHeightCut, 0.0f, 1.0f), clampf(m.uEdgeCur - cloud_type[0], 0.0f, 1.0f));
-        return clampf(density - detail, 0.0f, 1.0f) * mc.uDensity * height01;
-    } else if (MAT == SKY_MATERIAL_MINIMAL) {  // VolumetricCloudMaterialMinimal.glsl:6-8
-        return M.m.u.minimal.uDensity;
-    } else {  // VolumetricCloudMaterialVoxel.glsl:12-17
-        const SkyMaterialVoxelBufferData& m = M.m.u.voxel;
-        float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
-        float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
-        int level = level_from_distance2(distance2(pos, M.camera_pos), m.uSampleLodK, m.uLodBias, M.thr2_voxel, M.voxel.levels);
-        float density = HW ? sample3d_hw(M.voxel, u, v, height01, level) : sample3d_border_exact(M.voxel, u, v, height01, level);
-        if (fetches) *fetches += 1;
-        return density * m.uDensity;
-    }
+    SigmaEval<MAT, HW> e;
+    e.issue(M, pos, height01);
+    e.advance(M);
+    return e.finish(M, fetches);
 }
 
 // Call `f.template operator()<MAT, HW>()` for the runtime (material type, filtering) pair.

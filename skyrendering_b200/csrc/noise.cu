@@ -174,11 +174,11 @@ __global__ void __launch_bounds__(256) k_mip_level(const __grid_constant__ MipPa
     P.dst[idx] = uint8_t((2 * sum + n) / (2 * n));
 }
 
-// Corner packing of level 0 (see MipView::cells).  One thread per cell.
+// Corner packing of one level (see MipView::cells).  One thread per cell.
 struct PackParams {
     const uint8_t* src;
     uint8_t* dst;
-    int w, h, d, channels, border, cw, ch, cd;
+    int w, h, d, channels, border, is3d, cw, ch, cd, pad_xy, pad_z;
 };
 __global__ void __launch_bounds__(256) k_pack_cells(const __grid_constant__ PackParams P) {
     size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -187,14 +187,13 @@ __global__ void __launch_bounds__(256) k_pack_cells(const __grid_constant__ Pack
     int ci = int(idx % P.cw);
     size_t t = idx / P.cw;
     int cj = int(t % P.ch), ck = int(t / P.ch);
-    const bool is3d = P.d > 1;
-    const int corners = is3d ? 8 : 4;
+    const int corners = P.is3d ? 8 : 4;
     uint8_t* out = P.dst + idx * size_t(corners) * P.channels;
     for (int n = 0; n < corners; ++n) {
         int x = ci + (n & 1), y = cj + ((n >> 1) & 1), z = ck + ((n >> 2) & 1);
         bool inside = true;
         if (P.border) {
-            x -= 1; y -= 1; if (is3d) z -= 1;  // cell index = base texel + 1
+            x -= P.pad_xy; y -= P.pad_xy; if (P.is3d) z -= P.pad_z;
             inside = x >= 0 && x < P.w && y >= 0 && y < P.h && z >= 0 && z < P.d;
         } else {
             x %= P.w; y %= P.h; z %= P.d;
@@ -231,10 +230,17 @@ int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, in
     t.bytes = off * channels;
     SKY_CUDA(ctx, cudaMalloc(&t.data, t.bytes));
     v.base = t.data;
-    v.cell_w = border ? w + 1 : w;
-    v.cell_h = border ? h + 1 : h;
-    v.cell_d = t.is3d ? (border ? d + 1 : d) : 1;
-    t.cell_bytes = size_t(v.cell_w) * v.cell_h * v.cell_d * (t.is3d ? 8 : 4) * channels;
+    v.pad_xy = border ? 2 : 0;
+    v.pad_z = border && t.is3d ? 1 : 0;
+    size_t cells = 0;
+    for (int l = 0; l < levels; ++l) {
+        v.cell_off[l] = cells;
+        v.cell_w[l] = border ? v.w[l] + 3 : v.w[l];
+        v.cell_h[l] = border ? v.h[l] + 3 : v.h[l];
+        v.cell_d[l] = t.is3d ? (border ? v.d[l] + 1 : v.d[l]) : 1;
+        cells += size_t(v.cell_w[l]) * v.cell_h[l] * v.cell_d[l];
+    }
+    t.cell_bytes = cells * (t.is3d ? 8 : 4) * channels;
     SKY_CUDA(ctx, cudaMalloc(&t.cells, t.cell_bytes));
     v.cells = t.cells;
 
@@ -264,17 +270,19 @@ int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, in
 // level 0 is in t.data already: build levels 1.. and mirror every level into the CUDA array
 int launch_mip_chain(SkyContext* ctx, MipTextureDev& t) {
     MipView& v = t.view;
-    {
-        PackParams P{t.data, static_cast<uint8_t*>(t.cells), v.w[0], v.h[0], v.d[0], v.channels, t.border ? 1 : 0, v.cell_w, v.cell_h, v.cell_d};
-        size_t total = size_t(v.cell_w) * v.cell_h * v.cell_d;
-        k_pack_cells<<<unsigned((total + 255) / 256), 256, 0, ctx->stream>>>(P);
-        SKY_LAUNCH_CHECK(ctx);
-    }
     for (int l = 1; l < v.levels; ++l) {
         MipParams P{t.data + v.off[l - 1] * v.channels, t.data + v.off[l] * v.channels,
                     v.w[l - 1], v.h[l - 1], v.d[l - 1], v.w[l], v.h[l], v.d[l], v.channels};
         size_t total = size_t(v.w[l]) * v.h[l] * v.d[l] * v.channels;
         k_mip_level<<<unsigned((total + 255) / 256), 256, 0, ctx->stream>>>(P);
+        SKY_LAUNCH_CHECK(ctx);
+    }
+    const size_t cell_bytes = size_t(t.is3d ? 8 : 4) * v.channels;
+    for (int l = 0; l < v.levels; ++l) {
+        PackParams P{t.data + v.off[l] * v.channels, static_cast<uint8_t*>(t.cells) + v.cell_off[l] * cell_bytes, v.w[l], v.h[l], v.d[l], v.channels,
+                     t.border ? 1 : 0, t.is3d ? 1 : 0, v.cell_w[l], v.cell_h[l], v.cell_d[l], v.pad_xy, v.pad_z};
+        size_t total = size_t(v.cell_w[l]) * v.cell_h[l] * v.cell_d[l];
+        k_pack_cells<<<unsigned((total + 255) / 256), 256, 0, ctx->stream>>>(P);
         SKY_LAUNCH_CHECK(ctx);
     }
     for (int l = 0; l < v.levels; ++l) {

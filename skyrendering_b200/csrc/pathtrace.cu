@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
     float fp_x_lo = -INFINITY, fp_x_hi = INFINITY, fp_y_lo = -INFINITY, fp_y_hi = INFINITY;
     if (MAT == SKY_MATERIAL_VOXEL) {
         const SkyMaterialVoxelBufferData& vm = P.mat.m.u.voxel;
-        const float margin = 1e-3f;
-        float hu = 0.5f / float(P.mat.voxel.w[0]) + margin, hv = 0.5f / float(P.mat.voxel.h[0]) + margin;
+        // 0.2 texel beyond the half-texel apron: far more than the fp32 error of a position along the ray, and inside the
+        // quarter texel the padded cell layout allows without a range test (MipView::cells, voxel_tap)
+        float hu = 0.7f / float(P.mat.voxel.w[0]), hv = 0.7f / float(P.mat.voxel.h[0]);
         fp_x_lo = (-hu - vm.uSampleBias[0]) / vm.uSampleFrequency[0];
         fp_x_hi = (1.0f + hu - vm.uSampleBias[0]) / vm.uSampleFrequency[0];
         fp_y_lo = (-hv - vm.uSampleBias[1]) / vm.uSampleFrequency[1];
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                 float sig[kBatch];
                 bool live[kBatch];
 #pragma unroll
-                for (int k = 0; k < kBatch; ++k) live[k] = !(tk[k] < t_in || tk[k] > t_out) && !(tk[k] > t_max);
+                for (int k = 0; k < kBatch; ++k) live[k] = tk[k] >= t_in && tk[k] <= t_out && tk[k] <= t_max;  // NaN bounds (ray inside a footprint edge plane): not live, and sigma_t is 0 there
                 if (MAT == SKY_MATERIAL_VOXEL && !HW && ray_magnified) {
                     const SkyMaterialVoxelBufferData& vm = P.mat.m.u.voxel;
                     VoxelTap tap[kBatch];
@@ -388,15 +389,13 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                         float height01 = clampf((pos.z - P.c.uBottomAltitude) * inv_thickness, 0.0f, 1.0f);
                         float u = pos.x * vm.uSampleFrequency[0] + vm.uSampleBias[0];
                         float v = pos.y * vm.uSampleFrequency[1] + vm.uSampleBias[1];
-                        tap[k] = voxel_tap(P.mat.voxel, u, v, height01);  // outside the grid: border, the exact empty-space test
-                        if (!live[k]) tap[k].cell = kVoxelTapBorder;
-                        live[k] = tap[k].cell != kVoxelTapBorder;
+                        tap[k] = voxel_tap(P.mat.voxel, u, v, height01);  // live: inside the padded cell range, no test
                     }
                     uint2 cell[kBatch];
 #pragma unroll
-                    for (int k = 0; k < kBatch; ++k) cell[k] = voxel_tap_load(P.mat.voxel, tap[k]);
+                    for (int k = 0; k < kBatch; ++k) cell[k] = voxel_tap_load(P.mat.voxel, tap[k], live[k]);
 #pragma unroll
-                    for (int k = 0; k < kBatch; ++k) sig[k] = voxel_tap_blend(tap[k], cell[k]) * vm.uDensity;
+                    for (int k = 0; k < kBatch; ++k) sig[k] = live[k] ? blend_cell(cell[k], tap[k].a, tap[k].b, tap[k].c) * vm.uDensity : 0.0f;
                 } else {  // other materials, hardware filtering, rays reaching minified (NEAREST mip level) distances: the general sampler
 #pragma unroll
                     for (int k = 0; k < kBatch; ++k) {

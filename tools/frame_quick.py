@@ -6,7 +6,7 @@ from skyrendering_b200 import abi
 from skyrendering_b200.renderer import Renderer
 from tests.parity import oracle_library, rel_rms, run_cloud_frames
 name = os.environ.get('SKYB200_LIB', 'default').split('/')[-1]
-for scene in ("c3", "c1"):
+for scene in (() if os.environ.get("QUICK") else ("c3", "c1")):
     g = run_cloud_frames(scene, 384, 216, abi.cuda_library(), frames=4, device="cuda")
     o = run_cloud_frames(scene, 384, 216, oracle_library(), frames=4, device="cpu")
     print(name, scene, " ".join(f"{k} {rel_rms(g[k], o[k]):.2e}" for k in ("shadow", "froxel", "render", "reconstruct", "hdr")), flush=True)
