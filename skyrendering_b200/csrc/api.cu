@@ -122,6 +122,26 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     int rc = 0;
     rc |= sky_alloc(ctx, ctx->transmittance, 256, 64);   // Atmosphere.cpp:11-12
     rc |= sky_alloc(ctx, ctx->multiscattering, 32, 32);  // Atmosphere.cpp:17-18
+    if (!rc) {
+        // GL_LINEAR + CLAMP_TO_EDGE texture views over the LUT memory (Samplers.cpp linear_clamp_no_mipmap)
+        auto make_tex = [](const Lut<float4>& l, cudaTextureObject_t* out) {
+            cudaResourceDesc res{};
+            res.resType = cudaResourceTypePitch2D;
+            res.res.pitch2D.devPtr = l.p;
+            res.res.pitch2D.desc = cudaCreateChannelDesc<float4>();
+            res.res.pitch2D.width = size_t(l.w);
+            res.res.pitch2D.height = size_t(l.h);
+            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(float4);
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 1;
+            return cudaCreateTextureObject(out, &res, &td, nullptr) == cudaSuccess ? 0 : 1;
+        };
+        rc |= make_tex(ctx->transmittance, &ctx->transmittance_tex);
+        rc |= make_tex(ctx->multiscattering, &ctx->multiscattering_tex);
+    }
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);  // VolumetricCloud.cpp:52,102-105
     if (cudaMalloc(&ctx->blue_noise, 64 * 64 * sizeof(uint16_t)) != cudaSuccess) rc = 1;
     if (cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) rc = 1;
@@ -150,6 +170,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
     if (ctx->blue_noise) cudaFree(ctx->blue_noise);
+    if (ctx->transmittance_tex) cudaDestroyTextureObject(ctx->transmittance_tex);
+    if (ctx->multiscattering_tex) cudaDestroyTextureObject(ctx->multiscattering_tex);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->ray_setup) cudaFree(ctx->ray_setup);
     if (ctx->ray_raw) cudaFree(ctx->ray_raw);

@@ -45,7 +45,7 @@ SKY_D float3 GetExtinction(const SkyAtmosphereBufferData& u, float altitude) {
 }
 
 // Atmosphere.glsl:220-295.  MS = MULTISCATTERING_COMPUTE_PROGRAM permutation.
-template <bool MS>
+template <bool MS, bool TEXLUT = false>
 SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture,
                                        const LutView& multiscattering_texture, float start_i, float3 earth_center,
                                        float3 start_position, float3 view_direction, float3 sun_direction,
@@ -88,14 +88,14 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
         float3 transmittance_i = lut_exp3(-extinction_i * dx);
         float3 up_direction_i = normalize(position_i - earth_center);
         float mu_s_i = dot(sun_direction, up_direction_i);
-        float3 luminance_i = scattering_with_phase_i * atm.GetSunVisibility(transmittance_texture, r_i, mu_s_i);
+        float3 luminance_i = scattering_with_phase_i * atm.template GetSunVisibility<TEXLUT>(transmittance_texture, r_i, mu_s_i);
         if (!MS) {
             // GetMultiscatteringContribution, :169-178
             float x_mu_s = mu_s_i * 0.5f + 0.5f;
             float x_r = (r_i - u.bottom_radius) / (u.top_radius - u.bottom_radius);
             float uu = 0.5f / float(multiscattering_texture.w) + x_mu_s * (1.0f - 1.0f / float(multiscattering_texture.w));
             float vv = 0.5f / float(multiscattering_texture.h) + x_r * (1.0f - 1.0f / float(multiscattering_texture.h));
-            float3 multiscattering_contribution = xyz(sample_lut2d(multiscattering_texture, uu, vv));
+            float3 multiscattering_contribution = xyz(sample_lut2d_sel<TEXLUT>(multiscattering_texture, uu, vv));
             luminance_i += u.multiscattering_mask * multiscattering_contribution * scattering_i;
             luminance_i *= f3(u.solar_illuminance);
         }
@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
             transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
         } else {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
-            luminance = ComputeScatteredLuminance<false>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
-                                                         view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused);
+            luminance = ComputeScatteredLuminance<false, true>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                               view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused);
         }
     }
     if (P.froxel.p) luminance *= SampleRayScatterVisibility(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);
@@ -452,12 +452,12 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.atm.u = ctx->atm;
     P.r = ctx->render;
     P.cfg = ctx->lut_cfg;
-    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
-    P.multiscattering = LutView{ctx->multiscattering.p, ctx->multiscattering.w, ctx->multiscattering.h, 1};
-    P.sky_lum = LutView{ctx->sky_lum.p, ctx->sky_lum.w, ctx->sky_lum.h, 1};
-    P.sky_trans = LutView{ctx->sky_trans.p, ctx->sky_trans.w, ctx->sky_trans.h, 1};
-    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d};
-    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d};
+    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1, ctx->transmittance_tex};
+    P.multiscattering = LutView{ctx->multiscattering.p, ctx->multiscattering.w, ctx->multiscattering.h, 1, ctx->multiscattering_tex};
+    P.sky_lum = LutView{ctx->sky_lum.p, ctx->sky_lum.w, ctx->sky_lum.h, 1, 0};
+    P.sky_trans = LutView{ctx->sky_trans.p, ctx->sky_trans.w, ctx->sky_trans.h, 1, 0};
+    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d, 0};
+    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, 0};
     P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
     P.blue_noise = ctx->blue_noise;
     P.sky_lum_out = ctx->sky_lum.p; P.sky_trans_out = ctx->sky_trans.p;
@@ -475,7 +475,7 @@ RenderParams make_render_params(SkyContext* ctx) {
 int launch_atmosphere_bake(SkyContext* ctx) {
     BakeParams P{};
     P.atm.u = ctx->atm;
-    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
+    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1, 0};
     P.transmittance_out = ctx->transmittance.p;
     P.multiscattering_out = ctx->multiscattering.p;
     P.ms_w = ctx->multiscattering.w; P.ms_h = ctx->multiscattering.h;

@@ -9,6 +9,7 @@
 struct LutView {
     const float4* p;
     int w, h, d;
+    cudaTextureObject_t tex;  // optional (2-D LUTs): LINEAR + CLAMP_TO_EDGE over the same memory, see sample_lut2d_hw
 };
 
 // GL_LINEAR + CLAMP_TO_EDGE on an RGBA32F image: u*w - 0.5, floor, fract (GL 4.6 section 8.14.2)
@@ -22,6 +23,15 @@ SKY_D float4 sample_lut2d(const LutView& t, float u, float v) {
     float4 t00 = __ldg(t.p + j0 * t.w + i0), t10 = __ldg(t.p + j0 * t.w + i1);
     float4 t01 = __ldg(t.p + j1 * t.w + i0), t11 = __ldg(t.p + j1 * t.w + i1);
     return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+}
+
+// The same fetch through the texture unit (8-bit interpolation weights: an error of at most 1/512 of the difference
+// between neighbouring texels, ~1e-4 relative on these smooth LUTs).  Only the per-pixel raymarch of the composite
+// K6 -- a frame, tolerance 1e-2 relative RMS, 40 steps x 2 LUT fetches per ground pixel -- uses it.
+template <bool TEXLUT>
+SKY_D float4 sample_lut2d_sel(const LutView& t, float u, float v) {
+    if (TEXLUT) return tex2D<float4>(t.tex, u, v);
+    return sample_lut2d(t, u, v);
 }
 
 SKY_D float4 sample_lut3d(const LutView& t, float u, float v, float w) {
@@ -79,6 +89,7 @@ struct AtmosphereModel {
         return false;
     }
     // Atmosphere.glsl:90-108; GetTextureCoordFromUnitRange :53-55
+    template <bool TEXLUT = false>
     SKY_D float3 GetTransmittanceToTopAtmosphereBoundary(const LutView& tex, float r, float mu) const {
         float H = sqrtf(u.top_radius * u.top_radius - u.bottom_radius * u.bottom_radius);
         float rho = SafeSqrt(r * r - u.bottom_radius * u.bottom_radius);
@@ -89,13 +100,14 @@ struct AtmosphereModel {
         float x_r = rho / H;
         float uu = 0.5f / float(tex.w) + x_mu * (1.0f - 1.0f / float(tex.w));
         float vv = 0.5f / float(tex.h) + x_r * (1.0f - 1.0f / float(tex.h));
-        return xyz(sample_lut2d(tex, uu, vv));
+        return xyz(sample_lut2d_sel<TEXLUT>(tex, uu, vv));
     }
     // Atmosphere.glsl:110-117
+    template <bool TEXLUT = false>
     SKY_D float3 GetSunVisibility(const LutView& tex, float r, float mu_s) const {
         float sin_theta_h = u.bottom_radius / r;
         float cos_theta_h = -sqrtf(fmaxf(1.0f - sin_theta_h * sin_theta_h, 0.0f));
-        return GetTransmittanceToTopAtmosphereBoundary(tex, r, mu_s) *
+        return GetTransmittanceToTopAtmosphereBoundary<TEXLUT>(tex, r, mu_s) *
                smoothstepf(-sin_theta_h * u.sun_angular_radius, sin_theta_h * u.sun_angular_radius, mu_s - cos_theta_h);
     }
 };

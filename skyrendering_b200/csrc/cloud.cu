@@ -715,9 +715,9 @@ CloudParams make_cloud_params(SkyContext* ctx, const SkyCloudCommonBufferData& c
     P.inv_thickness = 1.0f / (c.uTopAltitude - c.uBottomAltitude);
     P.atm.u = ctx->atm;
     make_material_params(ctx, c.uCameraPos, P.mat);
-    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1};
-    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d};
-    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d};
+    P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1, 0};
+    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d, 0};
+    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, 0};
     P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
     P.blue_noise = ctx->blue_noise;
     P.counters = ctx->counters;

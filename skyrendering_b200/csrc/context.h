@@ -68,6 +68,7 @@ struct SkyContext {
     // K1-K5
     Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
     Lut<half4> env;  // [6][S][S]
+    cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0;  // LINEAR views of the two 2-D bake LUTs (K6 raymarch)
     uint16_t* blue_noise = nullptr;  // 64x64 u16
 
     // materials

@@ -159,22 +159,12 @@ SKY_D uint2 voxel_tap_load(const MipView& t, const VoxelTap& tap, bool live) {  
 
 // ---- hardware path ----------------------------------------------------------------------------------
 // LINEAR on level 0 and POINT over the mip chain are two texture objects (a CUDA texture object has one filter mode)
-#ifndef SKY_HW_HANDLE_SELECT
-#define SKY_HW_HANDLE_SELECT 0
-#endif
+// (one TEX with the handle selected per lane measured 20 % slower than the branch: 534 vs 445 us for K16 at 4K)
 SKY_D float4 sample2d_hw(const MipView& t, float u, float v, int level) {
-#if SKY_HW_HANDLE_SELECT  // one TEX with a per-lane handle
-    return tex2DLod<float4>(level < 0 ? t.tex_linear : t.tex_point, u, v, float(max(level, 0)));
-#else
     return level < 0 ? tex2DLod<float4>(t.tex_linear, u, v, 0.0f) : tex2DLod<float4>(t.tex_point, u, v, float(level));
-#endif
 }
 SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, int level) {
-#if SKY_HW_HANDLE_SELECT
-    return tex3DLod<float>(level < 0 ? t.tex_linear : t.tex_point, u, v, w, float(max(level, 0)));
-#else
     return level < 0 ? tex3DLod<float>(t.tex_linear, u, v, w, 0.0f) : tex3DLod<float>(t.tex_point, u, v, w, float(level));
-#endif
 }
 
 // ---- SampleSigmaT ------------------------------------------------------------------------------------
