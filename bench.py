@@ -121,6 +121,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full capture
+    of the same launch shape (profiles/traffic_r01.json, written by tools/ncu_traffic.py); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        entry = json.load(f).get(kernel)
+    return None if entry is None else entry["dram_read_bytes"] + entry["dram_write_bytes"]
+
+
 def workload_config(args, reference=False):
     return {
         "workload": "c5 voxel-cloud path tracer 1280x720 (bin/config_voxel.json, synthetic 126x154x86 R8 grid at the wdas_cloud_sixteenth bounds), "
@@ -141,7 +152,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--spp", type=int, default=64, help="samples per pixel per step (whole job, all ranks)")
+    ap.add_argument("--spp", type=int, default=256, help="samples per pixel per step (whole job, all ranks): a quarter of the 1024-spp job")
     ap.add_argument("--hw-filtering", action="store_true", help="texture-unit filtering (8-bit weights) instead of exact fp32")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-frame", action="store_true")
@@ -248,10 +259,13 @@ def main():
     h2d = 384 + 16 + 16  # common block + region + frame ids: the only inputs of a step
     d2h = PT_W * PT_H * 16
 
-    # dominant kernel K19 on this rank: duration, work counters, roofline
-    k19_ms = kernel_ms(lambda: rp.ctx.pt_samples(common_pt, my_begin, max(my_count, 1), region), reps=2)
+    # dominant kernel K19 on this rank: duration, work counters, roofline -- on ONE launch (<= 64 kFrameIds; a step
+    # issues ceil(my_count / 72) such launches).  The counting variant walks every tentative collision of the
+    # reference algorithm (no dead-stream cut): its totals are the algorithmic work of the launch.
+    roof_frames = max(1, min(my_count, 64))
+    k19_ms = kernel_ms(lambda: rp.ctx.pt_samples(common_pt, my_begin, roof_frames, region), reps=2)
     rp.ctx.counters_enable(True)
-    rp.ctx.pt_samples(common_pt, my_begin, max(my_count, 1), region)
+    rp.ctx.pt_samples(common_pt, my_begin, roof_frames, region)
     rp.ctx.sync()
     cnt = rp.ctx.counters()
     rp.ctx.counters_enable(False)
@@ -266,9 +280,11 @@ def main():
     lookups_per_s = lookups / (k19_ms * 1e-3)
     pt_roofline = {
         "kernel": "k19_path_trace", "bound": "tex", "achieved": lookups_per_s / 1e9, "peak": tex_peak / 1e9, "unit": "Gfetch/s",
-        "frac": lookups_per_s / tex_peak, "traffic": None,
-        "note": "grid (1.7 MB + mips) is L2-resident: trilinear-lookup rate vs the same-run tex-pipe microbenchmark; "
-                "the kernel is bound by the sequential RNG/log chain of null collisions, see DESIGN.md",
+        "frac": lookups_per_s / tex_peak, "traffic": ncu_traffic("k19_path_trace"),
+        "launch": f"{PT_W}x{PT_H} x {roof_frames} kFrameIds",
+        "note": "grid (14 MB corner-packed, L2-resident): algorithmic trilinear lookups (what the reference's loop issues inside the "
+                "voxel footprint) per second vs the same-run tex-pipe microbenchmark; the kernel is bound by instruction issue "
+                "on the RNG / log / software-trilinear chain, see DESIGN.md",
         "hbm": {"achieved": lookups * 8 / (k19_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": lookups * 8 / (k19_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind},
         "lookups_per_launch": lookups, "tentative_collisions_per_launch": collisions, "paths_per_launch": int(cnt[abi.CNT_PT_PATHS]),
@@ -293,7 +309,11 @@ def main():
             scf.frame(common, cloud, depth, hdr)
             state["u"] = (common, cloud)
 
-        frame_ms = timed_steps(frame_step, max(args.steps, 5), max(args.warmup, 8))
+        frame_serial_ms = timed_steps(frame_step, max(args.steps, 5), max(args.warmup, 8))
+        # the product's frame mode: the two independent halves of the frame on two streams (sky_set_frame_overlap)
+        rf.ctx.set_frame_overlap(True)
+        frame_ms = timed_steps(frame_step, max(args.steps, 5), 3)
+        rf.ctx.set_frame_overlap(False)
         common, cloud = state["u"]
         parts = {
             "bake_K1_K2": kernel_ms(rf.earth_update), "luts_K3_K5": kernel_ms(rf.atmosphere_render_luts),
@@ -324,12 +344,14 @@ def main():
         depth_host = torch.from_numpy(depth_np).pin_memory()
         e2e_frame_ms = timed_steps(lambda: rf.ctx.cloud_frame_host(common, cloud, depth_host.numpy(), hdr_host.numpy()), 3, 1) if world == 1 else None
         frame = {
-            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "unit": "ms", "higher_is_better": False,
-            "frame_definition": "one AppWindow::HandleDisplayEvent: K1,K2 bake, K11-K13 shadow chain, K3-K5 LUTs, K6 composite, K14-K18 cloud chain",
+            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "ms_per_frame_single_stream": frame_serial_ms, "unit": "ms", "higher_is_better": False,
+            "frame_definition": "one AppWindow::HandleDisplayEvent: K1,K2 bake, K11-K13 shadow chain, K3-K5 LUTs, K6 composite, K14-K18 cloud chain; "
+                                "ms_per_frame with sky_set_frame_overlap (shadow + cloud chain beside LUTs + composite on a second stream), "
+                                "parts_ms each kernel group alone",
             "parts_ms": parts, "gpu_launches": 15,
             "sigma_evals_per_frame": evals, "tex_fetches_per_frame": fetches,
             "roofline": {"kernel": "k16_render (+K14,K15)", "bound": "tex", "achieved": fetches / k16_s / 1e9, "peak": mix_peak / 1e9,
-                         "unit": "Gfetch/s", "frac": fetches / k16_s / mix_peak, "traffic": None,
+                         "unit": "Gfetch/s", "frac": fetches / k16_s / mix_peak, "traffic": ncu_traffic("k16_render"),
                          "peak_3d_trilinear_r8": tex_peak / 1e9, "peak_2d_bilinear_rg8": tex_peak_2d / 1e9,
                          "peak_source": "same-run microbenchmarks (coherent fetches over the L2-resident 128^3 R8 volume and the 512^2 RG8 map), "
                                         "combined for Material0's 3 x 2-D + 1 x 3-D fetches per SampleSigmaT"},
@@ -372,7 +394,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-            # per step and rank: K19 (persistent state machine) + K19b (ordered accumulate) per chunk of <= 72 frames
+            # per step and rank: K19 (persistent state machine) + K19b (ordered accumulate) per chunk of <= 72 kFrameIds
             "gpu_launches": args.steps * 2 * max(1, -(-my_count // 72)),
             "roofline": pt_roofline, "cpu_baseline": cpu_baseline, "frame_4k": frame,
         }

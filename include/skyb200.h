@@ -141,6 +141,11 @@ int SKY_FN(counters_enable)(SkyContext* ctx, int enable);
 /* Which filtering the material textures use: 0 = exact fp32 software filtering on gathered
  * texels (default; matches the oracle), 1 = hardware linear filtering (8-bit weights). */
 int SKY_FN(set_hw_filtering)(SkyContext* ctx, int enable);
+/* Opt-in overlap of the two independent halves of a frame (AppWindow::Render, AppWindow.cpp:148-175) on a second,
+ * internal stream: {cloud shadow chain K11-K13, K14-K17} run beside {K3-K5, composite K6}; K18 joins them.  Results are
+ * bit-identical.  While enabled, the work of cloud_shadow / cloud_frame_begin is ordered on the caller's stream at
+ * cloud_frame_end and in every other entry point (they join first), not at the return of those two calls. */
+int SKY_FN(set_frame_overlap)(SkyContext* ctx, int enable);
 
 /* Microbenchmark for the texture-pipe roofline: launches `iters` dependent-free trilinear R8
  * fetches per thread over the detail volume and returns texel-quads per second. */

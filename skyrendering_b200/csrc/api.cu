@@ -170,6 +170,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
     if (ctx->blue_noise) cudaFree(ctx->blue_noise);
+    if (ctx->lane2) { cudaStreamSynchronize(ctx->lane2); cudaStreamDestroy(ctx->lane2); }
+    for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2}) if (ev) cudaEventDestroy(ev);
     if (ctx->transmittance_tex) cudaDestroyTextureObject(ctx->transmittance_tex);
     if (ctx->multiscattering_tex) cudaDestroyTextureObject(ctx->multiscattering_tex);
     if (ctx->counters) cudaFree(ctx->counters);
@@ -185,9 +187,46 @@ void sky_ctx_destroy(SkyContext* ctx) {
     delete ctx;
 }
 
+// ---- frame overlap ------------------------------------------------------------------------------------------
+// A frame has two independent halves until the upscale: {K11-K13 shadow chain, K14-K17 cloud chain} only meet
+// {K1-K5 LUTs, K6 composite} at the froxels (K6 reads them), the LUTs (K16 reads them) and the HDR target (K18).  With
+// overlap enabled the first half runs on `lane2`, ordered against the caller's stream with events; nothing waits on
+// the host.  Every entry point outside this protocol joins the lanes first.
+namespace {
+struct LaneScope {  // launchers issue on ctx->stream: point it at lane2 for the scope
+    SkyContext* ctx; cudaStream_t saved;
+    LaneScope(SkyContext* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+    ~LaneScope() { ctx->stream = saved; }
+};
+int lanes_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lane2
+    if (!ctx->lane2_pending) return 0;
+    SKY_CUDA(ctx, cudaEventRecord(ctx->ev_lane2, ctx->lane2));
+    SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane2, 0));
+    ctx->lane2_pending = ctx->shadow_pending = ctx->pre_composite_recorded = ctx->lane2_reads_luts = false;
+    return 0;
+}
+int lane2_fork(SkyContext* ctx, cudaEvent_t after) {  // lane2 is ordered after `after` (recorded on the caller's stream)
+    SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lane2, after, 0));
+    ctx->lane2_pending = true;
+    return 0;
+}
+}  // namespace
+
+int sky_set_frame_overlap(SkyContext* ctx, int enable) {
+    if (int e = lanes_join(ctx)) return e;
+    if (enable && !ctx->lane2) {
+        SKY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane2, cudaStreamNonBlocking));
+        for (cudaEvent_t* ev : {&ctx->ev_fork, &ctx->ev_shadow, &ctx->ev_pre_composite, &ctx->ev_lane2})
+            SKY_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    }
+    ctx->overlap = enable != 0;
+    return 0;
+}
+
 const char* sky_last_error(SkyContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
 int sky_sync(SkyContext* ctx) {
+    if (int e = lanes_join(ctx)) return e;
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -200,6 +239,7 @@ int sky_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
 
 int sky_set_viewport(SkyContext* ctx, int w, int h) {
     if (w < 12 || h < 12) return sky_fail(ctx, "viewport too small");
+    if (int e = lanes_join(ctx)) return e;
     sky_peer_detach(ctx);  // the exported buffers are about to be reallocated
     ctx->width = w; ctx->height = h;
     int rc = 0;  // VolumetricCloud.cpp:120-136; histories zero-filled
@@ -217,6 +257,7 @@ int sky_set_viewport(SkyContext* ctx, int w, int h) {
 }
 
 int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
+    if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }
     ctx->atm = *a;
     return launch_atmosphere_bake(ctx);
 }
@@ -224,6 +265,7 @@ int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
 int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg) {
     if (cfg->sky_view_width < 2 || cfg->sky_view_height < 2 || cfg->aerial_perspective_depth < 2 || cfg->environment_size < 1)
         return sky_fail(ctx, "bad LUT sizes");
+    if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }  // (the shadow chain on lane2 does not touch the LUTs)
     ctx->render = *r;
     ctx->lut_cfg = *cfg;
     int rc = 0;
@@ -238,13 +280,28 @@ int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
 
 int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
     if (!ctx->sky_lum.p) return sky_fail(ctx, "atmosphere LUTs have not been baked");
+    if (ctx->overlap) {
+        if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }  // out-of-order use: a cloud frame is still open
+        if (ctx->shadow_pending) {  // K6 reads the god-ray froxels
+            SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_shadow, 0));
+            ctx->shadow_pending = false;
+        }
+        // what the cloud chain needs from the caller's stream (depth, LUTs) is complete here; K6 is not part of it
+        SKY_CUDA(ctx, cudaEventRecord(ctx->ev_pre_composite, ctx->stream));
+        ctx->pre_composite_recorded = true;
+        ctx->pre_composite_depth = depth;
+    }
     return launch_composite(ctx, depth, static_cast<half4*>(hdr), width, height);
 }
 
-int sky_noise_generate(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info) { return launch_noise(ctx, kind, info); }
+int sky_noise_generate(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info) {
+    if (int e = lanes_join(ctx)) return e;
+    return launch_noise(ctx, kind, info);
+}
 
 int sky_voxel_upload(SkyContext* ctx, const uint8_t* host_voxels, int dx, int dy, int dz) {
     if (dx < 1 || dy < 1 || dz < 1 || dx > 4096 || dy > 4096 || dz > 4096) return sky_fail(ctx, "voxel grid dimensions out of range");
+    if (int e = lanes_join(ctx)) return e;
     ctx->voxel.valid = false;
     if (int e = build_mip_texture(ctx, ctx->voxel, dx, dy, dz, 1, true)) return e;
     SKY_CUDA(ctx, cudaMemcpyAsync(ctx->voxel.data, host_voxels, size_t(dx) * dy * dz, cudaMemcpyHostToDevice, ctx->stream));
@@ -261,7 +318,18 @@ int sky_set_material(SkyContext* ctx, const SkyMaterialBlock* m) {
 
 int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");  // VolumetricCloud.cpp:169-170
-    return launch_cloud_shadow(ctx, *common);
+    if (!ctx->overlap) return launch_cloud_shadow(ctx, *common);
+    if (int e = lanes_join(ctx)) return e;
+    ctx->pre_composite_recorded = false;  // a new frame
+    SKY_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if (int e = lane2_fork(ctx, ctx->ev_fork)) return e;
+    {
+        LaneScope lane(ctx, ctx->lane2);
+        if (int e = launch_cloud_shadow(ctx, *common)) return e;
+    }
+    SKY_CUDA(ctx, cudaEventRecord(ctx->ev_shadow, ctx->lane2));
+    ctx->shadow_pending = true;
+    return 0;
 }
 
 int sky_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
@@ -269,21 +337,40 @@ int sky_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* commo
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (band_count < 1 || band_index < 0 || band_index >= band_count || band_rows < 0) return sky_fail(ctx, "bad band arguments");
     ctx->last_common = *common;  // cloud_frame_end runs K17/K18 with the same uniforms
+    if (!ctx->overlap) return launch_cloud_begin(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
+    // K14-K16 need the depth and the LUTs from the caller's stream -- complete before the composite if there was one --
+    // and the froxels, which are on lane2 already
+    if (!ctx->pre_composite_recorded || ctx->pre_composite_depth != depth) SKY_CUDA(ctx, cudaEventRecord(ctx->ev_pre_composite, ctx->stream));
+    if (int e = lane2_fork(ctx, ctx->ev_pre_composite)) return e;
+    ctx->pre_composite_recorded = false;
+    ctx->shadow_pending = false;  // from here on the caller's stream joins lane2 as a whole
+    ctx->lane2_reads_luts = true;
+    LaneScope lane(ctx, ctx->lane2);
     return launch_cloud_begin(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
 }
 
 int sky_cloud_frame(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
                     const float* depth, void* hdr) {
     if (int e = sky_cloud_frame_begin(ctx, common, cloud, depth, 0, 0, 1)) return e;
-    return launch_cloud_end(ctx, *common, depth, static_cast<half4*>(hdr));
+    return sky_cloud_frame_end(ctx, depth, hdr);
 }
 
 int sky_cloud_frame_end(SkyContext* ctx, const float* depth, void* hdr) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
-    return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr));
+    if (!ctx->overlap || !ctx->lane2_reads_luts) {
+        if (int e = lanes_join(ctx)) return e;
+        return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr));
+    }
+    {
+        LaneScope lane(ctx, ctx->lane2);  // K17 follows K16
+        if (int e = launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 1)) return e;
+    }
+    if (int e = lanes_join(ctx)) return e;  // K18 composites over what K6 wrote
+    return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 2);
 }
 
 int sky_peer_detach(SkyContext* ctx) {
+    if (int e = lanes_join(ctx)) return e;
     for (int k = 0; k < ctx->peer_world; ++k) {
         if (k == ctx->peer_rank) continue;
         if (ctx->peer_render[k]) cudaIpcCloseMemHandle(ctx->peer_render[k]);
@@ -296,6 +383,7 @@ int sky_peer_detach(SkyContext* ctx) {
 }
 
 int sky_peer_export(SkyContext* ctx, SkyPeerHandles* out) {
+    if (int e = lanes_join(ctx)) return e;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "SkyPeerHandles carries 64-byte IPC handles");
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (!ctx->my_flags) {
@@ -314,6 +402,7 @@ int sky_peer_export(SkyContext* ctx, SkyPeerHandles* out) {
 }
 
 int sky_peer_attach(SkyContext* ctx, int rank, int world_size, const SkyPeerHandles* all) {
+    if (int e = lanes_join(ctx)) return e;
     if (world_size < 1 || world_size > SKY_MAX_PEERS || rank < 0 || rank >= world_size) return sky_fail(ctx, "bad rank / world size");
     if (!ctx->my_flags) return sky_fail(ctx, "peer_export must be called first");
     sky_peer_detach(ctx);
@@ -355,6 +444,7 @@ int sky_cloud_frame_host(SkyContext* ctx, const SkyCloudCommonBufferData* common
 }
 
 int sky_pt_begin(SkyContext* ctx, const SkyPathTracingInit* init) {
+    if (int e = lanes_join(ctx)) return e;
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (init->prng != SKY_PRNG_WANG && init->prng != SKY_PRNG_PCG) return sky_fail(ctx, "unknown PRNG");
     if (init->environment_lighting < SKY_ENV_OFF || init->environment_lighting > SKY_ENV_GROUND_MULTI_BOUNCE) return sky_fail(ctx, "unknown environment lighting mode");
@@ -366,13 +456,18 @@ int sky_pt_begin(SkyContext* ctx, const SkyPathTracingInit* init) {
 
 int sky_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
                    const int32_t region[4]) {
+    if (int e = lanes_join(ctx)) return e;
     return launch_pt_samples(ctx, *common, frame_begin, count, region);
 }
 
-int sky_pt_resolve(SkyContext* ctx, uint32_t frame_count, void* hdr) { return launch_pt_resolve(ctx, frame_count, static_cast<half4*>(hdr)); }
+int sky_pt_resolve(SkyContext* ctx, uint32_t frame_count, void* hdr) {
+    if (int e = lanes_join(ctx)) return e;
+    return launch_pt_resolve(ctx, frame_count, static_cast<half4*>(hdr));
+}
 
 int sky_pt_samples_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
                         const int32_t region[4], float* accum_host) {
+    if (int e = lanes_join(ctx)) return e;
     if (int e = launch_pt_samples(ctx, *common, frame_begin, count, region)) return e;
     SKY_CUDA(ctx, cudaMemcpyAsync(accum_host, ctx->pt_accum.p, ctx->pt_accum.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -392,12 +487,14 @@ int sky_read_resource(SkyContext* ctx, int resource, void* host_dst, uint64_t by
     SkyResourceDesc d;
     if (int e = sky_get_resource(ctx, resource, &d)) return e;
     if (bytes != d.bytes) return sky_fail(ctx, "read_resource: size mismatch, expected " + std::to_string(d.bytes));
+    if (int e = lanes_join(ctx)) return e;
     SKY_CUDA(ctx, cudaMemcpyAsync(host_dst, d.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
 int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint64_t bytes) {
+    if (int e = lanes_join(ctx)) return e;
     switch (resource) {
         case SKY_RES_CLOUD_MAP: if (int e = build_mip_texture(ctx, ctx->cloud_map, 512, 512, 1, 2, false)) return e; break;
         case SKY_RES_DETAIL: if (int e = build_mip_texture(ctx, ctx->detail, 128, 128, 128, 1, false)) return e; break;
@@ -418,6 +515,7 @@ int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint
 }
 
 int sky_counters_enable(SkyContext* ctx, int enable) {
+    if (int e = lanes_join(ctx)) return e;
     ctx->counting = enable != 0;
     SKY_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     return 0;
@@ -428,6 +526,9 @@ int sky_set_hw_filtering(SkyContext* ctx, int enable) {
     return 0;
 }
 
-int sky_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) { return launch_tex_peak(ctx, mode, fetches_per_second); }
+int sky_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
+    if (int e = lanes_join(ctx)) return e;
+    return launch_tex_peak(ctx, mode, fetches_per_second);
+}
 
 }  // extern "C"

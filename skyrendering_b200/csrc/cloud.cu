@@ -852,33 +852,37 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
     return 0;
 }
 
-int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr) {
+int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr, int phases) {
     CloudParams P = make_cloud_params(ctx, c);
     P.depth = depth;
     P.hdr = hdr;
     P.reconstruct_out = ctx->reconstruct[0].p;
     P.reconstruct_prev = ctx->reconstruct[1].p;
     const int HW_ = P.width / 2, HH = P.height / 2;
-    const bool peer_frame = ctx->peer_band_frame;
-    PeerBarrierParams B{};
-    if (peer_frame) {
-        for (int k = 0; k < ctx->peer_world; ++k) B.peer_flags[k] = ctx->peer_flags[k];
-        B.my_flags = ctx->my_flags; B.rank = ctx->peer_rank; B.world = ctx->peer_world; B.epoch = ctx->peer_epoch;
-        B.offset = 0; B.signal = 1; B.wait = 1;  // my rows are everywhere; wait for everybody else's
-        k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+    if (phases & 1) {
+        const bool peer_frame = ctx->peer_band_frame;
+        PeerBarrierParams B{};
+        if (peer_frame) {
+            for (int k = 0; k < ctx->peer_world; ++k) B.peer_flags[k] = ctx->peer_flags[k];
+            B.my_flags = ctx->my_flags; B.rank = ctx->peer_rank; B.world = ctx->peer_world; B.epoch = ctx->peer_epoch;
+            B.offset = 0; B.signal = 1; B.wait = 1;  // my rows are everywhere; wait for everybody else's
+            k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+            SKY_LAUNCH_CHECK(ctx);
+            ctx->peer_band_frame = false;
+        }
+        k17_reconstruct<<<dim3(ceil_div(HW_, 16), ceil_div(HH, 8)), 128, 0, ctx->stream>>>(P);
+        if (peer_frame) {
+            B.offset = 8; B.signal = 1; B.wait = 0;  // K17 was the last reader of the exchanged buffers
+            k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+            SKY_LAUNCH_CHECK(ctx);
+        }
         SKY_LAUNCH_CHECK(ctx);
-        ctx->peer_band_frame = false;
     }
-    k17_reconstruct<<<dim3(ceil_div(HW_, 16), ceil_div(HH, 8)), 128, 0, ctx->stream>>>(P);
-    if (peer_frame) {
-        B.offset = 8; B.signal = 1; B.wait = 0;  // K17 was the last reader of the exchanged buffers
-        k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+    if (phases & 2) {
+        k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(P.height, 8)), 256, 0, ctx->stream>>>(P);
         SKY_LAUNCH_CHECK(ctx);
+        std::swap(ctx->reconstruct[0], ctx->reconstruct[1]);  // VolumetricCloud.cpp:421-422
     }
-    SKY_LAUNCH_CHECK(ctx);
-    k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(P.height, 8)), 256, 0, ctx->stream>>>(P);
-    SKY_LAUNCH_CHECK(ctx);
-    std::swap(ctx->reconstruct[0], ctx->reconstruct[1]);  // VolumetricCloud.cpp:421-422
     return 0;
 }
 

@@ -57,6 +57,16 @@ struct SkyContext {
     bool hw_filtering = false;
     bool counting = false;
 
+    // frame overlap (sky_set_frame_overlap): second lane of a frame, see api.cu
+    bool overlap = false;
+    cudaStream_t lane2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_shadow = nullptr, ev_pre_composite = nullptr, ev_lane2 = nullptr;
+    bool lane2_pending = false;        // lane2 holds work the caller's stream has not been ordered after
+    bool shadow_pending = false;       // ... of which the shadow chain (the composite waits for it)
+    bool pre_composite_recorded = false;
+    const float* pre_composite_depth = nullptr;
+    bool lane2_reads_luts = false;     // K16 / K17 are queued on lane2
+
     // uniforms last seen
     SkyAtmosphereBufferData atm{};
     SkyAtmosphereRenderBufferData render{};
@@ -149,7 +159,7 @@ int launch_mip_chain(SkyContext* ctx, MipTextureDev& t);                       /
 int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c);   // cloud.cu       K11-K13
 int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const SkyCloudBufferData& b, const float* depth,
                        int band_rows, int band_index, int band_count);         // cloud.cu       K14-K16
-int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr);  // K17,K18
+int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr, int phases = 3);  // K17 (1), K18 (2)
 int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32_t frame_begin, uint32_t count,
                       const int32_t region[4]);                                // pathtrace.cu   K19
 int launch_pt_resolve(SkyContext* ctx, uint32_t frame_count, half4* hdr);      // pathtrace.cu   K20

@@ -180,6 +180,28 @@ def test_hardware_filtering_within_frame_tolerance(libs):
     assert not np.array_equal(hw["render"], sw["render"])  # the two paths are really different code
 
 
+@pytest.mark.parametrize("scene", ["c3", "c1"])
+def test_frame_overlap_is_bit_identical(libs, scene):
+    """sky_set_frame_overlap runs {shadow chain, K14-K17} beside {LUTs, composite} on a second stream: same bits, frame
+    after frame (the temporal chain would amplify any race)."""
+    cuda, _ = libs
+    outs = []
+    for overlap in (False, True):
+        r = Renderer(scene, 640, 360, library=cuda)
+        r.ctx.set_frame_overlap(overlap)
+        r.prime()
+        depth_np = r.scene.ground_depth(640, 360)
+        depth, hdr = make_buffers(640, 360, depth_np, "cuda")
+        for f in range(6):
+            hdr.zero_()
+            r.frame(depth, hdr, 0.0)
+        r.ctx.sync()
+        outs.append((to_numpy(hdr).copy(), r.ctx.read(abi.RES_RECONSTRUCT).copy(), r.ctx.read(abi.RES_SHADOW_FROXEL).copy(),
+                     r.ctx.read(abi.RES_CLOUD_RENDER).copy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_banded_render_equals_full_and_is_deterministic(libs):
     cuda, _ = libs
     w, h = 768, 432

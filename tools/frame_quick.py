@@ -25,5 +25,12 @@ for scene in ("c3", "c1"):
         depth = torch.from_numpy(r.scene.ground_depth(w, h)).cuda(); hdr = torch.zeros((h, w, 4), dtype=torch.float16, device="cuda")
         for _ in range(4): r.frame(depth, hdr)
         common, cloud, _ = r.last_uniforms
+        def whole():
+            r.frame(depth, hdr)
+        t_serial = timed(whole)
+        r.ctx.set_frame_overlap(True)
+        t_overlap = timed(whole)
+        r.ctx.set_frame_overlap(False)
+        print(name, scene, f"hw={hw} frame {t_serial:.0f} us, with overlap {t_overlap:.0f} us", flush=True)
         print(name, scene, f"hw={hw} shadow {timed(lambda: r.ctx.cloud_shadow(common)):.0f} K6 {timed(lambda: r.ctx.composite(depth, hdr, w, h)):.0f} "
               f"K14-16 {timed(lambda: r.ctx.cloud_frame_begin(common, cloud, depth)):.0f} K17-18 {timed(lambda: r.ctx.cloud_frame_end(depth, hdr)):.0f} us", flush=True)

@@ -9,7 +9,7 @@ r.ctx.set_hw_filtering(bool(int(os.environ.get("HW", "0"))))
 r.upload_voxels(synthetic_voxel_grid()); r.prime()
 common, cloud, _ = r.cloud_update(0.0)
 r.ctx.cloud_shadow(common); r.atmosphere_render_luts(); r.path_trace_begin()
-for spp in (2, 8, 32):
+for spp in [int(x) for x in os.environ.get("SPP", "2,8,32").split(",")]:
     r.ctx.pt_samples(common, 1, spp, [0, 0, 1280, 720]); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); r.ctx.pt_samples(common, 1, spp, [0, 0, 1280, 720]); e1.record(); torch.cuda.synchronize()
