@@ -21,9 +21,11 @@ constexpr int kMarchSteps = SKY_K16_MARCH_STEPS;
 #ifndef SKY_K16_OCC
 #define SKY_K16_OCC 5  // resident 128-thread blocks per SM the register budget is cut for
 #endif
-#ifndef SKY_K16_WARP_8X4
-#define SKY_K16_WARP_8X4 1  // a warp renders an 8x4 block of rays (more alike than a 16x2 strip)
+#ifndef SKY_K16_BLOCK
+#define SKY_K16_BLOCK 128  // threads per block: 32, 64 or 128; a warp renders an 8x4 block of rays, warps pair up to 16 columns
 #endif
+constexpr int kK16Block = SKY_K16_BLOCK;
+constexpr int kK16TileW = kK16Block >= 64 ? 16 : 8, kK16TileH = kK16Block >= 64 ? kK16Block / 16 : 4;
 
 struct CloudParams {
     SkyCloudCommonBufferData c;  // VolumetricCloudCommon.glsl:6-28
@@ -323,17 +325,13 @@ SKY_D void ShadeDenseStep(const CloudParams& P, RayMarchContext& ctx, float sigm
 }
 
 template <int MAT, bool HW, bool COUNT>
-__global__ void __launch_bounds__(128, SKY_K16_OCC) k16_render(const __grid_constant__ CloudParams P) {
+__global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_render(const __grid_constant__ CloudParams P) {
     const SkyCloudCommonBufferData& c = P.c;
     const SkyCloudBufferData& b = P.b;
     const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
-#if SKY_K16_WARP_8X4
-    int px = blockIdx.x * 16 + int((threadIdx.x >> 5) & 1u) * 8 + int(threadIdx.x & 7u);
-    int row_in_band = blockIdx.y * 8 + int(threadIdx.x >> 6) * 4 + int((threadIdx.x >> 3) & 3u);
-#else
-    int px = blockIdx.x * 16 + (threadIdx.x & 15);
-    int row_in_band = blockIdx.y * 8 + (threadIdx.x >> 4);
-#endif
+    const int warp_in_block = int(threadIdx.x >> 5);
+    int px = blockIdx.x * kK16TileW + (kK16Block >= 64 ? (warp_in_block & 1) * 8 : 0) + int(threadIdx.x & 7u);
+    int row_in_band = blockIdx.y * kK16TileH + (kK16Block >= 64 ? (warp_in_block >> 1) * 4 : 0) + int((threadIdx.x >> 3) & 3u);
     int py = row_in_band;
     if (P.band_rows > 0) {
         // rows owned by this rank: ((py / band_rows) % band_count) == band_index
@@ -840,11 +838,11 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
         int my_bands = (bands_total - band_index + band_count - 1) / band_count;
         rows = my_bands * band_rows;
     }
-    dim3 grid(ceil_div(QW, 16), ceil_div(rows, 8));
+    dim3 grid(ceil_div(QW, kK16TileW), ceil_div(rows, kK16TileH));
     const bool count = ctx->counting;
     int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
-        if (count) k16_render<MAT, HW, true><<<grid, 128, 0, ctx->stream>>>(P);
-        else k16_render<MAT, HW, false><<<grid, 128, 0, ctx->stream>>>(P);
+        if (count) k16_render<MAT, HW, true><<<grid, kK16Block, 0, ctx->stream>>>(P);
+        else k16_render<MAT, HW, false><<<grid, kK16Block, 0, ctx->stream>>>(P);
         return 0;
     });
     if (rc) return sky_fail(ctx, "unknown material");

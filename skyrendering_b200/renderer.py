@@ -57,6 +57,39 @@ def synthetic_voxel_grid(dx=126, dy=154, dz=86, seed=0, blobs=64):
     return np.round(np.sqrt(dens) * 255.0).astype(np.uint8)
 
 
+def synthetic_voxel_grid_large(scale, seed=0, blobs=64, device="cuda", slab=16):
+    """The same field as synthetic_voxel_grid sampled `scale` times finer per axis (4: about wdas_cloud_quarter,
+    497 x 612 x 338; 16: about the full-resolution wdas bounds, 1987 x 2449 x 1351 = 6.6 GB), evaluated slab by slab
+    with torch on `device`.  The threshold is the 126 x 154 x 86 grid's, so occupancy stays about a quarter."""
+    import torch
+    dx, dy, dz = {4: (497, 612, 338), 16: (1987, 2449, 1351)}.get(scale, (126 * scale, 154 * scale, 86 * scale))  # SURVEY.md 8d
+    rng = np.random.RandomState(seed)
+    centres = torch.tensor(rng.uniform(0.2, 0.8, size=(blobs, 3)).astype(np.float32), device=device)
+    radii = torch.tensor(rng.uniform(0.06, 0.16, size=blobs).astype(np.float32), device=device)
+
+    def field_of(zs, ny, nx):
+        z = zs.view(-1, 1, 1)
+        y = torch.linspace(0, 1, ny, device=device).view(1, -1, 1)
+        x = torch.linspace(0, 1, nx, device=device).view(1, 1, -1)
+        f = torch.zeros((zs.numel(), ny, nx), device=device)
+        for b in range(blobs):
+            cx, cy, cz = centres[b]
+            f += torch.exp(-((x - cx) ** 2 + (y - cy) ** 2 + ((z - cz * 0.6 - 0.1) * 1.4) ** 2) / (radii[b] * radii[b]))
+        ripple = torch.sin(37.0 * x + 11.0 * z) * torch.sin(29.0 * y + 5.0 * x) * torch.sin(23.0 * z + 17.0 * y)
+        return f * (1.0 + 0.35 * ripple)
+
+    small = field_of(torch.linspace(0, 1, 86, device=device), 154, 126)
+    thresh = float(torch.quantile(small.flatten()[:: 7], 0.75))
+    fmax = float(small.max())
+    out = np.empty((dz, dy, dx), np.uint8)
+    zs_all = torch.linspace(0, 1, dz, device=device)
+    for z0 in range(0, dz, slab):
+        f = field_of(zs_all[z0:z0 + slab], dy, dx)
+        dens = torch.clamp((f - thresh) / max(fmax - thresh, 1e-6), 0.0, 1.0)
+        out[z0:z0 + slab] = torch.round(torch.sqrt(dens) * 255.0).to(torch.uint8).cpu().numpy()
+    return out
+
+
 class Renderer:
     def __init__(self, scene, width, height, library=None, device=0, stream=0, blue_noise=None):
         self.scene = scene if isinstance(scene, Scene) else Scene.from_file(scene_path(scene))
