@@ -87,11 +87,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = os.cpu_count()
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every core
     from tests.parity import oracle_library
     from skyrendering_b200 import abi
     from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
     orc = oracle_library()
-    cores = os.cpu_count()
+    use_all_host_threads(cores)
     r = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
     r.upload_voxels(synthetic_voxel_grid())
     r.prime()
@@ -119,6 +121,15 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def use_all_host_threads(n):
+    """The oracle is OpenMP code; make its runtime use `n` threads even if the launcher exported OMP_NUM_THREADS=1."""
+    import ctypes
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
 
 
 def ncu_traffic(kernel):
@@ -367,6 +378,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         from tests.parity import oracle_library
         orc = oracle_library()
+        use_all_host_threads(os.cpu_count())
         ro = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
         ro.upload_voxels(synthetic_voxel_grid())
         ro.prime()

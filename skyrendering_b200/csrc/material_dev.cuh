@@ -255,6 +255,9 @@ struct SigmaEval {
             if (!HW) { cloud_type[0] = blend_rg8(c_cm, 0, t_cm.a, t_cm.b); cloud_type[1] = blend_rg8(c_cm, 1, t_cm.a, t_cm.b); }
             density = cloud_type[0] * CalHeightMask(cloud_type[1], height01);  // `base`
             need = !(M.m0_zero_base_is_zero && density == 0.0f);
+#ifdef SKY_EXPERIMENT_FORCE_SKIP  // timing experiment only (wrong images): what an evaluation costs when it ends at the early-out
+            need = false;
+#endif
             if (need) {
                 if (!HW) {
                     disp[0] = blend_rgba8(c_d0, 0, t_d0.a, t_d0.b); disp[1] = blend_rgba8(c_d0, 1, t_d0.a, t_d0.b);
