@@ -340,6 +340,7 @@ struct samplerCube : Sampler {};      // levels[l].d = 6 faces; see textureCubeL
 struct sampler2DShadow : Sampler {};  // only in permutations that are off in every BASELINE config (mesh shadow map)
 inline float texture(const sampler2DShadow&, const vec3&) { return 1.0f; }
 inline vec4 texture(const Sampler& s, const vec2& uv) { return s.sample(uv.x, uv.y, 0.0f, 0.0f); }
+inline vec4 texture2D(const Sampler& s, const vec2& uv) { return s.sample(uv.x, uv.y, 0.0f, 0.0f); }
 inline vec4 texture(const Sampler& s, const vec3& uvw) { return s.sample(uvw.x, uvw.y, uvw.z, 0.0f); }
 inline vec4 textureLod(const Sampler& s, const vec2& uv, float lod) { return s.sample(uv.x, uv.y, 0.0f, lod); }
 inline vec4 textureLod(const Sampler& s, const vec3& uvw, float lod) { return s.sample(uvw.x, uvw.y, uvw.z, lod); }

@@ -1,0 +1,129 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  K3 / K4 / K5: the reference's sky-view, aerial-perspective and environment-cube
+// programs (AtmosphereRenderer.glsl, composed by AtmosphereRenderer.cpp:91-148; dispatched by :219-239).  The header
+// the host prepends is reproduced as #defines; the two sizes it bakes in as text become run-time variables.
+#define REF_MATH_DET
+#include "ref_common.h"
+
+namespace ref { int g_sky_w = 128, g_sky_h = 128, g_ap_depth = 32; }
+#define SKY_VIEW_LUT_SIZE ivec2(ref::g_sky_w, ref::g_sky_h)
+#define AERIAL_PERSPECTIVE_LUT_SIZE ivec3(32, 32, ref::g_ap_depth)
+#define PCSS_ENABLE 0
+#define VOLUMETRIC_LIGHT_ENABLE 0
+#define MOON_SHADOW_ENABLE 0
+#define USE_SKY_VIEW_LUT 1
+#define USE_AERIAL_PERSPECTIVE_LUT 1
+#define ROUGHNESS_COUNT 5
+#define LOCAL_SIZE_X 8
+#define LOCAL_SIZE_Y 4
+#define LOCAL_SIZE_Z 1
+
+#define REF_LOAD_RENDER(r)                                                                                   \
+    do {                                                                                                     \
+        sun_direction = REF_V3((r)->sun_direction); star_luminance_scale = (r)->star_luminance_scale;         \
+        earth_center = REF_V3((r)->earth_center); camera_earth_center_distance = (r)->camera_earth_center_distance; \
+        camera_position = REF_V3((r)->camera_position); raymarching_steps = (r)->raymarching_steps;           \
+        up_direction = REF_V3((r)->up_direction); sky_view_lut_steps = (r)->sky_view_lut_steps;               \
+        right_direction = REF_V3((r)->right_direction); aerial_perspective_lut_steps = (r)->aerial_perspective_lut_steps; \
+        front_direction = REF_V3((r)->front_direction);                                                       \
+        aerial_perspective_lut_max_distance = (r)->aerial_perspective_lut_max_distance;                       \
+        moon_position = REF_V3((r)->moon_position); moon_radius = (r)->moon_radius;                           \
+        inv_view_projection = ref::mat4((r)->inv_view_projection);                                            \
+        light_view_projection = ref::mat4((r)->light_view_projection);                                        \
+        uInvShadowFroxelMaxDistance = (r)->uInvShadowFroxelMaxDistance;                                       \
+        blocker_kernel_size_k = (r)->blocker_kernel_size_k; pcss_size_k = (r)->pcss_size_k;                   \
+        uCloudShadowMapMat = ref::mat4((r)->uCloudShadowMapMat);                                              \
+    } while (0)
+
+#define REF_PROGRAM(NS, PROGRAM, DITHER)                    \
+    namespace ref { namespace NS {                          \
+    _Pragma("push_macro(\"DITHER_SAMPLE_POINT_ENABLE\")")   \
+    } }
+// (the shader text is included once per (program, dither) pair; include guards are reset in between)
+#define REF_RESET_GUARDS
+
+namespace ref { namespace k3d0 {
+#define SKY_VIEW_COMPUTE_PROGRAM
+#define DITHER_SAMPLE_POINT_ENABLE 0
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#undef DITHER_SAMPLE_POINT_ENABLE
+#include "ref_undef_guards.h"
+} namespace k3d1 {
+#define DITHER_SAMPLE_POINT_ENABLE 1
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#undef DITHER_SAMPLE_POINT_ENABLE
+#undef SKY_VIEW_COMPUTE_PROGRAM
+#include "ref_undef_guards.h"
+} namespace k4d0 {
+#define AERIAL_PERSPECTIVE_COMPUTE_PROGRAM
+#define DITHER_SAMPLE_POINT_ENABLE 0
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#undef DITHER_SAMPLE_POINT_ENABLE
+#include "ref_undef_guards.h"
+} namespace k4d1 {
+#define DITHER_SAMPLE_POINT_ENABLE 1
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#undef DITHER_SAMPLE_POINT_ENABLE
+#undef AERIAL_PERSPECTIVE_COMPUTE_PROGRAM
+#include "ref_undef_guards.h"
+} namespace k5 {
+#define ENVIRONMENT_LUMINANCE_COMPUTE_PROGRAM
+#define DITHER_SAMPLE_POINT_ENABLE 1
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#undef DITHER_SAMPLE_POINT_ENABLE
+#undef ENVIRONMENT_LUMINANCE_COMPUTE_PROGRAM
+} }
+
+struct RefLutIO {
+    const float* transmittance;      // [64][256][4]
+    const float* multiscattering;    // [32][32][4]
+    const float* blue_noise;         // [64][64][4] (R16 texels as floats in .x), may be null when no dither flag is set
+    float* sky_luminance;            // [sky_h][sky_w][4]
+    float* sky_transmittance;
+    float* ap_luminance;             // [depth][32][32][4]
+    float* ap_transmittance;
+    float* environment;              // [6][size][size][4] (values rounded to fp16)
+};
+
+template <class F>
+static void with_common_bindings(const SkyAtmosphereBufferData* a, const SkyAtmosphereRenderBufferData* r, const RefLutIO* io, F&& f) { f(); }
+
+#define REF_BIND_COMMON()                                                                                                  \
+    REF_LOAD_ATMOSPHERE(a);                                                                                                \
+    REF_LOAD_RENDER(r);                                                                                                    \
+    ref_bind_texture(transmittance_texture, io->transmittance, 256, 64, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);               \
+    ref_bind_texture(multiscattering_texture, io->multiscattering, 32, 32, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);            \
+    if (io->blue_noise) ref_bind_texture(blue_noise, io->blue_noise, 64, 64, 1, ref::REPEAT, ref::NEAREST)
+
+extern "C" int ref_atmosphere_luts(const SkyAtmosphereBufferData* a, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg,
+                                   const RefLutIO* io) {
+    ref::g_sky_w = cfg->sky_view_width; ref::g_sky_h = cfg->sky_view_height; ref::g_ap_depth = cfg->aerial_perspective_depth;
+    const int sw = cfg->sky_view_width, sh = cfg->sky_view_height, D = cfg->aerial_perspective_depth, E = cfg->environment_size;
+    if ((cfg->sky_view_dither || cfg->aerial_perspective_dither) && !io->blue_noise) return 1;
+#define RUN_K3(NS)                                                                                               \
+    {                                                                                                            \
+        using namespace ref::NS;                                                                                 \
+        REF_BIND_COMMON();                                                                                       \
+        ref_bind_image(luminance_image, io->sky_luminance, sw, sh, 1, ref::FMT_RGBA32F);                         \
+        ref_bind_image(transmittance_image, io->sky_transmittance, sw, sh, 1, ref::FMT_RGBA32F);                 \
+        ref::dispatch(main, ref_ceil_div(sw, LOCAL_SIZE_X), ref_ceil_div(sh, LOCAL_SIZE_Y), 1, LOCAL_SIZE_X, LOCAL_SIZE_Y, 1, false); \
+    }
+    if (cfg->sky_view_dither) RUN_K3(k3d1) else RUN_K3(k3d0)
+#define RUN_K4(NS)                                                                                               \
+    {                                                                                                            \
+        using namespace ref::NS;                                                                                 \
+        REF_BIND_COMMON();                                                                                       \
+        ref_bind_image(luminance_image, io->ap_luminance, 32, 32, D, ref::FMT_RGBA32F);                          \
+        ref_bind_image(transmittance_image, io->ap_transmittance, 32, 32, D, ref::FMT_RGBA32F);                  \
+        ref::dispatch(main, ref_ceil_div(32, LOCAL_SIZE_X), ref_ceil_div(32, LOCAL_SIZE_Y), D, LOCAL_SIZE_X, LOCAL_SIZE_Y, 1, false); \
+    }
+    if (cfg->aerial_perspective_dither) RUN_K4(k4d1) else RUN_K4(k4d0)
+    {
+        using namespace ref::k5;
+        REF_BIND_COMMON();
+        ref_bind_texture(sky_view_luminance_texture, io->sky_luminance, sw, sh, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);
+        ref_bind_texture(sky_view_transmittance_texture, io->sky_transmittance, sw, sh, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);
+        ref_bind_image(env_luminance_image, io->environment, E, E, 6, ref::FMT_RGBA16F);
+        ref::dispatch(main, ref_ceil_div(E, LOCAL_SIZE_X), ref_ceil_div(E, LOCAL_SIZE_Y), 6, LOCAL_SIZE_X, LOCAL_SIZE_Y, 1, false);
+    }
+    return 0;
+}

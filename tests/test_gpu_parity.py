@@ -57,6 +57,27 @@ def test_lut_bake_parity(libs, scene):
     assert rg.ctx.read(abi.RES_AERIAL_LUMINANCE).shape == (depth, 32, 32, 4)
 
 
+@pytest.mark.parametrize("scene", ["c1", "c2", "c3", "c5"])
+def test_cuda_matches_reference_shader_digests(libs, scene):
+    """The CUDA LUTs and noise volumes against what the reference's OWN GLSL computes (tests/refpin.py: the shader text
+    compiled as C++ in the build container, shipped as SHA-256 digests): bit for bit, no oracle in between."""
+    from tests import refpin
+    gold = refpin.load_golden()
+    cuda, _ = libs
+    r = Renderer(scene, 192, 108, library=cuda)
+    r.prime()
+    r.ctx.sync()
+    for name, res in refpin.LUTS:
+        g = gold["luts"][scene][name]
+        arr = refpin.canonical_rgb(r.ctx.read(res))
+        assert refpin.digest(arr, g["undefined_texels"]) == g["sha256"], (scene, name)
+    if scene in gold["noise"]:
+        for name, kind, res, shape in refpin.NOISES:
+            if name in gold["noise"][scene]:
+                r.ctx.noise_generate(kind, r.scene.noise_info(kind))
+                assert refpin.digest(r.ctx.read(res)) == gold["noise"][scene][name]["sha256"], (scene, name)
+
+
 def test_sky_view_192x108_variant(libs):
     """BASELINE names a 192x108 sky-view LUT; the reference hard-codes 128x128.  The size is a parameter."""
     cuda, orc = libs
