@@ -15,6 +15,8 @@ are purely syntactic -- no arithmetic is added, removed or reordered:
      variables of a fragment shader become plain variables.
   5. GLSL array constructors `T[](...)` / `T[n](...)` -> `{...}`; `discard` -> `return`.
   6. `imageSize(x)` / `textureSize(x, l)` keep their names (the shim overloads them on the image / sampler type).
+  7. file-scope scalar / vector variables with an initialiser become macros (GLSL initialises them per invocation,
+     after the uniforms are bound; a C++ global would be initialised once, at load time).
 
 usage: glsl2cpp.py <shader path> <output path> [search dir ...]
 """
@@ -80,7 +82,33 @@ def rewrite(text):
     text = re.sub(r"=\s*\w+\s*\[\s*\w*\s*\]\s*\(", "= REF_ARRAY_BEGIN(", text)
     text = convert_array_ctors(text)
     text = re.sub(r"\bdiscard\s*;", "return;", text)
+    # 7. file-scope scalars / vectors with initialisers (`const vec3 kCloudAABBMin = vec3(..., uBottomAltitude);`): GLSL
+    #    evaluates them per invocation, after the uniforms are set -- C++ would at load time.  They become macros.
+    text = globals_to_macros(text)
     return text
+
+
+GLOBAL_INIT = re.compile(r"(?:const\s+)?\b(float|int|uint|bool|vec[234]|ivec[234]|uvec[234])\s+(\w+)\s*=\s*([^;{}]+);")
+
+
+def globals_to_macros(text):
+    out, depth, i = [], 0, 0
+    while i < len(text):
+        c = text[i]
+        if c == "{":
+            depth += 1
+        elif c == "}":
+            depth -= 1
+        if depth == 0 and (i == 0 or text[i - 1] in "\n;}"):
+            m = GLOBAL_INIT.match(text, i + (1 if c in " \t" else 0)) if c in " \tcfiubv" else None
+            if m and text[i:m.start()].strip() == "":
+                rhs = " ".join(m.group(3).split())
+                out.append(f"\n#define {m.group(2)} ({m.group(1)}({rhs}))\n")
+                i = m.end()
+                continue
+        out.append(c)
+        i += 1
+    return "".join(out)
 
 
 def convert_array_ctors(text):

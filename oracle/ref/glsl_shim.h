@@ -106,6 +106,7 @@ struct vec2; struct vec3; struct vec4; struct ivec2; struct ivec3; struct ivec4;
         template <class T, class U, class = std::enable_if_t<std::is_arithmetic_v<T> && std::is_arithmetic_v<U>>> \
         NAME(const V2& v, T c_, U d_) : x(v.x), y(v.y), z(S(c_)), w(S(d_)) {}                          \
         NAME(const V2& p, const V2& q) : x(p.x), y(p.y), z(q.x), w(q.y) {}                             \
+        NAME(const V3& p, const V3& q) : x(p.x), y(p.y), z(p.z), w(q.x) {} /* GLSL drops the unused tail of the last argument */ \
         S& operator[](int i) { return d[i]; }                                                          \
         S operator[](int i) const { return d[i]; }                                                     \
     };
@@ -192,6 +193,8 @@ inline float smoothstep(float e0, float e1, float x) {
     float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
     return t * t * (3.0f - 2.0f * t);
 }
+inline bool all(bool b) { return b; }
+inline bool any(bool b) { return b; }
 inline float mod(float x, float y) { return x - y * std::floor(x / y); }
 
 #define REF_MAP1(T, N, name) inline T name(const T& a) { T r; for (int i = 0; i < N; ++i) r.d[i] = name(a.d[i]); return r; }
@@ -278,13 +281,17 @@ struct Image {
 struct image2D : Image {};
 struct image3D : Image {};
 struct imageCube : Image {};  // d = 6 faces
+struct uimage2D : Image {};   // r8ui: the integer lives in .x
 inline ivec2 imageSize(const image2D& im) { return ivec2(im.w, im.h); }
 inline ivec3 imageSize(const image3D& im) { return ivec3(im.w, im.h, im.d); }
 inline ivec2 imageSize(const imageCube& im) { return ivec2(im.w, im.h); }
+inline ivec2 imageSize(const uimage2D& im) { return ivec2(im.w, im.h); }
 inline void imageStore(Image& im, const ivec2& p, const vec4& v) { im.store(p.x, p.y, 0, v); }
 inline void imageStore(Image& im, const ivec3& p, const vec4& v) { im.store(p.x, p.y, p.z, v); }
-inline vec4 imageLoad(const Image& im, const ivec2& p) { return im.load(p.x, p.y, 0); }
-inline vec4 imageLoad(const Image& im, const ivec3& p) { return im.load(p.x, p.y, p.z); }
+inline vec4 imageLoad(const image2D& im, const ivec2& p) { return im.load(p.x, p.y, 0); }
+inline uvec4 imageLoad(const uimage2D& im, const ivec2& p) { vec4 v = im.load(p.x, p.y, 0); return uvec4(uint(v.x), uint(v.y), uint(v.z), uint(v.w)); }
+inline void imageStore(uimage2D& im, const ivec2& p, const uvec4& v) { im.store(p.x, p.y, 0, vec4(float(v.x), float(v.y), float(v.z), float(v.w))); }
+inline vec4 imageLoad(const image3D& im, const ivec3& p) { return im.load(p.x, p.y, p.z); }
 
 enum Wrap { CLAMP_TO_EDGE, REPEAT, CLAMP_TO_BORDER };
 enum Filter { NEAREST, LINEAR };
@@ -346,6 +353,25 @@ inline vec4 textureLod(const Sampler& s, const vec2& uv, float lod) { return s.s
 inline vec4 textureLod(const Sampler& s, const vec3& uvw, float lod) { return s.sample(uvw.x, uvw.y, uvw.z, lod); }
 inline vec4 texelFetch(const Sampler& s, const ivec2& p, int lod) { return s.levels[lod].load(p.x, p.y, 0); }
 inline vec4 texelFetch(const Sampler& s, const ivec3& p, int lod) { return s.levels[lod].load(p.x, p.y, p.z); }
+// samplerCube inside a compute shader: implicit derivatives are undefined, so the LOD is the driver's choice.  Convention
+// (same as the oracle and the kernels): level 0, bilinear inside the face the GL cube-map table
+// (spec 8.13) selects, clamped at the face edge.
+inline vec4 texture(const samplerCube& s, const vec3& dir) {
+    float ax = std::fabs(dir.x), ay = std::fabs(dir.y), az = std::fabs(dir.z);
+    int face; float sc, tc, ma;
+    if (ax >= ay && ax >= az) { ma = ax; if (dir.x >= 0) { face = 0; sc = -dir.z; tc = -dir.y; } else { face = 1; sc = dir.z; tc = -dir.y; } }
+    else if (ay >= az)        { ma = ay; if (dir.y >= 0) { face = 2; sc = dir.x; tc = dir.z; } else { face = 3; sc = dir.x; tc = -dir.z; } }
+    else                      { ma = az; if (dir.z >= 0) { face = 4; sc = dir.x; tc = -dir.y; } else { face = 5; sc = -dir.x; tc = -dir.y; } }
+    float ss = 0.5f * (sc / ma + 1.0f), tt = 0.5f * (tc / ma + 1.0f);
+    const Image& env = s.levels[0];
+    int n = env.w;
+    float u = ss * float(n) - 0.5f, v = tt * float(n) - 0.5f;
+    float fu = std::floor(u), fv = std::floor(v);
+    int i0 = int(fu), j0 = int(fv);
+    float a = u - fu, b = v - fv;
+    auto L = [&](int i, int j) { return env.load(clamp(i, 0, n - 1), clamp(j, 0, n - 1), face); };
+    return (1.0f - a) * (1.0f - b) * L(i0, j0) + a * (1.0f - b) * L(i0 + 1, j0) + (1.0f - a) * b * L(i0, j0 + 1) + a * b * L(i0 + 1, j0 + 1);
+}
 inline ivec2 textureSize(const sampler2D& s, int lod) { return ivec2(s.levels[lod].w, s.levels[lod].h); }
 inline ivec3 textureSize(const sampler3D& s, int lod) { return ivec3(s.levels[lod].w, s.levels[lod].h, s.levels[lod].d); }
 

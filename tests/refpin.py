@@ -98,3 +98,69 @@ def sample(array, stride=997):
 def load_golden():
     with open(GOLDEN) as f:
         return json.load(f)
+
+
+# ---- path tracer (K19) ---------------------------------------------------------------------------------------------
+class RefVoxelLevel(C.Structure):
+    _fields_ = [("rgba", C.c_void_p), ("w", C.c_int), ("h", C.c_int), ("d", C.c_int)]
+
+
+class RefPtIO(C.Structure):
+    _fields_ = [("transmittance", C.c_void_p), ("ap_luminance", C.c_void_p), ("ap_transmittance", C.c_void_p), ("ap_depth", C.c_int),
+                ("froxel", C.c_void_p), ("fw", C.c_int), ("fh", C.c_int), ("fd", C.c_int), ("environment", C.c_void_p), ("env_size", C.c_int),
+                ("voxel_levels", C.c_void_p), ("voxel_level_count", C.c_int), ("accum", C.c_void_p), ("mask", C.c_void_p), ("display", C.c_void_p),
+                ("width", C.c_int), ("height", C.c_int)]
+
+
+def as_rgba(array, channels_last=True):
+    """float32 [...][4] copy of a resource (the shim's texel storage); scalar resources land in .x."""
+    a = np.asarray(array).astype(np.float32)
+    if not channels_last:
+        a = a[..., None]
+    out = np.zeros(a.shape[:-1] + (4,), np.float32)
+    out[..., :a.shape[-1]] = a
+    if a.shape[-1] < 4:
+        out[..., 3] = 1.0
+    return np.ascontiguousarray(out)
+
+
+def voxel_mip_chain(grid, mips_bytes):
+    """[level arrays [d][h][w] uint8] from the level-0 grid and the packed levels 1.. of RES_VOXEL_MIPS (floor convention)."""
+    levels, off = [np.asarray(grid)], 0
+    d, h, w = grid.shape
+    flat = np.asarray(mips_bytes).reshape(-1)
+    while (w, h, d) != (1, 1, 1):
+        w, h, d = max(w // 2, 1), max(h // 2, 1), max(d // 2, 1)
+        n = w * h * d
+        levels.append(flat[off:off + n].reshape(d, h, w))
+        off += n
+    assert off == flat.size
+    return levels
+
+
+def ref_path_trace(ref, renderer, common, grid, width, height, frame_begin, count, region=None):
+    """`count` kFrameIds of the reference's path-tracing program on the state of `renderer` (an oracle-backed Renderer after
+    cloud_shadow / atmosphere_render_luts / path_trace_begin); returns the RGBA32F accumulation image."""
+    ctx = renderer.ctx
+    keep = []
+    def rgba(res, scale=1.0, channels_last=True):
+        a = as_rgba(np.asarray(ctx.read(res)).astype(np.float32) * scale, channels_last)
+        keep.append(a)
+        return a
+    T = rgba(abi.RES_TRANSMITTANCE); al = rgba(abi.RES_AERIAL_LUMINANCE); at = rgba(abi.RES_AERIAL_TRANSMITTANCE)
+    fr = rgba(abi.RES_SHADOW_FROXEL, 1.0 / 65535.0, channels_last=False)
+    env = rgba(abi.RES_ENVIRONMENT)
+    levels = voxel_mip_chain(np.asarray(grid), ctx.read(abi.RES_VOXEL_MIPS))
+    lv = (RefVoxelLevel * len(levels))()
+    for i, l in enumerate(levels):
+        a = as_rgba(l.astype(np.float32) / np.float32(255.0), channels_last=False); keep.append(a)
+        lv[i] = RefVoxelLevel(a.ctypes.data, l.shape[2], l.shape[1], l.shape[0])
+    accum = np.zeros((height, width, 4), np.float32); mask = np.zeros_like(accum); display = np.zeros_like(accum)
+    io = RefPtIO(T.ctypes.data, al.ctypes.data, at.ctypes.data, al.shape[0], fr.ctypes.data, fr.shape[2], fr.shape[1], fr.shape[0],
+                 env.ctypes.data, env.shape[1], C.cast(lv, C.c_void_p), len(levels), accum.ctypes.data, mask.ctypes.data, display.ctypes.data, width, height)
+    region = (C.c_int32 * 4)(*(region or [0, 0, width, height]))
+    mat = renderer.last_uniforms[2].u.voxel
+    rc = ref.ref_pt_samples(C.byref(renderer.atmosphere), C.byref(common), C.byref(mat), C.byref(renderer.pt_init), C.byref(io),
+                            C.c_uint32(frame_begin), C.c_uint32(count), region)
+    assert rc == 0, rc
+    return accum

@@ -58,3 +58,26 @@ def test_fixture_is_what_the_reference_shaders_compute_now(gold):
     info = r.scene.noise_info(abi.NOISE_DISPLACEMENT)
     out = refpin.ref_noise(ref, abi.NOISE_DISPLACEMENT, info, (128, 128, 4))
     assert refpin.digest(out) == gold["noise"]["c3"]["displacement"]["sha256"]
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("kw", [
+    dict(max_bounces=8, region_box_half_width=8.0),
+    dict(max_bounces=8, region_box_half_width=8.0, prng=abi.PRNG_WANG, environment_lighting=abi.ENV_GROUND_SINGLE_BOUNCE),
+    dict(max_bounces=8, region_box_half_width=8.0, environment_lighting=abi.ENV_CONST_ENVIRONMENT_MAP),
+    dict(max_bounces=8, region_box_half_width=8.0, environment_lighting=abi.ENV_OFF, importance_sampling=False),
+    dict(),  # reference defaults: 128 bounces, +-100 km box, PCG, ground multi-bounce
+])
+def test_oracle_path_tracer_is_the_reference_shader(kw):
+    """K19: VolumetricCloudPathTracing.comp + the voxel material, compiled from the reference's text, against the
+    oracle's restatement on the same state, kFrameIds and random streams: the RGBA32F accumulation is bit-identical."""
+    from skyrendering_b200.renderer import synthetic_voxel_grid
+    from tests.parity import run_path_trace
+    ref = refpin.ref_library()
+    grid = synthetic_voxel_grid(63, 77, 43)
+    w, h, spp = (96, 54, 4) if kw else (48, 27, 2)
+    r, common, oracle_accum = run_path_trace("c5", w, h, oracle_library(), spp, grid=grid, **kw)
+    ref_accum = refpin.ref_path_trace(ref, r, common, grid, w, h, 1, spp)
+    assert oracle_accum.shape == ref_accum.shape
+    assert np.array_equal(oracle_accum, ref_accum, equal_nan=True)
+    assert float(oracle_accum[..., :3].sum()) > 0.0
