@@ -15,6 +15,7 @@ are purely syntactic -- no arithmetic is added, removed or reordered:
      variables of a fragment shader become plain variables.
   5. GLSL array constructors `T[](...)` / `T[n](...)` -> `{...}`; `discard` -> `return`.
   6. `imageSize(x)` / `textureSize(x, l)` keep their names (the shim overloads them on the image / sampler type).
+  8. GLSL-style array types `T[N] name` (function return types, locals) become std::array<T, N>.
   7. file-scope scalar / vector variables with an initialiser become macros (GLSL initialises them per invocation,
      after the uniforms are bound; a C++ global would be initialised once, at load time).
 
@@ -82,6 +83,8 @@ def rewrite(text):
     text = re.sub(r"=\s*\w+\s*\[\s*\w*\s*\]\s*\(", "= REF_ARRAY_BEGIN(", text)
     text = convert_array_ctors(text)
     text = re.sub(r"\bdiscard\s*;", "return;", text)
+    # 8. array types written GLSL-style: `T[N] name` (return types, locals) -> std::array<T, N> name
+    text = re.sub(r"\b([A-Za-z_]\w*)\s*\[\s*(\d+)\s*\]\s+([A-Za-z_]\w*)", r"std::array<\1, \2> \3", text)
     # 7. file-scope scalars / vectors with initialisers (`const vec3 kCloudAABBMin = vec3(..., uBottomAltitude);`): GLSL
     #    evaluates them per invocation, after the uniforms are set -- C++ would at load time.  They become macros.
     text = globals_to_macros(text)

@@ -11,6 +11,7 @@
 // -- when REF_MATH_DET is defined, as for the LUT programs -- exp / sin / cos / acos / x^1.5 from include/sky_detmath.h.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -62,7 +63,7 @@ struct vec2; struct vec3; struct vec4; struct ivec2; struct ivec3; struct ivec4;
         S& operator[](int i) { return d[i]; }                                                          \
         S operator[](int i) const { return d[i]; }                                                     \
     };
-#define REF_VEC3(NAME, V2, S, O1, O2)                                                                          \
+#define REF_VEC3(NAME, V2, S, O1, O2, A2, B2)                                                                          \
     struct NAME {                                                                                      \
         union {                                                                                        \
             struct { S x, y, z; };                                                                     \
@@ -80,6 +81,8 @@ struct vec2; struct vec3; struct vec4; struct ivec2; struct ivec3; struct ivec4;
         template <class T, class U, class W, class = std::enable_if_t<std::is_arithmetic_v<T> && std::is_arithmetic_v<U> && std::is_arithmetic_v<W>>> \
         NAME(T a, U b, W c) : x(S(a)), y(S(b)), z(S(c)) {}                                             \
         template <class T, class = std::enable_if_t<std::is_arithmetic_v<T>>> NAME(const V2& v, T c) : x(v.x), y(v.y), z(S(c)) {} \
+        template <class T, class = std::enable_if_t<std::is_arithmetic_v<T>>> NAME(const A2& v, T c); \
+        template <class T, class = std::enable_if_t<std::is_arithmetic_v<T>>> NAME(const B2& v, T c); \
         template <class T, class = std::enable_if_t<std::is_arithmetic_v<T>>> NAME(T a, const V2& v) : x(S(a)), y(v.x), z(v.y) {} \
         S& operator[](int i) { return d[i]; }                                                          \
         S operator[](int i) const { return d[i]; }                                                     \
@@ -111,10 +114,12 @@ struct vec2; struct vec3; struct vec4; struct ivec2; struct ivec3; struct ivec4;
         S operator[](int i) const { return d[i]; }                                                     \
     };
 
-REF_VEC2(vec2, float, ivec2, uvec2) REF_VEC3(vec3, vec2, float, ivec3, uvec3) REF_VEC4(vec4, vec2, vec3, float, ivec4, uvec4)
-REF_VEC2(ivec2, int, vec2, uvec2) REF_VEC3(ivec3, ivec2, int, vec3, uvec3) REF_VEC4(ivec4, ivec2, ivec3, int, vec4, uvec4)
-REF_VEC2(uvec2, uint, vec2, ivec2) REF_VEC3(uvec3, uvec2, uint, vec3, ivec3) REF_VEC4(uvec4, uvec2, uvec3, uint, vec4, ivec4)
+REF_VEC2(vec2, float, ivec2, uvec2) REF_VEC3(vec3, vec2, float, ivec3, uvec3, ivec2, uvec2) REF_VEC4(vec4, vec2, vec3, float, ivec4, uvec4)
+REF_VEC2(ivec2, int, vec2, uvec2) REF_VEC3(ivec3, ivec2, int, vec3, uvec3, vec2, uvec2) REF_VEC4(ivec4, ivec2, ivec3, int, vec4, uvec4)
+REF_VEC2(uvec2, uint, vec2, ivec2) REF_VEC3(uvec3, uvec2, uint, vec3, ivec3, vec2, ivec2) REF_VEC4(uvec4, uvec2, uvec3, uint, vec4, ivec4)
 // casts between the float / int / uint families (explicit in GLSL as well): component-wise C++ conversions
+#define REF_CONV21(T, A2) template <class U, class> inline T::T(const A2& v, U c) : x(decltype(x)(v.x)), y(decltype(y)(v.y)), z(decltype(z)(c)) {}
+REF_CONV21(vec3, ivec2) REF_CONV21(vec3, uvec2) REF_CONV21(ivec3, vec2) REF_CONV21(ivec3, uvec2) REF_CONV21(uvec3, vec2) REF_CONV21(uvec3, ivec2)
 #define REF_CONV2(T, O) inline T::T(const O& o) : x(decltype(x)(o.x)), y(decltype(y)(o.y)) {}
 #define REF_CONV3(T, O) inline T::T(const O& o) : x(decltype(x)(o.x)), y(decltype(y)(o.y)), z(decltype(z)(o.z)) {}
 #define REF_CONV4(T, O) inline T::T(const O& o) : x(decltype(x)(o.x)), y(decltype(y)(o.y)), z(decltype(z)(o.z)), w(decltype(w)(o.w)) {}
@@ -140,6 +145,13 @@ REF_ARITH(ivec2, int, 2) REF_ARITH(ivec3, int, 3) REF_ARITH(ivec4, int, 4)
 REF_ARITH(uvec2, uint, 2) REF_ARITH(uvec3, uint, 3) REF_ARITH(uvec4, uint, 4)
 REF_INTOPS(ivec2, int, 2) REF_INTOPS(ivec3, int, 3) REF_INTOPS(ivec4, int, 4)
 REF_INTOPS(uvec2, uint, 2) REF_INTOPS(uvec3, uint, 3) REF_INTOPS(uvec4, uint, 4)
+
+// GLSL converts ivec -> vec implicitly in mixed arithmetic (vec2 / ivec2 ...)
+#define REF_MIXED(V, I, N, op) \
+    inline V operator op(const V& a, const I& b) { V r; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] op float(b.d[i]); return r; } \
+    inline V operator op(const I& a, const V& b) { V r; for (int i = 0; i < N; ++i) r.d[i] = float(a.d[i]) op b.d[i]; return r; }
+REF_MIXED(vec2, ivec2, 2, +) REF_MIXED(vec2, ivec2, 2, -) REF_MIXED(vec2, ivec2, 2, *) REF_MIXED(vec2, ivec2, 2, /)
+REF_MIXED(vec3, ivec3, 3, +) REF_MIXED(vec3, ivec3, 3, -) REF_MIXED(vec3, ivec3, 3, *) REF_MIXED(vec3, ivec3, 3, /)
 
 // ---- elementary functions -----------------------------------------------------------------------------------
 #ifdef REF_MATH_DET
@@ -251,8 +263,10 @@ inline vec3 operator*(const mat3& m, const vec3& v) {
 
 // ---- images and samplers ------------------------------------------------------------------------------------
 enum ImageFormat { FMT_RGBA32F, FMT_RG32F, FMT_R32F, FMT_RGBA16F, FMT_RGBA8, FMT_RG8, FMT_R8, FMT_R16 };
+inline float unorm16_round(float x);
 inline float half_round(float x) { return (float)(_Float16)x; }
 inline float unorm8_round(float x) { return std::nearbyint(clamp(x, 0.0f, 1.0f) * 255.0f) / 255.0f; }
+inline float unorm16_round(float x) { return std::nearbyint(clamp(x, 0.0f, 1.0f) * 65535.0f) / 65535.0f; }
 
 // One level of texel storage, always 4 floats per texel in memory (the format decides the rounding of a store).
 struct Image {
@@ -270,6 +284,7 @@ struct Image {
             case FMT_RGBA8: for (int i = 0; i < 4; ++i) v.d[i] = unorm8_round(v.d[i]); break;
             case FMT_RG8: v = vec4(unorm8_round(v.x), unorm8_round(v.y), 0.0f, 1.0f); break;
             case FMT_R8: v = vec4(unorm8_round(v.x), 0.0f, 0.0f, 1.0f); break;
+            case FMT_R16: v = vec4(unorm16_round(v.x), 0.0f, 0.0f, 1.0f); break;
             case FMT_RG32F: v = vec4(v.x, v.y, 0.0f, 1.0f); break;
             case FMT_R32F: v = vec4(v.x, 0.0f, 0.0f, 1.0f); break;
             default: break;
@@ -351,8 +366,27 @@ inline vec4 texture2D(const Sampler& s, const vec2& uv) { return s.sample(uv.x, 
 inline vec4 texture(const Sampler& s, const vec3& uvw) { return s.sample(uvw.x, uvw.y, uvw.z, 0.0f); }
 inline vec4 textureLod(const Sampler& s, const vec2& uv, float lod) { return s.sample(uv.x, uv.y, 0.0f, lod); }
 inline vec4 textureLod(const Sampler& s, const vec3& uvw, float lod) { return s.sample(uvw.x, uvw.y, uvw.z, lod); }
-inline vec4 texelFetch(const Sampler& s, const ivec2& p, int lod) { return s.levels[lod].load(p.x, p.y, 0); }
-inline vec4 texelFetch(const Sampler& s, const ivec3& p, int lod) { return s.levels[lod].load(p.x, p.y, p.z); }
+// textureGather (spec 8.14.2 / 8.15): the 2x2 footprint LINEAR filtering would use; (i0,j1) (i1,j1) (i1,j0) (i0,j0).
+// VolumetricCloudReconstruct.comp:38-39 and VolumetricCloudUpscale.comp:17 aim the coordinate EXACTLY at a texel corner
+// ((q +- 0.5) / size), where fp32 rounding of u * size - 0.5 would pick the block at random.  The texture unit works on
+// a fixed-point coordinate with 8 sub-texel bits (round to nearest), which makes the intended block the answer; so does
+// this shim (and the oracle and the kernels, which index that block directly).
+inline vec4 textureGather(const Sampler& s, const vec2& uv, int comp = 0) {
+    const Image& im = s.levels[0];
+    auto base = [](float u, int n) { return int(std::floor(std::nearbyint((u * float(n) - 0.5f) * 256.0f) / 256.0f)); };
+    int i0 = base(uv.x, im.w), j0 = base(uv.y, im.h);
+    return vec4(s.texel(im, i0, j0 + 1, 0).d[comp], s.texel(im, i0 + 1, j0 + 1, 0).d[comp], s.texel(im, i0 + 1, j0, 0).d[comp], s.texel(im, i0, j0, 0).d[comp]);
+}
+// texelFetch outside the image is undefined in GL (zero with robust access); convention here and in the oracle / kernels:
+// the edge texel (only VolumetricCloudIndexGen.comp:31 gets there, for the tiles on the image border)
+inline vec4 texelFetch(const Sampler& s, const ivec2& p, int lod) {
+    const Image& im = s.levels[lod];
+    return im.load(clamp(p.x, 0, im.w - 1), clamp(p.y, 0, im.h - 1), 0);
+}
+inline vec4 texelFetch(const Sampler& s, const ivec3& p, int lod) {
+    const Image& im = s.levels[lod];
+    return im.load(clamp(p.x, 0, im.w - 1), clamp(p.y, 0, im.h - 1), clamp(p.z, 0, im.d - 1));
+}
 // samplerCube inside a compute shader: implicit derivatives are undefined, so the LOD is the driver's choice.  Convention
 // (same as the oracle and the kernels): level 0, bilinear inside the face the GL cube-map table
 // (spec 8.13) selects, clamped at the face edge.

@@ -164,3 +164,83 @@ def ref_path_trace(ref, renderer, common, grid, width, height, frame_begin, coun
                             C.c_uint32(frame_begin), C.c_uint32(count), region)
     assert rc == 0, rc
     return accum
+
+
+# ---- cloud shadow chain + real-time cloud chain (K11-K18), pass by pass -------------------------------------------------
+class RefTex(C.Structure):
+    _fields_ = [("rgba", C.c_void_p), ("w", C.c_int), ("h", C.c_int), ("d", C.c_int)]
+
+
+class RefCloudIO(C.Structure):
+    _fields_ = [("atm", C.c_void_p), ("common", C.c_void_p), ("cloud", C.c_void_p), ("material", C.c_void_p),
+                ("cloud_map", C.c_void_p), ("cloud_map_levels", C.c_int), ("detail", C.c_void_p), ("detail_levels", C.c_int),
+                ("displacement", C.c_void_p), ("displacement_levels", C.c_int), ("voxel", C.c_void_p), ("voxel_levels", C.c_int),
+                ("blue_noise", C.c_void_p),
+                ("shadow_prev", C.c_void_p), ("shadow_raw", C.c_void_p), ("shadow_tmp", C.c_void_p), ("shadow_blurred", C.c_void_p), ("shadow_size", C.c_int),
+                ("froxel", C.c_void_p), ("fw", C.c_int), ("fh", C.c_int), ("fd", C.c_int),
+                ("depth", C.c_void_p), ("width", C.c_int), ("height", C.c_int),
+                ("checkerboard", C.c_void_p), ("index_linear", C.c_void_p), ("render", C.c_void_p), ("cloud_distance", C.c_void_p),
+                ("reconstruct_prev", C.c_void_p), ("reconstruct_out", C.c_void_p), ("hdr", C.c_void_p),
+                ("transmittance", C.c_void_p), ("ap_luminance", C.c_void_p), ("ap_transmittance", C.c_void_p), ("ap_depth", C.c_int)]
+
+
+def mip_chain(level0, mips_bytes, channels):
+    """[level arrays [d][h][w][c] uint8] from level 0 and the packed levels 1.. (RES_*_MIPS)."""
+    l0 = np.asarray(level0)
+    if l0.ndim == 2 + (channels > 1):
+        l0 = l0[None]                      # 2-D texture: depth 1
+    if channels == 1 and l0.ndim == 3:
+        l0 = l0[..., None]
+    levels, off = [l0], 0
+    d, h, w = l0.shape[:3]
+    flat = np.asarray(mips_bytes).reshape(-1)
+    while (w, h, d) != (1, 1, 1):
+        w, h, d = max(w // 2, 1), max(h // 2, 1), max(d // 2, 1)
+        n = w * h * d * channels
+        levels.append(flat[off:off + n].reshape(d, h, w, channels))
+        off += n
+    assert off == flat.size, (off, flat.size)
+    return levels
+
+
+class CloudPassHarness:
+    """Holds float-RGBA copies of every buffer of a frame and runs single passes of the reference's programs on them."""
+
+    def __init__(self, ref, renderer, width, height, grid=None):
+        self.ref, self.r, self.w, self.h = ref, renderer, width, height
+        self.keep = []
+        ctx = renderer.ctx
+        self.io = RefCloudIO()
+        self.io.width, self.io.height, self.io.shadow_size = width, height, 512
+        mtype = renderer.last_uniforms[2].type
+        if mtype in (abi.MATERIAL_DEFAULT0, abi.MATERIAL_DEFAULT1):
+            for name, res, mips, ch in (("cloud_map", abi.RES_CLOUD_MAP, abi.RES_CLOUD_MAP_MIPS, 2), ("detail", abi.RES_DETAIL, abi.RES_DETAIL_MIPS, 1),
+                                        ("displacement", abi.RES_DISPLACEMENT, abi.RES_DISPLACEMENT_MIPS, 4)):
+                self._bind_levels(name, mip_chain(ctx.read(res), ctx.read(mips), ch))
+        elif mtype == abi.MATERIAL_VOXEL:
+            self._bind_levels("voxel", mip_chain(np.asarray(grid), ctx.read(abi.RES_VOXEL_MIPS), 1))
+        self.buf = {}
+
+    def _bind_levels(self, name, levels):
+        arr = (RefTex * len(levels))()
+        for i, l in enumerate(levels):
+            a = as_rgba(l.astype(np.float32) / np.float32(255.0)); self.keep.append(a)
+            arr[i] = RefTex(a.ctypes.data, l.shape[2], l.shape[1], l.shape[0])
+        self.keep.append(arr)
+        setattr(self.io, name, C.cast(arr, C.c_void_p))
+        setattr(self.io, name + "_levels", len(levels))
+
+    def set(self, name, array, channels_last=True, scale=1.0):
+        a = as_rgba(np.asarray(array).astype(np.float32) * np.float32(scale), channels_last)
+        self.buf[name] = a
+        setattr(self.io, name, a.ctypes.data)
+        return a
+
+    def uniforms(self, common, cloud, material):
+        self.keep += [common, cloud, material, self.r.atmosphere]
+        self.io.atm = C.addressof(self.r.atmosphere); self.io.common = C.addressof(common)
+        self.io.cloud = C.addressof(cloud); self.io.material = C.addressof(material)
+
+    def run(self, pass_id):
+        rc = self.ref.ref_cloud_pass(pass_id, C.byref(self.io))
+        assert rc == 0, (pass_id, rc)

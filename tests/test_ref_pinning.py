@@ -81,3 +81,72 @@ def test_oracle_path_tracer_is_the_reference_shader(kw):
     assert oracle_accum.shape == ref_accum.shape
     assert np.array_equal(oracle_accum, ref_accum, equal_nan=True)
     assert float(oracle_accum[..., :3].sum()) > 0.0
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("scene", ["c3", "c1", "c5"])  # Material0, Material1, voxel material
+def test_oracle_cloud_chain_is_the_reference_shaders_pass_by_pass(scene):
+    """K11-K18: every program of the cloud shadow chain and of the real-time cloud chain, compiled from the reference's
+    text, run on the oracle's own inputs of the third frame of a sequence: each output buffer is bit-identical."""
+    from skyrendering_b200.renderer import load_blue_noise, synthetic_voxel_grid
+    from tests.parity import make_buffers, to_numpy
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 192, 108
+    grid = synthetic_voxel_grid(63, 77, 43) if scene == "c5" else None
+    r = Renderer(scene, w, h, library=orc)
+    if grid is not None:
+        r.upload_voxels(grid)
+    r.prime()
+    depth_np = r.scene.ground_depth(w, h)
+    depth, hdr = make_buffers(w, h, depth_np, "cpu")
+    for _ in range(2):
+        hdr[...] = 0
+        r.frame(depth, hdr, 0.0)
+    prev_raw = r.ctx.read(abi.RES_SHADOW_MAP_RAW).copy()
+    prev_rec = r.ctx.read(abi.RES_RECONSTRUCT).astype(np.float32).copy()
+    hdr[...] = 0
+    r.earth_update()
+    common, cloud, mat = r.cloud_update(0.0)
+    r.ctx.cloud_shadow(common)
+    r.atmosphere_render_luts()
+    r.ctx.composite(depth, hdr, w, h)
+    hdr_before = to_numpy(hdr).astype(np.float32).copy()
+    r.ctx.cloud_frame(common, cloud, depth, hdr)
+    O = {k: r.ctx.read(res).astype(np.float32) for k, res in (
+        ("shadow_raw", abi.RES_SHADOW_MAP_RAW), ("shadow", abi.RES_SHADOW_MAP), ("froxel", abi.RES_SHADOW_FROXEL), ("checker", abi.RES_CHECKERBOARD_DEPTH),
+        ("index", abi.RES_INDEX_LINEAR_DEPTH), ("render", abi.RES_CLOUD_RENDER), ("distance", abi.RES_CLOUD_DISTANCE), ("reconstruct", abi.RES_RECONSTRUCT))}
+    O["hdr"] = to_numpy(hdr).astype(np.float32)
+    fd, fh, fw = O["froxel"].shape[:3]
+    q, hh = (h // 4, w // 4), (h // 2, w // 2)
+
+    H = refpin.CloudPassHarness(ref, r, w, h, grid)
+    H.uniforms(common, cloud, mat)
+    H.set("blue_noise", load_blue_noise().astype(np.float32) / np.float32(65535.0), channels_last=False)
+    H.set("transmittance", r.ctx.read(abi.RES_TRANSMITTANCE))
+    H.set("ap_luminance", r.ctx.read(abi.RES_AERIAL_LUMINANCE))
+    H.set("ap_transmittance", r.ctx.read(abi.RES_AERIAL_TRANSMITTANCE))
+    H.io.ap_depth = r.lut_config.aerial_perspective_depth
+    H.io.fw, H.io.fh, H.io.fd = fw, fh, fd
+    same = lambda a, b: np.array_equal(a, b, equal_nan=True)
+
+    H.set("shadow_prev", prev_raw); out = H.set("shadow_raw", np.zeros((512, 512, 2), np.float32)); H.run(11)
+    assert same(out[..., :2], O["shadow_raw"]), "K11"
+    H.set("shadow_raw", O["shadow_raw"]); H.set("shadow_tmp", np.zeros((512, 512, 2), np.float32))
+    out = H.set("shadow_blurred", np.zeros((512, 512, 2), np.float32)); H.run(12)
+    assert same(out[..., :2], O["shadow"]), "K12"
+    H.set("shadow_blurred", O["shadow"]); out = H.set("froxel", np.zeros((fd, fh, fw), np.float32), channels_last=False); H.run(13)
+    assert same(np.rint(out[..., 0] * 65535.0), O["froxel"].reshape(fd, fh, fw)), "K13"
+    H.set("depth", depth_np, channels_last=False); out = H.set("checkerboard", np.zeros(hh, np.float32), channels_last=False); H.run(14)
+    assert same(out[..., 0], O["checker"].reshape(hh)), "K14"
+    H.set("checkerboard", O["checker"].reshape(hh), channels_last=False); out = H.set("index_linear", np.zeros(q + (2,), np.float32)); H.run(15)
+    assert same(out[..., :2], O["index"].reshape(q + (2,))), "K15"
+    H.set("index_linear", O["index"].reshape(q + (2,)))
+    H.set("froxel", O["froxel"].reshape(fd, fh, fw), channels_last=False, scale=1.0 / 65535.0)
+    out = H.set("render", np.zeros(q + (4,), np.float32)); dist = H.set("cloud_distance", np.zeros(q, np.float32), channels_last=False); H.run(16)
+    assert same(out, O["render"].reshape(q + (4,))) and same(dist[..., 0], O["distance"].reshape(q)), "K16"
+    assert float(O["render"][..., :3].sum()) > 0.0
+    H.set("render", O["render"].reshape(q + (4,))); H.set("cloud_distance", O["distance"].reshape(q), channels_last=False)
+    H.set("reconstruct_prev", prev_rec.reshape(hh + (4,))); out = H.set("reconstruct_out", np.zeros(hh + (4,), np.float32)); H.run(17)
+    assert same(out, O["reconstruct"].reshape(hh + (4,))), "K17"
+    H.set("reconstruct_out", O["reconstruct"].reshape(hh + (4,))); out = H.set("hdr", hdr_before); H.run(18)
+    assert same(out, O["hdr"]), "K18"
