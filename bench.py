@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the SkyRendering hot path on B200 (contract in the task brief).
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's shader text compiled as C++ on the host cores (oracle/_ref)
 
 BASELINE.json's metric has two halves; one JSON line carries both:
   * headline `value`: path-traced samples/s (Gsamples/s) of the voxel-cloud path tracer (scene c5,
@@ -82,42 +82,69 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
+def cpu_path_tracer():
+    """The CPU arm of the path tracer on the bounded sample: returns (step, kind, what).  `step()` runs CPU_PT_SPP kFrameIds of
+    the CPU_PT_W x CPU_PT_H image and returns the seconds spent in the program.  kind "reference": oracle/_ref/libskyref.so, the
+    reference's OWN shader text (VolumetricCloudPathTracing.comp + the voxel material) compiled as C++ in the build container
+    (oracle/Makefile `ref`; the .so travels to the box, /root/reference does not); kind "port": the oracle restatement, used
+    only if that library is absent.  The LUT / shadow-froxel inputs come from the oracle either way (bit-identical to the
+    reference shaders, tests/test_ref_pinning.py)."""
+    from tests import refpin
+    from tests.parity import oracle_library
+    from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
+    cores = os.cpu_count()
+    orc = oracle_library()
+    use_all_host_threads(cores)
+    grid = synthetic_voxel_grid()
+    r = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
+    r.upload_voxels(grid)
+    r.prime()
+    common, _, _ = r.cloud_update(0.0)
+    r.ctx.cloud_shadow(common)
+    r.atmosphere_render_luts()
+    r.path_trace_begin()
+    ref = refpin.ref_library() if (os.path.exists(refpin.REF_LIB) or refpin.reference_present()) else None
+    region = [0, 0, CPU_PT_W, CPU_PT_H]
+
+    def step_ref():
+        timing = {}
+        refpin.ref_path_trace(ref, r, common, grid, CPU_PT_W, CPU_PT_H, 1, CPU_PT_SPP, timing=timing)
+        return timing["seconds"]
+
+    def step_port():
+        r.path_trace_begin()
+        t0 = time.perf_counter()
+        r.ctx.pt_samples(common, 1, CPU_PT_SPP, region)
+        return time.perf_counter() - t0
+
+    if ref is not None:
+        return step_ref, "reference", "the reference's VolumetricCloudPathTracing.comp compiled as C++ (oracle/_ref), OpenMP over work groups"
+    return step_port, "port", "oracle port, OpenMP"
+
+
 def run_reference(args):
-    """The reference's own algorithm on the host cores: the oracle port (the GLSL cannot run here)."""
+    """The reference's own algorithm on the host cores (the GLSL cannot run on a GL driver here): its shader
+    text compiled as C++ (oracle/_ref) when that library was built, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
     os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every core
-    from tests.parity import oracle_library
-    from skyrendering_b200 import abi
-    from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
-    orc = oracle_library()
-    use_all_host_threads(cores)
-    r = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
-    r.upload_voxels(synthetic_voxel_grid())
-    r.prime()
-    common, cloud, _ = r.cloud_update(0.0)
-    r.ctx.cloud_shadow(common)
-    r.atmosphere_render_luts()
-    r.path_trace_begin()
+    step, kind, what = cpu_path_tracer()
     times = []
     for i in range(args.warmup + args.steps):
-        r.path_trace_begin()
-        t0 = time.perf_counter()
-        r.ctx.pt_samples(common, 1, CPU_PT_SPP, [0, 0, CPU_PT_W, CPU_PT_H])
-        dt = time.perf_counter() - t0
+        dt = step()
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = CPU_PT_W * CPU_PT_H * CPU_PT_SPP / (ms * 1e-3) / 1e9
-    sample = f"{CPU_PT_W}x{CPU_PT_H} x {CPU_PT_SPP} spp per step of the same scene/grid/parameters (oracle port, OpenMP)"
+    sample = f"{CPU_PT_W}x{CPU_PT_H} x {CPU_PT_SPP} spp per step of the same scene/grid/parameters ({what})"
     line = {
         "impl": "reference", "metric": "path_traced_gsamples_per_s", "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, reference=True),
-        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -378,19 +405,10 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         from tests.parity import oracle_library
         orc = oracle_library()
-        use_all_host_threads(os.cpu_count())
-        ro = Renderer("c5", CPU_PT_W, CPU_PT_H, library=orc)
-        ro.upload_voxels(synthetic_voxel_grid())
-        ro.prime()
-        c, _, _ = ro.cloud_update(0.0)
-        ro.ctx.cloud_shadow(c)
-        ro.atmosphere_render_luts()
-        ro.path_trace_begin()
-        t0 = time.perf_counter()
-        ro.ctx.pt_samples(c, 1, CPU_PT_SPP, [0, 0, CPU_PT_W, CPU_PT_H])
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": CPU_PT_W * CPU_PT_H * CPU_PT_SPP / dt / 1e9, "unit": "Gsamples/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"{CPU_PT_W}x{CPU_PT_H} x {CPU_PT_SPP} spp of the same scene, grid and parameters ({dt:.1f} s of OpenMP oracle)"}
+        step, kind, what = cpu_path_tracer()
+        dt = step()
+        cpu_baseline = {"value": CPU_PT_W * CPU_PT_H * CPU_PT_SPP / dt / 1e9, "unit": "Gsamples/s", "cores": os.cpu_count(), "kind": kind,
+                        "sample": f"{CPU_PT_W}x{CPU_PT_H} x {CPU_PT_SPP} spp of the same scene, grid and parameters ({dt:.1f} s; {what})"}
         if frame is not None:
             from tests.parity import run_cloud_frames
             t0 = time.perf_counter()

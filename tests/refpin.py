@@ -11,6 +11,7 @@ import hashlib
 import json
 import os
 import subprocess
+import time
 
 import numpy as np
 
@@ -138,9 +139,10 @@ def voxel_mip_chain(grid, mips_bytes):
     return levels
 
 
-def ref_path_trace(ref, renderer, common, grid, width, height, frame_begin, count, region=None):
+def ref_path_trace(ref, renderer, common, grid, width, height, frame_begin, count, region=None, timing=None):
     """`count` kFrameIds of the reference's path-tracing program on the state of `renderer` (an oracle-backed Renderer after
-    cloud_shadow / atmosphere_render_luts / path_trace_begin); returns the RGBA32F accumulation image."""
+    cloud_shadow / atmosphere_render_luts / path_trace_begin); returns the RGBA32F accumulation image.  `timing` (a dict)
+    receives the seconds spent inside the program itself (input conversion excluded) under "seconds"."""
     ctx = renderer.ctx
     keep = []
     def rgba(res, scale=1.0, channels_last=True):
@@ -160,8 +162,11 @@ def ref_path_trace(ref, renderer, common, grid, width, height, frame_begin, coun
                  env.ctypes.data, env.shape[1], C.cast(lv, C.c_void_p), len(levels), accum.ctypes.data, mask.ctypes.data, display.ctypes.data, width, height)
     region = (C.c_int32 * 4)(*(region or [0, 0, width, height]))
     mat = renderer.last_uniforms[2].u.voxel
+    t0 = time.perf_counter()
     rc = ref.ref_pt_samples(C.byref(renderer.atmosphere), C.byref(common), C.byref(mat), C.byref(renderer.pt_init), C.byref(io),
                             C.c_uint32(frame_begin), C.c_uint32(count), region)
+    if timing is not None:
+        timing["seconds"] = time.perf_counter() - t0
     assert rc == 0, rc
     return accum
 
