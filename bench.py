@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--hw-filtering", action="store_true", help="texture-unit filtering (8-bit weights) instead of exact fp32")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-frame", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the single-GPU configurations C1-C3")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -202,7 +203,7 @@ def main():
     import torch.distributed as dist
     from skyrendering_b200 import abi
     from skyrendering_b200.distributed import ShardedCloudFrame, ShardedPathTracer, frame_ranges
-    from skyrendering_b200.renderer import Renderer, synthetic_voxel_grid
+    from skyrendering_b200.renderer import SCENE_FILES, Renderer, synthetic_voxel_grid
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -400,6 +401,61 @@ def main():
             "e2e_h2d_bytes": FRAME_W * FRAME_H * 12, "e2e_d2h_bytes": FRAME_W * FRAME_H * 8,
         }
 
+    # ---- the single-GPU configurations of BASELINE.json (C1-C3): N == 1 only, "replicas only" -------------
+    configs = None
+    if rank == 0 and world == 1 and not args.skip_configs:
+        configs = {}
+        cpu = None
+        if not args.skip_cpu_baseline:
+            from tests.parity import oracle_library
+            cpu = oracle_library()
+            use_all_host_threads(os.cpu_count())
+
+        def cpu_ms(fn):
+            t0 = time.perf_counter(); fn(); return (time.perf_counter() - t0) * 1e3
+
+        # C1: Earth atmosphere LUT bake (bin/config.json): K1 256x64, K2 32x32, K3 128x128, K4 32^3, K5 6x128^2
+        r1 = Renderer("c1", 1920, 1080, library=cuda, device=local_rank)
+        r1.prime()
+        c1 = {"workload": "c1 LUT bake: transmittance 256x64, multiscattering 32x32, sky-view 128x128, aerial perspective 32^3, environment cube",
+              "bake_K1_K2_us": kernel_ms(r1.earth_update) * 1e3, "luts_K3_K5_us": kernel_ms(r1.atmosphere_render_luts) * 1e3,
+              "bound": "latency / launch (5 M march steps, < 2 MB written)", "parity": "bit-exact (tests/test_gpu_parity.py)"}
+        if cpu is not None:
+            o1 = Renderer("c1", 1920, 1080, library=cpu)
+            o1.prime()
+            c1["cpu_baseline"] = {"value": cpu_ms(o1.prime), "unit": "ms", "cores": os.cpu_count(), "kind": "port", "sample": "the whole bake (K1-K5)"}
+        configs["c1_lut_bake"] = c1
+
+        # C2 / C3 at 1920x1080: composite alone (C2) and the whole cloud frame (C3)
+        for key, scene, clouds in (("c2_composite_1080p", "c2", False), ("c3_cloud_frame_1080p", "c3", True)):
+            W, H = 1920, 1080
+            r = Renderer(scene, W, H, library=cuda, device=local_rank)
+            r.prime()
+            dnp = r.scene.ground_depth(W, H)
+            d = torch.from_numpy(dnp).cuda()
+            h = torch.zeros((H, W, 4), dtype=torch.float16, device="cuda")
+            for _ in range(8):   # 8 warm-up frames fill the temporal histories
+                r.frame(d, h, 0.0, clouds=clouds)
+            common, cloud, _ = r.last_uniforms
+            entry = {"workload": f"{scene} (scenes/{SCENE_FILES[scene]}) {W}x{H}, synthetic analytic ground depth",
+                     "frame_ms": kernel_ms(lambda: r.frame(d, h, 0.0, clouds=clouds)),
+                     "composite_K6_us": kernel_ms(lambda: r.ctx.composite(d, h, W, H)) * 1e3}
+            k6_bytes = W * H * (4 + 8)   # depth read + HDR write; the LUTs stay in L1/L2
+            entry["composite_roofline"] = {"bound": "hbm", "achieved": k6_bytes / (entry["composite_K6_us"] * 1e-6) / 1e9, "peak": peaks["hbm_gbs"],
+                                           "unit": "GB/s", "frac": k6_bytes / (entry["composite_K6_us"] * 1e-6) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind}
+            if clouds:
+                entry["parts_us"] = {"shadow_K11_K13": kernel_ms(lambda: r.ctx.cloud_shadow(common)) * 1e3,
+                                     "K14_K16": kernel_ms(lambda: r.ctx.cloud_frame_begin(common, cloud, d)) * 1e3,
+                                     "K17_K18": kernel_ms(lambda: r.ctx.cloud_frame_end(d, h)) * 1e3}
+            if cpu is not None:
+                o = Renderer(scene, W, H, library=cpu)
+                o.prime()
+                hd = np.zeros((H, W, 4), np.float16)
+                o.frame(dnp, hd, 0.0, clouds=clouds)   # first frame generates the noise textures
+                entry["cpu_baseline"] = {"value": cpu_ms(lambda: o.frame(dnp, hd, 0.0, clouds=clouds)), "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                                         "sample": "one whole frame at the same resolution (noise textures already generated)"}
+            configs[key] = entry
+
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample ------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -426,7 +482,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             # per step and rank: K19 (persistent state machine) + K19b (ordered accumulate) per chunk of <= 72 kFrameIds
             "gpu_launches": args.steps * 2 * max(1, -(-my_count // 72)),
-            "roofline": pt_roofline, "cpu_baseline": cpu_baseline, "frame_4k": frame,
+            "roofline": pt_roofline, "cpu_baseline": cpu_baseline, "frame_4k": frame, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

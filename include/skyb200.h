@@ -141,6 +141,13 @@ int SKY_FN(counters_enable)(SkyContext* ctx, int enable);
 /* Which filtering the material textures use: 0 = exact fp32 software filtering on gathered
  * texels (default; matches the oracle), 1 = hardware linear filtering (8-bit weights). */
 int SKY_FN(set_hw_filtering)(SkyContext* ctx, int enable);
+/* Validation mode: 1 routes the frame kernels (K6, K11-K18) and the path tracer (K19/K20) to objects compiled from the
+ * same sources WITHOUT FMA contraction and with IEEE division / square root / elementary functions, i.e. the unfused
+ * fp32 arithmetic the oracle (and a GLSL compiler honouring `precise`) performs, operation by operation.  The default
+ * (0) objects contract FMAs and use the hardware approximations, like a GLSL compiler is free to (frames are compared at
+ * relative RMS 1e-2 because the altitude |p| - R of VolumetricCloudCommon.glsl:36-39 cancels four digits, which makes any
+ * frame sensitive to contraction at the 1e-3 level).  The LUT bake and the noise kernels are always strict. */
+int SKY_FN(set_strict_arithmetic)(SkyContext* ctx, int enable);
 /* Opt-in overlap of the two independent halves of a frame (AppWindow::Render, AppWindow.cpp:148-175) on a second,
  * internal stream: {cloud shadow chain K11-K13, K14-K17} run beside {K3-K5, composite K6}; K18 joins them.  Results are
  * bit-identical.  While enabled, the work of cloud_shadow / cloud_frame_begin is ordered on the caller's stream at

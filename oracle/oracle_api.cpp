@@ -321,6 +321,7 @@ int orc_peer_export(SkyContext* ctx, SkyPeerHandles*) { return fail(ctx, "peer m
 int orc_peer_attach(SkyContext* ctx, int, int, const SkyPeerHandles*) { return fail(ctx, "peer memory is a CUDA feature"); }
 int orc_peer_detach(SkyContext*) { return 0; }
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
+int orc_set_strict_arithmetic(SkyContext*, int) { return 0; }  // the oracle IS the strict arithmetic
 int orc_set_frame_overlap(SkyContext*, int) { return 0; }
 int orc_tex_peak(SkyContext* ctx, int, double*) { return fail(ctx, "tex_peak is a GPU microbenchmark"); }
 

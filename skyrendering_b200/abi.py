@@ -184,6 +184,7 @@ KERNEL_API = {
     "write_resource": ([I, _VOIDP, C.c_uint64], I),
     "counters_enable": ([I], I),
     "set_hw_filtering": ([I], I),
+    "set_strict_arithmetic": ([I], I),
     "set_frame_overlap": ([I], I),
     "tex_peak": ([I, P(C.c_double)], I),
 }
@@ -326,6 +327,7 @@ class Context:
     def pt_resolve(self, frame_count, hdr): self._call("pt_resolve", frame_count, _ptr(hdr))
     def counters_enable(self, on): self._call("counters_enable", int(on))
     def set_hw_filtering(self, on): self._call("set_hw_filtering", int(on))
+    def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))
     def set_frame_overlap(self, on): self._call("set_frame_overlap", int(on))
 
     def tex_peak(self, mode=0):

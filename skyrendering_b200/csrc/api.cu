@@ -291,7 +291,7 @@ int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int
         ctx->pre_composite_recorded = true;
         ctx->pre_composite_depth = depth;
     }
-    return launch_composite(ctx, depth, static_cast<half4*>(hdr), width, height);
+    return (ctx->strict_arithmetic ? launch_composite_strict : launch_composite)(ctx, depth, static_cast<half4*>(hdr), width, height);
 }
 
 int sky_noise_generate(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info) {
@@ -318,14 +318,14 @@ int sky_set_material(SkyContext* ctx, const SkyMaterialBlock* m) {
 
 int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");  // VolumetricCloud.cpp:169-170
-    if (!ctx->overlap) return launch_cloud_shadow(ctx, *common);
+    if (!ctx->overlap) return (ctx->strict_arithmetic ? launch_cloud_shadow_strict : launch_cloud_shadow)(ctx, *common);
     if (int e = lanes_join(ctx)) return e;
     ctx->pre_composite_recorded = false;  // a new frame
     SKY_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     if (int e = lane2_fork(ctx, ctx->ev_fork)) return e;
     {
         LaneScope lane(ctx, ctx->lane2);
-        if (int e = launch_cloud_shadow(ctx, *common)) return e;
+        if (int e = (ctx->strict_arithmetic ? launch_cloud_shadow_strict : launch_cloud_shadow)(ctx, *common)) return e;
     }
     SKY_CUDA(ctx, cudaEventRecord(ctx->ev_shadow, ctx->lane2));
     ctx->shadow_pending = true;
@@ -337,7 +337,7 @@ int sky_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* commo
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (band_count < 1 || band_index < 0 || band_index >= band_count || band_rows < 0) return sky_fail(ctx, "bad band arguments");
     ctx->last_common = *common;  // cloud_frame_end runs K17/K18 with the same uniforms
-    if (!ctx->overlap) return launch_cloud_begin(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
+    if (!ctx->overlap) return (ctx->strict_arithmetic ? launch_cloud_begin_strict : launch_cloud_begin)(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
     // K14-K16 need the depth and the LUTs from the caller's stream -- complete before the composite if there was one --
     // and the froxels, which are on lane2 already
     if (!ctx->pre_composite_recorded || ctx->pre_composite_depth != depth) SKY_CUDA(ctx, cudaEventRecord(ctx->ev_pre_composite, ctx->stream));
@@ -346,7 +346,7 @@ int sky_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* commo
     ctx->shadow_pending = false;  // from here on the caller's stream joins lane2 as a whole
     ctx->lane2_reads_luts = true;
     LaneScope lane(ctx, ctx->lane2);
-    return launch_cloud_begin(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
+    return (ctx->strict_arithmetic ? launch_cloud_begin_strict : launch_cloud_begin)(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
 }
 
 int sky_cloud_frame(SkyContext* ctx, const SkyCloudCommonBufferData* common, const SkyCloudBufferData* cloud,
@@ -359,14 +359,14 @@ int sky_cloud_frame_end(SkyContext* ctx, const float* depth, void* hdr) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (!ctx->overlap || !ctx->lane2_reads_luts) {
         if (int e = lanes_join(ctx)) return e;
-        return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr));
+        return (ctx->strict_arithmetic ? launch_cloud_end_strict : launch_cloud_end)(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 3);
     }
     {
         LaneScope lane(ctx, ctx->lane2);  // K17 follows K16
-        if (int e = launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 1)) return e;
+        if (int e = (ctx->strict_arithmetic ? launch_cloud_end_strict : launch_cloud_end)(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 1)) return e;
     }
     if (int e = lanes_join(ctx)) return e;  // K18 composites over what K6 wrote
-    return launch_cloud_end(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 2);
+    return (ctx->strict_arithmetic ? launch_cloud_end_strict : launch_cloud_end)(ctx, ctx->last_common, depth, static_cast<half4*>(hdr), 2);
 }
 
 int sky_peer_detach(SkyContext* ctx) {
@@ -457,18 +457,18 @@ int sky_pt_begin(SkyContext* ctx, const SkyPathTracingInit* init) {
 int sky_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
                    const int32_t region[4]) {
     if (int e = lanes_join(ctx)) return e;
-    return launch_pt_samples(ctx, *common, frame_begin, count, region);
+    return (ctx->strict_arithmetic ? launch_pt_samples_strict : launch_pt_samples)(ctx, *common, frame_begin, count, region);
 }
 
 int sky_pt_resolve(SkyContext* ctx, uint32_t frame_count, void* hdr) {
     if (int e = lanes_join(ctx)) return e;
-    return launch_pt_resolve(ctx, frame_count, static_cast<half4*>(hdr));
+    return (ctx->strict_arithmetic ? launch_pt_resolve_strict : launch_pt_resolve)(ctx, frame_count, static_cast<half4*>(hdr));
 }
 
 int sky_pt_samples_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
                         const int32_t region[4], float* accum_host) {
     if (int e = lanes_join(ctx)) return e;
-    if (int e = launch_pt_samples(ctx, *common, frame_begin, count, region)) return e;
+    if (int e = (ctx->strict_arithmetic ? launch_pt_samples_strict : launch_pt_samples)(ctx, *common, frame_begin, count, region)) return e;
     SKY_CUDA(ctx, cudaMemcpyAsync(accum_host, ctx->pt_accum.p, ctx->pt_accum.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -518,6 +518,12 @@ int sky_counters_enable(SkyContext* ctx, int enable) {
     if (int e = lanes_join(ctx)) return e;
     ctx->counting = enable != 0;
     SKY_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+int sky_set_strict_arithmetic(SkyContext* ctx, int enable) {
+    if (!ctx) return 1;
+    ctx->strict_arithmetic = enable != 0;
     return 0;
 }
 

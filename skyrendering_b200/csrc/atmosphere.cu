@@ -9,7 +9,7 @@
 
 // The LUT kernels use the deterministic fp32 elementary functions shared with the oracle (bit-for-bit
 // comparable results); the composite translation unit uses the hardware intrinsics.
-#ifdef SKY_COMPOSITE_TU
+#if defined(SKY_COMPOSITE_TU) && !defined(SKY_STRICT_TU)
 #define LUT_EXP(x) __expf(x)
 #define LUT_COS(x) __cosf(x)
 #define LUT_SIN(x) __sinf(x)
@@ -45,6 +45,13 @@ SKY_D float3 GetExtinction(const SkyAtmosphereBufferData& u, float altitude) {
 }
 
 // Atmosphere.glsl:220-295.  MS = MULTISCATTERING_COMPUTE_PROGRAM permutation.
+// K6's per-pixel raymarch fetches the bake LUTs through texture objects (8-bit filter weights) in the production object,
+// with exact fp32 software filtering in the strict one
+#ifdef SKY_STRICT_TU
+constexpr bool kCompositeTexLut = false;
+#else
+constexpr bool kCompositeTexLut = true;
+#endif
 template <bool MS, bool TEXLUT = false>
 SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture,
                                        const LutView& multiscattering_texture, float start_i, float3 earth_center,
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
             transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
         } else {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
-            luminance = ComputeScatteredLuminance<false, true>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+            luminance = ComputeScatteredLuminance<false, kCompositeTexLut>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
                                                                view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused);
         }
     }
@@ -499,6 +506,9 @@ int launch_atmosphere_luts(SkyContext* ctx) {
 }
 
 #else   // SKY_COMPOSITE_TU
+#ifdef SKY_STRICT_TU
+#define launch_composite launch_composite_strict
+#endif
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h) {
     RenderParams P = make_render_params(ctx);
     P.depth = depth; P.hdr = hdr; P.width = w; P.height = h;

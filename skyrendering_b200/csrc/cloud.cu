@@ -5,6 +5,15 @@
 //
 // Bounds: the reference dispatches ceil-div groups with no in-shader bounds checks and relies on GL
 // dropping out-of-range image stores (GLReloadableProgram.h:55-59); every kernel here guards explicitly.
+// Compiled twice (Makefile): the production objects keep FMA contraction and the approximate division / sqrt / exp of
+// -use_fast_math (frames are compared at relative RMS 1e-2); with -DSKY_STRICT_TU the same source is built with
+// -fmad=false and IEEE division / sqrt into *_strict entry points (sky_set_strict_arithmetic), which follow the
+// oracle's unfused fp32 arithmetic operation by operation -- the validation mode the bit-level parity tests use.
+#ifdef SKY_STRICT_TU
+#define launch_cloud_shadow launch_cloud_shadow_strict
+#define launch_cloud_begin launch_cloud_begin_strict
+#define launch_cloud_end launch_cloud_end_strict
+#endif
 #include "atmosphere_dev.cuh"
 #include "context.h"
 #include "material_dev.cuh"
@@ -730,6 +739,7 @@ CloudParams make_cloud_params(SkyContext* ctx, const SkyCloudCommonBufferData& c
 
 }  // namespace
 
+#ifndef SKY_STRICT_TU  // host-only helper, shared with the strict objects
 int make_material_params(SkyContext* ctx, const float* camera_pos, MaterialParams& M) {
     M.m = ctx->material;
     M.cloud_map = ctx->cloud_map.view;
@@ -758,6 +768,8 @@ int make_material_params(SkyContext* ctx, const float* camera_pos, MaterialParam
     M.m0_zero_base_is_zero = M.m.type == SKY_MATERIAL_DEFAULT0 && dp[0] >= 0.0f && dp[1] >= 0.0f && dp[0] + dp[1] <= 1.0f;
     return 0;
 }
+
+#endif  // SKY_STRICT_TU
 
 static int check_material_ready(SkyContext* ctx) {
     switch (ctx->material.type) {
@@ -884,6 +896,7 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
     return 0;
 }
 
+#ifndef SKY_STRICT_TU
 int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
     if (!ctx->detail.valid) return sky_fail(ctx, "tex_peak needs the detail volume (noise_generate(SKY_NOISE_DETAIL))");
     const int iters = 1024, blocks = 148 * 16, threads = 256;
@@ -906,3 +919,4 @@ int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
     *fetches_per_second = double(blocks) * threads * iters / (double(best) * 1e-3);
     return 0;
 }
+#endif  // SKY_STRICT_TU

@@ -55,6 +55,7 @@ struct SkyContext {
     cudaStream_t stream = nullptr;
     std::string error;
     bool hw_filtering = false;
+    bool strict_arithmetic = false;  // sky_set_strict_arithmetic: route K6, K11-K18, K19/K20 to the *_strict objects
     bool counting = false;
 
     // frame overlap (sky_set_frame_overlap): second lane of a frame, see api.cu
@@ -164,3 +165,13 @@ int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32
                       const int32_t region[4]);                                // pathtrace.cu   K19
 int launch_pt_resolve(SkyContext* ctx, uint32_t frame_count, half4* hdr);      // pathtrace.cu   K20
 int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second);    // cloud.cu
+// the same entry points of the strict objects (cloud_strict.o, pathtrace_strict.o, composite_strict.o)
+#ifndef SKY_STRICT_TU  // (inside those objects the plain names above ARE these, by macro)
+int launch_composite_strict(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);
+int launch_cloud_shadow_strict(SkyContext* ctx, const SkyCloudCommonBufferData& c);
+int launch_cloud_begin_strict(SkyContext* ctx, const SkyCloudCommonBufferData& c, const SkyCloudBufferData& b, const float* depth,
+                              int band_rows, int band_index, int band_count);
+int launch_cloud_end_strict(SkyContext* ctx, const SkyCloudCommonBufferData& c, const float* depth, half4* hdr, int phases);
+int launch_pt_samples_strict(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32_t frame_begin, uint32_t count, const int32_t region[4]);
+int launch_pt_resolve_strict(SkyContext* ctx, uint32_t frame_count, half4* hdr);
+#endif

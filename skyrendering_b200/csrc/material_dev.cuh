@@ -14,6 +14,15 @@
 #include "common.cuh"
 #include "context.h"
 
+// Approximate division / log2 in the production objects, IEEE ones in the strict objects (see cloud.cu)
+#ifdef SKY_STRICT_TU
+#define SKY_FDIV(a, b) ((a) / (b))
+#define SKY_LOG2(x) log2f(x)
+#else
+#define SKY_FDIV(a, b) __fdividef(a, b)
+#define SKY_LOG2(x) __log2f(x)
+#endif
+
 struct MaterialParams {
     SkyMaterialBlock m;
     MipView cloud_map, detail, displacement, voxel;
@@ -170,10 +179,10 @@ SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, int level) 
 // ---- SampleSigmaT ------------------------------------------------------------------------------------
 // VolumetricCloudDefaultMaterial0.glsl:9-16
 SKY_D float CalHeightMask(float cloud_type, float height01) {
-    float height_in_type = clampf(__fdividef(height01, cloud_type), 0.0f, 1.0f);  // same inf / NaN cases as '/'
+    float height_in_type = clampf(SKY_FDIV(height01, cloud_type), 0.0f, 1.0f);  // same inf / NaN cases as '/'
     return clampf(height_in_type * (height_in_type - 1.0f) * -4.0f, 0.0f, 1.0f);
 }
-SKY_D float Remap01(float x, float x0, float x1) { return clampf(__fdividef(x - x0, x1 - x0), 0.0f, 1.0f); }
+SKY_D float Remap01(float x, float x0, float x1) { return clampf(SKY_FDIV(x - x0, x1 - x0), 0.0f, 1.0f); }
 SKY_D float distance2(float3 a, float3 b) { float3 d = a - b; return dot(d, d); }
 
 // One SampleSigmaT(pos, height01) evaluation split at its texture fetches, so a caller can keep several evaluations
@@ -206,7 +215,7 @@ struct SigmaEval {
         pos = p; height01 = h01; need = true;
         if (MAT == SKY_MATERIAL_DEFAULT0 || MAT == SKY_MATERIAL_DEFAULT1) {
             const SkyMaterialCommonBufferData& mc = M.m.common;
-            log2_d2 = __log2f(distance2(pos, M.camera_pos));
+            log2_d2 = SKY_LOG2(distance2(pos, M.camera_pos));
             const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
             int lc = level_from_log2(log2_d2, M.lod_h_cloud_map, M.cloud_map.levels);
             float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
@@ -238,7 +247,7 @@ struct SigmaEval {
             const SkyMaterialVoxelBufferData& m = M.m.u.voxel;
             float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
             float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
-            int level = level_from_log2(__log2f(distance2(pos, M.camera_pos)), M.lod_h_voxel, M.voxel.levels);
+            int level = level_from_log2(SKY_LOG2(distance2(pos, M.camera_pos)), M.lod_h_voxel, M.voxel.levels);
             if (HW) {
                 detail = sample3d_hw(M.voxel, u, v, height01, level);
             } else {
@@ -266,7 +275,7 @@ struct SigmaEval {
                 float3 displace_vector = f3(0.0f + disp[0] + disp[2], 0.0f + disp[1], 0.0f + disp[3]);
                 float3 p = pos + m.uDisplacementScale * displace_vector;
                 const SkySampleInfo& ti = mc.uDetailSampleInfo;
-                int lt = level_from_log2(__log2f(distance2(p, M.camera_pos)), M.lod_h_detail, M.detail.levels);
+                int lt = level_from_log2(SKY_LOG2(distance2(p, M.camera_pos)), M.lod_h_detail, M.detail.levels);
                 float tu = p.x * ti.frequency + ti.bias[0], tv = p.y * ti.frequency + ti.bias[1], tw = p.z * ti.frequency;
                 if (HW) {
                     detail = sample3d_hw(M.detail, tu, tv, tw, lt);

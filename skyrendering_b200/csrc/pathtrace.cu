@@ -19,6 +19,12 @@
 // counter, so a finished path never idles its lane.  Each job writes its sample to its own slot and
 // a second kernel adds the slots to the RGBA32F accumulator in kFrameId order, which keeps the
 // reference's order of fp32 additions and makes the result independent of scheduling.
+// Compiled twice like cloud.cu: -DSKY_STRICT_TU builds the unfused, IEEE-division objects behind sky_set_strict_arithmetic.
+#ifdef SKY_STRICT_TU
+#define launch_pt_samples launch_pt_samples_strict
+#define launch_pt_resolve launch_pt_resolve_strict
+#define SKY_K19_PRECISE_LOG
+#endif
 #include "atmosphere_dev.cuh"
 #include "context.h"
 #include "material_dev.cuh"

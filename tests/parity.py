@@ -58,12 +58,14 @@ def to_numpy(x):
     return x if isinstance(x, np.ndarray) else x.detach().cpu().numpy()
 
 
-def run_cloud_frames(scene, width, height, library, frames, device, composite=True, move=None, hw=False, count=False):
+def run_cloud_frames(scene, width, height, library, frames, device, composite=True, move=None, hw=False, count=False, strict=False):
     """Bake, zero histories, run `frames` HandleDisplayEvent iterations (static camera unless `move`
     gives a per-frame camera delta), return the final HDR and the intermediate buffers."""
     r = Renderer(scene, width, height, library=library)
     if hw:
         r.ctx.set_hw_filtering(True)
+    if strict:
+        r.ctx.set_strict_arithmetic(True)
     r.prime()
     depth_np = r.scene.ground_depth(width, height)
     depth, hdr = make_buffers(width, height, depth_np, device)
@@ -93,8 +95,10 @@ def run_cloud_frames(scene, width, height, library, frames, device, composite=Tr
     return out
 
 
-def run_path_trace(scene, width, height, library, spp, grid=None, frame_begin=1, region=None, **pt):
+def run_path_trace(scene, width, height, library, spp, grid=None, frame_begin=1, region=None, strict=False, **pt):
     r = Renderer(scene, width, height, library=library)
+    if strict:
+        r.ctx.set_strict_arithmetic(True)
     if grid is not None:
         r.upload_voxels(grid)
     r.prime()
