@@ -456,6 +456,22 @@ def main():
                                          "sample": "one whole frame at the same resolution (noise textures already generated)"}
             configs[key] = entry
 
+        # C5 on the shipped data set: data/wdas/wdas_cloud_sixteenth.vdb read by host/vdb.cpp (committed R8 fixture)
+        from skyrendering_b200.renderer import wdas_sixteenth_grid
+        rw = Renderer("c5", PT_W, PT_H, library=cuda, device=local_rank)
+        rw.upload_voxels(wdas_sixteenth_grid())
+        rw.prime()
+        cw, _, _ = rw.cloud_update(0.0)
+        rw.ctx.cloud_shadow(cw)
+        rw.atmosphere_render_luts()
+        rw.path_trace_begin()
+        wdas_spp = 64
+        wdas_ms = kernel_ms(lambda: rw.ctx.pt_samples(cw, 1, wdas_spp, [0, 0, PT_W, PT_H]), reps=2)
+        configs["c5_wdas_cloud_sixteenth"] = {
+            "workload": f"c5 path tracer {PT_W}x{PT_H} on wdas_cloud_sixteenth.vdb (126x154x86 R8, 415 642 active voxels), reference defaults, one launch of {wdas_spp} kFrameIds",
+            "ms_per_launch": wdas_ms, "gsamples_per_s": PT_W * PT_H * wdas_spp / (wdas_ms * 1e-3) / 1e9}
+        del rw
+
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample ------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:

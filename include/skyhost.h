@@ -51,6 +51,31 @@ int skyhost_noise_info(SkyScene* scene, int kind, SkyNoiseCreateInfo out[2], int
 int skyhost_set_voxel_dim(SkyScene* scene, int dx, int dy, int dz);
 int skyhost_material_type(SkyScene* scene, int* type);
 
+/* VolumetricCloudVoxelMaterial ctor (VolumetricCloudVoxelMaterial.cpp:40-74): what openvdb::io::File::readGrid + the
+ * dense fill + the GL_FLOAT -> GL_R8 upload produce for the first grid of an OpenVDB file.  A minimal reader of the
+ * published FloatGrid ("Tree_float_5_4_3") layout, file versions 222-224 without ZIP / BLOSC (the shipped
+ * data/wdas/wdas_cloud_sixteenth.vdb); anything else fails with a message.  dim = {dx, dy, dz} = vdb {x, z, y}
+ * ("swap yz"); voxels [dz][dy][dx], ready for sky_voxel_upload + skyhost_set_voxel_dim. */
+typedef struct SkyVdbGrid SkyVdbGrid;
+typedef struct SkyVdbInfo {
+    int32_t dim[3];            /* dx, dy, dz */
+    int32_t bbox_min[3];       /* index-space bounding box of the active values, vdb x, y, z */
+    int32_t bbox_max[3];
+    int32_t file_version;
+    int64_t active_voxels;
+    int64_t file_voxel_count;  /* the grid's own "file_voxel_count" metadata, -1 if absent */
+    int32_t file_bbox_min[3];  /* the grid's own "file_bbox_min/max" metadata (zeros if absent) */
+    int32_t file_bbox_max[3];
+    float background;
+    int32_t has_file_bbox;
+} SkyVdbInfo;
+int skyhost_vdb_open(const char* path, SkyVdbGrid** out);
+int skyhost_vdb_parse(const void* bytes, int64_t size, SkyVdbGrid** out);
+void skyhost_vdb_close(SkyVdbGrid* grid);
+int skyhost_vdb_info(SkyVdbGrid* grid, SkyVdbInfo* out);
+int skyhost_vdb_fill_r8(SkyVdbGrid* grid, uint8_t* voxels, int64_t capacity);
+int skyhost_vdb_fill_float(SkyVdbGrid* grid, float* voxels, int64_t capacity);
+
 /* PathTracing ctor constants + tile schedule (VolumetricCloud.cpp:495-519,571-581). */
 int skyhost_pt_params(SkyScene* scene, int sqrt_tile_count, int max_bounces, float region_box_half_width,
                       int importance_sampling, int prng, int environment_lighting);

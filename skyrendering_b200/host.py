@@ -12,6 +12,13 @@ from .abi import (AtmosphereBufferData, AtmosphereRenderBufferData, CloudBufferD
 _lib = None
 
 
+class VdbInfo(C.Structure):
+    """SkyVdbInfo (include/skyhost.h)."""
+    _fields_ = [("dim", C.c_int32 * 3), ("bbox_min", C.c_int32 * 3), ("bbox_max", C.c_int32 * 3), ("file_version", C.c_int32),
+                ("active_voxels", C.c_int64), ("file_voxel_count", C.c_int64), ("file_bbox_min", C.c_int32 * 3),
+                ("file_bbox_max", C.c_int32 * 3), ("background", C.c_float), ("has_file_bbox", C.c_int32)]
+
+
 def _host():
     global _lib
     if _lib is None:
@@ -41,6 +48,12 @@ def _host():
             "skyhost_camera_move": ([V, P(C.c_float * 3), C.c_float, C.c_float], I),
             "skyhost_view_projection": ([V, P(C.c_float * 16)], I),
             "skyhost_ground_depth": ([V, C.c_void_p, I, I], I),
+            "skyhost_vdb_open": ([C.c_char_p, P(V)], I),
+            "skyhost_vdb_parse": ([C.c_void_p, C.c_int64, P(V)], I),
+            "skyhost_vdb_close": ([V], None),
+            "skyhost_vdb_info": ([V, P(VdbInfo)], I),
+            "skyhost_vdb_fill_r8": ([V, C.c_void_p, C.c_int64], I),
+            "skyhost_vdb_fill_float": ([V, C.c_void_p, C.c_int64], I),
         }
         for name, (args, res) in sig.items():
             fn = getattr(L, name)
@@ -54,7 +67,8 @@ HOST_SYMBOLS = [
     "skyhost_atmosphere_buffer", "skyhost_lut_config", "skyhost_atmosphere_render_buffer", "skyhost_set_viewport",
     "skyhost_cloud_update", "skyhost_noise_info", "skyhost_set_voxel_dim", "skyhost_material_type", "skyhost_pt_params",
     "skyhost_pt_init", "skyhost_pt_region", "skyhost_camera_get", "skyhost_camera_move", "skyhost_view_projection",
-    "skyhost_ground_depth",
+    "skyhost_ground_depth", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
+    "skyhost_vdb_fill_float",
 ]
 
 
@@ -169,3 +183,48 @@ class Scene:
         out = np.empty((h, w), np.float32)
         self._check(_host().skyhost_ground_depth(self.h, out.ctypes.data, w, h))
         return out
+
+
+class VdbGrid:
+    """The first grid of an OpenVDB file as the voxel material loads it (VolumetricCloudVoxelMaterial.cpp:40-74)."""
+
+    def __init__(self, source):
+        L = _host()
+        h = C.c_void_p()
+        if isinstance(source, (bytes, bytearray)):
+            rc = L.skyhost_vdb_parse(bytes(source), len(source), C.byref(h))
+        else:
+            rc = L.skyhost_vdb_open(os.fsencode(source), C.byref(h))
+        if rc != 0:
+            raise SkyError(L.skyhost_last_error().decode())
+        self.h = h
+        self.info = VdbInfo()
+        if L.skyhost_vdb_info(self.h, C.byref(self.info)) != 0:
+            raise SkyError(L.skyhost_last_error().decode())
+
+    def __del__(self):
+        try:
+            if self.h:
+                _host().skyhost_vdb_close(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def dim(self):
+        """(dx, dy, dz) = vdb (x, z, y)."""
+        return tuple(self.info.dim)
+
+    def _fill(self, fn, dtype):
+        dx, dy, dz = self.dim
+        out = np.empty((dz, dy, dx), dtype)
+        if fn(self.h, out.ctypes.data_as(C.c_void_p), out.size) != 0:
+            raise SkyError(_host().skyhost_last_error().decode())
+        return out
+
+    def voxels_r8(self):
+        """uint8 [dz][dy][dx]: the level-0 texels of the GL_R8 voxel texture."""
+        return self._fill(_host().skyhost_vdb_fill_r8, np.uint8)
+
+    def voxels_float(self):
+        return self._fill(_host().skyhost_vdb_fill_float, np.float32)

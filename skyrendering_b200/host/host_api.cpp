@@ -4,11 +4,15 @@
 #include <string>
 
 #include "scene.h"
+#include "vdb.h"
 
 using namespace skyhost;
 
 struct SkyScene {
     Scene scene;
+};
+struct SkyVdbGrid {
+    std::unique_ptr<VdbGrid> grid;
 };
 
 static thread_local std::string g_error;
@@ -85,6 +89,46 @@ int skyhost_set_voxel_dim(SkyScene* s, int dx, int dy, int dz) {
         auto& m = s->scene.volumetric_cloud_.material;
         if (!m) throw std::runtime_error("no material");
         m->SetVoxelDim(dx, dy, dz);
+    });
+}
+
+int skyhost_vdb_open(const char* path, SkyVdbGrid** out) {
+    *out = nullptr;
+    return guarded([&] { *out = new SkyVdbGrid{VdbGrid::open(path)}; });
+}
+int skyhost_vdb_parse(const void* bytes, int64_t size, SkyVdbGrid** out) {
+    *out = nullptr;
+    return guarded([&] { *out = new SkyVdbGrid{VdbGrid::parse(static_cast<const uint8_t*>(bytes), size_t(size))}; });
+}
+void skyhost_vdb_close(SkyVdbGrid* g) { delete g; }
+int skyhost_vdb_info(SkyVdbGrid* g, SkyVdbInfo* out) {
+    return guarded([&] {
+        SkyVdbInfo info{};
+        g->grid->voxel_dim(info.dim);
+        g->grid->bbox(info.bbox_min, info.bbox_max);
+        info.file_version = int32_t(g->grid->file_version());
+        info.active_voxels = g->grid->active_voxel_count();
+        if (!g->grid->metadata_int("file_voxel_count", info.file_voxel_count)) info.file_voxel_count = -1;
+        info.has_file_bbox = g->grid->metadata_vec3i("file_bbox_min", info.file_bbox_min) && g->grid->metadata_vec3i("file_bbox_max", info.file_bbox_max);
+        info.background = g->grid->background();
+        *out = info;
+    });
+}
+static int64_t vdb_voxels(SkyVdbGrid* g) {
+    int32_t d[3];
+    g->grid->voxel_dim(d);
+    return int64_t(d[0]) * d[1] * d[2];
+}
+int skyhost_vdb_fill_r8(SkyVdbGrid* g, uint8_t* voxels, int64_t capacity) {
+    return guarded([&] {
+        if (capacity < vdb_voxels(g)) throw std::runtime_error("vdb: output buffer too small");
+        g->grid->fill_r8(voxels);
+    });
+}
+int skyhost_vdb_fill_float(SkyVdbGrid* g, float* voxels, int64_t capacity) {
+    return guarded([&] {
+        if (capacity < vdb_voxels(g)) throw std::runtime_error("vdb: output buffer too small");
+        g->grid->fill_dense(voxels);
     });
 }
 

@@ -57,6 +57,13 @@ def synthetic_voxel_grid(dx=126, dy=154, dz=86, seed=0, blobs=64):
     return np.round(np.sqrt(dens) * 255.0).astype(np.uint8)
 
 
+def wdas_sixteenth_grid():
+    """The R8 voxel texture of data/wdas/wdas_cloud_sixteenth.vdb (the file config_voxel.json's material loads), from the
+    committed fixture tests/golden/wdas_cloud_sixteenth_r8.npz (tools/make_vdb_fixture.py; the .vdb itself does not travel).
+    (c) 2017 Disney Enterprises, Inc., CC BY-SA 3.0."""
+    return np.load(os.path.join(abi.REPO_ROOT, "tests", "golden", "wdas_cloud_sixteenth_r8.npz"))["voxels"]
+
+
 def synthetic_voxel_grid_large(scale, seed=0, blobs=64, device="cuda", slab=16):
     """The same field as synthetic_voxel_grid sampled `scale` times finer per axis (4: about wdas_cloud_quarter,
     497 x 612 x 338; 16: about the full-resolution wdas bounds, 1987 x 2449 x 1351 = 6.6 GB), evaluated slab by slab
@@ -120,6 +127,14 @@ class Renderer:
         dz, dy, dx = grid.shape
         self.scene.set_voxel_dim(dx, dy, dz)
         self.ctx.voxel_upload(grid)
+
+    def upload_vdb(self, path):
+        """VolumetricCloudVoxelMaterial's constructor (VolumetricCloudVoxelMaterial.cpp:40-75): first grid of an OpenVDB
+        file -> dense R8 texture with y/z swapped (host/vdb.cpp) -> device + mip chain."""
+        from .host import VdbGrid
+        grid = VdbGrid(path).voxels_r8()
+        self.upload_voxels(grid)
+        return grid
 
     def _material_update(self, common_cloud_material):
         """DynamicTexture::GenerateIfParameterChanged (VolumetricCloudDefaultMaterial.h:32-37)."""

@@ -319,6 +319,21 @@ def test_path_tracer_stream_parity(libs):
     assert np.mean(np.all(ag == ao, axis=-1)) > 0.5  # most pixels are bit-identical
 
 
+def test_path_tracer_on_the_wdas_sixteenth_cloud(libs):
+    """The real data set of bin/config_voxel.json (read by host/vdb.cpp, committed as an R8 fixture): same stream parity."""
+    from skyrendering_b200.renderer import wdas_sixteenth_grid
+    cuda, orc = libs
+    grid = wdas_sixteenth_grid()
+    kw = dict(max_bounces=16, region_box_half_width=10.0)
+    _, _, ag = run_path_trace("c5", 128, 72, cuda, 8, grid=grid, **kw)
+    _, _, ao = run_path_trace("c5", 128, 72, orc, 8, grid=grid, **kw)
+    assert ao[..., 3].min() < 8 * 0.99   # the cloud is in view (alpha accumulates the no-scatter decisions)
+    assert rel_rms(ag[..., :3], ao[..., :3]) < 2e-2
+    assert np.mean(ag[..., 3] == ao[..., 3]) > 0.99
+    _, _, as_ = run_path_trace("c5", 128, 72, cuda, 8, grid=grid, strict=True, **kw)
+    assert rel_rms(as_[..., :3], ao[..., :3]) < 1e-4
+
+
 def test_path_tracer_default_parameters_small(libs):
     """Reference defaults (128 bounces, +-100 km box, PCG, ground multi-bounce) at a size the oracle finishes."""
     cuda, orc = libs
