@@ -114,6 +114,22 @@ SKY_DM float sky_det_acosf(float x) {
     return 2.0f * (df + w);
 }
 
+/* asin(x), |x| <= 1 (callers clamp): the same rational kernel; |x| < 0.5: x + x R(x^2); else pi/2 - 2 (s + s R(z)),
+ * z = (1 - |x|)/2, s = sqrt(z)  (GetVisibilityFromMoonShadow, Atmosphere.glsl:213). */
+SKY_DM float sky_det_asinf(float x) {
+    const float pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f;
+    float ax = x < 0.0f ? -x : x;
+    if (ax >= 1.0f) return x < 0.0f ? -(pio2_hi + pio2_lo) : (pio2_hi + pio2_lo);
+    if (ax < 0.5f) {
+        if (ax < 2.4414062e-04f) return x;
+        return x + x * sky_det_acos_r(x * x);
+    }
+    float z = (1.0f - ax) * 0.5f;
+    float s = sqrtf(z);
+    float t = pio2_hi - (2.0f * (s + s * sky_det_acos_r(z)) - pio2_lo);
+    return x < 0.0f ? -t : t;
+}
+
 /* x^1.5 for x >= 0 (MiePhaseFunction, Atmosphere.glsl:150): x * sqrt(x) */
 SKY_DM float sky_det_pow15f(float x) { return x * sqrtf(x); }
 

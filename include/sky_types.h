@@ -201,7 +201,9 @@ typedef struct SkyLutConfig {
     int32_t sky_view_dither;            /* sky_view_lut_dither_sample_point_enable            */
     int32_t aerial_perspective_dither;  /* aerial_perspective_lut_dither_sample_point_enable  */
     int32_t raymarching_dither;         /* raymarching_dither_sample_point_enable             */
-    int32_t _pad[3];
+    int32_t moon_shadow;                /* moon_shadow_enable: eclipse term (Atmosphere.glsl:190-218,281-284)                 */
+    int32_t volumetric_light;           /* volumetric_light_enable: mesh shadow map in the march (Atmosphere.glsl:180-188,274-277) */
+    int32_t _pad[1];
 } SkyLutConfig;
 
 /* VolumetricCloud::PathTracing::InitParam (VolumetricCloud.h:158-168) plus the compile-time
@@ -258,6 +260,9 @@ enum SkyResource {
     SKY_RES_DISPLACEMENT_MIPS = 23,
     SKY_RES_VOXEL_MIPS = 24,
     SKY_RES_COUNTERS = 25,            /* uint64 [8]: work counters, see sky_counters */
+    SKY_RES_MESH_SHADOW_MAP = 26,     /* float  [2048][2048] light-space depth of the mesh shadow pass (ShadowMap.cpp:8-27,
+                                         AppWindow.cpp:25,183-190), cleared to 1.0; an INPUT: written by the caller with
+                                         sky_write_resource, read by K3/K4/K6 when volumetric_light is set */
     SKY_RES_COUNT_
 };
 

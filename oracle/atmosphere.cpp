@@ -63,6 +63,7 @@ void Atmosphere::BakeMultiscattering(const Image<4>& transmittance_texture, Imag
 
 // K3 -- AtmosphereRenderer.glsl:153-186
 void AtmosphereRenderer::BakeSkyView(Image<4>& luminance_image, Image<4>& transmittance_image) const {
+    const Atmosphere::ScatterExtras ex = extras();
 #pragma omp parallel for schedule(dynamic)
     for (int y = 0; y < cfg.sky_view_height; ++y)
         for (int x = 0; x < cfg.sky_view_width; ++x) {
@@ -80,7 +81,7 @@ void AtmosphereRenderer::BakeSkyView(Image<4>& luminance_image, Image<4>& transm
                 float start_i = DitherStart(cfg.sky_view_dither != 0, x, y);
                 luminance = atm.ComputeScatteredLuminance<false>(
                     transmittance_texture, &multiscattering_texture, start_i, earth_center(), start_position,
-                    view_direction, sun_direction(), marching_distance, u.sky_view_lut_steps, transmittance, nullptr);
+                    view_direction, sun_direction(), marching_distance, u.sky_view_lut_steps, transmittance, nullptr, &ex);
             }
             luminance_image.store(x, y, vec4(luminance, 0.0f));
             transmittance_image.store(x, y, vec4(transmittance, 0.0f));
@@ -91,6 +92,7 @@ void AtmosphereRenderer::BakeSkyView(Image<4>& luminance_image, Image<4>& transm
 void AtmosphereRenderer::BakeAerialPerspective(Image<4>& luminance_image, Image<4>& transmittance_image) const {
     const ivec3 size(luminance_image.w, luminance_image.h, luminance_image.d);
     const mat4 inv_view_projection(u.inv_view_projection);
+    const Atmosphere::ScatterExtras ex = extras();
 #pragma omp parallel for schedule(dynamic) collapse(2)
     for (int z = 0; z < size.z; ++z)
         for (int y = 0; y < size.y; ++y)
@@ -113,7 +115,7 @@ void AtmosphereRenderer::BakeAerialPerspective(Image<4>& luminance_image, Image<
                     luminance = atm.ComputeScatteredLuminance<false>(
                         transmittance_texture, &multiscattering_texture, start_i, earth_center(), start_position,
                         view_direction, sun_direction(), marching_distance, u.aerial_perspective_lut_steps, transmittance,
-                        nullptr);
+                        nullptr, &ex);
                 }
                 luminance_image.store(x, y, z, vec4(luminance, 0.0f));
                 transmittance_image.store(x, y, z, vec4(transmittance, 0.0f));
@@ -181,6 +183,7 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
                                    int width, int height, uint16_t* hdr) const {
     const mat4 inv_view_projection(u.inv_view_projection);
     const ivec3 ap_size(ap_lum.w, ap_lum.h, ap_lum.d);
+    const Atmosphere::ScatterExtras ex = extras();
 #pragma omp parallel for schedule(dynamic)
     for (int py = 0; py < height; ++py)
         for (int px = 0; px < width; ++px) {
@@ -217,7 +220,7 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
                 } else {
                     luminance = atm.ComputeScatteredLuminance<false>(
                         transmittance_texture, &multiscattering_texture, start_i, earth_center(), start_position,
-                        view_direction, sun_direction(), marching_distance, u.raymarching_steps, transmittance, nullptr);
+                        view_direction, sun_direction(), marching_distance, u.raymarching_steps, transmittance, nullptr, &ex);
                 }
             }
             if (shadow_froxel)

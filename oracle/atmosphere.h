@@ -164,13 +164,68 @@ struct Atmosphere {
         return texture_linear(tex, uv, Sampler()).rgb();
     }
 
-    // Atmosphere.glsl:220-295.  VOLUMETRIC_LIGHT_ENABLE and MOON_SHADOW_ENABLE are 0 in all four
-    // BASELINE scenes and are not restated.
+    // Atmosphere.glsl:180-188: sampler2DShadow lookup with Samplers::GetShadowMapSampler (Samplers.cpp:43-51): LINEAR,
+    // CLAMP_TO_BORDER with border 1, compare LEQUAL -- the bilinear blend of the four comparison results (PCF).
+    static float GetVisibilityFromShadowMap(const Image<1>& shadow_map, const mat4& light_view_projection, vec3 position) {
+        vec4 xyzw = light_view_projection * vec4(position, 1.0f);
+        vec3 xyz = vec3(xyzw.x, xyzw.y, xyzw.z) / xyzw.w;
+        xyz = xyz * 0.5f + 0.5f;
+        float depth = xyz.z;
+        if (depth >= 1.0f) return 1.0f;
+        float x = xyz.x * float(shadow_map.w) - 0.5f, y = xyz.y * float(shadow_map.h) - 0.5f;
+        float fx = std::floor(x), fy = std::floor(y);
+        float a = x - fx, b = y - fy;
+        auto cmp = [&](float i, float j) {
+            bool inside = i >= 0.0f && j >= 0.0f && i < float(shadow_map.w) && j < float(shadow_map.h);
+            float texel = inside ? shadow_map.load(int(i), int(j)).x : 1.0f;
+            return depth <= texel ? 1.0f : 0.0f;
+        };
+        return (1.0f - a) * (1.0f - b) * cmp(fx, fy) + a * (1.0f - b) * cmp(fx + 1.0f, fy) + (1.0f - a) * b * cmp(fx, fy + 1.0f) +
+               a * b * cmp(fx + 1.0f, fy + 1.0f);
+    }
+
+    // Atmosphere.glsl:190-210
+    static float GetVisibilityFromMoonShadow(float sun_moon_angular_distance, float sun_angular_radius, float moon_angular_radius) {
+        float max_radius = sun_angular_radius + moon_angular_radius;
+        float min_radius = std::fabs(sun_angular_radius - moon_angular_radius);
+        float sun_r2 = sun_angular_radius * sun_angular_radius;
+        float moon_r2 = moon_angular_radius * moon_angular_radius;
+        if (sun_moon_angular_distance >= max_radius) return 1.0f;
+        if (sun_moon_angular_distance <= min_radius) return clamp((sun_r2 - moon_r2) / sun_r2, 0.0f, 1.0f);
+        float distance2 = sun_moon_angular_distance * sun_moon_angular_distance;
+        float cos_half_sun = (distance2 + sun_r2 - moon_r2) / (2 * sun_moon_angular_distance * sun_angular_radius);
+        float cos_half_moon = (distance2 + moon_r2 - sun_r2) / (2 * sun_moon_angular_distance * moon_angular_radius);
+        float half_sun = sky_det_acosf(cos_half_sun);
+        float half_moon = sky_det_acosf(cos_half_moon);
+        float triangle_h = sun_angular_radius * std::sqrt(1 - cos_half_sun * cos_half_sun);
+        float area_total = (PI - half_sun) * sun_r2 + (PI - half_moon) * moon_r2 + triangle_h * sun_moon_angular_distance;
+        float area_uncovered = area_total - PI * moon_r2;
+        return area_uncovered / (PI * sun_r2);
+    }
+    // Atmosphere.glsl:212-218
+    float GetVisibilityFromMoonShadow(vec3 moon_vector, float moon_radius, vec3 sun_direction) const {
+        float inv_moon_distance = 1.0f / std::sqrt(dot(moon_vector, moon_vector));
+        vec3 moon_direction = moon_vector * inv_moon_distance;
+        float moon_angular_radius = sky_det_asinf(clamp(moon_radius * inv_moon_distance, -1.0f, 1.0f));
+        return GetVisibilityFromMoonShadow(sky_det_acosf(clamp(dot(sun_direction, moon_direction), -1.0f, 1.0f)), u.sun_angular_radius,
+                                           moon_angular_radius);
+    }
+
+    // The two optional terms of the march (the host writes them into the shader text as #defines, AtmosphereRenderer.cpp:99-101)
+    struct ScatterExtras {
+        bool moon_shadow = false;          // MOON_SHADOW_ENABLE
+        vec3 moon_position{0.0f};
+        float moon_radius = 0.0f;
+        const Image<1>* shadow_map = nullptr;  // VOLUMETRIC_LIGHT_ENABLE when non-null
+        mat4 light_view_projection;
+    };
+
+    // Atmosphere.glsl:220-295
     template <bool MS>
     vec3 ComputeScatteredLuminance(const Image<4>& transmittance_texture, const Image<4>* multiscattering_texture,
                                    float start_i, vec3 earth_center, vec3 start_position, vec3 view_direction,
                                    vec3 sun_direction, float marching_distance, float steps, vec3& transmittance,
-                                   vec3* L_f) const {
+                                   vec3* L_f, const ScatterExtras* extras = nullptr) const {
         float r = length(start_position - earth_center);
         vec3 up_direction = normalize(start_position - earth_center);
         float mu = dot(view_direction, up_direction);
@@ -201,8 +256,12 @@ struct Atmosphere {
             float mu_s_i = dot(sun_direction, up_direction_i);
             vec3 luminance_i = scattering_with_phase_i * GetSunVisibility(transmittance_texture, r_i, mu_s_i);
             if (!MS) {
+                if (extras && extras->shadow_map)  // :274-277
+                    luminance_i *= GetVisibilityFromShadowMap(*extras->shadow_map, extras->light_view_projection, position_i);
                 vec3 multiscattering_contribution = GetMultiscatteringContribution(*multiscattering_texture, r_i, mu_s_i);
                 luminance_i += u.multiscattering_mask * multiscattering_contribution * scattering_i;
+                if (extras && extras->moon_shadow)  // :281-284
+                    luminance_i *= GetVisibilityFromMoonShadow(extras->moon_position - position_i, extras->moon_radius, sun_direction);
                 luminance_i *= solar_illuminance();
             }
             luminance += transmittance * (luminance_i - luminance_i * transmittance_i) / extinction_i;
@@ -262,6 +321,17 @@ struct AtmosphereRenderer {
     const Image<4>& transmittance_texture;
     const Image<4>& multiscattering_texture;
     const Image<1>* blue_noise = nullptr;  // R16 64x64
+    const Image<1>* mesh_shadow_map = nullptr;  // DEPTH32F 2048^2 (ShadowMap.cpp:8-27), used when cfg.volumetric_light
+
+    Atmosphere::ScatterExtras extras() const {
+        Atmosphere::ScatterExtras e;
+        e.moon_shadow = cfg.moon_shadow != 0;
+        e.moon_position = vec3(u.moon_position);
+        e.moon_radius = u.moon_radius;
+        e.shadow_map = cfg.volumetric_light ? mesh_shadow_map : nullptr;
+        e.light_view_projection = mat4(u.light_view_projection);
+        return e;
+    }
 
     vec3 sun_direction() const { return vec3(u.sun_direction); }
     vec3 earth_center() const { return vec3(u.earth_center); }

@@ -57,6 +57,14 @@ void set_desc_f32(SkyResourceDesc* d, Image<C>& img) {
     d->ptr = img.data.data(); d->width = img.w; d->height = img.h; d->depth = img.d; d->channels = C;
     d->format = SKY_FMT_F32; d->bytes = img.data.size() * 4;
 }
+// ShadowMap(2048, 2048) cleared to 1.0 (AppWindow.cpp:25, ShadowMap.cpp:8-27); allocated on first use
+Image<1>& mesh_shadow_map(CloudScene& s) {
+    if (s.mesh_shadow_map.w == 0) {
+        s.mesh_shadow_map.resize(2048, 2048);
+        std::fill(s.mesh_shadow_map.data.begin(), s.mesh_shadow_map.data.end(), 1.0f);
+    }
+    return s.mesh_shadow_map;
+}
 }  // namespace
 
 extern "C" {
@@ -100,6 +108,7 @@ int orc_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
     s.ap_trans.resize(32, 32, cfg->aerial_perspective_depth);
     s.env.resize(cfg->environment_size, cfg->environment_size, 6);
     AtmosphereRenderer ar{s.atm, *r, *cfg, s.transmittance, s.multiscattering, &s.blue_noise};
+    if (cfg->volumetric_light) ar.mesh_shadow_map = &mesh_shadow_map(s);
     ar.BakeSkyView(s.sky_lum, s.sky_trans);
     ar.BakeAerialPerspective(s.ap_lum, s.ap_trans);
     ar.BakeEnvironment(s.sky_lum, s.sky_trans, s.env);
@@ -109,6 +118,7 @@ int orc_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
 int orc_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
     CloudScene& s = ctx->scene;
     AtmosphereRenderer ar{s.atm, s.render_u, s.lut_cfg, s.transmittance, s.multiscattering, &s.blue_noise};
+    if (s.lut_cfg.volumetric_light) ar.mesh_shadow_map = &mesh_shadow_map(s);
     const Image<1>* froxel = (s.shadow_froxel.w > 0) ? &s.shadow_froxel : nullptr;
     ar.Composite(s.sky_lum, s.sky_trans, s.ap_lum, s.ap_trans, froxel, depth, width, height, static_cast<uint16_t*>(hdr));
     return 0;
@@ -245,6 +255,7 @@ int orc_get_resource(SkyContext* ctx, int resource, SkyResourceDesc* d) {
         case SKY_RES_PT_MASK:
             d->ptr = s.pt_mask.data(); d->width = s.width; d->height = s.height; d->depth = 1; d->channels = 1; d->format = SKY_FMT_U8;
             d->bytes = s.pt_mask.size(); return 0;
+        case SKY_RES_MESH_SHADOW_MAP: set_desc_f32(d, mesh_shadow_map(s)); return 0;
         case SKY_RES_COUNTERS:
             ctx->counter_copy.resize(8);
             for (int i = 0; i < 8; ++i) ctx->counter_copy[i] = s.counters[i].load();
@@ -287,6 +298,7 @@ int orc_write_resource(SkyContext* ctx, int resource, const void* src, uint64_t 
         case SKY_RES_CLOUD_DISTANCE: return put_f32(s.cloud_distance.data);
         case SKY_RES_RECONSTRUCT: return put_half(s.reconstruct[1].data);
         case SKY_RES_PT_ACCUM: return put_f32(s.pt_accum.data);
+        case SKY_RES_MESH_SHADOW_MAP: return put_f32(mesh_shadow_map(s).data);
         case SKY_RES_SHADOW_FROXEL: {
             if (bytes != s.shadow_froxel.data.size() * 2) return fail(ctx, "write_resource: size mismatch");
             const uint16_t* p = static_cast<const uint16_t*>(src);

@@ -159,12 +159,14 @@ inline float exp(float x) { return sky_det_expf(x); }
 inline float sin(float x) { return sky_det_sinf(x); }
 inline float cos(float x) { return sky_det_cosf(x); }
 inline float acos(float x) { return sky_det_acosf(x); }
+inline float asin(float x) { return sky_det_asinf(x); }
 inline float pow(float x, float y) { return y == 1.5f ? sky_det_pow15f(x) : std::pow(x, y); }
 #else
 inline float exp(float x) { return std::exp(x); }
 inline float sin(float x) { return std::sin(x); }
 inline float cos(float x) { return std::cos(x); }
 inline float acos(float x) { return std::acos(x); }
+inline float asin(float x) { return std::asin(x); }
 inline float pow(float x, float y) { return std::pow(x, y); }
 #endif
 inline float sqrt(float x) { return std::sqrt(x); }
@@ -173,7 +175,6 @@ inline float log(float x) { return std::log(x); }
 inline float log2(float x) { return std::log2(x); }
 inline float exp2(float x) { return std::exp2(x); }
 inline float tan(float x) { return std::tan(x); }
-inline float asin(float x) { return std::asin(x); }
 inline float atan(float y, float x) { return std::atan2(y, x); }
 inline float abs(float x) { return std::fabs(x); }
 inline int abs(int x) { return x < 0 ? -x : x; }
@@ -359,8 +360,19 @@ struct Sampler {
 struct sampler2D : Sampler {};
 struct sampler3D : Sampler {};
 struct samplerCube : Sampler {};      // levels[l].d = 6 faces; see textureCubeLod0
-struct sampler2DShadow : Sampler {};  // only in permutations that are off in every BASELINE config (mesh shadow map)
-inline float texture(const sampler2DShadow&, const vec3&) { return 1.0f; }
+struct sampler2DShadow : Sampler {};  // mesh shadow map (VOLUMETRIC_LIGHT_ENABLE permutation)
+// GL 4.6 section 8.23 with COMPARE_REF_TO_TEXTURE / LEQUAL and LINEAR filtering: the comparison is made per texel and the
+// 0/1 results are blended with the bilinear weights (what every implementation does; the spec leaves it open)
+inline float texture(const sampler2DShadow& s, const vec3& p) {
+    if (s.levels.empty()) return 1.0f;
+    const Image& im = s.levels[0];
+    float x = p.x * float(im.w) - 0.5f, y = p.y * float(im.h) - 0.5f;
+    float fx = std::floor(x), fy = std::floor(y);
+    float a = x - fx, b = y - fy;
+    int i0 = int(fx), j0 = int(fy);
+    auto cmp = [&](int i, int j) { return p.z <= s.texel(im, i, j, 0).x ? 1.0f : 0.0f; };
+    return (1.0f - a) * (1.0f - b) * cmp(i0, j0) + a * (1.0f - b) * cmp(i0 + 1, j0) + (1.0f - a) * b * cmp(i0, j0 + 1) + a * b * cmp(i0 + 1, j0 + 1);
+}
 inline vec4 texture(const Sampler& s, const vec2& uv) { return s.sample(uv.x, uv.y, 0.0f, 0.0f); }
 inline vec4 texture2D(const Sampler& s, const vec2& uv) { return s.sample(uv.x, uv.y, 0.0f, 0.0f); }
 inline vec4 texture(const Sampler& s, const vec3& uvw) { return s.sample(uvw.x, uvw.y, uvw.z, 0.0f); }

@@ -65,7 +65,60 @@ namespace ref { namespace k3d0 {
 #undef DITHER_SAMPLE_POINT_ENABLE
 #undef AERIAL_PERSPECTIVE_COMPUTE_PROGRAM
 #include "ref_undef_guards.h"
-} namespace k5 {
+}
+// the optional march terms (off in the shipped scenes): moon shadow / mesh shadow map / both, no dither
+#define REF_PERMUTATION(NS, PROGRAM_MACRO, VOL, MOON)
+#undef VOLUMETRIC_LIGHT_ENABLE
+#undef MOON_SHADOW_ENABLE
+#define DITHER_SAMPLE_POINT_ENABLE 0
+#define SKY_VIEW_COMPUTE_PROGRAM
+#define VOLUMETRIC_LIGHT_ENABLE 0
+#define MOON_SHADOW_ENABLE 1
+namespace k3v0m1 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef VOLUMETRIC_LIGHT_ENABLE
+#undef MOON_SHADOW_ENABLE
+#define VOLUMETRIC_LIGHT_ENABLE 1
+#define MOON_SHADOW_ENABLE 0
+namespace k3v1m0 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef MOON_SHADOW_ENABLE
+#define MOON_SHADOW_ENABLE 1
+namespace k3v1m1 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef SKY_VIEW_COMPUTE_PROGRAM
+#define AERIAL_PERSPECTIVE_COMPUTE_PROGRAM
+namespace k4v1m1 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef VOLUMETRIC_LIGHT_ENABLE
+#define VOLUMETRIC_LIGHT_ENABLE 0
+namespace k4v0m1 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef VOLUMETRIC_LIGHT_ENABLE
+#undef MOON_SHADOW_ENABLE
+#define VOLUMETRIC_LIGHT_ENABLE 1
+#define MOON_SHADOW_ENABLE 0
+namespace k4v1m0 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef AERIAL_PERSPECTIVE_COMPUTE_PROGRAM
+#undef VOLUMETRIC_LIGHT_ENABLE
+#undef MOON_SHADOW_ENABLE
+#undef DITHER_SAMPLE_POINT_ENABLE
+#define VOLUMETRIC_LIGHT_ENABLE 0
+#define MOON_SHADOW_ENABLE 0
+namespace k5 {
 #define ENVIRONMENT_LUMINANCE_COMPUTE_PROGRAM
 #define DITHER_SAMPLE_POINT_ENABLE 1
 #include "../_ref/gen/AtmosphereRenderer.glsl.inc"
@@ -82,6 +135,8 @@ struct RefLutIO {
     float* ap_luminance;             // [depth][32][32][4]
     float* ap_transmittance;
     float* environment;              // [6][size][size][4] (values rounded to fp16)
+    const float* mesh_shadow_map;    // [S][S][4] (light-space depth in .x) when cfg->volumetric_light, else unused
+    int mesh_shadow_size;
 };
 
 template <class F>
@@ -107,7 +162,23 @@ extern "C" int ref_atmosphere_luts(const SkyAtmosphereBufferData* a, const SkyAt
         ref_bind_image(transmittance_image, io->sky_transmittance, sw, sh, 1, ref::FMT_RGBA32F);                 \
         ref::dispatch(main, ref_ceil_div(sw, LOCAL_SIZE_X), ref_ceil_div(sh, LOCAL_SIZE_Y), 1, LOCAL_SIZE_X, LOCAL_SIZE_Y, 1, false); \
     }
-    if (cfg->sky_view_dither) RUN_K3(k3d1) else RUN_K3(k3d0)
+#define RUN_PERM(RUN, NS)                                                                                         \
+    {                                                                                                            \
+        using namespace ref::NS;                                                                                 \
+        if (cfg->volumetric_light) {                                                                             \
+            ref_bind_texture(ref::NS::shadow_map_texture, io->mesh_shadow_map, io->mesh_shadow_size, io->mesh_shadow_size, 1, ref::CLAMP_TO_BORDER, ref::LINEAR); \
+            ref::NS::shadow_map_texture.border = ref::vec4(1.0f);                                                \
+        }                                                                                                        \
+    }                                                                                                            \
+    RUN(NS)
+    const bool perm = cfg->volumetric_light || cfg->moon_shadow;
+    if (perm && (cfg->sky_view_dither || cfg->aerial_perspective_dither)) return 3;  // permutation not compiled
+    if (cfg->volumetric_light && !io->mesh_shadow_map) return 4;
+    if (perm) {
+        if (cfg->volumetric_light && cfg->moon_shadow) { RUN_PERM(RUN_K3, k3v1m1) }
+        else if (cfg->volumetric_light) { RUN_PERM(RUN_K3, k3v1m0) }
+        else { RUN_PERM(RUN_K3, k3v0m1) }
+    } else if (cfg->sky_view_dither) RUN_K3(k3d1) else RUN_K3(k3d0)
 #define RUN_K4(NS)                                                                                               \
     {                                                                                                            \
         using namespace ref::NS;                                                                                 \
@@ -116,7 +187,11 @@ extern "C" int ref_atmosphere_luts(const SkyAtmosphereBufferData* a, const SkyAt
         ref_bind_image(transmittance_image, io->ap_transmittance, 32, 32, D, ref::FMT_RGBA32F);                  \
         ref::dispatch(main, ref_ceil_div(32, LOCAL_SIZE_X), ref_ceil_div(32, LOCAL_SIZE_Y), D, LOCAL_SIZE_X, LOCAL_SIZE_Y, 1, false); \
     }
-    if (cfg->aerial_perspective_dither) RUN_K4(k4d1) else RUN_K4(k4d0)
+    if (perm) {
+        if (cfg->volumetric_light && cfg->moon_shadow) { RUN_PERM(RUN_K4, k4v1m1) }
+        else if (cfg->volumetric_light) { RUN_PERM(RUN_K4, k4v1m0) }
+        else { RUN_PERM(RUN_K4, k4v0m1) }
+    } else if (cfg->aerial_perspective_dither) RUN_K4(k4d1) else RUN_K4(k4d0)
     {
         using namespace ref::k5;
         REF_BIND_COMMON();

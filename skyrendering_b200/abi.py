@@ -122,7 +122,8 @@ class NoiseCreateInfo(_Pod):
 class LutConfig(_Pod):
     _fields_ = [("sky_view_width", I), ("sky_view_height", I), ("aerial_perspective_depth", I),
                 ("environment_size", I), ("use_sky_view_lut", I), ("use_aerial_perspective_lut", I),
-                ("sky_view_dither", I), ("aerial_perspective_dither", I), ("raymarching_dither", I), ("_pad", I * 3)]
+                ("sky_view_dither", I), ("aerial_perspective_dither", I), ("raymarching_dither", I), ("moon_shadow", I),
+                ("volumetric_light", I), ("_pad", I * 1)]
 
 
 class PathTracingInit(_Pod):
@@ -145,7 +146,7 @@ ENV_OFF, ENV_CONST_ENVIRONMENT_MAP, ENV_GROUND_SINGLE_BOUNCE, ENV_GROUND_MULTI_B
  RES_AERIAL_TRANSMITTANCE, RES_ENVIRONMENT, RES_CLOUD_MAP, RES_DETAIL, RES_DISPLACEMENT, RES_SHADOW_MAP_RAW,
  RES_SHADOW_MAP, RES_SHADOW_FROXEL, RES_CHECKERBOARD_DEPTH, RES_INDEX_LINEAR_DEPTH, RES_CLOUD_RENDER,
  RES_CLOUD_DISTANCE, RES_RECONSTRUCT, RES_PT_ACCUM, RES_PT_MASK, RES_VOXEL, RES_CLOUD_MAP_MIPS, RES_DETAIL_MIPS,
- RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS) = range(26)
+ RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS, RES_MESH_SHADOW_MAP) = range(27)
 FMT_F32, FMT_F16, FMT_U8, FMT_U16, FMT_U64 = range(5)
 _FMT_DTYPE = {FMT_F32: np.float32, FMT_F16: np.float16, FMT_U8: np.uint8, FMT_U16: np.uint16, FMT_U64: np.uint64}
 (CNT_RENDER_SIGMA_EVALS, CNT_RENDER_TEX_FETCHES, CNT_PT_PATHS, CNT_PT_LOOKUPS, CNT_PT_COLLISIONS,

@@ -1,6 +1,7 @@
 // C ABI of libskyb200.so (include/skyb200.h).  Plain pointers and PODs only; no exceptions and no
 // torch types cross this boundary.  There is no CPU fallback anywhere in this library: without a
 // CUDA device sky_ctx_create fails.
+#include <vector>
 #include "../../include/skyb200.h"
 
 #include <cstring>
@@ -77,6 +78,7 @@ bool resolve(SkyContext* ctx, int resource, ResView& v) {
         case SKY_RES_SHADOW_MAP_RAW: v = view_of(ctx->shadow_maps[0], 2, SKY_FMT_F32); return true;
         case SKY_RES_SHADOW_MAP: v = view_of(ctx->shadow_maps[2], 2, SKY_FMT_F32); return true;
         case SKY_RES_SHADOW_FROXEL: v = view_of(ctx->shadow_froxel, 1, SKY_FMT_U16); return true;
+        case SKY_RES_MESH_SHADOW_MAP: v = view_of(ctx->mesh_shadow_map, 1, SKY_FMT_F32); return true;
         case SKY_RES_CHECKERBOARD_DEPTH: v = view_of(ctx->checkerboard_depth, 1, SKY_FMT_F32); return true;
         case SKY_RES_INDEX_LINEAR_DEPTH: v = view_of(ctx->index_linear_depth, 2, SKY_FMT_F32); return true;
         case SKY_RES_CLOUD_RENDER: v = view_of(ctx->render_texture, 4, SKY_FMT_F16); return true;
@@ -165,7 +167,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->transmittance); free_lut(ctx->multiscattering); free_lut(ctx->sky_lum); free_lut(ctx->sky_trans);
     free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
     for (auto& m : ctx->shadow_maps) free_lut(m);
-    free_lut(ctx->shadow_froxel); free_lut(ctx->checkerboard_depth); free_lut(ctx->cloud_distance);
+    free_lut(ctx->mesh_shadow_map); free_lut(ctx->shadow_froxel); free_lut(ctx->checkerboard_depth); free_lut(ctx->cloud_distance);
     free_lut(ctx->index_linear_depth); free_lut(ctx->render_texture); free_lut(ctx->reconstruct[0]); free_lut(ctx->reconstruct[1]);
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
@@ -493,8 +495,19 @@ int sky_read_resource(SkyContext* ctx, int resource, void* host_dst, uint64_t by
     return 0;
 }
 
+// ShadowMap(2048, 2048) + ClearBindViewport's glClearDepthf(1) (AppWindow.cpp:25, ShadowMap.cpp:8-27)
+extern "C++" int ensure_mesh_shadow_map(SkyContext* ctx) {
+    if (ctx->mesh_shadow_map.p) return 0;
+    if (int e = sky_alloc(ctx, ctx->mesh_shadow_map, 2048, 2048, 1, false)) return e;
+    std::vector<float> ones(size_t(2048) * 2048, 1.0f);
+    SKY_CUDA(ctx, cudaMemcpyAsync(ctx->mesh_shadow_map.p, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint64_t bytes) {
     if (int e = lanes_join(ctx)) return e;
+    if (resource == SKY_RES_MESH_SHADOW_MAP) { if (int e = ensure_mesh_shadow_map(ctx)) return e; }
     switch (resource) {
         case SKY_RES_CLOUD_MAP: if (int e = build_mip_texture(ctx, ctx->cloud_map, 512, 512, 1, 2, false)) return e; break;
         case SKY_RES_DETAIL: if (int e = build_mip_texture(ctx, ctx->detail, 128, 128, 128, 1, false)) return e; break;

@@ -14,11 +14,13 @@
 #define LUT_COS(x) __cosf(x)
 #define LUT_SIN(x) __sinf(x)
 #define LUT_ACOS(x) acosf(x)
+#define LUT_ASIN(x) asinf(x)
 #else
 #define LUT_EXP(x) sky_det_expf(x)
 #define LUT_COS(x) sky_det_cosf(x)
 #define LUT_SIN(x) sky_det_sinf(x)
 #define LUT_ACOS(x) sky_det_acosf(x)
+#define LUT_ASIN(x) sky_det_asinf(x)
 #endif
 
 namespace {
@@ -52,11 +54,72 @@ constexpr bool kCompositeTexLut = false;
 #else
 constexpr bool kCompositeTexLut = true;
 #endif
-template <bool MS, bool TEXLUT = false>
+// The two optional terms of the march: MOON_SHADOW_ENABLE (Atmosphere.glsl:190-218,281-284) and VOLUMETRIC_LIGHT_ENABLE
+// (:180-188,274-277); the host writes them into the shader text, here they are a template flag (EXTRA) + this block.
+struct ScatterExtras {
+    int moon_shadow;
+    float moon_radius;
+    float moon_position[3];
+    int shadow_size;             // 0: VOLUMETRIC_LIGHT_ENABLE off
+    const float* shadow_map;     // float[S][S] light-space depth (ShadowMap.cpp:8-27)
+    float light_view_projection[16];
+};
+
+// Atmosphere.glsl:180-188 through Samplers::GetShadowMapSampler (Samplers.cpp:43-51): LINEAR, CLAMP_TO_BORDER (1),
+// compare LEQUAL -- the bilinear blend of the four comparison results
+SKY_D float GetVisibilityFromShadowMap(const ScatterExtras& e, float3 position) {
+    const float* m = e.light_view_projection;
+    float X = m[0] * position.x + m[4] * position.y + m[8] * position.z + m[12] * 1.0f;
+    float Y = m[1] * position.x + m[5] * position.y + m[9] * position.z + m[13] * 1.0f;
+    float Z = m[2] * position.x + m[6] * position.y + m[10] * position.z + m[14] * 1.0f;
+    float Wc = m[3] * position.x + m[7] * position.y + m[11] * position.z + m[15] * 1.0f;
+    float sx = X / Wc * 0.5f + 0.5f, sy = Y / Wc * 0.5f + 0.5f, depth = Z / Wc * 0.5f + 0.5f;
+    if (depth >= 1.0f) return 1.0f;
+    const float S = float(e.shadow_size);
+    float x = sx * S - 0.5f, y = sy * S - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    auto cmp = [&](float i, float j) {
+        bool inside = i >= 0.0f && j >= 0.0f && i < S && j < S;
+        float texel = inside ? __ldg(e.shadow_map + size_t(int(j)) * e.shadow_size + int(i)) : 1.0f;
+        return depth <= texel ? 1.0f : 0.0f;
+    };
+    return (1.0f - a) * (1.0f - b) * cmp(fx, fy) + a * (1.0f - b) * cmp(fx + 1.0f, fy) + (1.0f - a) * b * cmp(fx, fy + 1.0f) +
+           a * b * cmp(fx + 1.0f, fy + 1.0f);
+}
+
+// Atmosphere.glsl:190-210
+SKY_D float GetVisibilityFromMoonShadow(float sun_moon_angular_distance, float sun_angular_radius, float moon_angular_radius) {
+    float max_radius = sun_angular_radius + moon_angular_radius;
+    float min_radius = fabsf(sun_angular_radius - moon_angular_radius);
+    float sun_r2 = sun_angular_radius * sun_angular_radius;
+    float moon_r2 = moon_angular_radius * moon_angular_radius;
+    if (sun_moon_angular_distance >= max_radius) return 1.0f;
+    if (sun_moon_angular_distance <= min_radius) return clampf((sun_r2 - moon_r2) / sun_r2, 0.0f, 1.0f);
+    float distance2 = sun_moon_angular_distance * sun_moon_angular_distance;
+    float cos_half_sun = (distance2 + sun_r2 - moon_r2) / (2 * sun_moon_angular_distance * sun_angular_radius);
+    float cos_half_moon = (distance2 + moon_r2 - sun_r2) / (2 * sun_moon_angular_distance * moon_angular_radius);
+    float half_sun = LUT_ACOS(cos_half_sun);
+    float half_moon = LUT_ACOS(cos_half_moon);
+    float triangle_h = sun_angular_radius * sqrtf(1 - cos_half_sun * cos_half_sun);
+    float area_total = (kPi - half_sun) * sun_r2 + (kPi - half_moon) * moon_r2 + triangle_h * sun_moon_angular_distance;
+    float area_uncovered = area_total - kPi * moon_r2;
+    return area_uncovered / (kPi * sun_r2);
+}
+// Atmosphere.glsl:212-218
+SKY_D float GetVisibilityFromMoonShadow(float3 moon_vector, float moon_radius, float3 sun_direction, float sun_angular_radius) {
+    float inv_moon_distance = 1.0f / sqrtf(dot(moon_vector, moon_vector));
+    float3 moon_direction = moon_vector * inv_moon_distance;
+    float moon_angular_radius = LUT_ASIN(clampf(moon_radius * inv_moon_distance, -1.0f, 1.0f));
+    return GetVisibilityFromMoonShadow(LUT_ACOS(clampf(dot(sun_direction, moon_direction), -1.0f, 1.0f)), sun_angular_radius, moon_angular_radius);
+}
+
+template <bool MS, bool TEXLUT = false, bool EXTRA = false>
 SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture,
                                        const LutView& multiscattering_texture, float start_i, float3 earth_center,
                                        float3 start_position, float3 view_direction, float3 sun_direction,
-                                       float marching_distance, float steps, float3& transmittance, float3& L_f) {
+                                       float marching_distance, float steps, float3& transmittance, float3& L_f,
+                                       const ScatterExtras* extras = nullptr) {
     const SkyAtmosphereBufferData& u = atm.u;
     float r = length(start_position - earth_center);
     float3 up_direction = normalize(start_position - earth_center);
@@ -97,6 +160,7 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
         float mu_s_i = dot(sun_direction, up_direction_i);
         float3 luminance_i = scattering_with_phase_i * atm.template GetSunVisibility<TEXLUT>(transmittance_texture, r_i, mu_s_i);
         if (!MS) {
+            if (EXTRA && extras->shadow_size > 0) luminance_i *= GetVisibilityFromShadowMap(*extras, position_i);  // :274-277
             // GetMultiscatteringContribution, :169-178
             float x_mu_s = mu_s_i * 0.5f + 0.5f;
             float x_r = (r_i - u.bottom_radius) / (u.top_radius - u.bottom_radius);
@@ -104,6 +168,8 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
             float vv = 0.5f / float(multiscattering_texture.h) + x_r * (1.0f - 1.0f / float(multiscattering_texture.h));
             float3 multiscattering_contribution = xyz(sample_lut2d_sel<TEXLUT>(multiscattering_texture, uu, vv));
             luminance_i += u.multiscattering_mask * multiscattering_contribution * scattering_i;
+            if (EXTRA && extras->moon_shadow)  // :281-284
+                luminance_i *= GetVisibilityFromMoonShadow(f3(extras->moon_position) - position_i, extras->moon_radius, sun_direction, u.sun_angular_radius);
             luminance_i *= f3(u.solar_illuminance);
         }
         luminance += transmittance * (luminance_i - luminance_i * transmittance_i) / extinction_i;
@@ -218,6 +284,7 @@ struct RenderParams {
     SkyLutConfig cfg;
     LutView transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
     FroxelView froxel;  // p == nullptr: no cloud shadow froxel yet (visibility 1)
+    ScatterExtras extras;
     const uint16_t* blue_noise;
     float4 *sky_lum_out, *sky_trans_out, *ap_lum_out, *ap_trans_out;
     half4* env_out;
@@ -287,6 +354,7 @@ SKY_D float DitherStart(const RenderParams& P, int enable, int x, int y) {
 }
 
 // K3 -- AtmosphereRenderer.glsl:153-186 (+ :81-111)
+template <bool EXTRA>
 __global__ void __launch_bounds__(64) k3_sky_view(const __grid_constant__ RenderParams P) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     const int W = P.cfg.sky_view_width, H = P.cfg.sky_view_height;
@@ -320,15 +388,16 @@ __global__ void __launch_bounds__(64) k3_sky_view(const __grid_constant__ Render
     float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
     if (marching_distance > 0) {
         float start_i = DitherStart(P, P.cfg.sky_view_dither, x, y);
-        luminance = ComputeScatteredLuminance<false>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
-                                                     view_direction, f3(P.r.sun_direction), marching_distance, P.r.sky_view_lut_steps,
-                                                     transmittance, unused);
+        luminance = ComputeScatteredLuminance<false, false, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                                   view_direction, f3(P.r.sun_direction), marching_distance, P.r.sky_view_lut_steps,
+                                                                   transmittance, unused, &P.extras);
     }
     P.sky_lum_out[y * W + x] = f4(luminance, 0.0f);
     P.sky_trans_out[y * W + x] = f4(transmittance, 0.0f);
 }
 
 // K4 -- AtmosphereRenderer.glsl:191-243
+template <bool EXTRA>
 __global__ void __launch_bounds__(64) k4_aerial_perspective(const __grid_constant__ RenderParams P) {
     const int W = P.ap_lum.w, H = P.ap_lum.h, D = P.ap_lum.d;
     int x = threadIdx.x % W, y = blockIdx.x * (blockDim.x / W) + threadIdx.x / W, z = blockIdx.y;
@@ -347,9 +416,9 @@ __global__ void __launch_bounds__(64) k4_aerial_perspective(const __grid_constan
     float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
     if (marching_distance > 0) {
         float start_i = DitherStart(P, P.cfg.aerial_perspective_dither, x, y);
-        luminance = ComputeScatteredLuminance<false>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
-                                                     view_direction, f3(P.r.sun_direction), marching_distance,
-                                                     P.r.aerial_perspective_lut_steps, transmittance, unused);
+        luminance = ComputeScatteredLuminance<false, false, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                                   view_direction, f3(P.r.sun_direction), marching_distance,
+                                                                   P.r.aerial_perspective_lut_steps, transmittance, unused, &P.extras);
     }
     size_t o = (size_t(z) * H + y) * W + x;
     P.ap_lum_out[o] = f4(luminance, 0.0f);
@@ -399,6 +468,7 @@ __global__ void __launch_bounds__(128) k5_environment(const __grid_constant__ Re
 // in-scatter only and alpha = 0 (ComputeObjectLuminance needs the G-buffer + IBL chain);
 // the star-map term of sky pixels (:427-429) is in the same "next" row.
 // HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
+template <bool EXTRA>
 __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
     if (px >= P.width) return;
@@ -432,8 +502,9 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
             transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
         } else {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
-            luminance = ComputeScatteredLuminance<false, kCompositeTexLut>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
-                                                               view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused);
+            luminance = ComputeScatteredLuminance<false, kCompositeTexLut, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
+                                                                                  view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused,
+                                                                                  &P.extras);
         }
     }
     if (P.froxel.p) luminance *= SampleRayScatterVisibility(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);
@@ -470,6 +541,12 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.sky_lum_out = ctx->sky_lum.p; P.sky_trans_out = ctx->sky_trans.p;
     P.ap_lum_out = ctx->ap_lum.p; P.ap_trans_out = ctx->ap_trans.p;
     P.env_out = ctx->env.p;
+    P.extras.moon_shadow = P.cfg.moon_shadow;
+    P.extras.moon_radius = P.r.moon_radius;
+    for (int i = 0; i < 3; ++i) P.extras.moon_position[i] = P.r.moon_position[i];
+    P.extras.shadow_size = P.cfg.volumetric_light ? ctx->mesh_shadow_map.w : 0;
+    P.extras.shadow_map = ctx->mesh_shadow_map.p;
+    for (int i = 0; i < 16; ++i) P.extras.light_view_projection[i] = P.r.light_view_projection[i];
     return P;
 }
 
@@ -495,10 +572,19 @@ int launch_atmosphere_bake(SkyContext* ctx) {
 
 int launch_atmosphere_luts(SkyContext* ctx) {
     RenderParams P = make_render_params(ctx);
-    k3_sky_view<<<dim3(ceil_div(P.cfg.sky_view_width, 64), P.cfg.sky_view_height), 64, 0, ctx->stream>>>(P);
+    if (P.cfg.volumetric_light) {
+        if (int e = ensure_mesh_shadow_map(ctx)) return e;
+        P = make_render_params(ctx);
+    }
+    const bool extra = P.cfg.moon_shadow || P.cfg.volumetric_light;
+    const dim3 g3(ceil_div(P.cfg.sky_view_width, 64), P.cfg.sky_view_height);
+    if (extra) k3_sky_view<true><<<g3, 64, 0, ctx->stream>>>(P);
+    else k3_sky_view<false><<<g3, 64, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     // 64 threads = two rows of the 32-wide froxel slice
-    k4_aerial_perspective<<<dim3(ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), P.ap_lum.d), 64, 0, ctx->stream>>>(P);
+    const dim3 g4(ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), P.ap_lum.d);
+    if (extra) k4_aerial_perspective<true><<<g4, 64, 0, ctx->stream>>>(P);
+    else k4_aerial_perspective<false><<<g4, 64, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     k5_environment<<<dim3(ceil_div(P.cfg.environment_size, 128), P.cfg.environment_size, 6), 128, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
@@ -510,9 +596,11 @@ int launch_atmosphere_luts(SkyContext* ctx) {
 #define launch_composite launch_composite_strict
 #endif
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h) {
+    if (ctx->lut_cfg.volumetric_light) { if (int e = ensure_mesh_shadow_map(ctx)) return e; }
     RenderParams P = make_render_params(ctx);
     P.depth = depth; P.hdr = hdr; P.width = w; P.height = h;
-    k6_composite<<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
+    if (P.cfg.moon_shadow || P.cfg.volumetric_light) k6_composite<true><<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
+    else k6_composite<false><<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
 }

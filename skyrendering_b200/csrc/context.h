@@ -88,6 +88,7 @@ struct SkyContext {
     // shadow chain
     Lut<float2> shadow_maps[3];
     Lut<uint16_t> shadow_froxel;
+    Lut<float> mesh_shadow_map;  // SKY_RES_MESH_SHADOW_MAP: 2048^2 light-space depth, allocated on first use, cleared to 1
 
     // viewport
     int width = 0, height = 0;
@@ -151,6 +152,7 @@ int sky_alloc(SkyContext* ctx, Lut<T>& l, int w, int h, int d = 1, bool zero = t
 }
 
 // per-subsystem launchers (defined in the .cu files) -----------------------------------------------------------
+int ensure_mesh_shadow_map(SkyContext* ctx);                                   // api.cu
 int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
 int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6

@@ -460,8 +460,8 @@ void Scene::LutConfig(SkyLutConfig& c) const {
     c.sky_view_dither = p.sky_view_lut_dither_sample_point_enable;
     c.aerial_perspective_dither = p.aerial_perspective_lut_dither_sample_point_enable;
     c.raymarching_dither = p.raymarching_dither_sample_point_enable;
-    if (p.volumetric_light_enable || p.moon_shadow_enable)
-        throw std::runtime_error("volumetric_light_enable / moon_shadow_enable permutations are outside the hot path (off in all shipped scenes)");
+    c.moon_shadow = p.moon_shadow_enable;            // MOON_SHADOW_ENABLE, AtmosphereRenderer.cpp:101
+    c.volumetric_light = p.volumetric_light_enable;  // VOLUMETRIC_LIGHT_ENABLE, :100 (reads SKY_RES_MESH_SHADOW_MAP)
 }
 
 // AtmosphereRenderer.cpp:52-83 and :168-174
@@ -475,7 +475,17 @@ void Scene::AtmosphereRenderBuffer(SkyAtmosphereRenderBufferData& d) {
     vec3 camera_position = camera_.position_;  // AppWindow.cpp:208
     put(d.camera_position, camera_position);
     inverse(camera_.ViewProjection()).store(d.inv_view_projection);
-    mat4().store(d.light_view_projection);  // mesh shadow map: outside the hot path
+    // AppWindow::Render (AppWindow.cpp:148-157) + ComputeLightMatrix (src/Base/src/ShadowMap.cpp:53-66): the ortho frustum of
+    // the mesh shadow map, an 8 km square around the origin seen from 5 km along the sun direction, 0..50 km deep
+    {
+        vec3 light_direction = sun_direction;
+        vec3 position = light_direction * 5.0f;
+        vec3 right_direction = normalize(cross(light_direction, vec3(0, 1, 0)));
+        vec3 up_direction = light_direction.y == 1.0f ? vec3(1, 0, 0) : normalize(cross(right_direction, light_direction));
+        mat4 view_matrix = lookAt(position, position - light_direction, up_direction);
+        mat4 projection_matrix = ortho(-4.0f, 4.0f, -4.0f, 4.0f, 0.0f, 5e1f);
+        (projection_matrix * view_matrix).store(d.light_view_projection);
+    }
     d.raymarching_steps = p.raymarching_steps;
     d.sky_view_lut_steps = p.sky_view_lut_steps;
     d.aerial_perspective_lut_steps = p.aerial_perspective_lut_steps;

@@ -33,7 +33,7 @@ NOISES = (("cloud_map", abi.NOISE_CLOUD_MAP, abi.RES_CLOUD_MAP, (512, 512, 2)), 
 
 class RefLutIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("transmittance", "multiscattering", "blue_noise", "sky_luminance", "sky_transmittance",
-                                          "ap_luminance", "ap_transmittance", "environment")]
+                                          "ap_luminance", "ap_transmittance", "environment", "mesh_shadow_map")] + [("mesh_shadow_size", C.c_int)]
 
 
 def reference_present():
@@ -50,8 +50,9 @@ def ref_library():
     return C.CDLL(REF_LIB)
 
 
-def ref_luts(ref, renderer):
-    """K1-K5 of the reference shader text for the uniforms of `renderer` (an oracle- or CUDA-backed Renderer after prime())."""
+def ref_luts(ref, renderer, mesh_shadow_map=None):
+    """K1-K5 of the reference shader text for the uniforms of `renderer` (an oracle- or CUDA-backed Renderer after prime()).
+    `mesh_shadow_map`: float32 [S][S] light-space depth for the VOLUMETRIC_LIGHT_ENABLE permutation."""
     a, rb, cfg = renderer.atmosphere, renderer.render_buffer, renderer.lut_config
     out = {"transmittance": np.zeros((64, 256, 4), np.float32), "multiscattering": np.zeros((32, 32, 4), np.float32)}
     ref.ref_transmittance(C.byref(a), out["transmittance"].ctypes.data_as(C.c_void_p), 256, 64)
@@ -62,9 +63,14 @@ def ref_luts(ref, renderer):
     out["aerial_luminance"] = np.zeros((d, 32, 32, 4), np.float32)
     out["aerial_transmittance"] = np.zeros_like(out["aerial_luminance"])
     out["environment"] = np.zeros((6, e, e, 4), np.float32)
+    shadow_rgba = None
+    if mesh_shadow_map is not None:
+        shadow_rgba = np.zeros(mesh_shadow_map.shape + (4,), np.float32)
+        shadow_rgba[..., 0] = mesh_shadow_map
     io = RefLutIO(out["transmittance"].ctypes.data, out["multiscattering"].ctypes.data, None, out["sky_view_luminance"].ctypes.data,
                   out["sky_view_transmittance"].ctypes.data, out["aerial_luminance"].ctypes.data, out["aerial_transmittance"].ctypes.data,
-                  out["environment"].ctypes.data)
+                  out["environment"].ctypes.data, None if shadow_rgba is None else shadow_rgba.ctypes.data,
+                  0 if shadow_rgba is None else shadow_rgba.shape[0])
     rc = ref.ref_atmosphere_luts(C.byref(a), C.byref(rb), C.byref(cfg), C.byref(io))
     assert rc == 0
     return {k: v[..., :3].copy() for k, v in out.items()}

@@ -78,6 +78,35 @@ def test_cuda_matches_reference_shader_digests(libs, scene):
                 assert refpin.digest(r.ctx.read(res)) == gold["noise"][scene][name]["sha256"], (scene, name)
 
 
+@pytest.mark.parametrize("moon,volumetric", [(True, False), (False, True), (True, True)])
+def test_optional_march_terms(libs, moon, volumetric):
+    """MOON_SHADOW_ENABLE / VOLUMETRIC_LIGHT_ENABLE: the K3 / K4 / K5 LUTs stay bit-exact against the oracle
+    (which is bit-identical to the reference's shader text for these permutations, tests/test_permutations_cpu.py); the K6
+    per-pixel raymarch, which carries the same terms, stays inside the frame tolerance and is near bit-level when strict."""
+    from tests import permutations
+    cuda, orc = libs
+    shadow = permutations.mesh_shadow_map() if volumetric else None
+    w, h = 384, 216
+    hdrs = {}
+    for key, lib, dev, strict in (("cuda", cuda, "cuda", False), ("strict", cuda, "cuda", True), ("oracle", orc, "cpu", False)):
+        r = Renderer(permutations.scene(moon, volumetric, raymarch=True), w, h, library=lib)
+        r.ctx.set_strict_arithmetic(strict)
+        if shadow is not None:
+            r.ctx.write(abi.RES_MESH_SHADOW_MAP, shadow)
+        r.prime()
+        if key != "strict":
+            hdrs[key + "_luts"] = {name: r.ctx.read(res) for name, res in (("sky", abi.RES_SKY_VIEW_LUMINANCE), ("ap", abi.RES_AERIAL_LUMINANCE),
+                                                                          ("apt", abi.RES_AERIAL_TRANSMITTANCE), ("env", abi.RES_ENVIRONMENT))}
+        depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), dev)
+        r.ctx.composite(depth, hdr, w, h)
+        r.ctx.sync()
+        hdrs[key] = to_numpy(hdr).astype(np.float32)
+    for name in ("sky", "ap", "apt", "env"):
+        assert np.array_equal(hdrs["cuda_luts"][name], hdrs["oracle_luts"][name]), name
+    assert rel_rms(hdrs["cuda"][..., :3], hdrs["oracle"][..., :3]) < 1e-2
+    assert rel_rms(hdrs["strict"][..., :3], hdrs["oracle"][..., :3]) < 1e-4
+
+
 def test_sky_view_192x108_variant(libs):
     """BASELINE names a 192x108 sky-view LUT; the reference hard-codes 128x128.  The size is a parameter."""
     cuda, orc = libs
