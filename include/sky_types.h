@@ -206,6 +206,14 @@ typedef struct SkyLutConfig {
     int32_t _pad[1];
 } SkyLutConfig;
 
+/* HDRBufferParams subset used by the tone-map pass (src/Base/include/HDRBuffer.h:11-22), see sky_tonemap */
+typedef struct SkyToneMapParams {
+    int32_t tone_mapping;  /* 0 = CEToneMapping, 1 = ACESToneMapping (default of the reference) */
+    float exposure;        /* reference default 10 */
+    int32_t dither;        /* dither_color_enable */
+    int32_t _pad;
+} SkyToneMapParams;
+
 /* VolumetricCloud::PathTracing::InitParam (VolumetricCloud.h:158-168) plus the compile-time
  * constants its constructor bakes into the shader text (VolumetricCloud.cpp:505-519). */
 enum SkyPrng { SKY_PRNG_WANG = 0, SKY_PRNG_PCG = 1 };

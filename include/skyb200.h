@@ -122,6 +122,12 @@ int SKY_FN(pt_samples)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
  * avg = accum / frame_count. */
 int SKY_FN(pt_resolve)(SkyContext* ctx, uint32_t frame_count, void* hdr_dev);
 
+/* HDRBuffer::DoPostProcessAndBindSdrFramebuffer's last pass (src/Base/src/HDRBuffer.cpp:96-100, shaders/Base/BloomPass2.frag:15-42)
+ * without the bloom term (bloom_intensity 0: BloomPass1 + the blur pyramid are display sugar outside the path):
+ * ToneMapping(luminance, exposure) (CE or ACES, HDRBuffer.h:11-22) -> pow(1 / 2.2) [-> + blue noise / 255 when dither != 0]
+ * -> RGBA8 (round to nearest even, alpha 255).  hdr_dev half4[H][W] in, rgba8_dev uchar4[H][W] out. */
+int SKY_FN(tonemap)(SkyContext* ctx, const void* hdr_dev, int width, int height, const SkyToneMapParams* params, void* rgba8_dev);
+
 /* pt_samples + host read-back of the accumulation buffer (float4[H][W]). */
 int SKY_FN(pt_samples_host)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
                             uint32_t frame_begin, uint32_t count, const int32_t region[4],

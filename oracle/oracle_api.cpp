@@ -205,6 +205,32 @@ int orc_pt_resolve(SkyContext* ctx, uint32_t frame_count, void* hdr) {
     return 0;
 }
 
+// shaders/Base/BloomPass2.frag:15-42 without the bloom term (see skyb200.h)
+int orc_tonemap(SkyContext* ctx, const void* hdr, int width, int height, const SkyToneMapParams* p, void* rgba8) {
+    if (p->tone_mapping != 0 && p->tone_mapping != 1) return fail(ctx, "tonemap: unknown tone mapping operator");
+    const uint16_t* in = static_cast<const uint16_t*>(hdr);
+    uint8_t* out = static_cast<uint8_t*>(rgba8);
+    auto tone = [&](float luminance) {
+        if (p->tone_mapping == 0) return 1 - std::exp(-p->exposure * luminance);
+        const float k = 10.0f / 16.0f;
+        const float A = 2.51f * k * k, B = 0.03f * k, C = 2.43f * k * k, D = 0.59f * k, E = 0.14f;
+        luminance *= p->exposure;
+        return (luminance * (A * luminance + B)) / (luminance * (C * luminance + D) + E);
+    };
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            size_t pix = size_t(y) * width + x;
+            for (int k = 0; k < 3; ++k) {
+                float v = std::pow(tone(half_bits_to_float(in[pix * 4 + k])), 1.0f / 2.2f);
+                if (p->dither) v += ctx->scene.blue_noise.data[size_t(y & 63) * 64 + (x & 63)] / 255.0f;
+                v = std::fmin(std::fmax(v, 0.0f), 1.0f);
+                out[pix * 4 + k] = uint8_t(std::nearbyintf(v * 255.0f));
+            }
+            out[pix * 4 + 3] = 255;
+        }
+    return 0;
+}
+
 int orc_pt_samples_host(SkyContext* ctx, const SkyCloudCommonBufferData* common, uint32_t frame_begin, uint32_t count,
                         const int32_t region[4], float* accum_host) {
     if (int e = orc_pt_samples(ctx, common, frame_begin, count, region)) return e;

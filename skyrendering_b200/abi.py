@@ -126,6 +126,10 @@ class LutConfig(_Pod):
                 ("volumetric_light", I), ("_pad", I * 1)]
 
 
+class ToneMapParams(_Pod):
+    _fields_ = [("tone_mapping", I), ("exposure", F), ("dither", I), ("_pad", I)]
+
+
 class PathTracingInit(_Pod):
     _fields_ = [("sqrt_tile_count", I), ("max_bounces", I), ("region_box_half_width", F), ("importance_sampling", I),
                 ("forward_phase_g", F), ("back_phase_g", F), ("forward_scattering_ratio", F), ("prng", I),
@@ -179,6 +183,7 @@ KERNEL_API = {
     "pt_begin": ([P(PathTracingInit)], I),
     "pt_samples": ([P(CloudCommonBufferData), U, U, P(I * 4)], I),
     "pt_resolve": ([U, _VOIDP], I),
+    "tonemap": ([_VOIDP, I, I, C.POINTER(ToneMapParams), _VOIDP], I),
     "pt_samples_host": ([P(CloudCommonBufferData), U, U, P(I * 4), _VOIDP], I),
     "get_resource": ([I, P(ResourceDesc)], I),
     "read_resource": ([I, _VOIDP, C.c_uint64], I),
@@ -326,6 +331,11 @@ class Context:
         self._call("pt_samples_host", C.byref(common), frame_begin, count, C.byref((I * 4)(*region)), _ptr(accum_host))
 
     def pt_resolve(self, frame_count, hdr): self._call("pt_resolve", frame_count, _ptr(hdr))
+    def tonemap(self, hdr, width, height, out, tone_mapping=1, exposure=10.0, dither=False):
+        """BloomPass2.frag's tone map + gamma into an RGBA8 image (`out`: uint8 [H][W][4] in the library's memory space)."""
+        p = ToneMapParams(int(tone_mapping), float(exposure), int(dither), 0)
+        self._call("tonemap", _ptr(hdr), width, height, C.byref(p), _ptr(out))
+
     def counters_enable(self, on): self._call("counters_enable", int(on))
     def set_hw_filtering(self, on): self._call("set_hw_filtering", int(on))
     def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))

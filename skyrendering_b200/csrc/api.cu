@@ -534,6 +534,12 @@ int sky_counters_enable(SkyContext* ctx, int enable) {
     return 0;
 }
 
+int sky_tonemap(SkyContext* ctx, const void* hdr_dev, int width, int height, const SkyToneMapParams* params, void* rgba8_dev) {
+    if (!ctx || !hdr_dev || !params || !rgba8_dev || width <= 0 || height <= 0) return ctx ? sky_fail(ctx, "tonemap: bad arguments") : 1;
+    if (int e = lanes_join(ctx)) return e;
+    return (ctx->strict_arithmetic ? launch_tonemap_strict : launch_tonemap)(ctx, static_cast<const half4*>(hdr_dev), width, height, *params, rgba8_dev);
+}
+
 int sky_set_strict_arithmetic(SkyContext* ctx, int enable) {
     if (!ctx) return 1;
     ctx->strict_arithmetic = enable != 0;

@@ -594,7 +594,48 @@ int launch_atmosphere_luts(SkyContext* ctx) {
 #else   // SKY_COMPOSITE_TU
 #ifdef SKY_STRICT_TU
 #define launch_composite launch_composite_strict
+#define launch_tonemap launch_tonemap_strict
 #endif
+namespace {
+// shaders/Base/BloomPass2.frag:15-42 without the bloom term
+struct ToneMapKernelParams {
+    SkyToneMapParams p;
+    const half4* hdr;
+    uchar4* out;
+    const uint16_t* blue_noise;
+    int width, height;
+};
+SKY_D float ToneMapping(float luminance, float exposure, int mode) {
+    if (mode == 0) return 1 - expf(-exposure * luminance);
+    const float k = 10.0f / 16.0f;
+    const float A = 2.51f * k * k, B = 0.03f * k, C = 2.43f * k * k, D = 0.59f * k, E = 0.14f;
+    luminance *= exposure;
+    return (luminance * (A * luminance + B)) / (luminance * (C * luminance + D) + E);
+}
+__global__ void __launch_bounds__(256) k21_tonemap(const __grid_constant__ ToneMapKernelParams P) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= P.width) return;
+    float4 c = load_half4(P.hdr + size_t(y) * P.width + x);
+    float rgb[3] = {c.x, c.y, c.z};
+    unsigned char o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = powf(ToneMapping(rgb[k], P.p.exposure, P.p.tone_mapping), 1.0f / 2.2f);
+        if (P.p.dither) v += (float(__ldg(P.blue_noise + (y & 63) * 64 + (x & 63))) / 65535.0f) / 255.0f;
+        v = fminf(fmaxf(v, 0.0f), 1.0f);   // the SDR framebuffer clamps (NaN -> 0, fmaxf)
+        o[k] = (unsigned char)__float2int_rn(v * 255.0f);
+    }
+    P.out[size_t(y) * P.width + x] = make_uchar4(o[0], o[1], o[2], 255);
+}
+}  // namespace
+int launch_tonemap(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out) {
+    if (p.tone_mapping != 0 && p.tone_mapping != 1) return sky_fail(ctx, "tonemap: unknown tone mapping operator");
+    ToneMapKernelParams P{p, hdr, static_cast<uchar4*>(out), ctx->blue_noise, w, h};
+    k21_tonemap<<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h) {
     if (ctx->lut_cfg.volumetric_light) { if (int e = ensure_mesh_shadow_map(ctx)) return e; }
     RenderParams P = make_render_params(ctx);

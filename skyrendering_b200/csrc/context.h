@@ -156,6 +156,7 @@ int ensure_mesh_shadow_map(SkyContext* ctx);                                   /
 int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
 int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6
+int launch_tonemap(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out);  // atmosphere.cu K21
 int launch_noise(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info);   // noise.cu       K8-K10
 int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, int channels, bool border);
 int launch_mip_chain(SkyContext* ctx, MipTextureDev& t);                       // noise.cu       glGenerateTextureMipmap
@@ -170,6 +171,7 @@ int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second);    /
 // the same entry points of the strict objects (cloud_strict.o, pathtrace_strict.o, composite_strict.o)
 #ifndef SKY_STRICT_TU  // (inside those objects the plain names above ARE these, by macro)
 int launch_composite_strict(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);
+int launch_tonemap_strict(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out);
 int launch_cloud_shadow_strict(SkyContext* ctx, const SkyCloudCommonBufferData& c);
 int launch_cloud_begin_strict(SkyContext* ctx, const SkyCloudCommonBufferData& c, const SkyCloudBufferData& b, const float* depth,
                               int band_rows, int band_index, int band_count);

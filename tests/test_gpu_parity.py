@@ -453,6 +453,25 @@ def test_path_tracer_statistical_self_consistency(libs):
 
 
 # ---------------------------------------------------------------------------------------------- errors
+def test_tonemap_parity(libs):
+    """K21 (BloomPass2.frag tone map + gamma) on a rendered HDR frame: CUDA == oracle to one RGBA8 code, both operators, dither."""
+    import torch
+    cuda, orc = libs
+    w, h = 384, 216
+    o = run_cloud_frames("c3", w, h, orc, frames=2, device="cpu")
+    hdr_np = o["hdr"].astype(np.float16)
+    rc, ro = o["renderer"], Renderer("c3", w, h, library=cuda)
+    for mode, dither in ((1, False), (0, False), (1, True)):
+        out_o = np.zeros((h, w, 4), np.uint8)
+        rc.ctx.tonemap(hdr_np, w, h, out_o, tone_mapping=mode, exposure=10.0, dither=dither)
+        out_g = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        ro.ctx.tonemap(torch.from_numpy(hdr_np).cuda(), w, h, out_g, tone_mapping=mode, exposure=10.0, dither=dither)
+        ro.ctx.sync()
+        d = np.abs(out_g.cpu().numpy().astype(np.int32) - out_o.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02
+        assert 20 < out_o[..., :3].mean() < 235   # a real image, not black / white
+
+
 def test_error_behaviour(libs):
     cuda, _ = libs
     ctx = abi.Context(cuda)

@@ -276,3 +276,27 @@ def test_temporal_reconstruction_converges():
     early = np.abs(outs[1] - outs[0]).mean()
     late = np.abs(outs[3] - outs[2]).mean()
     assert late <= early + 1e-6
+
+
+def test_tonemap_known_answers():
+    """BloomPass2.frag:15-42 without bloom: ACES / CE curve, gamma 1/2.2, RGBA8 (HDRBuffer.h defaults: ACES, exposure 10)."""
+    from skyrendering_b200 import abi
+    orc = oracle_library()
+    ctx = abi.Context(orc, 0, 0)
+    lum = np.array([0.0, 0.01, 0.05, 0.18, 1.0, 100.0], np.float32)
+    hdr = np.zeros((1, lum.size, 4), np.float16)
+    hdr[0, :, :3] = lum[:, None]
+    out = np.zeros((1, lum.size, 4), np.uint8)
+    for mode in (0, 1):
+        ctx.tonemap(hdr, lum.size, 1, out, tone_mapping=mode, exposure=10.0)
+        x = hdr[0, :, 0].astype(np.float64) * 10.0
+        if mode == 0:
+            tone = 1.0 - np.exp(-x)
+        else:
+            k = 10.0 / 16.0
+            A, B, Cc, D, E = 2.51 * k * k, 0.03 * k, 2.43 * k * k, 0.59 * k, 0.14
+            tone = (x * (A * x + B)) / (x * (Cc * x + D) + E)
+        want = np.rint(np.clip(tone ** (1 / 2.2), 0, 1) * 255.0)
+        assert np.all(np.abs(out[0, :, 0].astype(np.float64) - want) <= 1), (mode, out[0, :, 0], want)
+        assert np.all(out[..., 3] == 255) and out[0, 0, 0] == 0 and out[0, -1, 0] == 255
+        assert np.array_equal(out[..., 0], out[..., 1]) and np.array_equal(out[..., 0], out[..., 2])
