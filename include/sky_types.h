@@ -206,6 +206,12 @@ typedef struct SkyLutConfig {
     int32_t _pad[1];
 } SkyLutConfig;
 
+/* Collision sampling of the path tracer (sky_pt_set_tracking) */
+enum SkyPtTracking {
+    SKY_PT_TRACKING_REFERENCE = 0,     /* the reference's global majorant kSigmaTMax: identical random streams (default) */
+    SKY_PT_TRACKING_MAJORANT_GRID = 1  /* local majorants on a macro-cell grid: same expectation, different streams */
+};
+
 /* HDRBufferParams subset used by the tone-map pass (src/Base/include/HDRBuffer.h:11-22), see sky_tonemap */
 typedef struct SkyToneMapParams {
     int32_t tone_mapping;  /* 0 = CEToneMapping, 1 = ACESToneMapping (default of the reference) */

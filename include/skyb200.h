@@ -118,6 +118,13 @@ int SKY_FN(pt_begin)(SkyContext* ctx, const SkyPathTracingInit* init);
 int SKY_FN(pt_samples)(SkyContext* ctx, const SkyCloudCommonBufferData* common,
                        uint32_t frame_begin, uint32_t count, const int32_t region[4]);
 
+/* Collision sampling of K19.  SKY_PT_TRACKING_REFERENCE (default) is the reference's algorithm with the reference's random
+ * streams (VolumetricCloudPathTracing.comp:135-196: one global majorant kSigmaTMax inside the +-region box).
+ * SKY_PT_TRACKING_MAJORANT_GRID keeps the estimator (delta tracking + ratio tracking + NEE) but samples collisions against
+ * local majorants stored per 8^3-texel macro cell of the voxel texture and skips empty cells: the image has the same
+ * expectation, not the same samples -- a fast mode that is validated statistically and reported separately.  Voxel material only. */
+int SKY_FN(pt_set_tracking)(SkyContext* ctx, int mode);
+
 /* PathTracing::Render display pass (VolumetricCloud.cpp:562-565, K20): hdr = hdr*avg.a + avg.rgb,
  * avg = accum / frame_count. */
 int SKY_FN(pt_resolve)(SkyContext* ctx, uint32_t frame_count, void* hdr_dev);

@@ -126,6 +126,9 @@ class LutConfig(_Pod):
                 ("volumetric_light", I), ("_pad", I * 1)]
 
 
+PT_TRACKING_REFERENCE, PT_TRACKING_MAJORANT_GRID = 0, 1
+
+
 class ToneMapParams(_Pod):
     _fields_ = [("tone_mapping", I), ("exposure", F), ("dither", I), ("_pad", I)]
 
@@ -183,6 +186,7 @@ KERNEL_API = {
     "pt_begin": ([P(PathTracingInit)], I),
     "pt_samples": ([P(CloudCommonBufferData), U, U, P(I * 4)], I),
     "pt_resolve": ([U, _VOIDP], I),
+    "pt_set_tracking": ([I], I),
     "tonemap": ([_VOIDP, I, I, C.POINTER(ToneMapParams), _VOIDP], I),
     "pt_samples_host": ([P(CloudCommonBufferData), U, U, P(I * 4), _VOIDP], I),
     "get_resource": ([I, P(ResourceDesc)], I),
@@ -331,6 +335,8 @@ class Context:
         self._call("pt_samples_host", C.byref(common), frame_begin, count, C.byref((I * 4)(*region)), _ptr(accum_host))
 
     def pt_resolve(self, frame_count, hdr): self._call("pt_resolve", frame_count, _ptr(hdr))
+    def pt_set_tracking(self, mode): self._call("pt_set_tracking", int(mode))
+
     def tonemap(self, hdr, width, height, out, tone_mapping=1, exposure=10.0, dither=False):
         """BloomPass2.frag's tone map + gamma into an RGBA8 image (`out`: uint8 [H][W][4] in the library's memory space)."""
         p = ToneMapParams(int(tone_mapping), float(exposure), int(dither), 0)

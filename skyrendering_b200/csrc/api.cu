@@ -305,6 +305,7 @@ int sky_voxel_upload(SkyContext* ctx, const uint8_t* host_voxels, int dx, int dy
     if (dx < 1 || dy < 1 || dz < 1 || dx > 4096 || dy > 4096 || dz > 4096) return sky_fail(ctx, "voxel grid dimensions out of range");
     if (int e = lanes_join(ctx)) return e;
     ctx->voxel.valid = false;
+    ctx->voxel_majorant_valid = false;
     if (int e = build_mip_texture(ctx, ctx->voxel, dx, dy, dz, 1, true)) return e;
     SKY_CUDA(ctx, cudaMemcpyAsync(ctx->voxel.data, host_voxels, size_t(dx) * dy * dz, cudaMemcpyHostToDevice, ctx->stream));
     if (int e = launch_mip_chain(ctx, ctx->voxel)) return e;
@@ -531,6 +532,13 @@ int sky_counters_enable(SkyContext* ctx, int enable) {
     if (int e = lanes_join(ctx)) return e;
     ctx->counting = enable != 0;
     SKY_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+int sky_pt_set_tracking(SkyContext* ctx, int mode) {
+    if (!ctx) return 1;
+    if (mode != SKY_PT_TRACKING_REFERENCE && mode != SKY_PT_TRACKING_MAJORANT_GRID) return sky_fail(ctx, "pt_set_tracking: unknown mode");
+    ctx->pt_tracking = mode;
     return 0;
 }
 

@@ -108,6 +108,10 @@ struct SkyContext {
     void* pt_samples = nullptr;           // per-job sample slots of K19, float4[frames][region pixels]
     size_t pt_samples_bytes = 0;
     unsigned int* pt_job_counter = nullptr;
+    int pt_tracking = 0;                   // SkyPtTracking (sky_pt_set_tracking)
+    uint8_t* voxel_majorant = nullptr;     // majorant-grid mode: max density code per 8^3-texel macro cell of the voxel texture
+    size_t voxel_majorant_cells = 0;
+    bool voxel_majorant_valid = false;
 
     unsigned long long* counters = nullptr;  // SkyCounter slots
 

@@ -433,6 +433,13 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                     }
                 }
                 if (state == ST_TRACK) { t = tk[kBatch - 1]; seed = s; }
+#ifndef SKY_K19_NO_ZERO_CUT
+                // Zero-transmittance cut (exact): once the running product of a shadow ray is exactly 0 -- a texel at the
+                // majorant, or the underflow of ~10^2 collisions deep inside the cloud -- every further factor multiplies
+                // zero and the stream the ray consumes is a copy (:135), so the ray may end here.  (The counting variant
+                // walks the whole chain: its totals are the reference algorithm's.)
+                if (!COUNT && state == ST_TRACK && in_shadow && transmittance == 0.0f) state = ST_SHADOW_END;
+#endif
             }
         }
 
@@ -581,6 +588,251 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ majorant-grid mode
+// the same estimator (delta tracking for the free flight, ratio tracking for the sun transmittance, NEE at
+// every vertex, VolumetricCloudPathTracing.comp:135-249) with LOCAL majorants instead of the reference's single global
+// kSigmaTMax over the +-100 km box: a coarse grid over the voxel texture holds, per 8^3-texel macro cell, the largest
+// density any lookup inside the cell can return (level 0 with its bilinear apron and every mip level the LOD rule may pick),
+// and tracking walks that grid with a DDA, restarting the exponential at each cell boundary (memorylessness keeps it
+// unbiased).  Cells with majorant 0 -- 3/4 of the data set, and all of space outside the footprint -- are crossed without a
+// lookup.  The image has the same expectation but NOT the reference's random streams: it is validated statistically against
+// the stream-exact kernel (tests) and reported separately (bench.py: "majorant_grid").
+constexpr int kMacro = 8;
+
+__global__ void __launch_bounds__(128) k_majorant_build(const MipView vox, uint8_t* __restrict__ out, int gw, int gh, int gd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= gw * gh * gd) return;
+    const int cx = c % gw, cy = (c / gw) % gh, cz = c / (gw * gh);
+    const float W0 = float(vox.w[0]), H0 = float(vox.h[0]), D0 = float(vox.d[0]);
+    // normalised extent of the macro cell (the last one may be partial)
+    const float u0 = float(cx * kMacro) / W0, u1 = fminf(float(cx * kMacro + kMacro) / W0, 1.0f);
+    const float v0 = float(cy * kMacro) / H0, v1 = fminf(float(cy * kMacro + kMacro) / H0, 1.0f);
+    const float w0 = float(cz * kMacro) / D0, w1 = fminf(float(cz * kMacro + kMacro) / D0, 1.0f);
+    int m = 0;
+    for (int l = 0; l < vox.levels; ++l) {
+        const int wl = vox.w[l], hl = vox.h[l], dl = vox.d[l];
+        // texels a lookup with coordinates inside the cell can read at this level: LINEAR reaches half a texel beyond,
+        // NEAREST stays inside; one more texel on each side absorbs the fp32 rounding of u * size
+        const int i0 = max(int(floorf(u0 * float(wl) - 0.5f)) - 1, 0), i1 = min(int(floorf(u1 * float(wl) - 0.5f)) + 2, wl - 1);
+        const int j0 = max(int(floorf(v0 * float(hl) - 0.5f)) - 1, 0), j1 = min(int(floorf(v1 * float(hl) - 0.5f)) + 2, hl - 1);
+        const int k0 = max(int(floorf(w0 * float(dl) - 0.5f)) - 1, 0), k1 = min(int(floorf(w1 * float(dl) - 0.5f)) + 2, dl - 1);
+        const uint8_t* base = vox.base + vox.off[l];
+        for (int k = k0; k <= k1; ++k)
+            for (int j = j0; j <= j1; ++j)
+                for (int i = i0; i <= i1; ++i) m = max(m, int(base[(size_t(k) * hl + j) * wl + i]));
+    }
+    out[c] = uint8_t(m);
+}
+
+struct MajorantView {
+    const uint8_t* p;
+    int w, h, d;
+};
+
+// One tracking ray through the majorant grid over [t0, t1] (already inside the region box).  RATIO: ratio tracking, returns
+// the transmittance estimate in `transmittance`, never "hits"; otherwise delta tracking, returns true with the collision
+// distance in t_hit.
+template <bool RATIO, int PRNG_KIND>
+SKY_D bool TrackMajorantGrid(const PtParams& P, const MajorantView& G, float3 ro, float3 rd, float t0, float t1, float inv_thickness,
+                             uint32_t& seed, float& t_hit, float& transmittance, int& lookups) {
+    transmittance = 1.0f;
+    const SkyMaterialVoxelBufferData& vm = P.mat.m.u.voxel;
+    const float W0 = float(P.mat.voxel.w[0]), H0 = float(P.mat.voxel.h[0]), D0 = float(P.mat.voxel.d[0]);
+    // (u, v, w)(t) = a + b t; outside u, v in [-1/2W, 1 + 1/2W] every tap of every level is the border (sigma_t = 0)
+    const float au = ro.x * vm.uSampleFrequency[0] + vm.uSampleBias[0], bu = rd.x * vm.uSampleFrequency[0];
+    const float av = ro.y * vm.uSampleFrequency[1] + vm.uSampleBias[1], bv = rd.y * vm.uSampleFrequency[1];
+    const float aw = (ro.z - P.c.uBottomAltitude) * inv_thickness, bw = rd.z * inv_thickness;
+    {
+        const float hu = 0.75f / W0, hv = 0.75f / H0;
+        float iu = 1.0f / bu, iv = 1.0f / bv;
+        float ta = (-hu - au) * iu, tb = (1.0f + hu - au) * iu, tc = (-hv - av) * iv, td = (1.0f + hv - av) * iv;
+        if (!(fabsf(bu) > 1e-30f)) { bool in = au >= -hu && au <= 1.0f + hu; ta = in ? -INFINITY : INFINITY; tb = in ? INFINITY : -INFINITY; }
+        if (!(fabsf(bv) > 1e-30f)) { bool in = av >= -hv && av <= 1.0f + hv; tc = in ? -INFINITY : INFINITY; td = in ? INFINITY : -INFINITY; }
+        t0 = fmaxf(t0, fmaxf(fminf(ta, tb), fminf(tc, td)));
+        t1 = fminf(t1, fminf(fmaxf(ta, tb), fmaxf(tc, td)));
+    }
+    if (!(t0 < t1)) return false;
+    // macro-grid coordinates g(t) = g0 + gd t
+    const float sx = W0 / float(kMacro), sy = H0 / float(kMacro), sz = D0 / float(kMacro);
+    const float g0x = au * sx, g0y = av * sy, g0z = aw * sz, gdx = bu * sx, gdy = bv * sy, gdz = bw * sz;
+    const float igx = fabsf(gdx) > 1e-30f ? 1.0f / gdx : 0.0f, igy = fabsf(gdy) > 1e-30f ? 1.0f / gdy : 0.0f, igz = fabsf(gdz) > 1e-30f ? 1.0f / gdz : 0.0f;
+    const int stx = gdx > 0.0f ? 1 : -1, sty = gdy > 0.0f ? 1 : -1, stz = gdz > 0.0f ? 1 : -1;
+    float t = t0;
+    // the first cell is found from a point just inside the interval
+    const float te = fminf(t0 + 1e-5f * fmaxf(1.0f, fabsf(t0)), t1);
+    int cx = clampi(int(floorf(g0x + gdx * te)), 0, G.w - 1), cy = clampi(int(floorf(g0y + gdy * te)), 0, G.h - 1),
+        cz = clampi(int(floorf(g0z + gdz * te)), 0, G.d - 1);
+    const float density = vm.uDensity * (1.0f / 255.0f);
+    for (int guard = 0; guard < 4096; ++guard) {
+        // exit of this macro cell: the next grid plane on each axis, unless that plane is the outside of the grid (the apron
+        // beyond the last cell belongs to it; the ray then ends at t1)
+        const int nx = cx + stx, ny = cy + sty, nz = cz + stz;
+        float tx = (igx != 0.0f && nx >= 0 && nx < G.w) ? (float(stx > 0 ? cx + 1 : cx) - g0x) * igx : INFINITY;
+        float ty = (igy != 0.0f && ny >= 0 && ny < G.h) ? (float(sty > 0 ? cy + 1 : cy) - g0y) * igy : INFINITY;
+        float tz = (igz != 0.0f && nz >= 0 && nz < G.d) ? (float(stz > 0 ? cz + 1 : cz) - g0z) * igz : INFINITY;
+        float t_exit = fminf(fminf(tx, ty), fminf(tz, t1));
+        const float mu = float(__ldg(G.p + (size_t(cz) * G.h + cy) * G.w + cx)) * density;
+        if (mu > 0.0f) {
+            const float inv_mu = 1.0f / mu;
+            for (;;) {
+                t += -SKY_K19_LOG(1.0f - Random01<PRNG_KIND>(seed)) * inv_mu;   // InfiniteTransmittanceIS, :82-84
+                if (!(t < t_exit)) break;
+                float sigma_t = SampleSigmaTAt<SKY_MATERIAL_VOXEL, false>(P, ro + rd * t, inv_thickness);
+                ++lookups;
+                if (RATIO) {
+                    transmittance *= 1.0f - fmaxf(0.0f, sigma_t * inv_mu);   // :148
+                    if (transmittance <= 0.0f) return false;
+                } else if (Random01<PRNG_KIND>(seed) < sigma_t * inv_mu) {          // :193
+                    t_hit = t;
+                    return true;
+                }
+            }
+        }
+        if (!(t_exit < t1)) return false;
+        t = t_exit;
+        if (tx <= ty && tx <= tz) cx = nx; else if (ty <= tz) cy = ny; else cz = nz;
+    }
+    return false;
+}
+
+// K19, majorant-grid mode: one lane per (pixel, block of 8 kFrameIds); VolumetricCloudPathTracing.comp:160-284 as written
+// (the loop nest is fine here: a path is ~10^2 lookups, not ~5 10^3).
+template <int PRNG_KIND, bool COUNT>
+__global__ void __launch_bounds__(128) k19_majorant_grid(const __grid_constant__ PtParams P, const MajorantView G) {
+    const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
+    const int tiles_x = (rw + 7) >> 3, tiles_y = (rh + 3) >> 2;
+    const unsigned int npix = (unsigned int)rw * (unsigned int)rh;
+    const unsigned int npix_padded = (unsigned int)tiles_x * (unsigned int)tiles_y * 32u;
+    constexpr unsigned int kFramesPerJob = 8;
+    const unsigned int frame_blocks = (P.frame_count + kFramesPerJob - 1) / kFramesPerJob;
+    const unsigned int njobs = npix_padded * frame_blocks;
+    const float3 camera = f3(P.c.uCameraPos), sun = f3(P.c.uSunDirection);
+    const float inv_thickness = 1.0f / (P.c.uTopAltitude - P.c.uBottomAltitude);
+    int lookups = 0, paths = 0;
+    for (;;) {
+        // warp-aggregated job fetch among the lanes that arrive together
+        unsigned int job;
+        {
+            const unsigned int m = __activemask();
+            const int leader = __ffs(m) - 1;
+            unsigned int base = 0;
+            if ((threadIdx.x & 31u) == (unsigned int)leader) base = atomicAdd(P.job_counter, (unsigned int)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            job = base + __popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+        }
+        if (job >= njobs) break;
+        const unsigned int fb = job / npix_padded, p = job - fb * npix_padded;
+        const unsigned int tile = p >> 5, in_tile = p & 31u;
+        const int px = P.x0 + int(tile % (unsigned int)tiles_x) * 8 + int(in_tile & 7u);
+        const int py = P.y0 + int(tile / (unsigned int)tiles_x) * 4 + int(in_tile >> 3);
+        if (px >= P.x1 || py >= P.y1) continue;
+        const float2 uv = f2((float(px) + 0.5f) / float(P.width), (float(py) + 0.5f) / float(P.height));
+        const float3 frag_pos = projective_mul(P.c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 1.0f));
+        const float3 view_dir = normalize(frag_pos - camera);
+        const unsigned int f_end = min(fb * kFramesPerJob + kFramesPerJob, P.frame_count);
+        for (unsigned int frame_index = fb * kFramesPerJob; frame_index < f_end; ++frame_index) {
+            uint32_t seed = PRNG<PRNG_KIND>(PRNG<PRNG_KIND>(PRNG<PRNG_KIND>(uint32_t(px)) + uint32_t(py)) + (P.frame_begin + frame_index));  // :260
+            // ---- Trace, :160-249
+            float3 L = f3(0.0f), throughput = f3(1.0f);
+            bool has_scattered = false;
+            float scattered_t = 0.0f;
+            float3 ro = camera, rd = view_dir;
+            if (COUNT) ++paths;
+            float2 camera_inter_t = CloudRegionIntersect(P, ro, rd);
+            if (!(camera_inter_t.x >= camera_inter_t.y)) {
+                ro += camera_inter_t.x * rd;
+                int istep = 0;
+                while (istep < P.pt.max_bounces && fmaxf(throughput.x, fmaxf(throughput.y, throughput.z)) > 0.0f) {
+                    float2 inter_t = CloudRegionIntersect(P, ro, rd);
+                    if (inter_t.x >= inter_t.y) break;
+                    float t_hit = 0.0f, unused_tr;
+                    bool event_scatter = P.pt.sigma_t_max > 0 &&
+                                         TrackMajorantGrid<false, PRNG_KIND>(P, G, ro, rd, inter_t.x, inter_t.y, inv_thickness, seed, t_hit, unused_tr, lookups);
+                    float3 nee_pos, nee_bsdf;
+                    bool nee = false;
+                    if (!event_scatter) {  // :198-230
+                        if (P.pt.environment_lighting == SKY_ENV_OFF) break;
+                        if (!has_scattered) break;
+                        const float* M = P.pt.model_matrix3;
+                        float3 env_dir = f3(M[0] * rd.x + M[3] * rd.y + M[6] * rd.z, M[1] * rd.x + M[4] * rd.y + M[7] * rd.z, M[2] * rd.x + M[5] * rd.y + M[8] * rd.z);
+                        if (P.pt.environment_lighting == SKY_ENV_CONST_ENVIRONMENT_MAP) { L += throughput * SampleEnvironment(P, env_dir); break; }
+                        float3 up_dir = f3(ro.x, ro.y, ro.z + P.c.uEarthRadius);
+                        float r = length(up_dir);
+                        up_dir /= r;
+                        float mu = dot(rd, up_dir);
+                        if (!P.atm.RayIntersectsGround(r, mu)) { L += throughput * SampleEnvironment(P, env_dir); break; }
+                        ro += rd * P.atm.DistanceToBottomAtmosphereBoundary(r, mu);
+                        float3 ground_normal = normalize(f3(ro.x, ro.y, ro.z + P.c.uEarthRadius));
+                        nee = true; nee_pos = ro; nee_bsdf = kInvPi * P.atm.ground_albedo() * dot(ground_normal, sun);
+                    } else {               // :231-243
+                        if (!has_scattered) scattered_t = distance(camera, ro);
+                        has_scattered = true;
+                        ro += rd * t_hit;
+                        nee = true; nee_pos = ro; nee_bsdf = f3(GetPhase(P, dot(rd, sun)));
+                    }
+                    if (nee) {  // SampleLuminanceFromLight, :153-158 (the estimate of the sun transmittance uses its own draws here)
+                        float tr = 1.0f, th;
+                        float2 it = CloudRegionIntersect(P, nee_pos, sun);
+                        if (!(it.x >= it.y)) TrackMajorantGrid<true, PRNG_KIND>(P, G, nee_pos, sun, it.x, it.y, inv_thickness, seed, th, tr, lookups);
+                        L += throughput * (clampf(tr, 0.0f, 1.0f) * GetSunIlluminance(P, nee_pos) * nee_bsdf);
+                    }
+                    if (!event_scatter) {
+                        if (P.pt.environment_lighting == SKY_ENV_GROUND_SINGLE_BOUNCE) break;
+                        // GenerateLambertSample, :117-129 (cosine-weighted hemisphere about the ground normal)
+                        float3 N = normalize(f3(ro.x, ro.y, ro.z + P.c.uEarthRadius));
+                        float3 b0, b1;
+                        CreateOrthonormalBasis(N, b0, b1);
+                        float sin_theta = sqrtf(Random01<PRNG_KIND>(seed));
+                        float cos_theta = sqrtf(clampf(1.0f - sin_theta * sin_theta, 0.0f, 1.0f));
+                        float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
+                        rd = sin_theta * sinf(phi) * b0 + sin_theta * cosf(phi) * b1 + cos_theta * N;
+                        throughput *= P.atm.ground_albedo();
+                    } else if (P.pt.importance_sampling) {
+                        // GenerateHGSample with importance sampling, :98-111
+                        float g = Random01<PRNG_KIND>(seed) < P.pt.forward_scattering_ratio ? P.pt.forward_phase_g : P.pt.back_phase_g;
+                        float cos_theta = HenyeyGreensteinInvertcdf(Random01<PRNG_KIND>(seed), g);
+                        float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
+                        float3 b0, b1;
+                        CreateOrthonormalBasis(rd, b0, b1);
+                        float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
+                        rd = sin_theta * sinf(phi) * b0 + sin_theta * cosf(phi) * b1 + cos_theta * rd;
+                    } else {
+                        float phi = 2.0f * kPi * Random01<PRNG_KIND>(seed);
+                        float cos_theta = 1.0f - 2.0f * Random01<PRNG_KIND>(seed);
+                        float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
+                        float3 direction = f3(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta);
+                        throughput *= GetPhase(P, dot(rd, direction)) / (1.0f / (4.0f * kPi));
+                        rd = direction;
+                    }
+                    ++istep;
+                }
+            }
+            // ---- :248, :263-283
+            float4 this_res = f4(L, has_scattered ? 0.0f : 1.0f);
+            if (has_scattered) {
+                float r = P.c.uCameraPos[2] + P.c.uEarthRadius;
+                float mu = view_dir.z;
+                float ap_t = scattered_t;
+                if (r > P.atm.u.top_radius) {
+                    float near_distance;
+                    if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu, near_distance)) ap_t -= near_distance;
+                    else ap_t = 0;
+                }
+                float3 uvw = aerial_perspective_uvw(uv, ap_t, P.c.uAerialPerspectiveLutMaxDistance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
+                float3 atmosphere_transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
+                float3 atmosphere_luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
+                atmosphere_luminance *= SampleRayScatterVisibility(P.froxel, uv, scattered_t, P.c.uInvShadowFroxelMaxDistance);
+                this_res = f4(xyz(this_res) * atmosphere_transmittance + atmosphere_luminance, this_res.w);
+            }
+            P.samples[size_t(frame_index) * npix + size_t(py - P.y0) * rw + (px - P.x0)] = this_res;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(P.counters + SKY_CNT_PT_PATHS, (unsigned long long)paths);
+        atomicAdd(P.counters + SKY_CNT_PT_LOOKUPS, (unsigned long long)lookups);
+    }
+}
+
 // second half of K19 (:281-283): accumulated += this_res, one sample per kFrameId, in frame order.
 __global__ void __launch_bounds__(256) k19_accumulate(const __grid_constant__ PtParams P) {
     const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
@@ -663,12 +915,46 @@ int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
     const bool count_on = ctx->counting;
     const int prng = ctx->pt.prng;
+    // majorant-grid mode (sky_pt_set_tracking): build the macro-cell majorants of the current voxel texture on first use
+    const bool majorant_mode = ctx->pt_tracking == SKY_PT_TRACKING_MAJORANT_GRID;
+    MajorantView G{};
+    if (majorant_mode) {
+        if (ctx->material.type != SKY_MATERIAL_VOXEL) return sky_fail(ctx, "majorant-grid tracking needs the voxel material");
+        const MipView& v = ctx->voxel.view;
+        G.w = ceil_div(v.w[0], kMacro); G.h = ceil_div(v.h[0], kMacro); G.d = ceil_div(v.d[0], kMacro);
+        const size_t cells = size_t(G.w) * G.h * G.d;
+        if (!ctx->voxel_majorant || ctx->voxel_majorant_cells != cells || !ctx->voxel_majorant_valid) {
+            if (ctx->voxel_majorant) SKY_CUDA(ctx, cudaFree(ctx->voxel_majorant));
+            ctx->voxel_majorant = nullptr;
+            SKY_CUDA(ctx, cudaMalloc(&ctx->voxel_majorant, cells));
+            ctx->voxel_majorant_cells = cells;
+            k_majorant_build<<<unsigned((cells + 127) / 128), 128, 0, ctx->stream>>>(v, ctx->voxel_majorant, G.w, G.h, G.d);
+            SKY_LAUNCH_CHECK(ctx);
+            ctx->voxel_majorant_valid = true;
+        }
+        G.p = ctx->voxel_majorant;
+    }
     for (uint32_t done = 0; done < count; done += frames_per_launch) {
         P.frame_begin = frame_begin + done;
         P.frame_count = std::min(frames_per_launch, count - done);
         SKY_CUDA(ctx, cudaMemsetAsync(ctx->pt_job_counter, 0, sizeof(unsigned int), ctx->stream));
         // NOTE: the job space is the tile-padded pixel count, the slots are indexed by real pixels
         PtParams Q = P;
+        if (majorant_mode) {
+            auto launch = [&](auto kernel) {
+                int per_sm = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0);
+                size_t jobs = padded * ((Q.frame_count + 7) / 8);
+                unsigned blocks = unsigned(std::min<size_t>(size_t(sm_count) * std::max(per_sm, 1), (jobs + 127) / 128));
+                kernel<<<blocks, 128, 0, ctx->stream>>>(Q, G);
+            };
+            if (prng == SKY_PRNG_WANG) { if (count_on) launch(k19_majorant_grid<SKY_PRNG_WANG, true>); else launch(k19_majorant_grid<SKY_PRNG_WANG, false>); }
+            else { if (count_on) launch(k19_majorant_grid<SKY_PRNG_PCG, true>); else launch(k19_majorant_grid<SKY_PRNG_PCG, false>); }
+            SKY_LAUNCH_CHECK(ctx);
+            k19_accumulate<<<dim3(ceil_div(rw, 256), rh), 256, 0, ctx->stream>>>(Q);
+            SKY_LAUNCH_CHECK(ctx);
+            continue;
+        }
         int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
             auto launch = [&](auto kernel) {
                 int per_sm = 1;

@@ -95,7 +95,7 @@ def run_cloud_frames(scene, width, height, library, frames, device, composite=Tr
     return out
 
 
-def run_path_trace(scene, width, height, library, spp, grid=None, frame_begin=1, region=None, strict=False, **pt):
+def run_path_trace(scene, width, height, library, spp, grid=None, frame_begin=1, region=None, strict=False, tracking=0, **pt):
     r = Renderer(scene, width, height, library=library)
     if strict:
         r.ctx.set_strict_arithmetic(True)
@@ -106,6 +106,8 @@ def run_path_trace(scene, width, height, library, spp, grid=None, frame_begin=1,
     r.ctx.cloud_shadow(common)
     r.atmosphere_render_luts()
     r.path_trace_begin(**pt)
+    if tracking:
+        r.ctx.pt_set_tracking(tracking)
     r.ctx.pt_samples(common, frame_begin, spp, region or [0, 0, width, height])
     r.ctx.sync()
     return r, common, r.ctx.read(abi.RES_PT_ACCUM)

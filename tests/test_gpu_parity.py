@@ -363,6 +363,28 @@ def test_path_tracer_on_the_wdas_sixteenth_cloud(libs):
     assert rel_rms(as_[..., :3], ao[..., :3]) < 1e-4
 
 
+@pytest.mark.parametrize("data,kw", [("synthetic", dict(max_bounces=16, region_box_half_width=10.0)), ("wdas", dict()),
+                                     ("synthetic", dict(environment_lighting=abi.ENV_CONST_ENVIRONMENT_MAP, importance_sampling=False, max_bounces=32))])
+def test_majorant_grid_tracking_is_statistically_equal(libs, data, kw):
+    """SKY_PT_TRACKING_MAJORANT_GRID changes the random streams, not the expectation: its image differs from
+    a stream-exact image by no more than two stream-exact images of DIFFERENT kFrameIds differ from each other."""
+    from skyrendering_b200.renderer import wdas_sixteenth_grid
+    cuda, _ = libs
+    grid = wdas_sixteenth_grid() if data == "wdas" else synthetic_voxel_grid(63, 77, 43)
+    w, h, spp = 96, 54, 256
+    _, _, a = run_path_trace("c5", w, h, cuda, spp, grid=grid, frame_begin=1, **kw)
+    _, _, b = run_path_trace("c5", w, h, cuda, spp, grid=grid, frame_begin=1 + spp, **kw)
+    _, _, f = run_path_trace("c5", w, h, cuda, spp, grid=grid, frame_begin=1, tracking=abi.PT_TRACKING_MAJORANT_GRID, **kw)
+    assert np.all(np.isfinite(f))
+    noise = rel_rms(b[..., :3], a[..., :3])
+    assert rel_rms(f[..., :3], a[..., :3]) < 1.25 * noise and rel_rms(f[..., :3], b[..., :3]) < 1.25 * noise
+    ref_mean = 0.5 * (a[..., :3].mean() + b[..., :3].mean())
+    assert abs(f[..., :3].mean() - ref_mean) < 0.01 * ref_mean
+    # alpha accumulates the "never scattered" decisions: a transmittance estimate of the primary ray
+    assert abs(f[..., 3].mean() - 0.5 * (a[..., 3].mean() + b[..., 3].mean())) < 0.01 * spp
+    assert rel_rms(f[..., 3], a[..., 3]) < 1.25 * max(rel_rms(b[..., 3], a[..., 3]), 1e-3)
+
+
 def test_path_tracer_default_parameters_small(libs):
     """Reference defaults (128 bounces, +-100 km box, PCG, ground multi-bounce) at a size the oracle finishes."""
     cuda, orc = libs
