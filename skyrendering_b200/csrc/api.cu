@@ -125,15 +125,17 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     rc |= sky_alloc(ctx, ctx->transmittance, 256, 64);   // Atmosphere.cpp:11-12
     rc |= sky_alloc(ctx, ctx->multiscattering, 32, 32);  // Atmosphere.cpp:17-18
     if (!rc) {
-        // GL_LINEAR + CLAMP_TO_EDGE texture views over the LUT memory (Samplers.cpp linear_clamp_no_mipmap)
-        auto make_tex = [](const Lut<float4>& l, cudaTextureObject_t* out) {
+        // GL_LINEAR + CLAMP_TO_EDGE texture views (Samplers.cpp linear_clamp_no_mipmap) over RGBA16F copies of the two LUTs
+        rc |= sky_alloc(ctx, ctx->transmittance_h, 256, 64);
+        rc |= sky_alloc(ctx, ctx->multiscattering_h, 32, 32);
+        auto make_tex = [](const Lut<half4>& l, cudaTextureObject_t* out) {
             cudaResourceDesc res{};
             res.resType = cudaResourceTypePitch2D;
             res.res.pitch2D.devPtr = l.p;
-            res.res.pitch2D.desc = cudaCreateChannelDesc<float4>();
+            res.res.pitch2D.desc = cudaCreateChannelDescHalf4();
             res.res.pitch2D.width = size_t(l.w);
             res.res.pitch2D.height = size_t(l.h);
-            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(float4);
+            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(half4);
             cudaTextureDesc td{};
             td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
             td.filterMode = cudaFilterModeLinear;
@@ -141,8 +143,10 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
             td.normalizedCoords = 1;
             return cudaCreateTextureObject(out, &res, &td, nullptr) == cudaSuccess ? 0 : 1;
         };
-        rc |= make_tex(ctx->transmittance, &ctx->transmittance_tex);
-        rc |= make_tex(ctx->multiscattering, &ctx->multiscattering_tex);
+        if (!rc) {
+            rc |= make_tex(ctx->transmittance_h, &ctx->transmittance_tex);
+            rc |= make_tex(ctx->multiscattering_h, &ctx->multiscattering_tex);
+        }
     }
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);  // VolumetricCloud.cpp:52,102-105
     if (cudaMalloc(&ctx->blue_noise, 64 * 64 * sizeof(uint16_t)) != cudaSuccess) rc = 1;
@@ -164,6 +168,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h);
     free_lut(ctx->transmittance); free_lut(ctx->multiscattering); free_lut(ctx->sky_lum); free_lut(ctx->sky_trans);
     free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
     for (auto& m : ctx->shadow_maps) free_lut(m);
@@ -176,6 +181,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2}) if (ev) cudaEventDestroy(ev);
     if (ctx->transmittance_tex) cudaDestroyTextureObject(ctx->transmittance_tex);
     if (ctx->multiscattering_tex) cudaDestroyTextureObject(ctx->multiscattering_tex);
+    for (cudaTextureObject_t t : {ctx->sky_lum_tex, ctx->sky_trans_tex, ctx->ap_lum_tex, ctx->ap_trans_tex}) if (t) cudaDestroyTextureObject(t);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->ray_setup) cudaFree(ctx->ray_setup);
     if (ctx->ray_raw) cudaFree(ctx->ray_raw);
@@ -277,6 +283,30 @@ int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
     rc |= sky_alloc(ctx, ctx->ap_trans, 32, 32, cfg->aerial_perspective_depth, false);
     rc |= sky_alloc(ctx, ctx->env, cfg->environment_size, cfg->environment_size, 6, false);
     if (rc) return rc;
+    // texture views for K6 (production object): recreated when sky_alloc moved or resized a LUT
+    {
+        Lut<float4>* luts[4] = {&ctx->sky_lum, &ctx->sky_trans, &ctx->ap_lum, &ctx->ap_trans};
+        cudaTextureObject_t* tex[4] = {&ctx->sky_lum_tex, &ctx->sky_trans_tex, &ctx->ap_lum_tex, &ctx->ap_trans_tex};
+        for (int i = 0; i < 4; ++i) {
+            const Lut<float4>& l = *luts[i];
+            if (*tex[i] && ctx->lut_tex_key[i] == l.p && ctx->lut_tex_dims[i][0] == l.w && ctx->lut_tex_dims[i][1] == l.h && ctx->lut_tex_dims[i][2] == l.d) continue;
+            if (*tex[i]) { cudaDestroyTextureObject(*tex[i]); *tex[i] = 0; }
+            cudaResourceDesc res{};
+            res.resType = cudaResourceTypePitch2D;
+            res.res.pitch2D.devPtr = l.p;
+            res.res.pitch2D.desc = cudaCreateChannelDesc<float4>();
+            res.res.pitch2D.width = size_t(l.w);
+            res.res.pitch2D.height = size_t(l.h) * size_t(l.d);   // 3-D LUT: its slices stacked
+            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(float4);
+            cudaTextureDesc td{};
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 1;
+            SKY_CUDA(ctx, cudaCreateTextureObject(tex[i], &res, &td, nullptr));
+            ctx->lut_tex_key[i] = l.p; ctx->lut_tex_dims[i][0] = l.w; ctx->lut_tex_dims[i][1] = l.h; ctx->lut_tex_dims[i][2] = l.d;
+        }
+    }
     return launch_atmosphere_luts(ctx);
 }
 
@@ -521,6 +551,7 @@ int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint
     if (int e = sky_get_resource(ctx, resource, &d)) return e;
     if (bytes != d.bytes) return sky_fail(ctx, "write_resource: size mismatch, expected " + std::to_string(d.bytes));
     SKY_CUDA(ctx, cudaMemcpyAsync(d.ptr, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (resource == SKY_RES_TRANSMITTANCE || resource == SKY_RES_MULTISCATTERING) { if (int e = launch_lut_half_copies(ctx)) return e; }
     if (resource == SKY_RES_CLOUD_MAP) { if (int e = launch_mip_chain(ctx, ctx->cloud_map)) return e; }
     if (resource == SKY_RES_DETAIL) { if (int e = launch_mip_chain(ctx, ctx->detail)) return e; }
     if (resource == SKY_RES_DISPLACEMENT) { if (int e = launch_mip_chain(ctx, ctx->displacement)) return e; }

@@ -114,70 +114,104 @@ SKY_D float GetVisibilityFromMoonShadow(float3 moon_vector, float moon_radius, f
     return GetVisibilityFromMoonShadow(LUT_ACOS(clampf(dot(sun_direction, moon_direction), -1.0f, 1.0f)), sun_angular_radius, moon_angular_radius);
 }
 
+// One step of the march of Atmosphere.glsl:244-290: everything that depends on the step alone (not on the running
+// transmittance).  A = luminance_i - luminance_i * transmittance_i, B = scattering_i - scattering_i * transmittance_i.
+struct MarchSetup {
+    float r, mu, dx, rayleigh_phase, mie_phase;
+};
+struct MarchStep {
+    float3 A, B, extinction, transmittance;
+};
+template <bool MS>
+SKY_D MarchSetup march_setup(const AtmosphereModel& atm, float3 earth_center, float3 start_position, float3 view_direction,
+                             float3 sun_direction, float marching_distance, float steps) {
+    const SkyAtmosphereBufferData& u = atm.u;
+    MarchSetup m;
+    m.r = length(start_position - earth_center);
+    float3 up_direction = normalize(start_position - earth_center);
+    m.mu = dot(view_direction, up_direction);
+    float cos_sun_view = dot(view_direction, sun_direction);
+    m.dx = marching_distance / steps;
+    if (MS) {
+        m.rayleigh_phase = m.mie_phase = 1.0f / (4.0f * kPi);  // IsotropicPhaseFunction, :134-136
+    } else {
+        // RayleighPhaseFunction / MiePhaseFunction, :138-154
+        m.rayleigh_phase = (3.0f / (16.0f * kPi)) * (1.0f + cos_sun_view * cos_sun_view);
+        float g = u.mie_phase_g;
+        float k = 3.0f / (8.0f * kPi) * (1.0f - g * g) / (2.0f + g * g);
+        m.mie_phase = k * (1.0f + cos_sun_view * cos_sun_view) / sky_det_pow15f(1.0f + g * g - 2.0f * g * cos_sun_view);
+    }
+    return m;
+}
+template <bool MS, bool TEXLUT, bool EXTRA>
+SKY_D MarchStep march_step(const AtmosphereModel& atm, const LutView& transmittance_texture, const LutView& multiscattering_texture,
+                           const MarchSetup& m, float i, float3 earth_center, float3 start_position, float3 view_direction,
+                           float3 sun_direction, const ScatterExtras* extras) {
+    const SkyAtmosphereBufferData& u = atm.u;
+    const float r = m.r, mu = m.mu, dx = m.dx;
+    float d_i = i * dx;
+    float r_i = sqrtf(d_i * d_i + 2.0f * r * mu * d_i + r * r);
+    float3 position_i = start_position + view_direction * d_i;
+    float altitude_i = r_i - u.bottom_radius;
+
+    // GetScattering, :156-159
+    float3 rayleigh_scattering_i = f3(u.rayleigh_scattering) * clampf(LUT_EXP(-altitude_i * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+    float3 mie_scattering_i = f3(u.mie_scattering) * clampf(LUT_EXP(-altitude_i * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+    float3 scattering_i = rayleigh_scattering_i + mie_scattering_i;
+    float3 scattering_with_phase_i = rayleigh_scattering_i * m.rayleigh_phase + mie_scattering_i * m.mie_phase;
+
+    float3 extinction_i = GetExtinction(u, altitude_i);
+    float3 transmittance_i = lut_exp3(-extinction_i * dx);
+    float3 up_direction_i = normalize(position_i - earth_center);
+    float mu_s_i = dot(sun_direction, up_direction_i);
+    float3 luminance_i = scattering_with_phase_i * atm.template GetSunVisibility<TEXLUT>(transmittance_texture, r_i, mu_s_i);
+    if (!MS) {
+        if (EXTRA && extras->shadow_size > 0) luminance_i *= GetVisibilityFromShadowMap(*extras, position_i);  // :274-277
+        // GetMultiscatteringContribution, :169-178
+        float x_mu_s = mu_s_i * 0.5f + 0.5f;
+        float x_r = (r_i - u.bottom_radius) / (u.top_radius - u.bottom_radius);
+        float uu = 0.5f / float(multiscattering_texture.w) + x_mu_s * (1.0f - 1.0f / float(multiscattering_texture.w));
+        float vv = 0.5f / float(multiscattering_texture.h) + x_r * (1.0f - 1.0f / float(multiscattering_texture.h));
+        float3 multiscattering_contribution = xyz(sample_lut2d_sel<TEXLUT>(multiscattering_texture, uu, vv));
+        luminance_i += u.multiscattering_mask * multiscattering_contribution * scattering_i;
+        if (EXTRA && extras->moon_shadow)  // :281-284
+            luminance_i *= GetVisibilityFromMoonShadow(f3(extras->moon_position) - position_i, extras->moon_radius, sun_direction, u.sun_angular_radius);
+        luminance_i *= f3(u.solar_illuminance);
+    }
+    MarchStep s;
+    s.A = luminance_i - luminance_i * transmittance_i;
+    s.B = MS ? scattering_i - scattering_i * transmittance_i : f3(0.0f);
+    s.extinction = extinction_i;
+    s.transmittance = transmittance_i;
+    return s;
+}
+
+// Atmosphere.glsl:220-295, one thread per march.  MS = MULTISCATTERING_COMPUTE_PROGRAM permutation.
 template <bool MS, bool TEXLUT = false, bool EXTRA = false>
 SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture,
                                        const LutView& multiscattering_texture, float start_i, float3 earth_center,
                                        float3 start_position, float3 view_direction, float3 sun_direction,
                                        float marching_distance, float steps, float3& transmittance, float3& L_f,
                                        const ScatterExtras* extras = nullptr) {
-    const SkyAtmosphereBufferData& u = atm.u;
-    float r = length(start_position - earth_center);
-    float3 up_direction = normalize(start_position - earth_center);
-    float mu = dot(view_direction, up_direction);
-    float cos_sun_view = dot(view_direction, sun_direction);
     const float SAMPLE_COUNT = steps;
-    float dx = marching_distance / SAMPLE_COUNT;
-
+    const MarchSetup m = march_setup<MS>(atm, earth_center, start_position, view_direction, sun_direction, marching_distance, steps);
     transmittance = f3(1.0f);
     float3 luminance = f3(0.0f);
-    float rayleigh_phase, mie_phase;
-    if (MS) {
-        L_f = f3(0.0f);
-        start_i = 0.5f;
-        rayleigh_phase = mie_phase = 1.0f / (4.0f * kPi);  // IsotropicPhaseFunction, :134-136
-    } else {
-        // RayleighPhaseFunction / MiePhaseFunction, :138-154
-        rayleigh_phase = (3.0f / (16.0f * kPi)) * (1.0f + cos_sun_view * cos_sun_view);
-        float g = u.mie_phase_g;
-        float k = 3.0f / (8.0f * kPi) * (1.0f - g * g) / (2.0f + g * g);
-        mie_phase = k * (1.0f + cos_sun_view * cos_sun_view) / sky_det_pow15f(1.0f + g * g - 2.0f * g * cos_sun_view);
-    }
+    if (MS) { L_f = f3(0.0f); start_i = 0.5f; }
     for (float i = start_i; i < SAMPLE_COUNT; ++i) {
-        float d_i = i * dx;
-        float r_i = sqrtf(d_i * d_i + 2.0f * r * mu * d_i + r * r);
-        float3 position_i = start_position + view_direction * d_i;
-        float altitude_i = r_i - u.bottom_radius;
-
-        // GetScattering, :156-159
-        float3 rayleigh_scattering_i = f3(u.rayleigh_scattering) * clampf(LUT_EXP(-altitude_i * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
-        float3 mie_scattering_i = f3(u.mie_scattering) * clampf(LUT_EXP(-altitude_i * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
-        float3 scattering_i = rayleigh_scattering_i + mie_scattering_i;
-        float3 scattering_with_phase_i = rayleigh_scattering_i * rayleigh_phase + mie_scattering_i * mie_phase;
-
-        float3 extinction_i = GetExtinction(u, altitude_i);
-        float3 transmittance_i = lut_exp3(-extinction_i * dx);
-        float3 up_direction_i = normalize(position_i - earth_center);
-        float mu_s_i = dot(sun_direction, up_direction_i);
-        float3 luminance_i = scattering_with_phase_i * atm.template GetSunVisibility<TEXLUT>(transmittance_texture, r_i, mu_s_i);
-        if (!MS) {
-            if (EXTRA && extras->shadow_size > 0) luminance_i *= GetVisibilityFromShadowMap(*extras, position_i);  // :274-277
-            // GetMultiscatteringContribution, :169-178
-            float x_mu_s = mu_s_i * 0.5f + 0.5f;
-            float x_r = (r_i - u.bottom_radius) / (u.top_radius - u.bottom_radius);
-            float uu = 0.5f / float(multiscattering_texture.w) + x_mu_s * (1.0f - 1.0f / float(multiscattering_texture.w));
-            float vv = 0.5f / float(multiscattering_texture.h) + x_r * (1.0f - 1.0f / float(multiscattering_texture.h));
-            float3 multiscattering_contribution = xyz(sample_lut2d_sel<TEXLUT>(multiscattering_texture, uu, vv));
-            luminance_i += u.multiscattering_mask * multiscattering_contribution * scattering_i;
-            if (EXTRA && extras->moon_shadow)  // :281-284
-                luminance_i *= GetVisibilityFromMoonShadow(f3(extras->moon_position) - position_i, extras->moon_radius, sun_direction, u.sun_angular_radius);
-            luminance_i *= f3(u.solar_illuminance);
-        }
-        luminance += transmittance * (luminance_i - luminance_i * transmittance_i) / extinction_i;
-        if (MS) L_f += transmittance * (scattering_i - scattering_i * transmittance_i) / extinction_i;
-        transmittance *= transmittance_i;
+        const MarchStep s = march_step<MS, TEXLUT, EXTRA>(atm, transmittance_texture, multiscattering_texture, m, i, earth_center, start_position,
+                                                          view_direction, sun_direction, extras);
+        luminance += transmittance * s.A / s.extinction;
+        if (MS) L_f += transmittance * s.B / s.extinction;
+        transmittance *= s.transmittance;
     }
     return luminance;
 }
+
+// (Measured and removed: the same march spread over the 32 lanes of a warp -- lane l evaluates steps l, l + 32, ..., then every
+// lane replays the running transmittance product / luminance sum over the broadcast records in the reference's order.  It is
+// bit-identical, but K2 went 78 -> 520 us and K3-K5 230 -> 470 us: these kernels already issue at ~50 % of the machine with one
+// thread per march, and the replicated serial part costs 5x the instructions.)
 
 // Atmosphere.glsl:297-306
 template <bool MS>
@@ -275,6 +309,13 @@ __global__ void __launch_bounds__(64) k2_multiscattering(const __grid_constant__
         float3 F_ms = 1.0f / (f3(1.0f) - f_ms);
         P.multiscattering_out[gy * P.ms_w + gx] = f4(L_2nd_order * F_ms, 1.0f);
     }
+}
+
+__global__ void __launch_bounds__(256) k_luts_to_half(const float4* __restrict__ a, half4* __restrict__ ah, int na, const float4* __restrict__ b,
+                                                      half4* __restrict__ bh, int nb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na) ah[i] = to_half4(a[i]);
+    else if (i - na < nb) bh[i - na] = to_half4(b[i - na]);
 }
 
 // ------------------------------------------------------------------------------------------- K3 / K4 / K5 / K6
@@ -494,12 +535,12 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
             float cos_lat, cos_lon;
             GetCosLatLonFromViewDirection(P, view_direction, cos_lat, cos_lon);
             float2 uv = GetSkyViewTextureUvFromCosLatLon(P, r, cos_lat, cos_lon);
-            luminance = xyz(sample_lut2d(P.sky_lum, uv.x, uv.y));
-            transmittance = xyz(sample_lut2d(P.sky_trans, uv.x, uv.y));
+            luminance = xyz(sample_lut2d_sel<kCompositeTexLut>(P.sky_lum, uv.x, uv.y));
+            transmittance = xyz(sample_lut2d_sel<kCompositeTexLut>(P.sky_trans, uv.x, uv.y));
         } else if (P.cfg.use_aerial_perspective_lut && intersect_object) {
             float3 uvw = aerial_perspective_uvw(vTexCoord, marching_distance, P.r.aerial_perspective_lut_max_distance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
-            luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
-            transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
+            luminance = xyz(sample_lut3d_sel<kCompositeTexLut>(P.ap_lum, uvw.x, uvw.y, uvw.z));
+            transmittance = xyz(sample_lut3d_sel<kCompositeTexLut>(P.ap_trans, uvw.x, uvw.y, uvw.z));
         } else {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
             luminance = ComputeScatteredLuminance<false, kCompositeTexLut, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
@@ -532,10 +573,10 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.cfg = ctx->lut_cfg;
     P.transmittance = LutView{ctx->transmittance.p, ctx->transmittance.w, ctx->transmittance.h, 1, ctx->transmittance_tex};
     P.multiscattering = LutView{ctx->multiscattering.p, ctx->multiscattering.w, ctx->multiscattering.h, 1, ctx->multiscattering_tex};
-    P.sky_lum = LutView{ctx->sky_lum.p, ctx->sky_lum.w, ctx->sky_lum.h, 1, 0};
-    P.sky_trans = LutView{ctx->sky_trans.p, ctx->sky_trans.w, ctx->sky_trans.h, 1, 0};
-    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d, 0};
-    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, 0};
+    P.sky_lum = LutView{ctx->sky_lum.p, ctx->sky_lum.w, ctx->sky_lum.h, 1, ctx->sky_lum_tex};
+    P.sky_trans = LutView{ctx->sky_trans.p, ctx->sky_trans.w, ctx->sky_trans.h, 1, ctx->sky_trans_tex};
+    P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d, ctx->ap_lum_tex};
+    P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, ctx->ap_trans_tex};
     P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
     P.blue_noise = ctx->blue_noise;
     P.sky_lum_out = ctx->sky_lum.p; P.sky_trans_out = ctx->sky_trans.p;
@@ -556,6 +597,15 @@ RenderParams make_render_params(SkyContext* ctx) {
 // reference's unfused arithmetic) and once with -DSKY_COMPOSITE_TU -use_fast_math for the full-screen
 // composite K6, which is a frame (tolerance: relative RMS 1e-2) and ALU-bound on its per-pixel raymarch.
 #ifndef SKY_COMPOSITE_TU
+// RGBA16F copies of the two bake LUTs for K6's texture fetches (context.h)
+int launch_lut_half_copies(SkyContext* ctx) {
+    const int na = ctx->transmittance.w * ctx->transmittance.h, nb = ctx->multiscattering.w * ctx->multiscattering.h;
+    k_luts_to_half<<<ceil_div(na + nb, 256), 256, 0, ctx->stream>>>(ctx->transmittance.p, ctx->transmittance_h.p, na, ctx->multiscattering.p,
+                                                                     ctx->multiscattering_h.p, nb);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int launch_atmosphere_bake(SkyContext* ctx) {
     BakeParams P{};
     P.atm.u = ctx->atm;
@@ -567,7 +617,7 @@ int launch_atmosphere_bake(SkyContext* ctx) {
     SKY_LAUNCH_CHECK(ctx);
     k2_multiscattering<<<dim3(P.ms_w, P.ms_h), 64, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
-    return 0;
+    return launch_lut_half_copies(ctx);
 }
 
 int launch_atmosphere_luts(SkyContext* ctx) {

@@ -34,6 +34,21 @@ SKY_D float4 sample_lut2d_sel(const LutView& t, float u, float v) {
     return sample_lut2d(t, u, v);
 }
 
+// 3-D LUT through the texture unit: the slices of the LUT are stacked in one 2-D texture (LutView::tex over the same memory);
+// two bilinear fetches (8-bit weights) + the slice blend in fp32.  v is clamped to the texel centres of its slice, which is
+// what CLAMP_TO_EDGE does and keeps the bilinear footprint out of the neighbouring slice.
+template <bool TEXLUT>
+SKY_D float4 sample_lut3d_sel(const LutView& t, float u, float v, float w);
+SKY_D float4 sample_lut3d_atlas(const LutView& t, float u, float v, float w) {
+    float z = w * float(t.d) - 0.5f;
+    float fz = floorf(z), c = z - fz;
+    int k0 = clampi(int(fz), 0, t.d - 1), k1 = clampi(int(fz) + 1, 0, t.d - 1);
+    float hv = 0.5f / float(t.h);
+    float vc = fminf(fmaxf(v, hv), 1.0f - hv);
+    float inv_d = 1.0f / float(t.d);
+    float4 a = tex2D<float4>(t.tex, u, (float(k0) + vc) * inv_d), b = tex2D<float4>(t.tex, u, (float(k1) + vc) * inv_d);
+    return f4(a.x + c * (b.x - a.x), a.y + c * (b.y - a.y), a.z + c * (b.z - a.z), a.w + c * (b.w - a.w));
+}
 SKY_D float4 sample_lut3d(const LutView& t, float u, float v, float w) {
     float x = u * float(t.w) - 0.5f, y = v * float(t.h) - 0.5f, z = w * float(t.d) - 0.5f;
     float fx = floorf(x), fy = floorf(y), fz = floorf(z);
@@ -150,4 +165,10 @@ SKY_D float sample_froxel(const FroxelView& t, float u, float v, float w) {
 SKY_D float SampleRayScatterVisibility(const FroxelView& froxel, float2 uv, float dist, float inv_max_dist) {
     float w = dist * inv_max_dist;
     return mixf(1.0f, sample_froxel(froxel, uv.x, uv.y, w), clampf(1.0f / w, 0.0f, 1.0f));
+}
+
+template <bool TEXLUT>
+SKY_D float4 sample_lut3d_sel(const LutView& t, float u, float v, float w) {
+    if (TEXLUT) return sample_lut3d_atlas(t, u, v, w);
+    return sample_lut3d(t, u, v, w);
 }

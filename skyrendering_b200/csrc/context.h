@@ -79,7 +79,15 @@ struct SkyContext {
     // K1-K5
     Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
     Lut<half4> env;  // [6][S][S]
-    cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0;  // LINEAR views of the two 2-D bake LUTs (K6 raymarch)
+    // K6's raymarch fetches the two bake LUTs twice per step through the texture unit, which is what bounds it (ncu: L1/TEX at
+    // 86 % of peak with RGBA32F texels, quarter rate); it reads RGBA16F copies (half rate), refreshed after every bake.  The
+    // fp16 rounding (2^-11 relative) is far inside the frame tolerance; the strict objects filter the fp32 LUTs in software.
+    Lut<half4> transmittance_h, multiscattering_h;
+    cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0;  // LINEAR views of those copies
+    // LINEAR views of the per-frame LUTs for K6's look-ups: sky view as 2-D, aerial perspective as a 32 x (32 D) atlas of its slices
+    cudaTextureObject_t sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
+    const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int lut_tex_dims[4][3] = {};
     uint16_t* blue_noise = nullptr;  // 64x64 u16
 
     // materials
@@ -157,6 +165,7 @@ int sky_alloc(SkyContext* ctx, Lut<T>& l, int w, int h, int d = 1, bool zero = t
 
 // per-subsystem launchers (defined in the .cu files) -----------------------------------------------------------
 int ensure_mesh_shadow_map(SkyContext* ctx);                                   // api.cu
+int launch_lut_half_copies(SkyContext* ctx);                                  // atmosphere.cu
 int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
 int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6

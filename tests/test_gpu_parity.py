@@ -364,7 +364,7 @@ def test_path_tracer_on_the_wdas_sixteenth_cloud(libs):
 
 
 @pytest.mark.parametrize("data,kw", [("synthetic", dict(max_bounces=16, region_box_half_width=10.0)), ("wdas", dict()),
-                                     ("synthetic", dict(environment_lighting=abi.ENV_CONST_ENVIRONMENT_MAP, importance_sampling=False, max_bounces=32))])
+                                     ("synthetic", dict(environment_lighting=abi.ENV_CONST_ENVIRONMENT_MAP, max_bounces=32))])
 def test_majorant_grid_tracking_is_statistically_equal(libs, data, kw):
     """SKY_PT_TRACKING_MAJORANT_GRID changes the random streams, not the expectation: its image differs from
     a stream-exact image by no more than two stream-exact images of DIFFERENT kFrameIds differ from each other."""
