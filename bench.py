@@ -352,6 +352,13 @@ def main():
         # the product's frame mode: the two independent halves of the frame on two streams (sky_set_frame_overlap)
         rf.ctx.set_frame_overlap(True)
         frame_ms = timed_steps(frame_step, max(args.steps, 5), 3)
+        # the same frame with the texture unit filtering the material textures (8-bit weights; inside the frame tolerance,
+        # tests/test_gpu_parity.py::test_hardware_filtering_within_frame_tolerance) -- what north_star allows for production
+        frame_hw_ms = None
+        if not args.hw_filtering:
+            rf.ctx.set_hw_filtering(True)
+            frame_hw_ms = timed_steps(frame_step, max(args.steps, 5), 3)
+            rf.ctx.set_hw_filtering(False)
         rf.ctx.set_frame_overlap(False)
         common, cloud = state["u"]
         parts = {
@@ -383,7 +390,7 @@ def main():
         depth_host = torch.from_numpy(depth_np).pin_memory()
         e2e_frame_ms = timed_steps(lambda: rf.ctx.cloud_frame_host(common, cloud, depth_host.numpy(), hdr_host.numpy()), 3, 1) if world == 1 else None
         frame = {
-            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "ms_per_frame_single_stream": frame_serial_ms, "unit": "ms", "higher_is_better": False,
+            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "ms_per_frame_single_stream": frame_serial_ms, "ms_per_frame_hardware_filtering": frame_hw_ms, "unit": "ms", "higher_is_better": False,
             "frame_definition": "one AppWindow::HandleDisplayEvent: K1,K2 bake, K11-K13 shadow chain, K3-K5 LUTs, K6 composite, K14-K18 cloud chain; "
                                 "ms_per_frame with sky_set_frame_overlap (shadow + cloud chain beside LUTs + composite on a second stream), "
                                 "parts_ms each kernel group alone",
