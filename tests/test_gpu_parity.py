@@ -12,6 +12,8 @@ Tolerances (stated here, explained in DESIGN.md section "Parity"):
   * path tracer: identical RNG streams -> relative RMS 2e-2 on the 16-spp accumulator and means within
     0.2 %; decisions that sit within an ulp of a threshold are the only differences.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -492,6 +494,57 @@ def test_tonemap_parity(libs):
         d = np.abs(out_g.cpu().numpy().astype(np.int32) - out_o.astype(np.int32))
         assert d.max() <= 1 and (d > 0).mean() < 0.02
         assert 20 < out_o[..., :3].mean() < 235   # a real image, not black / white
+
+
+def test_cpp_frame_driver_matches_the_python_driver(libs, tmp_path):
+    """skyrendering_b200/host/skyrender (C++ over the two C ABIs, no Python in the path) renders the same RGBA8 image, byte for
+    byte, as the Python frame driver: real-time frame of scene c3 and the path tracer on the raw wdas grid."""
+    import subprocess
+    import torch
+    from skyrendering_b200.renderer import scene_path, wdas_sixteenth_grid
+    cuda, _ = libs
+    exe = os.path.join(abi.REPO_ROOT, "skyrendering_b200", "host", "skyrender")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    w, h = 384, 216
+    # real-time frame
+    dump = str(tmp_path / "frame.rgba8")
+    out = subprocess.run([exe, scene_path("c3"), str(w), str(h), "--warmup", "4", "--frames", "0", "--dump-rgba8", dump], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert '"mode": "frame"' in out.stdout
+    r = Renderer("c3", w, h, library=cuda)
+    r.prime()
+    depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), "cuda")
+    for _ in range(4):
+        hdr.zero_()
+        r.frame(depth, hdr, 0.0)
+    img = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    r.ctx.tonemap(hdr, w, h, img)
+    r.ctx.sync()
+    assert np.array_equal(np.fromfile(dump, np.uint8).reshape(h, w, 4), img.cpu().numpy())
+    # path tracer on a raw grid file
+    grid = wdas_sixteenth_grid()
+    raw = str(tmp_path / "grid.u8")
+    grid.tofile(raw)
+    dz, dy, dx = grid.shape
+    dump = str(tmp_path / "pt.rgba8")
+    out = subprocess.run([exe, scene_path("c5"), str(w), str(h), "--spp", "4", "--raw8", raw, str(dx), str(dy), str(dz), "--dump-rgba8", dump],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert '"mode": "path_trace"' in out.stdout
+    r = Renderer("c5", w, h, library=cuda)
+    r.upload_voxels(grid)
+    r.prime()
+    depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), "cuda")
+    common, _, _ = r.cloud_update(0.0)
+    r.ctx.cloud_shadow(common)
+    r.atmosphere_render_luts()
+    r.ctx.composite(depth, hdr, w, h)
+    r.path_trace_begin()
+    r.path_trace_frames(common, 4)
+    r.ctx.pt_resolve(4, hdr)
+    r.ctx.tonemap(hdr, w, h, img)
+    r.ctx.sync()
+    assert np.array_equal(np.fromfile(dump, np.uint8).reshape(h, w, 4), img.cpu().numpy())
 
 
 def test_error_behaviour(libs):

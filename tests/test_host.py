@@ -262,3 +262,25 @@ def test_ground_depth_and_fixtures():
     assert g.shape == (86, 154, 126) and g.dtype == np.uint8
     assert 0.2 < (g > 0).mean() < 0.3  # about a quarter active, like wdas_cloud_sixteenth
     assert np.array_equal(g, synthetic_voxel_grid())
+
+
+def test_cpp_frame_driver_is_built_and_has_no_cpu_path(tmp_path):
+    """skyrender (C++ over the two C ABIs) links against libskyhost.so / libskyb200.so only and fails loudly without a GPU."""
+    import subprocess
+    exe = os.path.join(abi.REPO_ROOT, "skyrendering_b200", "host", "skyrender")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libskyhost.so" in ldd and "libskyb200.so" in ldd and "liboracle" not in ldd and "libskyref" not in ldd
+    usage = subprocess.run([exe], capture_output=True, text=True)
+    assert usage.returncode != 0 and "usage: skyrender" in usage.stderr
+    bad = subprocess.run([exe, str(tmp_path / "missing.json"), "192", "108"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "cannot open" in bad.stderr
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        from skyrendering_b200.renderer import scene_path
+        run = subprocess.run([exe, scene_path("c3"), "192", "108"], capture_output=True, text=True)
+        assert run.returncode != 0 and "no CPU path" in run.stderr
