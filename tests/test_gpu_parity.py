@@ -216,6 +216,38 @@ def test_strict_arithmetic_path_tracer(libs):
     assert np.mean(np.all(ag == ao, axis=-1)) > 0.6
 
 
+def test_ragged_viewport_and_clipped_region(libs):
+    """Sizes that are multiples of nothing: 250 x 134 -> half 125 x 67, quarter 62 x 33, froxels 20 x 11 (the reference relies on GL
+    dropping out-of-range image stores, GLReloadableProgram.h:55-59); a path-tracing region that sticks out of a 101 x 57 image."""
+    cuda, orc = libs
+    w, h = 250, 134
+    g = run_cloud_frames("c3", w, h, cuda, frames=3, device="cuda")
+    o = run_cloud_frames("c3", w, h, orc, frames=3, device="cpu")
+    for key in ("checker", "index", "render", "distance", "reconstruct", "froxel", "hdr"):
+        assert g[key].shape == o[key].shape, key
+    assert g["render"].shape == (33, 62, 4) and g["froxel"].shape == (128, 11, 20)
+    assert np.array_equal(g["checker"], o["checker"])
+    assert rel_rms(g["render"], o["render"]) < 1e-2 and rel_rms(g["reconstruct"], o["reconstruct"]) < 1e-2
+    assert rel_rms(g["hdr"][..., :3], o["hdr"][..., :3]) < 1e-2 and np.all(np.isfinite(g["hdr"]))
+    s = run_cloud_frames("c3", w, h, cuda, frames=3, device="cuda", strict=True)
+    assert np.mean(np.all(s["render"] == o["render"], axis=-1)) > 0.98 and np.mean(np.all(s["hdr"] == o["hdr"], axis=-1)) > 0.98
+    grid = synthetic_voxel_grid(63, 77, 43)
+    kw = dict(max_bounces=8, region_box_half_width=8.0, region=[10, 7, 133, 71])
+    rg, _, ag = run_path_trace("c5", 101, 57, cuda, 4, grid=grid, **kw)
+    _, _, ao = run_path_trace("c5", 101, 57, orc, 4, grid=grid, **kw)
+    assert ag.shape == (57, 101, 4)
+    assert not ag[:7].any() and not ag[:, :10].any()            # outside the region: untouched
+    mask = rg.ctx.read(abi.RES_PT_MASK)
+    assert mask[7:, 10:].all() and not mask[:7].any() and not mask[:, :10].any()
+    assert rel_rms(ag[..., :3], ao[..., :3]) < 2e-2 and np.array_equal(ag[..., 3], ao[..., 3])
+    # an empty job and an empty region are no-ops
+    before = rg.ctx.read(abi.RES_PT_ACCUM).copy()
+    rg.ctx.pt_samples(rg.last_uniforms[0], 5, 0, [0, 0, 101, 57])
+    rg.ctx.pt_samples(rg.last_uniforms[0], 5, 3, [50, 20, 50, 40])
+    rg.ctx.sync()
+    assert np.array_equal(rg.ctx.read(abi.RES_PT_ACCUM), before)
+
+
 def test_voxel_realtime_parity(libs):
     cuda, orc = libs
     grid = synthetic_voxel_grid(63, 77, 43)
