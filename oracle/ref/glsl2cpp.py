@@ -12,7 +12,7 @@ are purely syntactic -- no arithmetic is added, removed or reordered:
      dropped: uniform-block members, samplers, images and shared arrays become namespace-scope variables the driver fills;
      `layout(local_size...) in;` lines disappear (the driver passes the local size to ref::dispatch).
   4. parameter qualifiers: `out T x` / `inout T x` -> `T& x`, `in T x` -> `T x`; file-scope `in` / `out` interface
-     variables of a fragment shader become plain variables.
+     variables of a fragment shader become thread_local variables (one fragment per thread).
   5. GLSL array constructors `T[](...)` / `T[n](...)` -> `{...}`; `discard` -> `return`.
   6. `imageSize(x)` / `textureSize(x, l)` keep their names (the shim overloads them on the image / sampler type).
   8. GLSL-style array types `T[N] name` (function return types, locals) become std::array<T, N>.
@@ -75,7 +75,7 @@ def rewrite(text):
     text = re.sub(r"layout\s*\([^)]*\)\s*", "", text)
     text = re.sub(r"\b(uniform|shared|readonly|writeonly|restrict|coherent|highp|mediump|lowp|flat)\s+", "", text)
     # 4. file-scope interface variables of fragment shaders
-    text = re.sub(r"^(\s*)(in|out)\s+(\w+\s+\w+\s*;)", r"\1\3", text, flags=re.M)
+    text = re.sub(r"^(\s*)(in|out)\s+(\w+\s+\w+\s*;)", r"\1thread_local \3", text, flags=re.M)
     # parameter qualifiers
     text = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)", r"\1& \2", text)
     text = re.sub(r"([(,]\s*(?:const\s+)?)in\s+(\w+\s+\w+)", r"\1\2", text)

@@ -118,6 +118,42 @@ namespace k4v1m0 {
 #undef DITHER_SAMPLE_POINT_ENABLE
 #define VOLUMETRIC_LIGHT_ENABLE 0
 #define MOON_SHADOW_ENABLE 0
+// K6: the full-screen fragment program (AtmosphereRenderer.cpp:150-160), raymarching dither on (all shipped scenes),
+// permutations by LUT use: s = USE_SKY_VIEW_LUT, a = USE_AERIAL_PERSPECTIVE_LUT
+#define ATMOSPHERE_RENDER_FRAGMENT_SHADER
+#define DITHER_SAMPLE_POINT_ENABLE 1
+#undef USE_SKY_VIEW_LUT
+#undef USE_AERIAL_PERSPECTIVE_LUT
+#define USE_SKY_VIEW_LUT 1
+#define USE_AERIAL_PERSPECTIVE_LUT 1
+namespace k6s1a1 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef USE_AERIAL_PERSPECTIVE_LUT
+#define USE_AERIAL_PERSPECTIVE_LUT 0
+namespace k6s1a0 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef USE_SKY_VIEW_LUT
+#define USE_SKY_VIEW_LUT 0
+namespace k6s0a0 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef DITHER_SAMPLE_POINT_ENABLE
+#define DITHER_SAMPLE_POINT_ENABLE 0
+namespace k6s0a0d0 {
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef DITHER_SAMPLE_POINT_ENABLE
+#undef ATMOSPHERE_RENDER_FRAGMENT_SHADER
+#undef USE_SKY_VIEW_LUT
+#undef USE_AERIAL_PERSPECTIVE_LUT
+#define USE_SKY_VIEW_LUT 1
+#define USE_AERIAL_PERSPECTIVE_LUT 1
 namespace k5 {
 #define ENVIRONMENT_LUMINANCE_COMPUTE_PROGRAM
 #define DITHER_SAMPLE_POINT_ENABLE 1
@@ -200,5 +236,77 @@ extern "C" int ref_atmosphere_luts(const SkyAtmosphereBufferData* a, const SkyAt
         ref_bind_image(env_luminance_image, io->environment, E, E, 6, ref::FMT_RGBA16F);
         ref::dispatch(main, ref_ceil_div(E, LOCAL_SIZE_X), ref_ceil_div(E, LOCAL_SIZE_Y), 6, LOCAL_SIZE_X, LOCAL_SIZE_Y, 1, false);
     }
+    return 0;
+}
+
+
+// ---- K6 ------------------------------------------------------------------------------------------------------------
+struct RefCompositeIO {
+    const float* transmittance;      // [64][256][4]
+    const float* multiscattering;    // [32][32][4]
+    const float* blue_noise;         // [64][64][4]
+    const float* sky_luminance;      // [sky_h][sky_w][4]
+    const float* sky_transmittance;
+    const float* ap_luminance;       // [depth][32][32][4]
+    const float* ap_transmittance;
+    const float* froxel;             // [fd][fh][fw][4] (unorm16 / 65535 in .x) or null (no cloud shadow froxel yet: visibility 1)
+    int fw, fh, fd;
+    const float* depth;              // [h][w][4], the D24 depth in .x
+    const float* star;               // [sh][sw][4] linear RGB (sRGB already decoded) or null (black)
+    int star_w, star_h;
+    float* out;                      // [h][w][4]: FragColor
+    int width, height;
+};
+
+extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg,
+                             const RefCompositeIO* io) {
+    ref::g_sky_w = cfg->sky_view_width; ref::g_sky_h = cfg->sky_view_height; ref::g_ap_depth = cfg->aerial_perspective_depth;
+    if (cfg->moon_shadow || cfg->volumetric_light) return 3;  // permutation not compiled
+    static const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    static const float one4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    static float zero_cube[6 * 4] = {};
+    const int W = io->width, H = io->height;
+#define RUN_K6(NS)                                                                                                          \
+    {                                                                                                                       \
+        using namespace ref::NS;                                                                                            \
+        REF_LOAD_ATMOSPHERE(a);                                                                                             \
+        REF_LOAD_RENDER(r);                                                                                                 \
+        ref_bind_texture(transmittance_texture, io->transmittance, 256, 64, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);            \
+        ref_bind_texture(multiscattering_texture, io->multiscattering, 32, 32, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);         \
+        ref_bind_texture(depth_stencil_texture, io->depth, W, H, 1, ref::CLAMP_TO_EDGE, ref::NEAREST);                      \
+        /* an all-zero G-buffer makes ComputeObjectLuminance vanish: object pixels keep the in-scatter term alone */        \
+        ref_bind_texture(albedo_texture, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                  \
+        ref_bind_texture(normal_texture, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                  \
+        ref_bind_texture(orm_texture, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                     \
+        ref::NS::shadow_map_texture.levels.clear();  /* no mesh shadow map: lit */                                          \
+        ref_bind_texture(blue_noise, io->blue_noise, 64, 64, 1, ref::REPEAT, ref::NEAREST);                                 \
+        if (io->star) ref_bind_texture(star_luminance, io->star, io->star_w, io->star_h, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
+        else ref_bind_texture(star_luminance, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                             \
+        ref_bind_texture(sky_view_luminance_texture, io->sky_luminance, cfg->sky_view_width, cfg->sky_view_height, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);     \
+        ref_bind_texture(sky_view_transmittance_texture, io->sky_transmittance, cfg->sky_view_width, cfg->sky_view_height, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
+        ref_bind_texture(aerial_perspective_luminance_texture, io->ap_luminance, 32, 32, cfg->aerial_perspective_depth, ref::CLAMP_TO_EDGE, ref::LINEAR);    \
+        ref_bind_texture(aerial_perspective_transmittance_texture, io->ap_transmittance, 32, 32, cfg->aerial_perspective_depth, ref::CLAMP_TO_EDGE, ref::LINEAR); \
+        ref_bind_texture(shadow_map_depth_sampler, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::NEAREST);                        \
+        ref_bind_texture(cloud_shadow_map, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                 \
+        if (io->froxel) ref_bind_texture(cloud_shadow_froxel, io->froxel, io->fw, io->fh, io->fd, ref::CLAMP_TO_EDGE, ref::LINEAR); \
+        else ref_bind_texture(cloud_shadow_froxel, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                         \
+        ref_bind_texture(prefiltered_radiance_texture, zero_cube, 1, 1, 6, ref::CLAMP_TO_EDGE, ref::LINEAR);                \
+        ref_bind_texture(env_brdf_lut, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                    \
+        for (int i = 0; i < 9; ++i) Llm[i] = ref::vec4(0.0f);                                                               \
+        _Pragma("omp parallel for schedule(dynamic, 4)")                                                                    \
+        for (int py = 0; py < H; ++py)                                                                                      \
+            for (int px = 0; px < W; ++px) {                                                                                \
+                ref::g_builtins.frag_coord = ref::vec4(float(px) + 0.5f, float(py) + 0.5f, 0.0f, 1.0f);                     \
+                vTexCoord = ref::vec2((float(px) + 0.5f) / float(W), (float(py) + 0.5f) / float(H));                        \
+                main();                                                                                                     \
+                float* o = io->out + (size_t(py) * W + px) * 4;                                                             \
+                o[0] = FragColor.x; o[1] = FragColor.y; o[2] = FragColor.z; o[3] = FragColor.w;                             \
+            }                                                                                                               \
+    }
+    if (cfg->use_sky_view_lut && cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a1)
+    else if (cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a0)
+    else if (!cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s0a0)
+    else if (!cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && !cfg->raymarching_dither) RUN_K6(k6s0a0d0)
+    else return 3;
     return 0;
 }

@@ -76,6 +76,39 @@ def ref_luts(ref, renderer, mesh_shadow_map=None):
     return {k: v[..., :3].copy() for k, v in out.items()}
 
 
+class RefCompositeIO(C.Structure):
+    _fields_ = [("transmittance", C.c_void_p), ("multiscattering", C.c_void_p), ("blue_noise", C.c_void_p), ("sky_luminance", C.c_void_p),
+                ("sky_transmittance", C.c_void_p), ("ap_luminance", C.c_void_p), ("ap_transmittance", C.c_void_p), ("froxel", C.c_void_p),
+                ("fw", C.c_int), ("fh", C.c_int), ("fd", C.c_int), ("depth", C.c_void_p), ("star", C.c_void_p), ("star_w", C.c_int),
+                ("star_h", C.c_int), ("out", C.c_void_p), ("width", C.c_int), ("height", C.c_int)]
+
+
+def ref_composite(ref, renderer, depth, width, height, blue_noise, froxel=None, star_linear=None):
+    """K6: the reference's full-screen fragment program (AtmosphereRenderer.glsl:345-432, permutation of the scene's flags) on the
+    LUT state of `renderer` (an oracle-backed Renderer after atmosphere_render_luts) with an all-zero G-buffer -- which makes
+    ComputeObjectLuminance vanish, so object pixels carry the in-scatter term alone, like sky_composite's.  Returns FragColor
+    float32 [H][W][4].  `froxel`: uint16 [128][H/12][W/12] or None; `star_linear`: float32 [sh][sw][3] decoded star map or None."""
+    ctx = renderer.ctx
+    keep = []
+    def rgba(a, channels_last=True):
+        b = as_rgba(a, channels_last); keep.append(b); return b
+    T = rgba(ctx.read(abi.RES_TRANSMITTANCE)); M = rgba(ctx.read(abi.RES_MULTISCATTERING))
+    sl = rgba(ctx.read(abi.RES_SKY_VIEW_LUMINANCE)); st = rgba(ctx.read(abi.RES_SKY_VIEW_TRANSMITTANCE))
+    al = rgba(ctx.read(abi.RES_AERIAL_LUMINANCE)); at = rgba(ctx.read(abi.RES_AERIAL_TRANSMITTANCE))
+    bn = rgba(np.asarray(blue_noise).astype(np.float32) / np.float32(65535.0), channels_last=False)
+    dp = rgba(np.asarray(depth, np.float32), channels_last=False)
+    fr = None if froxel is None else rgba(np.asarray(froxel).astype(np.float32) / np.float32(65535.0), channels_last=False)
+    sr = None if star_linear is None else rgba(np.asarray(star_linear, np.float32))
+    out = np.zeros((height, width, 4), np.float32)
+    io = RefCompositeIO(T.ctypes.data, M.ctypes.data, bn.ctypes.data, sl.ctypes.data, st.ctypes.data, al.ctypes.data, at.ctypes.data,
+                        None if fr is None else fr.ctypes.data, 0 if fr is None else fr.shape[2], 0 if fr is None else fr.shape[1],
+                        0 if fr is None else fr.shape[0], dp.ctypes.data, None if sr is None else sr.ctypes.data,
+                        0 if sr is None else sr.shape[1], 0 if sr is None else sr.shape[0], out.ctypes.data, width, height)
+    rc = ref.ref_composite(C.byref(renderer.atmosphere), C.byref(renderer.render_buffer), C.byref(renderer.lut_config), C.byref(io))
+    assert rc == 0, rc
+    return out
+
+
 def ref_noise(ref, kind, info, shape):
     out = np.zeros(shape, np.uint8)
     w, h, d = (128, 128, 128) if kind == abi.NOISE_DETAIL else (shape[1], shape[0], 1)

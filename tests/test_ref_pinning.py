@@ -150,3 +150,34 @@ def test_oracle_cloud_chain_is_the_reference_shaders_pass_by_pass(scene):
     assert same(out, O["reconstruct"].reshape(hh + (4,))), "K17"
     H.set("reconstruct_out", O["reconstruct"].reshape(hh + (4,))); out = H.set("hdr", hdr_before); H.run(18)
     assert same(out, O["hdr"]), "K18"
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("scene", ["c1", "c2", "c3", "raymarch"])
+def test_oracle_composite_is_the_reference_fragment_program(scene):
+    """K6: AtmosphereRenderer.glsl's fragment program compiled from the reference's text (permutation of the scene's LUT flags,
+    all-zero G-buffer so that ComputeObjectLuminance vanishes) against the oracle's composite: RGB bit-identical in every pixel
+    -- sky look-up, aerial-perspective look-up or per-pixel raymarch, god-ray froxel factor, sun disc."""
+    from skyrendering_b200.renderer import load_blue_noise
+    from tests.parity import make_buffers
+    from tests import permutations
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 192, 108
+    r = Renderer(permutations.scene(raymarch=True) if scene == "raymarch" else scene, w, h, library=orc)
+    r.prime()
+    depth_np = r.scene.ground_depth(w, h)
+    depth, hdr = make_buffers(w, h, depth_np, "cpu")
+    # one whole frame first: K6 multiplies by the cloud-shadow froxels of VolumetricCloud::RenderShadow (the god-ray factor)
+    r.frame(depth, hdr, 0.0)
+    froxel = r.ctx.read(abi.RES_SHADOW_FROXEL)
+    assert froxel.max() > 0
+    hdr[...] = 0
+    r.ctx.composite(depth, hdr, w, h)
+    got = hdr.astype(np.float32)
+    want = refpin.ref_composite(ref, r, depth_np, w, h, load_blue_noise(), froxel=froxel)
+    want16 = want.astype(np.float16).astype(np.float32)   # the HDR target is RGBA16F
+    undefined = ~np.isfinite(want16[..., :3]).all(axis=-1)
+    assert undefined.sum() <= 8
+    assert np.array_equal(got[..., :3][~undefined], want16[..., :3][~undefined])
+    # both kinds of pixel are present, and the reference writes alpha 1 everywhere (the oracle marks object pixels with 0)
+    assert 0.1 < got[..., 3].mean() < 0.9 and np.all(want[..., 3][~undefined] == 1.0)
