@@ -44,6 +44,12 @@ int SKY_FN(sync)(SkyContext* ctx);
  * in GL order (i.e. the PNG flipped vertically, StbImage.cpp:12-17). */
 int SKY_FN(set_blue_noise)(SkyContext* ctx, const uint16_t* host_texels_64x64);
 
+/* Textures::Textures star map upload (src/Base/src/Textures.cpp:43-50): GL_SRGB8 texels, RGB8 [H][W][3], rows in GL order; K6 adds
+ * star_luminance_scale * texture(star_luminance, equirect(view_direction)) to sky pixels outside the sun disc
+ * (AtmosphereRenderer.glsl:326-331,427-429; sampler LinearNoMipmapClampToEdge: level 0, texels decoded to linear before
+ * filtering).  Without a star map the term is absent (a black sky behind the atmosphere).  width or height 0 removes it. */
+int SKY_FN(set_star_map)(SkyContext* ctx, const uint8_t* host_srgb8, int width, int height);
+
 /* VolumetricCloud::SetViewport (VolumetricCloud.cpp:115-136): (re)allocates the per-viewport
  * targets and zero-fills the temporal histories. */
 int SKY_FN(set_viewport)(SkyContext* ctx, int width, int height);

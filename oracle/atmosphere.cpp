@@ -176,8 +176,7 @@ float SampleRayScatterVisibility(const Image<1>& shadow_froxel, vec2 uv, float d
 
 // K6 -- AtmosphereRenderer.glsl:345-432.  gl_FragCoord.xy = pixel + 0.5, vTexCoord = that / size.
 // Object pixels (depth != 1) get the in-scatter only and alpha 0: ComputeObjectLuminance
-// (:284-324) needs the G-buffer + IBL chain that SURVEY.md 8f-1 leaves for later.  Sky pixels
-// outside the sun disc omit the star map term (:427-429, same "next" row).
+// (:284-324) needs the G-buffer + IBL chain that SURVEY.md 8f-1 leaves for later.
 void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_trans, const Image<4>& ap_lum,
                                    const Image<4>& ap_trans, const Image<1>* shadow_froxel, const float* depth_img,
                                    int width, int height, uint16_t* hdr) const {
@@ -239,6 +238,8 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
                 vec3 factor = vec3(1.0f) - uu * (vec3(1.0f) - pow(vec3(mu2), a));
                 vec3 solar_illuminance_at_eye = atm.solar_illuminance() * transmittance;
                 luminance += solar_illuminance_at_eye / (PI * atm.u.sun_angular_radius * atm.u.sun_angular_radius) * factor;
+            } else if (star_map) {  // :427-429
+                luminance += transmittance * GetStarLuminance(view_direction);
             }
             uint16_t* o = hdr + (size_t(py) * width + px) * 4;
             o[0] = float_to_half_bits(luminance.x);

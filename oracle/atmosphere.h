@@ -321,7 +321,16 @@ struct AtmosphereRenderer {
     const Image<4>& transmittance_texture;
     const Image<4>& multiscattering_texture;
     const Image<1>* blue_noise = nullptr;  // R16 64x64
+    const Image<4>* star_map = nullptr;  // GL_SRGB8 star map decoded to linear RGB (Textures.cpp:43-50); null: no star term
     const Image<1>* mesh_shadow_map = nullptr;  // DEPTH32F 2048^2 (ShadowMap.cpp:8-27), used when cfg.volumetric_light
+
+    // AtmosphereRenderer.glsl:326-331 (sampler LinearNoMipmapClampToEdge, AtmosphereRenderer.cpp:204)
+    vec3 GetStarLuminance(vec3 view_direction) const {
+        float theta = sky_det_acosf(view_direction.y);
+        float phi = std::atan2(view_direction.x, view_direction.z);
+        vec2 coord(INV_PI * 0.5f * phi + 0.5f, 1.0f - theta * INV_PI);
+        return u.star_luminance_scale * texture_linear(*star_map, coord, Sampler()).rgb();
+    }
 
     Atmosphere::ScatterExtras extras() const {
         Atmosphere::ScatterExtras e;

@@ -23,6 +23,7 @@ struct CloudScene {
     SkyLutConfig lut_cfg{};
 
     Image<1> blue_noise;  // 64x64, u16/65535 (Textures.cpp:19-26)
+    Image<4> star_map;         // decoded (linear) star map, empty when none was set (Textures.cpp:43-50)
     Image<1> mesh_shadow_map;  // 2048x2048 light-space depth (ShadowMap.cpp:8-27), allocated on first use, cleared to 1
 
     // ---- material ----

@@ -80,6 +80,22 @@ void orc_ctx_destroy(SkyContext* ctx) { delete ctx; }
 const char* orc_last_error(SkyContext* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 int orc_sync(SkyContext*) { return 0; }
 
+int orc_set_star_map(SkyContext* ctx, const uint8_t* srgb8, int width, int height) {
+    if (width <= 0 || height <= 0) { ctx->scene.star_map.resize(0, 0); return 0; }
+    float decode[256];  // GL 4.6 section 8.24: sRGB -> linear, applied to each texel before filtering
+    for (int c = 0; c < 256; ++c) {
+        double cs = c / 255.0;
+        decode[c] = float(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+    }
+    Image<4>& m = ctx->scene.star_map;
+    m.resize(width, height);
+    for (size_t i = 0; i < size_t(width) * height; ++i) {
+        for (int k = 0; k < 3; ++k) m.data[i * 4 + k] = decode[srgb8[i * 3 + k]];
+        m.data[i * 4 + 3] = 1.0f;
+    }
+    return 0;
+}
+
 int orc_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
     for (int i = 0; i < 64 * 64; ++i) ctx->scene.blue_noise.data[i] = float(texels[i]) / 65535.0f;
     return 0;
@@ -119,6 +135,7 @@ int orc_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int
     CloudScene& s = ctx->scene;
     AtmosphereRenderer ar{s.atm, s.render_u, s.lut_cfg, s.transmittance, s.multiscattering, &s.blue_noise};
     if (s.lut_cfg.volumetric_light) ar.mesh_shadow_map = &mesh_shadow_map(s);
+    if (s.star_map.w > 0) ar.star_map = &s.star_map;
     const Image<1>* froxel = (s.shadow_froxel.w > 0) ? &s.shadow_froxel : nullptr;
     ar.Composite(s.sky_lum, s.sky_trans, s.ap_lum, s.ap_trans, froxel, depth, width, height, static_cast<uint16_t*>(hdr));
     return 0;

@@ -187,6 +187,7 @@ KERNEL_API = {
     "pt_samples": ([P(CloudCommonBufferData), U, U, P(I * 4)], I),
     "pt_resolve": ([U, _VOIDP], I),
     "pt_set_tracking": ([I], I),
+    "set_star_map": ([_VOIDP, I, I], I),
     "tonemap": ([_VOIDP, I, I, C.POINTER(ToneMapParams), _VOIDP], I),
     "pt_samples_host": ([P(CloudCommonBufferData), U, U, P(I * 4), _VOIDP], I),
     "get_resource": ([I, P(ResourceDesc)], I),
@@ -335,6 +336,15 @@ class Context:
         self._call("pt_samples_host", C.byref(common), frame_begin, count, C.byref((I * 4)(*region)), _ptr(accum_host))
 
     def pt_resolve(self, frame_count, hdr): self._call("pt_resolve", frame_count, _ptr(hdr))
+    def set_star_map(self, srgb8):
+        """GL_SRGB8 star map, uint8 [H][W][3] in GL row order (None removes it)."""
+        if srgb8 is None:
+            self._call("set_star_map", None, 0, 0)
+            return
+        a = np.ascontiguousarray(srgb8, np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 3
+        self._call("set_star_map", _ptr(a), a.shape[1], a.shape[0])
+
     def pt_set_tracking(self, mode): self._call("pt_set_tracking", int(mode))
 
     def tonemap(self, hdr, width, height, out, tone_mapping=1, exposure=10.0, dither=False):

@@ -1,6 +1,7 @@
 // C ABI of libskyb200.so (include/skyb200.h).  Plain pointers and PODs only; no exceptions and no
 // torch types cross this boundary.  There is no CPU fallback anywhere in this library: without a
 // CUDA device sky_ctx_create fails.
+#include <cmath>
 #include <vector>
 #include "../../include/skyb200.h"
 
@@ -172,6 +173,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->transmittance); free_lut(ctx->multiscattering); free_lut(ctx->sky_lum); free_lut(ctx->sky_trans);
     free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
     for (auto& m : ctx->shadow_maps) free_lut(m);
+    free_lut(ctx->star_map); if (ctx->srgb_decode) cudaFree(ctx->srgb_decode);
     free_lut(ctx->mesh_shadow_map); free_lut(ctx->shadow_froxel); free_lut(ctx->checkerboard_depth); free_lut(ctx->cloud_distance);
     free_lut(ctx->index_linear_depth); free_lut(ctx->render_texture); free_lut(ctx->reconstruct[0]); free_lut(ctx->reconstruct[1]);
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
@@ -242,6 +244,28 @@ int sky_sync(SkyContext* ctx) {
 int sky_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
     SKY_CUDA(ctx, cudaMemcpyAsync(ctx->blue_noise, texels, 64 * 64 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer may be a temporary
+    return 0;
+}
+
+int sky_set_star_map(SkyContext* ctx, const uint8_t* host_srgb8, int width, int height) {
+    if (int e = lanes_join(ctx)) return e;
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_lut(ctx->star_map);
+    if (width <= 0 || height <= 0 || !host_srgb8) return 0;
+    if (width > 16384 || height > 16384) return sky_fail(ctx, "star map too large");
+    if (!ctx->srgb_decode) {
+        float decode[256];  // GL 4.6 section 8.24: sRGB -> linear, applied to each texel before filtering
+        for (int c = 0; c < 256; ++c) {
+            double cs = c / 255.0;
+            decode[c] = float(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+        }
+        SKY_CUDA(ctx, cudaMalloc(&ctx->srgb_decode, sizeof(decode)));
+        SKY_CUDA(ctx, cudaMemcpy(ctx->srgb_decode, decode, sizeof(decode), cudaMemcpyHostToDevice));
+    }
+    if (int e = sky_alloc(ctx, ctx->star_map, width, height, 1, false)) return e;
+    std::vector<uchar4> rgbx(size_t(width) * height);
+    for (size_t i = 0; i < rgbx.size(); ++i) rgbx[i] = make_uchar4(host_srgb8[i * 3], host_srgb8[i * 3 + 1], host_srgb8[i * 3 + 2], 255);
+    SKY_CUDA(ctx, cudaMemcpy(ctx->star_map.p, rgbx.data(), rgbx.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
     return 0;
 }
 

@@ -326,6 +326,9 @@ struct RenderParams {
     LutView transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
     FroxelView froxel;  // p == nullptr: no cloud shadow froxel yet (visibility 1)
     ScatterExtras extras;
+    const uchar4* star_map;      // GL_SRGB8 codes (RGBX), nullptr: no star term
+    const float* srgb_decode;    // 256 entries
+    int star_w, star_h;
     const uint16_t* blue_noise;
     float4 *sky_lum_out, *sky_trans_out, *ap_lum_out, *ap_trans_out;
     half4* env_out;
@@ -562,6 +565,22 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
         float3 factor = f3(1.0f) - f3(1.0f) * (f3(1.0f) - f3(powf(mu2, a.x), powf(mu2, a.y), powf(mu2, a.z)));
         float3 solar_illuminance_at_eye = P.atm.solar_illuminance() * transmittance;
         luminance += solar_illuminance_at_eye / (kPi * P.atm.u.sun_angular_radius * P.atm.u.sun_angular_radius) * factor;
+    } else if (P.star_map) {
+        // GetStarLuminance, :326-331 and :427-429: equirectangular look-up, LinearNoMipmapClampToEdge, texels decoded before filtering
+        float theta = LUT_ACOS(fminf(fmaxf(view_direction.y, -1.0f), 1.0f));
+        float phi = atan2f(view_direction.x, view_direction.z);
+        float u = kInvPi * 0.5f * phi + 0.5f, v = 1.0f - theta * kInvPi;
+        float x = u * float(P.star_w) - 0.5f, y = v * float(P.star_h) - 0.5f;
+        float fx = floorf(x), fy = floorf(y);
+        float a = x - fx, b = y - fy;
+        int i0 = clampi(int(fx), 0, P.star_w - 1), i1 = clampi(int(fx) + 1, 0, P.star_w - 1);
+        int j0 = clampi(int(fy), 0, P.star_h - 1), j1 = clampi(int(fy) + 1, 0, P.star_h - 1);
+        auto texel = [&](int i, int j) {
+            uchar4 c = __ldg(P.star_map + size_t(j) * P.star_w + i);
+            return f3(__ldg(P.srgb_decode + c.x), __ldg(P.srgb_decode + c.y), __ldg(P.srgb_decode + c.z));
+        };
+        float3 star = (1.0f - a) * (1.0f - b) * texel(i0, j0) + a * (1.0f - b) * texel(i1, j0) + (1.0f - a) * b * texel(i0, j1) + a * b * texel(i1, j1);
+        luminance += transmittance * (P.r.star_luminance_scale * star);
     }
     P.hdr[size_t(py) * P.width + px] = to_half4(f4(luminance, alpha));
 }
@@ -579,6 +598,7 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, ctx->ap_trans_tex};
     P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
     P.blue_noise = ctx->blue_noise;
+    P.star_map = ctx->star_map.p; P.srgb_decode = ctx->srgb_decode; P.star_w = ctx->star_map.w; P.star_h = ctx->star_map.h;
     P.sky_lum_out = ctx->sky_lum.p; P.sky_trans_out = ctx->sky_trans.p;
     P.ap_lum_out = ctx->ap_lum.p; P.ap_trans_out = ctx->ap_trans.p;
     P.env_out = ctx->env.p;

@@ -96,6 +96,8 @@ struct SkyContext {
     // shadow chain
     Lut<float2> shadow_maps[3];
     Lut<uint16_t> shadow_froxel;
+    Lut<uchar4> star_map;        // GL_SRGB8 star map as RGBX codes (sky_set_star_map); p == nullptr: no star term
+    float* srgb_decode = nullptr; // 256-entry sRGB -> linear table (device)
     Lut<float> mesh_shadow_map;  // SKY_RES_MESH_SHADOW_MAP: 2048^2 light-space depth, allocated on first use, cleared to 1
 
     // viewport

@@ -44,3 +44,21 @@ def mesh_shadow_map(size=2048):
     m[(x - 0.55 * size) ** 2 + (y - 0.5 * size) ** 2 < (0.12 * size) ** 2] = 0.02
     m[(np.abs(x - 0.3 * size) < 0.03 * size)] = 0.05
     return m
+
+
+def star_map(width=512, height=256, seed=3):
+    """A synthetic GL_SRGB8 star map (uint8 [H][W][3]): dim background gradient + sparse bright stars (the NASA star map of the
+    reference, data/NASA/starmap_2020_4k.jpg, is a 4096 x 2048 JPEG that is not shipped here)."""
+    rng = np.random.RandomState(seed)
+    y = np.linspace(0, 1, height, dtype=np.float32)[:, None, None]
+    img = np.broadcast_to(8 + 20 * y, (height, width, 3)).astype(np.float32).copy()
+    n = width * height // 40
+    img[rng.randint(height, size=n), rng.randint(width, size=n)] = rng.randint(60, 256, size=(n, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def srgb_decode(codes):
+    """GL 4.6 section 8.24 sRGB -> linear, float32 like the table both libraries build."""
+    cs = np.arange(256) / 255.0
+    table = np.where(cs <= 0.04045, cs / 12.92, ((cs + 0.055) / 1.055) ** 2.4).astype(np.float32)
+    return table[np.asarray(codes)]

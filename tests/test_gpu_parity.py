@@ -287,6 +287,35 @@ def test_composite_c2_parity(libs):
     assert rel_rms(g[sky][:, :3], o[sky][:, :3]) < 1e-2 and rel_rms(g[~sky][:, :3], o[~sky][:, :3]) < 1e-2
 
 
+def test_star_term_parity(libs):
+    """K6's star-map term (GL_SRGB8 equirectangular map, decoded before filtering) on the sunset scene."""
+    from tests import permutations
+    cuda, orc = libs
+    w, h = 480, 270
+    stars = permutations.star_map()
+    outs = {}
+    for key, lib, dev, strict in (("cuda", cuda, "cuda", False), ("strict", cuda, "cuda", True), ("oracle", orc, "cpu", False)):
+        r = Renderer("c2", w, h, library=lib)
+        r.ctx.set_strict_arithmetic(strict)
+        r.ctx.set_star_map(stars)
+        r.prime()
+        depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), dev)
+        r.frame(depth, hdr, 0.0, clouds=False)
+        r.ctx.sync()
+        outs[key] = to_numpy(hdr).astype(np.float32)
+        if key == "cuda":
+            r.ctx.set_star_map(None)
+            hdr.zero_()
+            r.frame(depth, hdr, 0.0, clouds=False)
+            r.ctx.sync()
+            outs["plain"] = to_numpy(hdr).astype(np.float32)
+    sky = outs["oracle"][..., 3] == 1
+    assert (outs["cuda"][sky][:, :3] > outs["plain"][sky][:, :3]).mean() > 0.5
+    assert rel_rms(outs["cuda"][..., :3], outs["oracle"][..., :3]) < 1e-2
+    assert rel_rms(outs["strict"][..., :3], outs["oracle"][..., :3]) < 1e-4
+    assert np.mean(np.all(outs["strict"] == outs["oracle"], axis=-1)) > 0.98
+
+
 def test_hardware_filtering_within_frame_tolerance(libs):
     """The 8-bit interpolation weights of the texture unit stay inside the frame tolerance (north_star)."""
     cuda, orc = libs

@@ -181,3 +181,34 @@ def test_oracle_composite_is_the_reference_fragment_program(scene):
     assert np.array_equal(got[..., :3][~undefined], want16[..., :3][~undefined])
     # both kinds of pixel are present, and the reference writes alpha 1 everywhere (the oracle marks object pixels with 0)
     assert 0.1 < got[..., 3].mean() < 0.9 and np.all(want[..., 3][~undefined] == 1.0)
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+def test_oracle_star_term_is_the_reference_fragment_program():
+    """GetStarLuminance (AtmosphereRenderer.glsl:326-331,427-429) through a GL_SRGB8 star map: bit-identical, and visible."""
+    from skyrendering_b200.renderer import load_blue_noise
+    from tests.parity import make_buffers
+    from tests import permutations
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 192, 108
+    stars = permutations.star_map()
+    r = Renderer("c2", w, h, library=orc)   # sunset: a dark sky
+    r.prime()
+    depth_np = r.scene.ground_depth(w, h)
+    depth, hdr = make_buffers(w, h, depth_np, "cpu")
+    r.frame(depth, hdr, 0.0)
+    froxel = r.ctx.read(abi.RES_SHADOW_FROXEL)
+    hdr[...] = 0
+    r.ctx.composite(depth, hdr, w, h)
+    plain = hdr.astype(np.float32).copy()
+    r.ctx.set_star_map(stars)
+    r.ctx.composite(depth, hdr, w, h)
+    got = hdr.astype(np.float32)
+    want = refpin.ref_composite(ref, r, depth_np, w, h, load_blue_noise(), froxel=froxel, star_linear=permutations.srgb_decode(stars))
+    want16 = want.astype(np.float16).astype(np.float32)
+    assert np.array_equal(got[..., :3], want16[..., :3])
+    sky = got[..., 3] == 1
+    assert (got[sky][:, :3] > plain[sky][:, :3]).mean() > 0.5 and np.array_equal(got[~sky], plain[~sky])
+    r.ctx.set_star_map(None)
+    r.ctx.composite(depth, hdr, w, h)
+    assert np.array_equal(hdr.astype(np.float32), plain)
