@@ -399,8 +399,7 @@ SKY_D float DitherStart(const RenderParams& P, int enable, int x, int y) {
 
 // K3 -- AtmosphereRenderer.glsl:153-186 (+ :81-111)
 template <bool EXTRA>
-__global__ void __launch_bounds__(64) k3_sky_view(const __grid_constant__ RenderParams P) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+SKY_D void k3_sky_view_texel(const RenderParams& P, int x, int y) {
     const int W = P.cfg.sky_view_width, H = P.cfg.sky_view_height;
     if (x >= W || y >= H) return;
     float r = P.r.camera_earth_center_distance;
@@ -442,9 +441,8 @@ __global__ void __launch_bounds__(64) k3_sky_view(const __grid_constant__ Render
 
 // K4 -- AtmosphereRenderer.glsl:191-243
 template <bool EXTRA>
-__global__ void __launch_bounds__(64) k4_aerial_perspective(const __grid_constant__ RenderParams P) {
+SKY_D void k4_aerial_perspective_froxel(const RenderParams& P, int x, int y, int z) {
     const int W = P.ap_lum.w, H = P.ap_lum.h, D = P.ap_lum.d;
-    int x = threadIdx.x % W, y = blockIdx.x * (blockDim.x / W) + threadIdx.x / W, z = blockIdx.y;
     if (y >= H || z >= D) return;
     float3 uvw = f3(float(x) / float(W - 1), float(y) / float(H - 1), float(z) / float(D - 1));
     float3 position = projective_mul(P.r.inv_view_projection, f3(uvw.x * 2.0f - 1.0f, uvw.y * 2.0f - 1.0f, 0.0f));
@@ -467,6 +465,19 @@ __global__ void __launch_bounds__(64) k4_aerial_perspective(const __grid_constan
     size_t o = (size_t(z) * H + y) * W + x;
     P.ap_lum_out[o] = f4(luminance, 0.0f);
     P.ap_trans_out[o] = f4(transmittance, 0.0f);
+}
+
+// K3 and K4 are independent (both read only the bake LUTs) and each is a few hundred 64-thread blocks of long dependent
+// marches -- far too little to fill 148 SMs alone -- so they share ONE launch: the first n3 blocks are K3's texel rows, the
+// rest K4's froxel rows.  Same per-thread code, same results; the LUT phase of a frame costs max(K3, K4) instead of K3 + K4.
+template <bool EXTRA>
+__global__ void __launch_bounds__(64) k34_sky_view_and_aerial_perspective(const __grid_constant__ RenderParams P, int n3, int g3x, int g4x) {
+    if (int(blockIdx.x) < n3) {
+        k3_sky_view_texel<EXTRA>(P, int(blockIdx.x % g3x) * 64 + int(threadIdx.x), int(blockIdx.x / g3x));
+    } else {
+        const int b = int(blockIdx.x) - n3, W = P.ap_lum.w;
+        k4_aerial_perspective_froxel<EXTRA>(P, int(threadIdx.x) % W, (b % g4x) * (64 / W) + int(threadIdx.x) / W, b / g4x);
+    }
 }
 
 // shaders/Base/Common.glsl:13-30
@@ -647,14 +658,11 @@ int launch_atmosphere_luts(SkyContext* ctx) {
         P = make_render_params(ctx);
     }
     const bool extra = P.cfg.moon_shadow || P.cfg.volumetric_light;
-    const dim3 g3(ceil_div(P.cfg.sky_view_width, 64), P.cfg.sky_view_height);
-    if (extra) k3_sky_view<true><<<g3, 64, 0, ctx->stream>>>(P);
-    else k3_sky_view<false><<<g3, 64, 0, ctx->stream>>>(P);
-    SKY_LAUNCH_CHECK(ctx);
-    // 64 threads = two rows of the 32-wide froxel slice
-    const dim3 g4(ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), P.ap_lum.d);
-    if (extra) k4_aerial_perspective<true><<<g4, 64, 0, ctx->stream>>>(P);
-    else k4_aerial_perspective<false><<<g4, 64, 0, ctx->stream>>>(P);
+    // K3: 64 texels of a row per block; K4: 64 threads = two rows of the 32-wide froxel slice
+    const int g3x = ceil_div(P.cfg.sky_view_width, 64), n3 = g3x * P.cfg.sky_view_height;
+    const int g4x = ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), n4 = g4x * P.ap_lum.d;
+    if (extra) k34_sky_view_and_aerial_perspective<true><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
+    else k34_sky_view_and_aerial_perspective<false><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
     SKY_LAUNCH_CHECK(ctx);
     k5_environment<<<dim3(ceil_div(P.cfg.environment_size, 128), P.cfg.environment_size, 6), 128, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
