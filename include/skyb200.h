@@ -173,6 +173,13 @@ int SKY_FN(set_strict_arithmetic)(SkyContext* ctx, int enable);
  * cloud_frame_end and in every other entry point (they join first), not at the return of those two calls. */
 int SKY_FN(set_frame_overlap)(SkyContext* ctx, int enable);
 
+/* Opt-in pipelining of consecutive frames: the context keeps two sets of the atmosphere LUTs; sky_atmosphere_bake flips to the
+ * set the frame before last used and runs the LUT phase (K1-K5, small latency-bound kernels that gate both full-machine
+ * kernels of a frame) on an internal high-priority stream beside the PREVIOUS frame's K6 / K16; the caller's stream waits for
+ * it where the LUTs are first read.  Results are bit-identical; getters return the newest set.  Independent of
+ * sky_set_frame_overlap (they compose). */
+int SKY_FN(set_frame_pipelining)(SkyContext* ctx, int enable);
+
 /* Microbenchmark for the texture-pipe roofline: launches `iters` dependent-free trilinear R8
  * fetches per thread over the detail volume and returns texel-quads per second. */
 int SKY_FN(tex_peak)(SkyContext* ctx, int mode, double* fetches_per_second);

@@ -379,6 +379,7 @@ int orc_pt_set_tracking(SkyContext* ctx, int mode) { return mode == SKY_PT_TRACK
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
 int orc_set_strict_arithmetic(SkyContext*, int) { return 0; }  // the oracle IS the strict arithmetic
 int orc_set_frame_overlap(SkyContext*, int) { return 0; }
+int orc_set_frame_pipelining(SkyContext*, int) { return 0; }
 int orc_tex_peak(SkyContext* ctx, int, double*) { return fail(ctx, "tex_peak is a GPU microbenchmark"); }
 
 // ---- test hooks (not part of skyb200.h): expose the leaf functions to the known-answer tests ------

@@ -197,6 +197,7 @@ KERNEL_API = {
     "set_hw_filtering": ([I], I),
     "set_strict_arithmetic": ([I], I),
     "set_frame_overlap": ([I], I),
+    "set_frame_pipelining": ([I], I),
     "tex_peak": ([I, P(C.c_double)], I),
 }
 
@@ -356,6 +357,7 @@ class Context:
     def set_hw_filtering(self, on): self._call("set_hw_filtering", int(on))
     def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))
     def set_frame_overlap(self, on): self._call("set_frame_overlap", int(on))
+    def set_frame_pipelining(self, on): self._call("set_frame_pipelining", int(on))
 
     def tex_peak(self, mode=0):
         v = C.c_double()

@@ -110,6 +110,51 @@ int ensure_stage(SkyContext* ctx) {
 
 extern "C" {
 
+// The two bake LUTs (Atmosphere.cpp:11-18) of the CURRENT set + the RGBA16F copies K6 fetches through the texture unit
+static int alloc_bake_luts(SkyContext* ctx) {
+    int rc = 0;
+    rc |= sky_alloc(ctx, ctx->transmittance, 256, 64);   // Atmosphere.cpp:11-12
+    rc |= sky_alloc(ctx, ctx->multiscattering, 32, 32);  // Atmosphere.cpp:17-18
+    rc |= sky_alloc(ctx, ctx->transmittance_h, 256, 64);
+    rc |= sky_alloc(ctx, ctx->multiscattering_h, 32, 32);
+    if (rc) return rc;
+    // GL_LINEAR + CLAMP_TO_EDGE texture views (Samplers.cpp linear_clamp_no_mipmap) over the RGBA16F copies
+    auto make_tex = [](const Lut<half4>& l, cudaTextureObject_t* out) {
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypePitch2D;
+        res.res.pitch2D.devPtr = l.p;
+        res.res.pitch2D.desc = cudaCreateChannelDescHalf4();
+        res.res.pitch2D.width = size_t(l.w);
+        res.res.pitch2D.height = size_t(l.h);
+        res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(half4);
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 1;
+        return cudaCreateTextureObject(out, &res, &td, nullptr) == cudaSuccess ? 0 : 1;
+    };
+    rc |= make_tex(ctx->transmittance_h, &ctx->transmittance_tex);
+    rc |= make_tex(ctx->multiscattering_h, &ctx->multiscattering_tex);
+    return rc;
+}
+
+// current LUT set <-> alternate LUT set (frame pipelining)
+static void swap_lut_sets(SkyContext* ctx) {
+    SkyContext::LutSet& a = ctx->alt;
+    std::swap(ctx->transmittance, a.transmittance); std::swap(ctx->multiscattering, a.multiscattering);
+    std::swap(ctx->sky_lum, a.sky_lum); std::swap(ctx->sky_trans, a.sky_trans);
+    std::swap(ctx->ap_lum, a.ap_lum); std::swap(ctx->ap_trans, a.ap_trans);
+    std::swap(ctx->env, a.env); std::swap(ctx->transmittance_h, a.transmittance_h); std::swap(ctx->multiscattering_h, a.multiscattering_h);
+    std::swap(ctx->transmittance_tex, a.transmittance_tex); std::swap(ctx->multiscattering_tex, a.multiscattering_tex);
+    std::swap(ctx->sky_lum_tex, a.sky_lum_tex); std::swap(ctx->sky_trans_tex, a.sky_trans_tex);
+    std::swap(ctx->ap_lum_tex, a.ap_lum_tex); std::swap(ctx->ap_trans_tex, a.ap_trans_tex);
+    for (int i = 0; i < 4; ++i) {
+        std::swap(ctx->lut_tex_key[i], a.lut_tex_key[i]);
+        for (int k = 0; k < 3; ++k) std::swap(ctx->lut_tex_dims[i][k], a.lut_tex_dims[i][k]);
+    }
+}
+
 int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     *out = nullptr;
     int count = 0;
@@ -123,32 +168,7 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     int rc = 0;
-    rc |= sky_alloc(ctx, ctx->transmittance, 256, 64);   // Atmosphere.cpp:11-12
-    rc |= sky_alloc(ctx, ctx->multiscattering, 32, 32);  // Atmosphere.cpp:17-18
-    if (!rc) {
-        // GL_LINEAR + CLAMP_TO_EDGE texture views (Samplers.cpp linear_clamp_no_mipmap) over RGBA16F copies of the two LUTs
-        rc |= sky_alloc(ctx, ctx->transmittance_h, 256, 64);
-        rc |= sky_alloc(ctx, ctx->multiscattering_h, 32, 32);
-        auto make_tex = [](const Lut<half4>& l, cudaTextureObject_t* out) {
-            cudaResourceDesc res{};
-            res.resType = cudaResourceTypePitch2D;
-            res.res.pitch2D.devPtr = l.p;
-            res.res.pitch2D.desc = cudaCreateChannelDescHalf4();
-            res.res.pitch2D.width = size_t(l.w);
-            res.res.pitch2D.height = size_t(l.h);
-            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(half4);
-            cudaTextureDesc td{};
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModeLinear;
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 1;
-            return cudaCreateTextureObject(out, &res, &td, nullptr) == cudaSuccess ? 0 : 1;
-        };
-        if (!rc) {
-            rc |= make_tex(ctx->transmittance_h, &ctx->transmittance_tex);
-            rc |= make_tex(ctx->multiscattering_h, &ctx->multiscattering_tex);
-        }
-    }
+    rc |= alloc_bake_luts(ctx);
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);  // VolumetricCloud.cpp:52,102-105
     if (cudaMalloc(&ctx->blue_noise, 64 * 64 * sizeof(uint16_t)) != cudaSuccess) rc = 1;
     if (cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) rc = 1;
@@ -180,7 +200,13 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
     if (ctx->blue_noise) cudaFree(ctx->blue_noise);
     if (ctx->lane2) { cudaStreamSynchronize(ctx->lane2); cudaStreamDestroy(ctx->lane2); }
-    for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2, ctx->ev_frame_mark[0], ctx->ev_frame_mark[1], ctx->ev_luts_ready}) if (ev) cudaEventDestroy(ev);
+    if (ctx->lut_stream) { cudaStreamSynchronize(ctx->lut_stream); cudaStreamDestroy(ctx->lut_stream); }
+    swap_lut_sets(ctx);  // free the alternate set through the same path
+    free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->transmittance); free_lut(ctx->multiscattering);
+    free_lut(ctx->sky_lum); free_lut(ctx->sky_trans); free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
+    for (cudaTextureObject_t t : {ctx->transmittance_tex, ctx->multiscattering_tex, ctx->sky_lum_tex, ctx->sky_trans_tex, ctx->ap_lum_tex, ctx->ap_trans_tex}) if (t) cudaDestroyTextureObject(t);
+    swap_lut_sets(ctx);
     if (ctx->transmittance_tex) cudaDestroyTextureObject(ctx->transmittance_tex);
     if (ctx->multiscattering_tex) cudaDestroyTextureObject(ctx->multiscattering_tex);
     for (cudaTextureObject_t t : {ctx->sky_lum_tex, ctx->sky_trans_tex, ctx->ap_lum_tex, ctx->ap_trans_tex}) if (t) cudaDestroyTextureObject(t);
@@ -208,7 +234,15 @@ struct LaneScope {  // launchers issue on ctx->stream: point it at lane2 for the
     LaneScope(SkyContext* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
     ~LaneScope() { ctx->stream = saved; }
 };
-int lanes_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lane2
+int luts_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lut_stream (frame pipelining)
+    if (!ctx->luts_pending) return 0;
+    SKY_CUDA(ctx, cudaEventRecord(ctx->ev_luts_ready, ctx->lut_stream));
+    SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_luts_ready, 0));
+    ctx->luts_pending = false;
+    return 0;
+}
+int lanes_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lane2 (and on lut_stream)
+    if (int e = luts_join(ctx)) return e;
     if (!ctx->lane2_pending) return 0;
     SKY_CUDA(ctx, cudaEventRecord(ctx->ev_lane2, ctx->lane2));
     SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_lane2, 0));
@@ -230,6 +264,32 @@ int sky_set_frame_overlap(SkyContext* ctx, int enable) {
             SKY_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
     ctx->overlap = enable != 0;
+    return 0;
+}
+
+// ---- frame pipelining -------------------------------------------------------------------------------------------
+// Per frame the atmosphere LUT phase (K1, K2, K3+K4, K5: ~0.35 ms of small, latency-bound kernels) must finish before either
+// full-machine kernel of the frame (K6, K16) can start, and nothing else is runnable meanwhile.  With pipelining enabled the
+// context owns TWO LUT sets: sky_atmosphere_bake flips to the set the frame before last used and issues the LUT phase on
+// `lut_stream`, where it runs beside the PREVIOUS frame's K6 / K16 (which read the other set); the caller's stream waits for
+// it only where the LUTs are first read.  Same kernels, same inputs, same results (the sets are independent copies).
+int sky_set_frame_pipelining(SkyContext* ctx, int enable) {
+    if (int e = lanes_join(ctx)) return e;
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (enable && !ctx->lut_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        SKY_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->lut_stream, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t* ev : {&ctx->ev_frame_mark[0], &ctx->ev_frame_mark[1], &ctx->ev_luts_ready})
+            SKY_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        swap_lut_sets(ctx);                       // allocate the bake LUTs of the second set
+        int rc = alloc_bake_luts(ctx);
+        swap_lut_sets(ctx);
+        if (rc) return sky_fail(ctx, "device allocation failed");
+        SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->pipelining = enable != 0;
+    ctx->mark_count = 0;
     return 0;
 }
 
@@ -289,6 +349,21 @@ int sky_set_viewport(SkyContext* ctx, int w, int h) {
 }
 
 int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
+    if (ctx->pipelining) {
+        // everything queued on the caller's stream before this call -- i.e. all of the previous frame, whose lane2 work was
+        // joined at its cloud_frame_end -- precedes mark[n]; the set this bake flips to was last read one frame earlier,
+        // i.e. before mark[n-1], recorded at the previous bake
+        const int n = ctx->mark_count & 1;
+        SKY_CUDA(ctx, cudaEventRecord(ctx->ev_frame_mark[n], ctx->stream));
+        swap_lut_sets(ctx);
+        if (ctx->mark_count >= 1) SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->ev_frame_mark[n ^ 1], 0));
+        else SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->ev_frame_mark[n], 0));
+        ++ctx->mark_count;
+        ctx->atm = *a;
+        ctx->luts_pending = true;
+        LaneScope lane(ctx, ctx->lut_stream);
+        return launch_atmosphere_bake(ctx);
+    }
     if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }
     ctx->atm = *a;
     return launch_atmosphere_bake(ctx);
@@ -297,7 +372,7 @@ int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
 int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg) {
     if (cfg->sky_view_width < 2 || cfg->sky_view_height < 2 || cfg->aerial_perspective_depth < 2 || cfg->environment_size < 1)
         return sky_fail(ctx, "bad LUT sizes");
-    if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }  // (the shadow chain on lane2 does not touch the LUTs)
+    if (!ctx->pipelining && ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }  // (the shadow chain on lane2 does not touch the LUTs)
     ctx->render = *r;
     ctx->lut_cfg = *cfg;
     int rc = 0;
@@ -331,11 +406,17 @@ int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
             ctx->lut_tex_key[i] = l.p; ctx->lut_tex_dims[i][0] = l.w; ctx->lut_tex_dims[i][1] = l.h; ctx->lut_tex_dims[i][2] = l.d;
         }
     }
+    if (ctx->pipelining) {  // follows this frame's bake on lut_stream
+        ctx->luts_pending = true;
+        LaneScope lane(ctx, ctx->lut_stream);
+        return launch_atmosphere_luts(ctx);
+    }
     return launch_atmosphere_luts(ctx);
 }
 
 int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
     if (!ctx->sky_lum.p) return sky_fail(ctx, "atmosphere LUTs have not been baked");
+    if (int e = luts_join(ctx)) return e;
     if (ctx->overlap) {
         if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }  // out-of-order use: a cloud frame is still open
         if (ctx->shadow_pending) {  // K6 reads the god-ray froxels
@@ -394,6 +475,7 @@ int sky_cloud_frame_begin(SkyContext* ctx, const SkyCloudCommonBufferData* commo
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (band_count < 1 || band_index < 0 || band_index >= band_count || band_rows < 0) return sky_fail(ctx, "bad band arguments");
     ctx->last_common = *common;  // cloud_frame_end runs K17/K18 with the same uniforms
+    if (int e = luts_join(ctx)) return e;
     if (!ctx->overlap) return (ctx->strict_arithmetic ? launch_cloud_begin_strict : launch_cloud_begin)(ctx, *common, *cloud, depth, band_rows, band_index, band_count);
     // K14-K16 need the depth and the LUTs from the caller's stream -- complete before the composite if there was one --
     // and the froxels, which are on lane2 already

@@ -68,6 +68,21 @@ struct SkyContext {
     const float* pre_composite_depth = nullptr;
     bool lane2_reads_luts = false;     // K16 / K17 are queued on lane2
 
+    // frame pipelining (sky_set_frame_pipelining): the atmosphere LUT phase of frame N+1 (K1-K5) runs on `lut_stream` into the
+    // OTHER of two LUT sets while frame N's full-machine kernels (K6, K16) still read theirs, see api.cu
+    bool pipelining = false;
+    cudaStream_t lut_stream = nullptr;
+    cudaEvent_t ev_frame_mark[2] = {nullptr, nullptr}, ev_luts_ready = nullptr;
+    int mark_count = 0;                // bake calls since pipelining was enabled
+    bool luts_pending = false;         // lut_stream holds work the caller's stream has not been ordered after
+    struct LutSet {                    // the alternate copy of everything sky_atmosphere_bake / sky_atmosphere_luts write
+        Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
+        Lut<half4> env, transmittance_h, multiscattering_h;
+        cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0, sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
+        const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
+        int lut_tex_dims[4][3] = {};
+    } alt;
+
     // uniforms last seen
     SkyAtmosphereBufferData atm{};
     SkyAtmosphereRenderBufferData render{};

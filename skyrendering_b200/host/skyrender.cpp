@@ -2,7 +2,7 @@
 // AppWindow::HandleDisplayEvent / Render do per frame (src/SkyRendering/AppWindow.cpp:139-181), without a window.
 //
 //   skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file.vdb] [--raw8 file dx dy dz]
-//             [--hw-filtering] [--strict] [--overlap] [--out image.ppm] [--dump-rgba8 file]
+//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--out image.ppm] [--dump-rgba8 file]
 //
 // The scene JSON is the reference's own config format (bin/config*.json); the host library deserialises it with the
 // reference's defaults and computes every uniform block; the CUDA library renders.  There is no Python and no CPU fallback in
@@ -103,13 +103,13 @@ struct Driver {
 
 int main(int argc, char** argv) {
     if (argc < 4) die("usage: skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file] [--raw8 file dx dy dz] "
-                      "[--hw-filtering] [--strict] [--overlap] [--out image.ppm] [--dump-rgba8 file]");
+                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--out image.ppm] [--dump-rgba8 file]");
     const std::string scene_path = argv[1];
     Driver d;
     d.width = std::atoi(argv[2]);
     d.height = std::atoi(argv[3]);
     int frames = 8, warmup = 8, spp = 0, raw_dim[3] = {0, 0, 0};
-    bool hw = false, strict = false, overlap = false;
+    bool hw = false, strict = false, overlap = false, pipeline = false;
     std::string out_ppm, dump_rgba8, vdb_path, raw8_path, data_dir;
     for (int i = 4; i < argc; ++i) {
         std::string a = argv[i];
@@ -122,6 +122,7 @@ int main(int argc, char** argv) {
         else if (a == "--hw-filtering") hw = true;
         else if (a == "--strict") strict = true;
         else if (a == "--overlap") overlap = true;
+        else if (a == "--pipeline") pipeline = true;
         else if (a == "--out") out_ppm = next();
         else if (a == "--dump-rgba8") dump_rgba8 = next();
         else if (a == "--data") data_dir = next();
@@ -186,6 +187,7 @@ int main(int argc, char** argv) {
     d.earth_update();
     d.atmosphere_luts();
     sky_ok(sky_set_frame_overlap(d.ctx, overlap), "set_frame_overlap");
+    sky_ok(sky_set_frame_pipelining(d.ctx, pipeline), "set_frame_pipelining");
 
     cudaEvent_t e0, e1;
     cuda_ok(cudaEventCreate(&e0), "cudaEventCreate");

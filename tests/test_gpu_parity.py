@@ -351,6 +351,35 @@ def test_frame_overlap_is_bit_identical(libs, scene):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("scene,overlap", [("c3", True), ("c3", False), ("c1", True)])
+def test_frame_pipelining_is_bit_identical(libs, scene, overlap):
+    """sky_set_frame_pipelining: the LUT phase of frame N+1 runs into the second LUT set beside frame N's K6 / K16.  Same kernels,
+    same inputs: every buffer of every frame is bit-identical to the serial run, with a moving camera (the LUTs change per frame)."""
+    cuda, _ = libs
+    w, h = 480, 270
+    outs = []
+    for pipelined in (False, True):
+        r = Renderer(scene, w, h, library=cuda)
+        r.prime()
+        r.ctx.set_frame_overlap(overlap)
+        r.ctx.set_frame_pipelining(pipelined)
+        frames = []
+        for f in range(6):
+            if f:
+                r.scene.camera_move((0.03, 0.01, 0.02))
+            depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), "cuda")
+            r.frame(depth, hdr, 0.0)
+            frames.append(hdr)      # no synchronisation between frames: they are in flight together
+        r.ctx.sync()
+        outs.append([to_numpy(x).copy() for x in frames] + [r.ctx.read(res) for res in (abi.RES_SKY_VIEW_LUMINANCE, abi.RES_AERIAL_LUMINANCE, abi.RES_TRANSMITTANCE,
+                                                                                         abi.RES_ENVIRONMENT, abi.RES_RECONSTRUCT, abi.RES_SHADOW_FROXEL)])
+        r.ctx.set_frame_pipelining(False)
+        r.ctx.set_frame_overlap(False)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert not np.array_equal(outs[0][0], outs[0][5])   # the camera moved
+
+
 def test_banded_render_equals_full_and_is_deterministic(libs):
     cuda, _ = libs
     w, h = 768, 432
