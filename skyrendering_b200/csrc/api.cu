@@ -200,7 +200,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
     if (ctx->blue_noise) cudaFree(ctx->blue_noise);
     if (ctx->lane2) { cudaStreamSynchronize(ctx->lane2); cudaStreamDestroy(ctx->lane2); }
-    for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2, ctx->ev_frame_mark[0], ctx->ev_frame_mark[1], ctx->ev_luts_ready}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2, ctx->ev_frame_mark[0], ctx->ev_frame_mark[1], ctx->ev_luts_ready, ctx->ev_main_to_lut}) if (ev) cudaEventDestroy(ev);
+    free_lut(ctx->alt.shadow_froxel);
     if (ctx->lut_stream) { cudaStreamSynchronize(ctx->lut_stream); cudaStreamDestroy(ctx->lut_stream); }
     swap_lut_sets(ctx);  // free the alternate set through the same path
     free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->transmittance); free_lut(ctx->multiscattering);
@@ -239,6 +240,12 @@ int luts_join(SkyContext* ctx) {  // the caller's stream is ordered after everyt
     SKY_CUDA(ctx, cudaEventRecord(ctx->ev_luts_ready, ctx->lut_stream));
     SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_luts_ready, 0));
     ctx->luts_pending = false;
+    return 0;
+}
+int lut_stream_follow_main(SkyContext* ctx) {  // lut_stream is ordered after everything queued on the caller's stream so far
+    if (!ctx->pipelining) return 0;
+    SKY_CUDA(ctx, cudaEventRecord(ctx->ev_main_to_lut, ctx->stream));
+    SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->ev_main_to_lut, 0));
     return 0;
 }
 int lanes_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lane2 (and on lut_stream)
@@ -280,7 +287,7 @@ int sky_set_frame_pipelining(SkyContext* ctx, int enable) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         SKY_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->lut_stream, cudaStreamNonBlocking, hi));
-        for (cudaEvent_t* ev : {&ctx->ev_frame_mark[0], &ctx->ev_frame_mark[1], &ctx->ev_luts_ready})
+        for (cudaEvent_t* ev : {&ctx->ev_frame_mark[0], &ctx->ev_frame_mark[1], &ctx->ev_luts_ready, &ctx->ev_main_to_lut})
             SKY_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         swap_lut_sets(ctx);                       // allocate the bake LUTs of the second set
         int rc = alloc_bake_luts(ctx);
@@ -345,6 +352,7 @@ int sky_set_viewport(SkyContext* ctx, int w, int h) {
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);
     free_lut(ctx->pt_accum);
     free_lut(ctx->pt_mask);
+    if (int e = lut_stream_follow_main(ctx)) return e;  // the zero-filled shadow maps are inputs of the shadow chain
     return rc;
 }
 
@@ -361,6 +369,7 @@ int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
         ++ctx->mark_count;
         ctx->atm = *a;
         ctx->luts_pending = true;
+        ctx->bake_since_shadow = true;
         LaneScope lane(ctx, ctx->lut_stream);
         return launch_atmosphere_bake(ctx);
     }
@@ -433,7 +442,8 @@ int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int
 
 int sky_noise_generate(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info) {
     if (int e = lanes_join(ctx)) return e;
-    return launch_noise(ctx, kind, info);
+    if (int e = launch_noise(ctx, kind, info)) return e;
+    return lut_stream_follow_main(ctx);  // the material textures are inputs of the shadow chain
 }
 
 int sky_voxel_upload(SkyContext* ctx, const uint8_t* host_voxels, int dx, int dy, int dz) {
@@ -456,6 +466,25 @@ int sky_set_material(SkyContext* ctx, const SkyMaterialBlock* m) {
 
 int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");  // VolumetricCloud.cpp:169-170
+    if (ctx->pipelining) {
+        // K11-K13 read nothing a frame in flight writes except their own shadow maps (same stream) and write the froxels, which
+        // K6 / K16 of the frame in flight still read: they go to the second froxel volume, on lut_stream after this frame's bake
+        Lut<uint16_t>& other = ctx->alt.shadow_froxel;
+        if (other.w != ctx->shadow_froxel.w || other.h != ctx->shadow_froxel.h || other.d != ctx->shadow_froxel.d) {
+            if (int e = sky_alloc(ctx, other, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d)) return e;
+            ctx->bake_since_shadow = false;
+        }
+        if (!ctx->bake_since_shadow) {  // out-of-protocol call (no bake since the last shadow pass): order conservatively
+            if (int e = lanes_join(ctx)) return e;
+            if (int e = lut_stream_follow_main(ctx)) return e;
+        }
+        ctx->bake_since_shadow = false;
+        std::swap(ctx->shadow_froxel, other);
+        ctx->pre_composite_recorded = false;  // a new frame
+        ctx->luts_pending = true;
+        LaneScope lane(ctx, ctx->lut_stream);
+        return (ctx->strict_arithmetic ? launch_cloud_shadow_strict : launch_cloud_shadow)(ctx, *common);
+    }
     if (!ctx->overlap) return (ctx->strict_arithmetic ? launch_cloud_shadow_strict : launch_cloud_shadow)(ctx, *common);
     if (int e = lanes_join(ctx)) return e;
     ctx->pre_composite_recorded = false;  // a new frame

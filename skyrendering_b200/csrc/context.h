@@ -75,9 +75,12 @@ struct SkyContext {
     cudaEvent_t ev_frame_mark[2] = {nullptr, nullptr}, ev_luts_ready = nullptr;
     int mark_count = 0;                // bake calls since pipelining was enabled
     bool luts_pending = false;         // lut_stream holds work the caller's stream has not been ordered after
+    bool bake_since_shadow = false;    // this frame's bake already ordered lut_stream after the frame before last
+    cudaEvent_t ev_main_to_lut = nullptr;
     struct LutSet {                    // the alternate copy of everything sky_atmosphere_bake / sky_atmosphere_luts write
         Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
         Lut<half4> env, transmittance_h, multiscattering_h;
+        Lut<uint16_t> shadow_froxel;   // second froxel volume: the shadow chain of frame N+1 also runs on lut_stream
         cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0, sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
         const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
         int lut_tex_dims[4][3] = {};
