@@ -342,7 +342,9 @@ def main():
         depth_np = rf.scene.ground_depth(FRAME_W, FRAME_H)
         depth = torch.from_numpy(depth_np).cuda()
         hdr = torch.zeros((FRAME_H, FRAME_W, 4), dtype=torch.float16, device="cuda")
-        scf = ShardedCloudFrame(rf, rank, world, band_rows=8)
+        # N > 1: K16 in quarter-res row bands (fused peer exchange) and the two full-res passes K6 / K18 in full-res row bands,
+        # then one all-gather of the HDR rows: every rank ends with the whole frame
+        scf = ShardedCloudFrame(rf, rank, world, band_rows=8, shard_output=True)
         state = {}
 
         def frame_step():
@@ -350,7 +352,7 @@ def main():
             common, cloud, _ = rf.cloud_update(0.0)
             rf.ctx.cloud_shadow(common)
             rf.atmosphere_render_luts()
-            rf.ctx.composite(depth, hdr, FRAME_W, FRAME_H)
+            scf.composite(depth, hdr)
             scf.frame(common, cloud, depth, hdr)
             state["u"] = (common, cloud)
 

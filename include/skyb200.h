@@ -94,6 +94,12 @@ int SKY_FN(cloud_frame_begin)(SkyContext* ctx, const SkyCloudCommonBufferData* c
                               int band_rows, int band_index, int band_count);
 int SKY_FN(cloud_frame_end)(SkyContext* ctx, const float* depth_dev, void* hdr_dev);
 
+/* Row bands of the FULL-RES passes of a tile-sharded frame: with band_count > 1 the composite (K6) and the
+ * upscale (K18) only touch full-res rows r with (r / band_rows) % band_count == band_index (band_rows a multiple of 8); K17 and
+ * everything else stay complete.  Every pixel of those rows is exactly what the unsharded frame computes; the caller gathers
+ * the HDR rows of the ranks (skyrendering_b200/distributed.py).  band_count <= 1 restores whole frames. */
+int SKY_FN(set_output_bands)(SkyContext* ctx, int band_rows, int band_index, int band_count);
+
 /* Tile-sharded K16 fused with its exchange over peer memory (NVLink / NVSwitch), one process per GPU.
  * sky_peer_export fills the CUDA IPC handles of this context's K16 outputs and of its arrival flags;
  * the host exchanges them (any transport) and hands all ranks' handles to sky_peer_attach.  From then

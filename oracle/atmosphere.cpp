@@ -186,6 +186,7 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
 #pragma omp parallel for schedule(dynamic)
     for (int py = 0; py < height; ++py)
         for (int px = 0; px < width; ++px) {
+            if (out_band_count > 1 && (py / out_band_rows) % out_band_count != out_band_index) continue;  // sky_set_output_bands
             vec2 vTexCoord((float(px) + 0.5f) / float(width), (float(py) + 0.5f) / float(height));
             float depth = depth_img[size_t(py) * width + px];
             vec3 fragment_position = ProjectiveMul(inv_view_projection, vec3(vTexCoord, depth) * 2.0f - 1.0f);

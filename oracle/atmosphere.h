@@ -321,6 +321,7 @@ struct AtmosphereRenderer {
     const Image<4>& transmittance_texture;
     const Image<4>& multiscattering_texture;
     const Image<1>* blue_noise = nullptr;  // R16 64x64
+    int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: rows the composite owns
     const Image<4>* star_map = nullptr;  // GL_SRGB8 star map decoded to linear RGB (Textures.cpp:43-50); null: no star term
     const Image<1>* mesh_shadow_map = nullptr;  // DEPTH32F 2048^2 (ShadowMap.cpp:8-27), used when cfg.volumetric_light
 

@@ -517,6 +517,7 @@ void CloudScene::Upscale(const float* depth_img, uint16_t* hdr) {
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < height; ++y)
         for (int x = 0; x < width; ++x) {
+            if (!owns_row(y)) continue;  // sky_set_output_bands
             ivec2 pos(x, y);
             float depth = depth_img[size_t(y) * width + x];
             float linear_depth = DepthToLinearDepth(depth);

@@ -23,6 +23,8 @@ struct CloudScene {
     SkyLutConfig lut_cfg{};
 
     Image<1> blue_noise;  // 64x64, u16/65535 (Textures.cpp:19-26)
+    int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: full-res rows K6 / K18 own
+    bool owns_row(int y) const { return out_band_count <= 1 || (y / out_band_rows) % out_band_count == out_band_index; }
     Image<4> star_map;         // decoded (linear) star map, empty when none was set (Textures.cpp:43-50)
     Image<1> mesh_shadow_map;  // 2048x2048 light-space depth (ShadowMap.cpp:8-27), allocated on first use, cleared to 1
 

@@ -136,6 +136,7 @@ int orc_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int
     AtmosphereRenderer ar{s.atm, s.render_u, s.lut_cfg, s.transmittance, s.multiscattering, &s.blue_noise};
     if (s.lut_cfg.volumetric_light) ar.mesh_shadow_map = &mesh_shadow_map(s);
     if (s.star_map.w > 0) ar.star_map = &s.star_map;
+    ar.out_band_rows = s.out_band_rows; ar.out_band_index = s.out_band_index; ar.out_band_count = s.out_band_count;
     const Image<1>* froxel = (s.shadow_froxel.w > 0) ? &s.shadow_froxel : nullptr;
     ar.Composite(s.sky_lum, s.sky_trans, s.ap_lum, s.ap_trans, froxel, depth, width, height, static_cast<uint16_t*>(hdr));
     return 0;
@@ -378,6 +379,13 @@ int orc_peer_detach(SkyContext*) { return 0; }
 int orc_pt_set_tracking(SkyContext* ctx, int mode) { return mode == SKY_PT_TRACKING_REFERENCE ? 0 : fail(ctx, "the oracle only implements the reference's tracking"); }
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
 int orc_set_strict_arithmetic(SkyContext*, int) { return 0; }  // the oracle IS the strict arithmetic
+int orc_set_output_bands(SkyContext* ctx, int band_rows, int band_index, int band_count) {
+    CloudScene& s = ctx->scene;
+    if (band_count <= 1) { s.out_band_rows = 0; s.out_band_index = 0; s.out_band_count = 1; return 0; }
+    if (band_rows < 8 || band_rows % 8 != 0 || band_index < 0 || band_index >= band_count) return fail(ctx, "set_output_bands: band_rows must be a positive multiple of 8 and 0 <= band_index < band_count");
+    s.out_band_rows = band_rows; s.out_band_index = band_index; s.out_band_count = band_count;
+    return 0;
+}
 int orc_set_frame_overlap(SkyContext*, int) { return 0; }
 int orc_set_frame_pipelining(SkyContext*, int) { return 0; }
 int orc_tex_peak(SkyContext* ctx, int, double*) { return fail(ctx, "tex_peak is a GPU microbenchmark"); }

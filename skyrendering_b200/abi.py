@@ -198,6 +198,7 @@ KERNEL_API = {
     "set_strict_arithmetic": ([I], I),
     "set_frame_overlap": ([I], I),
     "set_frame_pipelining": ([I], I),
+    "set_output_bands": ([I, I, I], I),
     "tex_peak": ([I, P(C.c_double)], I),
 }
 
@@ -273,6 +274,7 @@ class Context:
             raise SkyError(f"{library.prefix}ctx_create failed (rc={rc}); is a CUDA device visible?")
         self.h = h
         self.device = device
+        self.stream = int(stream)   # the CUDA stream all work is issued on (0: the legacy default stream)
 
     def close(self):
         if self.h:
@@ -358,6 +360,7 @@ class Context:
     def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))
     def set_frame_overlap(self, on): self._call("set_frame_overlap", int(on))
     def set_frame_pipelining(self, on): self._call("set_frame_pipelining", int(on))
+    def set_output_bands(self, band_rows, band_index, band_count): self._call("set_output_bands", int(band_rows), int(band_index), int(band_count))
 
     def tex_peak(self, mode=0):
         v = C.c_double()

@@ -701,6 +701,14 @@ int sky_counters_enable(SkyContext* ctx, int enable) {
     return 0;
 }
 
+int sky_set_output_bands(SkyContext* ctx, int band_rows, int band_index, int band_count) {
+    if (!ctx) return 1;
+    if (band_count <= 1) { ctx->out_band_rows = 0; ctx->out_band_index = 0; ctx->out_band_count = 1; return 0; }
+    if (band_rows < 8 || band_rows % 8 != 0 || band_index < 0 || band_index >= band_count) return sky_fail(ctx, "set_output_bands: band_rows must be a positive multiple of 8 and 0 <= band_index < band_count");
+    ctx->out_band_rows = band_rows; ctx->out_band_index = band_index; ctx->out_band_count = band_count;
+    return 0;
+}
+
 int sky_pt_set_tracking(SkyContext* ctx, int mode) {
     if (!ctx) return 1;
     if (mode != SKY_PT_TRACKING_REFERENCE && mode != SKY_PT_TRACKING_MAJORANT_GRID) return sky_fail(ctx, "pt_set_tracking: unknown mode");

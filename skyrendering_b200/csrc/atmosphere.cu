@@ -335,6 +335,7 @@ struct RenderParams {
     const float* depth;
     half4* hdr;
     int width, height;
+    int band_rows, band_index, band_count;  // sky_set_output_bands: blockIdx.y counts OWNED rows (band_count <= 1: all rows)
 };
 
 // AtmosphereRenderer.glsl:56-72
@@ -526,7 +527,8 @@ __global__ void __launch_bounds__(128) k5_environment(const __grid_constant__ Re
 template <bool EXTRA>
 __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
-    if (px >= P.width) return;
+    if (P.band_count > 1) py = ((py / P.band_rows) * P.band_count + P.band_index) * P.band_rows + py % P.band_rows;
+    if (px >= P.width || py >= P.height) return;
     float2 vTexCoord = f2((float(px) + 0.5f) / float(P.width), (float(py) + 0.5f) / float(P.height));
     float depth = __ldg(P.depth + size_t(py) * P.width + px);
     float3 camera_position = f3(P.r.camera_position);
@@ -718,8 +720,11 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
     if (ctx->lut_cfg.volumetric_light) { if (int e = ensure_mesh_shadow_map(ctx)) return e; }
     RenderParams P = make_render_params(ctx);
     P.depth = depth; P.hdr = hdr; P.width = w; P.height = h;
-    if (P.cfg.moon_shadow || P.cfg.volumetric_light) k6_composite<true><<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
-    else k6_composite<false><<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
+    P.band_rows = ctx->out_band_rows; P.band_index = ctx->out_band_index; P.band_count = ctx->out_band_count;
+    const int rows = owned_rows(ctx, h);
+    if (rows <= 0) return 0;
+    if (P.cfg.moon_shadow || P.cfg.volumetric_light) k6_composite<true><<<dim3(ceil_div(w, 256), rows), 256, 0, ctx->stream>>>(P);
+    else k6_composite<false><<<dim3(ceil_div(w, 256), rows), 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
 }

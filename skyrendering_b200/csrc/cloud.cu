@@ -48,6 +48,7 @@ struct CloudParams {
     // shadow chain
     const float2* shadow_prev;  // pre_raw_cloud_shadow_map
     float2* shadow_out;
+    int out_band_rows, out_band_index, out_band_count;  // sky_set_output_bands (K18)
     const float2* shadow_blurred;
     uint16_t* froxel_out;
     int shadow_w, shadow_h;
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(256) k18_upscale(const __grid_constant__ Cloud
     const SkyCloudCommonBufferData& c = P.c;
     const int HW_ = P.width / 2, HH = P.height / 2;
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (P.out_band_count > 1) y = ((y / P.out_band_rows) * P.out_band_count + P.out_band_index) * P.out_band_rows + y % P.out_band_rows;  // owned rows (multiples of 8)
     if (x >= P.width || y >= P.height) return;
     float depth = __ldg(P.depth + size_t(y) * P.width + x);
     float linear_depth = DepthToLinearDepth(c, depth);
@@ -889,7 +891,9 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
         SKY_LAUNCH_CHECK(ctx);
     }
     if (phases & 2) {
-        k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(P.height, 8)), 256, 0, ctx->stream>>>(P);
+        P.out_band_rows = ctx->out_band_rows; P.out_band_index = ctx->out_band_index; P.out_band_count = ctx->out_band_count;
+        const int rows = owned_rows(ctx, P.height);
+        if (rows > 0) k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(rows, 8)), 256, 0, ctx->stream>>>(P);
         SKY_LAUNCH_CHECK(ctx);
         std::swap(ctx->reconstruct[0], ctx->reconstruct[1]);  // VolumetricCloud.cpp:421-422
     }

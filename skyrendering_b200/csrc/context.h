@@ -1,6 +1,7 @@
 // SkyContext: everything one GL context owned in the reference (Atmosphere.h:84-91,
 // AtmosphereRenderer.h:118-128, VolumetricCloud.h:99-128), as device allocations on one GPU.
 #pragma once
+#include <algorithm>
 #include <string>
 
 #include "common.cuh"
@@ -57,6 +58,7 @@ struct SkyContext {
     bool hw_filtering = false;
     bool strict_arithmetic = false;  // sky_set_strict_arithmetic: route K6, K11-K18, K19/K20 to the *_strict objects
     bool counting = false;
+    int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: rows K6 / K18 own
 
     // frame overlap (sky_set_frame_overlap): second lane of a frame, see api.cu
     bool overlap = false;
@@ -185,6 +187,13 @@ int sky_alloc(SkyContext* ctx, Lut<T>& l, int w, int h, int d = 1, bool zero = t
 
 // per-subsystem launchers (defined in the .cu files) -----------------------------------------------------------
 int ensure_mesh_shadow_map(SkyContext* ctx);                                   // api.cu
+// rows of a height-h image owned under sky_set_output_bands, and the n-th owned row
+inline int owned_rows(const SkyContext* ctx, int h) {
+    if (ctx->out_band_count <= 1) return h;
+    int n = 0;
+    for (int r0 = ctx->out_band_index * ctx->out_band_rows; r0 < h; r0 += ctx->out_band_rows * ctx->out_band_count) n += std::min(ctx->out_band_rows, h - r0);
+    return n;
+}
 int launch_lut_half_copies(SkyContext* ctx);                                  // atmosphere.cu
 int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
 int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5

@@ -94,8 +94,18 @@ class ShardedPathTracer:
 class ShardedCloudFrame:
     """Tile-sharded K16 with an all-gather of its two outputs; everything else replicated."""
 
-    def __init__(self, renderer, rank, world_size, band_rows=8, group=None, fused=None):
+    def __init__(self, renderer, rank, world_size, band_rows=8, group=None, fused=None, shard_output=False, output_band_rows=8):
+        """shard_output: the two FULL-RES passes are sharded too -- K6 (through `composite`) and K18 only touch this rank's
+        row bands (sky_set_output_bands) and `frame` ends with an all-gather of the HDR rows, so every rank ends with the
+        complete frame.  K6 is the largest kernel of a frame; without this only K16 shrinks with the number of GPUs."""
         self.r, self.rank, self.world, self.band_rows, self.group = renderer, rank, world_size, band_rows, group
+        self.shard_output = bool(shard_output) and world_size > 1
+        self.output_band_rows = output_band_rows
+        if self.shard_output:
+            self.out_rows = [band_rows_of_rank(renderer.height, output_band_rows, k, world_size) for k in range(world_size)]
+            self.max_out_rows = max(len(x) for x in self.out_rows)
+            renderer.ctx.set_output_bands(output_band_rows, rank, world_size)
+            self._hdr_io = None
         qh = renderer.height // 4
         self.rows = [band_rows_of_rank(qh, band_rows, k, world_size) for k in range(world_size)]
         self.max_rows = max(len(x) for x in self.rows)
@@ -110,6 +120,38 @@ class ShardedCloudFrame:
             renderer.ctx.peer_attach(rank, world_size, everyone)
             dist.barrier(group=group)
 
+    def composite(self, depth, hdr):
+        """K6 over this rank's row bands (all rows unless shard_output)."""
+        self.r.ctx.composite(depth, hdr, self.r.width, self.r.height)
+
+    def gather_output(self, hdr):
+        """all-gather of the HDR row bands: every rank ends with the whole frame.  hdr: half4 [H][W] (torch tensor on the
+        library's device, or a numpy array for the CPU tests)."""
+        import torch
+        import torch.distributed as dist
+        ctx = self.r.ctx
+        is_numpy = isinstance(hdr, np.ndarray)
+        img = torch.from_numpy(hdr) if is_numpy else hdr
+        # when the context issues on torch's current stream (both default to the legacy stream) stream order already holds
+        same_stream = (not is_numpy) and getattr(ctx, "stream", None) == torch.cuda.current_stream().cuda_stream
+        if not is_numpy and not same_stream:
+            ctx.sync()
+        if self._hdr_io is None or self._hdr_io[0].device != img.device:
+            mk = lambda: torch.zeros((self.max_out_rows,) + tuple(img.shape[1:]), dtype=img.dtype, device=img.device)
+            idx = [torch.as_tensor(rows, device=img.device, dtype=torch.long) for rows in self.out_rows]
+            self._hdr_io = (mk(), [mk() for _ in range(self.world)], idx)
+        send, recv, idx = self._hdr_io
+        mine = idx[self.rank]
+        torch.index_select(img, 0, mine, out=send[: len(mine)])
+        # gloo has no fp16 all_gather on every build: move bytes
+        as_bytes = (lambda t: t.view(torch.uint8)) if img.dtype == torch.float16 else (lambda t: t)
+        dist.all_gather([as_bytes(t) for t in recv], as_bytes(send), group=self.group)
+        for k in range(self.world):
+            if k != self.rank:
+                img.index_copy_(0, idx[k], recv[k][: len(idx[k])])
+        if not is_numpy and not same_stream:
+            torch.cuda.current_stream().synchronize()
+
     def frame(self, common, cloud, depth, hdr):
         import torch
         import torch.distributed as dist
@@ -120,6 +162,8 @@ class ShardedCloudFrame:
         ctx.cloud_frame_begin(common, cloud, depth, self.band_rows, self.rank, self.world)
         if self.fused:
             ctx.cloud_frame_end(depth, hdr)  # waits on the device for every rank's rows, then K17 / K18
+            if self.shard_output:
+                self.gather_output(hdr)
             return
         for res in (abi.RES_CLOUD_RENDER, abi.RES_CLOUD_DISTANCE):
             t, zc = resource_tensor(ctx, res)
@@ -143,3 +187,5 @@ class ShardedCloudFrame:
                 torch.cuda.current_stream().synchronize()
             commit(ctx, res, t, zc)
         ctx.cloud_frame_end(depth, hdr)
+        if self.shard_output:
+            self.gather_output(hdr)

@@ -83,6 +83,19 @@ def _worker(rank, world, port, out_dir):
             scf.frame(common, cloud, depth, hdr)
         np.save(os.path.join(out_dir, f"hdr_{rank}.npy"), hdr)
         np.save(os.path.join(out_dir, f"render_{rank}.npy"), r.ctx.read(abi.RES_CLOUD_RENDER))
+        # the same with the full-res passes sharded too (K6 + K18 on this rank's row bands, all-gather of the HDR rows)
+        r, depth = _setup_cloud(96, 56)
+        scf = ShardedCloudFrame(r, rank, world, band_rows=4, shard_output=True, output_band_rows=8)
+        hdr = np.zeros((56, 96, 4), np.float16)
+        for _ in range(2):
+            hdr[...] = 0
+            r.earth_update()
+            common, cloud, _ = r.cloud_update(0.0)
+            r.ctx.cloud_shadow(common)
+            r.atmosphere_render_luts()
+            scf.composite(depth, hdr)
+            scf.frame(common, cloud, depth, hdr)
+        np.save(os.path.join(out_dir, f"hdr_sharded_{rank}.npy"), hdr)
     finally:
         dist.destroy_process_group()
 
@@ -110,3 +123,12 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     for k in range(world):
         assert np.array_equal(np.load(tmp_path / f"render_{k}.npy"), ref_render)  # rays are independent: bit-exact
         assert np.array_equal(np.load(tmp_path / f"hdr_{k}.npy"), hdr)
+    # full-res passes sharded: the composite is part of this frame
+    r, depth = _setup_cloud(96, 56)
+    hdr = np.zeros((56, 96, 4), np.float16)
+    for _ in range(2):
+        hdr[...] = 0
+        r.frame(depth, hdr, 0.0, composite=True)
+    assert hdr.astype(np.float32).sum() > 0
+    for k in range(world):
+        assert np.array_equal(np.load(tmp_path / f"hdr_sharded_{k}.npy"), hdr)

@@ -49,6 +49,27 @@ def _worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, f"hdr_{rank}.npy"), hdr.cpu().numpy())
         np.save(os.path.join(out_dir, f"render_{rank}.npy"), r.ctx.read(abi.RES_CLOUD_RENDER))
         dist.barrier()
+        # the same frames with the full-res passes sharded too (K6 + K18 on this rank's row bands, all-gather of the HDR rows),
+        # frames in flight (overlap + pipelining), no host synchronisation inside the loop
+        r2 = Renderer("c3", w, h, library=cuda, device=rank)
+        r2.prime()
+        r2.ctx.set_frame_overlap(True)
+        r2.ctx.set_frame_pipelining(True)
+        scf2 = ShardedCloudFrame(r2, rank, world, band_rows=8, shard_output=True)
+        for _ in range(4):
+            hdr.zero_()
+            r2.earth_update()
+            common, cloud, _ = r2.cloud_update(0.0)
+            r2.ctx.cloud_shadow(common)
+            r2.atmosphere_render_luts()
+            scf2.composite(depth, hdr)
+            scf2.frame(common, cloud, depth, hdr)
+        r2.ctx.sync()
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, f"hdr_sharded_{rank}.npy"), hdr.cpu().numpy())
+        r2.ctx.set_frame_pipelining(False)
+        r2.ctx.set_frame_overlap(False)
+        dist.barrier()
         # path tracer: split kFrameId range + one all-reduce
         rp = Renderer("c5", 256, 144, library=cuda, device=rank)
         rp.upload_voxels(synthetic_voxel_grid(63, 77, 43))
@@ -78,6 +99,7 @@ def test_two_gpu_sharding_matches_single_gpu(tmp_path):
     for k in range(world):
         assert np.array_equal(np.load(tmp_path / f"render_{k}.npy").astype(np.float32), ref["render"])  # rays are independent
         assert np.array_equal(np.load(tmp_path / f"hdr_{k}.npy").astype(np.float32), ref["hdr"])
+        assert np.array_equal(np.load(tmp_path / f"hdr_sharded_{k}.npy").astype(np.float32), ref["hdr"])
     _, _, whole = run_path_trace("c5", 256, 144, abi.cuda_library(), 8, grid=synthetic_voxel_grid(63, 77, 43), max_bounces=8,
                                  region_box_half_width=8.0)
     pts = [np.load(tmp_path / f"pt_{k}.npy")[0] for k in range(world)]
