@@ -302,8 +302,8 @@ def main():
     h2d = 384 + 16 + 16  # common block + region + frame ids: the only inputs of a step
     d2h = PT_W * PT_H * 16
 
-    # dominant kernel K19 on this rank: duration, work counters, roofline -- on ONE launch (<= 64 kFrameIds; a step
-    # issues ceil(my_count / 72) such launches).  The counting variant walks every tentative collision of the
+    # dominant kernel K19 on this rank: duration, work counters, roofline -- on ONE launch of <= 64 kFrameIds (the shape of the
+    # committed ncu capture; a step is one launch of my_count <= 291 kFrameIds).  The counting variant walks every tentative collision of the
     # reference algorithm (no dead-stream cut): its totals are the algorithmic work of the launch.
     roof_frames = max(1, min(my_count, 64))
     k19_ms = kernel_ms(lambda: rp.ctx.pt_samples(common_pt, my_begin, roof_frames, region), reps=2)
@@ -531,8 +531,8 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-            # per step and rank: K19 (persistent state machine) + K19b (ordered accumulate) per chunk of <= 72 kFrameIds
-            "gpu_launches": args.steps * 2 * max(1, -(-my_count // 72)),
+            # per step and rank: K19 (persistent state machine) + K19b (ordered accumulate) per chunk of <= 291 kFrameIds (4 GiB of sample slots)
+            "gpu_launches": args.steps * 2 * max(1, -(-my_count // 291)),
             "roofline": pt_roofline, "cpu_baseline": cpu_baseline, "frame_4k": frame, "configs": configs,
         }
         print(json.dumps(line), flush=True)

@@ -897,8 +897,9 @@ int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32
     if (rw <= 0 || rh <= 0) return 0;
     // tile-padded job space: ceil(rw/8) x ceil(rh/4) tiles of 32 pixels
     const size_t padded = size_t((rw + 7) / 8) * size_t((rh + 3) / 4) * 32;
-    // sample slots: at most ~1 GiB per launch, so long jobs run in chunks of frames
-    uint32_t frames_per_launch = uint32_t(std::max<size_t>(1, std::min<size_t>(count, (size_t(1) << 26) / padded)));
+    // sample slots: at most ~4 GiB per launch (HBM is plentiful; every launch ends with a drain phase in which a few lanes finish
+    // the longest paths, DESIGN.md section 7, so fewer, longer launches are better), longer jobs run in chunks of frames
+    uint32_t frames_per_launch = uint32_t(std::max<size_t>(1, std::min<size_t>(count, (size_t(1) << 28) / padded)));
     if (padded * frames_per_launch >= (size_t(1) << 32)) return sky_fail(ctx, "region too large for one launch");
     const size_t need = padded * frames_per_launch * sizeof(float4);
     if (ctx->pt_samples_bytes < need) {
