@@ -277,8 +277,19 @@ enum SkyResource {
     SKY_RES_MESH_SHADOW_MAP = 26,     /* float  [2048][2048] light-space depth of the mesh shadow pass (ShadowMap.cpp:8-27,
                                          AppWindow.cpp:25,183-190), cleared to 1.0; an INPUT: written by the caller with
                                          sky_write_resource, read by K3/K4/K6 when volumetric_light is set */
+    SKY_RES_ENV_BRDF_LUT = 27,        /* u16x2  [512][512] GL_RG16 environment-BRDF LUT        src/Base/src/Textures.cpp:60-75 (K22) */
+    SKY_RES_ENVIRONMENT_MIPS = 28,    /* half4  levels >= 1 of SKY_RES_ENVIRONMENT, concatenated ([6][S/2][S/2], [6][S/4][S/4], ...)
+                                         glGenerateTextureMipmap, AtmosphereRenderer.cpp:242 */
+    SKY_RES_ENV_RADIANCE_SH = 29,     /* float4 [9] Llm, the SH9 coefficients of the environment   src/Base/src/IBL.cpp:12-13,29-34 (K23) */
+    SKY_RES_PREFILTERED_RADIANCE = 30,/* half4  5 levels concatenated ([6][128][128], [6][64][64], ... [6][8][8]), level i filtered at
+                                         roughness i / 4                                          src/Base/src/IBL.cpp:21-22,35-42 (K24) */
     SKY_RES_COUNT_
 };
+
+/* IBL constants (src/Base/include/IBL.h:10-11, src/Base/src/Textures.cpp:61-62) */
+#define SKY_IBL_PREFILTERED_RESOLUTION 128
+#define SKY_IBL_ROUGHNESS_COUNT 5
+#define SKY_ENV_BRDF_LUT_SIZE 512
 
 enum SkyFormat {
     SKY_FMT_F32 = 0, SKY_FMT_F16 = 1, SKY_FMT_U8 = 2, SKY_FMT_U16 = 3, SKY_FMT_U64 = 4

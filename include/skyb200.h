@@ -62,6 +62,18 @@ int SKY_FN(atmosphere_bake)(SkyContext* ctx, const SkyAtmosphereBufferData* atmo
 int SKY_FN(atmosphere_luts)(SkyContext* ctx, const SkyAtmosphereRenderBufferData* render,
                             const SkyLutConfig* config);
 
+/* Textures::Textures environment-BRDF LUT bake (src/Base/src/Textures.cpp:60-75, shaders/Base/EnvBRDFLut.comp, K22):
+ * split-sum integral of the GGX BRDF, 1024 Hammersley samples per texel -> SKY_RES_ENV_BRDF_LUT (GL_RG16 512x512).
+ * Input-free; the reference bakes it once at start-up. */
+int SKY_FN(env_brdf_lut)(SkyContext* ctx);
+
+/* The tail of AtmosphereRenderer::Render's LUT phase (AtmosphereRenderer.cpp:242-244): glGenerateTextureMipmap of the
+ * environment cube (-> SKY_RES_ENVIRONMENT_MIPS) and IBL::Precompute (src/Base/src/IBL.cpp:25-45): K23 EnvRadianceSH.comp
+ * (-> SKY_RES_ENV_RADIANCE_SH) and K24 PrefilterRadiance.comp, one dispatch per roughness level
+ * (-> SKY_RES_PREFILTERED_RADIANCE).  Call after sky_atmosphere_luts; inputs of the object shading of the composite
+ * (ComputeObjectLuminance / GetAmbient, AtmosphereRenderer.glsl:284-324, BRDF.glsl:108-130). */
+int SKY_FN(ibl_precompute)(SkyContext* ctx);
+
 /* AtmosphereRenderer::Render full-screen pass (AtmosphereRenderer.cpp:246-250, K6), sky / aerial
  * perspective / sun-disc branches.  depth_dev: float[H][W] in [0,1]; hdr_dev: half4[H][W] (written).
  * Ground/object pixels receive the atmosphere in-scatter only and alpha = 0 marks them

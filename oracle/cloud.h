@@ -7,6 +7,7 @@
 #include <atomic>
 
 #include "atmosphere.h"
+#include "ibl.h"
 #include "noise.h"
 
 namespace orc {
@@ -19,6 +20,10 @@ struct CloudScene {
     Image<4> sky_lum, sky_trans; // K3
     Image<4> ap_lum, ap_trans;   // K4
     Image<4> env;                // K5: 6 faces along z, fp16-rounded
+    CubeChain env_chain;         // env + its mips (glGenerateTextureMipmap, AtmosphereRenderer.cpp:242), filled by ibl_precompute
+    Image<2> env_brdf_lut;       // K22: RG16 512x512
+    vec4 env_sh[9];              // K23
+    CubeChain prefiltered;       // K24: 5 levels from 128^2
     SkyAtmosphereRenderBufferData render_u{};
     SkyLutConfig lut_cfg{};
 

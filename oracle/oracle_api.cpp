@@ -131,6 +131,22 @@ int orc_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
     return 0;
 }
 
+int orc_env_brdf_lut(SkyContext* ctx) {
+    ctx->scene.env_brdf_lut.resize(SKY_ENV_BRDF_LUT_SIZE, SKY_ENV_BRDF_LUT_SIZE);
+    BakeEnvBRDFLut(ctx->scene.env_brdf_lut);
+    return 0;
+}
+
+int orc_ibl_precompute(SkyContext* ctx) {
+    CloudScene& s = ctx->scene;
+    if (s.env.w <= 0) return fail(ctx, "ibl_precompute: the environment cube has not been baked (call atmosphere_luts first)");
+    if (s.env.w & (s.env.w - 1)) return fail(ctx, "ibl_precompute: the environment size must be a power of two");
+    GenerateCubeMips(s.env, s.env_chain);
+    EnvRadianceSH(s.env_chain, s.env_sh);
+    PrefilterRadiance(s.env_chain, SKY_IBL_PREFILTERED_RESOLUTION, SKY_IBL_ROUGHNESS_COUNT, s.prefiltered);
+    return 0;
+}
+
 int orc_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
     CloudScene& s = ctx->scene;
     AtmosphereRenderer ar{s.atm, s.render_u, s.lut_cfg, s.transmittance, s.multiscattering, &s.blue_noise};
@@ -300,6 +316,20 @@ int orc_get_resource(SkyContext* ctx, int resource, SkyResourceDesc* d) {
             d->ptr = s.pt_mask.data(); d->width = s.width; d->height = s.height; d->depth = 1; d->channels = 1; d->format = SKY_FMT_U8;
             d->bytes = s.pt_mask.size(); return 0;
         case SKY_RES_MESH_SHADOW_MAP: set_desc_f32(d, mesh_shadow_map(s)); return 0;
+        case SKY_RES_ENV_BRDF_LUT:
+            if (s.env_brdf_lut.w == 0) return fail(ctx, "env_brdf_lut has not been baked");
+            pack_unorm(s.env_brdf_lut, 16, ctx->scratch); packed(s.env_brdf_lut.w, s.env_brdf_lut.h, 1, 2, SKY_FMT_U16); return 0;
+        case SKY_RES_ENVIRONMENT_MIPS: case SKY_RES_PREFILTERED_RADIANCE: {
+            const CubeChain& c = resource == SKY_RES_ENVIRONMENT_MIPS ? s.env_chain : s.prefiltered;
+            const size_t first = resource == SKY_RES_ENVIRONMENT_MIPS ? 1 : 0;
+            if (c.levels.size() <= first) return fail(ctx, "ibl_precompute has not run");
+            std::vector<uint8_t> all, one;
+            for (size_t l = first; l < c.levels.size(); ++l) { pack_half(c.levels[l], one); all.insert(all.end(), one.begin(), one.end()); }
+            ctx->scratch.swap(all);
+            packed(int(ctx->scratch.size() / 2), 1, 1, 1, SKY_FMT_F16); return 0;  // flat, like the *_MIPS resources
+        }
+        case SKY_RES_ENV_RADIANCE_SH:
+            d->ptr = &s.env_sh[0].x; d->width = 9; d->height = 1; d->depth = 1; d->channels = 4; d->format = SKY_FMT_F32; d->bytes = 9 * 16; return 0;
         case SKY_RES_COUNTERS:
             ctx->counter_copy.resize(8);
             for (int i = 0; i < 8; ++i) ctx->counter_copy[i] = s.counters[i].load();

@@ -9,7 +9,7 @@ are purely syntactic -- no arithmetic is added, removed or reordered:
      `#extension` lines are dropped; include guards and `#if` permutations are left to the C preprocessor.
   2. every real literal gets an `f` suffix (GLSL literals are fp32; C++'s would be double).
   3. `layout(...)` qualifiers and the `uniform` / `shared` / `readonly` / `writeonly` / `restrict` / `coherent` keywords are
-     dropped: uniform-block members, samplers, images and shared arrays become namespace-scope variables the driver fills;
+     dropped: uniform-block and storage-block members, samplers, images and shared arrays become namespace-scope variables the driver fills;
      `layout(local_size...) in;` lines disappear (the driver passes the local size to ref::dispatch).
   4. parameter qualifiers: `out T x` / `inout T x` -> `T& x`, `in T x` -> `T x`; file-scope `in` / `out` interface
      variables of a fragment shader become thread_local variables (one fragment per thread).
@@ -71,7 +71,7 @@ def rewrite(text):
         if inst:
             return f"struct {m.group(1)}_t {{{body}}} {inst};"
         return body
-    text = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+(\w+)\s*\{(.*?)\}\s*(\w*)\s*;", block, text, flags=re.S)
+    text = re.sub(r"layout\s*\([^)]*\)\s*(?:uniform|buffer)\s+(\w+)\s*\{(.*?)\}\s*(\w*)\s*;", block, text, flags=re.S)
     text = re.sub(r"layout\s*\([^)]*\)\s*", "", text)
     text = re.sub(r"\b(uniform|shared|readonly|writeonly|restrict|coherent|highp|mediump|lowp|flat)\s+", "", text)
     # 4. file-scope interface variables of fragment shaders

@@ -263,7 +263,7 @@ inline vec3 operator*(const mat3& m, const vec3& v) {
 }
 
 // ---- images and samplers ------------------------------------------------------------------------------------
-enum ImageFormat { FMT_RGBA32F, FMT_RG32F, FMT_R32F, FMT_RGBA16F, FMT_RGBA8, FMT_RG8, FMT_R8, FMT_R16 };
+enum ImageFormat { FMT_RGBA32F, FMT_RG32F, FMT_R32F, FMT_RGBA16F, FMT_RGBA8, FMT_RG8, FMT_R8, FMT_R16, FMT_RG16 };
 inline float unorm16_round(float x);
 inline float half_round(float x) { return (float)(_Float16)x; }
 inline float unorm8_round(float x) { return std::nearbyint(clamp(x, 0.0f, 1.0f) * 255.0f) / 255.0f; }
@@ -286,6 +286,7 @@ struct Image {
             case FMT_RG8: v = vec4(unorm8_round(v.x), unorm8_round(v.y), 0.0f, 1.0f); break;
             case FMT_R8: v = vec4(unorm8_round(v.x), 0.0f, 0.0f, 1.0f); break;
             case FMT_R16: v = vec4(unorm16_round(v.x), 0.0f, 0.0f, 1.0f); break;
+            case FMT_RG16: v = vec4(unorm16_round(v.x), unorm16_round(v.y), 0.0f, 1.0f); break;
             case FMT_RG32F: v = vec4(v.x, v.y, 0.0f, 1.0f); break;
             case FMT_R32F: v = vec4(v.x, 0.0f, 0.0f, 1.0f); break;
             default: break;
@@ -402,14 +403,13 @@ inline vec4 texelFetch(const Sampler& s, const ivec3& p, int lod) {
 // samplerCube inside a compute shader: implicit derivatives are undefined, so the LOD is the driver's choice.  Convention
 // (same as the oracle and the kernels): level 0, bilinear inside the face the GL cube-map table
 // (spec 8.13) selects, clamped at the face edge.
-inline vec4 texture(const samplerCube& s, const vec3& dir) {
+inline vec4 textureCubeLevel(const Image& env, const vec3& dir) {
     float ax = std::fabs(dir.x), ay = std::fabs(dir.y), az = std::fabs(dir.z);
     int face; float sc, tc, ma;
     if (ax >= ay && ax >= az) { ma = ax; if (dir.x >= 0) { face = 0; sc = -dir.z; tc = -dir.y; } else { face = 1; sc = dir.z; tc = -dir.y; } }
     else if (ay >= az)        { ma = ay; if (dir.y >= 0) { face = 2; sc = dir.x; tc = dir.z; } else { face = 3; sc = dir.x; tc = -dir.z; } }
     else                      { ma = az; if (dir.z >= 0) { face = 4; sc = dir.x; tc = -dir.y; } else { face = 5; sc = -dir.x; tc = -dir.y; } }
     float ss = 0.5f * (sc / ma + 1.0f), tt = 0.5f * (tc / ma + 1.0f);
-    const Image& env = s.levels[0];
     int n = env.w;
     float u = ss * float(n) - 0.5f, v = tt * float(n) - 0.5f;
     float fu = std::floor(u), fv = std::floor(v);
@@ -417,6 +417,22 @@ inline vec4 texture(const samplerCube& s, const vec3& dir) {
     float a = u - fu, b = v - fv;
     auto L = [&](int i, int j) { return env.load(clamp(i, 0, n - 1), clamp(j, 0, n - 1), face); };
     return (1.0f - a) * (1.0f - b) * L(i0, j0) + a * (1.0f - b) * L(i0 + 1, j0) + (1.0f - a) * b * L(i0, j0 + 1) + a * b * L(i0 + 1, j0 + 1);
+}
+inline vec4 texture(const samplerCube& s, const vec3& dir) { return textureCubeLevel(s.levels[0], dir); }
+// textureLod on a cube with a LINEAR_MIPMAP_LINEAR sampler (Samplers::GetAnisotropySampler, src/Base/src/Samplers.cpp:33-41; an
+// explicit LOD has no footprint, so the anisotropy limit is moot): GL 4.6 section 8.14.3 -- the LOD is clamped to
+// [0, q], levels floor(lod) and floor(lod) + 1 are filtered bilinearly inside the selected face and blended with the exact fp32
+// fraction, mix(t0, t1, frac).  A fraction of exactly 0 takes the lower level alone.
+inline vec4 textureLod(const samplerCube& s, const vec3& dir, float lod) {
+    const int q = int(s.levels.size()) - 1;
+    float l = lod < 0.0f ? 0.0f : lod > float(q) ? float(q) : lod;
+    float fl = std::floor(l);
+    int l0 = int(fl);
+    float f = l - fl;
+    vec4 t0 = textureCubeLevel(s.levels[l0], dir);
+    if (!(f > 0.0f)) return t0;
+    vec4 t1 = textureCubeLevel(s.levels[l0 + 1 > q ? q : l0 + 1], dir);
+    return t0 * (1.0f - f) + t1 * f;
 }
 inline ivec2 textureSize(const sampler2D& s, int lod) { return ivec2(s.levels[lod].w, s.levels[lod].h); }
 inline ivec3 textureSize(const sampler3D& s, int lod) { return ivec3(s.levels[lod].w, s.levels[lod].h, s.levels[lod].d); }

@@ -153,7 +153,9 @@ ENV_OFF, ENV_CONST_ENVIRONMENT_MAP, ENV_GROUND_SINGLE_BOUNCE, ENV_GROUND_MULTI_B
  RES_AERIAL_TRANSMITTANCE, RES_ENVIRONMENT, RES_CLOUD_MAP, RES_DETAIL, RES_DISPLACEMENT, RES_SHADOW_MAP_RAW,
  RES_SHADOW_MAP, RES_SHADOW_FROXEL, RES_CHECKERBOARD_DEPTH, RES_INDEX_LINEAR_DEPTH, RES_CLOUD_RENDER,
  RES_CLOUD_DISTANCE, RES_RECONSTRUCT, RES_PT_ACCUM, RES_PT_MASK, RES_VOXEL, RES_CLOUD_MAP_MIPS, RES_DETAIL_MIPS,
- RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS, RES_MESH_SHADOW_MAP) = range(27)
+ RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS, RES_MESH_SHADOW_MAP, RES_ENV_BRDF_LUT, RES_ENVIRONMENT_MIPS,
+ RES_ENV_RADIANCE_SH, RES_PREFILTERED_RADIANCE) = range(31)
+IBL_PREFILTERED_RESOLUTION, IBL_ROUGHNESS_COUNT, ENV_BRDF_LUT_SIZE = 128, 5, 512  # IBL.h:10-11, Textures.cpp:61-62
 FMT_F32, FMT_F16, FMT_U8, FMT_U16, FMT_U64 = range(5)
 _FMT_DTYPE = {FMT_F32: np.float32, FMT_F16: np.float16, FMT_U8: np.uint8, FMT_U16: np.uint16, FMT_U64: np.uint64}
 (CNT_RENDER_SIGMA_EVALS, CNT_RENDER_TEX_FETCHES, CNT_PT_PATHS, CNT_PT_LOOKUPS, CNT_PT_COLLISIONS,
@@ -172,6 +174,8 @@ KERNEL_API = {
     "atmosphere_bake": ([P(AtmosphereBufferData)], I),
     "atmosphere_luts": ([P(AtmosphereRenderBufferData), P(LutConfig)], I),
     "composite": ([_VOIDP, _VOIDP, I, I], I),
+    "env_brdf_lut": ([], I),
+    "ibl_precompute": ([], I),
     "noise_generate": ([I, P(NoiseCreateInfo)], I),
     "voxel_upload": ([_VOIDP, I, I, I], I),
     "set_material": ([P(MaterialBlock)], I),
@@ -299,6 +303,20 @@ class Context:
     def atmosphere_bake(self, atm): self._call("atmosphere_bake", C.byref(atm))
     def atmosphere_luts(self, render, cfg): self._call("atmosphere_luts", C.byref(render), C.byref(cfg))
     def composite(self, depth, hdr, w, h): self._call("composite", _ptr(depth), _ptr(hdr), w, h)
+    def env_brdf_lut(self): self._call("env_brdf_lut")
+    def ibl_precompute(self): self._call("ibl_precompute")
+
+    def read_cube_chain(self, res, size):
+        """RES_ENVIRONMENT_MIPS (size = environment size / 2) or RES_PREFILTERED_RADIANCE (size = 128) as a list of
+        float16 arrays [6][n][n][4], n = size, size / 2, ..."""
+        flat = self.read(res).reshape(-1)
+        out, off, n = [], 0, size
+        while off < flat.size:
+            cnt = 6 * n * n * 4
+            out.append(flat[off:off + cnt].reshape(6, n, n, 4))
+            off += cnt
+            n //= 2
+        return out
 
     def noise_generate(self, kind, infos):
         arr = (NoiseCreateInfo * 2)(*infos)
