@@ -68,6 +68,16 @@ bool resolve(SkyContext* ctx, int resource, ResView& v) {
         case SKY_RES_AERIAL_LUMINANCE: v = view_of(ctx->ap_lum, 4, SKY_FMT_F32); return true;
         case SKY_RES_AERIAL_TRANSMITTANCE: v = view_of(ctx->ap_trans, 4, SKY_FMT_F32); return true;
         case SKY_RES_ENVIRONMENT: v = view_of(ctx->env, 4, SKY_FMT_F16); return true;
+        case SKY_RES_ENV_BRDF_LUT: v = view_of(ctx->env_brdf_lut, 2, SKY_FMT_U16); return true;
+        case SKY_RES_ENV_RADIANCE_SH: if (ctx->ibl_valid) v = view_of(ctx->env_sh, 4, SKY_FMT_F32); return true;
+        case SKY_RES_ENVIRONMENT_MIPS: case SKY_RES_PREFILTERED_RADIANCE: {  // flat, like the *_MIPS resources
+            if (!ctx->ibl_valid) return true;
+            const bool mips = resource == SKY_RES_ENVIRONMENT_MIPS;
+            v.ptr = mips ? ctx->env_mips : ctx->prefiltered;
+            v.w = int((mips ? ctx->env_mips_texels : ctx->prefiltered_texels) * 4); v.h = 1; v.d = 1; v.ch = 1; v.fmt = SKY_FMT_F16;
+            v.bytes = size_t(v.w) * 2;
+            return true;
+        }
         case SKY_RES_CLOUD_MAP: v = mip0_of(ctx->cloud_map); return true;
         case SKY_RES_DETAIL: v = mip0_of(ctx->detail); return true;
         case SKY_RES_DISPLACEMENT: v = mip0_of(ctx->displacement); return true;
@@ -199,6 +209,9 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
     free_mip(ctx->cloud_map); free_mip(ctx->detail); free_mip(ctx->displacement); free_mip(ctx->voxel);
     if (ctx->blue_noise) cudaFree(ctx->blue_noise);
+    free_lut(ctx->env_brdf_lut); free_lut(ctx->env_sh);
+    if (ctx->env_mips) cudaFree(ctx->env_mips);
+    if (ctx->prefiltered) cudaFree(ctx->prefiltered);
     if (ctx->lane2) { cudaStreamSynchronize(ctx->lane2); cudaStreamDestroy(ctx->lane2); }
     for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2, ctx->ev_frame_mark[0], ctx->ev_frame_mark[1], ctx->ev_luts_ready, ctx->ev_main_to_lut}) if (ev) cudaEventDestroy(ev);
     free_lut(ctx->alt.shadow_froxel);
@@ -421,6 +434,35 @@ int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
         return launch_atmosphere_luts(ctx);
     }
     return launch_atmosphere_luts(ctx);
+}
+
+int sky_env_brdf_lut(SkyContext* ctx) {
+    if (int e = sky_alloc(ctx, ctx->env_brdf_lut, SKY_ENV_BRDF_LUT_SIZE, SKY_ENV_BRDF_LUT_SIZE, 1, false)) return e;
+    return launch_env_brdf_lut(ctx);
+}
+
+int sky_ibl_precompute(SkyContext* ctx) {
+    if (!ctx->env.p) return sky_fail(ctx, "ibl_precompute: the environment cube has not been baked (call atmosphere_luts first)");
+    const int n = ctx->env.w;
+    if (n & (n - 1)) return sky_fail(ctx, "ibl_precompute: the environment size must be a power of two");
+    if (n > 2048) return sky_fail(ctx, "ibl_precompute: environment size above 2048");
+    if (int e = luts_join(ctx)) return e;  // frame pipelining: K5 of this frame runs on lut_stream
+    if (ctx->env_mips_for != n) {
+        if (ctx->env_mips) { SKY_CUDA(ctx, cudaFree(ctx->env_mips)); ctx->env_mips = nullptr; }
+        size_t texels = 0;
+        for (int w = n >> 1; w >= 1; w >>= 1) texels += size_t(6) * w * w;
+        SKY_CUDA(ctx, cudaMalloc(&ctx->env_mips, std::max<size_t>(texels, 1) * sizeof(half4)));
+        ctx->env_mips_texels = texels; ctx->env_mips_for = n;
+    }
+    if (!ctx->prefiltered) {
+        size_t texels = 0;
+        for (int l = 0, w = SKY_IBL_PREFILTERED_RESOLUTION; l < SKY_IBL_ROUGHNESS_COUNT; ++l, w >>= 1) texels += size_t(6) * w * w;
+        SKY_CUDA(ctx, cudaMalloc(&ctx->prefiltered, texels * sizeof(half4)));
+        ctx->prefiltered_texels = texels;
+    }
+    if (int e = sky_alloc(ctx, ctx->env_sh, 9, 1, 1, false)) return e;
+    ctx->ibl_valid = true;
+    return launch_ibl_precompute(ctx);
 }
 
 int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {

@@ -99,6 +99,16 @@ struct SkyContext {
     // K1-K5
     Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
     Lut<half4> env;  // [6][S][S]
+    // IBL chain (ibl.cu): K22 RG16 LUT, the environment cube's mips (levels >= 1, concatenated), K23 Llm[9],
+    // K24 prefiltered cube (SKY_IBL_ROUGHNESS_COUNT levels from SKY_IBL_PREFILTERED_RESOLUTION, concatenated)
+    Lut<ushort2> env_brdf_lut;
+    half4* env_mips = nullptr;
+    int env_mips_for = 0;         // environment size the mips are allocated for
+    size_t env_mips_texels = 0;
+    bool ibl_valid = false;       // sky_ibl_precompute has run
+    Lut<float4> env_sh;           // w = 9
+    half4* prefiltered = nullptr;
+    size_t prefiltered_texels = 0;
     // K6's raymarch fetches the two bake LUTs twice per step through the texture unit, which is what bounds it (ncu: L1/TEX at
     // 86 % of peak with RGBA32F texels, quarter rate); it reads RGBA16F copies (half rate), refreshed after every bake.  The
     // fp16 rounding (2^-11 relative) is far inside the frame tolerance; the strict objects filter the fp32 LUTs in software.
@@ -198,6 +208,8 @@ int launch_lut_half_copies(SkyContext* ctx);                                  //
 int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
 int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6
+int launch_env_brdf_lut(SkyContext* ctx);                                      // ibl.cu         K22
+int launch_ibl_precompute(SkyContext* ctx);                                    // ibl.cu         cube mips, K23, K24
 int launch_tonemap(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out);  // atmosphere.cu K21
 int launch_noise(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info);   // noise.cu       K8-K10
 int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, int channels, bool border);

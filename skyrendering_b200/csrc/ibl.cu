@@ -1,0 +1,309 @@
+// Image-based-lighting chain: the inputs of the composite's object shading.
+//   K22 k22_env_brdf_lut       shaders/Base/EnvBRDFLut.comp        (Textures::Textures, src/Base/src/Textures.cpp:60-75)
+//   cube mips                  glGenerateTextureMipmap             (AtmosphereRenderer.cpp:242)
+//   K23 EnvRadianceSH          shaders/Base/EnvRadianceSH.comp     (IBL::Precompute, src/Base/src/IBL.cpp:29-34)
+//   K24 k24_prefilter_radiance shaders/Base/PrefilterRadiance.comp (IBL.cpp:35-42)
+// Compiled with -fmad=false like the LUT bake: IEEE division / sqrt, sin / cos from include/sky_detmath.h, the reference's
+// operation order (K23 keeps its shared-memory tree, K22 / K24 their serial sample sums), so K23, the mips and every
+// level of K24 whose LOD arithmetic does not involve log2 are bit-identical to the oracle; powf / log2f are CUDA's (see
+// tests/test_gpu_parity.py for the stated tolerance).
+//
+// Mapping (all three are small, latency-bound kernels of the per-frame LUT phase, so the point is FEW launches):
+//   * one launch does the cube mips (6 blocks, one per face, levels chained through __syncthreads -- a face's chain only
+//     depends on that face) AND K23 (9 blocks of 1024 threads like the reference's 9 work groups; it only reads level 0);
+//   * one launch does all five roughness levels of K24, heavy levels first (level 0 is a 1-sample copy);
+//   * K22 (start-up, input-free): a block is 256 texels of one row, i.e. one roughness, so the tangent-space half vectors
+//     of the 1024 Hammersley samples are computed once per block into shared memory (2 sqrt + 1 division + sin + cos per
+//     sample hoisted out of every thread's loop; same functions on the same inputs, so still bit-identical).
+#include "context.h"
+#include "../../include/sky_detmath.h"
+
+namespace {
+
+struct CubeChainView {
+    const half4* level[12];  // level l: [6][n >> l][n >> l]
+    int n;
+    int levels;
+};
+
+// GL 4.6 table 8.19 face selection + bilinear inside the face, clamped at its edge (oracle/ibl.cpp TextureCubeLevel)
+template <bool LDG>
+SKY_D float4 TextureCubeLevel(const half4* lvl, int n, float3 dir) {
+    float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+    int face; float sc, tc, ma;
+    if (ax >= ay && ax >= az) { ma = ax; if (dir.x >= 0) { face = 0; sc = -dir.z; tc = -dir.y; } else { face = 1; sc = dir.z; tc = -dir.y; } }
+    else if (ay >= az)        { ma = ay; if (dir.y >= 0) { face = 2; sc = dir.x; tc = dir.z; } else { face = 3; sc = dir.x; tc = -dir.z; } }
+    else                      { ma = az; if (dir.z >= 0) { face = 4; sc = dir.x; tc = -dir.y; } else { face = 5; sc = -dir.x; tc = -dir.y; } }
+    float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+    float u = s * float(n) - 0.5f, v = t * float(n) - 0.5f;
+    float fu = floorf(u), fv = floorf(v);
+    int i0 = int(fu), j0 = int(fv);
+    float a = u - fu, b = v - fv;
+    const half4* f = lvl + size_t(face) * n * n;
+    int x0 = clampi(i0, 0, n - 1), x1 = clampi(i0 + 1, 0, n - 1), y0 = clampi(j0, 0, n - 1), y1 = clampi(j0 + 1, 0, n - 1);
+    float4 t00 = load_half4(f + y0 * n + x0), t10 = load_half4(f + y0 * n + x1), t01 = load_half4(f + y1 * n + x0), t11 = load_half4(f + y1 * n + x1);
+    return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+}
+
+// textureLod(samplerCube, dir, lod), LINEAR_MIPMAP_LINEAR (oracle/ibl.cpp TextureCubeLod)
+SKY_D float4 TextureCubeLod(const CubeChainView& c, float3 dir, float lod) {
+    const int q = c.levels - 1;
+    float l = lod < 0.0f ? 0.0f : lod > float(q) ? float(q) : lod;
+    float fl = floorf(l);
+    int l0 = int(fl);
+    float f = l - fl;
+    float4 t0 = TextureCubeLevel<true>(c.level[l0], c.n >> l0, dir);
+    if (!(f > 0.0f)) return t0;
+    int l1 = l0 + 1 > q ? q : l0 + 1;
+    float4 t1 = TextureCubeLevel<true>(c.level[l1], c.n >> l1, dir);
+    return t0 * (1.0f - f) + t1 * f;
+}
+
+// shaders/Base/Noise.glsl:113-117 with Random = uvec2(0)
+SKY_D float2 Hammersley0(uint32_t Index, uint32_t NumSamples) {
+    float E1 = fractf(float(Index) / float(NumSamples) + float(0u & 0xffffu) / float(1 << 16));
+    float E2 = float(__brev(Index) ^ 0u) * 2.3283064365386963e-10f;
+    return f2(E1, E2);
+}
+// shaders/Base/BRDF.glsl:51-63 (tangent space)
+SKY_D float3 ImportanceSampleGGX(float2 E, float a) {
+    float a2 = a * a;
+    float Phi = 2.0f * kPi * E.x;
+    float CosTheta = sqrtf((1.0f - E.y) / (1.0f + (a2 - 1.0f) * E.y));
+    float SinTheta = sqrtf(1.0f - CosTheta * CosTheta);
+    return f3(SinTheta * sky_det_cosf(Phi), SinTheta * sky_det_sinf(Phi), CosTheta);
+}
+// shaders/Base/BRDF.glsl:36-40
+SKY_D float D_GGX(float a, float NdotH) {
+    float a2 = a * a;
+    float d = (NdotH * a2 - NdotH) * NdotH + 1.0f;
+    return a2 / (kPi * d * d);
+}
+// shaders/Base/Common.glsl:32-52
+SKY_D void CreateOrthonormalBasis(float3 N, float3& t0, float3& t1) {
+    float s = (N.z >= 0.0f ? 1.0f : -1.0f);
+    float a = -1.0f / (s + N.z);
+    float b = N.x * N.y * a;
+    t0 = f3(1.0f + s * N.x * N.x * a, s * b, -s * N.x);
+    t1 = f3(b, s + N.y * N.y * a, -N.y);
+}
+// shaders/Base/Common.glsl:13-30
+SKY_D float3 ConvertCubUvToDir(int index, float u, float v) {
+    float uc = 2.0f * u - 1.0f, vc = 2.0f * v - 1.0f;
+    float3 dir = f3(0.0f);
+    switch (index) {
+        case 0: dir = f3(1.0f, vc, -uc); break;
+        case 1: dir = f3(-1.0f, vc, uc); break;
+        case 2: dir = f3(uc, 1.0f, -vc); break;
+        case 3: dir = f3(uc, -1.0f, vc); break;
+        case 4: dir = f3(uc, vc, 1.0f); break;
+        case 5: dir = f3(-uc, vc, -1.0f); break;
+    }
+    return normalize(dir);
+}
+
+// ------------------------------------------------------------------------------------------------------------ K22
+constexpr int kBrdfSamples = 1024;  // EnvBRDFLut.comp:20
+__global__ void __launch_bounds__(256) k22_env_brdf_lut(ushort2* __restrict__ out, int W, int H) {
+    __shared__ float3 sH[kBrdfSamples];
+    const int y = blockIdx.y, x = blockIdx.x * 256 + threadIdx.x;
+    const float Roughness = (float(y) + 0.5f) / float(H);  // uv.y
+    const float a = Roughness * Roughness;
+    for (int i = threadIdx.x; i < kBrdfSamples; i += 256) sH[i] = ImportanceSampleGGX(Hammersley0(uint32_t(i), kBrdfSamples), a);
+    __syncthreads();
+    if (x >= W) return;
+    const float NoV = (float(x) + 0.5f) / float(W);  // uv.x
+    const float3 V = f3(sqrtf(1.0f - NoV * NoV), 0.0f, NoV);
+    float A = 0.0f, B = 0.0f;
+#pragma unroll 4
+    for (int i = 0; i < kBrdfSamples; ++i) {
+        const float3 Hh = sH[i];
+        const float VdotH = dot(V, Hh);
+        const float Lz = 2.0f * VdotH * Hh.z - V.z;
+        const float NoL = clampf(Lz, 0.0f, 1.0f);
+        const float NoH = clampf(Hh.z, 0.0f, 1.0f);
+        const float VoH = clampf(VdotH, 0.0f, 1.0f);
+        if (NoL > 0.0f) {
+            // Vis_SmithJointApprox, BRDF.glsl:42-46
+            float Vis_SmithV = NoL * (NoV * (1.0f - a) + a);
+            float Vis_SmithL = NoV * (NoL * (1.0f - a) + a);
+            float Vis = 0.5f / fmaxf(Vis_SmithV + Vis_SmithL, 1e-9f);
+            float NoL_Vis_PDF = NoL * Vis * (4.0f * VoH / NoH);
+            float Fc = powf(1.0f - VoH, 5.0f);
+            A += (1.0f - Fc) * NoL_Vis_PDF;
+            B += Fc * NoL_Vis_PDF;
+        }
+    }
+    A = A / float(kBrdfSamples);
+    B = B / float(kBrdfSamples);
+    // rg16 image store: round to nearest even
+    out[size_t(y) * W + x] = make_ushort2((unsigned short)__float2uint_rn(clampf(A, 0.0f, 1.0f) * 65535.0f),
+                                          (unsigned short)__float2uint_rn(clampf(B, 0.0f, 1.0f) * 65535.0f));
+}
+
+// ------------------------------------------------------------------------------------------- cube mips + K23 (one launch)
+struct MipShParams {
+    const half4* level0;  // [6][n][n]
+    half4* mips;          // levels 1 .. concatenated
+    int n, levels;
+    float4* sh;           // Llm[9]
+};
+
+SKY_D void cube_face_mips(const MipShParams& P, int face) {
+    const half4* src = P.level0 + size_t(face) * P.n * P.n;
+    half4* dst_level = P.mips;
+    for (int l = 1, n = P.n >> 1; l < P.levels; ++l, n >>= 1) {
+        half4* dst = dst_level + size_t(face) * n * n;
+        for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+            int x = t % n, y = t / n;
+            const half4* r0 = src + size_t(2 * y) * (2 * n) + 2 * x;
+            const half4* r1 = r0 + 2 * n;
+            float4 t00 = from_half4(r0[0]), t10 = from_half4(r0[1]), t01 = from_half4(r1[0]), t11 = from_half4(r1[1]);  // plain loads: written by this block
+            float4 m = ((t00 + t10) + (t01 + t11)) * 0.25f;
+            dst[t] = to_half4(m);
+        }
+        __syncthreads();
+        src = dst;
+        dst_level += size_t(6) * n * n;
+    }
+}
+
+// EnvRadianceSH.comp:29-85
+SKY_D void env_radiance_sh(const MipShParams& P, int index, float3* Llm_local) {
+    const float Y00 = 0.282095f, Y1n = 0.488603f, Y2n = 1.092548f, Y20 = 0.315392f, Y22 = 0.546274f;
+    const int local_index = threadIdx.x;
+    float unit_theta = (0.5f + float(local_index >> 5)) / 32.0f;
+    float unit_phi = (0.5f + float(local_index & 0x1f)) / 32.0f;
+    float cos_theta = 1.0f - 2.0f * unit_theta;
+    float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
+    float phi = 2.0f * kPi * unit_phi;
+    float cos_phi = sky_det_cosf(phi);
+    float sin_phi = sky_det_sinf(phi);
+    float3 dir = f3(cos_phi * sin_theta, cos_theta, sin_phi * sin_theta);
+    float3 radiance = xyz(TextureCubeLevel<true>(P.level0, P.n, dir));
+    float c;
+    switch (index) {
+        case 0: c = Y00; break;
+        case 1: c = Y1n * dir.y; break;
+        case 2: c = Y1n * dir.z; break;
+        case 3: c = Y1n * dir.x; break;
+        case 4: c = Y2n * dir.x * dir.y; break;
+        case 5: c = Y2n * dir.y * dir.z; break;
+        case 6: c = Y20 * (3.0f * dir.z * dir.z - 1.0f); break;
+        case 7: c = Y2n * dir.x * dir.z; break;
+        default: c = Y22 * (dir.x * dir.x - dir.y * dir.y); break;
+    }
+    Llm_local[local_index] = radiance * (c * (4.0f * kPi / 1024.0f));
+    __syncthreads();
+    for (int stride = 512; stride >= 1; stride >>= 1) {  // the reference's tree: [i] += [i + stride]
+        if (local_index < stride) Llm_local[local_index] = Llm_local[local_index] + Llm_local[local_index + stride];
+        __syncthreads();
+    }
+    if (local_index == 0) P.sh[index] = f4(Llm_local[0], 0.0f);
+}
+
+__global__ void __launch_bounds__(1024) k23_env_sh_and_cube_mips(const __grid_constant__ MipShParams P) {
+    __shared__ float3 Llm_local[1024];
+    if (blockIdx.x < 9) env_radiance_sh(P, blockIdx.x, Llm_local);
+    else cube_face_mips(P, blockIdx.x - 9);
+}
+
+// ------------------------------------------------------------------------------------------------------------ K24
+struct PrefilterParams {
+    CubeChainView env;
+    half4* out[SKY_IBL_ROUGHNESS_COUNT];
+    int size;
+    uint32_t num_samples[SKY_IBL_ROUGHNESS_COUNT];  // uint(mix(1, 64, pow(roughness, 0.3))), PrefilterRadiance.comp:20
+    int first_block[SKY_IBL_ROUGHNESS_COUNT + 1];    // launch order: levels 1, 2, ... then 0 (heavy first)
+};
+
+__global__ void __launch_bounds__(128) k24_prefilter_radiance(const __grid_constant__ PrefilterParams P) {
+    __shared__ float3 sH[64];  // kNumSamplesMax, PrefilterRadiance.comp:19
+    int slot = 0;
+#pragma unroll
+    for (int k = 1; k < SKY_IBL_ROUGHNESS_COUNT; ++k) slot += int(blockIdx.x) >= P.first_block[k];
+    const int level = (slot + 1) % SKY_IBL_ROUGHNESS_COUNT;
+    const int w = P.size >> level;
+    const int t = (int(blockIdx.x) - P.first_block[slot]) * 128 + threadIdx.x;
+    const float roughness = float(level) / float(SKY_IBL_ROUGHNESS_COUNT - 1);  // IBL.cpp:39
+    // a block is one roughness level: the tangent-space half vectors (sin, cos, 2 sqrt, 1 division per sample) depend on the
+    // sample index alone, so they are evaluated once per block instead of once per texel and sample (same values)
+    if (threadIdx.x < P.num_samples[level]) sH[threadIdx.x] = ImportanceSampleGGX(Hammersley0(threadIdx.x, P.num_samples[level]), roughness * roughness);
+    __syncthreads();
+    if (t >= 6 * w * w) return;
+    const int x = t % w, y = (t / w) % w, index = t / (w * w);
+    float fu = (float(x) + 0.5f) / float(w), fv = (float(y) + 0.5f) / float(w);
+    fv = 1.0f - fv;
+    const float3 R = ConvertCubUvToDir(index, fu, fv);
+    // PrefilterEnvMap, PrefilterRadiance.comp:12-40
+    const float a = roughness * roughness;
+    const float3 N = R, V = R;
+    float3 t0, t1;
+    CreateOrthonormalBasis(N, t0, t1);
+    float3 PrefilteredColor = f3(0.0f);
+    const uint32_t NumSamples = P.num_samples[level];
+    float TotalWeight = 0.0f;
+    const float invSaTexel = (6.0f * float(w) * float(w)) / (4.0f * kPi);
+    for (uint32_t i = 0; i < NumSamples; i++) {
+        float3 Hl = sH[i];
+        float3 Hw = t0 * Hl.x + t1 * Hl.y + N * Hl.z;
+        float3 L = 2.0f * dot(V, Hw) * Hw - V;
+        float NoL = clampf(dot(N, L), 0.0f, 1.0f);
+        if (NoL > 0.0f) {
+            float NoH = clampf(dot(N, Hw), 0.0f, 1.0f);
+            float HoV = clampf(dot(Hw, V), 0.0f, 1.0f);
+            float D = D_GGX(a, NoH);
+            float pdf = fmaxf(D * NoH / (4.0f * HoV), 0.0001f);
+            float saSample = 1.0f / fmaxf(float(NumSamples) * pdf, 0.00001f);
+            float mipLevel = roughness == 0.0f ? 0.0f : 0.5f * log2f(saSample * invSaTexel) + 2.5f;
+            PrefilteredColor = PrefilteredColor + xyz(TextureCubeLod(P.env, L, mipLevel)) * NoL;
+            TotalWeight += NoL;
+        }
+    }
+    float3 c = PrefilteredColor / TotalWeight;
+    P.out[level][(size_t(index) * w + y) * w + x] = to_half4(f4(c, 0.0f));
+}
+
+}  // namespace
+
+int launch_env_brdf_lut(SkyContext* ctx) {
+    const int S = SKY_ENV_BRDF_LUT_SIZE;
+    k22_env_brdf_lut<<<dim3(ceil_div(S, 256), S), 256, 0, ctx->stream>>>(ctx->env_brdf_lut.p, S, S);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_ibl_precompute(SkyContext* ctx) {
+    const int n = ctx->env.w;
+    int levels = 1;
+    while ((n >> levels) >= 1) ++levels;
+    MipShParams M{};
+    M.level0 = ctx->env.p; M.mips = ctx->env_mips; M.n = n; M.levels = levels; M.sh = ctx->env_sh.p;
+    k23_env_sh_and_cube_mips<<<9 + 6, 1024, 0, ctx->stream>>>(M);
+    SKY_LAUNCH_CHECK(ctx);
+
+    PrefilterParams P{};
+    P.env.n = n; P.env.levels = levels;
+    P.env.level[0] = ctx->env.p;
+    const half4* p = ctx->env_mips;
+    for (int l = 1; l < levels; ++l) { P.env.level[l] = p; p += size_t(6) * (n >> l) * (n >> l); }
+    P.size = SKY_IBL_PREFILTERED_RESOLUTION;
+    half4* o = ctx->prefiltered;
+    for (int l = 0; l < SKY_IBL_ROUGHNESS_COUNT; ++l) {
+        const int w = P.size >> l;
+        P.out[l] = o; o += size_t(6) * w * w;
+        const float roughness = float(l) / float(SKY_IBL_ROUGHNESS_COUNT - 1);
+        const float tpow = powf(roughness, 0.3f);
+        P.num_samples[l] = uint32_t(1.0f * (1.0f - tpow) + 64.0f * tpow);  // mix(kNumSamplesMin, kNumSamplesMax, pow(roughness, 0.3))
+    }
+    int blocks = 0;
+    for (int k = 0; k < SKY_IBL_ROUGHNESS_COUNT; ++k) {
+        const int level = (k + 1) % SKY_IBL_ROUGHNESS_COUNT, w = P.size >> level;
+        P.first_block[k] = blocks;
+        blocks += ceil_div(6 * w * w, 128);
+    }
+    P.first_block[SKY_IBL_ROUGHNESS_COUNT] = blocks;
+    k24_prefilter_radiance<<<blocks, 128, 0, ctx->stream>>>(P);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}

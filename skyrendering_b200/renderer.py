@@ -110,6 +110,8 @@ class Renderer:
         self._pt_frame_cnt = 0
         self._pt_tile = 0
         self.last_uniforms = None
+        self.ibl = False
+        self._env_brdf_baked = False
 
     # ---- pieces -------------------------------------------------------------------------------------
     def earth_update(self):
@@ -122,6 +124,17 @@ class Renderer:
         self.render_buffer = self.scene.atmosphere_render_buffer()
         self.lut_config = self.scene.lut_config()
         self.ctx.atmosphere_luts(self.render_buffer, self.lut_config)
+        if self.ibl:
+            self.ctx.ibl_precompute()
+
+    def enable_ibl(self, on=True):
+        """The tail of AtmosphereRenderer::Render's LUT phase (AtmosphereRenderer.cpp:242-244: environment mips +
+        IBL::Precompute) runs with every LUT update from now on; the environment-BRDF LUT (Textures.cpp:60-75) is baked
+        once, like the reference does at start-up.  These feed the object shading of the composite."""
+        if on and not self._env_brdf_baked:
+            self.ctx.env_brdf_lut()
+            self._env_brdf_baked = True
+        self.ibl = bool(on)
 
     def upload_voxels(self, grid):
         dz, dy, dx = grid.shape

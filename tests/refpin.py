@@ -288,3 +288,54 @@ class CloudPassHarness:
     def run(self, pass_id):
         rc = self.ref.ref_cloud_pass(pass_id, C.byref(self.io))
         assert rc == 0, (pass_id, rc)
+
+
+# ---- IBL chain (K22-K24) ------------------------------------------------------------------------------
+IBL_GOLDEN = os.path.join(ROOT, "tests", "golden", "ibl_digests.json")
+
+
+class RefIblIO(C.Structure):
+    _fields_ = [("environment", C.c_void_p), ("env_size", C.c_int), ("env_levels", C.c_int), ("sh", C.c_void_p),
+                ("prefiltered", C.c_void_p), ("pre_size", C.c_int), ("pre_levels", C.c_int)]
+
+
+def ref_env_brdf_lut(ref):
+    """K22: the reference's EnvBRDFLut.comp -> uint16 [512][512][2] (the GL_RG16 codes)."""
+    n = abi.ENV_BRDF_LUT_SIZE
+    out = np.zeros((n, n, 4), np.float32)
+    assert ref.ref_env_brdf_lut(out.ctypes.data_as(C.c_void_p), n, n) == 0
+    return np.rint(out[..., :2] * np.float32(65535.0)).astype(np.uint16)
+
+
+def ibl_state(ctx):
+    """(environment chain as a list of float16 [6][n][n][4], Llm float32 [9][4], prefiltered chain) of a context after ibl_precompute."""
+    env0 = ctx.read(abi.RES_ENVIRONMENT)
+    chain = [env0] + ctx.read_cube_chain(abi.RES_ENVIRONMENT_MIPS, env0.shape[1] // 2)
+    sh = ctx.read(abi.RES_ENV_RADIANCE_SH).reshape(9, 4)
+    pre = ctx.read_cube_chain(abi.RES_PREFILTERED_RADIANCE, abi.IBL_PREFILTERED_RESOLUTION)
+    return chain, sh, pre
+
+
+def ref_ibl(ref, env_chain):
+    """K23 + K24 of the reference shader text on a given environment chain (the mips are driver work, so they are an input).
+    Returns (Llm float32 [9][4], prefiltered chain as float16 arrays)."""
+    flat = np.concatenate([np.asarray(c, np.float32).reshape(-1) for c in env_chain])
+    sizes = [abi.IBL_PREFILTERED_RESOLUTION >> l for l in range(abi.IBL_ROUGHNESS_COUNT)]
+    sh = np.zeros((9, 4), np.float32)
+    pre = np.zeros(sum(6 * w * w * 4 for w in sizes), np.float32)
+    io = RefIblIO(flat.ctypes.data, env_chain[0].shape[1], len(env_chain), sh.ctypes.data, pre.ctypes.data, sizes[0], len(sizes))
+    assert ref.ref_ibl(C.byref(io)) == 0
+    out, off = [], 0
+    for w in sizes:
+        out.append(pre[off:off + 6 * w * w * 4].reshape(6, w, w, 4).astype(np.float16))
+        off += 6 * w * w * 4
+    return sh, out
+
+
+def ibl_digests(env_brdf_lut, chain, sh, pre):
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    return {"env_brdf_lut": None if env_brdf_lut is None else sha(env_brdf_lut),
+            "environment_mips": sha(np.concatenate([c.reshape(-1) for c in chain[1:]])),
+            "env_radiance_sh": sha(np.asarray(sh, np.float32)), "sh_values": [float(v) for v in np.asarray(sh, np.float32).reshape(-1)],
+            "prefiltered": [sha(p) for p in pre]}

@@ -1,0 +1,92 @@
+"""IBL chain on the GPU (ibl.cu: K22 EnvBRDFLut, environment mips + K23 EnvRadianceSH in one launch, K24 PrefilterRadiance) against
+the oracle and against the digests of the reference's own shader outputs (tests/golden/ibl_digests.json).
+
+Tolerances: the mips, K23 and level 0 of K24 involve only IEEE operations and the shared deterministic sin / cos: BIT-EXACT.
+K22 uses pow(x, 5) and the levels >= 1 of K24 use log2 for the LOD, which GLSL leaves to the driver; the oracle takes libm's,
+the kernels CUDA's (both within a few ulp): K22 may differ by one RG16 code on isolated texels, K24 by fp16 rounding flips --
+asserted as >= 99 % of the values bit-equal and a maximum difference of 1 code / 2^-9 relative."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from skyrendering_b200 import abi
+from skyrendering_b200.renderer import Renderer
+from tests import refpin
+from tests.parity import oracle_library
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return abi.cuda_library(), oracle_library()
+
+
+def test_env_brdf_lut_parity(libs):
+    cuda, orc = libs
+    rg, ro = Renderer("c1", 64, 36, library=cuda), Renderer("c1", 64, 36, library=orc)
+    rg.ctx.env_brdf_lut(); ro.ctx.env_brdf_lut(); rg.ctx.sync()
+    g, o = rg.ctx.read(abi.RES_ENV_BRDF_LUT), ro.ctx.read(abi.RES_ENV_BRDF_LUT)
+    assert g.shape == o.shape == (512, 512, 2) and g.dtype == np.uint16
+    diff = np.abs(g.astype(np.int32) - o.astype(np.int32))
+    equal = float(np.mean(diff == 0))
+    print("K22: bit-equal fraction", equal, "max code difference", int(diff.max()))
+    assert diff.max() <= 1 and equal >= 0.99
+
+
+@pytest.mark.parametrize("scene", ["c1", "c2", "c3", "c5"])
+def test_ibl_precompute_parity(libs, scene):
+    cuda, orc = libs
+    rg, ro = Renderer(scene, 192, 108, library=cuda), Renderer(scene, 192, 108, library=orc)
+    for r in (rg, ro):
+        r.enable_ibl()
+        r.prime()
+    rg.ctx.sync()
+    (gc, gsh, gpre), (oc, osh, opre) = refpin.ibl_state(rg.ctx), refpin.ibl_state(ro.ctx)
+    with open(refpin.IBL_GOLDEN) as f:
+        gold = json.load(f)["scenes"][scene]
+    # mips + SH: bit-exact against the oracle AND against the reference shader digests
+    assert len(gc) == len(oc) == 8
+    for a, b in zip(gc, oc):
+        assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
+    assert np.array_equal(gsh.view(np.uint32), osh.view(np.uint32)), (gsh, osh)
+    d = refpin.ibl_digests(None, gc, gsh, gpre)
+    assert d["environment_mips"] == gold["environment_mips"] and d["env_radiance_sh"] == gold["env_radiance_sh"]
+    # K24: level 0 (roughness 0: one sample at LOD 0) bit-exact; the others within fp16 rounding flips
+    assert np.array_equal(gpre[0].view(np.uint16), opre[0].view(np.uint16)) and d["prefiltered"][0] == gold["prefiltered"][0]
+    for level in range(1, 5):
+        a, b = gpre[level].astype(np.float32), opre[level].astype(np.float32)
+        assert np.all(np.isfinite(a))
+        equal = float(np.mean(gpre[level].view(np.uint16) == opre[level].view(np.uint16)))
+        rel = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)))
+        print(f"K24 {scene} level {level}: bit-equal fraction {equal:.5f}, max relative difference {rel:.2e}")
+        assert equal >= 0.99 and rel <= 2.0 ** -9
+
+
+def test_ibl_follows_the_lut_phase_under_pipelining(libs):
+    """sky_ibl_precompute reads the environment cube K5 wrote in the same frame, also when the LUT phase runs on the internal
+    stream of sky_set_frame_pipelining: identical output."""
+    cuda, _ = libs
+    outs = []
+    for pipelined in (False, True):
+        r = Renderer("c3", 192, 108, library=cuda)
+        r.ctx.set_frame_pipelining(pipelined)
+        r.enable_ibl()
+        for _ in range(3):
+            r.prime()
+        r.ctx.sync()
+        outs.append(refpin.ibl_state(r.ctx))
+    for a, b in zip(outs[0][0] + [outs[0][1]] + outs[0][2], outs[1][0] + [outs[1][1]] + outs[1][2]):
+        assert np.array_equal(a, b)
+
+
+def test_ibl_errors(libs):
+    cuda, _ = libs
+    r = Renderer("c1", 64, 36, library=cuda)
+    with pytest.raises(abi.SkyError):
+        r.ctx.ibl_precompute()
+    with pytest.raises(abi.SkyError):
+        r.ctx.read(abi.RES_PREFILTERED_RADIANCE)
