@@ -74,10 +74,20 @@ int SKY_FN(env_brdf_lut)(SkyContext* ctx);
  * (ComputeObjectLuminance / GetAmbient, AtmosphereRenderer.glsl:284-324, BRDF.glsl:108-130). */
 int SKY_FN(ibl_precompute)(SkyContext* ctx);
 
+/* AtmosphereRenderParameters::albedo / normal / orm (AtmosphereRenderer.h:37-41): the G-buffer the object branch of K6 reads,
+ * in the formats GBuffer.cpp:19-21 allocates -- albedo GL_RGBA8 uchar4[H][W], normal GL_RGBA16_SNORM short4[H][W], orm
+ * GL_RGBA16 ushort4[H][W] (occlusion, roughness, metallic) -- at the size of the following sky_composite calls.  The
+ * pointers are borrowed until the next call; three null pointers unbind the G-buffer.  It is an INPUT: the meshes / ground
+ * pass that would rasterise it are outside the path. */
+int SKY_FN(set_gbuffer)(SkyContext* ctx, const void* albedo_dev, const void* normal_dev, const void* orm_dev);
+
 /* AtmosphereRenderer::Render full-screen pass (AtmosphereRenderer.cpp:246-250, K6), sky / aerial
  * perspective / sun-disc branches.  depth_dev: float[H][W] in [0,1]; hdr_dev: half4[H][W] (written).
- * Ground/object pixels receive the atmosphere in-scatter only and alpha = 0 marks them
- * (object shading is outside the hot path). */
+ * Object pixels (depth != 1): with a G-buffer bound (sky_set_gbuffer; needs sky_env_brdf_lut and sky_ibl_precompute) they are
+ * shaded like the reference's (ComputeObjectLuminance + SampleVisibilityFromShadowMap, AtmosphereRenderer.glsl:284-343,
+ * 404-410: sun through the transmittance LUT, GGX / Lambert BRDF, SH9 + prefiltered-cube ambient, mesh shadow map x cloud
+ * shadow map; PCSS_ENABLE 0 as in every shipped config) and alpha = 1; without one they receive the atmosphere in-scatter
+ * only and alpha = 0 marks them. */
 int SKY_FN(composite)(SkyContext* ctx, const float* depth_dev, void* hdr_dev, int width, int height);
 
 /* DynamicTexture::Generate (VolumetricCloudDefaultMaterial.h:39-49): K8/K9/K10 + mip chain. */

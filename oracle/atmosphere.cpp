@@ -1,5 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see glsl.h).  K1-K6 entry points.
 #include "atmosphere.h"
+#include "ibl.h"
 
 namespace orc {
 
@@ -174,6 +175,132 @@ float SampleRayScatterVisibility(const Image<1>& shadow_froxel, vec2 uv, float d
     return mix(1.0f, f, clamp(1.0f / w, 0.0f, 1.0f));
 }
 
+namespace {
+// texture(sampler2D, uv) with LinearNoMipmapClampToEdge (AtmosphereRenderer.cpp:200-217) over a normalised-integer image
+template <class T, class Decode>
+vec4 gbuffer_texture(const T* img, int w, int h, vec2 uv, Decode decode) {
+    float x = uv.x * float(w) - 0.5f, y = uv.y * float(h) - 0.5f;
+    float fx = std::floor(x), fy = std::floor(y);
+    float a = x - fx, b = y - fy;
+    int i0 = int(fx), j0 = int(fy);
+    auto T4 = [&](int i, int j) {
+        const T* p = img + (size_t(clamp(j, 0, h - 1)) * w + clamp(i, 0, w - 1)) * 4;
+        return vec4(decode(p[0]), decode(p[1]), decode(p[2]), decode(p[3]));
+    };
+    return (1.0f - a) * (1.0f - b) * T4(i0, j0) + a * (1.0f - b) * T4(i0 + 1, j0) + (1.0f - a) * b * T4(i0, j0 + 1) + a * b * T4(i0 + 1, j0 + 1);
+}
+inline vec3 mix3(vec3 a, vec3 b, vec3 t) { return vec3(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z)); }
+// shaders/Base/BRDF.glsl:26-49
+inline float Pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
+inline vec3 F_Schlick(float HdotV, vec3 F0) { return F0 + (vec3(1.0f) - F0) * Pow5(1.0f - HdotV); }
+inline float D_GGX(float a, float NdotH) {
+    float a2 = a * a;
+    float d = (NdotH * a2 - NdotH) * NdotH + 1.0f;
+    return a2 / (PI * d * d);
+}
+inline float Vis_SmithJointApprox(float a, float NdotV, float NdotL) {
+    float Vis_SmithV = NdotL * (NdotV * (1.0f - a) + a);
+    float Vis_SmithL = NdotV * (NdotL * (1.0f - a) + a);
+    return 0.5f / max(Vis_SmithV + Vis_SmithL, 1e-9f);
+}
+struct MaterialData { vec3 F0, diffuse, normal; float roughness; };
+// shaders/Base/BRDF.glsl:69-78
+inline vec3 BRDF(float NdotL, float NdotV, float NdotH, float HdotV, const MaterialData& data) {
+    float a = data.roughness * data.roughness;
+    float D = min(D_GGX(a, NdotH), 1e9f);
+    float Vis = Vis_SmithJointApprox(a, NdotV, NdotL);
+    vec3 F = F_Schlick(HdotV, data.F0);
+    vec3 specular = vec3(D * Vis);
+    vec3 diffuse = INV_PI * data.diffuse;
+    return mix3(diffuse, specular, F);
+}
+// shaders/Base/BRDF.glsl:81-106
+inline vec3 GetSHIrradiance(vec3 N, const vec4* Llm) {
+    const float c1 = 0.429043f, c2 = 0.511664f, c3 = 0.743125f, c4 = 0.886227f, c5 = 0.247708f;
+    vec3 L00 = Llm[0].rgb(), L1_1 = Llm[1].rgb(), L10 = Llm[2].rgb(), L11 = Llm[3].rgb(), L2_2 = Llm[4].rgb(), L2_1 = Llm[5].rgb(),
+         L20 = Llm[6].rgb(), L21 = Llm[7].rgb(), L22 = Llm[8].rgb();
+    float x = N.x, y = N.y, z = N.z;
+    return c1 * (x * x - y * y) * L22 + c3 * (z * z) * L20 + c4 * L00 - c5 * L20
+        + 2.0f * c1 * (x * y * L2_2 + x * z * L21 + y * z * L2_1)
+        + 2.0f * c2 * (x * L11 + y * L1_1 + z * L10);
+}
+}  // namespace
+
+// AtmosphereRenderer.glsl:333-343 with PCSS_ENABLE 0 (every shipped config); the mesh shadow map is an input that is all 1.0
+// (lit) until the caller writes SKY_RES_MESH_SHADOW_MAP
+float AtmosphereRenderer::SampleVisibilityFromShadowMap(vec3 position) const {
+    float visibility = mesh_shadow_map ? Atmosphere::GetVisibilityFromShadowMap(*mesh_shadow_map, mat4(u.light_view_projection), position) : 1.0f;
+    if (object->cloud_shadow_map) {
+        vec3 light_ndc = ProjectiveMul(mat4(u.uCloudShadowMapMat), position);
+        // SampleCloudShadowTransmittance, VolumetricCloudShadowInterface.glsl:4-8; sampler border (1e10, 1), VolumetricCloud.cpp:106-112
+        Sampler s; s.wrap = CLAMP_TO_BORDER; s.border = vec4(1e10f, 1.0f, 0.0f, 0.0f);
+        const float kInvTransitionDepth = 1.0f / 0.5f;
+        vec4 dt = texture_linear(*object->cloud_shadow_map, light_ndc.xy() * 0.5f + 0.5f, s);
+        visibility = min(visibility, mix(dt.y, 1.0f, clamp((dt.x - light_ndc.z) * kInvTransitionDepth, 0.0f, 1.0f)));
+    }
+    return visibility;
+}
+
+// AtmosphereRenderer.glsl:284-324 (LoadMeterialData / BRDF / GetAmbient: shaders/Base/BRDF.glsl:10-23,69-78,108-130)
+vec3 AtmosphereRenderer::ComputeObjectLuminance(vec3 position, vec3 view_direction, float shadow_visibility, vec2 vTexCoord,
+                                                int width, int height) const {
+    float r = length(position - earth_center());
+    vec3 object_up_direction = normalize(position - earth_center());
+    float mu_s = dot(sun_direction(), object_up_direction);
+    vec3 sun_visibility;
+    if (r > atm.u.top_radius) {
+        float near_distance;
+        if (atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu_s, near_distance)) {
+            position += near_distance * sun_direction();
+            r = length(position - earth_center());
+            object_up_direction = normalize(position - earth_center());
+            mu_s = dot(sun_direction(), object_up_direction);
+            sun_visibility = atm.GetSunVisibility(transmittance_texture, r, mu_s);
+        } else {
+            sun_visibility = vec3(1.0f);
+        }
+    } else {
+        sun_visibility = atm.GetSunVisibility(transmittance_texture, r, mu_s);
+    }
+    vec3 solar_illuminance_at_object = atm.solar_illuminance() * sun_visibility;
+
+    vec3 albedo = gbuffer_texture(object->albedo, width, height, vTexCoord, [](uint8_t c) { return float(c) / 255.0f; }).rgb();
+    vec3 normal = gbuffer_texture(object->normal, width, height, vTexCoord, [](int16_t c) { return std::fmax(float(c) / 32767.0f, -1.0f); }).rgb();
+    vec3 orm = gbuffer_texture(object->orm, width, height, vTexCoord, [](uint16_t c) { return float(c) / 65535.0f; }).rgb();
+    MaterialData material_data;
+    float metallic = orm.z;
+    material_data.F0 = vec3(0.04f) * (1.0f - metallic) + albedo * metallic;
+    material_data.diffuse = albedo - albedo * metallic;
+    material_data.normal = normal;
+    material_data.roughness = orm.y;
+
+    vec3 N = material_data.normal;
+    vec3 L = sun_direction();
+    vec3 V = -view_direction;
+    vec3 H = normalize(L + V);
+    float NdotL = clamp(dot(N, L), 0.0f, 1.0f);
+    float NdotV = clamp(dot(N, V), 0.0f, 1.0f);
+    float NdotH = clamp(dot(N, H), 0.0f, 1.0f);
+    float HdotV = clamp(dot(H, V), 0.0f, 1.0f);
+    vec3 brdf = BRDF(NdotL, NdotV, NdotH, HdotV, material_data);
+    vec3 direct_lumiance = brdf * solar_illuminance_at_object * (NdotL * shadow_visibility);
+    // GetAmbient(env_brdf_lut, ROUGHNESS_COUNT - 1, prefiltered_radiance_texture, V, material_data, Llm)
+    vec3 ambient_lumiance;
+    {
+        const float roughness_lod_max = float(SKY_IBL_ROUGHNESS_COUNT - 1);
+        vec3 F = F_Schlick(NdotV * 0.8f + 0.2f, material_data.F0);
+        vec3 approx_irradiance_over_pi = GetSHIrradiance(N, object->Llm) * INV_PI;
+        vec3 diffuse = (material_data.diffuse - material_data.diffuse * F) * approx_irradiance_over_pi;
+        vec3 R = 2.0f * NdotV * N - V;
+        vec3 prefiltered_radiance = TextureCubeLod(*object->prefiltered, R, material_data.roughness * roughness_lod_max).rgb();
+        vec4 brdf_lut = texture_linear(*object->env_brdf_lut, vec2(NdotV, material_data.roughness), Sampler());
+        vec3 specular = prefiltered_radiance * (material_data.F0 * brdf_lut.x + vec3(brdf_lut.y));
+        ambient_lumiance = diffuse + specular;
+    }
+    float ambient_fade = clamp(10.0f - 0.1f * length(position - camera_position()), 0.0f, 1.0f);
+    return direct_lumiance + ambient_lumiance * ambient_fade;
+}
+
 // K6 -- AtmosphereRenderer.glsl:345-432.  gl_FragCoord.xy = pixel + 0.5, vTexCoord = that / size.
 // Object pixels (depth != 1) get the in-scatter only and alpha 0: ComputeObjectLuminance
 // (:284-324) needs the G-buffer + IBL chain that SURVEY.md 8f-1 leaves for later.
@@ -228,7 +355,14 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
 
             float alpha = 1.0f;
             if (intersect_object) {
-                alpha = 0.0f;
+                if (object) {  // :404-410
+                    float shadow_visibility = SampleVisibilityFromShadowMap(fragment_position);
+                    if (ex.moon_shadow)
+                        shadow_visibility *= atm.GetVisibilityFromMoonShadow(ex.moon_position - fragment_position, ex.moon_radius, sun_direction());
+                    luminance += transmittance * ComputeObjectLuminance(fragment_position, view_direction, shadow_visibility, vTexCoord, width, height);
+                } else {
+                    alpha = 0.0f;
+                }
             } else if (dot(view_direction, sun_direction()) >= std::cos(atm.u.sun_angular_radius)) {
                 vec3 uu(1.0f, 1.0f, 1.0f);
                 vec3 a(0.397f, 0.503f, 0.652f);

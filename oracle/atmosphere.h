@@ -313,6 +313,20 @@ struct Atmosphere {
     void BakeMultiscattering(const Image<4>& transmittance, Image<4>& out) const;
 };
 
+struct CubeChain;  // ibl.h
+
+// Inputs of the object branch of K6 (AtmosphereRenderer.glsl:284-343,404-410): the G-buffer the host binds
+// (AtmosphereRenderer.h:37-41; formats GBuffer.cpp:19-21), the IBL chain (ibl.h) and the cloud shadow map (K12 output).
+struct ObjectShading {
+    const uint8_t* albedo = nullptr;    // GL_RGBA8        [H][W][4]
+    const int16_t* normal = nullptr;    // GL_RGBA16_SNORM [H][W][4]
+    const uint16_t* orm = nullptr;      // GL_RGBA16       [H][W][4]
+    const Image<2>* env_brdf_lut = nullptr;
+    const CubeChain* prefiltered = nullptr;
+    const vec4* Llm = nullptr;
+    const Image<2>* cloud_shadow_map = nullptr;  // shadow_maps_[2]; null before the first shadow pass (visibility 1)
+};
+
 // AtmosphereRenderer.glsl K3-K6.
 struct AtmosphereRenderer {
     const Atmosphere& atm;
@@ -324,6 +338,10 @@ struct AtmosphereRenderer {
     int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: rows the composite owns
     const Image<4>* star_map = nullptr;  // GL_SRGB8 star map decoded to linear RGB (Textures.cpp:43-50); null: no star term
     const Image<1>* mesh_shadow_map = nullptr;  // DEPTH32F 2048^2 (ShadowMap.cpp:8-27), used when cfg.volumetric_light
+    const ObjectShading* object = nullptr;      // null: object pixels keep the in-scatter alone and alpha 0
+    // AtmosphereRenderer.glsl:284-324 and :333-343
+    vec3 ComputeObjectLuminance(vec3 position, vec3 view_direction, float shadow_visibility, vec2 vTexCoord, int width, int height) const;
+    float SampleVisibilityFromShadowMap(vec3 position) const;
 
     // AtmosphereRenderer.glsl:326-331 (sampler LinearNoMipmapClampToEdge, AtmosphereRenderer.cpp:204)
     vec3 GetStarLuminance(vec3 view_direction) const {

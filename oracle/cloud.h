@@ -24,6 +24,7 @@ struct CloudScene {
     Image<2> env_brdf_lut;       // K22: RG16 512x512
     vec4 env_sh[9];              // K23
     CubeChain prefiltered;       // K24: 5 levels from 128^2
+    ObjectShading gbuffer;       // sky_set_gbuffer (albedo / normal / orm only)
     SkyAtmosphereRenderBufferData render_u{};
     SkyLutConfig lut_cfg{};
 

@@ -147,10 +147,26 @@ int orc_ibl_precompute(SkyContext* ctx) {
     return 0;
 }
 
+int orc_set_gbuffer(SkyContext* ctx, const void* albedo, const void* normal, const void* orm) {
+    if ((albedo != nullptr) != (normal != nullptr) || (albedo != nullptr) != (orm != nullptr)) return fail(ctx, "set_gbuffer: bind all three targets or none");
+    ctx->scene.gbuffer.albedo = static_cast<const uint8_t*>(albedo);
+    ctx->scene.gbuffer.normal = static_cast<const int16_t*>(normal);
+    ctx->scene.gbuffer.orm = static_cast<const uint16_t*>(orm);
+    return 0;
+}
+
 int orc_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
     CloudScene& s = ctx->scene;
     AtmosphereRenderer ar{s.atm, s.render_u, s.lut_cfg, s.transmittance, s.multiscattering, &s.blue_noise};
     if (s.lut_cfg.volumetric_light) ar.mesh_shadow_map = &mesh_shadow_map(s);
+    ObjectShading object = s.gbuffer;
+    if (object.albedo) {
+        if (s.env_brdf_lut.w == 0 || s.prefiltered.levels.empty()) return fail(ctx, "composite: a G-buffer is bound but env_brdf_lut / ibl_precompute have not run");
+        object.env_brdf_lut = &s.env_brdf_lut; object.prefiltered = &s.prefiltered; object.Llm = s.env_sh;
+        if (s.shadow_maps[2].w > 0) object.cloud_shadow_map = &s.shadow_maps[2];
+        if (s.mesh_shadow_map.w > 0) ar.mesh_shadow_map = &s.mesh_shadow_map;
+        ar.object = &object;
+    }
     if (s.star_map.w > 0) ar.star_map = &s.star_map;
     ar.out_band_rows = s.out_band_rows; ar.out_band_index = s.out_band_index; ar.out_band_count = s.out_band_count;
     const Image<1>* froxel = (s.shadow_froxel.w > 0) ? &s.shadow_froxel : nullptr;

@@ -256,6 +256,14 @@ struct RefCompositeIO {
     int star_w, star_h;
     float* out;                      // [h][w][4]: FragColor
     int width, height;
+    // object shading; albedo == null: an all-zero G-buffer, which makes ComputeObjectLuminance vanish
+    const float* albedo;             // [h][w][4] decoded GL_RGBA8
+    const float* normal;             // [h][w][4] decoded GL_RGBA16_SNORM
+    const float* orm;                // [h][w][4] decoded GL_RGBA16
+    const float* env_brdf_lut;       // [512][512][4] decoded GL_RG16
+    const float* prefiltered;        // 5 levels from 128^2, concatenated, [6][n][n][4]
+    const float* llm;                // [9][4]
+    const float* cloud_shadow_map;   // [512][512][4] (depth, transmittance) or null (unshadowed)
 };
 
 extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg,
@@ -275,9 +283,9 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
         ref_bind_texture(multiscattering_texture, io->multiscattering, 32, 32, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);         \
         ref_bind_texture(depth_stencil_texture, io->depth, W, H, 1, ref::CLAMP_TO_EDGE, ref::NEAREST);                      \
         /* an all-zero G-buffer makes ComputeObjectLuminance vanish: object pixels keep the in-scatter term alone */        \
-        ref_bind_texture(albedo_texture, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                  \
-        ref_bind_texture(normal_texture, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                  \
-        ref_bind_texture(orm_texture, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                     \
+        ref_bind_texture(albedo_texture, io->albedo ? io->albedo : zero4, io->albedo ? W : 1, io->albedo ? H : 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
+        ref_bind_texture(normal_texture, io->albedo ? io->normal : zero4, io->albedo ? W : 1, io->albedo ? H : 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
+        ref_bind_texture(orm_texture, io->albedo ? io->orm : zero4, io->albedo ? W : 1, io->albedo ? H : 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         ref::NS::shadow_map_texture.levels.clear();  /* no mesh shadow map: lit */                                          \
         ref_bind_texture(blue_noise, io->blue_noise, 64, 64, 1, ref::REPEAT, ref::NEAREST);                                 \
         if (io->star) ref_bind_texture(star_luminance, io->star, io->star_w, io->star_h, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
@@ -287,12 +295,29 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
         ref_bind_texture(aerial_perspective_luminance_texture, io->ap_luminance, 32, 32, cfg->aerial_perspective_depth, ref::CLAMP_TO_EDGE, ref::LINEAR);    \
         ref_bind_texture(aerial_perspective_transmittance_texture, io->ap_transmittance, 32, 32, cfg->aerial_perspective_depth, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         ref_bind_texture(shadow_map_depth_sampler, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::NEAREST);                        \
-        ref_bind_texture(cloud_shadow_map, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                 \
+        if (io->albedo && io->cloud_shadow_map) {                                                                           \
+            ref_bind_texture(cloud_shadow_map, io->cloud_shadow_map, 512, 512, 1, ref::CLAMP_TO_BORDER, ref::LINEAR);       \
+            ref::NS::cloud_shadow_map.border = ref::vec4(1e10f, 1.0f, 0.0f, 0.0f);  /* VolumetricCloud.cpp:106-112 */       \
+        } else ref_bind_texture(cloud_shadow_map, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                          \
         if (io->froxel) ref_bind_texture(cloud_shadow_froxel, io->froxel, io->fw, io->fh, io->fd, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         else ref_bind_texture(cloud_shadow_froxel, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                         \
-        ref_bind_texture(prefiltered_radiance_texture, zero_cube, 1, 1, 6, ref::CLAMP_TO_EDGE, ref::LINEAR);                \
-        ref_bind_texture(env_brdf_lut, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                    \
-        for (int i = 0; i < 9; ++i) Llm[i] = ref::vec4(0.0f);                                                               \
+        if (io->albedo) {                                                                                                   \
+            ref::Sampler& pr = prefiltered_radiance_texture;                                                                \
+            pr.levels.assign(ROUGHNESS_COUNT, ref::Image());                                                                \
+            const float* lp = io->prefiltered;                                                                              \
+            for (int l = 0, n = 128; l < ROUGHNESS_COUNT; ++l, n >>= 1) {                                                   \
+                ref::Image& im = pr.levels[l];                                                                              \
+                im.data = const_cast<float*>(lp); im.w = n; im.h = n; im.d = 6; im.fmt = ref::FMT_RGBA32F;                  \
+                lp += size_t(6) * n * n * 4;                                                                                \
+            }                                                                                                               \
+            pr.wrap = ref::CLAMP_TO_EDGE; pr.mag = pr.min_filter = ref::LINEAR;                                             \
+            ref_bind_texture(env_brdf_lut, io->env_brdf_lut, 512, 512, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                 \
+            for (int i = 0; i < 9; ++i) Llm[i] = ref::vec4(io->llm[i * 4], io->llm[i * 4 + 1], io->llm[i * 4 + 2], io->llm[i * 4 + 3]); \
+        } else {                                                                                                            \
+            ref_bind_texture(prefiltered_radiance_texture, zero_cube, 1, 1, 6, ref::CLAMP_TO_EDGE, ref::LINEAR);            \
+            ref_bind_texture(env_brdf_lut, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                \
+            for (int i = 0; i < 9; ++i) Llm[i] = ref::vec4(0.0f);                                                           \
+        }                                                                                                                   \
         _Pragma("omp parallel for schedule(dynamic, 4)")                                                                    \
         for (int py = 0; py < H; ++py)                                                                                      \
             for (int px = 0; px < W; ++px) {                                                                                \

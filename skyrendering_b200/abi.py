@@ -175,6 +175,7 @@ KERNEL_API = {
     "atmosphere_luts": ([P(AtmosphereRenderBufferData), P(LutConfig)], I),
     "composite": ([_VOIDP, _VOIDP, I, I], I),
     "env_brdf_lut": ([], I),
+    "set_gbuffer": ([_VOIDP, _VOIDP, _VOIDP], I),
     "ibl_precompute": ([], I),
     "noise_generate": ([I, P(NoiseCreateInfo)], I),
     "voxel_upload": ([_VOIDP, I, I, I], I),
@@ -304,6 +305,12 @@ class Context:
     def atmosphere_luts(self, render, cfg): self._call("atmosphere_luts", C.byref(render), C.byref(cfg))
     def composite(self, depth, hdr, w, h): self._call("composite", _ptr(depth), _ptr(hdr), w, h)
     def env_brdf_lut(self): self._call("env_brdf_lut")
+
+    def set_gbuffer(self, albedo=None, normal=None, orm=None):
+        """albedo uint8 [H][W][4], normal int16 [H][W][4] (SNORM), orm uint16 [H][W][4] in the library's memory space; the
+        arrays are kept alive here until the next call."""
+        self._gbuffer = (albedo, normal, orm)
+        self._call("set_gbuffer", *[None if a is None else _ptr(a) for a in self._gbuffer])
     def ibl_precompute(self): self._call("ibl_precompute")
 
     def read_cube_chain(self, res, size):

@@ -97,6 +97,38 @@ def synthetic_voxel_grid_large(scale, seed=0, blobs=64, device="cuda", slab=16):
     return out
 
 
+def synthetic_gbuffer(width, height, up_direction, seed=0):
+    """A synthetic G-buffer in the formats GBuffer.cpp:19-21 allocates -- albedo GL_RGBA8, normal GL_RGBA16_SNORM, orm GL_RGBA16 --
+    standing in for the rasterised ground / mesh passes that are outside the path (the object branch of K6 only reads it).
+    Smooth fields rather than white noise, so that a frame rendered from it looks like terrain: unit normals within ~25 degrees
+    of `up_direction`, mid-grey albedo, roughness 0.15..1, metallic 0..0.6."""
+    rng = np.random.default_rng(seed)
+    def field(channels):
+        coarse = rng.random((max(height // 16, 2), max(width // 16, 2), channels)).astype(np.float32)
+        yi = np.linspace(0, coarse.shape[0] - 1, height, dtype=np.float32)
+        xi = np.linspace(0, coarse.shape[1] - 1, width, dtype=np.float32)
+        y0 = np.minimum(yi.astype(int), coarse.shape[0] - 2); x0 = np.minimum(xi.astype(int), coarse.shape[1] - 2)
+        fy = (yi - y0)[:, None, None]; fx = (xi - x0)[None, :, None]
+        c = coarse
+        return ((c[y0][:, x0] * (1 - fx) + c[y0][:, x0 + 1] * fx) * (1 - fy) + (c[y0 + 1][:, x0] * (1 - fx) + c[y0 + 1][:, x0 + 1] * fx) * fy)
+    albedo = np.empty((height, width, 4), np.uint8)
+    albedo[..., :3] = np.rint((0.15 + 0.5 * field(3)) * 255.0)
+    albedo[..., 3] = 255
+    up = np.asarray(up_direction, np.float32)
+    n = up[None, None, :] + 0.45 * (field(3) - 0.5)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    normal = np.empty((height, width, 4), np.int16)
+    normal[..., :3] = np.rint(n * 32767.0)
+    normal[..., 3] = 32767
+    f = field(2)
+    orm = np.empty((height, width, 4), np.uint16)
+    orm[..., 0] = 65535
+    orm[..., 1] = np.rint((0.15 + 0.85 * f[..., 0]) * 65535.0)
+    orm[..., 2] = np.rint(0.6 * f[..., 1] * 65535.0)
+    orm[..., 3] = 65535
+    return albedo, normal, orm
+
+
 class Renderer:
     def __init__(self, scene, width, height, library=None, device=0, stream=0, blue_noise=None):
         self.scene = scene if isinstance(scene, Scene) else Scene.from_file(scene_path(scene))

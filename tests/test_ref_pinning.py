@@ -184,6 +184,45 @@ def test_oracle_composite_is_the_reference_fragment_program(scene):
 
 
 @pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("scene", ["c2", "c3"])
+def test_oracle_object_shading_is_the_reference_fragment_program(scene):
+    """The object branch of K6: ComputeObjectLuminance + SampleVisibilityFromShadowMap + BRDF.glsl's
+    LoadMeterialData / BRDF / GetAmbient of the reference's fragment program on a synthetic G-buffer, the IBL state of the
+    frame (K22-K24) and the frame's cloud shadow map -- RGB bit-identical to the oracle in every pixel, alpha 1 everywhere."""
+    from skyrendering_b200.renderer import load_blue_noise, synthetic_gbuffer
+    from tests.parity import make_buffers
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 192, 108
+    r = Renderer(scene, w, h, library=orc)
+    r.enable_ibl()
+    r.prime()
+    depth_np = r.scene.ground_depth(w, h)
+    depth, hdr = make_buffers(w, h, depth_np, "cpu")
+    r.frame(depth, hdr, 0.0)
+    froxel = r.ctx.read(abi.RES_SHADOW_FROXEL)
+    plain = hdr.astype(np.float32).copy()
+    hdr[...] = 0
+    r.ctx.composite(depth, hdr, w, h)
+    plain = hdr.astype(np.float32).copy()
+    gbuffer = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=3)
+    r.ctx.set_gbuffer(*gbuffer)
+    r.ctx.composite(depth, hdr, w, h)
+    got = hdr.astype(np.float32)
+    want = refpin.ref_composite(ref, r, depth_np, w, h, load_blue_noise(), froxel=froxel, gbuffer=gbuffer,
+                                cloud_shadow_map=r.ctx.read(abi.RES_SHADOW_MAP))
+    want16 = want.astype(np.float16).astype(np.float32)
+    assert np.all(np.isfinite(want16))
+    assert np.array_equal(got, want16)
+    obj = depth_np != 1.0
+    assert 0.1 < obj.mean() < 0.9 and np.all(got[..., 3] == 1.0)
+    # the shading is there (object pixels got brighter than their in-scatter alone), sky pixels are untouched
+    assert (got[obj][:, :3] > plain[obj][:, :3]).mean() > 0.9 and np.array_equal(got[~obj][:, :3], plain[~obj][:, :3])
+    r.ctx.set_gbuffer(None, None, None)
+    r.ctx.composite(depth, hdr, w, h)
+    assert np.array_equal(hdr.astype(np.float32), plain)
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
 def test_oracle_star_term_is_the_reference_fragment_program():
     """GetStarLuminance (AtmosphereRenderer.glsl:326-331,427-429) through a GL_SRGB8 star map: bit-identical, and visible."""
     from skyrendering_b200.renderer import load_blue_noise
