@@ -465,8 +465,16 @@ int sky_ibl_precompute(SkyContext* ctx) {
     return launch_ibl_precompute(ctx);
 }
 
+int sky_set_gbuffer(SkyContext* ctx, const void* albedo, const void* normal, const void* orm) {
+    if ((albedo != nullptr) != (normal != nullptr) || (albedo != nullptr) != (orm != nullptr)) return sky_fail(ctx, "set_gbuffer: bind all three targets or none");
+    ctx->gbuffer_albedo = albedo; ctx->gbuffer_normal = normal; ctx->gbuffer_orm = orm;
+    return 0;
+}
+
 int sky_composite(SkyContext* ctx, const float* depth, void* hdr, int width, int height) {
     if (!ctx->sky_lum.p) return sky_fail(ctx, "atmosphere LUTs have not been baked");
+    if (ctx->gbuffer_albedo && (!ctx->env_brdf_lut.p || !ctx->ibl_valid))
+        return sky_fail(ctx, "composite: a G-buffer is bound but env_brdf_lut / ibl_precompute have not run");
     if (int e = luts_join(ctx)) return e;
     if (ctx->overlap) {
         if (ctx->lane2_reads_luts) { if (int e = lanes_join(ctx)) return e; }  // out-of-order use: a cloud frame is still open

@@ -5,6 +5,7 @@
 // so keeping the reference's unfused fp32 operation order is worth more than the FMAs.
 #include "../../include/sky_detmath.h"
 #include "atmosphere_dev.cuh"
+#include "ibl_dev.cuh"
 #include "context.h"
 
 // The LUT kernels use the deterministic fp32 elementary functions shared with the oracle (bit-for-bit
@@ -319,6 +320,21 @@ __global__ void __launch_bounds__(256) k_luts_to_half(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------- K3 / K4 / K5 / K6
+// Inputs of K6's object branch (AtmosphereRenderer.glsl:284-343,404-410): G-buffer (sky_set_gbuffer), IBL chain
+// (ibl.cu), cloud shadow map (K12) and the mesh shadow map (an input, all 1.0 until written)
+struct ObjectParams {
+    const uchar4* albedo;        // GL_RGBA8
+    const short4* normal;        // GL_RGBA16_SNORM
+    const ushort4* orm;          // GL_RGBA16
+    const ushort2* env_brdf_lut; // GL_RG16 [S][S]
+    int env_brdf_size;
+    CubeChainView prefiltered;   // SKY_IBL_ROUGHNESS_COUNT levels
+    const float4* Llm;           // [9]
+    const float2* cloud_shadow_map;  // shadow_maps_[2]: [512][512] (depth, transmittance), zero until the first shadow pass like the reference's
+    int cloud_shadow_size;
+    ScatterExtras mesh;          // shadow_size == 0: no mesh shadow map allocated (lit)
+};
+
 struct RenderParams {
     AtmosphereModel atm;
     SkyAtmosphereRenderBufferData r;  // AtmosphereRenderer.glsl:25-50
@@ -336,6 +352,7 @@ struct RenderParams {
     half4* hdr;
     int width, height;
     int band_rows, band_index, band_count;  // sky_set_output_bands: blockIdx.y counts OWNED rows (band_count <= 1: all rows)
+    ObjectParams object;  // K6 object branch (template flag OBJECT)
 };
 
 // AtmosphereRenderer.glsl:56-72
@@ -519,12 +536,135 @@ __global__ void __launch_bounds__(128) k5_environment(const __grid_constant__ Re
     P.env_out[(size_t(index) * S + y) * S + x] = to_half4(f4(luminance, 0.0f));
 }
 
+// ---- object branch of K6 ----------------------------------------------------------------------------------------------
+// texture(sampler2D, uv), LinearNoMipmapClampToEdge, over a normalised-integer G-buffer target (exact fp32 weights)
+template <class T4, class Decode>
+SKY_D float3 gbuffer_texture(const T4* img, int w, int h, float2 uv, Decode decode) {
+    float x = uv.x * float(w) - 0.5f, y = uv.y * float(h) - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    int i0 = clampi(int(fx), 0, w - 1), i1 = clampi(int(fx) + 1, 0, w - 1), j0 = clampi(int(fy), 0, h - 1), j1 = clampi(int(fy) + 1, 0, h - 1);
+    auto T = [&](int i, int j) { T4 c = __ldg(img + size_t(j) * w + i); return f3(decode(c.x), decode(c.y), decode(c.z)); };
+    return (1.0f - a) * (1.0f - b) * T(i0, j0) + a * (1.0f - b) * T(i1, j0) + (1.0f - a) * b * T(i0, j1) + a * b * T(i1, j1);
+}
+// shaders/Base/BRDF.glsl:26-49
+SKY_D float Pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
+SKY_D float3 F_Schlick(float HdotV, float3 F0) { return F0 + (f3(1.0f) - F0) * Pow5(1.0f - HdotV); }
+SKY_D float D_GGX(float a, float NdotH) {
+    float a2 = a * a;
+    float d = (NdotH * a2 - NdotH) * NdotH + 1.0f;
+    return a2 / (kPi * d * d);
+}
+SKY_D float Vis_SmithJointApprox(float a, float NdotV, float NdotL) {
+    float Vis_SmithV = NdotL * (NdotV * (1.0f - a) + a);
+    float Vis_SmithL = NdotV * (NdotL * (1.0f - a) + a);
+    return 0.5f / fmaxf(Vis_SmithV + Vis_SmithL, 1e-9f);
+}
+SKY_D float3 mix3v(float3 a, float3 b, float3 t) { return f3(mixf(a.x, b.x, t.x), mixf(a.y, b.y, t.y), mixf(a.z, b.z, t.z)); }
+// shaders/Base/BRDF.glsl:81-106
+SKY_D float3 GetSHIrradiance(float3 N, const float4* Llm) {
+    const float c1 = 0.429043f, c2 = 0.511664f, c3 = 0.743125f, c4 = 0.886227f, c5 = 0.247708f;
+    float3 L00 = xyz(__ldg(Llm + 0)), L1_1 = xyz(__ldg(Llm + 1)), L10 = xyz(__ldg(Llm + 2)), L11 = xyz(__ldg(Llm + 3)), L2_2 = xyz(__ldg(Llm + 4)),
+           L2_1 = xyz(__ldg(Llm + 5)), L20 = xyz(__ldg(Llm + 6)), L21 = xyz(__ldg(Llm + 7)), L22 = xyz(__ldg(Llm + 8));
+    float x = N.x, y = N.y, z = N.z;
+    return c1 * (x * x - y * y) * L22 + c3 * (z * z) * L20 + c4 * L00 - c5 * L20
+        + 2.0f * c1 * (x * y * L2_2 + x * z * L21 + y * z * L2_1)
+        + 2.0f * c2 * (x * L11 + y * L1_1 + z * L10);
+}
+// AtmosphereRenderer.glsl:333-343 with PCSS_ENABLE 0; SampleCloudShadowTransmittance (VolumetricCloudShadowInterface.glsl:4-8)
+// through the cloud shadow sampler: LINEAR, CLAMP_TO_BORDER (1e10, 1) (VolumetricCloud.cpp:106-112)
+SKY_D float SampleVisibilityFromShadowMap(const RenderParams& P, float3 position) {
+    const ObjectParams& O = P.object;
+    float visibility = O.mesh.shadow_size > 0 ? GetVisibilityFromShadowMap(O.mesh, position) : 1.0f;
+    if (O.cloud_shadow_map) {
+        float3 light_ndc = projective_mul(P.r.uCloudShadowMapMat, position);
+        const int S = O.cloud_shadow_size;
+        float x = (light_ndc.x * 0.5f + 0.5f) * float(S) - 0.5f, y = (light_ndc.y * 0.5f + 0.5f) * float(S) - 0.5f;
+        float fx = floorf(x), fy = floorf(y);
+        float a = x - fx, b = y - fy;
+        auto T = [&](float i, float j) {
+            bool inside = i >= 0.0f && j >= 0.0f && i < float(S) && j < float(S);
+            return inside ? __ldg(O.cloud_shadow_map + size_t(int(j)) * S + int(i)) : f2(1e10f, 1.0f);
+        };
+        float2 dt = (1.0f - a) * (1.0f - b) * T(fx, fy) + a * (1.0f - b) * T(fx + 1.0f, fy) + (1.0f - a) * b * T(fx, fy + 1.0f) + a * b * T(fx + 1.0f, fy + 1.0f);
+        const float kInvTransitionDepth = 1.0f / 0.5f;
+        visibility = fminf(visibility, mixf(dt.y, 1.0f, clampf((dt.x - light_ndc.z) * kInvTransitionDepth, 0.0f, 1.0f)));
+    }
+    return visibility;
+}
+// AtmosphereRenderer.glsl:284-324 (LoadMeterialData / BRDF / GetAmbient: shaders/Base/BRDF.glsl:10-23,69-78,108-130)
+SKY_D float3 ComputeObjectLuminance(const RenderParams& P, float3 position, float3 view_direction, float shadow_visibility, float2 vTexCoord) {
+    const ObjectParams& O = P.object;
+    const float3 earth_center = f3(P.r.earth_center), sun_direction = f3(P.r.sun_direction);
+    float r = length(position - earth_center);
+    float3 object_up_direction = normalize(position - earth_center);
+    float mu_s = dot(sun_direction, object_up_direction);
+    float3 sun_visibility;
+    if (r > P.atm.u.top_radius) {
+        float near_distance;
+        if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu_s, near_distance)) {
+            position += near_distance * sun_direction;
+            r = length(position - earth_center);
+            object_up_direction = normalize(position - earth_center);
+            mu_s = dot(sun_direction, object_up_direction);
+            sun_visibility = P.atm.GetSunVisibility(P.transmittance, r, mu_s);
+        } else {
+            sun_visibility = f3(1.0f);
+        }
+    } else {
+        sun_visibility = P.atm.GetSunVisibility(P.transmittance, r, mu_s);
+    }
+    float3 solar_illuminance_at_object = P.atm.solar_illuminance() * sun_visibility;
+
+    float3 albedo = gbuffer_texture(O.albedo, P.width, P.height, vTexCoord, [](unsigned char c) { return float(c) / 255.0f; });
+    float3 normal = gbuffer_texture(O.normal, P.width, P.height, vTexCoord, [](short c) { return fmaxf(float(c) / 32767.0f, -1.0f); });
+    float3 orm = gbuffer_texture(O.orm, P.width, P.height, vTexCoord, [](unsigned short c) { return float(c) / 65535.0f; });
+    float metallic = orm.z, roughness = orm.y;
+    float3 F0 = f3(0.04f) * (1.0f - metallic) + albedo * metallic;
+    float3 mdiffuse = albedo - albedo * metallic;
+
+    float3 N = normal, L = sun_direction, V = -view_direction;
+    float3 H = normalize(L + V);
+    float NdotL = clampf(dot(N, L), 0.0f, 1.0f), NdotV = clampf(dot(N, V), 0.0f, 1.0f);
+    float NdotH = clampf(dot(N, H), 0.0f, 1.0f), HdotV = clampf(dot(H, V), 0.0f, 1.0f);
+    float3 brdf;
+    {
+        float a = roughness * roughness;
+        float D = fminf(D_GGX(a, NdotH), 1e9f);
+        float Vis = Vis_SmithJointApprox(a, NdotV, NdotL);
+        float3 F = F_Schlick(HdotV, F0);
+        brdf = mix3v(kInvPi * mdiffuse, f3(D * Vis), F);
+    }
+    float3 direct_lumiance = brdf * solar_illuminance_at_object * (NdotL * shadow_visibility);
+    float3 ambient_lumiance;
+    {
+        const float roughness_lod_max = float(SKY_IBL_ROUGHNESS_COUNT - 1);
+        float3 F = F_Schlick(NdotV * 0.8f + 0.2f, F0);
+        float3 approx_irradiance_over_pi = GetSHIrradiance(N, O.Llm) * kInvPi;
+        float3 diffuse = (mdiffuse - mdiffuse * F) * approx_irradiance_over_pi;
+        float3 R = 2.0f * NdotV * N - V;
+        float3 prefiltered_radiance = xyz(TextureCubeLod(O.prefiltered, R, roughness * roughness_lod_max));
+        // texture(env_brdf_lut, vec2(NdotV, roughness)).rg, LinearNoMipmapClampToEdge over GL_RG16
+        const int S = O.env_brdf_size;
+        float x = NdotV * float(S) - 0.5f, y = roughness * float(S) - 0.5f;
+        float fx = floorf(x), fy = floorf(y);
+        float a = x - fx, b = y - fy;
+        int i0 = clampi(int(fx), 0, S - 1), i1 = clampi(int(fx) + 1, 0, S - 1), j0 = clampi(int(fy), 0, S - 1), j1 = clampi(int(fy) + 1, 0, S - 1);
+        auto T = [&](int i, int j) { ushort2 c = __ldg(O.env_brdf_lut + size_t(j) * S + i); return f2(float(c.x) / 65535.0f, float(c.y) / 65535.0f); };
+        float2 lut = (1.0f - a) * (1.0f - b) * T(i0, j0) + a * (1.0f - b) * T(i1, j0) + (1.0f - a) * b * T(i0, j1) + a * b * T(i1, j1);
+        float3 specular = prefiltered_radiance * (F0 * lut.x + f3(lut.y));
+        ambient_lumiance = diffuse + specular;
+    }
+    float ambient_fade = clampf(10.0f - 0.1f * length(position - f3(P.r.camera_position)), 0.0f, 1.0f);
+    return direct_lumiance + ambient_lumiance * ambient_fade;
+}
+
 // K6 -- AtmosphereRenderer.glsl:345-432: sky-view LUT / aerial-perspective LUT / per-pixel raymarch,
 // x cloud-shadow froxel, + sun disc with limb darkening.  Object pixels (depth != 1) get the
 // in-scatter only and alpha = 0 (ComputeObjectLuminance needs the G-buffer + IBL chain);
 // the star-map term of sky pixels (:427-429) is in the same "next" row.
 // HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
-template <bool EXTRA>
+template <bool EXTRA, bool OBJECT>
 __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
     if (P.band_count > 1) py = ((py / P.band_rows) * P.band_count + P.band_index) * P.band_rows + py % P.band_rows;
@@ -568,7 +708,14 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
 
     float alpha = 1.0f;
     if (intersect_object) {
-        alpha = 0.0f;
+        if (OBJECT) {  // :404-410
+            float shadow_visibility = SampleVisibilityFromShadowMap(P, fragment_position);
+            if (EXTRA && P.extras.moon_shadow)
+                shadow_visibility *= GetVisibilityFromMoonShadow(f3(P.extras.moon_position) - fragment_position, P.extras.moon_radius, sun_direction, P.atm.u.sun_angular_radius);
+            luminance += transmittance * ComputeObjectLuminance(P, fragment_position, view_direction, shadow_visibility, vTexCoord);
+        } else {
+            alpha = 0.0f;
+        }
     } else if (dot(view_direction, sun_direction) >= cosf(P.atm.u.sun_angular_radius)) {
         const float3 a = f3(0.397f, 0.503f, 0.652f);
         float cos_view_sun = dot(view_direction, sun_direction);
@@ -621,6 +768,18 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.extras.shadow_size = P.cfg.volumetric_light ? ctx->mesh_shadow_map.w : 0;
     P.extras.shadow_map = ctx->mesh_shadow_map.p;
     for (int i = 0; i < 16; ++i) P.extras.light_view_projection[i] = P.r.light_view_projection[i];
+    ObjectParams& O = P.object;
+    O.albedo = static_cast<const uchar4*>(ctx->gbuffer_albedo);
+    O.normal = static_cast<const short4*>(ctx->gbuffer_normal);
+    O.orm = static_cast<const ushort4*>(ctx->gbuffer_orm);
+    O.env_brdf_lut = ctx->env_brdf_lut.p; O.env_brdf_size = ctx->env_brdf_lut.w;
+    O.prefiltered.n = SKY_IBL_PREFILTERED_RESOLUTION; O.prefiltered.levels = SKY_IBL_ROUGHNESS_COUNT;
+    const half4* pl = ctx->prefiltered;
+    for (int l = 0; l < SKY_IBL_ROUGHNESS_COUNT && pl; ++l) { O.prefiltered.level[l] = pl; pl += size_t(6) * (O.prefiltered.n >> l) * (O.prefiltered.n >> l); }
+    O.Llm = ctx->env_sh.p;
+    O.cloud_shadow_map = ctx->shadow_maps[2].p; O.cloud_shadow_size = ctx->shadow_maps[2].w;
+    O.mesh = P.extras;
+    O.mesh.shadow_size = ctx->mesh_shadow_map.p ? ctx->mesh_shadow_map.w : 0;
     return P;
 }
 
@@ -723,8 +882,13 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
     P.band_rows = ctx->out_band_rows; P.band_index = ctx->out_band_index; P.band_count = ctx->out_band_count;
     const int rows = owned_rows(ctx, h);
     if (rows <= 0) return 0;
-    if (P.cfg.moon_shadow || P.cfg.volumetric_light) k6_composite<true><<<dim3(ceil_div(w, 256), rows), 256, 0, ctx->stream>>>(P);
-    else k6_composite<false><<<dim3(ceil_div(w, 256), rows), 256, 0, ctx->stream>>>(P);
+    const bool extra = P.cfg.moon_shadow || P.cfg.volumetric_light;
+    const dim3 grid(ceil_div(w, 256), rows);
+    if (ctx->gbuffer_albedo) {  // object branch (sky_set_gbuffer); api.cu has checked that the IBL chain exists
+        if (extra) k6_composite<true, true><<<grid, 256, 0, ctx->stream>>>(P);
+        else k6_composite<false, true><<<grid, 256, 0, ctx->stream>>>(P);
+    } else if (extra) k6_composite<true, false><<<grid, 256, 0, ctx->stream>>>(P);
+    else k6_composite<false, false><<<grid, 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
 }

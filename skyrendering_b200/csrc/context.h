@@ -109,6 +109,7 @@ struct SkyContext {
     Lut<float4> env_sh;           // w = 9
     half4* prefiltered = nullptr;
     size_t prefiltered_texels = 0;
+    const void *gbuffer_albedo = nullptr, *gbuffer_normal = nullptr, *gbuffer_orm = nullptr;  // sky_set_gbuffer (borrowed)
     // K6's raymarch fetches the two bake LUTs twice per step through the texture unit, which is what bounds it (ncu: L1/TEX at
     // 86 % of peak with RGBA32F texels, quarter rate); it reads RGBA16F copies (half rate), refreshed after every bake.  The
     // fp16 rounding (2^-11 relative) is far inside the frame tolerance; the strict objects filter the fp32 LUTs in software.

@@ -90,3 +90,72 @@ def test_ibl_errors(libs):
         r.ctx.ibl_precompute()
     with pytest.raises(abi.SkyError):
         r.ctx.read(abi.RES_PREFILTERED_RADIANCE)
+
+
+@pytest.mark.parametrize("scene", ["c2", "c3"])
+@pytest.mark.parametrize("strict", [False, True])
+def test_object_shading_parity(libs, scene, strict):
+    """The object branch of K6 (ComputeObjectLuminance + SampleVisibilityFromShadowMap, AtmosphereRenderer.glsl:284-343,404-410) on
+    a synthetic G-buffer, after a whole frame (so the cloud shadow map and the god-ray froxels exist): the production object
+    within the frame tolerance (HDR relative RMS 1e-2), the strict object at bit level (>= 98 % of the RGBA16F texels
+    bit-equal, relative RMS 1e-4) -- the same bars as the rest of the frame."""
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    from tests.parity import make_buffers, rel_rms
+    cuda, orc = libs
+    w, h = 384, 216
+    out = {}
+    for name, lib, dev in (("cuda", cuda, "cuda"), ("oracle", orc, "cpu")):
+        r = Renderer(scene, w, h, library=lib)
+        if name == "cuda":
+            r.ctx.set_strict_arithmetic(strict)
+        r.enable_ibl()
+        r.prime()
+        depth_np = r.scene.ground_depth(w, h)
+        depth, hdr = make_buffers(w, h, depth_np, dev)
+        r.frame(depth, hdr, 0.0)
+        g = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=3)
+        gb = [torch.from_numpy(a).cuda() for a in g] if dev == "cuda" else list(g)
+        r.ctx.set_gbuffer(*gb)
+        hdr[...] = 0
+        r.ctx.composite(depth, hdr, w, h)
+        if dev == "cuda":
+            r.ctx.sync()
+        shaded = (hdr.cpu().numpy() if dev == "cuda" else hdr).copy()
+        r.ctx.set_gbuffer(None, None, None)
+        hdr[...] = 0
+        r.ctx.composite(depth, hdr, w, h)
+        if dev == "cuda":
+            r.ctx.sync()
+        out[name] = (shaded, (hdr.cpu().numpy() if dev == "cuda" else hdr).copy(), depth_np)
+    (gs, gp, depth_np), (os_, op, _) = out["cuda"], out["oracle"]
+    obj = depth_np != 1.0
+    assert 0.1 < obj.mean() < 0.9
+    assert np.all(gs[..., 3] == 1.0) and np.all(gp[..., 3][obj] == 0.0)
+    a, b = gs.astype(np.float32), os_.astype(np.float32)
+    assert np.all(np.isfinite(a))
+    err = rel_rms(a[obj][:, :3], b[obj][:, :3])
+    equal = float(np.mean(gs.view(np.uint16)[obj] == os_.view(np.uint16)[obj]))
+    print(f"object shading {scene} strict={strict}: relative RMS {err:.2e}, bit-equal texels {equal:.4f}")
+    if strict:
+        assert err <= 1e-4 and equal >= 0.98
+    else:
+        assert err <= 1e-2
+    # shading adds light on object pixels and leaves the sky alone
+    assert (a[obj][:, :3] > gp.astype(np.float32)[obj][:, :3]).mean() > 0.9
+    assert np.array_equal(gs[~obj][:, :3], gp[~obj][:, :3])
+
+
+def test_composite_needs_the_ibl_chain_for_a_gbuffer(libs):
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    from tests.parity import make_buffers
+    cuda, _ = libs
+    w, h = 192, 108
+    r = Renderer("c3", w, h, library=cuda)
+    r.prime()
+    depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), "cuda")
+    gb = [torch.from_numpy(a).cuda() for a in synthetic_gbuffer(w, h, r.render_buffer.up_direction[:])]
+    r.ctx.set_gbuffer(*gb)
+    with pytest.raises(abi.SkyError):
+        r.ctx.composite(depth, hdr, w, h)
+    with pytest.raises(abi.SkyError):
+        r.ctx.set_gbuffer(gb[0], None, None)
