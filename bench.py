@@ -374,6 +374,19 @@ def main():
         frame_overlap_ms = timed_frames(max(args.steps, 3), 1)
         rf.ctx.set_frame_pipelining(True)
         frame_ms = timed_frames(max(args.steps, 3), 1)
+        # the same frame with the reference's object shading: the IBL tail of the LUT phase every frame (cube mips +
+        # K23 + K24, AtmosphereRenderer.cpp:242-244) and K6's object branch on a synthetic G-buffer (ground pixels get sun + ambient)
+        object_variant = None
+        if world == 1:
+            from skyrendering_b200.renderer import synthetic_gbuffer
+            gb = [torch.from_numpy(a).cuda() for a in synthetic_gbuffer(FRAME_W, FRAME_H, rf.render_buffer.up_direction[:], seed=1)]
+            rf.enable_ibl()
+            rf.ctx.set_gbuffer(*gb)
+            object_ms = timed_frames(max(args.steps, 3), 1)
+            rf.ctx.set_gbuffer(None, None, None)
+            rf.enable_ibl(False)
+            object_variant = {"ms_per_frame": object_ms, "extra_gpu_launches": 2,
+                              "gbuffer": "synthetic (albedo RGBA8, normal RGBA16_SNORM, orm RGBA16), 20 B/pixel read on object pixels"}
         # the same frame with the other filtering of the material textures.  north_star allows the texture unit's 8-bit weights
         # where they stay inside the frame tolerance: measured (tools/hw_error_probe.py) the quarter-res render differs from the
         # oracle by 2.43e-3 (384x216) / 3.25e-3 (960x540) relative RMS with EITHER filtering -- the difference is below the noise
@@ -391,6 +404,11 @@ def main():
             "K14_K16": kernel_ms(lambda: rf.ctx.cloud_frame_begin(common, cloud, depth)),
             "K17_K18": kernel_ms(lambda: rf.ctx.cloud_frame_end(depth, hdr)),
         }
+        if object_variant is not None:  # single stream, like parts_ms
+            object_variant["ibl_mips_K23_K24_ms"] = kernel_ms(rf.ctx.ibl_precompute)
+            rf.ctx.set_gbuffer(*gb)
+            object_variant["composite_K6_ms"] = kernel_ms(lambda: rf.ctx.composite(depth, hdr, FRAME_W, FRAME_H))
+            rf.ctx.set_gbuffer(None, None, None)
         rf.ctx.counters_enable(True)
         rf.ctx.cloud_frame_begin(common, cloud, depth)
         rf.ctx.sync()
@@ -427,6 +445,7 @@ def main():
             "roofline_K17_K18": {"bound": "hbm", "achieved": hbm_bytes / (parts["K17_K18"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": hbm_bytes / (parts["K17_K18"] * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind},
             "filtering_variant": other_variant,
+            "object_shading_variant": object_variant,
             "e2e_host_buffers_ms": e2e_frame_ms,
             "e2e_h2d_bytes": FRAME_W * FRAME_H * 12, "e2e_d2h_bytes": FRAME_W * FRAME_H * 8,
         }

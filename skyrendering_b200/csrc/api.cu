@@ -163,6 +163,9 @@ static void swap_lut_sets(SkyContext* ctx) {
         std::swap(ctx->lut_tex_key[i], a.lut_tex_key[i]);
         for (int k = 0; k < 3; ++k) std::swap(ctx->lut_tex_dims[i][k], a.lut_tex_dims[i][k]);
     }
+    std::swap(ctx->env_mips, a.env_mips); std::swap(ctx->env_mips_for, a.env_mips_for); std::swap(ctx->env_mips_texels, a.env_mips_texels);
+    std::swap(ctx->env_sh, a.env_sh); std::swap(ctx->prefiltered, a.prefiltered); std::swap(ctx->prefiltered_texels, a.prefiltered_texels);
+    std::swap(ctx->ibl_valid, a.ibl_valid);
 }
 
 int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
@@ -212,6 +215,9 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->env_brdf_lut); free_lut(ctx->env_sh);
     if (ctx->env_mips) cudaFree(ctx->env_mips);
     if (ctx->prefiltered) cudaFree(ctx->prefiltered);
+    free_lut(ctx->alt.env_sh);
+    if (ctx->alt.env_mips) cudaFree(ctx->alt.env_mips);
+    if (ctx->alt.prefiltered) cudaFree(ctx->alt.prefiltered);
     if (ctx->lane2) { cudaStreamSynchronize(ctx->lane2); cudaStreamDestroy(ctx->lane2); }
     for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2, ctx->ev_frame_mark[0], ctx->ev_frame_mark[1], ctx->ev_luts_ready, ctx->ev_main_to_lut}) if (ev) cudaEventDestroy(ev);
     free_lut(ctx->alt.shadow_froxel);
@@ -446,7 +452,6 @@ int sky_ibl_precompute(SkyContext* ctx) {
     const int n = ctx->env.w;
     if (n & (n - 1)) return sky_fail(ctx, "ibl_precompute: the environment size must be a power of two");
     if (n > 2048) return sky_fail(ctx, "ibl_precompute: environment size above 2048");
-    if (int e = luts_join(ctx)) return e;  // frame pipelining: K5 of this frame runs on lut_stream
     if (ctx->env_mips_for != n) {
         if (ctx->env_mips) { SKY_CUDA(ctx, cudaFree(ctx->env_mips)); ctx->env_mips = nullptr; }
         size_t texels = 0;
@@ -462,6 +467,11 @@ int sky_ibl_precompute(SkyContext* ctx) {
     }
     if (int e = sky_alloc(ctx, ctx->env_sh, 9, 1, 1, false)) return e;
     ctx->ibl_valid = true;
+    if (ctx->pipelining) {  // follows this frame's K5 on lut_stream, into this frame's set of the double-buffered outputs
+        ctx->luts_pending = true;
+        LaneScope lane(ctx, ctx->lut_stream);
+        return launch_ibl_precompute(ctx);
+    }
     return launch_ibl_precompute(ctx);
 }
 

@@ -86,6 +86,9 @@ struct SkyContext {
         cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0, sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
         const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
         int lut_tex_dims[4][3] = {};
+        // the IBL tail of the LUT phase (sky_ibl_precompute) is double-buffered with the LUTs it follows
+        half4* env_mips = nullptr; int env_mips_for = 0; size_t env_mips_texels = 0;
+        Lut<float4> env_sh; half4* prefiltered = nullptr; size_t prefiltered_texels = 0; bool ibl_valid = false;
     } alt;
 
     // uniforms last seen
