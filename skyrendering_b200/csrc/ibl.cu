@@ -11,7 +11,8 @@
 // Mapping (all three are small, latency-bound kernels of the per-frame LUT phase, so the point is FEW launches):
 //   * one launch does the cube mips (6 blocks, one per face, levels chained through __syncthreads -- a face's chain only
 //     depends on that face) AND K23 (9 blocks of 1024 threads like the reference's 9 work groups; it only reads level 0);
-//   * one launch does all five roughness levels of K24, heavy levels first (level 0 is a 1-sample copy);
+//   * one launch does all five roughness levels of K24, heavy levels first (level 0 is a 1-sample copy); 8 lanes evaluate a
+//     texel's samples side by side, one lane adds them in the reference's order;
 //   * K22 (start-up, input-free): a block is 256 texels of one row, i.e. one roughness, so the tangent-space half vectors
 //     of the 1024 Hammersley samples are computed once per block into shared memory (2 sqrt + 1 division + sin + cos per
 //     sample hoisted out of every thread's loop; same functions on the same inputs, so still bit-identical).
@@ -179,21 +180,34 @@ struct PrefilterParams {
     int first_block[SKY_IBL_ROUGHNESS_COUNT + 1];    // launch order: levels 1, 2, ... then 0 (heavy first)
 };
 
-__global__ void __launch_bounds__(128) k24_prefilter_radiance(const __grid_constant__ PrefilterParams P) {
-    __shared__ float3 sH[64];  // kNumSamplesMax, PrefilterRadiance.comp:19
+// The reference sums a texel's samples serially.  What is expensive per sample -- two divisions, log2, two bilinear cube taps on
+// two mip levels -- does not depend on the running sum, so kLanes lanes evaluate a texel's samples side by side into shared
+// memory and ONE lane then adds them in the reference's order (same operands, same order: same bits).  The dependent chain of a
+// level-4 texel drops from 64 x (tap latency) to 8 x (tap latency) + 64 additions.  Level 0 is one sample per texel: 1 lane.
+constexpr int kPrefilterThreads = 128, kPrefilterLanes = 8, kPrefilterMaxSamples = 64;  // kNumSamplesMax, PrefilterRadiance.comp:19
+SKY_HD int prefilter_lanes(int level) { return level == 0 ? 1 : kPrefilterLanes; }
+
+__global__ void __launch_bounds__(kPrefilterThreads) k24_prefilter_radiance(const __grid_constant__ PrefilterParams P) {
+    __shared__ float3 sH[kPrefilterMaxSamples];
+    // (radiance * NoL, NoL) of sample i of the block's texel `local` at [local * NumSamples + i]; NoL == 0: sample skipped.
+    // 16 texels x <= 64 samples with 8 lanes per texel, 128 texels x 1 sample on level 0: at most 1024 entries either way
+    __shared__ float4 sC[kPrefilterThreads / kPrefilterLanes * kPrefilterMaxSamples];
     int slot = 0;
 #pragma unroll
     for (int k = 1; k < SKY_IBL_ROUGHNESS_COUNT; ++k) slot += int(blockIdx.x) >= P.first_block[k];
     const int level = (slot + 1) % SKY_IBL_ROUGHNESS_COUNT;
     const int w = P.size >> level;
-    const int t = (int(blockIdx.x) - P.first_block[slot]) * 128 + threadIdx.x;
+    const int lanes = prefilter_lanes(level), texels_per_block = kPrefilterThreads / lanes;
+    const int local = threadIdx.x / lanes, lane = threadIdx.x % lanes;
+    const int t = (int(blockIdx.x) - P.first_block[slot]) * texels_per_block + local;
     const float roughness = float(level) / float(SKY_IBL_ROUGHNESS_COUNT - 1);  // IBL.cpp:39
+    const uint32_t NumSamples = P.num_samples[level];
     // a block is one roughness level: the tangent-space half vectors (sin, cos, 2 sqrt, 1 division per sample) depend on the
     // sample index alone, so they are evaluated once per block instead of once per texel and sample (same values)
-    if (threadIdx.x < P.num_samples[level]) sH[threadIdx.x] = ImportanceSampleGGX(Hammersley0(threadIdx.x, P.num_samples[level]), roughness * roughness);
+    if (threadIdx.x < NumSamples) sH[threadIdx.x] = ImportanceSampleGGX(Hammersley0(threadIdx.x, NumSamples), roughness * roughness);
     __syncthreads();
-    if (t >= 6 * w * w) return;
-    const int x = t % w, y = (t / w) % w, index = t / (w * w);
+    const bool valid = t < 6 * w * w;
+    const int x = t % w, y = (t / w) % w, index = valid ? t / (w * w) : 0;
     float fu = (float(x) + 0.5f) / float(w), fv = (float(y) + 0.5f) / float(w);
     fv = 1.0f - fv;
     const float3 R = ConvertCubUvToDir(index, fu, fv);
@@ -202,24 +216,35 @@ __global__ void __launch_bounds__(128) k24_prefilter_radiance(const __grid_const
     const float3 N = R, V = R;
     float3 t0, t1;
     CreateOrthonormalBasis(N, t0, t1);
-    float3 PrefilteredColor = f3(0.0f);
-    const uint32_t NumSamples = P.num_samples[level];
-    float TotalWeight = 0.0f;
     const float invSaTexel = (6.0f * float(w) * float(w)) / (4.0f * kPi);
+    if (valid) {
+        for (uint32_t i = lane; i < NumSamples; i += lanes) {
+            float3 Hl = sH[i];
+            float3 Hw = t0 * Hl.x + t1 * Hl.y + N * Hl.z;
+            float3 L = 2.0f * dot(V, Hw) * Hw - V;
+            float NoL = clampf(dot(N, L), 0.0f, 1.0f);
+            float4 c = f4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (NoL > 0.0f) {
+                float NoH = clampf(dot(N, Hw), 0.0f, 1.0f);
+                float HoV = clampf(dot(Hw, V), 0.0f, 1.0f);
+                float D = D_GGX(a, NoH);
+                float pdf = fmaxf(D * NoH / (4.0f * HoV), 0.0001f);
+                float saSample = 1.0f / fmaxf(float(NumSamples) * pdf, 0.00001f);
+                float mipLevel = roughness == 0.0f ? 0.0f : 0.5f * log2f(saSample * invSaTexel) + 2.5f;
+                c = f4(xyz(TextureCubeLod(P.env, L, mipLevel)) * NoL, NoL);
+            }
+            sC[local * NumSamples + i] = c;
+        }
+    }
+    __syncthreads();
+    if (!valid || lane != 0) return;
+    float3 PrefilteredColor = f3(0.0f);
+    float TotalWeight = 0.0f;
     for (uint32_t i = 0; i < NumSamples; i++) {
-        float3 Hl = sH[i];
-        float3 Hw = t0 * Hl.x + t1 * Hl.y + N * Hl.z;
-        float3 L = 2.0f * dot(V, Hw) * Hw - V;
-        float NoL = clampf(dot(N, L), 0.0f, 1.0f);
-        if (NoL > 0.0f) {
-            float NoH = clampf(dot(N, Hw), 0.0f, 1.0f);
-            float HoV = clampf(dot(Hw, V), 0.0f, 1.0f);
-            float D = D_GGX(a, NoH);
-            float pdf = fmaxf(D * NoH / (4.0f * HoV), 0.0001f);
-            float saSample = 1.0f / fmaxf(float(NumSamples) * pdf, 0.00001f);
-            float mipLevel = roughness == 0.0f ? 0.0f : 0.5f * log2f(saSample * invSaTexel) + 2.5f;
-            PrefilteredColor = PrefilteredColor + xyz(TextureCubeLod(P.env, L, mipLevel)) * NoL;
-            TotalWeight += NoL;
+        float4 c = sC[local * NumSamples + i];
+        if (c.w > 0.0f) {
+            PrefilteredColor = PrefilteredColor + xyz(c);
+            TotalWeight += c.w;
         }
     }
     float3 c = PrefilteredColor / TotalWeight;
@@ -262,10 +287,10 @@ int launch_ibl_precompute(SkyContext* ctx) {
     for (int k = 0; k < SKY_IBL_ROUGHNESS_COUNT; ++k) {
         const int level = (k + 1) % SKY_IBL_ROUGHNESS_COUNT, w = P.size >> level;
         P.first_block[k] = blocks;
-        blocks += ceil_div(6 * w * w, 128);
+        blocks += ceil_div(6 * w * w, kPrefilterThreads / prefilter_lanes(level));
     }
     P.first_block[SKY_IBL_ROUGHNESS_COUNT] = blocks;
-    k24_prefilter_radiance<<<blocks, 128, 0, ctx->stream>>>(P);
+    k24_prefilter_radiance<<<blocks, kPrefilterThreads, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -101,7 +101,7 @@ def synthetic_gbuffer(width, height, up_direction, seed=0):
     """A synthetic G-buffer in the formats GBuffer.cpp:19-21 allocates -- albedo GL_RGBA8, normal GL_RGBA16_SNORM, orm GL_RGBA16 --
     standing in for the rasterised ground / mesh passes that are outside the path (the object branch of K6 only reads it).
     Smooth fields rather than white noise, so that a frame rendered from it looks like terrain: unit normals within ~25 degrees
-    of `up_direction`, mid-grey albedo, roughness 0.15..1, metallic 0..0.6."""
+    of `up_direction`, earthy mid-grey albedo, roughness 0.15..1, metallic 0..0.6."""
     rng = np.random.default_rng(seed)
     def field(channels):
         coarse = rng.random((max(height // 16, 2), max(width // 16, 2), channels)).astype(np.float32)
@@ -112,7 +112,7 @@ def synthetic_gbuffer(width, height, up_direction, seed=0):
         c = coarse
         return ((c[y0][:, x0] * (1 - fx) + c[y0][:, x0 + 1] * fx) * (1 - fy) + (c[y0 + 1][:, x0] * (1 - fx) + c[y0 + 1][:, x0 + 1] * fx) * fy)
     albedo = np.empty((height, width, 4), np.uint8)
-    albedo[..., :3] = np.rint((0.15 + 0.5 * field(3)) * 255.0)
+    albedo[..., :3] = np.rint((0.18 + 0.3 * field(1)) * (0.85 + 0.3 * field(3)) * np.float32([1.0, 0.95, 0.8]) * 255.0)  # earthy greys
     albedo[..., 3] = 255
     up = np.asarray(up_direction, np.float32)
     n = up[None, None, :] + 0.45 * (field(3) - 0.5)
