@@ -203,7 +203,8 @@ typedef struct SkyLutConfig {
     int32_t raymarching_dither;         /* raymarching_dither_sample_point_enable             */
     int32_t moon_shadow;                /* moon_shadow_enable: eclipse term (Atmosphere.glsl:190-218,281-284)                 */
     int32_t volumetric_light;           /* volumetric_light_enable: mesh shadow map in the march (Atmosphere.glsl:180-188,274-277) */
-    int32_t _pad[1];
+    int32_t pcss;                       /* pcss_enable: percentage-closer soft shadows from the mesh shadow map on object pixels
+                                           (PCSS_ENABLE, AtmosphereRenderer.cpp:99; Shadow.glsl:85-99); needs a G-buffer (sky_set_gbuffer) */
 } SkyLutConfig;
 
 /* Collision sampling of the path tracer (sky_pt_set_tracking) */

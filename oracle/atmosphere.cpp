@@ -226,10 +226,66 @@ inline vec3 GetSHIrradiance(vec3 N, const vec4* Llm) {
 }
 }  // namespace
 
-// AtmosphereRenderer.glsl:333-343 with PCSS_ENABLE 0 (every shipped config); the mesh shadow map is an input that is all 1.0
-// (lit) until the caller writes SKY_RES_MESH_SHADOW_MAP
+// Shadow.glsl:13-99 (PCSS_ENABLE 1).  shadowMap: Samplers::GetShadowMapSampler (LINEAR, border 1, compare LEQUAL: the bilinear
+// blend of four comparison results); shadow_map_depth_sampler: the same texture through NearestClampToEdge
+// (AtmosphereRenderer.cpp:196,213).  sin / cos: sky_detmath.h; pow: libm.
+float AtmosphereRenderer::PCSS(const Image<1>& shadow_map, vec3 position) const {
+    constexpr int NUM_SAMPLES = 25, NUM_RINGS = 3;
+    const float PI2 = PI * 2.0f;
+    vec4 xyzw = mat4(u.light_view_projection) * vec4(position, 1.0f);
+    vec3 coords = vec3(xyzw.x, xyzw.y, xyzw.z) / xyzw.w;
+    coords = coords * 0.5f + 0.5f;
+    if (coords.z >= 1.0f) return 1.0f;
+    vec2 poissonDisk[NUM_SAMPLES];
+    {   // poissonDiskSamples(coords.xy)
+        float ANGLE_STEP = PI2 * float(NUM_RINGS) / float(NUM_SAMPLES);
+        float INV_NUM_SAMPLES = 1.0f / float(NUM_SAMPLES);
+        // rand_2to1
+        const float a = 12.9898f, b = 78.233f, c = 43758.5453f;
+        float dt = dot(coords.xy(), vec2(a, b)), sn = dt - PI * std::floor(dt / PI);
+        float rnd = fract(sky_det_sinf(sn) * c);
+        float angle = rnd * PI2;
+        float radius = INV_NUM_SAMPLES;
+        float radiusStep = radius;
+        for (int i = 0; i < NUM_SAMPLES; i++) {
+            poissonDisk[i] = vec2(sky_det_cosf(angle), sky_det_sinf(angle)) * std::pow(radius, 0.75f);
+            radius += radiusStep;
+            angle += ANGLE_STEP;
+        }
+    }
+    const int W = shadow_map.w, H = shadow_map.h;
+    float kernelSizeApproximate = u.blocker_kernel_size_k * coords.z;
+    float avgblockerDepth;
+    {   // FindBlocker
+        float sum = 0.0f, cnt = 0.0f;
+        for (int i = 0; i < NUM_SAMPLES; ++i) {
+            vec2 samplePos = poissonDisk[i] * kernelSizeApproximate + coords.xy();
+            int tx = clamp(int(std::floor(samplePos.x * float(W))), 0, W - 1), ty = clamp(int(std::floor(samplePos.y * float(H))), 0, H - 1);
+            float shadow_depth = shadow_map.load(tx, ty).x;
+            if (coords.z - shadow_depth > 0.0f) {
+                cnt += 1.0f;
+                sum += shadow_depth;
+            }
+        }
+        avgblockerDepth = sum / max(cnt, 1e-5f);
+    }
+    float distanceToFragment = coords.z - avgblockerDepth;
+    float penumbraSize = u.pcss_size_k * distanceToFragment;
+    float sum = 0.0f;
+    for (int i = 0; i < NUM_SAMPLES; ++i) {  // Filtering
+        vec2 samplePos = poissonDisk[i] * penumbraSize + coords.xy();
+        sum += Atmosphere::ShadowCompare(shadow_map, samplePos.x, samplePos.y, coords.z);
+    }
+    return sum / float(NUM_SAMPLES);
+}
+
+// AtmosphereRenderer.glsl:333-343; the mesh shadow map is an input that is all 1.0 (lit) until the caller writes
+// SKY_RES_MESH_SHADOW_MAP
 float AtmosphereRenderer::SampleVisibilityFromShadowMap(vec3 position) const {
-    float visibility = mesh_shadow_map ? Atmosphere::GetVisibilityFromShadowMap(*mesh_shadow_map, mat4(u.light_view_projection), position) : 1.0f;
+    float visibility = 1.0f;
+    if (mesh_shadow_map)
+        visibility = cfg.pcss ? PCSS(*mesh_shadow_map, position)
+                              : Atmosphere::GetVisibilityFromShadowMap(*mesh_shadow_map, mat4(u.light_view_projection), position);
     if (object->cloud_shadow_map) {
         vec3 light_ndc = ProjectiveMul(mat4(u.uCloudShadowMapMat), position);
         // SampleCloudShadowTransmittance, VolumetricCloudShadowInterface.glsl:4-8; sampler border (1e10, 1), VolumetricCloud.cpp:106-112

@@ -166,13 +166,8 @@ struct Atmosphere {
 
     // Atmosphere.glsl:180-188: sampler2DShadow lookup with Samplers::GetShadowMapSampler (Samplers.cpp:43-51): LINEAR,
     // CLAMP_TO_BORDER with border 1, compare LEQUAL -- the bilinear blend of the four comparison results (PCF).
-    static float GetVisibilityFromShadowMap(const Image<1>& shadow_map, const mat4& light_view_projection, vec3 position) {
-        vec4 xyzw = light_view_projection * vec4(position, 1.0f);
-        vec3 xyz = vec3(xyzw.x, xyzw.y, xyzw.z) / xyzw.w;
-        xyz = xyz * 0.5f + 0.5f;
-        float depth = xyz.z;
-        if (depth >= 1.0f) return 1.0f;
-        float x = xyz.x * float(shadow_map.w) - 0.5f, y = xyz.y * float(shadow_map.h) - 0.5f;
+    static float ShadowCompare(const Image<1>& shadow_map, float u, float v, float depth) {  // texture(sampler2DShadow, vec3(u, v, depth))
+        float x = u * float(shadow_map.w) - 0.5f, y = v * float(shadow_map.h) - 0.5f;
         float fx = std::floor(x), fy = std::floor(y);
         float a = x - fx, b = y - fy;
         auto cmp = [&](float i, float j) {
@@ -182,6 +177,14 @@ struct Atmosphere {
         };
         return (1.0f - a) * (1.0f - b) * cmp(fx, fy) + a * (1.0f - b) * cmp(fx + 1.0f, fy) + (1.0f - a) * b * cmp(fx, fy + 1.0f) +
                a * b * cmp(fx + 1.0f, fy + 1.0f);
+    }
+    static float GetVisibilityFromShadowMap(const Image<1>& shadow_map, const mat4& light_view_projection, vec3 position) {
+        vec4 xyzw = light_view_projection * vec4(position, 1.0f);
+        vec3 xyz = vec3(xyzw.x, xyzw.y, xyzw.z) / xyzw.w;
+        xyz = xyz * 0.5f + 0.5f;
+        float depth = xyz.z;
+        if (depth >= 1.0f) return 1.0f;
+        return ShadowCompare(shadow_map, xyz.x, xyz.y, depth);
     }
 
     // Atmosphere.glsl:190-210
@@ -342,6 +345,7 @@ struct AtmosphereRenderer {
     // AtmosphereRenderer.glsl:284-324 and :333-343
     vec3 ComputeObjectLuminance(vec3 position, vec3 view_direction, float shadow_visibility, vec2 vTexCoord, int width, int height) const;
     float SampleVisibilityFromShadowMap(vec3 position) const;
+    float PCSS(const Image<1>& shadow_map, vec3 position) const;  // Shadow.glsl:85-99
 
     // AtmosphereRenderer.glsl:326-331 (sampler LinearNoMipmapClampToEdge, AtmosphereRenderer.cpp:204)
     vec3 GetStarLuminance(vec3 view_direction) const {

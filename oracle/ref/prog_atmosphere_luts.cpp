@@ -136,6 +136,14 @@ namespace k6s1a0 {
 #include "../_ref/gen/AtmosphereRenderer.glsl.inc"
 #include "ref_undef_guards.h"
 }
+#undef PCSS_ENABLE
+#define PCSS_ENABLE 1
+namespace k6s1a0p1 {  // scene c3's flags + PCSS_ENABLE (the object branch's soft shadows, Shadow.glsl)
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef PCSS_ENABLE
+#define PCSS_ENABLE 0
 #undef USE_SKY_VIEW_LUT
 #define USE_SKY_VIEW_LUT 0
 namespace k6s0a0 {
@@ -264,6 +272,8 @@ struct RefCompositeIO {
     const float* prefiltered;        // 5 levels from 128^2, concatenated, [6][n][n][4]
     const float* llm;                // [9][4]
     const float* cloud_shadow_map;   // [512][512][4] (depth, transmittance) or null (unshadowed)
+    const float* mesh_shadow_map;    // [S][S][4] light-space depth in .x, or null (lit): object pixels only
+    int mesh_shadow_size;
 };
 
 extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg,
@@ -286,7 +296,10 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
         ref_bind_texture(albedo_texture, io->albedo ? io->albedo : zero4, io->albedo ? W : 1, io->albedo ? H : 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         ref_bind_texture(normal_texture, io->albedo ? io->normal : zero4, io->albedo ? W : 1, io->albedo ? H : 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         ref_bind_texture(orm_texture, io->albedo ? io->orm : zero4, io->albedo ? W : 1, io->albedo ? H : 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
-        ref::NS::shadow_map_texture.levels.clear();  /* no mesh shadow map: lit */                                          \
+        if (io->albedo && io->mesh_shadow_map) {                                                                            \
+            ref_bind_texture(ref::NS::shadow_map_texture, io->mesh_shadow_map, io->mesh_shadow_size, io->mesh_shadow_size, 1, ref::CLAMP_TO_BORDER, ref::LINEAR); \
+            ref::NS::shadow_map_texture.border = ref::vec4(1.0f);                                                           \
+        } else ref::NS::shadow_map_texture.levels.clear();  /* no mesh shadow map: lit */                                   \
         ref_bind_texture(blue_noise, io->blue_noise, 64, 64, 1, ref::REPEAT, ref::NEAREST);                                 \
         if (io->star) ref_bind_texture(star_luminance, io->star, io->star_w, io->star_h, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         else ref_bind_texture(star_luminance, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                             \
@@ -294,7 +307,8 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
         ref_bind_texture(sky_view_transmittance_texture, io->sky_transmittance, cfg->sky_view_width, cfg->sky_view_height, 1, ref::CLAMP_TO_EDGE, ref::LINEAR); \
         ref_bind_texture(aerial_perspective_luminance_texture, io->ap_luminance, 32, 32, cfg->aerial_perspective_depth, ref::CLAMP_TO_EDGE, ref::LINEAR);    \
         ref_bind_texture(aerial_perspective_transmittance_texture, io->ap_transmittance, 32, 32, cfg->aerial_perspective_depth, ref::CLAMP_TO_EDGE, ref::LINEAR); \
-        ref_bind_texture(shadow_map_depth_sampler, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::NEAREST);                        \
+        if (io->albedo && io->mesh_shadow_map) ref_bind_texture(shadow_map_depth_sampler, io->mesh_shadow_map, io->mesh_shadow_size, io->mesh_shadow_size, 1, ref::CLAMP_TO_EDGE, ref::NEAREST); \
+        else ref_bind_texture(shadow_map_depth_sampler, one4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::NEAREST);                   \
         if (io->albedo && io->cloud_shadow_map) {                                                                           \
             ref_bind_texture(cloud_shadow_map, io->cloud_shadow_map, 512, 512, 1, ref::CLAMP_TO_BORDER, ref::LINEAR);       \
             ref::NS::cloud_shadow_map.border = ref::vec4(1e10f, 1.0f, 0.0f, 0.0f);  /* VolumetricCloud.cpp:106-112 */       \
@@ -318,7 +332,7 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
             ref_bind_texture(env_brdf_lut, zero4, 1, 1, 1, ref::CLAMP_TO_EDGE, ref::LINEAR);                                \
             for (int i = 0; i < 9; ++i) Llm[i] = ref::vec4(0.0f);                                                           \
         }                                                                                                                   \
-        _Pragma("omp parallel for schedule(dynamic, 4)")                                                                    \
+        _Pragma("omp parallel for schedule(dynamic, 4) if(!serial)")                                                        \
         for (int py = 0; py < H; ++py)                                                                                      \
             for (int px = 0; px < W; ++px) {                                                                                \
                 ref::g_builtins.frag_coord = ref::vec4(float(px) + 0.5f, float(py) + 0.5f, 0.0f, 1.0f);                     \
@@ -327,6 +341,14 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
                 float* o = io->out + (size_t(py) * W + px) * 4;                                                             \
                 o[0] = FragColor.x; o[1] = FragColor.y; o[2] = FragColor.z; o[3] = FragColor.w;                             \
             }                                                                                                               \
+    }
+    // Shadow.glsl keeps its sample table in a GLSL global (`vec2 poissonDisk[]`: one per invocation; here one per process), so the
+    // PCSS permutation runs its fragments one after the other
+    const bool serial = cfg->pcss != 0;
+    if (cfg->pcss) {
+        if (cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a0p1)
+        else return 3;
+        return 0;
     }
     if (cfg->use_sky_view_lut && cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a1)
     else if (cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a0)

@@ -7,3 +7,4 @@
 #undef _VOLUMETRIC_CLOUD_SHADOW_INTERFACE_GLSL
 #undef PI
 #undef INV_PI
+#undef _SHADOW_GLSL

@@ -123,7 +123,7 @@ class LutConfig(_Pod):
     _fields_ = [("sky_view_width", I), ("sky_view_height", I), ("aerial_perspective_depth", I),
                 ("environment_size", I), ("use_sky_view_lut", I), ("use_aerial_perspective_lut", I),
                 ("sky_view_dither", I), ("aerial_perspective_dither", I), ("raymarching_dither", I), ("moon_shadow", I),
-                ("volumetric_light", I), ("_pad", I * 1)]
+                ("volumetric_light", I), ("pcss", I)]
 
 
 PT_TRACKING_REFERENCE, PT_TRACKING_MAJORANT_GRID = 0, 1

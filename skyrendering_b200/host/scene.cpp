@@ -462,6 +462,7 @@ void Scene::LutConfig(SkyLutConfig& c) const {
     c.raymarching_dither = p.raymarching_dither_sample_point_enable;
     c.moon_shadow = p.moon_shadow_enable;            // MOON_SHADOW_ENABLE, AtmosphereRenderer.cpp:101
     c.volumetric_light = p.volumetric_light_enable;  // VOLUMETRIC_LIGHT_ENABLE, :100 (reads SKY_RES_MESH_SHADOW_MAP)
+    c.pcss = p.pcss_enable;                          // PCSS_ENABLE, :99 (object pixels; reads SKY_RES_MESH_SHADOW_MAP)
 }
 
 // AtmosphereRenderer.cpp:52-83 and :168-174

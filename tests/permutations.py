@@ -10,13 +10,16 @@ from skyrendering_b200.host import Scene
 from skyrendering_b200.renderer import scene_path
 
 
-def scene_text(moon=False, volumetric=False, raymarch=False):
+def scene_text(moon=False, volumetric=False, raymarch=False, pcss=None):
     cfg = json.loads(open(scene_path("c1")).read())
     init = cfg["atmosphere_render_init_parameters_"]
     init["moon_shadow_enable"], init["volumetric_light_enable"] = bool(moon), bool(volumetric)
     if raymarch:   # K6 marches every pixel itself instead of reading the sky-view / aerial-perspective LUTs
         init["use_sky_view_lut"] = init["use_aerial_perspective_lut"] = False
-    if volumetric:
+    if pcss is not None:  # PCSS_ENABLE on / off for the object pixels (Shadow.glsl), with scene c3's LUT flags; camera over the shadowed ground
+        init["pcss_enable"] = bool(pcss)
+        init["use_sky_view_lut"], init["use_aerial_perspective_lut"], init["raymarching_dither_sample_point_enable"] = True, False, True
+    if volumetric or pcss is not None:
         cfg["camera_"]["position_"] = [0.6, 0.35, -0.4]
     # the moon 2.5 degrees from the sun AS SEEN FROM THE CAMERA (the scene's moon is only 46 500 km from the earth's centre,
     # so parallax matters): target position -> (theta, phi, distance) of Earth::moon_model (Earth.cpp:67-77), which places
@@ -33,8 +36,8 @@ def scene_text(moon=False, volumetric=False, raymarch=False):
     return json.dumps(cfg)
 
 
-def scene(moon=False, volumetric=False, raymarch=False):
-    return Scene(scene_text(moon, volumetric, raymarch))
+def scene(moon=False, volumetric=False, raymarch=False, pcss=None):
+    return Scene(scene_text(moon, volumetric, raymarch, pcss))
 
 
 def mesh_shadow_map(size=2048):

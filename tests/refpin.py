@@ -82,16 +82,17 @@ class RefCompositeIO(C.Structure):
                 ("fw", C.c_int), ("fh", C.c_int), ("fd", C.c_int), ("depth", C.c_void_p), ("star", C.c_void_p), ("star_w", C.c_int),
                 ("star_h", C.c_int), ("out", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("albedo", C.c_void_p),
                 ("normal", C.c_void_p), ("orm", C.c_void_p), ("env_brdf_lut", C.c_void_p), ("prefiltered", C.c_void_p), ("llm", C.c_void_p),
-                ("cloud_shadow_map", C.c_void_p)]
+                ("cloud_shadow_map", C.c_void_p), ("mesh_shadow_map", C.c_void_p), ("mesh_shadow_size", C.c_int)]
 
 
-def ref_composite(ref, renderer, depth, width, height, blue_noise, froxel=None, star_linear=None, gbuffer=None, cloud_shadow_map=None):
+def ref_composite(ref, renderer, depth, width, height, blue_noise, froxel=None, star_linear=None, gbuffer=None, cloud_shadow_map=None, mesh_shadow_map=None):
     """K6: the reference's full-screen fragment program (AtmosphereRenderer.glsl:345-432, permutation of the scene's flags) on the
     LUT state of `renderer` (an oracle-backed Renderer after atmosphere_render_luts) with an all-zero G-buffer -- which makes
     ComputeObjectLuminance vanish, so object pixels carry the in-scatter term alone, like sky_composite's.  Returns FragColor
     float32 [H][W][4].  `froxel`: uint16 [128][H/12][W/12] or None; `star_linear`: float32 [sh][sw][3] decoded star map or None.
     `gbuffer`: (albedo uint8, normal int16, orm uint16) [H][W][4] -> the object branch runs on them with the IBL state of
-    `renderer` (after env_brdf_lut + ibl_precompute); `cloud_shadow_map`: float32 [512][512][2] (K12 output) or None."""
+    `renderer` (after env_brdf_lut + ibl_precompute); `cloud_shadow_map`: float32 [512][512][2] (K12 output) or None;
+    `mesh_shadow_map`: float32 [S][S] light-space depth or None (lit)."""
     ctx = renderer.ctx
     keep = []
     def rgba(a, channels_last=True):
@@ -103,7 +104,7 @@ def ref_composite(ref, renderer, depth, width, height, blue_noise, froxel=None, 
     dp = rgba(np.asarray(depth, np.float32), channels_last=False)
     fr = None if froxel is None else rgba(np.asarray(froxel).astype(np.float32) / np.float32(65535.0), channels_last=False)
     sr = None if star_linear is None else rgba(np.asarray(star_linear, np.float32))
-    obj = [None] * 7
+    obj = [None] * 8 + [0]
     if gbuffer is not None:
         alb = np.ascontiguousarray(gbuffer[0].astype(np.float32) / np.float32(255.0))
         nrm = np.ascontiguousarray(np.maximum(gbuffer[1].astype(np.float32) / np.float32(32767.0), np.float32(-1.0)))
@@ -113,8 +114,10 @@ def ref_composite(ref, renderer, depth, width, height, blue_noise, froxel=None, 
         pre = np.concatenate([p.astype(np.float32).reshape(-1) for p in pre])
         sh = np.ascontiguousarray(sh, np.float32)
         csm = None if cloud_shadow_map is None else rgba(np.asarray(cloud_shadow_map, np.float32))
+        msm = None if mesh_shadow_map is None else rgba(np.asarray(mesh_shadow_map, np.float32), channels_last=False)
         keep += [alb, nrm, orm, pre, sh]
-        obj = [alb.ctypes.data, nrm.ctypes.data, orm.ctypes.data, lut.ctypes.data, pre.ctypes.data, sh.ctypes.data, None if csm is None else csm.ctypes.data]
+        obj = [alb.ctypes.data, nrm.ctypes.data, orm.ctypes.data, lut.ctypes.data, pre.ctypes.data, sh.ctypes.data, None if csm is None else csm.ctypes.data,
+               None if msm is None else msm.ctypes.data, 0 if msm is None else msm.shape[0]]
     out = np.zeros((height, width, 4), np.float32)
     io = RefCompositeIO(T.ctypes.data, M.ctypes.data, bn.ctypes.data, sl.ctypes.data, st.ctypes.data, al.ctypes.data, at.ctypes.data,
                         None if fr is None else fr.ctypes.data, 0 if fr is None else fr.shape[2], 0 if fr is None else fr.shape[1],

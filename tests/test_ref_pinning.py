@@ -223,6 +223,40 @@ def test_oracle_object_shading_is_the_reference_fragment_program(scene):
 
 
 @pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+def test_oracle_pcss_is_the_reference_fragment_program():
+    """PCSS_ENABLE 1 (Shadow.glsl:13-99: Poisson disc seeded per pixel, blocker search through the NEAREST view of the mesh shadow
+    map, 25-tap percentage-closer filter through the comparison sampler) on object pixels under a synthetic occluder: the
+    oracle is bit-identical to the reference's fragment program, and the penumbra is there."""
+    from skyrendering_b200.renderer import load_blue_noise, synthetic_gbuffer
+    from tests.parity import make_buffers
+    from tests import permutations
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 192, 108
+    shadow = permutations.mesh_shadow_map()
+    out = {}
+    for pcss in (True, False):
+        r = Renderer(permutations.scene(pcss=pcss), w, h, library=orc)
+        assert r.scene.lut_config().pcss == int(pcss)
+        r.ctx.write(abi.RES_MESH_SHADOW_MAP, shadow)
+        r.enable_ibl()
+        r.prime()
+        depth_np = r.scene.ground_depth(w, h)
+        depth, hdr = make_buffers(w, h, depth_np, "cpu")
+        gbuffer = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=3)
+        r.ctx.set_gbuffer(*gbuffer)
+        r.ctx.composite(depth, hdr, w, h)
+        out[pcss] = hdr.astype(np.float32).copy()
+        if pcss:
+            want = refpin.ref_composite(ref, r, depth_np, w, h, load_blue_noise(), froxel=r.ctx.read(abi.RES_SHADOW_FROXEL), gbuffer=gbuffer,
+                                        cloud_shadow_map=r.ctx.read(abi.RES_SHADOW_MAP), mesh_shadow_map=shadow)
+            want16 = want.astype(np.float16).astype(np.float32)
+            assert np.all(np.isfinite(want16)) and np.array_equal(out[True], want16)
+    obj = depth_np != 1.0
+    changed = np.any(out[True] != out[False], axis=-1)
+    assert obj.mean() > 0.1 and 0.005 < changed[obj].mean() < 0.9 and not changed[~obj].any()
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
 def test_oracle_star_term_is_the_reference_fragment_program():
     """GetStarLuminance (AtmosphereRenderer.glsl:326-331,427-429) through a GL_SRGB8 star map: bit-identical, and visible."""
     from skyrendering_b200.renderer import load_blue_noise
