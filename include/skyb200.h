@@ -86,7 +86,7 @@ int SKY_FN(set_gbuffer)(SkyContext* ctx, const void* albedo_dev, const void* nor
  * Object pixels (depth != 1): with a G-buffer bound (sky_set_gbuffer; needs sky_env_brdf_lut and sky_ibl_precompute) they are
  * shaded like the reference's (ComputeObjectLuminance + SampleVisibilityFromShadowMap, AtmosphereRenderer.glsl:284-343,
  * 404-410: sun through the transmittance LUT, GGX / Lambert BRDF, SH9 + prefiltered-cube ambient, mesh shadow map x cloud
- * shadow map; PCSS_ENABLE 0 as in every shipped config) and alpha = 1; without one they receive the atmosphere in-scatter
+ * shadow map, with PCSS soft shadows when SkyLutConfig.pcss is set) and alpha = 1; without one they receive the atmosphere in-scatter
  * only and alpha = 0 marks them. */
 int SKY_FN(composite)(SkyContext* ctx, const float* depth_dev, void* hdr_dev, int width, int height);
 

@@ -571,11 +571,88 @@ SKY_D float3 GetSHIrradiance(float3 N, const float4* Llm) {
         + 2.0f * c1 * (x * y * L2_2 + x * z * L21 + y * z * L2_1)
         + 2.0f * c2 * (x * L11 + y * L1_1 + z * L10);
 }
-// AtmosphereRenderer.glsl:333-343 with PCSS_ENABLE 0; SampleCloudShadowTransmittance (VolumetricCloudShadowInterface.glsl:4-8)
+// texture(sampler2DShadow, vec3(u, v, depth)) through Samplers::GetShadowMapSampler: bilinear blend of four LEQUAL comparisons, border 1
+SKY_D float ShadowCompare(const ScatterExtras& e, float u, float v, float depth) {
+    const float S = float(e.shadow_size);
+    float x = u * S - 0.5f, y = v * S - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = x - fx, b = y - fy;
+    auto cmp = [&](float i, float j) {
+        bool inside = i >= 0.0f && j >= 0.0f && i < S && j < S;
+        float texel = inside ? __ldg(e.shadow_map + size_t(int(j)) * e.shadow_size + int(i)) : 1.0f;
+        return depth <= texel ? 1.0f : 0.0f;
+    };
+    return (1.0f - a) * (1.0f - b) * cmp(fx, fy) + a * (1.0f - b) * cmp(fx + 1.0f, fy) + (1.0f - a) * b * cmp(fx, fy + 1.0f) +
+           a * b * cmp(fx + 1.0f, fy + 1.0f);
+}
+// Shadow.glsl:13-99 (PCSS_ENABLE 1): per-pixel Poisson disc, blocker search through the NEAREST / CLAMP_TO_EDGE view of the mesh
+// shadow map (AtmosphereRenderer.cpp:196,213), 25-tap percentage-closer filter.  The strict object takes sin / cos from
+// sky_detmath.h like the oracle; the production object the hardware's -- except for the ONE sin per pixel behind the disc's
+// random rotation, fract(sin(x) * 43758.5), which no two sin implementations agree on: it is sky_detmath.h's in both objects,
+// so that the production penumbra is the oracle's penumbra and not just statistically alike
+SKY_D float PCSS(const RenderParams& P, const ScatterExtras& e, float3 position) {
+    constexpr int NUM_SAMPLES = 25, NUM_RINGS = 3;
+    const float PI2 = kPi * 2.0f;
+    const float* m = e.light_view_projection;
+    float X = m[0] * position.x + m[4] * position.y + m[8] * position.z + m[12] * 1.0f;
+    float Y = m[1] * position.x + m[5] * position.y + m[9] * position.z + m[13] * 1.0f;
+    float Z = m[2] * position.x + m[6] * position.y + m[10] * position.z + m[14] * 1.0f;
+    float Wc = m[3] * position.x + m[7] * position.y + m[11] * position.z + m[15] * 1.0f;
+    float cx = X / Wc * 0.5f + 0.5f, cy = Y / Wc * 0.5f + 0.5f, cz = Z / Wc * 0.5f + 0.5f;
+    if (cz >= 1.0f) return 1.0f;
+#ifdef SKY_STRICT_TU
+#define PCSS_SIN sky_det_sinf
+#define PCSS_COS sky_det_cosf
+#else
+#define PCSS_SIN sinf
+#define PCSS_COS cosf
+#endif
+    float2 poissonDisk[NUM_SAMPLES];
+    {
+        float ANGLE_STEP = PI2 * float(NUM_RINGS) / float(NUM_SAMPLES);
+        float INV_NUM_SAMPLES = 1.0f / float(NUM_SAMPLES);
+        const float a = 12.9898f, b = 78.233f, c = 43758.5453f;
+        float dt = cx * a + cy * b, sn = dt - kPi * floorf(dt / kPi);
+        float rnd = fractf(sky_det_sinf(sn) * c);  // both objects: see above
+        float angle = rnd * PI2;
+        float radius = INV_NUM_SAMPLES;
+        float radiusStep = radius;
+#pragma unroll
+        for (int i = 0; i < NUM_SAMPLES; i++) {
+            float pr = powf(radius, 0.75f);
+            poissonDisk[i] = f2(PCSS_COS(angle) * pr, PCSS_SIN(angle) * pr);
+            radius += radiusStep;
+            angle += ANGLE_STEP;
+        }
+    }
+    const int S = e.shadow_size;
+    float kernelSizeApproximate = P.r.blocker_kernel_size_k * cz;
+    float sum = 0.0f, cnt = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NUM_SAMPLES; ++i) {  // FindBlocker
+        float sx = poissonDisk[i].x * kernelSizeApproximate + cx, sy = poissonDisk[i].y * kernelSizeApproximate + cy;
+        int tx = clampi(int(floorf(sx * float(S))), 0, S - 1), ty = clampi(int(floorf(sy * float(S))), 0, S - 1);
+        float shadow_depth = __ldg(e.shadow_map + size_t(ty) * S + tx);
+        if (cz - shadow_depth > 0.0f) {
+            cnt += 1.0f;
+            sum += shadow_depth;
+        }
+    }
+    float avgblockerDepth = sum / fmaxf(cnt, 1e-5f);
+    float distanceToFragment = cz - avgblockerDepth;
+    float penumbraSize = P.r.pcss_size_k * distanceToFragment;
+    float vis = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NUM_SAMPLES; ++i)  // Filtering
+        vis += ShadowCompare(e, poissonDisk[i].x * penumbraSize + cx, poissonDisk[i].y * penumbraSize + cy, cz);
+    return vis / float(NUM_SAMPLES);
+}
+// AtmosphereRenderer.glsl:333-343; SampleCloudShadowTransmittance (VolumetricCloudShadowInterface.glsl:4-8)
 // through the cloud shadow sampler: LINEAR, CLAMP_TO_BORDER (1e10, 1) (VolumetricCloud.cpp:106-112)
 SKY_D float SampleVisibilityFromShadowMap(const RenderParams& P, float3 position) {
     const ObjectParams& O = P.object;
-    float visibility = O.mesh.shadow_size > 0 ? GetVisibilityFromShadowMap(O.mesh, position) : 1.0f;
+    float visibility = 1.0f;
+    if (O.mesh.shadow_size > 0) visibility = P.cfg.pcss ? PCSS(P, O.mesh, position) : GetVisibilityFromShadowMap(O.mesh, position);
     if (O.cloud_shadow_map) {
         float3 light_ndc = projective_mul(P.r.uCloudShadowMapMat, position);
         const int S = O.cloud_shadow_size;

@@ -150,6 +150,47 @@ def test_object_shading_parity(libs, scene, strict):
         assert np.allclose(gs[~obj][:, :3].astype(np.float32), gp[~obj][:, :3].astype(np.float32), rtol=4e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("strict", [False, True])
+def test_pcss_parity(libs, strict):
+    """PCSS_ENABLE (Shadow.glsl:13-99) on object pixels under the synthetic occluder of tests/permutations.py: same bars as the
+    object branch itself; and the soft shadow differs from the hard one on a visible part of the ground."""
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    from tests import permutations
+    from tests.parity import make_buffers, rel_rms
+    cuda, orc = libs
+    w, h = 384, 216
+    shadow = permutations.mesh_shadow_map()
+    out = {}
+    for name, lib, dev, pcss in (("cuda", cuda, "cuda", True), ("oracle", orc, "cpu", True), ("hard", cuda, "cuda", False)):
+        r = Renderer(permutations.scene(pcss=pcss), w, h, library=lib)
+        if dev == "cuda":
+            r.ctx.set_strict_arithmetic(strict)
+        r.ctx.write(abi.RES_MESH_SHADOW_MAP, shadow)
+        r.enable_ibl()
+        r.prime()
+        depth_np = r.scene.ground_depth(w, h)
+        depth, hdr = make_buffers(w, h, depth_np, dev)
+        g = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=3)
+        gb = [torch.from_numpy(a).cuda() for a in g] if dev == "cuda" else list(g)
+        r.ctx.set_gbuffer(*gb)
+        r.ctx.composite(depth, hdr, w, h)
+        if dev == "cuda":
+            r.ctx.sync()
+        out[name] = (hdr.cpu().numpy() if dev == "cuda" else hdr).copy()
+    obj = depth_np != 1.0
+    a, b = out["cuda"].astype(np.float32), out["oracle"].astype(np.float32)
+    err = rel_rms(a[obj][:, :3], b[obj][:, :3])
+    equal = float(np.mean(out["cuda"].view(np.uint16)[obj] == out["oracle"].view(np.uint16)[obj]))
+    soft = float(np.mean(np.any(out["cuda"][obj] != out["hard"][obj], axis=-1)))
+    print(f"PCSS strict={strict}: relative RMS {err:.2e}, bit-equal texels {equal:.4f}, object pixels where soft != hard {soft:.3f}")
+    assert np.all(np.isfinite(a)) and obj.mean() > 0.1
+    if strict:
+        assert err <= 1e-4 and equal >= 0.98
+    else:
+        assert err <= 1e-2
+    assert soft > 0.005
+
+
 def test_composite_needs_the_ibl_chain_for_a_gbuffer(libs):
     from skyrendering_b200.renderer import synthetic_gbuffer
     from tests.parity import make_buffers
