@@ -57,6 +57,13 @@ def _setup_cloud(width, height):
     return r, depth
 
 
+def _bind_objects(r, width, height):
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    r.enable_ibl()
+    r.prime()
+    r.ctx.set_gbuffer(*synthetic_gbuffer(width, height, r.render_buffer.up_direction[:], seed=5))
+
+
 def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -96,6 +103,20 @@ def _worker(rank, world, port, out_dir):
             scf.composite(depth, hdr)
             scf.frame(common, cloud, depth, hdr)
         np.save(os.path.join(out_dir, f"hdr_sharded_{rank}.npy"), hdr)
+        # ... and with the object branch of K6 (G-buffer bound, IBL tail of the LUT phase replicated on every rank)
+        r, depth = _setup_cloud(96, 56)
+        _bind_objects(r, 96, 56)
+        scf = ShardedCloudFrame(r, rank, world, band_rows=4, shard_output=True, output_band_rows=8)
+        hdr = np.zeros((56, 96, 4), np.float16)
+        for _ in range(2):
+            hdr[...] = 0
+            r.earth_update()
+            common, cloud, _ = r.cloud_update(0.0)
+            r.ctx.cloud_shadow(common)
+            r.atmosphere_render_luts()
+            scf.composite(depth, hdr)
+            scf.frame(common, cloud, depth, hdr)
+        np.save(os.path.join(out_dir, f"hdr_objects_{rank}.npy"), hdr)
     finally:
         dist.destroy_process_group()
 
@@ -132,3 +153,14 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert hdr.astype(np.float32).sum() > 0
     for k in range(world):
         assert np.array_equal(np.load(tmp_path / f"hdr_sharded_{k}.npy"), hdr)
+    # object branch: every pixel is shaded by exactly one rank with the unsharded arithmetic
+    plain = hdr.copy()
+    r, depth = _setup_cloud(96, 56)
+    _bind_objects(r, 96, 56)
+    hdr = np.zeros((56, 96, 4), np.float16)
+    for _ in range(2):
+        hdr[...] = 0
+        r.frame(depth, hdr, 0.0, composite=True)
+    assert not np.array_equal(hdr, plain)
+    for k in range(world):
+        assert np.array_equal(np.load(tmp_path / f"hdr_objects_{k}.npy"), hdr)
