@@ -91,6 +91,12 @@ int skyhost_view_projection(SkyScene* scene, float view_projection[16]);
  * into the D24 depth buffer, 1.0 elsewhere. */
 int skyhost_ground_depth(SkyScene* scene, float* depth, int width, int height);
 
+/* Synthetic G-buffer input for sky_set_gbuffer: what the same ground pass writes into the three colour targets
+ * (EarthRender.frag:53-59; formats GBuffer.cpp:19-21) for the pixels it keeps -- normal = the sphere's normal (RGBA16_SNORM),
+ * ORM = (1, 1, 0) (RGBA16), albedo RGBA8 = `albedo_rgb` in place of the earth map (data/NASA, an external asset with a seamless
+ * textureGrad that is not shipped) -- and 0 (the cleared value) elsewhere.  Host arrays [height][width][4]. */
+int skyhost_ground_gbuffer(SkyScene* scene, const float albedo_rgb[3], uint8_t* albedo, int16_t* normal, uint16_t* orm, int width, int height);
+
 #ifdef __cplusplus
 }
 #endif

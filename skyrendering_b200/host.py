@@ -48,6 +48,7 @@ def _host():
             "skyhost_camera_move": ([V, P(C.c_float * 3), C.c_float, C.c_float], I),
             "skyhost_view_projection": ([V, P(C.c_float * 16)], I),
             "skyhost_ground_depth": ([V, C.c_void_p, I, I], I),
+            "skyhost_ground_gbuffer": ([V, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, I, I], I),
             "skyhost_vdb_open": ([C.c_char_p, P(V)], I),
             "skyhost_vdb_parse": ([C.c_void_p, C.c_int64, P(V)], I),
             "skyhost_vdb_close": ([V], None),
@@ -67,7 +68,7 @@ HOST_SYMBOLS = [
     "skyhost_atmosphere_buffer", "skyhost_lut_config", "skyhost_atmosphere_render_buffer", "skyhost_set_viewport",
     "skyhost_cloud_update", "skyhost_noise_info", "skyhost_set_voxel_dim", "skyhost_material_type", "skyhost_pt_params",
     "skyhost_pt_init", "skyhost_pt_region", "skyhost_camera_get", "skyhost_camera_move", "skyhost_view_projection",
-    "skyhost_ground_depth", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
+    "skyhost_ground_depth", "skyhost_ground_gbuffer", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
     "skyhost_vdb_fill_float",
 ]
 
@@ -183,6 +184,14 @@ class Scene:
         out = np.empty((h, w), np.float32)
         self._check(_host().skyhost_ground_depth(self.h, out.ctypes.data, w, h))
         return out
+
+    def ground_gbuffer(self, w, h, albedo_rgb=(0.3, 0.3, 0.3)):
+        """(albedo uint8, normal int16, orm uint16) [h][w][4]: the colour targets of the ground pass (EarthRender.frag:53-59) with a
+        constant albedo in place of the earth map."""
+        albedo, normal, orm = np.empty((h, w, 4), np.uint8), np.empty((h, w, 4), np.int16), np.empty((h, w, 4), np.uint16)
+        rgb = (C.c_float * 3)(*albedo_rgb)
+        self._check(_host().skyhost_ground_gbuffer(self.h, C.cast(rgb, C.c_void_p), albedo.ctypes.data, normal.ctypes.data, orm.ctypes.data, w, h))
+        return albedo, normal, orm
 
 
 class VdbGrid:

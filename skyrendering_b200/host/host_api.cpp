@@ -184,4 +184,8 @@ int skyhost_ground_depth(SkyScene* s, float* depth, int width, int height) {
     return guarded([&] { s->scene.GroundDepth(depth, width, height); });
 }
 
+int skyhost_ground_gbuffer(SkyScene* s, const float albedo_rgb[3], uint8_t* albedo, int16_t* normal, uint16_t* orm, int width, int height) {
+    return guarded([&] { s->scene.GroundGBuffer(albedo_rgb, albedo, normal, orm, width, height); });
+}
+
 }  // extern "C"

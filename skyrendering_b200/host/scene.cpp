@@ -555,4 +555,41 @@ void Scene::GroundDepth(float* depth, int width, int height) const {
         }
 }
 
+// EarthRender.frag:40-59: what the ground pass writes into the three G-buffer targets (GBuffer.cpp:19-21) for the pixels it
+// keeps -- Normal = normalize(ground_position - earth_center), ORM = (1, roughness 1, metallic 0), Albedo from the earth map
+// (data/NASA/*.jpg + a seamless textureGrad: an external asset that is not shipped; here the caller's colour) -- pixels it
+// discards keep the cleared value 0.
+void Scene::GroundGBuffer(const float albedo_rgb[3], uint8_t* albedo, int16_t* normal, uint16_t* orm, int width, int height) const {
+    const mat4 view_projection = camera_.ViewProjection();
+    const mat4 inv_view_projection = inverse(view_projection);
+    const vec3 camera_position = camera_.position_;
+    const vec3 earth_center = earth_.center();
+    const float bottom_radius = earth_.parameters.bottom_radius;
+    const float r = distance(camera_position, earth_center);
+    const vec3 up_direction = normalize(camera_position - earth_center);
+    auto unorm = [](float v, float m) { return std::nearbyint(std::min(std::max(v, 0.0f), 1.0f) * m); };
+    auto snorm16 = [](float v) { return int16_t(std::nearbyint(std::min(std::max(v, -1.0f), 1.0f) * 32767.0f)); };
+#pragma omp parallel for schedule(static)
+    for (int py = 0; py < height; ++py)
+        for (int px = 0; px < width; ++px) {
+            const size_t o = (size_t(py) * width + px) * 4;
+            for (int k = 0; k < 4; ++k) { albedo[o + k] = 0; normal[o + k] = 0; orm[o + k] = 0; }
+            float u = (float(px) + 0.5f) / float(width), v = (float(py) + 0.5f) / float(height);
+            vec4 h = inv_view_projection * vec4(u * 2.0f - 1.0f, v * 2.0f - 1.0f, 1.0f, 1.0f);
+            vec3 fragment_position(h.x / h.w, h.y / h.w, h.z / h.w);
+            vec3 view_direction = normalize(fragment_position - camera_position);
+            float mu = dot(view_direction, up_direction);
+            float discriminant = r * r * (mu * mu - 1.0f) + bottom_radius * bottom_radius;
+            if (!(mu < 0.0f && discriminant >= 0.0f)) continue;
+            float dist = std::max(-r * mu - std::sqrt(std::max(discriminant, 0.0f)), 0.0f);
+            if (dist >= distance(fragment_position, camera_position)) continue;
+            vec3 ground_position = camera_position + view_direction * dist;
+            vec3 n = normalize(ground_position - earth_center);
+            for (int k = 0; k < 3; ++k) albedo[o + k] = uint8_t(unorm(albedo_rgb[k], 255.0f));
+            albedo[o + 3] = 255;
+            normal[o + 0] = snorm16(n.x); normal[o + 1] = snorm16(n.y); normal[o + 2] = snorm16(n.z); normal[o + 3] = 32767;
+            orm[o + 0] = 65535; orm[o + 1] = 65535; orm[o + 2] = 0; orm[o + 3] = 65535;
+        }
+}
+
 }  // namespace skyhost

@@ -284,3 +284,24 @@ def test_cpp_frame_driver_is_built_and_has_no_cpu_path(tmp_path):
         from skyrendering_b200.renderer import scene_path
         run = subprocess.run([exe, scene_path("c3"), "192", "108"], capture_output=True, text=True)
         assert run.returncode != 0 and "no CPU path" in run.stderr
+
+
+def test_ground_gbuffer_matches_the_ground_pass():
+    """skyhost_ground_gbuffer: the colour targets EarthRender.frag:53-59 writes -- unit sphere normals (RGBA16_SNORM), ORM = (1, 1, 0),
+    the caller's albedo -- exactly on the pixels whose depth skyhost_ground_depth wrote, the cleared value 0 elsewhere."""
+    from skyrendering_b200.host import Scene
+    from skyrendering_b200.renderer import scene_path
+    s = Scene.from_file(scene_path("c3"))
+    w, h = 96, 54
+    s.set_viewport(w, h)
+    depth = s.ground_depth(w, h)
+    albedo, normal, orm = s.ground_gbuffer(w, h, (0.25, 0.5, 0.75))
+    ground = depth != 1.0
+    assert 0.1 < ground.mean() < 0.9
+    assert np.all(albedo[~ground] == 0) and np.all(normal[~ground] == 0) and np.all(orm[~ground] == 0)
+    assert np.all(albedo[ground] == np.array([64, 128, 191, 255], np.uint8))
+    assert np.all(orm[ground] == np.array([65535, 65535, 0, 65535], np.uint16))
+    n = normal[ground][:, :3].astype(np.float64) / 32767.0
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-4)
+    up = np.array(s.atmosphere_render_buffer().up_direction[:])
+    assert np.all(n @ up > 0.999)   # the visible ground is within ~2.5 degrees of the camera's nadir on a 6360 km sphere

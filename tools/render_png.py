@@ -1,6 +1,6 @@
 """Render a scene to a PNG through sky_tonemap (the reference's BloomPass2 tone map without bloom).
 usage: python tools/render_png.py c3|c1|c2|c5[:wdas] WIDTH HEIGHT out.png [--oracle] [--frames N] [--spp N] [--objects]
---objects: shade object pixels (K6's ComputeObjectLuminance) from a synthetic G-buffer + the IBL chain"""
+--objects [synthetic|ground]: shade object pixels (K6's ComputeObjectLuminance) from a G-buffer + the IBL chain"""
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,7 +13,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("scene"); ap.add_argument("width", type=int); ap.add_argument("height", type=int); ap.add_argument("out")
 ap.add_argument("--oracle", action="store_true"); ap.add_argument("--frames", type=int, default=8); ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--exposure", type=float, default=10.0); ap.add_argument("--tracking", type=int, default=0)
-ap.add_argument("--objects", action="store_true")
+ap.add_argument("--objects", nargs="?", const="synthetic", default=None, choices=["synthetic", "ground"],
+                help="shade object pixels: 'synthetic' terrain-like G-buffer, or 'ground' = the analytic ground pass (EarthRender.frag) with a grey albedo")
 a = ap.parse_args()
 if a.oracle:
     from tests.parity import oracle_library
@@ -31,7 +32,7 @@ r.prime()
 depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), dev)
 if a.objects:
     from skyrendering_b200.renderer import synthetic_gbuffer
-    gb = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=1)
+    gb = r.scene.ground_gbuffer(w, h) if a.objects == "ground" else synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=1)
     if dev == "cuda":
         import torch
         gb = [torch.from_numpy(x).cuda() for x in gb]
