@@ -649,10 +649,12 @@ SKY_D float PCSS(const RenderParams& P, const ScatterExtras& e, float3 position)
 }
 // AtmosphereRenderer.glsl:333-343; SampleCloudShadowTransmittance (VolumetricCloudShadowInterface.glsl:4-8)
 // through the cloud shadow sampler: LINEAR, CLAMP_TO_BORDER (1e10, 1) (VolumetricCloud.cpp:106-112)
+template <bool PCSS_ON>  // PCSS_ENABLE is a template flag like the host's #define: as a run-time branch its 25-entry sample table cost
+                         // the plain object kernel 0.5 ms at 4K (1.14 -> 1.64 ms, measured)
 SKY_D float SampleVisibilityFromShadowMap(const RenderParams& P, float3 position) {
     const ObjectParams& O = P.object;
     float visibility = 1.0f;
-    if (O.mesh.shadow_size > 0) visibility = P.cfg.pcss ? PCSS(P, O.mesh, position) : GetVisibilityFromShadowMap(O.mesh, position);
+    if (O.mesh.shadow_size > 0) visibility = PCSS_ON ? PCSS(P, O.mesh, position) : GetVisibilityFromShadowMap(O.mesh, position);
     if (O.cloud_shadow_map) {
         float3 light_ndc = projective_mul(P.r.uCloudShadowMapMat, position);
         const int S = O.cloud_shadow_size;
@@ -741,7 +743,7 @@ SKY_D float3 ComputeObjectLuminance(const RenderParams& P, float3 position, floa
 // in-scatter only and alpha = 0 (ComputeObjectLuminance needs the G-buffer + IBL chain);
 // the star-map term of sky pixels (:427-429) is in the same "next" row.
 // HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
-template <bool EXTRA, bool OBJECT>
+template <bool EXTRA, bool OBJECT, bool PCSS_ON = false>
 __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
     if (P.band_count > 1) py = ((py / P.band_rows) * P.band_count + P.band_index) * P.band_rows + py % P.band_rows;
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
     float alpha = 1.0f;
     if (intersect_object) {
         if (OBJECT) {  // :404-410
-            float shadow_visibility = SampleVisibilityFromShadowMap(P, fragment_position);
+            float shadow_visibility = SampleVisibilityFromShadowMap<PCSS_ON>(P, fragment_position);
             if (EXTRA && P.extras.moon_shadow)
                 shadow_visibility *= GetVisibilityFromMoonShadow(f3(P.extras.moon_position) - fragment_position, P.extras.moon_radius, sun_direction, P.atm.u.sun_angular_radius);
             luminance += transmittance * ComputeObjectLuminance(P, fragment_position, view_direction, shadow_visibility, vTexCoord);
@@ -962,7 +964,10 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
     const bool extra = P.cfg.moon_shadow || P.cfg.volumetric_light;
     const dim3 grid(ceil_div(w, 256), rows);
     if (ctx->gbuffer_albedo) {  // object branch (sky_set_gbuffer); api.cu has checked that the IBL chain exists
-        if (extra) k6_composite<true, true><<<grid, 256, 0, ctx->stream>>>(P);
+        if (P.cfg.pcss) {
+            if (extra) k6_composite<true, true, true><<<grid, 256, 0, ctx->stream>>>(P);
+            else k6_composite<false, true, true><<<grid, 256, 0, ctx->stream>>>(P);
+        } else if (extra) k6_composite<true, true><<<grid, 256, 0, ctx->stream>>>(P);
         else k6_composite<false, true><<<grid, 256, 0, ctx->stream>>>(P);
     } else if (extra) k6_composite<true, false><<<grid, 256, 0, ctx->stream>>>(P);
     else k6_composite<false, false><<<grid, 256, 0, ctx->stream>>>(P);
