@@ -6,7 +6,7 @@
 // Compiled with -fmad=false like the LUT bake: IEEE division / sqrt, sin / cos from include/sky_detmath.h, the reference's
 // operation order (K23 keeps its shared-memory tree, K22 / K24 their serial sample sums), so K23, the mips and every
 // level of K24 whose LOD arithmetic does not involve log2 are bit-identical to the oracle; powf / log2f are CUDA's (see
-// tests/test_gpu_parity.py for the stated tolerance).
+// tests/test_gpu_ibl.py for the stated tolerance).
 //
 // Mapping (all three are small, latency-bound kernels of the per-frame LUT phase, so the point is FEW launches):
 //   * one launch does the cube mips (6 blocks, one per face, levels chained through __syncthreads -- a face's chain only
@@ -143,7 +143,7 @@ SKY_D void env_radiance_sh(const MipShParams& P, int index, float3* Llm_local) {
     float cos_phi = sky_det_cosf(phi);
     float sin_phi = sky_det_sinf(phi);
     float3 dir = f3(cos_phi * sin_theta, cos_theta, sin_phi * sin_theta);
-    float3 radiance = xyz(TextureCubeLevel<true>(P.level0, P.n, dir));
+    float3 radiance = xyz(TextureCubeLevel(P.level0, P.n, dir));
     float c;
     switch (index) {
         case 0: c = Y00; break;

@@ -13,7 +13,6 @@ struct CubeChainView {
 };
 
 // GL 4.6 table 8.19 face selection + bilinear inside the face, clamped at its edge (oracle/ibl.cpp TextureCubeLevel)
-template <bool LDG>
 SKY_D float4 TextureCubeLevel(const half4* lvl, int n, float3 dir) {
     float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
     int face; float sc, tc, ma;
@@ -38,10 +37,10 @@ SKY_D float4 TextureCubeLod(const CubeChainView& c, float3 dir, float lod) {
     float fl = floorf(l);
     int l0 = int(fl);
     float f = l - fl;
-    float4 t0 = TextureCubeLevel<true>(c.level[l0], c.n >> l0, dir);
+    float4 t0 = TextureCubeLevel(c.level[l0], c.n >> l0, dir);
     if (!(f > 0.0f)) return t0;
     int l1 = l0 + 1 > q ? q : l0 + 1;
-    float4 t1 = TextureCubeLevel<true>(c.level[l1], c.n >> l1, dir);
+    float4 t1 = TextureCubeLevel(c.level[l1], c.n >> l1, dir);
     return t0 * (1.0f - f) + t1 * f;
 }
 
