@@ -2,7 +2,9 @@
 // AppWindow::HandleDisplayEvent / Render do per frame (src/SkyRendering/AppWindow.cpp:139-181), without a window.
 //
 //   skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file.vdb] [--raw8 file dx dy dz]
-//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--out image.ppm] [--dump-rgba8 file]
+//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--out image.ppm] [--dump-rgba8 file]
+// --objects shades object pixels like the reference (AtmosphereRenderer.glsl:284-343): the environment-BRDF LUT once, the IBL tail
+// of the LUT phase every frame, and the G-buffer of the analytic ground pass (skyhost_ground_gbuffer) bound with sky_set_gbuffer.
 //
 // The scene JSON is the reference's own config format (bin/config*.json); the host library deserialises it with the
 // reference's defaults and computes every uniform block; the CUDA library renders.  There is no Python and no CPU fallback in
@@ -60,6 +62,7 @@ struct Driver {
     SkyCloudCommonBufferData common{};
     SkyCloudBufferData cloud{};
     SkyMaterialBlock material{};
+    bool objects = false;  // --objects: the object branch of the composite on the ground pass's G-buffer
 
     void earth_update() {  // Earth::Update (Earth.cpp:42-44)
         SkyAtmosphereBufferData a;
@@ -72,6 +75,7 @@ struct Driver {
         host_ok(skyhost_atmosphere_render_buffer(scene, &r), "atmosphere_render_buffer");
         host_ok(skyhost_lut_config(scene, &cfg), "lut_config");
         sky_ok(sky_atmosphere_luts(ctx, &r, &cfg), "atmosphere_luts");
+        if (objects) sky_ok(sky_ibl_precompute(ctx), "ibl_precompute");  // glGenerateTextureMipmap + IBL::Precompute (AtmosphereRenderer.cpp:242-244)
     }
     void cloud_update(float dt) {  // VolumetricCloud::Update (VolumetricCloud.cpp:168-280) + DynamicTexture::GenerateIfParameterChanged
         host_ok(skyhost_cloud_update(scene, dt, &common, &cloud, &material), "cloud_update");
@@ -103,7 +107,7 @@ struct Driver {
 
 int main(int argc, char** argv) {
     if (argc < 4) die("usage: skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file] [--raw8 file dx dy dz] "
-                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--out image.ppm] [--dump-rgba8 file]");
+                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--out image.ppm] [--dump-rgba8 file]");
     const std::string scene_path = argv[1];
     Driver d;
     d.width = std::atoi(argv[2]);
@@ -123,6 +127,7 @@ int main(int argc, char** argv) {
         else if (a == "--strict") strict = true;
         else if (a == "--overlap") overlap = true;
         else if (a == "--pipeline") pipeline = true;
+        else if (a == "--objects") d.objects = true;
         else if (a == "--out") out_ppm = next();
         else if (a == "--dump-rgba8") dump_rgba8 = next();
         else if (a == "--data") data_dir = next();
@@ -182,6 +187,23 @@ int main(int argc, char** argv) {
     cuda_ok(cudaMalloc(&rgba8, npix * 4), "cudaMalloc");
     cuda_ok(cudaMemcpy(depth, depth_host.data(), npix * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
     cuda_ok(cudaMemset(hdr, 0, npix * 8), "cudaMemset");
+
+    void *gb_albedo = nullptr, *gb_normal = nullptr, *gb_orm = nullptr;
+    if (d.objects) {  // Textures::Textures bakes the environment-BRDF LUT once (Textures.cpp:60-75); Earth::RenderToGBuffer's targets are inputs
+        sky_ok(sky_env_brdf_lut(d.ctx), "env_brdf_lut");
+        std::vector<uint8_t> albedo(npix * 4);
+        std::vector<int16_t> normal(npix * 4);
+        std::vector<uint16_t> orm(npix * 4);
+        const float grey[3] = {0.3f, 0.3f, 0.3f};
+        host_ok(skyhost_ground_gbuffer(d.scene, grey, albedo.data(), normal.data(), orm.data(), d.width, d.height), "ground_gbuffer");
+        cuda_ok(cudaMalloc(&gb_albedo, npix * 4), "cudaMalloc");
+        cuda_ok(cudaMalloc(&gb_normal, npix * 8), "cudaMalloc");
+        cuda_ok(cudaMalloc(&gb_orm, npix * 8), "cudaMalloc");
+        cuda_ok(cudaMemcpy(gb_albedo, albedo.data(), npix * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
+        cuda_ok(cudaMemcpy(gb_normal, normal.data(), npix * 8, cudaMemcpyHostToDevice), "cudaMemcpy");
+        cuda_ok(cudaMemcpy(gb_orm, orm.data(), npix * 8, cudaMemcpyHostToDevice), "cudaMemcpy");
+        sky_ok(sky_set_gbuffer(d.ctx, gb_albedo, gb_normal, gb_orm), "set_gbuffer");
+    }
 
     // frame 0 state: the atmosphere once, so that the first cloud update sees a sun direction
     d.earth_update();
