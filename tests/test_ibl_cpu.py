@@ -114,3 +114,51 @@ def test_ibl_errors():
         r.ctx.ibl_precompute()  # no environment cube yet
     with pytest.raises(abi.SkyError):
         r.ctx.read(abi.RES_ENV_BRDF_LUT)
+
+
+def test_gbuffer_binding_errors():
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    from tests.parity import make_buffers
+    w, h = 64, 36
+    r = Renderer("c3", w, h, library=oracle_library())
+    r.prime()
+    depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), "cpu")
+    g = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:])
+    with pytest.raises(abi.SkyError):
+        r.ctx.set_gbuffer(g[0], None, None)            # all three targets or none
+    r.ctx.set_gbuffer(*g)
+    with pytest.raises(abi.SkyError):
+        r.ctx.composite(depth, hdr, w, h)              # the IBL chain has not run
+    r.ctx.set_gbuffer(None, None, None)
+    r.ctx.composite(depth, hdr, w, h)                  # unbound again: the plain composite
+
+
+def test_pcss_limits():
+    """PCSS (Shadow.glsl:85-99) known answers: under a cleared shadow map (all 1.0) every comparison passes -- visibility 1, the frame
+    equals the hard-shadow frame bit for bit; under an all-blocking map (all 0.0) visibility is 0 with either filter, so both
+    frames lose exactly the direct term and agree again (away from the edge of the light frustum)."""
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    from tests import permutations
+    from tests.parity import make_buffers
+    w, h = 96, 54
+    frames = {}
+    for fill in (1.0, 0.0):
+        for pcss in (True, False):
+            r = Renderer(permutations.scene(pcss=pcss), w, h, library=oracle_library())
+            r.ctx.write(abi.RES_MESH_SHADOW_MAP, np.full((2048, 2048), fill, np.float32))
+            r.enable_ibl()
+            r.prime()
+            depth_np = r.scene.ground_depth(w, h)
+            depth, hdr = make_buffers(w, h, depth_np, "cpu")
+            r.ctx.set_gbuffer(*synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=2))
+            r.ctx.composite(depth, hdr, w, h)
+            frames[(fill, pcss)] = hdr.astype(np.float32).copy()
+    obj = depth_np != 1.0
+    assert np.array_equal(frames[(1.0, True)], frames[(1.0, False)])
+    # (except where the filter footprint straddles the edge of the light frustum: outside it the comparison sampler's border is lit)
+    same = np.all(frames[(0.0, True)] == frames[(0.0, False)], axis=-1)
+    print("all-blocking map: PCSS == hard shadow on", float(same[obj].mean()), "of the object pixels")
+    assert same[obj].mean() > 0.9 and np.all(same[~obj])
+    lit, dark = frames[(1.0, True)][obj][:, :3], frames[(0.0, True)][obj][:, :3]
+    assert np.all(lit >= dark) and (lit > dark).mean() > 0.1   # inside the 8 km light frustum the sun term is gone, the ambient term stays
+    assert dark.min() > 0.0
