@@ -130,6 +130,14 @@ namespace k6s1a1 {
 #include "../_ref/gen/AtmosphereRenderer.glsl.inc"
 #include "ref_undef_guards.h"
 }
+#undef MOON_SHADOW_ENABLE
+#define MOON_SHADOW_ENABLE 1
+namespace k6s1a1m1 {  // scene c1's flags + MOON_SHADOW_ENABLE: the eclipse factor on the object branch's shadow visibility (:406-408)
+#include "../_ref/gen/AtmosphereRenderer.glsl.inc"
+#include "ref_undef_guards.h"
+}
+#undef MOON_SHADOW_ENABLE
+#define MOON_SHADOW_ENABLE 0
 #undef USE_AERIAL_PERSPECTIVE_LUT
 #define USE_AERIAL_PERSPECTIVE_LUT 0
 namespace k6s1a0 {
@@ -279,7 +287,8 @@ struct RefCompositeIO {
 extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphereRenderBufferData* r, const SkyLutConfig* cfg,
                              const RefCompositeIO* io) {
     ref::g_sky_w = cfg->sky_view_width; ref::g_sky_h = cfg->sky_view_height; ref::g_ap_depth = cfg->aerial_perspective_depth;
-    if (cfg->moon_shadow || cfg->volumetric_light) return 3;  // permutation not compiled
+    if (cfg->volumetric_light) return 3;  // permutation not compiled
+    if (cfg->moon_shadow && !(cfg->use_sky_view_lut && cfg->use_aerial_perspective_lut && cfg->raymarching_dither && !cfg->pcss)) return 3;
     static const float zero4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     static const float one4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
     static float zero_cube[6 * 4] = {};
@@ -350,6 +359,7 @@ extern "C" int ref_composite(const SkyAtmosphereBufferData* a, const SkyAtmosphe
         else return 3;
         return 0;
     }
+    if (cfg->moon_shadow) { RUN_K6(k6s1a1m1) return 0; }
     if (cfg->use_sky_view_lut && cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a1)
     else if (cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s1a0)
     else if (!cfg->use_sky_view_lut && !cfg->use_aerial_perspective_lut && cfg->raymarching_dither) RUN_K6(k6s0a0)

@@ -223,6 +223,36 @@ def test_oracle_object_shading_is_the_reference_fragment_program(scene):
 
 
 @pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+def test_oracle_object_shading_under_the_moon_shadow_is_the_reference_fragment_program():
+    """MOON_SHADOW_ENABLE on the object branch (AtmosphereRenderer.glsl:406-408: the eclipse factor multiplies the shadow
+    visibility of the direct term): bit-identical to the reference's fragment program compiled with that define, and the
+    partial eclipse of tests/permutations.py darkens the ground."""
+    from skyrendering_b200.renderer import load_blue_noise, synthetic_gbuffer
+    from tests.parity import make_buffers
+    from tests import permutations
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 192, 108
+    out = {}
+    for moon in (True, False):
+        r = Renderer(permutations.scene(moon=moon), w, h, library=orc)
+        r.enable_ibl()
+        r.prime()
+        depth_np = r.scene.ground_depth(w, h)
+        depth, hdr = make_buffers(w, h, depth_np, "cpu")
+        gbuffer = synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=3)
+        r.ctx.set_gbuffer(*gbuffer)
+        r.ctx.composite(depth, hdr, w, h)
+        out[moon] = hdr.astype(np.float32).copy()
+        if moon:
+            want = refpin.ref_composite(ref, r, depth_np, w, h, load_blue_noise(), froxel=r.ctx.read(abi.RES_SHADOW_FROXEL), gbuffer=gbuffer,
+                                        cloud_shadow_map=r.ctx.read(abi.RES_SHADOW_MAP))
+            want16 = want.astype(np.float16).astype(np.float32)
+            assert np.all(np.isfinite(want16)) and np.array_equal(out[True], want16)
+    obj = depth_np != 1.0
+    assert obj.mean() > 0.1 and (out[True][obj][:, :3] < out[False][obj][:, :3]).mean() > 0.9
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
 def test_oracle_pcss_is_the_reference_fragment_program():
     """PCSS_ENABLE 1 (Shadow.glsl:13-99: Poisson disc seeded per pixel, blocker search through the NEAREST view of the mesh shadow
     map, 25-tap percentage-closer filter through the comparison sampler) on object pixels under a synthetic occluder: the
