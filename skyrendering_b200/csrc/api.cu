@@ -176,7 +176,11 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
         g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
         return 1;
     }
-    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
     SkyContext* ctx = new SkyContext();
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -191,7 +195,7 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     }
     if (rc) {
         g_create_error = ctx->error.empty() ? "device allocation failed" : ctx->error;
-        delete ctx;
+        sky_ctx_destroy(ctx);  // frees whatever was allocated before the failure
         return 1;
     }
     *out = ctx;
@@ -238,6 +242,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     if (ctx->stage_hdr) cudaFree(ctx->stage_hdr);
     if (ctx->pt_samples) cudaFree(ctx->pt_samples);
     if (ctx->pt_job_counter) cudaFree(ctx->pt_job_counter);
+    if (ctx->voxel_majorant) cudaFree(ctx->voxel_majorant);
+    free_lut(ctx->alt.shadow_blurred);
     sky_peer_detach(ctx);
     if (ctx->my_flags) cudaFree(ctx->my_flags);
     delete ctx;
@@ -321,10 +327,21 @@ int sky_set_frame_pipelining(SkyContext* ctx, int enable) {
 
 const char* sky_last_error(SkyContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
+// a device-side wait of the tile-sharded frame's peer barrier gave up (k_peer_flags): report it once the stream has drained
+static int check_peer_timeout(SkyContext* ctx) {
+    if (!ctx->my_flags || ctx->peer_world <= 1) return 0;
+    unsigned int flag = 0;
+    SKY_CUDA(ctx, cudaMemcpy(&flag, ctx->my_flags + SKY_PEER_TIMEOUT_SLOT, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (!flag) return 0;
+    SKY_CUDA(ctx, cudaMemset(ctx->my_flags + SKY_PEER_TIMEOUT_SLOT, 0, sizeof(flag)));
+    return sky_fail(ctx, "tile-sharded frame: timed out waiting for the rows of rank " + std::to_string(flag - 1) +
+                             " (a rank skipped a frame, died, or attached out of step)");
+}
+
 int sky_sync(SkyContext* ctx) {
     if (int e = lanes_join(ctx)) return e;
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return check_peer_timeout(ctx);
 }
 
 int sky_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
@@ -369,6 +386,7 @@ int sky_set_viewport(SkyContext* ctx, int w, int h) {
     rc |= sky_alloc(ctx, ctx->reconstruct[1], w / 2, h / 2);
     rc |= sky_alloc(ctx, ctx->shadow_froxel, w / 12, h / 12, 128);
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);
+    if (ctx->alt.shadow_blurred.p) rc |= sky_alloc(ctx, ctx->alt.shadow_blurred, 512, 512);
     free_lut(ctx->pt_accum);
     free_lut(ctx->pt_mask);
     if (int e = lut_stream_follow_main(ctx)) return e;  // the zero-filled shadow maps are inputs of the shadow chain
@@ -527,11 +545,19 @@ int sky_set_material(SkyContext* ctx, const SkyMaterialBlock* m) {
 int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");  // VolumetricCloud.cpp:169-170
     if (ctx->pipelining) {
-        // K11-K13 read nothing a frame in flight writes except their own shadow maps (same stream) and write the froxels, which
-        // K6 / K16 of the frame in flight still read: they go to the second froxel volume, on lut_stream after this frame's bake
+        // K11-K13 run on lut_stream after this frame's bake, beside the K6 / K16 of the frame in flight.  What they WRITE and that
+        // frame still READS is double-buffered: the froxels (K6, K16) and the blurred shadow map shadow_maps[2] (the object
+        // branch of K6, ComputeObjectLuminance's cloud shadow).  The raw / half-blurred maps [0], [1] are only touched by the
+        // chain itself (same stream).  The set written now was last read two frames ago, i.e. before the event lut_stream
+        // waited for at this frame's bake.
         Lut<uint16_t>& other = ctx->alt.shadow_froxel;
         if (other.w != ctx->shadow_froxel.w || other.h != ctx->shadow_froxel.h || other.d != ctx->shadow_froxel.d) {
             if (int e = sky_alloc(ctx, other, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d)) return e;
+            ctx->bake_since_shadow = false;
+        }
+        Lut<float2>& other_map = ctx->alt.shadow_blurred;
+        if (other_map.w != ctx->shadow_maps[2].w || other_map.h != ctx->shadow_maps[2].h) {
+            if (int e = sky_alloc(ctx, other_map, ctx->shadow_maps[2].w, ctx->shadow_maps[2].h)) return e;
             ctx->bake_since_shadow = false;
         }
         if (!ctx->bake_since_shadow) {  // out-of-protocol call (no bake since the last shadow pass): order conservatively
@@ -540,6 +566,7 @@ int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
         }
         ctx->bake_since_shadow = false;
         std::swap(ctx->shadow_froxel, other);
+        std::swap(ctx->shadow_maps[2], other_map);
         ctx->pre_composite_recorded = false;  // a new frame
         ctx->luts_pending = true;
         LaneScope lane(ctx, ctx->lut_stream);
@@ -615,10 +642,15 @@ int sky_peer_export(SkyContext* ctx, SkyPeerHandles* out) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "SkyPeerHandles carries 64-byte IPC handles");
     if (ctx->width == 0) return sky_fail(ctx, "Volumetric cloud viewport is undefined");
     if (!ctx->my_flags) {
-        // [0, 8): "rows arrived" epochs, [8, 16): "finished reading" epochs, one slot per peer
-        SKY_CUDA(ctx, cudaMalloc(&ctx->my_flags, 2 * SKY_MAX_PEERS * sizeof(unsigned int)));
-        SKY_CUDA(ctx, cudaMemset(ctx->my_flags, 0, 2 * SKY_MAX_PEERS * sizeof(unsigned int)));
+        // [0, 8): "rows arrived" epochs, [8, 16): "finished reading" epochs, one slot per peer; [16]: a wait timed out
+        SKY_CUDA(ctx, cudaMalloc(&ctx->my_flags, SKY_PEER_FLAG_SLOTS * sizeof(unsigned int)));
     }
+    // Export + attach is a collective (every rank needs every rank's handles, so nobody can attach before everybody has
+    // exported): all ranks restart from epoch 0 with cleared flags HERE, which keeps the per-context epochs in step even
+    // when one rank re-created its context and another kept its own.
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SKY_CUDA(ctx, cudaMemset(ctx->my_flags, 0, SKY_PEER_FLAG_SLOTS * sizeof(unsigned int)));
+    ctx->peer_epoch = 0;
     cudaIpcMemHandle_t h;
     SKY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->render_texture.p));
     std::memcpy(out->render, &h, 64);
@@ -654,7 +686,6 @@ int sky_peer_attach(SkyContext* ctx, int rank, int world_size, const SkyPeerHand
         SKY_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         ctx->peer_flags[k] = static_cast<unsigned int*>(p);
     }
-    // peer_epoch keeps counting across re-attachments: flags only ever grow
     return 0;
 }
 

@@ -884,9 +884,14 @@ int launch_atmosphere_bake(SkyContext* ctx) {
     P.transmittance_out = ctx->transmittance.p;
     P.multiscattering_out = ctx->multiscattering.p;
     P.ms_w = ctx->multiscattering.w; P.ms_h = ctx->multiscattering.h;
+    SKY_PERF_MARKER("UpdateLuts");  // Atmosphere.cpp:102
+    nvtxRangePushA("Transmittance");  // :112
     k1_transmittance<<<dim3(ceil_div(P.transmittance.w, 128), P.transmittance.h), 128, 0, ctx->stream>>>(P);
+    nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
+    nvtxRangePushA("Multiscattering");  // :116
     k2_multiscattering<<<dim3(P.ms_w, P.ms_h), 64, 0, ctx->stream>>>(P);
+    nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
     return launch_lut_half_copies(ctx);
 }
@@ -901,9 +906,12 @@ int launch_atmosphere_luts(SkyContext* ctx) {
     // K3: 64 texels of a row per block; K4: 64 threads = two rows of the 32-wide froxel slice
     const int g3x = ceil_div(P.cfg.sky_view_width, 64), n3 = g3x * P.cfg.sky_view_height;
     const int g4x = ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), n4 = g4x * P.ap_lum.d;
+    nvtxRangePushA("SkyViewLut + AerialPerspective");  // AtmosphereRenderer.cpp:222,229 (one launch here)
     if (extra) k34_sky_view_and_aerial_perspective<true><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
     else k34_sky_view_and_aerial_perspective<false><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
+    nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
+    SKY_PERF_MARKER("EnvironmentLuminance");  // :236
     k5_environment<<<dim3(ceil_div(P.cfg.environment_size, 128), P.cfg.environment_size, 6), 128, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
@@ -948,6 +956,7 @@ __global__ void __launch_bounds__(256) k21_tonemap(const __grid_constant__ ToneM
 }  // namespace
 int launch_tonemap(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out) {
     if (p.tone_mapping != 0 && p.tone_mapping != 1) return sky_fail(ctx, "tonemap: unknown tone mapping operator");
+    SKY_PERF_MARKER("PostProcess");  // HDRBuffer.cpp:42
     ToneMapKernelParams P{p, hdr, static_cast<uchar4*>(out), ctx->blue_noise, w, h};
     k21_tonemap<<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
@@ -962,6 +971,7 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
     const int rows = owned_rows(ctx, h);
     if (rows <= 0) return 0;
     const bool extra = P.cfg.moon_shadow || P.cfg.volumetric_light;
+    SKY_PERF_MARKER("Render");  // AtmosphereRenderer.cpp:247
     const dim3 grid(ceil_div(w, 256), rows);
     if (ctx->gbuffer_albedo) {  // object branch (sky_set_gbuffer); api.cu has checked that the IBL chain exists
         if (P.cfg.pcss) {

@@ -678,6 +678,7 @@ __global__ void __launch_bounds__(256) k_tex_peak(cudaTextureObject_t tex, int i
 // message.  Epochs only grow, so a late reader never sees a stale match.
 // Two flag sets per rank: [0, 8) "rows of frame e arrived", [8, 16) "I finished reading frame e" -- the second
 // one keeps a fast rank from overwriting a slow rank's copy while its K17 is still reading it.
+constexpr unsigned long long kPeerWaitTimeoutNs = 10ull * 1000 * 1000 * 1000;  // 10 s
 struct PeerBarrierParams {
     unsigned int* peer_flags[8];
     unsigned int* my_flags;
@@ -696,7 +697,16 @@ __global__ void __launch_bounds__(32) k_peer_flags(const __grid_constant__ PeerB
         }
         if (P.wait) {
             volatile unsigned int* mine = P.my_flags + P.offset + k;
-            while (*mine < P.epoch) __nanosleep(200);
+            // bounded: a rank that died, skipped a frame or attached out of step must not hang this GPU's stream for ever.
+            // After kPeerWaitTimeoutNs the frame goes on with whatever rows arrived and slot SKY_PEER_TIMEOUT_SLOT records the
+            // peer; sky_sync / sky_read_resource turn it into an error.
+            unsigned long long t0 = 0, now = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*mine < P.epoch) {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > kPeerWaitTimeoutNs) { P.my_flags[SKY_PEER_TIMEOUT_SLOT] = 1u + (unsigned int)k; break; }
+            }
             __threadfence_system();
         }
     }
@@ -791,6 +801,7 @@ static int check_material_ready(SkyContext* ctx) {
 
 int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
     if (int e = check_material_ready(ctx)) return e;
+    SKY_PERF_MARKER("VolumetricCloudShadow");  // VolumetricCloud.cpp:283
     std::swap(ctx->shadow_maps[0], ctx->shadow_maps[1]);  // VolumetricCloud.cpp:284
     CloudParams P = make_cloud_params(ctx, c);
     P.shadow_prev = ctx->shadow_maps[1].p;
@@ -800,6 +811,7 @@ int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
     const bool count = ctx->counting;
     dim3 grid(ceil_div(P.shadow_w, 16), ceil_div(P.shadow_h, 8));
     int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
+        SKY_PERF_MARKER("VolumetricCloudShadowMap");  // :288
         if (count) k11_shadow_map<MAT, HW, true><<<grid, 128, 0, ctx->stream>>>(P);
         else k11_shadow_map<MAT, HW, false><<<grid, 128, 0, ctx->stream>>>(P);
         return 0;
@@ -807,10 +819,13 @@ int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
     if (rc) return sky_fail(ctx, "unknown material");
     SKY_LAUNCH_CHECK(ctx);
     dim3 bgrid(ceil_div(P.shadow_w, 128), P.shadow_h);
+    nvtxRangePushA("VolumetricCloudShadowMapBlur");  // :300
     k12_blur<true><<<bgrid, 128, 0, ctx->stream>>>(ctx->shadow_maps[0].p, ctx->shadow_maps[1].p, P.shadow_w, P.shadow_h);
     SKY_LAUNCH_CHECK(ctx);
     k12_blur<false><<<bgrid, 128, 0, ctx->stream>>>(ctx->shadow_maps[1].p, ctx->shadow_maps[2].p, P.shadow_w, P.shadow_h);
+    nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
+    SKY_PERF_MARKER("VolumetricCloudShadowFroxel");  // :316
     k13_shadow_froxel<<<dim3(ceil_div(P.froxel.w, 64), P.froxel.h), 64, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
@@ -824,10 +839,18 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
     P.b = b;
     P.depth = depth;
     const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
-    k14_checkerboard<<<dim3(ceil_div(HW_, 256), HH), 256, 0, ctx->stream>>>(P);
-    SKY_LAUNCH_CHECK(ctx);
-    k15_index_gen<<<dim3(ceil_div(QW, 128), QH), 128, 0, ctx->stream>>>(P);
-    SKY_LAUNCH_CHECK(ctx);
+    SKY_PERF_MARKER("VolumetricCloud");  // VolumetricCloud.cpp:333
+    {
+        SKY_PERF_MARKER("Checkerboard Depth");  // :335
+        k14_checkerboard<<<dim3(ceil_div(HW_, 256), HH), 256, 0, ctx->stream>>>(P);
+        SKY_LAUNCH_CHECK(ctx);
+    }
+    {
+        SKY_PERF_MARKER("Index Generate");  // :349
+        k15_index_gen<<<dim3(ceil_div(QW, 128), QH), 128, 0, ctx->stream>>>(P);
+        SKY_LAUNCH_CHECK(ctx);
+    }
+    SKY_PERF_MARKER("Render");  // :362
     int rows = QH;
     ctx->peer_band_frame = false;
     if (band_rows > 0 && band_count > 1) {
@@ -871,7 +894,9 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
     P.reconstruct_out = ctx->reconstruct[0].p;
     P.reconstruct_prev = ctx->reconstruct[1].p;
     const int HW_ = P.width / 2, HH = P.height / 2;
+    SKY_PERF_MARKER("VolumetricCloud");
     if (phases & 1) {
+        SKY_PERF_MARKER("Reconstruct");  // VolumetricCloud.cpp:388
         const bool peer_frame = ctx->peer_band_frame;
         PeerBarrierParams B{};
         if (peer_frame) {
@@ -891,6 +916,7 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
         SKY_LAUNCH_CHECK(ctx);
     }
     if (phases & 2) {
+        SKY_PERF_MARKER("Upscale");  // VolumetricCloud.cpp:407
         P.out_band_rows = ctx->out_band_rows; P.out_band_index = ctx->out_band_index; P.out_band_count = ctx->out_band_count;
         const int rows = owned_rows(ctx, P.height);
         if (rows > 0) k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(rows, 8)), 256, 0, ctx->stream>>>(P);

@@ -4,9 +4,12 @@
 #include <algorithm>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
-constexpr int kMaxMipLevels = 13;  // up to 4096 texels per axis
+constexpr int kMaxMipLevels = 13;
+constexpr int SKY_PEER_TIMEOUT_SLOT = 16, SKY_PEER_FLAG_SLOTS = 32;  // see k_peer_flags (cloud.cu)  // up to 4096 texels per axis
 
 // A UNORM8 texture with its full mip chain, kept twice: as linear device memory (exact fp32
 // software filtering, the default) and as a CUDA mip-mapped array behind two texture objects
@@ -83,6 +86,8 @@ struct SkyContext {
         Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
         Lut<half4> env, transmittance_h, multiscattering_h;
         Lut<uint16_t> shadow_froxel;   // second froxel volume: the shadow chain of frame N+1 also runs on lut_stream
+        Lut<float2> shadow_blurred;    // second blurred cloud shadow map (shadow_maps[2]): the object branch of frame N's K6 samples
+                                       // it on the caller's stream while K12 of frame N+1 writes the other one on lut_stream
         cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0, sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
         const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
         int lut_tex_dims[4][3] = {};
@@ -164,7 +169,7 @@ struct SkyContext {
     half4* peer_render[8] = {};      // [rank] -> that rank's render_texture (own entry = local pointer)
     float* peer_distance[8] = {};
     unsigned int* peer_flags[8] = {};  // [rank] -> that rank's arrival flags
-    unsigned int* my_flags = nullptr;  // unsigned int[8], written by peers
+    unsigned int* my_flags = nullptr;  // unsigned int[SKY_PEER_FLAG_SLOTS]: [0,8) arrival epochs, [8,16) done epochs (written by peers), [16] timeout
     unsigned int peer_epoch = 0;
     bool peer_band_frame = false;      // the open frame rendered bands into peer memory
 
@@ -173,6 +178,19 @@ struct SkyContext {
     half4* stage_hdr = nullptr;
     size_t stage_pixels = 0;
 };
+
+// NVTX ranges named like the reference's PERF_MARKER debug groups (src/Base/include/PerformanceMarker.h:8-18; call sites
+// Atmosphere.cpp:102-116, AtmosphereRenderer.cpp:222-247, VolumetricCloud.cpp:283-316,333-407, IBL.cpp:29-35): a timeline tool
+// shows the same pass names the reference shows in a GL debugger.  Header-only NVTX 3: a no-op unless a tool is attached.
+struct SkyPerfMarker {
+    explicit SkyPerfMarker(const char* message) { nvtxRangePushA(message); }
+    ~SkyPerfMarker() { nvtxRangePop(); }
+    SkyPerfMarker(const SkyPerfMarker&) = delete;
+    SkyPerfMarker& operator=(const SkyPerfMarker&) = delete;
+};
+#define SKY_PERF_CONCAT_INNER(a, b) a##b
+#define SKY_PERF_CONCAT(a, b) SKY_PERF_CONCAT_INNER(a, b)
+#define SKY_PERF_MARKER(message) SkyPerfMarker SKY_PERF_CONCAT(sky_perf_marker_, __LINE__)(message)
 
 // error plumbing ------------------------------------------------------------------------------------------
 int sky_fail(SkyContext* ctx, const std::string& msg);

@@ -266,7 +266,9 @@ int launch_ibl_precompute(SkyContext* ctx) {
     while ((n >> levels) >= 1) ++levels;
     MipShParams M{};
     M.level0 = ctx->env.p; M.mips = ctx->env_mips; M.n = n; M.levels = levels; M.sh = ctx->env_sh.p;
+    nvtxRangePushA("Environment Radiance SH");  // IBL.cpp:29 (+ glGenerateTextureMipmap of the cube, AtmosphereRenderer.cpp:243)
     k23_env_sh_and_cube_mips<<<9 + 6, 1024, 0, ctx->stream>>>(M);
+    nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
 
     PrefilterParams P{};
@@ -290,6 +292,7 @@ int launch_ibl_precompute(SkyContext* ctx) {
         blocks += ceil_div(6 * w * w, kPrefilterThreads / prefilter_lanes(level));
     }
     P.first_block[SKY_IBL_ROUGHNESS_COUNT] = blocks;
+    SKY_PERF_MARKER("Prefilter Radiance");  // IBL.cpp:35
     k24_prefilter_radiance<<<blocks, kPrefilterThreads, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;

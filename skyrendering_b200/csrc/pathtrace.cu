@@ -884,6 +884,7 @@ PtParams make_pt_params(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
 }  // namespace
 
 int launch_pt_samples(SkyContext* ctx, const SkyCloudCommonBufferData& c, uint32_t frame_begin, uint32_t count, const int32_t region[4]) {
+    SKY_PERF_MARKER("PathTracing");  // PathTracing::Render, VolumetricCloud.cpp:533-560 (the reference sets no marker of its own here)
     if (!ctx->pt_accum.p) return sky_fail(ctx, "pt_begin was not called");
     if (!ctx->ap_lum.p || !ctx->env.p) return sky_fail(ctx, "atmosphere LUTs have not been baked");
     if (ctx->material.type == SKY_MATERIAL_VOXEL && !ctx->voxel.valid) return sky_fail(ctx, "voxel grid has not been uploaded");

@@ -187,9 +187,20 @@ void read_tree_topology(Reader& r, Context& c, Tree& tree) {
     if (buffer_count != 1) throw std::runtime_error("vdb: multi-buffer trees are not supported");
     c.background = r.get<float>();
     uint32_t num_tiles = r.get<uint32_t>(), num_children = r.get<uint32_t>();
+    // Root-level origins come verbatim from the file: a root child / tile of Tree_float_5_4_3 spans 4096 voxels per axis and
+    // sits on a multiple of 4096, and everything derived from an origin (child origins, the dense bounding box) must stay
+    // inside int32 with room for the node's extent.  Anything else is a malformed file, not a grid.
+    auto check_root_origin = [](const int32_t o[3]) {
+        for (int a = 0; a < 3; ++a) {
+            if (o[a] & 4095) throw std::runtime_error("vdb: root-level origin is not aligned to the 4096-voxel root node size");
+            if (int64_t(o[a]) > int64_t(INT32_MAX) - 4096 || int64_t(o[a]) < int64_t(INT32_MIN) + 4096)
+                throw std::runtime_error("vdb: root-level origin out of range");
+        }
+    };
     for (uint32_t i = 0; i < num_tiles; ++i) {
         Tile t;
         r.read(t.origin, 12);
+        check_root_origin(t.origin);
         t.value = r.get<float>();
         bool active = r.get<uint8_t>() != 0;
         t.dim = 1 << 12;
@@ -198,6 +209,7 @@ void read_tree_topology(Reader& r, Context& c, Tree& tree) {
     for (uint32_t i = 0; i < num_children; ++i) {
         int32_t origin[3];
         r.read(origin, 12);
+        check_root_origin(origin);
         read_internal<5, 12, 7>(r, c, origin, tree, [&](const int32_t o5[3]) {
             read_internal<4, 7, 3>(r, c, o5, tree, [&](const int32_t o4[3]) {
                 Leaf leaf;
@@ -221,6 +233,8 @@ void read_tree_buffers(Reader& r, const Context& c, Tree& tree) {
 }
 
 }  // namespace
+
+constexpr int64_t kMaxDenseExtent = 4096;  // = the per-axis limit of sky_voxel_upload (include/skyb200.h)
 
 struct VdbGrid::Impl {
     Tree tree;
@@ -298,6 +312,14 @@ std::unique_ptr<VdbGrid> VdbGrid::parse(const uint8_t* data, size_t size) {
         I.active_voxels += int64_t(t.dim) * t.dim * t.dim;
     }
     if (I.active_voxels == 0) throw std::runtime_error("vdb: the grid has no active values");
+    // the dense fill (VolumetricCloudVoxelMaterial.cpp:54-69) allocates the whole bounding box: refuse boxes beyond what
+    // sky_voxel_upload accepts (4096 texels per axis) instead of overflowing int32 extents or allocating many GiB
+    for (int a = 0; a < 3; ++a) {
+        const int64_t extent = int64_t(hi[a]) - int64_t(lo[a]) + 1;
+        if (extent < 1 || extent > kMaxDenseExtent)
+            throw std::runtime_error("vdb: active bounding box spans " + std::to_string(extent) + " voxels on axis " + std::to_string(a) +
+                                     " (dense grids are limited to " + std::to_string(kMaxDenseExtent) + " per axis)");
+    }
     std::memcpy(I.bbox_min, lo, 12);
     std::memcpy(I.bbox_max, hi, 12);
     return g;

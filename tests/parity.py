@@ -58,15 +58,21 @@ def to_numpy(x):
     return x if isinstance(x, np.ndarray) else x.detach().cpu().numpy()
 
 
-def run_cloud_frames(scene, width, height, library, frames, device, composite=True, move=None, hw=False, count=False, strict=False):
+def run_cloud_frames(scene, width, height, library, frames, device, composite=True, move=None, hw=False, count=False, strict=False,
+                     overlap=False, pipelining=False):
     """Bake, zero histories, run `frames` HandleDisplayEvent iterations (static camera unless `move`
-    gives a per-frame camera delta), return the final HDR and the intermediate buffers."""
+    gives a per-frame camera delta), return the final HDR and the intermediate buffers.
+    overlap / pipelining: the production frame mode bench.py times (sky_set_frame_overlap, sky_set_frame_pipelining)."""
     r = Renderer(scene, width, height, library=library)
     if hw:
         r.ctx.set_hw_filtering(True)
     if strict:
         r.ctx.set_strict_arithmetic(True)
     r.prime()
+    if overlap:
+        r.ctx.set_frame_overlap(True)
+    if pipelining:
+        r.ctx.set_frame_pipelining(True)
     depth_np = r.scene.ground_depth(width, height)
     depth, hdr = make_buffers(width, height, depth_np, device)
     out = {}

@@ -14,7 +14,7 @@ import torch
 from skyrendering_b200 import abi
 from skyrendering_b200.renderer import Renderer
 from tests import refpin
-from tests.parity import oracle_library
+from tests.parity import make_buffers, oracle_library, to_numpy
 
 pytestmark = pytest.mark.gpu
 
@@ -81,6 +81,42 @@ def test_ibl_follows_the_lut_phase_under_pipelining(libs):
         outs.append(refpin.ibl_state(r.ctx))
     for a, b in zip(outs[0][0] + [outs[0][1]] + outs[0][2], outs[1][0] + [outs[1][1]] + outs[1][2]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_object_shading_under_pipelining_is_bit_identical(libs, overlap):
+    """Pipelined frames WITH a G-buffer: the object branch of frame N's K6 samples the blurred cloud shadow map (shadow_maps[2]) on
+    the caller's stream while frame N+1's shadow chain (K11-K13) already runs on the internal LUT stream.  That map is
+    double-buffered with the froxels, so every frame of an animated sequence (moving camera: the light-space fit and with it the
+    shadow map change per frame) is bit-identical to the serial run -- at a size where K6 runs long enough to overlap."""
+    from skyrendering_b200.renderer import synthetic_gbuffer
+    cuda, _ = libs
+    w, h = 1920, 1080
+    outs = []
+    for pipelined in (False, True):
+        r = Renderer("c3", w, h, library=cuda)
+        r.enable_ibl()
+        r.prime()
+        gb = [torch.from_numpy(a).cuda() for a in synthetic_gbuffer(w, h, r.render_buffer.up_direction[:], seed=5)]
+        r.ctx.set_gbuffer(*gb)
+        r.ctx.set_frame_overlap(overlap)
+        r.ctx.set_frame_pipelining(pipelined)
+        frames = []
+        for f in range(6):
+            if f:
+                r.scene.camera_move((0.4, 0.05, 0.3))
+            depth, hdr = make_buffers(w, h, r.scene.ground_depth(w, h), "cuda")
+            r.frame(depth, hdr, 0.0)
+            frames.append(hdr)      # six frames in flight, no synchronisation between them
+        r.ctx.sync()
+        outs.append([to_numpy(x).copy() for x in frames] + [r.ctx.read(abi.RES_SHADOW_MAP), r.ctx.read(abi.RES_SHADOW_FROXEL)])
+        r.ctx.set_frame_pipelining(False)
+        r.ctx.set_frame_overlap(False)
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert np.array_equal(a, b, equal_nan=True), i
+    assert not np.array_equal(outs[0][1], outs[0][5])   # the sequence is animated
+    obj = outs[0][5][..., 3] == 1.0
+    assert obj.any()
 
 
 def test_ibl_errors(libs):

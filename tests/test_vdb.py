@@ -68,6 +68,24 @@ def test_unsupported_files_fail_loudly():
         VdbGrid("/nonexistent/file.vdb")
 
 
+def test_malformed_extents_are_refused():
+    """Root origins are read verbatim from the file: a bounding box beyond what sky_voxel_upload accepts (4096 per axis), a
+    misaligned or out-of-range root origin must be an error, not an int32 overflow or a many-GiB dense fill."""
+    import struct
+    far = vdbwrite.write_vdb({(0, 0, 0): 1.0, (5000, 0, 0): 0.5})
+    with pytest.raises(SkyError, match="limited to 4096"):
+        VdbGrid(far)
+    # the root child origin of a one-voxel file is (0, 0, 0) right after (tiles = 0, children = 1): patch it
+    good = vdbwrite.write_vdb({(1, 2, 3): 1.0})
+    marker = struct.pack("<I", 1) + struct.pack("<f", 0.0) + struct.pack("<II", 0, 1) + struct.pack("<iii", 0, 0, 0)  # tree header + first root child
+    at = good.find(marker)
+    assert at > 0
+    for origin, what in (((8, 0, 0), "not aligned"), ((0x7FFFF000, 0, 0), "out of range"), ((0, -0x80000000, 0), "out of range")):
+        bad = good[:at + 16] + struct.pack("<iii", *origin) + good[at + 28:]
+        with pytest.raises(SkyError, match=what):
+            VdbGrid(bad)
+
+
 @pytest.mark.skipif(not os.path.exists(WDAS), reason="the reference tree is only mounted in the build container")
 def test_wdas_sixteenth_against_its_own_metadata_and_the_fixture():
     g = VdbGrid(WDAS)

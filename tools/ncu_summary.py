@@ -2,6 +2,7 @@
 usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.md"""
 import csv
 import io
+import re
 import subprocess
 import sys
 
@@ -38,6 +39,23 @@ def main(path):
             if key in d:
                 print(f"| {label} (`{key}`) | {d[key]} {units[hdr.index(key)]} |")
         print()
+        # warp-state statistics (why warps do not issue) and per-pipe instruction / utilisation counters
+        extra = [k for k in hdr if re.search(r"issue_stalled_\w+_per_warp_active\.pct|average_warps?_issue_stalled_\w+_per_issue_active|"
+                                             r"inst_executed_pipe_\w+\.sum$|pipe_\w+_cycles_active\.avg\.pct_of_peak_sustained_active|"
+                                             r"inst_executed_pipe_\w+\.avg\.pct_of_peak_sustained_active|smsp__warp_issue_stalled", k)]
+        rows_ = []
+        for k in extra:
+            try:
+                v = float(d[k].replace(",", ""))
+            except ValueError:
+                continue
+            if v != 0.0:
+                rows_.append((k, v, units[hdr.index(k)]))
+        if rows_:
+            print("| stall / pipe counter | value |\n|---|---|")
+            for k, v, u in sorted(rows_, key=lambda t: (t[0].split("__")[0], -t[1])):
+                print(f"| `{k}` | {v:.6g} {u} |")
+            print()
 
 
 if __name__ == "__main__":
