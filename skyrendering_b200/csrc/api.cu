@@ -5,6 +5,7 @@
 #include <vector>
 #include "../../include/skyb200.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "context.h"
@@ -184,6 +185,7 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     SkyContext* ctx = new SkyContext();
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    if (const char* lit = std::getenv("SKYB200_K16_LITERAL")) ctx->k16_literal = lit[0] == '1';   // A/B switch for measurements (tools/)
     int rc = 0;
     rc |= alloc_bake_luts(ctx);
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);  // VolumetricCloud.cpp:52,102-105

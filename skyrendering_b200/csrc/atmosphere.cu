@@ -209,6 +209,104 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
     return luminance;
 }
 
+#if defined(SKY_COMPOSITE_TU) && !defined(SKY_STRICT_TU)
+// The production march of K6 (the composite translation unit, -use_fast_math, frame tolerance 1e-2 relative RMS): the SAME
+// quadrature as ComputeScatteredLuminance<false, true, EXTRA> above -- same steps, same midpoint rule, same two LUT fetches per
+// step, same analytic in-segment integral -- with the per-step algebra reduced to what actually depends on the step.  ncu on the
+// statement-by-statement version (profiles/k6_r01i.md): 148 warp instructions and 17 MUFU per step, 80 % issue-active with the
+// XU pipe at ~73 % -- instruction-bound.  Here (96 instructions, 12 MUFU per step):
+//   * |position_i - earth_center| IS r_i, and dot(sun, position_i - earth_center) is linear in d_i: mu_s_i = (a_s + b_s d_i) / r_i
+//     without building or normalising position_i (it is only built for the optional EXTRA terms);
+//   * r_i^2 = dd + r^2 with dd = d_i (d_i + 2 r mu); rho^2 = r_i^2 - bottom^2 = dd + (r^2 - bottom^2) and the discriminant of
+//     DistanceToTopAtmosphereBoundary = (r_i mu_s)^2 + (top^2 - r^2) - dd: the ray constants carry the large cancelling terms once,
+//     in fp32 but from (r - bottom)(r + bottom), which is MORE accurate than the shader's r_i * r_i - bottom * bottom;
+//   * one MUFU.RSQ gives r_i and 1 / r_i; cos_theta_h = -rho / r_i and the smoothstep's 1 / (e1 - e0) = r_i / (2 bottom alpha), so
+//     GetSunVisibility's edge term is ((r_i mu_s + rho) / (2 bottom alpha) + 1/2) saturated: no division, no extra square root;
+//   * every uniform-only factor (phase x scattering x solar illuminance, log2(e) / scale height, LUT texel insets) is folded once per ray.
+// The strict object keeps the shader's statement order (bit-level parity); this one is checked against the oracle at frame tolerance
+// (tests/test_gpu_parity.py: C2 / C3 at 1920x1080, C4 at 3840x2160).
+template <bool EXTRA>
+SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const LutView& transmittance_texture, const LutView& multiscattering_texture,
+                                           float start_i, float3 earth_center, float3 start_position, float3 view_direction, float3 sun_direction,
+                                           float marching_distance, float steps, float3& transmittance, const ScatterExtras* extras) {
+    const SkyAtmosphereBufferData& u = atm.u;
+    const float kLog2e = 1.4426950408889634f;
+    const float3 rel = start_position - earth_center;
+    const float r2 = dot(rel, rel);
+    const float two_rmu = 2.0f * dot(view_direction, rel);               // 2 r mu
+    const float a_s = dot(sun_direction, rel), b_s = dot(sun_direction, view_direction);  // r_i mu_s_i = a_s + b_s d_i
+    const float cos_sun_view = b_s;
+    const float dx = marching_distance / steps;
+    // phase functions (Atmosphere.glsl:138-154) x scattering coefficients x solar illuminance
+    const float rayleigh_phase = (3.0f / (16.0f * kPi)) * (1.0f + cos_sun_view * cos_sun_view);
+    const float g = u.mie_phase_g;
+    const float mie_k = 3.0f / (8.0f * kPi) * (1.0f - g * g) / (2.0f + g * g);
+    const float mie_b = 1.0f + g * g - 2.0f * g * cos_sun_view;
+    const float mie_phase = mie_k * (1.0f + cos_sun_view * cos_sun_view) / (mie_b * sqrtf(mie_b));
+    const float3 solar = f3(u.solar_illuminance);
+    const float3 Rs = f3(u.rayleigh_scattering), Ms = f3(u.mie_scattering), Ma = f3(u.mie_absorption), Oz = f3(u.ozone_absorption);
+    const float3 RsP = Rs * rayleigh_phase * solar, MsP = Ms * mie_phase * solar;   // single scattering, phase and illuminance folded
+    const float3 Qms = solar * u.multiscattering_mask;                                // multiple scattering: x scattering_i x LUT
+    const float k_r = -u.inv_rayleigh_exponential_distribution * kLog2e, k_m = -u.inv_mie_exponential_distribution * kLog2e;
+    const float k_t = -dx * kLog2e;
+    // ray constants of the (r, mu_s) -> transmittance-LUT mapping (Atmosphere.glsl:90-108)
+    const float bottom = u.bottom_radius, top = u.top_radius;
+    const float H = sqrtf((top - bottom) * (top + bottom));
+    const float r0 = sqrtf(r2);
+    const float r2_minus_b2 = (r0 - bottom) * (r0 + bottom), t2_minus_r2 = (top - r0) * (top + r0);
+    const float tw = float(transmittance_texture.w), th = float(transmittance_texture.h);
+    const float uu_a = 1.0f - 1.0f / tw, uu_b = 0.5f / tw, vv_a = (1.0f - 1.0f / th) / H, vv_b = 0.5f / th;
+    const float H_minus_top = H - top;
+    const float edge_k = 0.5f / (bottom * u.sun_angular_radius);
+    // multiscattering LUT (Atmosphere.glsl:169-178): u from mu_s, v from the altitude
+    const float mw = float(multiscattering_texture.w), mh = float(multiscattering_texture.h);
+    const float mu_a = 0.5f * (1.0f - 1.0f / mw), mu_b = 0.5f / mw + mu_a;
+    const float mv_a = (1.0f - 1.0f / mh) / (top - bottom), mv_b = 0.5f / mh;
+
+    float3 T = f3(1.0f), L = f3(0.0f);
+    for (float i = start_i; i < steps; ++i) {
+        const float d = i * dx;
+        const float dd = d * (d + two_rmu);
+        const float ri2 = dd + r2;
+        const float inv_r = rsqrtf(ri2);
+        const float r_i = ri2 * inv_r;
+        const float altitude = r_i - bottom;
+        const float rms = a_s + b_s * d;            // r_i mu_s_i
+        const float mu_s = rms * inv_r;
+        // densities (GetScattering / GetExtinction, :119-132,156-159)
+        const float dR = __saturatef(exp2f(altitude * k_r)), dM = __saturatef(exp2f(altitude * k_m));
+        const float dO = fmaxf(0.0f, 1.0f - fabsf(altitude - u.ozone_center_altitude) * u.inv_ozone_width);
+        const float3 scattering = Rs * dR + Ms * dM;
+        const float3 extinction = scattering + Ma * dM + Oz * dO;
+        const float3 T_i = f3(exp2f(extinction.x * k_t), exp2f(extinction.y * k_t), exp2f(extinction.z * k_t));
+        // GetSunVisibility (:110-117) = LUT(r_i, mu_s) x smoothstep around the geometric horizon
+        const float rho = sqrtf(fmaxf(dd + r2_minus_b2, 0.0f));
+        const float disc = fmaxf(rms * rms + (t2_minus_r2 - dd), 0.0f);
+        const float d_top = fmaxf(sqrtf(disc) - rms, 0.0f);
+        const float d_min = top - r_i;
+        const float x_mu = (d_top - d_min) / (rho + r_i + H_minus_top);   // (d - d_min) / (d_max - d_min)
+        const float4 t_sun = tex2D<float4>(transmittance_texture.tex, uu_b + x_mu * uu_a, vv_b + rho * vv_a);
+        const float4 ms = tex2D<float4>(multiscattering_texture.tex, mu_b + mu_s * mu_a, mv_b + altitude * mv_a);
+        const float e = __saturatef((rms + rho) * edge_k + 0.5f);
+        float vis = e * e * (3.0f - 2.0f * e);
+        float3 position_i;
+        if (EXTRA) {
+            position_i = start_position + view_direction * d;
+            if (extras->shadow_size > 0) vis *= GetVisibilityFromShadowMap(*extras, position_i);  // :274-277 (single scattering only)
+        }
+        float3 L_i = f3(RsP.x * dR + MsP.x * dM, RsP.y * dR + MsP.y * dM, RsP.z * dR + MsP.z * dM) * (f3(t_sun.x, t_sun.y, t_sun.z) * vis) +
+                     f3(ms.x, ms.y, ms.z) * scattering * Qms;
+        if (EXTRA && extras->moon_shadow)  // :281-284
+            L_i *= GetVisibilityFromMoonShadow(f3(extras->moon_position) - position_i, extras->moon_radius, sun_direction, u.sun_angular_radius);
+        // analytic integral over the segment (:288): (L_i - L_i T_i) / extinction, attenuated by the transmittance so far
+        L += T * (L_i - L_i * T_i) * f3(1.0f / extinction.x, 1.0f / extinction.y, 1.0f / extinction.z);
+        T *= T_i;
+    }
+    transmittance = T;
+    return L;
+}
+#endif
+
 // (Measured and removed: the same march spread over the 32 lanes of a warp -- lane l evaluates steps l, l + 32, ..., then every
 // lane replays the running transmittance product / luminance sum over the broadcast records in the reference's order.  It is
 // bit-identical, but K2 went 78 -> 520 us and K3-K5 230 -> 470 us: these kernels already issue at ~50 % of the machine with one
@@ -744,7 +842,7 @@ SKY_D float3 ComputeObjectLuminance(const RenderParams& P, float3 position, floa
 // the star-map term of sky pixels (:427-429) is in the same "next" row.
 // HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
 template <bool EXTRA, bool OBJECT, bool PCSS_ON = false>
-__global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : 3) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
     if (P.band_count > 1) py = ((py / P.band_rows) * P.band_count + P.band_index) * P.band_rows + py % P.band_rows;
     if (px >= P.width || py >= P.height) return;
@@ -778,9 +876,14 @@ __global__ void __launch_bounds__(256) k6_composite(const __grid_constant__ Rend
             transmittance = xyz(sample_lut3d_sel<kCompositeTexLut>(P.ap_trans, uvw.x, uvw.y, uvw.z));
         } else {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
+#if defined(SKY_COMPOSITE_TU) && !defined(SKY_STRICT_TU) && !defined(SKY_K6_REFERENCE_ORDER_MARCH)
+            luminance = ComputeScatteredLuminanceFast<EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position, view_direction,
+                                                             sun_direction, marching_distance, P.r.raymarching_steps, transmittance, &P.extras);
+#else
             luminance = ComputeScatteredLuminance<false, kCompositeTexLut, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
                                                                                   view_direction, sun_direction, marching_distance, P.r.raymarching_steps, transmittance, unused,
                                                                                   &P.extras);
+#endif
         }
     }
     if (P.froxel.p) luminance *= SampleRayScatterVisibility(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);

@@ -334,14 +334,21 @@ SKY_D void ShadeDenseStep(const CloudParams& P, RayMarchContext& ctx, float sigm
     ctx.transmittance *= tr;
 }
 
-template <int MAT, bool HW, bool COUNT>
-__global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_render(const __grid_constant__ CloudParams P) {
+// Per-ray constants of VolumetricCloudRender.comp:139-169: everything main() computes before its two step loops.
+struct RaySetup {
+    int px, py;
+    bool valid;
+    float2 uv;
+    float3 view_dir;
+    float r, mu, frag_dist;
+    float i0t1, i0t2, i1t1, i1t2;
+    float jitter, cos_sun_view;
+};
+SKY_D RaySetup k16_ray_setup(const CloudParams& P, int px, int row_in_band) {   // quarter-res column, row among the rows this launch renders
     const SkyCloudCommonBufferData& c = P.c;
     const SkyCloudBufferData& b = P.b;
     const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
-    const int warp_in_block = int(threadIdx.x >> 5);
-    int px = blockIdx.x * kK16TileW + (kK16Block >= 64 ? (warp_in_block & 1) * 8 : 0) + int(threadIdx.x & 7u);
-    int row_in_band = blockIdx.y * kK16TileH + (kK16Block >= 64 ? (warp_in_block >> 1) * 4 : 0) + int((threadIdx.x >> 3) & 3u);
+    RaySetup S;
     int py = row_in_band;
     if (P.band_rows > 0) {
         // rows owned by this rank: ((py / band_rows) % band_count) == band_index
@@ -350,21 +357,22 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
     }
     // lanes past the image edge march a clamped duplicate ray and skip the stores: every lane reaches the
     // warp votes of the marching loop
-    const bool valid = px < QW && py < QH;
+    S.valid = px < QW && py < QH;
     px = min(px, QW - 1);
     py = min(py, QH - 1);
+    S.px = px; S.py = py;
     uint32_t index = uint32_t(__ldg(P.index_linear + size_t(py) * QW + px).x);
     int2 off = IndexToOffset(index);
     int cx = px * 2 + off.x, cy = py * 2 + off.y;
-    float2 uv = f2((float(cx) + 0.5f) / float(HW_), (float(cy) + 0.5f) / float(HH));
+    S.uv = f2((float(cx) + 0.5f) / float(HW_), (float(cy) + 0.5f) / float(HH));
     float depth = checker_clamped(P, cx, cy);
     float3 camera = f3(c.uCameraPos);
-    float3 sun = f3(c.uSunDirection);
-    float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
-    float3 view_dir = normalize(frag_pos - camera);
+    float3 frag_pos = projective_mul(c.uInvMVP, f3(S.uv.x * 2.0f - 1.0f, S.uv.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
+    S.view_dir = normalize(frag_pos - camera);
 
     float r = c.uCameraPos[2] + c.uEarthRadius;
-    float mu = view_dir.z;
+    float mu = S.view_dir.z;
+    S.r = r; S.mu = mu;
     // RayShellIntersect, :39-71
     float i0t1 = 0.0f, i0t2 = 0.0f, i1t1 = 0.0f, i1t2 = 0.0f;
     {
@@ -397,15 +405,97 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
             }
         }
     }
-    float frag_dist = distance(frag_pos, camera);
-    float limit = fminf(frag_dist, b.uMaxVisibleDistance);
+    S.frag_dist = distance(frag_pos, camera);
+    float limit = fminf(S.frag_dist, b.uMaxVisibleDistance);
     i0t2 = fminf(fmaxf(limit, i0t1), i0t2);  // clamp(x, minVal, maxVal) = min(max(x, minVal), maxVal)
     i1t2 = fminf(fmaxf(limit, i1t1), i1t2);
+    S.i0t1 = i0t1; S.i0t2 = i0t2; S.i1t1 = i1t1; S.i1t2 = i1t2;
+    S.cos_sun_view = dot(f3(c.uSunDirection), S.view_dir);
+    float noise = blue_noise_at(P.blue_noise, px, py);
+    S.jitter = fractf(noise + c.uFrameID * 0.61803398875f);
+    return S;
+}
 
+// VolumetricCloudRender.comp:189-209: what main() does with the marched context, and the stores (local, or every rank's copy
+// over NVLink when the frame is tile-sharded)
+SKY_D void k16_ray_finish(const CloudParams& P, const RaySetup& S, RayMarchContext& ctx) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const SkyCloudBufferData& b = P.b;
+    const int QW = P.width / 4;
+    const float3 camera = f3(c.uCameraPos), sun = f3(c.uSunDirection);
+    float average_t = ctx.weighted_t_sum == 0 ? S.frag_dist : ctx.weighted_t_sum / ctx.transmittance_sum;
+    float3 average_pos = camera + S.view_dir * average_t;
+    // GetSunVisibility(pos), VolumetricCloudCommon.glsl:73-79
+    float3 up_dir = f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius);
+    float up_len = length(up_dir);
+    up_dir /= up_len;
+    float mu_s = dot(sun, up_dir);
+    float3 sun_visibility = P.atm.GetSunVisibility(P.transmittance, up_len, mu_s);
+    float sun_cos_theta = clampf(dot(normalize(f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius)), sun), 0.0f, 1.0f);  // SunCosTheta :85-88
+    float3 luminance = ctx.sun_env.x * b.uSunIlluminanceScale * sun_visibility * P.atm.solar_illuminance() +
+                       ctx.sun_env.y * powf(sun_cos_theta, b.uEnvSunHeightCurveExp) * f3(b.uEnvColorScale);
+    // GetAerialPerspective, VolumetricCloudCommon.glsl:81-97
+    float ap_t = average_t;
+    if (S.r > P.atm.u.top_radius) {
+        float near_distance;
+        if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(S.r, S.mu, near_distance)) ap_t -= near_distance;
+        else ap_t = 0;
+    }
+    float3 uvw = aerial_perspective_uvw(S.uv, ap_t, c.uAerialPerspectiveLutMaxDistance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
+    float3 atmosphere_transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
+    float3 atmosphere_luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
+    atmosphere_luminance *= SampleRayScatterVisibility(P.froxel, S.uv, average_t, c.uInvShadowFroxelMaxDistance);
+    luminance = luminance * atmosphere_transmittance + atmosphere_luminance * (1 - ctx.transmittance);
+
+    luminance /= fmaxf(1e-5f, (1 - ctx.transmittance));
+    float fade = smoothstepf(b.uMaxVisibleDistance * 0.75f, b.uMaxVisibleDistance, S.i0t1);
+    ctx.transmittance = mixf(ctx.transmittance, 1.0f, fade);
+    luminance *= 1 - ctx.transmittance;
+    const half4 texel = to_half4(f4(luminance, ctx.transmittance));
+    const size_t at = size_t(S.py) * QW + S.px;
+    if (P.peer_count == 0) {
+        P.render[at] = texel;
+        P.cloud_distance[at] = average_t;
+    } else {
+        // the exchange step of a tile-sharded frame, fused into the producer: plain stores to every rank's
+        // copy over NVLink (12 B per ray and rank); k_peer_arrive_and_wait orders them before K17
+#pragma unroll 1
+        for (int k = 0; k < P.peer_count; ++k) {
+            P.peer_render[k][at] = texel;
+            P.peer_distance[k][at] = average_t;
+        }
+    }
+}
+
+// The tail of RayMarchStep (:120-136) once the shadow march of the step is known
+SKY_D void ShadeDenseStepTail(const CloudParams& P, RayMarchContext& ctx, float sigma_t, float transmittance_to_sun) {
+    float tr = expf(-ctx.step_size * sigma_t);
+    float phase = mixf(HenyeyGreenstein(ctx.cos_sun_view, -0.15f) * 2.16f, HenyeyGreenstein(ctx.cos_sun_view, 0.85f),
+                       expf(-P.b.uSunMultiscatteringSigmaScale * sigma_t));
+    float2 sun_env;
+    sun_env.x = transmittance_to_sun * phase;
+    sun_env.y = mixf(P.b.uEnvBottomVisibility, 1.0f, ctx.height01);
+    sun_env.y = sun_env.y - sun_env.y * expf(-P.b.uEnvMultiscatteringSigmaScale * sigma_t);
+    sun_env = sun_env - sun_env * tr;
+    ctx.sun_env += ctx.transmittance * sun_env;
+    ctx.transmittance_sum += ctx.transmittance;
+    ctx.weighted_t_sum += ctx.t * ctx.transmittance;
+    ctx.transmittance *= tr;
+}
+
+template <int MAT, bool HW, bool COUNT>
+__global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_render(const __grid_constant__ CloudParams P) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const SkyCloudBufferData& b = P.b;
+    const int warp_in_block = int(threadIdx.x >> 5);
+    const RaySetup S = k16_ray_setup(P, blockIdx.x * kK16TileW + (kK16Block >= 64 ? (warp_in_block & 1) * 8 : 0) + int(threadIdx.x & 7u),
+                                     blockIdx.y * kK16TileH + (kK16Block >= 64 ? (warp_in_block >> 1) * 4 : 0) + int((threadIdx.x >> 3) & 3u));
+    const float3 camera = f3(c.uCameraPos);
+    const float3 view_dir = S.view_dir;
     int evals = 0, fetches = 0;
     RayMarchContext ctx;
-    ctx.cos_sun_view = dot(sun, view_dir);
-    float dist = i0t2 - i0t1;
+    ctx.cos_sun_view = S.cos_sun_view;
+    float dist = S.i0t2 - S.i0t1;
     dist = fminf(dist, b.uMaxRaymarchDistance);
     uint32_t num_steps = uint32_t(fmaxf(b.uMaxRaymarchSteps * (dist / b.uMaxRaymarchDistance), 1.0f));
     ctx.step_size = dist / float(num_steps);
@@ -413,15 +503,14 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
     ctx.transmittance_sum = 0.0f;
     ctx.weighted_t_sum = 0.0f;
     ctx.sun_env = f2(0.0f, 0.0f);
-    float noise = blue_noise_at(P.blue_noise, px, py);
-    float jitter = fractf(noise + c.uFrameID * 0.61803398875f);
-    ctx.t = i0t1 + ctx.step_size * jitter;
+    const float jitter = S.jitter;
+    ctx.t = S.i0t1 + ctx.step_size * jitter;
     // The two step loops of :170-188, run as two convergent phases per trip: (A) up to kMarchSteps steps
     // that find no cloud (one SampleSigmaT each), stopping at the first step with cloud in it; (B) the
     // shading of that step (5-tap shadow march + phase functions).  A lane's own sequence of operations is
     // exactly the shader's, but lanes crossing clear air no longer idle through their neighbours' shadow
     // marches, and the shadow marches of a warp run together.
-    float dist1 = i1t2 - i1t1;
+    float dist1 = S.i1t2 - S.i1t1;
     uint32_t cnt = num_steps;
     int segment = 0;
     bool marching = true, dense_pending = false;
@@ -437,7 +526,7 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
                         float d1 = fminf(dist1, b.uMaxRaymarchDistance);
                         cnt = uint32_t(fmaxf(b.uMaxRaymarchSteps * (d1 / b.uMaxRaymarchDistance), 1.0f));
                         ctx.step_size = d1 / float(cnt);
-                        ctx.t = i1t1 + ctx.step_size * jitter;
+                        ctx.t = S.i1t1 + ctx.step_size * jitter;
                     } else {
                         marching = false;
                         break;
@@ -463,55 +552,206 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
             else { cnt--; ctx.t += ctx.step_size; }
         }
     }
-    if (!valid) return;
-    float average_t = ctx.weighted_t_sum == 0 ? frag_dist : ctx.weighted_t_sum / ctx.transmittance_sum;
-    float3 average_pos = camera + view_dir * average_t;
-    // GetSunVisibility(pos), VolumetricCloudCommon.glsl:73-79
-    float3 up_dir = f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius);
-    float up_len = length(up_dir);
-    up_dir /= up_len;
-    float mu_s = dot(sun, up_dir);
-    float3 sun_visibility = P.atm.GetSunVisibility(P.transmittance, up_len, mu_s);
-    float sun_cos_theta = clampf(dot(normalize(f3(average_pos.x, average_pos.y, average_pos.z + c.uEarthRadius)), sun), 0.0f, 1.0f);  // SunCosTheta :85-88
-    float3 luminance = ctx.sun_env.x * b.uSunIlluminanceScale * sun_visibility * P.atm.solar_illuminance() +
-                       ctx.sun_env.y * powf(sun_cos_theta, b.uEnvSunHeightCurveExp) * f3(b.uEnvColorScale);
-    // GetAerialPerspective, VolumetricCloudCommon.glsl:81-97
-    float ap_t = average_t;
-    if (r > P.atm.u.top_radius) {
-        float near_distance;
-        if (P.atm.FromSpaceIntersectTopAtmosphereBoundary(r, mu, near_distance)) ap_t -= near_distance;
-        else ap_t = 0;
-    }
-    float3 uvw = aerial_perspective_uvw(uv, ap_t, c.uAerialPerspectiveLutMaxDistance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
-    float3 atmosphere_transmittance = xyz(sample_lut3d(P.ap_trans, uvw.x, uvw.y, uvw.z));
-    float3 atmosphere_luminance = xyz(sample_lut3d(P.ap_lum, uvw.x, uvw.y, uvw.z));
-    atmosphere_luminance *= SampleRayScatterVisibility(P.froxel, uv, average_t, c.uInvShadowFroxelMaxDistance);
-    luminance = luminance * atmosphere_transmittance + atmosphere_luminance * (1 - ctx.transmittance);
-
-    luminance /= fmaxf(1e-5f, (1 - ctx.transmittance));
-    float fade = smoothstepf(b.uMaxVisibleDistance * 0.75f, b.uMaxVisibleDistance, i0t1);
-    ctx.transmittance = mixf(ctx.transmittance, 1.0f, fade);
-    luminance *= 1 - ctx.transmittance;
-    const half4 texel = to_half4(f4(luminance, ctx.transmittance));
-    const size_t at = size_t(py) * QW + px;
-    if (P.peer_count == 0) {
-        P.render[at] = texel;
-        P.cloud_distance[at] = average_t;
-    } else {
-        // the exchange step of a tile-sharded frame, fused into the producer: plain stores to every rank's
-        // copy over NVLink (12 B per ray and rank); k_peer_arrive_and_wait orders them before K17
-#pragma unroll 1
-        for (int k = 0; k < P.peer_count; ++k) {
-            P.peer_render[k][at] = texel;
-            P.peer_distance[k][at] = average_t;
-        }
-    }
-
+    if (!S.valid) return;
+    k16_ray_finish(P, S, ctx);
     if (COUNT) {  // counting variant is never the timed one
         atomicAdd(P.counters + SKY_CNT_RENDER_SIGMA_EVALS, (unsigned long long)evals);
         atomicAdd(P.counters + SKY_CNT_RENDER_TEX_FETCHES, (unsigned long long)fetches);
     }
 }
+
+#ifndef SKY_STRICT_TU
+// ---- K16, ray-group wavefront (the production kernel) --------------------------------------------------------------------
+// What bounds k16_render (one lane = one ray) is not a throughput but the LENGTH of a ray: a ray through thin cloud is up to 143
+// steps, every step with cloud in it is 6 serial SampleSigmaT evaluations (the step + 5 shadow taps), and every evaluation is two
+// dependent texture round trips: ~10^6 cycles of pure latency for one ray, i.e. the whole kernel time (measured: K14-K16 308 us at
+// 1920x1080 against 433 us at 3840x2160 -- four times the rays, 1.4x the time; occupancy 5 -> 8 blocks/SM and 2..5 evaluations
+// in flight per lane change nothing, profiles/k16_variants_r02d.log).  But within a ray only the running transmittance product
+// and the sums it weights are sequential: sigma_t, the shadow march and the phase terms of a step depend on the step's position
+// alone.  So here a warp works on a GROUP of 8 of its 32 rays at a time (the 8 lowest-numbered ones still marching), and its 32 lanes
+// evaluate (group ray, look-ahead step) pairs side by side:
+//   stage 1: the A <= 8 group rays x K = min(32 / A, kK16LookAhead) next steps of their segment -- one SampleSigmaT per lane;
+//   stage 2: the D steps that found cloud x the shadow taps (tap-major, neighbouring lanes = neighbouring rays), dealt to all 32
+//            lanes in ceil(D taps / 32) passes; each step's lane then adds its taps in the shader's order and forms the step-local
+//            terms exp(-step sigma_t), sun / environment in-scatter of RayMarchStep (:120-133);
+//   stage 3: each group ray's own lane consumes its K steps IN ORDER exactly like the shader's loop body (:134-137, :170-188): running
+//            transmittance, sums, the `break` at kMinTransmittance (steps evaluated past it are discarded: the only speculation,
+//            at most K - 1 steps once per segment), step count and t.
+// A ray's operations are the shader's in the shader's order; only the look-ahead positions are formed as t + k * step with one FMA.
+// The critical path of a ray drops from 12 texture round trips per step to <= 3, and lanes are full while rays of a group remain.
+// The strict objects and the counting variant keep k16_render, whose lanes follow the shader's loop literally.
+#ifndef SKY_K16_LOOKAHEAD
+#define SKY_K16_LOOKAHEAD 8
+#endif
+constexpr int kK16MaxTaps = 8, kK16LookAhead = SKY_K16_LOOKAHEAD, kK16GroupRays = 8;
+struct K16WaveScratch {
+    float4 dir[kK16GroupRays];                 // group ray: view_dir.xyz, back lobe
+    float4 state[kK16GroupRays];               // group ray: t, step_size, steps evaluated this round (uint bits), forward lobe
+    float4 out[kK16GroupRays][kK16LookAhead];  // per group ray and look-ahead step: (tr, sun, env, state); state 0 clear, 1 cloud
+    float4 pos[32];                            // steps with cloud in them, by rank: position
+    float res[32 * kK16MaxTaps];               // optical-depth terms of the shadow taps [tap * D + rank]
+};
+
+// number of taps SampleShadow's float loop (:103) makes, and their (mid point, delta_t)
+inline int k16_shadow_taps(float shadow_steps, float* mid, float* weight, int cap) {
+    float inv_shadow_steps = 1.0f / shadow_steps, previous_t = 0.0f;
+    int n = 0;
+    for (float t = inv_shadow_steps; t <= 1.0f && n < 4096; t += inv_shadow_steps) {
+        float current_t = t * t;
+        float delta_t = current_t - previous_t;
+        if (n < cap) { mid[n] = previous_t + 0.5f * delta_t; weight[n] = delta_t; }
+        ++n;
+        previous_t = current_t;
+    }
+    return n;
+}
+struct K16Taps {
+    int count;
+    float mid[kK16MaxTaps], weight[kK16MaxTaps];
+};
+
+template <int MAT, bool HW>
+__global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_render_wave(const __grid_constant__ CloudParams P, const __grid_constant__ K16Taps taps) {
+    const SkyCloudCommonBufferData& c = P.c;
+    const SkyCloudBufferData& b = P.b;
+    __shared__ K16WaveScratch scratch[kK16Block / 32];
+    __shared__ float tap_mid[kK16MaxTaps], tap_weight[kK16MaxTaps];   // indexed per lane: shared memory, not the constant bank
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    K16WaveScratch& W = scratch[threadIdx.x >> 5];
+    const int n_taps = taps.count;
+    if (threadIdx.x < unsigned(kK16MaxTaps)) { tap_mid[threadIdx.x] = taps.mid[threadIdx.x]; tap_weight[threadIdx.x] = taps.weight[threadIdx.x]; }
+    __syncthreads();
+    const float3 camera = f3(c.uCameraPos);
+    const float3 sample_vector = b.uShadowDistance * f3(c.uSunDirection);
+
+    // ---- every lane sets up one ray (the warp's 8x4 tile, like k16_render); at any time the 8 lowest-numbered rays still marching
+    //      form the group the warp works on
+    const int warp_in_block = int(threadIdx.x >> 5);
+    const RaySetup S = k16_ray_setup(P, blockIdx.x * kK16TileW + (kK16Block >= 64 ? (warp_in_block & 1) * 8 : 0) + int(threadIdx.x & 7u),
+                                     blockIdx.y * kK16TileH + (kK16Block >= 64 ? (warp_in_block >> 1) * 4 : 0) + int((threadIdx.x >> 3) & 3u));
+    RayMarchContext ctx;
+    ctx.cos_sun_view = S.cos_sun_view;
+    float dist = S.i0t2 - S.i0t1;
+    dist = fminf(dist, b.uMaxRaymarchDistance);
+    uint32_t cnt = uint32_t(fmaxf(b.uMaxRaymarchSteps * (dist / b.uMaxRaymarchDistance), 1.0f));
+    ctx.step_size = dist / float(cnt);
+    ctx.transmittance = 1.0f;
+    ctx.transmittance_sum = 0.0f;
+    ctx.weighted_t_sum = 0.0f;
+    ctx.sun_env = f2(0.0f, 0.0f);
+    ctx.t = S.i0t1 + ctx.step_size * S.jitter;
+    const float dist1 = S.i1t2 - S.i1t1;
+    int segment = 0;
+    bool marching = S.valid;
+    // the two lobes of :125-127 depend on the ray only
+    const float hg_back = HenyeyGreenstein(ctx.cos_sun_view, -0.15f) * 2.16f, hg_forward = HenyeyGreenstein(ctx.cos_sun_view, 0.85f);
+#pragma unroll 1
+    while (true) {
+        // the segment's `for` ended (count exhausted or `break`): second shell segment (:178-188), or the ray is done
+        if (marching && cnt == 0) {
+            if (segment == 0 && dist1 > 0) {
+                segment = 1;
+                float d1 = fminf(dist1, b.uMaxRaymarchDistance);
+                cnt = uint32_t(fmaxf(b.uMaxRaymarchSteps * (d1 / b.uMaxRaymarchDistance), 1.0f));
+                ctx.step_size = d1 / float(cnt);
+                ctx.t = S.i1t1 + ctx.step_size * S.jitter;
+            } else {
+                marching = false;
+            }
+        }
+        const unsigned amask = __ballot_sync(0xffffffffu, marching);
+        if (amask == 0) break;
+        const int rank = __popc(amask & lt);
+        const bool selected = marching && rank < kK16GroupRays;
+        const int A = min(__popc(amask), kK16GroupRays);
+        const int K = min(32 / A, kK16LookAhead);
+        if (selected) {
+            W.dir[rank] = f4(S.view_dir, hg_back);
+            W.state[rank] = f4(ctx.t, ctx.step_size, __uint_as_float(min(cnt, uint32_t(K))), hg_forward);
+        }
+        __syncwarp();
+        // ---- stage 1: lane -> (group ray j, look-ahead step k), step-major ------------------------------------------------------
+        const int k = __float2int_rd((float(lane) + 0.5f) * (1.0f / float(A)));
+        const int j = int(lane) - k * A;
+        const bool has_task = k < K;
+        float4 rd = f4(0.0f, 0.0f, 0.0f, 0.0f), rs = rd;
+        if (has_task) { rd = W.dir[j]; rs = W.state[j]; }
+        const bool valid = has_task && uint32_t(k) < __float_as_uint(rs.z);
+        float sigma_t = 0.0f, height01 = 0.0f;
+        float3 pos = camera;
+        if (valid) {
+            pos = camera + f3(rd.x, rd.y, rd.z) * fmaf(float(k), rs.y, rs.x);   // UpdateContext, :90-93
+            height01 = CalHeight01(P, pos);
+            sigma_t = SampleSigmaT<MAT, HW>(P.mat, pos, height01);               // :117
+        }
+        const bool cloud = valid && !(sigma_t < 1e-5f);                           // :118-119
+        // ---- stage 2: the shadow marches of the steps with cloud in them (:98-114), all lanes --------------------------------------
+        const unsigned dmask = __ballot_sync(0xffffffffu, cloud);
+        unsigned cloud_rays = 0;                                                  // group rays with cloud in one of their K steps
+        if (dmask != 0) {
+            cloud_rays = __reduce_or_sync(0xffffffffu, cloud ? (1u << j) : 0u);
+            const int D = __popc(dmask);
+            const int d = __popc(dmask & lt);
+            if (cloud) W.pos[d] = f4(pos, 0.0f);
+            __syncwarp();
+            const int total = D * n_taps;
+            const float inv_D = 1.0f / float(D);
+#pragma unroll 1
+            for (int task = int(lane); task < total; task += 32) {
+                const int tap = __float2int_rd((float(task) + 0.5f) * inv_D);
+                const float4 p = W.pos[task - tap * D];
+                const float3 sample_pos = f3(p.x, p.y, p.z) + sample_vector * tap_mid[tap];
+                const float sample_height01 = CalHeight01(P, sample_pos);
+                W.res[task] = SampleSigmaT<MAT, HW>(P.mat, sample_pos, sample_height01) * b.uShadowDistance * tap_weight[tap];
+            }
+            __syncwarp();
+            float4 o = f4(1.0f, 0.0f, 0.0f, valid ? 0.0f : -1.0f);
+            if (cloud) {
+                float optical_depth = 0.0f;
+                for (int tap = 0; tap < n_taps; ++tap) optical_depth += W.res[tap * D + d];   // the shader's order
+                const float transmittance_to_sun = expf(-optical_depth);
+                // the step-local part of RayMarchStep, :120-133
+                const float tr = expf(-rs.y * sigma_t);
+                const float phase = mixf(rd.w, rs.w, expf(-b.uSunMultiscatteringSigmaScale * sigma_t));
+                float2 sun_env;
+                sun_env.x = transmittance_to_sun * phase;
+                sun_env.y = mixf(b.uEnvBottomVisibility, 1.0f, height01);
+                sun_env.y = sun_env.y - sun_env.y * expf(-b.uEnvMultiscatteringSigmaScale * sigma_t);
+                sun_env = sun_env - sun_env * tr;
+                o = f4(tr, sun_env.x, sun_env.y, 1.0f);
+            }
+            if (has_task && ((cloud_rays >> j) & 1u)) W.out[j][k] = o;
+            __syncwarp();
+        }
+        // ---- stage 3: each group ray consumes its steps in order: the loop body of :170-177 / :182-187 ------------------------------
+        if (selected) {
+            const uint32_t n = min(cnt, uint32_t(K));            // steps of this ray that were evaluated
+            if (!((cloud_rays >> rank) & 1u)) {
+                // clear air all the way: the transmittance does not change, so `break` fires after the first step or never
+                if (ctx.transmittance < kMinTransmittance) cnt = 0;
+                else { cnt -= n; ctx.t = fmaf(float(n), ctx.step_size, ctx.t); }
+            } else {
+#pragma unroll 1
+                for (uint32_t kk = 0; kk < n; ++kk) {
+                    const float4 s = W.out[rank][kk];
+                    if (s.w > 0.0f) {                           // :134-137
+                        ctx.sun_env += ctx.transmittance * f2(s.y, s.z);
+                        ctx.transmittance_sum += ctx.transmittance;
+                        ctx.weighted_t_sum += ctx.t * ctx.transmittance;
+                        ctx.transmittance *= s.x;
+                    }
+                    if (ctx.transmittance < kMinTransmittance) { cnt = 0; break; }   // :175 / :186 `break`
+                    cnt--; ctx.t += ctx.step_size;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (!S.valid) return;
+    k16_ray_finish(P, S, ctx);
+}
+#endif  // SKY_STRICT_TU
 
 // ------------------------------------------------------------------------------------------------ K17
 // VolumetricCloudReconstruct.comp:28-110: reproject last frame's half-res image through the cloud
@@ -877,8 +1117,17 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
     }
     dim3 grid(ceil_div(QW, kK16TileW), ceil_div(rows, kK16TileH));
     const bool count = ctx->counting;
+#ifndef SKY_STRICT_TU
+    K16Taps taps{};
+    taps.count = k16_shadow_taps(b.uShadowSteps, taps.mid, taps.weight, kK16MaxTaps);
+    // the ray-group wavefront kernel: production object, not counting, a shadow march it can deal out (1..8 taps)
+    const bool wave = !count && !ctx->k16_literal && taps.count >= 1 && taps.count <= kK16MaxTaps;
+#endif
     int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
         if (count) k16_render<MAT, HW, true><<<grid, kK16Block, 0, ctx->stream>>>(P);
+#ifndef SKY_STRICT_TU
+        else if (wave) k16_render_wave<MAT, HW><<<grid, kK16Block, 0, ctx->stream>>>(P, taps);
+#endif
         else k16_render<MAT, HW, false><<<grid, kK16Block, 0, ctx->stream>>>(P);
         return 0;
     });

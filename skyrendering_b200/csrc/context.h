@@ -61,6 +61,7 @@ struct SkyContext {
     bool hw_filtering = false;
     bool strict_arithmetic = false;  // sky_set_strict_arithmetic: route K6, K11-K18, K19/K20 to the *_strict objects
     bool counting = false;
+    bool k16_literal = false;        // SKYB200_K16_LITERAL=1: the production object launches k16_render (one lane = one ray, the shader's loop) instead of k16_render_coop
     int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: rows K6 / K18 own
 
     // frame overlap (sky_set_frame_overlap): second lane of a frame, see api.cu
