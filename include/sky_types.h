@@ -213,6 +213,18 @@ enum SkyPtTracking {
     SKY_PT_TRACKING_MAJORANT_GRID = 1  /* local majorants on a macro-cell grid: same expectation, different streams */
 };
 
+/* src/SkyRendering/Earth.cpp:12-21, shaders/SkyRendering/EarthRender.frag:6-15: uniforms of the ground pass (160 B) */
+typedef struct SkyEarthBufferData {
+    float view_projection[16];
+    float inv_view_projection[16];
+    float camera_position[3];
+    float camera_earth_center_distance;
+    float earth_center[3];
+    float padding;
+    float up_direction[3];
+    float padding1;
+} SkyEarthBufferData;
+
 /* HDRBufferParams subset used by the tone-map pass (src/Base/include/HDRBuffer.h:11-22), see sky_tonemap */
 typedef struct SkyToneMapParams {
     int32_t tone_mapping;  /* 0 = CEToneMapping, 1 = ACESToneMapping (default of the reference) */

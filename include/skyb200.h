@@ -81,6 +81,21 @@ int SKY_FN(ibl_precompute)(SkyContext* ctx);
  * pass that would rasterise it are outside the path. */
 int SKY_FN(set_gbuffer)(SkyContext* ctx, const void* albedo_dev, const void* normal_dev, const void* orm_dev);
 
+/* Textures::Textures earth albedo upload (src/Base/src/Textures.cpp:52-58): GL_SRGB8 texels RGB8 [H][W][3], rows in GL order, +
+ * glGenerateTextureMipmap (2x2 box on the decoded values, re-encoded to sRGB8, floor sizes).  An equirectangular map: u = longitude,
+ * v = latitude (EarthRender.frag:22-26).  width or height 0 removes it (the ground pass then writes albedo 0). */
+int SKY_FN(set_earth_albedo)(SkyContext* ctx, const uint8_t* host_srgb8, int width, int height);
+
+/* Earth::RenderToGBuffer (src/SkyRendering/Earth.cpp:46-65, shaders/SkyRendering/EarthRender.frag, K7): the analytic ground pass.  For every pixel
+ * whose view ray meets the ground sphere in front of what the depth buffer already holds it writes gl_FragDepth (quantised to
+ * the D24 of GBuffer.cpp:22) and the three G-buffer targets in the formats of GBuffer.cpp:19-21 -- albedo GL_RGBA8 from the earth
+ * map through textureGrad with the seamless-longitude gradients of :27-35 (sampler of Earth.cpp:34-42; include/sky_texgrad.h),
+ * normal GL_RGBA16_SNORM = the sphere normal, ORM GL_RGBA16 = (1, 1, 0, 1); every other pixel is left untouched (`discard`).
+ * depth_dev float[H][W] is read and written; needs sky_atmosphere_bake (bottom_radius).  The G-buffer it fills is what
+ * sky_set_gbuffer binds for the composite. */
+int SKY_FN(earth_gbuffer)(SkyContext* ctx, const SkyEarthBufferData* earth, float* depth_dev, void* albedo_dev, void* normal_dev,
+                          void* orm_dev, int width, int height);
+
 /* AtmosphereRenderer::Render full-screen pass (AtmosphereRenderer.cpp:246-250, K6), sky / aerial
  * perspective / sun-disc branches.  depth_dev: float[H][W] in [0,1]; hdr_dev: half4[H][W] (written).
  * Object pixels (depth != 1): with a G-buffer bound (sky_set_gbuffer; needs sky_env_brdf_lut and sky_ibl_precompute) they are

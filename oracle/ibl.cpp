@@ -1,12 +1,15 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see glsl.h and ibl.h).
 #include "ibl.h"
 
+#include "../include/sky_cubemap.h"
+
 #include <cmath>
 
 namespace orc {
 
-// GL 4.6 table 8.19 (cube-map face selection) + section 8.14.2 (bilinear), clamped at the face edge -- the convention the
-// path tracer's environment lookup already uses (pathtrace.cpp, SampleEnvironment).
+// GL 4.6 table 8.19 (cube-map face selection) + section 8.14.2 (bilinear) with SEAMLESS filtering (section 8.14.1; the reference
+// enables GL_TEXTURE_CUBE_MAP_SEAMLESS, AtmosphereRenderer.cpp:151): taps off the face come from the adjacent face
+// (include/sky_cubemap.h, shared with the kernels and the reference-shader shim).
 vec4 TextureCubeLevel(const Image<4>& env, vec3 dir) {
     float ax = std::fabs(dir.x), ay = std::fabs(dir.y), az = std::fabs(dir.z);
     int face; float sc, tc, ma;
@@ -19,8 +22,7 @@ vec4 TextureCubeLevel(const Image<4>& env, vec3 dir) {
     float fu = std::floor(u), fv = std::floor(v);
     int i0 = int(fu), j0 = int(fv);
     float a = u - fu, b = v - fv;
-    auto L = [&](int i, int j) { return env.load(clamp(i, 0, n - 1), clamp(j, 0, n - 1), face); };
-    return (1.0f - a) * (1.0f - b) * L(i0, j0) + a * (1.0f - b) * L(i0 + 1, j0) + (1.0f - a) * b * L(i0, j0 + 1) + a * b * L(i0 + 1, j0 + 1);
+    return sky_cube_bilinear<vec4>(n, face, i0, j0, a, b, [&](int f, int i, int j) { return env.load(i, j, f); });
 }
 
 vec4 TextureCubeLod(const CubeChain& cube, vec3 dir, float lod) {

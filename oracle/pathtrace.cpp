@@ -6,6 +6,7 @@
 // purpose: Random01 returns then advances; TransmittanceEstimation takes
 // the context BY VALUE so the shadow ray's random numbers are replayed by the next bounce;
 // scattered_t is measured to the segment origin; CloudRegionIntersect divides by zero components.
+#include "../include/sky_cubemap.h"
 #include "cloud.h"
 
 namespace orc {
@@ -130,8 +131,8 @@ struct Tracer {
         return TransmittanceEstimation(ctx, Ray{pos, S.uSunDirection()}) * light_luminance * bsdf_with_cosine / pdf;
     }
     // environment_luminance_texture lookup, :206,215.  The cube is sampled with implicit LOD inside a
-    // compute shader (derivatives undefined): the oracle defines LOD 0 with bilinear filtering inside
-    // the selected face.  Face selection / (s,t) follow the GL cube-map table (spec 8.13).
+    // compute shader (derivatives undefined): the oracle defines LOD 0.  Face selection / (s,t) follow the GL cube-map table
+    // (spec 8.13); bilinear filtering is SEAMLESS (GL 4.6 8.14.1; glEnable(GL_TEXTURE_CUBE_MAP_SEAMLESS), AtmosphereRenderer.cpp:151).
     vec3 SampleEnvironment(vec3 dir) const {
         float ax = std::fabs(dir.x), ay = std::fabs(dir.y), az = std::fabs(dir.z);
         int face; float sc, tc, ma;
@@ -145,8 +146,7 @@ struct Tracer {
         float fu = std::floor(u), fv = std::floor(v);
         int i0 = int(fu), j0 = int(fv);
         float a = u - fu, b = v - fv;
-        auto L = [&](int i, int j) { return env.load(clamp(i, 0, n - 1), clamp(j, 0, n - 1), face).rgb(); };
-        return (1.0f - a) * (1.0f - b) * L(i0, j0) + a * (1.0f - b) * L(i0 + 1, j0) + (1.0f - a) * b * L(i0, j0 + 1) + a * b * L(i0 + 1, j0 + 1);
+        return sky_cube_bilinear<vec3>(n, face, i0, j0, a, b, [&](int f, int i, int j) { return env.load(i, j, f).rgb(); });
     }
 
     vec4 Trace(Context& ctx, vec3 view_dir, bool& has_scattered, float& scattered_t) const {  // :160-249

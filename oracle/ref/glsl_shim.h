@@ -10,6 +10,7 @@
 // exact fp32 filter weights, round-to-nearest-even UNORM / fp16 image stores, minNum / maxNum for min / max / clamp, and
 // -- when REF_MATH_DET is defined, as for the LUT programs -- exp / sin / cos / acos / x^1.5 from include/sky_detmath.h.
 #pragma once
+#include "../../include/sky_cubemap.h"
 #include <algorithm>
 #include <array>
 #include <barrier>
@@ -402,7 +403,8 @@ inline vec4 texelFetch(const Sampler& s, const ivec3& p, int lod) {
 }
 // samplerCube inside a compute shader: implicit derivatives are undefined, so the LOD is the driver's choice.  Convention
 // (same as the oracle and the kernels): level 0, bilinear inside the face the GL cube-map table
-// (spec 8.13) selects, clamped at the face edge.
+// (spec 8.13) selects, with SEAMLESS filtering at the face edges (GL 4.6 8.14.1: the reference calls
+// glEnable(GL_TEXTURE_CUBE_MAP_SEAMLESS), AtmosphereRenderer.cpp:151) -- include/sky_cubemap.h, the rule the oracle and the kernels share.
 inline vec4 textureCubeLevel(const Image& env, const vec3& dir) {
     float ax = std::fabs(dir.x), ay = std::fabs(dir.y), az = std::fabs(dir.z);
     int face; float sc, tc, ma;
@@ -415,8 +417,7 @@ inline vec4 textureCubeLevel(const Image& env, const vec3& dir) {
     float fu = std::floor(u), fv = std::floor(v);
     int i0 = int(fu), j0 = int(fv);
     float a = u - fu, b = v - fv;
-    auto L = [&](int i, int j) { return env.load(clamp(i, 0, n - 1), clamp(j, 0, n - 1), face); };
-    return (1.0f - a) * (1.0f - b) * L(i0, j0) + a * (1.0f - b) * L(i0 + 1, j0) + (1.0f - a) * b * L(i0, j0 + 1) + a * b * L(i0 + 1, j0 + 1);
+    return sky_cube_bilinear<vec4>(n, face, i0, j0, a, b, [&](int f, int i, int j) { return env.load(i, j, f); });
 }
 inline vec4 texture(const samplerCube& s, const vec3& dir) { return textureCubeLevel(s.levels[0], dir); }
 // textureLod on a cube with a LINEAR_MIPMAP_LINEAR sampler (Samplers::GetAnisotropySampler, src/Base/src/Samplers.cpp:33-41; an

@@ -581,7 +581,13 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
 // The critical path of a ray drops from 12 texture round trips per step to <= 3, and lanes are full while rays of a group remain.
 // The strict objects and the counting variant keep k16_render, whose lanes follow the shader's loop literally.
 #ifndef SKY_K16_LOOKAHEAD
-#define SKY_K16_LOOKAHEAD 8
+#define SKY_K16_LOOKAHEAD 4   // measured at 4K, scene c3, hardware filtering: 2 -> 585 us, 4 -> 408 us, 8 -> 436 us (8 blocks / SM)
+#endif
+#ifndef SKY_K16_WAVE_RAYS
+#define SKY_K16_WAVE_RAYS 8   // rays a warp owns: 8 (one group) or 32 (four groups, worked on one after the other)
+#endif
+#ifndef SKY_K16_WAVE_OCC
+#define SKY_K16_WAVE_OCC 8    // resident 128-thread blocks per SM: 5 -> 480 us, 8 -> 408 us (64 registers, 20 bytes of spill)
 #endif
 constexpr int kK16MaxTaps = 8, kK16LookAhead = SKY_K16_LOOKAHEAD, kK16GroupRays = 8;
 struct K16WaveScratch {
@@ -611,7 +617,7 @@ struct K16Taps {
 };
 
 template <int MAT, bool HW>
-__global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_render_wave(const __grid_constant__ CloudParams P, const __grid_constant__ K16Taps taps) {
+__global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block) k16_render_wave(const __grid_constant__ CloudParams P, const __grid_constant__ K16Taps taps) {
     const SkyCloudCommonBufferData& c = P.c;
     const SkyCloudBufferData& b = P.b;
     __shared__ K16WaveScratch scratch[kK16Block / 32];
@@ -625,11 +631,18 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
     const float3 camera = f3(c.uCameraPos);
     const float3 sample_vector = b.uShadowDistance * f3(c.uSunDirection);
 
+    const int warp_in_block = int(threadIdx.x >> 5);
+#if SKY_K16_WAVE_RAYS == 32
     // ---- every lane sets up one ray (the warp's 8x4 tile, like k16_render); at any time the 8 lowest-numbered rays still marching
     //      form the group the warp works on
-    const int warp_in_block = int(threadIdx.x >> 5);
     const RaySetup S = k16_ray_setup(P, blockIdx.x * kK16TileW + (kK16Block >= 64 ? (warp_in_block & 1) * 8 : 0) + int(threadIdx.x & 7u),
                                      blockIdx.y * kK16TileH + (kK16Block >= 64 ? (warp_in_block >> 1) * 4 : 0) + int((threadIdx.x >> 3) & 3u));
+#else
+    // ---- a warp owns ONE group: 8 rays (a row of 8 quarter-res texels, the block's warps are consecutive rows), held by lanes 0..7.
+    //      What a warp does one after the other is what decides the kernel's critical path, so it is one group, not four.
+    RaySetup S{};
+    if (lane < unsigned(kK16GroupRays)) S = k16_ray_setup(P, int(blockIdx.x) * kK16GroupRays + int(lane), int(blockIdx.y) * (kK16Block / 32) + warp_in_block);
+#endif
     RayMarchContext ctx;
     ctx.cos_sun_view = S.cos_sun_view;
     float dist = S.i0t2 - S.i0t1;
@@ -1122,11 +1135,12 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
     taps.count = k16_shadow_taps(b.uShadowSteps, taps.mid, taps.weight, kK16MaxTaps);
     // the ray-group wavefront kernel: production object, not counting, a shadow march it can deal out (1..8 taps)
     const bool wave = !count && !ctx->k16_literal && taps.count >= 1 && taps.count <= kK16MaxTaps;
+    const dim3 wave_grid = SKY_K16_WAVE_RAYS == 32 ? grid : dim3(ceil_div(QW, kK16GroupRays), ceil_div(rows, kK16Block / 32));
 #endif
     int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
         if (count) k16_render<MAT, HW, true><<<grid, kK16Block, 0, ctx->stream>>>(P);
 #ifndef SKY_STRICT_TU
-        else if (wave) k16_render_wave<MAT, HW><<<grid, kK16Block, 0, ctx->stream>>>(P, taps);
+        else if (wave) k16_render_wave<MAT, HW><<<wave_grid, kK16Block, 0, ctx->stream>>>(P, taps);
 #endif
         else k16_render<MAT, HW, false><<<grid, kK16Block, 0, ctx->stream>>>(P);
         return 0;

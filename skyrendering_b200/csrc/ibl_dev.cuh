@@ -1,7 +1,9 @@
 // Cube-map sampling shared by the IBL kernels (ibl.cu) and the object branch of the composite (atmosphere.cu, K6).
-// Conventions of oracle/ibl.h: GL 4.6 table 8.19 face selection, bilinear inside the face clamped at its edge,
+// Conventions of oracle/ibl.h: GL 4.6 table 8.19 face selection, SEAMLESS bilinear filtering (section 8.14.1; the reference enables
+// GL_TEXTURE_CUBE_MAP_SEAMLESS, AtmosphereRenderer.cpp:151: taps off a face come from the adjacent face, include/sky_cubemap.h),
 // LINEAR_MIPMAP_LINEAR blend t0 * (1 - f) + t1 * f with the exact fp32 fraction of the clamped LOD.
 #pragma once
+#include "../../include/sky_cubemap.h"
 #include "common.cuh"
 
 namespace {
@@ -12,7 +14,7 @@ struct CubeChainView {
     int levels;
 };
 
-// GL 4.6 table 8.19 face selection + bilinear inside the face, clamped at its edge (oracle/ibl.cpp TextureCubeLevel)
+// GL 4.6 table 8.19 face selection + seamless bilinear filtering (oracle/ibl.cpp TextureCubeLevel)
 SKY_D float4 TextureCubeLevel(const half4* lvl, int n, float3 dir) {
     float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
     int face; float sc, tc, ma;
@@ -24,10 +26,7 @@ SKY_D float4 TextureCubeLevel(const half4* lvl, int n, float3 dir) {
     float fu = floorf(u), fv = floorf(v);
     int i0 = int(fu), j0 = int(fv);
     float a = u - fu, b = v - fv;
-    const half4* f = lvl + size_t(face) * n * n;
-    int x0 = clampi(i0, 0, n - 1), x1 = clampi(i0 + 1, 0, n - 1), y0 = clampi(j0, 0, n - 1), y1 = clampi(j0 + 1, 0, n - 1);
-    float4 t00 = load_half4(f + y0 * n + x0), t10 = load_half4(f + y0 * n + x1), t01 = load_half4(f + y1 * n + x0), t11 = load_half4(f + y1 * n + x1);
-    return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+    return sky_cube_bilinear<float4>(n, face, i0, j0, a, b, [&](int f, int i, int j) { return load_half4(lvl + (size_t(f) * n + j) * n + i); });
 }
 
 // textureLod(samplerCube, dir, lod), LINEAR_MIPMAP_LINEAR (oracle/ibl.cpp TextureCubeLod)

@@ -25,6 +25,7 @@
 #define launch_pt_resolve launch_pt_resolve_strict
 #define SKY_K19_PRECISE_LOG
 #endif
+#include "../../include/sky_cubemap.h"
 #include "atmosphere_dev.cuh"
 #include "context.h"
 #include "material_dev.cuh"
@@ -151,9 +152,8 @@ SKY_D float3 SampleEnvironment(const PtParams& P, float3 dir) {
     float fu = floorf(u), fv = floorf(v);
     int i0 = int(fu), j0 = int(fv);
     float a = u - fu, b = v - fv;
-    const half4* base = P.env + size_t(face) * n * n;
-    auto L = [&](int i, int j) { return xyz(load_half4(base + clampi(j, 0, n - 1) * n + clampi(i, 0, n - 1))); };
-    return (1.0f - a) * (1.0f - b) * L(i0, j0) + a * (1.0f - b) * L(i0 + 1, j0) + (1.0f - a) * b * L(i0, j0 + 1) + a * b * L(i0 + 1, j0 + 1);
+    // seamless filtering at the face edges (GL 4.6 8.14.1; AtmosphereRenderer.cpp:151): include/sky_cubemap.h
+    return sky_cube_bilinear<float3>(n, face, i0, j0, a, b, [&](int f, int i, int j) { return xyz(load_half4(P.env + (size_t(f) * n + j) * n + i)); });
 }
 
 SKY_D float3 GetSunIlluminance(const PtParams& P, float3 pos) {  // :131-133 + VolumetricCloudCommon.glsl:73-79

@@ -161,8 +161,12 @@ def test_voxel_mips_bit_exact_non_power_of_two(libs):
 def test_cloud_chain_parity(libs, scene, move):
     cuda, orc = libs
     w, h = 384, 216
-    g = run_cloud_frames(scene, w, h, cuda, frames=4, device="cuda", move=move, count=True)
+    g = run_cloud_frames(scene, w, h, cuda, frames=4, device="cuda", move=move)     # the production kernels (K16: k16_render_wave)
+    gc = run_cloud_frames(scene, w, h, cuda, frames=4, device="cuda", move=move, count=True)  # last frame: the counting variant (k16_render)
     o = run_cloud_frames(scene, w, h, orc, frames=4, device="cpu", move=move, count=True)
+    g["counters"] = gc["counters"]
+    # both K16 kernels against the oracle, and against each other (they contract FMAs differently: same spread as against the oracle)
+    assert rel_rms(gc["render"], o["render"]) < 1e-2 and rel_rms(gc["render"], g["render"]) < 1e-2
     assert np.array_equal(g["checker"], o["checker"])                       # K14: pure min/max
     assert np.mean(g["index"][..., 0] == o["index"][..., 0]) > 0.999        # K15
     assert rel_rms(g["index"][..., 1], o["index"][..., 1]) < 1e-5
@@ -693,7 +697,8 @@ def test_c3_cloud_frame_1080p_protocol(libs):
     static camera; the final HDR and the K11 / K13 / K16 buffers against the oracle (VolumetricCloudRender.comp:139-210)."""
     cuda, orc = libs
     w, h = 1920, 1080
-    g = run_cloud_frames("c3", w, h, cuda, frames=9, device="cuda", count=True)
+    g = run_cloud_frames("c3", w, h, cuda, frames=9, device="cuda")
+    g["counters"] = run_cloud_frames("c3", w, h, cuda, frames=9, device="cuda", count=True)["counters"]
     o = run_cloud_frames("c3", w, h, orc, frames=9, device="cpu", count=True)
     assert g["render"].shape == (270, 480, 4) and g["froxel"].shape == (128, 90, 160) and g["reconstruct"].shape == (540, 960, 4)
     assert np.array_equal(g["checker"], o["checker"])
@@ -720,7 +725,8 @@ def test_c4_cloud_frame_4k_production_settings(libs, scene):
     Material0 (bin/config3.json), c1 is SURVEY.md 8d's second data point (Material1)."""
     cuda, orc = libs
     w, h = 3840, 2160
-    g = run_cloud_frames(scene, w, h, cuda, frames=3, device="cuda", hw=True, overlap=True, pipelining=True, count=True)
+    g = run_cloud_frames(scene, w, h, cuda, frames=3, device="cuda", hw=True, overlap=True, pipelining=True)
+    g["counters"] = run_cloud_frames(scene, w, h, cuda, frames=3, device="cuda", hw=True, count=True)["counters"]
     o = run_cloud_frames(scene, w, h, orc, frames=3, device="cpu", count=True)
     assert g["render"].shape == (540, 960, 4) and g["froxel"].shape == (128, 180, 320) and g["reconstruct"].shape == (1080, 1920, 4)
     assert np.array_equal(g["checker"], o["checker"])
@@ -728,7 +734,8 @@ def test_c4_cloud_frame_4k_production_settings(libs, scene):
     assert rel_rms(g["render"], o["render"]) < 1e-2
     # cloud distance: not a frame-type buffer -- a ray whose only (vanishing) cloud step flips the 1e-5 density threshold jumps between its
     # mean cloud distance and the fragment distance (1e4 km for sky rays, VolumetricCloudRender.comp:190), so it is compared per texel
-    assert np.mean(np.abs(g["distance"] - o["distance"]) <= 1e-2 * np.abs(o["distance"])) > 0.99
+    rel_d = np.abs(g["distance"] - o["distance"]) / np.abs(o["distance"])
+    assert np.median(rel_d) < 1e-5 and np.mean(rel_d <= 1e-2) > 0.95
     assert rel_rms(g["reconstruct"], o["reconstruct"]) < 1e-2
     assert rel_rms(g["hdr"][..., :3], o["hdr"][..., :3]) < 1e-2
     assert np.all(np.isfinite(g["hdr"])) and np.all(g["hdr"] >= 0)
@@ -796,7 +803,7 @@ def test_full_size_frame_determinism_and_layout(libs):
     """4K with the library defaults (exact filtering, one stream): layout, ranges, work bounds and run-to-run determinism."""
     cuda, _ = libs
     w, h = 3840, 2160
-    a = run_cloud_frames("c3", w, h, cuda, frames=2, device="cuda", count=True)
+    a = run_cloud_frames("c3", w, h, cuda, frames=2, device="cuda", count=True)   # last frame through the counting variant of K16
     assert a["render"].shape == (h // 4, w // 4, 4) and a["reconstruct"].shape == (h // 2, w // 2, 4)
     assert a["froxel"].shape == (128, h // 12, w // 12)
     assert np.all(np.isfinite(a["hdr"])) and np.all(a["hdr"] >= 0)
@@ -804,4 +811,7 @@ def test_full_size_frame_determinism_and_layout(libs):
     rays = (w // 4) * (h // 4)
     assert rays < evals < rays * 6 * 144  # <= (1 + 5 shadow taps) per step, <= 143 steps + second segment
     b = run_cloud_frames("c3", w, h, cuda, frames=2, device="cuda")
-    assert np.array_equal(a["hdr"], b["hdr"])
+    c = run_cloud_frames("c3", w, h, cuda, frames=2, device="cuda")
+    assert np.array_equal(b["hdr"], c["hdr"]) and np.array_equal(b["render"], c["render"])
+    # the counting variant (one lane = one ray, the shader's loop) and the production kernel (ray-group wavefront) render the same image
+    assert rel_rms(a["render"], b["render"]) < 1e-2 and rel_rms(a["hdr"][..., :3], b["hdr"][..., :3]) < 1e-2

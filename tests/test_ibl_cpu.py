@@ -4,6 +4,7 @@
   * always: the oracle against the committed digests of those shader outputs (tests/golden/ibl_digests.json,
     tools/make_ibl_goldens.py) and known-answer tests that need no reference at all."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -162,3 +163,97 @@ def test_pcss_limits():
     lit, dark = frames[(1.0, True)][obj][:, :3], frames[(0.0, True)][obj][:, :3]
     assert np.all(lit >= dark) and (lit > dark).mean() > 0.1   # inside the 8 km light frustum the sun term is gone, the ambient term stays
     assert dark.min() > 0.0
+
+
+# ---- seamless cube-map filtering (include/sky_cubemap.h; GL 4.6 section 8.14.1, AtmosphereRenderer.cpp:151) -----------------------
+@pytest.fixture(scope="module")
+def cubemap_rule(tmp_path_factory):
+    """include/sky_cubemap.h behind a two-function C wrapper (the header is shared by the kernels, the oracle and the shim)."""
+    import ctypes as C
+    import subprocess
+    d = tmp_path_factory.mktemp("cubemap")
+    src = d / "wrap.cpp"
+    src.write_text('#include "%s"\n'
+                   'extern "C" void adj(int n, int* f, int* i, int* j) { sky_cube_adjacent(n, f, i, j); }\n'
+                   'extern "C" float bil(const float* cube, int n, int face, int i0, int j0, float a, float b) {\n'
+                   '    return sky_cube_bilinear<float>(n, face, i0, j0, a, b, [&](int f, int i, int j) { return cube[(f * n + j) * n + i]; }); }\n'
+                   % os.path.join(abi.REPO_ROOT, "include", "sky_cubemap.h"))
+    so = d / "wrap.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so), str(src)])
+    lib = C.CDLL(str(so))
+    lib.bil.restype = C.c_float
+    lib.bil.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+    return lib
+
+
+def _texel_direction(n, f, i, j):
+    sc, tc = (2 * i + 1) / n - 1, (2 * j + 1) / n - 1     # GL 4.6 table 8.19, inverted
+    return np.array({0: (1, -tc, -sc), 1: (-1, -tc, sc), 2: (sc, 1, tc), 3: (sc, -1, -tc), 4: (sc, -tc, 1), 5: (-sc, -tc, -1)}[f], np.float64)
+
+
+def test_seamless_cube_adjacency(cubemap_rule):
+    """A tap one texel off a face edge lands on the texel directly across that edge: on another face, in range, sqrt(2) / n away
+    from the edge texel it left (both sit half a texel from the shared edge at the same position along it), and stepping back
+    across the edge returns to where it came from."""
+    import ctypes as C
+
+    def adj(n, f, i, j):
+        F, I, J = C.c_int(f), C.c_int(i), C.c_int(j)
+        cubemap_rule.adj(n, C.byref(F), C.byref(I), C.byref(J))
+        return F.value, I.value, J.value
+    for n in (1, 2, 4, 16):
+        for f in range(6):
+            for c in range(n):
+                for i, j in ((-1, c), (n, c), (c, -1), (c, n)):
+                    g, ig, jg = adj(n, f, i, j)
+                    assert g != f and 0 <= ig < n and 0 <= jg < n
+                    inside = (min(max(i, 0), n - 1), min(max(j, 0), n - 1))
+                    assert abs(np.linalg.norm(_texel_direction(n, f, *inside) - _texel_direction(n, g, ig, jg)) - np.sqrt(2) / n) < 1e-9
+                    back = [adj(n, g, ig + di, jg + dj) for di, dj in ((-1, 0), (1, 0), (0, -1), (0, 1))
+                            if ((ig + di < 0 or ig + di >= n) != (jg + dj < 0 or jg + dj >= n))]
+                    assert (f,) + inside in back
+
+
+def test_seamless_cube_filtering_is_continuous_across_edges_and_averages_corners(cubemap_rule):
+    """A smooth function of the direction, sampled on both sides of every face edge, filters to the same value on either side
+    (clamping at the edge would not); at a cube corner the missing fourth tap is the mean of the three that exist."""
+    n = 16
+    cube = np.zeros((6, n, n), np.float32)
+    fn = lambda d: 1.0 + 0.3 * d[0] - 0.2 * d[1] + 0.45 * d[2]          # linear in the (unnormalised) cube position
+    for f in range(6):
+        for j in range(n):
+            for i in range(n):
+                cube[f, j, i] = fn(_texel_direction(n, f, i, j))
+    ptr = cube.ctypes.data
+    import ctypes as C
+
+    def adj(f, i, j):
+        F, I, J = C.c_int(f), C.c_int(i), C.c_int(j)
+        cubemap_rule.adj(n, C.byref(F), C.byref(I), C.byref(J))
+        return F.value, I.value, J.value
+    # half-way between an edge texel and the texel across the edge: the mean of the two -- and because the function is smooth over
+    # the fold, that is its value at the edge point between them up to O(1 / n^2); CLAMP_TO_EDGE would return the edge texel itself
+    for f in range(6):
+        for c in range(1, n - 1):
+            for i0, j0, a, b in ((-1, c, 0.5, 0.0), (n - 1, c, 0.5, 0.0), (c, -1, 0.0, 0.5), (c, n - 1, 0.0, 0.5)):
+                got = cubemap_rule.bil(ptr, n, f, i0, j0, a, b)
+                inside = (0 if i0 < 0 else n - 1, j0) if a else (i0, 0 if j0 < 0 else n - 1)
+                outside = (-1 if i0 < 0 else n, j0) if a else (i0, -1 if j0 < 0 else n)
+                g, ig, jg = adj(f, *outside)
+                clamped = float(cube[f, inside[1], inside[0]])
+                assert abs(got - 0.5 * (clamped + float(cube[g, jg, ig]))) < 1e-6
+                edge_point = 0.5 * (_texel_direction(n, f, *inside) + _texel_direction(n, g, ig, jg))
+                assert abs(got - fn(edge_point)) < 1e-6 and abs(got - clamped) > 1e-3
+    # corner: base texel (-1, -1) of face 0 with weights (1/2, 1/2): three existing taps + their mean
+    got = cubemap_rule.bil(ptr, n, 0, -1, -1, 0.5, 0.5)
+    t11 = cube[0, 0, 0]
+    g, i, j = adj(0, 0, -1); t10 = cube[g, j, i]
+    g, i, j = adj(0, -1, 0); t01 = cube[g, j, i]
+    t00 = np.float32(np.float32(np.float32(t11 + t10) + t01) * np.float32(1.0 / 3.0))
+    expect = np.float32(0.25) * t00 + np.float32(0.25) * t10 + np.float32(0.25) * t01 + np.float32(0.25) * t11
+    assert abs(got - float(expect)) < 1e-6
+    # a constant cube filters to the constant everywhere (the spec's requirement on the corner construction)
+    const = np.full((6, n, n), 0.625, np.float32)
+    for f in range(6):
+        for i0, j0 in ((-1, -1), (n - 1, -1), (-1, n - 1), (n - 1, n - 1), (-1, 3), (5, n - 1)):
+            assert abs(cubemap_rule.bil(const.ctypes.data, n, f, i0, j0, 0.3, 0.7) - 0.625) < 1e-6

@@ -21,11 +21,12 @@ def timed(fn, n=7):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return float(np.median(ts)) * 1e3
-w, h = 3840, 2160
-for scene in ("c3", "c1"):
+for (w, h) in [tuple(int(v) for v in size.split("x")) for size in os.environ.get("SIZES", "3840x2160").split(",")]:
+  for scene in ("c3", "c1"):
     for hw in (1, 0):
         r = Renderer(scene, w, h); r.ctx.set_hw_filtering(bool(hw)); r.prime()
         depth = torch.from_numpy(r.scene.ground_depth(w, h)).cuda(); hdr = torch.zeros((h, w, 4), dtype=torch.float16, device="cuda")
         for _ in range(3): r.frame(depth, hdr)
         common, cloud, _ = r.last_uniforms
-        print(name, scene, f"hw={hw} K14-16 {timed(lambda: r.ctx.cloud_frame_begin(common, cloud, depth)):.0f} us", flush=True)
+        band = timed(lambda: r.ctx.cloud_frame_begin(common, cloud, depth, 8, 3, 8))   # what one of 8 ranks renders (interleaved 8-row bands)
+        print(name, scene, f"{w}x{h} hw={hw} K14-16 {timed(lambda: r.ctx.cloud_frame_begin(common, cloud, depth)):.0f} us; band 3 of 8: {band:.0f} us", flush=True)
