@@ -130,6 +130,59 @@ SKY_DM float sky_det_asinf(float x) {
     return x < 0.0f ? -t : t;
 }
 
+/* atan(x), any finite x: argument reduction to |t| < 0.4375 around atan(0.5), atan(1), atan(1.5), atan(inf) and an odd polynomial
+ * of degree 23 (the classic four-interval scheme); atan2(y, x) from it with the usual quadrant fix-up (GetEarthAlbedo,
+ * EarthRender.frag:25; atan2(0, 0) = 0 here, GLSL: undefined). */
+SKY_DM float sky_det_atanf(float x) {
+    const float hi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float lo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    float ax = x < 0.0f ? -x : x;
+    if (!(ax < 6.7108864e7f)) return x != x ? x : (x < 0.0f ? -(hi[3] + lo[3]) : (hi[3] + lo[3]));
+    int id;
+    float t;
+    if (ax < 0.4375f) {
+        if (ax < 2.4414062e-04f) return x;
+        id = -1; t = x;
+    } else if (ax < 1.1875f) {
+        if (ax < 0.6875f) { id = 0; t = (2.0f * ax - 1.0f) / (2.0f + ax); }
+        else { id = 1; t = (ax - 1.0f) / (ax + 1.0f); }
+    } else if (ax < 2.4375f) { id = 2; t = (ax - 1.5f) / (1.0f + 1.5f * ax); }
+    else { id = 3; t = -1.0f / ax; }
+    float z = t * t, w = z * z;
+    float s1 = z * (3.3333334327e-01f + w * (1.4285714924e-01f + w * (9.0908870101e-02f + w * (6.6610731184e-02f + w * (4.9768779427e-02f + w * 1.6285819933e-02f)))));
+    float s2 = w * (-2.0000000298e-01f + w * (-1.1111110449e-01f + w * (-7.6918758452e-02f + w * (-5.8335702866e-02f + w * -3.6531571299e-02f))));
+    if (id < 0) return t - t * (s1 + s2);
+    float r = hi[id] - ((t * (s1 + s2) - lo[id]) - t);
+    return x < 0.0f ? -r : r;
+}
+SKY_DM float sky_det_atan2f(float y, float x) {
+    const float pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f, pio2 = 1.5707963705e+00f;
+    if (x != x || y != y) return x + y;
+    if (y == 0.0f) return x < 0.0f || (x == 0.0f && sky_float_to_bits(x) >> 31) ? (sky_float_to_bits(y) >> 31 ? -pi : pi) : y;
+    if (x == 0.0f) return y < 0.0f ? -pio2 : pio2;
+    float q = y / x;
+    float z = sky_det_atanf(q < 0.0f ? -q : q);   /* [0, pi/2] */
+    if (x > 0.0f) return y < 0.0f ? -z : z;
+    return y < 0.0f ? (z - pi_lo) - pi : pi - (z - pi_lo);
+}
+
+/* log2(x) for positive, finite, normal x (the LOD of sky_texgrad.h): x = m 2^e with m in [sqrt(1/2), sqrt(2)), log(m) from the
+ * classic s = f / (2 + f) series, then e + log(m) / ln 2. */
+SKY_DM float sky_det_log2f(float x) {
+    uint32_t ix = sky_float_to_bits(x);
+    ix += 0x3f800000u - 0x3f3504f3u;                       /* m in [sqrt(1/2), sqrt(2)) */
+    const int e = int(ix >> 23) - 127;
+    const float m = sky_bits_to_float((ix & 0x007fffffu) + 0x3f3504f3u);
+    const float f = m - 1.0f;
+    const float s = f / (2.0f + f);
+    const float z = s * s, w = z * z;
+    const float t1 = w * (0.40000972152f + w * 0.24279078841f);
+    const float t2 = z * (0.66666662693f + w * 0.28498786688f);
+    const float hfsq = 0.5f * f * f;
+    const float lg = f - (hfsq - s * (hfsq + (t2 + t1)));  /* log(m) */
+    return float(e) + lg * 1.4426950216e+00f + lg * 1.9259629891e-08f;
+}
+
 /* x^1.5 for x >= 0 (MiePhaseFunction, Atmosphere.glsl:150): x * sqrt(x) */
 SKY_DM float sky_det_pow15f(float x) { return x * sqrtf(x); }
 

@@ -19,6 +19,8 @@
 
 #include <math.h>
 
+#include "sky_detmath.h"
+
 #ifdef __CUDACC__
 #define SKY_TEXGRAD_FN __host__ __device__ inline
 #else
@@ -58,7 +60,7 @@ SKY_TEXGRAD_FN V sky_texture_grad_2d(int w0, int h0, int levels, float u, float 
     const float rho = Pmax / N;
     const float q = float(levels - 1);
     if (!(rho > 1.0f)) return sky_texgrad_bilinear<V>(w0, h0, 0, u, v, load);   /* lambda <= 0 (also rho == 0 and NaN): magnification */
-    float lambda = log2f(rho);
+    float lambda = sky_det_log2f(rho);   /* deterministic fp32 (include/sky_detmath.h): the same bits on the host and on the device */
     lambda = lambda > q ? q : lambda;
     const float fl = floorf(lambda), frac = lambda - fl;
     const int d1 = int(fl), d2 = d1 + 1 > levels - 1 ? levels - 1 : d1 + 1;

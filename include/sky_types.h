@@ -213,7 +213,7 @@ enum SkyPtTracking {
     SKY_PT_TRACKING_MAJORANT_GRID = 1  /* local majorants on a macro-cell grid: same expectation, different streams */
 };
 
-/* src/SkyRendering/Earth.cpp:12-21, shaders/SkyRendering/EarthRender.frag:6-15: uniforms of the ground pass (160 B) */
+/* src/SkyRendering/Earth.cpp:12-21, shaders/SkyRendering/EarthRender.frag:6-15: uniforms of the ground pass (176 B) */
 typedef struct SkyEarthBufferData {
     float view_projection[16];
     float inv_view_projection[16];
@@ -296,6 +296,9 @@ enum SkyResource {
     SKY_RES_ENV_RADIANCE_SH = 29,     /* float4 [9] Llm, the SH9 coefficients of the environment   src/Base/src/IBL.cpp:12-13,29-34 (K23) */
     SKY_RES_PREFILTERED_RADIANCE = 30,/* half4  5 levels concatenated ([6][128][128], [6][64][64], ... [6][8][8]), level i filtered at
                                          roughness i / 4                                          src/Base/src/IBL.cpp:21-22,35-42 (K24) */
+    SKY_RES_EARTH_ALBEDO = 31,        /* u8x4   GL_SRGB8 codes (RGBX) of the earth albedo map, ALL levels concatenated (level l =
+                                         [max(H >> l, 1)][max(W >> l, 1)]): the upload of sky_set_earth_albedo + glGenerateTextureMipmap
+                                         src/Base/src/Textures.cpp:52-58 */
     SKY_RES_COUNT_
 };
 

@@ -101,8 +101,8 @@ int SKY_FN(earth_gbuffer)(SkyContext* ctx, const SkyEarthBufferData* earth, floa
  * Object pixels (depth != 1): with a G-buffer bound (sky_set_gbuffer; needs sky_env_brdf_lut and sky_ibl_precompute) they are
  * shaded like the reference's (ComputeObjectLuminance + SampleVisibilityFromShadowMap, AtmosphereRenderer.glsl:284-343,
  * 404-410: sun through the transmittance LUT, GGX / Lambert BRDF, SH9 + prefiltered-cube ambient, mesh shadow map x cloud
- * shadow map, with PCSS soft shadows when SkyLutConfig.pcss is set) and alpha = 1; without one they receive the atmosphere in-scatter
- * only and alpha = 0 marks them. */
+ * shadow map, with PCSS soft shadows when SkyLutConfig.pcss is set); without one they receive the atmosphere in-scatter
+ * only -- the reference's result on a cleared G-buffer.  Alpha is 1 in every pixel (AtmosphereRenderer.glsl:431). */
 int SKY_FN(composite)(SkyContext* ctx, const float* depth_dev, void* hdr_dev, int width, int height);
 
 /* DynamicTexture::Generate (VolumetricCloudDefaultMaterial.h:39-49): K8/K9/K10 + mip chain. */

@@ -87,6 +87,9 @@ int skyhost_camera_get(SkyScene* scene, float position[3], float front[3], float
 int skyhost_camera_move(SkyScene* scene, const float delta_position[3], float d_pitch, float d_yaw);
 int skyhost_view_projection(SkyScene* scene, float view_projection[16]);
 
+/* Earth::RenderToGBuffer's uniform block (src/SkyRendering/Earth.cpp:46-53) for the ground pass K7 (sky_earth_gbuffer). */
+int skyhost_earth_buffer(SkyScene* scene, SkyEarthBufferData* out);
+
 /* Synthetic depth input: what the ground pass (shaders/SkyRendering/EarthRender.frag:40-52) writes
  * into the D24 depth buffer, 1.0 elsewhere. */
 int skyhost_ground_depth(SkyScene* scene, float* depth, int width, int height);

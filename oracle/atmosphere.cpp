@@ -358,8 +358,8 @@ vec3 AtmosphereRenderer::ComputeObjectLuminance(vec3 position, vec3 view_directi
 }
 
 // K6 -- AtmosphereRenderer.glsl:345-432.  gl_FragCoord.xy = pixel + 0.5, vTexCoord = that / size.
-// Object pixels (depth != 1) get the in-scatter only and alpha 0: ComputeObjectLuminance
-// (:284-324) needs the G-buffer + IBL chain that SURVEY.md 8f-1 leaves for later.
+// Object pixels (depth != 1) are shaded by ComputeObjectLuminance (:284-324) when a G-buffer is bound; without one they carry the
+// in-scatter alone -- the program's result on a cleared G-buffer.  Alpha is 1 everywhere (:431).
 void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_trans, const Image<4>& ap_lum,
                                    const Image<4>& ap_trans, const Image<1>* shadow_froxel, const float* depth_img,
                                    int width, int height, uint16_t* hdr) const {
@@ -409,15 +409,12 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
             if (shadow_froxel)
                 luminance *= SampleRayScatterVisibility(*shadow_froxel, vTexCoord, marching_distance, u.uInvShadowFroxelMaxDistance);
 
-            float alpha = 1.0f;
             if (intersect_object) {
                 if (object) {  // :404-410
                     float shadow_visibility = SampleVisibilityFromShadowMap(fragment_position);
                     if (ex.moon_shadow)
                         shadow_visibility *= atm.GetVisibilityFromMoonShadow(ex.moon_position - fragment_position, ex.moon_radius, sun_direction());
                     luminance += transmittance * ComputeObjectLuminance(fragment_position, view_direction, shadow_visibility, vTexCoord, width, height);
-                } else {
-                    alpha = 0.0f;
                 }
             } else if (dot(view_direction, sun_direction()) >= std::cos(atm.u.sun_angular_radius)) {
                 vec3 uu(1.0f, 1.0f, 1.0f);
@@ -436,7 +433,7 @@ void AtmosphereRenderer::Composite(const Image<4>& sky_lum, const Image<4>& sky_
             o[0] = float_to_half_bits(luminance.x);
             o[1] = float_to_half_bits(luminance.y);
             o[2] = float_to_half_bits(luminance.z);
-            o[3] = float_to_half_bits(alpha);
+            o[3] = float_to_half_bits(1.0f);   // FragColor = vec4(luminance, 1.0), :431
         }
 }
 

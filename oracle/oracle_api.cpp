@@ -9,12 +9,15 @@
 #include <cstdio>
 #include <string>
 
+#include "../include/sky_detmath.h"
 #include "cloud.h"
+#include "earth.h"
 
 using namespace orc;
 
 struct SkyContext {
     CloudScene scene;
+    EarthAlbedo earth_albedo;       // sky_set_earth_albedo
     std::string error;
     std::vector<uint8_t> scratch;   // packed copies handed out by get_resource
     std::vector<uint64_t> counter_copy;
@@ -92,6 +95,35 @@ int orc_set_star_map(SkyContext* ctx, const uint8_t* srgb8, int width, int heigh
     for (size_t i = 0; i < size_t(width) * height; ++i) {
         for (int k = 0; k < 3; ++k) m.data[i * 4 + k] = decode[srgb8[i * 3 + k]];
         m.data[i * 4 + 3] = 1.0f;
+    }
+    return 0;
+}
+
+int orc_set_earth_albedo(SkyContext* ctx, const uint8_t* srgb8, int width, int height) {
+    BuildEarthAlbedo(srgb8, width, height, ctx->earth_albedo);
+    return 0;
+}
+
+int orc_earth_gbuffer(SkyContext* ctx, const SkyEarthBufferData* earth, float* depth, void* albedo, void* normal, void* orm, int width, int height) {
+    if (!earth || !depth || !albedo || !normal || !orm || width <= 0 || height <= 0) return fail(ctx, "earth_gbuffer: bad arguments");
+    EarthGBuffer(ctx->scene.atm, *earth, ctx->earth_albedo, depth, static_cast<uint8_t*>(albedo), static_cast<int16_t*>(normal), static_cast<uint16_t*>(orm), width, height);
+    return 0;
+}
+
+// Test hook (oracle only, not part of skyb200.h): the deterministic fp32 functions of include/sky_detmath.h on arrays, so that
+// tests/test_earth_cpu.py can check them against double precision.  fn: 0 exp, 1 sin, 2 cos, 3 acos, 4 asin, 5 atan2(x, y), 6 log2
+int orc_detmath(int fn, const float* x, const float* y, float* out, int n) {
+    for (int i = 0; i < n; ++i) {
+        switch (fn) {
+            case 0: out[i] = sky_det_expf(x[i]); break;
+            case 1: out[i] = sky_det_sinf(x[i]); break;
+            case 2: out[i] = sky_det_cosf(x[i]); break;
+            case 3: out[i] = sky_det_acosf(x[i]); break;
+            case 4: out[i] = sky_det_asinf(x[i]); break;
+            case 5: out[i] = sky_det_atan2f(x[i], y[i]); break;
+            case 6: out[i] = sky_det_log2f(x[i]); break;
+            default: return 1;
+        }
     }
     return 0;
 }
@@ -343,6 +375,14 @@ int orc_get_resource(SkyContext* ctx, int resource, SkyResourceDesc* d) {
             for (size_t l = first; l < c.levels.size(); ++l) { pack_half(c.levels[l], one); all.insert(all.end(), one.begin(), one.end()); }
             ctx->scratch.swap(all);
             packed(int(ctx->scratch.size() / 2), 1, 1, 1, SKY_FMT_F16); return 0;  // flat, like the *_MIPS resources
+        }
+        case SKY_RES_EARTH_ALBEDO: {
+            const EarthAlbedo& m = ctx->earth_albedo;
+            if (!m.valid()) return fail(ctx, "no earth albedo map");
+            ctx->scratch.clear();
+            for (const std::vector<uint8_t>& lvl : m.codes)
+                for (size_t i = 0; i < lvl.size(); i += 3) { ctx->scratch.push_back(lvl[i]); ctx->scratch.push_back(lvl[i + 1]); ctx->scratch.push_back(lvl[i + 2]); ctx->scratch.push_back(255); }
+            packed(int(ctx->scratch.size() / 4), 1, 1, 4, SKY_FMT_U8); return 0;
         }
         case SKY_RES_ENV_RADIANCE_SH:
             d->ptr = &s.env_sh[0].x; d->width = 9; d->height = 1; d->depth = 1; d->channels = 4; d->format = SKY_FMT_F32; d->bytes = 9 * 16; return 0;

@@ -13,7 +13,8 @@ are purely syntactic -- no arithmetic is added, removed or reordered:
      `layout(local_size...) in;` lines disappear (the driver passes the local size to ref::dispatch).
   4. parameter qualifiers: `out T x` / `inout T x` -> `T& x`, `in T x` -> `T x`; file-scope `in` / `out` interface
      variables of a fragment shader become thread_local variables (one fragment per thread).
-  5. GLSL array constructors `T[](...)` / `T[n](...)` -> `{...}`; `discard` -> `return`.
+  5. GLSL array constructors `T[](...)` / `T[n](...)` -> `{...}`; `discard` -> `REF_DISCARD` (a macro: `return`, or the helper-invocation flag of a
+     program that takes derivatives).
   6. `imageSize(x)` / `textureSize(x, l)` keep their names (the shim overloads them on the image / sampler type).
   8. GLSL-style array types `T[N] name` (function return types, locals) become std::array<T, N>.
   7. file-scope scalar / vector variables with an initialiser become macros (GLSL initialises them per invocation,
@@ -82,7 +83,7 @@ def rewrite(text):
     # 5. array constructors and discard
     text = re.sub(r"=\s*\w+\s*\[\s*\w*\s*\]\s*\(", "= REF_ARRAY_BEGIN(", text)
     text = convert_array_ctors(text)
-    text = re.sub(r"\bdiscard\s*;", "return;", text)
+    text = re.sub(r"\bdiscard\s*;", "REF_DISCARD;", text)
     # 8. array types written GLSL-style: `T[N] name` (return types, locals) -> std::array<T, N> name
     text = re.sub(r"\b([A-Za-z_]\w*)\s*\[\s*(\d+)\s*\]\s+([A-Za-z_]\w*)", r"std::array<\1, \2> \3", text)
     # 7. file-scope scalars / vectors with initialisers (`const vec3 kCloudAABBMin = vec3(..., uBottomAltitude);`): GLSL

@@ -11,6 +11,7 @@
 // -- when REF_MATH_DET is defined, as for the LUT programs -- exp / sin / cos / acos / x^1.5 from include/sky_detmath.h.
 #pragma once
 #include "../../include/sky_cubemap.h"
+#include "../../include/sky_texgrad.h"
 #include <algorithm>
 #include <array>
 #include <barrier>
@@ -176,7 +177,11 @@ inline float log(float x) { return std::log(x); }
 inline float log2(float x) { return std::log2(x); }
 inline float exp2(float x) { return std::exp2(x); }
 inline float tan(float x) { return std::tan(x); }
+#ifdef REF_ATAN_DET   // the ground pass (prog_earth.cpp): atan from include/sky_detmath.h like the oracle and the kernel
+inline float atan(float y, float x) { return sky_det_atan2f(y, x); }
+#else
 inline float atan(float y, float x) { return std::atan2(y, x); }
+#endif
 inline float abs(float x) { return std::fabs(x); }
 inline int abs(int x) { return x < 0 ? -x : x; }
 inline float floor(float x) { return std::floor(x); }
@@ -437,6 +442,43 @@ inline vec4 textureLod(const samplerCube& s, const vec3& dir, float lod) {
 }
 inline ivec2 textureSize(const sampler2D& s, int lod) { return ivec2(s.levels[lod].w, s.levels[lod].h); }
 inline ivec3 textureSize(const sampler3D& s, int lod) { return ivec3(s.levels[lod].w, s.levels[lod].h, s.levels[lod].d); }
+
+// ---- fragment programs: discard, gl_FragDepth, derivatives, textureGrad -----------------------------------------------------
+// A fragment program runs per 2x2 pixel quad (GL 4.6 section 15.1; helper invocations keep running after `discard` so that
+// their neighbours' derivatives stay defined).  Here the quad is evaluated twice: a RECORD pass, in which the k-th dFdx / dFdy
+// call of each of the four pixels stores its argument, and a REPLAY pass, in which the same call returns the fine difference of
+// the recorded values inside the quad row / column.  Valid while no derivative argument depends on an earlier derivative and the
+// four pixels take the same path to every derivative call -- true for EarthRender.frag, the one user.
+struct QuadState {
+    int mode = 0;       // 0 record, 1 replay
+    int pixel = 0;      // (y & 1) << 1 | (x & 1)
+    int call = 0;
+    bool discarded = false;
+    float frag_depth = 0.0f;
+    std::vector<std::array<float, 4>> values;
+};
+inline thread_local QuadState g_quad;
+#define gl_FragDepth (ref::g_quad.frag_depth)
+#define REF_DISCARD_HELPER do { ref::g_quad.discarded = true; } while (0)
+inline float quad_derivative(float v, int lo, int hi) {
+    QuadState& q = g_quad;
+    const size_t k = size_t(q.call++);
+    if (q.mode == 0) {
+        if (q.values.size() <= k) q.values.resize(k + 1);
+        q.values[k][q.pixel] = v;
+        return 0.0f;
+    }
+    return q.values[k][hi] - q.values[k][lo];
+}
+inline float dFdx(float v) { const int row = g_quad.pixel & 2; return quad_derivative(v, row, row | 1); }
+inline float dFdy(float v) { const int col = g_quad.pixel & 1; return quad_derivative(v, col, col | 2); }
+// textureGrad on a mip-mapped 2-D texture with the anisotropic LINEAR_MIPMAP_LINEAR sampler of Earth.cpp:34-42 (REPEAT in s,
+// CLAMP_TO_EDGE in t): include/sky_texgrad.h, the rule the oracle and the kernel share.  The levels hold decoded (linear) texels.
+inline vec4 textureGrad(const sampler2D& s, const vec2& P, const vec2& dPdx, const vec2& dPdy) {
+    const Image& l0 = s.levels[0];
+    return sky_texture_grad_2d<vec4>(l0.w, l0.h, int(s.levels.size()), P.x, P.y, dPdx.x, dPdx.y, dPdy.x, dPdy.y, 16.0f,
+                                     [&](int l, int i, int j) { return s.levels[l].load(i, j, 0); });
+}
 
 // ---- compute dispatch ------------------------------------------------------------------------------------------
 struct Builtins {

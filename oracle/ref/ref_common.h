@@ -3,6 +3,11 @@
 #include "../../include/sky_types.h"
 #include "glsl_shim.h"
 
+// `discard` of a fragment program (glsl2cpp.py rule 5): end the invocation, unless the program driver says otherwise
+#ifndef REF_DISCARD
+#define REF_DISCARD return
+#endif
+
 // std140 blocks -> the namespace-scope variables glsl2cpp.py makes of the uniform-block members
 #define REF_V3(p) ref::vec3((p)[0], (p)[1], (p)[2])
 #define REF_LOAD_ATMOSPHERE(a)                                                                 \

@@ -129,6 +129,11 @@ class LutConfig(_Pod):
 PT_TRACKING_REFERENCE, PT_TRACKING_MAJORANT_GRID = 0, 1
 
 
+class EarthBufferData(_Pod):  # Earth.cpp:12-21
+    _fields_ = [("view_projection", F * 16), ("inv_view_projection", F * 16), ("camera_position", F * 3),
+                ("camera_earth_center_distance", F), ("earth_center", F * 3), ("padding", F), ("up_direction", F * 3), ("padding1", F)]
+
+
 class ToneMapParams(_Pod):
     _fields_ = [("tone_mapping", I), ("exposure", F), ("dither", I), ("_pad", I)]
 
@@ -154,7 +159,7 @@ ENV_OFF, ENV_CONST_ENVIRONMENT_MAP, ENV_GROUND_SINGLE_BOUNCE, ENV_GROUND_MULTI_B
  RES_SHADOW_MAP, RES_SHADOW_FROXEL, RES_CHECKERBOARD_DEPTH, RES_INDEX_LINEAR_DEPTH, RES_CLOUD_RENDER,
  RES_CLOUD_DISTANCE, RES_RECONSTRUCT, RES_PT_ACCUM, RES_PT_MASK, RES_VOXEL, RES_CLOUD_MAP_MIPS, RES_DETAIL_MIPS,
  RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS, RES_MESH_SHADOW_MAP, RES_ENV_BRDF_LUT, RES_ENVIRONMENT_MIPS,
- RES_ENV_RADIANCE_SH, RES_PREFILTERED_RADIANCE) = range(31)
+ RES_ENV_RADIANCE_SH, RES_PREFILTERED_RADIANCE, RES_EARTH_ALBEDO) = range(32)
 IBL_PREFILTERED_RESOLUTION, IBL_ROUGHNESS_COUNT, ENV_BRDF_LUT_SIZE = 128, 5, 512  # IBL.h:10-11, Textures.cpp:61-62
 FMT_F32, FMT_F16, FMT_U8, FMT_U16, FMT_U64 = range(5)
 _FMT_DTYPE = {FMT_F32: np.float32, FMT_F16: np.float16, FMT_U8: np.uint8, FMT_U16: np.uint16, FMT_U64: np.uint64}
@@ -193,6 +198,8 @@ KERNEL_API = {
     "pt_resolve": ([U, _VOIDP], I),
     "pt_set_tracking": ([I], I),
     "set_star_map": ([_VOIDP, I, I], I),
+    "set_earth_albedo": ([_VOIDP, I, I], I),
+    "earth_gbuffer": ([P(EarthBufferData), _VOIDP, _VOIDP, _VOIDP, _VOIDP, I, I], I),
     "tonemap": ([_VOIDP, I, I, C.POINTER(ToneMapParams), _VOIDP], I),
     "pt_samples_host": ([P(CloudCommonBufferData), U, U, P(I * 4), _VOIDP], I),
     "get_resource": ([I, P(ResourceDesc)], I),
@@ -372,6 +379,32 @@ class Context:
         a = np.ascontiguousarray(srgb8, np.uint8)
         assert a.ndim == 3 and a.shape[2] == 3
         self._call("set_star_map", _ptr(a), a.shape[1], a.shape[0])
+
+    def set_earth_albedo(self, srgb8):
+        """GL_SRGB8 equirectangular earth albedo map, uint8 [H][W][3] in GL row order (None removes it); builds the mip chain."""
+        if srgb8 is None:
+            self._call("set_earth_albedo", None, 0, 0)
+            self._earth_dims = None
+            return
+        a = np.ascontiguousarray(srgb8, np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 3
+        self._call("set_earth_albedo", _ptr(a), a.shape[1], a.shape[0])
+        self._earth_dims = (a.shape[1], a.shape[0])
+
+    def earth_albedo_levels(self):
+        """The GL_SRGB8 codes of every level of the earth albedo map: list of uint8 [h_l][w_l][4] (RGBX)."""
+        flat = self.read(RES_EARTH_ALBEDO).reshape(-1, 4)
+        out, o = [], 0
+        while o < flat.shape[0]:
+            l = len(out)
+            w, h = max(self._earth_dims[0] >> l, 1), max(self._earth_dims[1] >> l, 1)
+            out.append(flat[o:o + w * h].reshape(h, w, 4))
+            o += w * h
+        return out
+
+    def earth_gbuffer(self, earth, depth, albedo, normal, orm, width, height):
+        """K7 (Earth::RenderToGBuffer): depth float32 [H][W] in/out; albedo uint8, normal int16, orm uint16 [H][W][4] written where the ground is hit."""
+        self._call("earth_gbuffer", C.byref(earth), _ptr(depth), _ptr(albedo), _ptr(normal), _ptr(orm), width, height)
 
     def pt_set_tracking(self, mode): self._call("pt_set_tracking", int(mode))
 

@@ -98,6 +98,10 @@ bool resolve(SkyContext* ctx, int resource, ResView& v) {
         case SKY_RES_RECONSTRUCT: v = view_of(ctx->reconstruct[1], 4, SKY_FMT_F16); return true;  // newest after the swap
         case SKY_RES_PT_ACCUM: v = view_of(ctx->pt_accum, 4, SKY_FMT_F32); return true;
         case SKY_RES_PT_MASK: v = view_of(ctx->pt_mask, 1, SKY_FMT_U8); return true;
+        case SKY_RES_EARTH_ALBEDO:
+            if (!ctx->earth_albedo) return true;
+            v.ptr = ctx->earth_albedo; v.w = int(ctx->earth_texels); v.h = 1; v.d = 1; v.ch = 4; v.fmt = SKY_FMT_U8; v.bytes = ctx->earth_texels * 4;
+            return true;
         case SKY_RES_COUNTERS:
             v.ptr = ctx->counters; v.w = 8; v.h = 1; v.d = 1; v.ch = 1; v.fmt = SKY_FMT_U64; v.bytes = 64;
             return true;
@@ -213,6 +217,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
     for (auto& m : ctx->shadow_maps) free_lut(m);
     free_lut(ctx->star_map); if (ctx->srgb_decode) cudaFree(ctx->srgb_decode);
+    if (ctx->earth_albedo) cudaFree(ctx->earth_albedo);
     free_lut(ctx->mesh_shadow_map); free_lut(ctx->shadow_froxel); free_lut(ctx->checkerboard_depth); free_lut(ctx->cloud_distance);
     free_lut(ctx->index_linear_depth); free_lut(ctx->render_texture); free_lut(ctx->reconstruct[0]); free_lut(ctx->reconstruct[1]);
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
@@ -352,21 +357,81 @@ int sky_set_blue_noise(SkyContext* ctx, const uint16_t* texels) {
     return 0;
 }
 
+// GL 4.6 section 8.24: sRGB -> linear, applied to each texel before filtering
+static int ensure_srgb_decode(SkyContext* ctx) {
+    if (ctx->srgb_decode) return 0;
+    float decode[256];
+    for (int c = 0; c < 256; ++c) {
+        double cs = c / 255.0;
+        decode[c] = float(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
+    }
+    SKY_CUDA(ctx, cudaMalloc(&ctx->srgb_decode, sizeof(decode)));
+    SKY_CUDA(ctx, cudaMemcpy(ctx->srgb_decode, decode, sizeof(decode), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int sky_set_earth_albedo(SkyContext* ctx, const uint8_t* host_srgb8, int width, int height) {
+    if (int e = lanes_join(ctx)) return e;
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->earth_albedo) { cudaFree(ctx->earth_albedo); ctx->earth_albedo = nullptr; }
+    ctx->earth_w = ctx->earth_h = ctx->earth_levels = 0; ctx->earth_texels = 0;
+    if (width <= 0 || height <= 0 || !host_srgb8) return 0;
+    if (width > 16384 || height > 16384) return sky_fail(ctx, "earth albedo map too large");
+    if (int e = ensure_srgb_decode(ctx)) return e;
+    // sRGB transfer function (GL 4.6 section 17.3.7), rounded to the nearest code: monotonic, so "the code of v" is the number of
+    // thresholds <= v.  thr[c] = the smallest fp32 value whose code is >= c, found by bisection on the bit pattern.
+    auto code_of = [](float cl) {
+        double c = cl;
+        double cs = !(c > 0.0) ? 0.0 : c < 0.0031308 ? 12.92 * c : c < 1.0 ? 1.055 * std::pow(c, 0.41666) - 0.055 : 1.0;
+        return int(std::floor(cs * 255.0 + 0.5));
+    };
+    float thr[256];
+    thr[0] = -INFINITY;
+    for (int c = 1; c < 256; ++c) {
+        uint32_t lo = 0u, hi = 0x3f800000u;  // code_of(bits lo) < c <= code_of(bits hi)
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + (hi - lo) / 2u;
+            float f; std::memcpy(&f, &mid, 4);
+            if (code_of(f) >= c) hi = mid; else lo = mid;
+        }
+        std::memcpy(&thr[c], &hi, 4);
+    }
+    int levels = 1;
+    size_t texels = size_t(width) * height;
+    ctx->earth_off[0] = 0;
+    for (int w = width, h = height; w > 1 || h > 1;) {
+        w = std::max(w / 2, 1); h = std::max(h / 2, 1);
+        ctx->earth_off[levels++] = texels;
+        texels += size_t(w) * h;
+    }
+    SKY_CUDA(ctx, cudaMalloc(&ctx->earth_albedo, texels * sizeof(uchar4)));
+    ctx->earth_w = width; ctx->earth_h = height; ctx->earth_levels = levels; ctx->earth_texels = texels;
+    std::vector<uchar4> rgbx(size_t(width) * height);
+    for (size_t i = 0; i < rgbx.size(); ++i) rgbx[i] = make_uchar4(host_srgb8[i * 3], host_srgb8[i * 3 + 1], host_srgb8[i * 3 + 2], 255);
+    SKY_CUDA(ctx, cudaMemcpy(ctx->earth_albedo, rgbx.data(), rgbx.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
+    float* thr_dev = nullptr;
+    SKY_CUDA(ctx, cudaMalloc(&thr_dev, sizeof(thr)));
+    SKY_CUDA(ctx, cudaMemcpy(thr_dev, thr, sizeof(thr), cudaMemcpyHostToDevice));
+    int rc = launch_earth_albedo_mips(ctx, thr_dev);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(thr_dev);
+    return rc;
+}
+
+int sky_earth_gbuffer(SkyContext* ctx, const SkyEarthBufferData* earth, float* depth, void* albedo, void* normal, void* orm, int width, int height) {
+    if (!earth || !depth || !albedo || !normal || !orm || width <= 0 || height <= 0) return sky_fail(ctx, "earth_gbuffer: bad arguments");
+    if (!ctx->transmittance.p) return sky_fail(ctx, "earth_gbuffer: the atmosphere has not been baked (bottom_radius)");
+    if (int e = lanes_join(ctx)) return e;  // the depth plane may still be read by a frame in flight on the second lane
+    return launch_earth_gbuffer(ctx, *earth, depth, albedo, normal, orm, width, height);
+}
+
 int sky_set_star_map(SkyContext* ctx, const uint8_t* host_srgb8, int width, int height) {
     if (int e = lanes_join(ctx)) return e;
     SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_lut(ctx->star_map);
     if (width <= 0 || height <= 0 || !host_srgb8) return 0;
     if (width > 16384 || height > 16384) return sky_fail(ctx, "star map too large");
-    if (!ctx->srgb_decode) {
-        float decode[256];  // GL 4.6 section 8.24: sRGB -> linear, applied to each texel before filtering
-        for (int c = 0; c < 256; ++c) {
-            double cs = c / 255.0;
-            decode[c] = float(cs <= 0.04045 ? cs / 12.92 : std::pow((cs + 0.055) / 1.055, 2.4));
-        }
-        SKY_CUDA(ctx, cudaMalloc(&ctx->srgb_decode, sizeof(decode)));
-        SKY_CUDA(ctx, cudaMemcpy(ctx->srgb_decode, decode, sizeof(decode), cudaMemcpyHostToDevice));
-    }
+    if (int e = ensure_srgb_decode(ctx)) return e;
     if (int e = sky_alloc(ctx, ctx->star_map, width, height, 1, false)) return e;
     std::vector<uchar4> rgbx(size_t(width) * height);
     for (size_t i = 0; i < rgbx.size(); ++i) rgbx[i] = make_uchar4(host_srgb8[i * 3], host_srgb8[i * 3 + 1], host_srgb8[i * 3 + 2], 255);

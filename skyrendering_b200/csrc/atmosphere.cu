@@ -837,9 +837,9 @@ SKY_D float3 ComputeObjectLuminance(const RenderParams& P, float3 position, floa
 }
 
 // K6 -- AtmosphereRenderer.glsl:345-432: sky-view LUT / aerial-perspective LUT / per-pixel raymarch,
-// x cloud-shadow froxel, + sun disc with limb darkening.  Object pixels (depth != 1) get the
-// in-scatter only and alpha = 0 (ComputeObjectLuminance needs the G-buffer + IBL chain);
-// the star-map term of sky pixels (:427-429) is in the same "next" row.
+// x cloud-shadow froxel, + sun disc with limb darkening, + the star map on sky pixels (:427-429).  Object pixels (depth != 1) are
+// shaded by ComputeObjectLuminance when a G-buffer is bound (template flag OBJECT); without one they carry the in-scatter alone,
+// which is what the reference's program computes on a cleared (all-zero) G-buffer.  Alpha is 1 everywhere (:431).
 // HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
 template <bool EXTRA, bool OBJECT, bool PCSS_ON = false>
 __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : 3) k6_composite(const __grid_constant__ RenderParams P) {
@@ -888,15 +888,12 @@ __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : 3) k6_composit
     }
     if (P.froxel.p) luminance *= SampleRayScatterVisibility(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);
 
-    float alpha = 1.0f;
     if (intersect_object) {
         if (OBJECT) {  // :404-410
             float shadow_visibility = SampleVisibilityFromShadowMap<PCSS_ON>(P, fragment_position);
             if (EXTRA && P.extras.moon_shadow)
                 shadow_visibility *= GetVisibilityFromMoonShadow(f3(P.extras.moon_position) - fragment_position, P.extras.moon_radius, sun_direction, P.atm.u.sun_angular_radius);
             luminance += transmittance * ComputeObjectLuminance(P, fragment_position, view_direction, shadow_visibility, vTexCoord);
-        } else {
-            alpha = 0.0f;
         }
     } else if (dot(view_direction, sun_direction) >= cosf(P.atm.u.sun_angular_radius)) {
         const float3 a = f3(0.397f, 0.503f, 0.652f);
@@ -924,7 +921,7 @@ __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : 3) k6_composit
         float3 star = (1.0f - a) * (1.0f - b) * texel(i0, j0) + a * (1.0f - b) * texel(i1, j0) + (1.0f - a) * b * texel(i0, j1) + a * b * texel(i1, j1);
         luminance += transmittance * (P.r.star_luminance_scale * star);
     }
-    P.hdr[size_t(py) * P.width + px] = to_half4(f4(luminance, alpha));
+    P.hdr[size_t(py) * P.width + px] = to_half4(f4(luminance, 1.0f));   // FragColor = vec4(luminance, 1.0), :431
 }
 
 RenderParams make_render_params(SkyContext* ctx) {

@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 constexpr int kMaxMipLevels = 13;
+constexpr int kEarthMaxLevels = 15;  // earth albedo map: up to 16384 texels per axis
 constexpr int SKY_PEER_TIMEOUT_SLOT = 16, SKY_PEER_FLAG_SLOTS = 32;  // see k_peer_flags (cloud.cu)  // up to 4096 texels per axis
 
 // A UNORM8 texture with its full mip chain, kept twice: as linear device memory (exact fp32
@@ -138,6 +139,11 @@ struct SkyContext {
     Lut<uint16_t> shadow_froxel;
     Lut<uchar4> star_map;        // GL_SRGB8 star map as RGBX codes (sky_set_star_map); p == nullptr: no star term
     float* srgb_decode = nullptr; // 256-entry sRGB -> linear table (device)
+    // earth albedo map (sky_set_earth_albedo; earth.cu): GL_SRGB8 codes as RGBX, every mip level, level l at earth_albedo + earth_off[l]
+    uchar4* earth_albedo = nullptr;
+    int earth_w = 0, earth_h = 0, earth_levels = 0;
+    unsigned long long earth_off[kEarthMaxLevels] = {};
+    size_t earth_texels = 0;
     Lut<float> mesh_shadow_map;  // SKY_RES_MESH_SHADOW_MAP: 2048^2 light-space depth, allocated on first use, cleared to 1
 
     // viewport
@@ -233,6 +239,8 @@ int launch_atmosphere_luts(SkyContext* ctx);                                   /
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6
 int launch_env_brdf_lut(SkyContext* ctx);                                      // ibl.cu         K22
 int launch_ibl_precompute(SkyContext* ctx);                                    // ibl.cu         cube mips, K23, K24
+int launch_earth_albedo_mips(SkyContext* ctx, const float* thresholds_dev);    // earth.cu       glGenerateTextureMipmap (GL_SRGB8)
+int launch_earth_gbuffer(SkyContext* ctx, const SkyEarthBufferData& e, float* depth, void* albedo, void* normal, void* orm, int width, int height);  // earth.cu K7
 int launch_tonemap(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out);  // atmosphere.cu K21
 int launch_noise(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info);   // noise.cu       K8-K10
 int build_mip_texture(SkyContext* ctx, MipTextureDev& t, int w, int h, int d, int channels, bool border);

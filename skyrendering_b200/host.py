@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 from . import abi
-from .abi import (AtmosphereBufferData, AtmosphereRenderBufferData, CloudBufferData, CloudCommonBufferData, I,
+from .abi import (EarthBufferData, AtmosphereBufferData, AtmosphereRenderBufferData, CloudBufferData, CloudCommonBufferData, I,
                   LutConfig, MaterialBlock, NoiseCreateInfo, PathTracingInit, SkyError)
 
 _lib = None
@@ -47,6 +47,7 @@ def _host():
             "skyhost_camera_get": ([V, P(C.c_float * 3), P(C.c_float * 3), P(C.c_float), P(C.c_float), P(C.c_float)], I),
             "skyhost_camera_move": ([V, P(C.c_float * 3), C.c_float, C.c_float], I),
             "skyhost_view_projection": ([V, P(C.c_float * 16)], I),
+            "skyhost_earth_buffer": ([V, P(EarthBufferData)], I),
             "skyhost_ground_depth": ([V, C.c_void_p, I, I], I),
             "skyhost_ground_gbuffer": ([V, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, I, I], I),
             "skyhost_vdb_open": ([C.c_char_p, P(V)], I),
@@ -68,7 +69,7 @@ HOST_SYMBOLS = [
     "skyhost_atmosphere_buffer", "skyhost_lut_config", "skyhost_atmosphere_render_buffer", "skyhost_set_viewport",
     "skyhost_cloud_update", "skyhost_noise_info", "skyhost_set_voxel_dim", "skyhost_material_type", "skyhost_pt_params",
     "skyhost_pt_init", "skyhost_pt_region", "skyhost_camera_get", "skyhost_camera_move", "skyhost_view_projection",
-    "skyhost_ground_depth", "skyhost_ground_gbuffer", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
+    "skyhost_earth_buffer", "skyhost_ground_depth", "skyhost_ground_gbuffer", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
     "skyhost_vdb_fill_float",
 ]
 
@@ -179,6 +180,12 @@ class Scene:
         m = (C.c_float * 16)()
         self._check(_host().skyhost_view_projection(self.h, C.byref(m)))
         return np.array(m, np.float32).reshape(4, 4).T  # row-major numpy view of the column-major matrix
+
+    def earth_buffer(self):
+        """Earth::RenderToGBuffer's uniform block (Earth.cpp:46-53)."""
+        b = EarthBufferData()
+        self._check(_host().skyhost_earth_buffer(self.h, C.byref(b)))
+        return b
 
     def ground_depth(self, w, h):
         out = np.empty((h, w), np.float32)

@@ -180,6 +180,10 @@ int skyhost_view_projection(SkyScene* s, float vp[16]) {
     return guarded([&] { s->scene.camera_.ViewProjection().store(vp); });
 }
 
+int skyhost_earth_buffer(SkyScene* s, SkyEarthBufferData* out) {
+    return guarded([&] { s->scene.EarthBuffer(out); });
+}
+
 int skyhost_ground_depth(SkyScene* s, float* depth, int width, int height) {
     return guarded([&] { s->scene.GroundDepth(depth, width, height); });
 }

@@ -522,6 +522,21 @@ void Scene::AtmosphereRenderBuffer(SkyAtmosphereRenderBufferData& d) {
     aerial_perspective_lut_max_distance_ = d.aerial_perspective_lut_max_distance;
 }
 
+// Earth::RenderToGBuffer (Earth.cpp:46-53): the uniform block of the ground pass K7
+void Scene::EarthBuffer(SkyEarthBufferData* out) const {
+    SkyEarthBufferData b{};
+    const mat4 view_projection = camera_.ViewProjection();
+    view_projection.store(b.view_projection);
+    inverse(view_projection).store(b.inv_view_projection);
+    const vec3 camera_position = camera_.position_, earth_center = earth_.center();
+    const vec3 up = normalize(camera_position - earth_center);
+    b.camera_position[0] = camera_position.x; b.camera_position[1] = camera_position.y; b.camera_position[2] = camera_position.z;
+    b.earth_center[0] = earth_center.x; b.earth_center[1] = earth_center.y; b.earth_center[2] = earth_center.z;
+    b.camera_earth_center_distance = distance(camera_position, earth_center);
+    b.up_direction[0] = up.x; b.up_direction[1] = up.y; b.up_direction[2] = up.z;
+    *out = b;
+}
+
 // EarthRender.frag:40-52 + Atmosphere.glsl:57-69 evaluated in fp32 like the shader
 void Scene::GroundDepth(float* depth, int width, int height) const {
     const mat4 view_projection = camera_.ViewProjection();

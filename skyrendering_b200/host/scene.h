@@ -299,6 +299,7 @@ struct Scene {
     void AtmosphereRenderBuffer(SkyAtmosphereRenderBufferData& out);
     // analytic ground depth exactly as EarthRender.frag:40-52 writes gl_FragDepth (else 1.0),
     // quantised to the D24 depth buffer (GBuffer.cpp:22)
+    void EarthBuffer(SkyEarthBufferData* out) const;
     void GroundDepth(float* depth, int width, int height) const;
     void GroundGBuffer(const float albedo_rgb[3], uint8_t* albedo, int16_t* normal, uint16_t* orm, int width, int height) const;
 };

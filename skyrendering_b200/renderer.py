@@ -129,6 +129,27 @@ def synthetic_gbuffer(width, height, up_direction, seed=0):
     return albedo, normal, orm
 
 
+def synthetic_earth_albedo(width=1024, height=512, seed=0):
+    """A synthetic equirectangular GL_SRGB8 earth albedo map, uint8 [height][width][3] in GL row order (row 0 = south pole), standing in
+    for the reference's data/NASA blue-marble JPEG (Textures.cpp:52-58: an external asset).  Periodic in longitude, so REPEAT wrapping
+    is seamless; continents / oceans at low frequency plus texel-scale detail, so minification, anisotropy and the seam logic of
+    EarthRender.frag:27-35 all have something to filter."""
+    rng = np.random.default_rng(seed)
+    lon = (np.arange(width, dtype=np.float64) + 0.5) / width * 2.0 * np.pi
+    lat = ((np.arange(height, dtype=np.float64) + 0.5) / height - 0.5) * np.pi
+    field = np.zeros((height, width))
+    for k in range(1, 9):
+        for m in range(0, 6):
+            a, p1, p2 = rng.normal() / (k + m + 1.0), rng.uniform(0, 2 * np.pi), rng.uniform(0, 2 * np.pi)
+            field += a * np.cos(k * lon[None, :] + p1) * np.cos((2 * m + 1) * lat[:, None] + p2)
+    land = field > 0.05
+    detail = rng.random((height, width, 3))
+    rgb = np.where(land[..., None], np.array([0.35, 0.45, 0.2]) + 0.25 * detail * np.array([1.0, 0.8, 0.5]), np.array([0.03, 0.08, 0.25]) + 0.04 * detail)
+    ice = np.abs(lat)[:, None] > 1.25 + 0.1 * field
+    rgb = np.where(ice[..., None], 0.85 + 0.1 * detail, rgb)
+    return np.ascontiguousarray(np.rint(np.clip(rgb, 0.0, 1.0) * 255.0).astype(np.uint8))
+
+
 class Renderer:
     def __init__(self, scene, width, height, library=None, device=0, stream=0, blue_noise=None):
         self.scene = scene if isinstance(scene, Scene) else Scene.from_file(scene_path(scene))
@@ -167,6 +188,13 @@ class Renderer:
             self.ctx.env_brdf_lut()
             self._env_brdf_baked = True
         self.ibl = bool(on)
+
+    def ground_pass(self, depth, albedo, normal, orm):
+        """Earth::RenderToGBuffer (Earth.cpp:46-65, K7): the analytic ground into the depth plane and the three G-buffer targets
+        (uint8 / int16 / uint16 [H][W][4] in the library's memory space), which it then binds for the composite's object branch."""
+        self.earth_buffer = self.scene.earth_buffer()
+        self.ctx.earth_gbuffer(self.earth_buffer, depth, albedo, normal, orm, self.width, self.height)
+        self.ctx.set_gbuffer(albedo, normal, orm)
 
     def upload_voxels(self, grid):
         dz, dy, dx = grid.shape

@@ -358,3 +358,53 @@ def ibl_digests(env_brdf_lut, chain, sh, pre):
             "environment_mips": sha(np.concatenate([c.reshape(-1) for c in chain[1:]])),
             "env_radiance_sh": sha(np.asarray(sh, np.float32)), "sh_values": [float(v) for v in np.asarray(sh, np.float32).reshape(-1)],
             "prefiltered": [sha(p) for p in pre]}
+
+
+# ---- ground pass (K7) ----------------------------------------------------------------------------------------------
+class RefEarthLevel(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("w", C.c_int), ("h", C.c_int)]
+
+
+class RefEarthIO(C.Structure):
+    _fields_ = [("atmosphere", C.c_void_p), ("earth", C.c_void_p), ("levels", C.c_void_p), ("level_count", C.c_int), ("depth", C.c_void_p),
+                ("albedo", C.c_void_p), ("normal", C.c_void_p), ("orm", C.c_void_p), ("width", C.c_int), ("height", C.c_int)]
+
+
+def srgb_decode_table():
+    """GL 4.6 section 8.24 in double precision, rounded to fp32 (math.pow is libm's pow, like the oracle's std::pow)."""
+    import math
+    return np.array([c / 255.0 / 12.92 if c / 255.0 <= 0.04045 else math.pow((c / 255.0 + 0.055) / 1.055, 2.4) for c in range(256)]).astype(np.float32)
+
+
+def ref_earth_gbuffer(ref, renderer, depth, width, height, albedo_levels=None):
+    """K7: the reference's EarthRender.frag on the uniforms of `renderer` (after earth_update).  `albedo_levels`: the GL_SRGB8 codes of
+    every mip level (uint8 [h][w][4], Context.earth_albedo_levels) or None.  Returns (depth float32 [H][W] with the kept fragments'
+    D24-quantised gl_FragDepth, Albedo, Normal, ORM float32 [H][W][4] as the shader wrote them -- untouched (0) where it discards)."""
+    keep = []
+    levels = None
+    if albedo_levels:
+        table = srgb_decode_table()
+        arr = (RefEarthLevel * len(albedo_levels))()
+        for i, codes in enumerate(albedo_levels):
+            lin = np.ones(codes.shape[:2] + (4,), np.float32)
+            lin[..., :3] = table[codes[..., :3]]
+            lin = np.ascontiguousarray(lin); keep.append(lin)
+            arr[i] = RefEarthLevel(lin.ctypes.data, codes.shape[1], codes.shape[0])
+        levels = arr
+    d = np.ascontiguousarray(depth, np.float32).copy()
+    outs = [np.zeros((height, width, 4), np.float32) for _ in range(3)]
+    earth = renderer.scene.earth_buffer()
+    io = RefEarthIO(C.addressof(renderer.atmosphere), C.addressof(earth), None if levels is None else C.addressof(levels), 0 if levels is None else len(albedo_levels),
+                    d.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, width, height)
+    rc = ref.ref_earth_gbuffer(C.byref(io))
+    assert rc == 0, rc
+    return d, outs[0], outs[1], outs[2]
+
+
+def quantise_gbuffer(albedo, normal, orm):
+    """The stores into GL_RGBA8 / GL_RGBA16_SNORM / GL_RGBA16 targets (GBuffer.cpp:19-21): clamp, scale, round to nearest even."""
+    f = np.float32
+    a = np.rint(np.clip(albedo, f(0), f(1)) * f(255.0)).astype(np.uint8)
+    n = np.rint(np.clip(normal, f(-1), f(1)) * f(32767.0)).astype(np.int16)
+    o = np.rint(np.clip(orm, f(0), f(1)) * f(65535.0)).astype(np.uint16)
+    return a, n, o
