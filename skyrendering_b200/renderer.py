@@ -59,9 +59,9 @@ def synthetic_voxel_grid(dx=126, dy=154, dz=86, seed=0, blobs=64):
 
 def wdas_sixteenth_grid():
     """The R8 voxel texture of data/wdas/wdas_cloud_sixteenth.vdb (the file config_voxel.json's material loads), from the
-    committed fixture tests/golden/wdas_cloud_sixteenth_r8.npz (tools/make_vdb_fixture.py; the .vdb itself does not travel).
+    committed fixture skyrendering_b200/data/wdas_cloud_sixteenth_r8.npz (tools/make_vdb_fixture.py; the .vdb itself does not travel).
     (c) 2017 Disney Enterprises, Inc., CC BY-SA 3.0."""
-    return np.load(os.path.join(abi.REPO_ROOT, "tests", "golden", "wdas_cloud_sixteenth_r8.npz"))["voxels"]
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "wdas_cloud_sixteenth_r8.npz"))["voxels"]
 
 
 def synthetic_voxel_grid_large(scale, seed=0, blobs=64, device="cuda", slab=16):

@@ -67,7 +67,11 @@ def ref_luts(ref, renderer, mesh_shadow_map=None):
     if mesh_shadow_map is not None:
         shadow_rgba = np.zeros(mesh_shadow_map.shape + (4,), np.float32)
         shadow_rgba[..., 0] = mesh_shadow_map
-    io = RefLutIO(out["transmittance"].ctypes.data, out["multiscattering"].ctypes.data, None, out["sky_view_luminance"].ctypes.data,
+    bn = None
+    if cfg.sky_view_dither or cfg.aerial_perspective_dither:   # DITHER_SAMPLE_POINT_ENABLE of K3 / K4 reads the blue-noise texture
+        from skyrendering_b200.renderer import load_blue_noise
+        bn = as_rgba(np.asarray(load_blue_noise()).astype(np.float32) / np.float32(65535.0), channels_last=False)
+    io = RefLutIO(out["transmittance"].ctypes.data, out["multiscattering"].ctypes.data, None if bn is None else bn.ctypes.data, out["sky_view_luminance"].ctypes.data,
                   out["sky_view_transmittance"].ctypes.data, out["aerial_luminance"].ctypes.data, out["aerial_transmittance"].ctypes.data,
                   out["environment"].ctypes.data, None if shadow_rgba is None else shadow_rgba.ctypes.data,
                   0 if shadow_rgba is None else shadow_rgba.shape[0])

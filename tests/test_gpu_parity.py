@@ -109,6 +109,21 @@ def test_optional_march_terms(libs, moon, volumetric):
     assert rel_rms(hdrs["strict"][..., :3], hdrs["oracle"][..., :3]) < 1e-4
 
 
+@pytest.mark.parametrize("scene", ["c1", "c3"])
+def test_lut_dither_flags(libs, scene):
+    """sky_view_lut_dither_sample_point_enable / aerial_perspective_lut_dither_sample_point_enable (false in the shipped configs): K3 /
+    K4 with the blue-noise start offset stay bit-exact against the oracle (itself bit-identical to the reference's shader text compiled
+    with DITHER_SAMPLE_POINT_ENABLE, tests/test_permutations_cpu.py)."""
+    from tests.test_permutations_cpu import dithered_luts
+    cuda, orc = libs
+    _, g = dithered_luts(cuda, scene)
+    _, o = dithered_luts(orc, scene)
+    _, plain = dithered_luts(cuda, scene, 0, 0)
+    for name in g:
+        assert np.array_equal(g[name], o[name]), name
+    assert not np.array_equal(g["sky_view_luminance"], plain["sky_view_luminance"]) and not np.array_equal(g["aerial_luminance"], plain["aerial_luminance"])
+
+
 def test_sky_view_192x108_variant(libs):
     """BASELINE names a 192x108 sky-view LUT; the reference hard-codes 128x128.  The size is a parameter."""
     cuda, orc = libs

@@ -43,6 +43,34 @@ def test_oracle_permutations_are_the_reference_shader(moon, volumetric):
     assert not np.array_equal(got["aerial_luminance"], plain["aerial_luminance"])
 
 
+def dithered_luts(library, scene="c1", sky=1, aerial=1):
+    """K3 / K4 with sky_view_lut_dither_sample_point_enable / aerial_perspective_lut_dither_sample_point_enable
+    (DITHER_SAMPLE_POINT_ENABLE of the two compute programs, AtmosphereRenderer.cpp:89-97; false in the shipped configs)."""
+    r = Renderer(scene, 192, 108, library=library)
+    r.earth_update()
+    r.render_buffer, r.lut_config = r.scene.atmosphere_render_buffer(), r.scene.lut_config()
+    r.lut_config.sky_view_dither, r.lut_config.aerial_perspective_dither = sky, aerial
+    r.ctx.atmosphere_luts(r.render_buffer, r.lut_config)
+    return r, {name: refpin.canonical_rgb(r.ctx.read(res)) for name, res in refpin.LUTS}
+
+
+@pytest.mark.skipif(not refpin.reference_present(), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("scene", ["c1", "c3"])
+def test_oracle_lut_dither_flags_are_the_reference_shader(scene):
+    ref = refpin.ref_library()
+    r, got = dithered_luts(oracle_library(), scene)
+    want = refpin.ref_luts(ref, r)
+    for name in LUT_NAMES:
+        undefined = np.isnan(want[name]).any(axis=-1)
+        assert undefined.sum() <= 8, name
+        assert np.array_equal(got[name][~undefined], want[name][~undefined]), name
+    _, plain = dithered_luts(oracle_library(), scene, 0, 0)
+    # the blue-noise start offset moves the sample points of both LUTs (but not the environment cube, whose program has no dither)
+    assert not np.array_equal(got["sky_view_luminance"], plain["sky_view_luminance"])
+    assert not np.array_equal(got["aerial_luminance"], plain["aerial_luminance"])
+    assert np.allclose(got["sky_view_luminance"].mean(), plain["sky_view_luminance"].mean(), rtol=0.05)
+
+
 def test_cleared_mesh_shadow_map_changes_nothing():
     """ShadowMap::ClearBindViewport clears to 1.0 (ShadowMap.cpp:22-27): without occluders VOLUMETRIC_LIGHT_ENABLE is the identity
     (up to the rounding of the four PCF weights)."""

@@ -3,7 +3,7 @@
 Pinned three ways: (1) files written by tests/vdbwrite.py (an independent statement of the same published layout) covering
 every readCompressedValues code, tiles, negative coordinates and several root children; (2) the shipped
 data/wdas/wdas_cloud_sixteenth.vdb against its OWN metadata (file_bbox_min/max, file_voxel_count) where the reference tree
-is mounted; (3) the committed R8 fixture of that file (tests/golden/wdas_cloud_sixteenth_r8.npz)."""
+is mounted; (3) the committed R8 fixture of that file (skyrendering_b200/data/wdas_cloud_sixteenth_r8.npz)."""
 import hashlib
 import os
 
@@ -15,7 +15,7 @@ from skyrendering_b200.host import VdbGrid
 from tests import vdbwrite
 
 WDAS = "/root/reference/data/wdas/wdas_cloud_sixteenth.vdb"
-FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wdas_cloud_sixteenth_r8.npz")
+FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "skyrendering_b200", "data", "wdas_cloud_sixteenth_r8.npz")
 
 
 def random_voxels(seed, count=4000, lo=-140, hi=150):

@@ -38,6 +38,33 @@ __global__ void __launch_bounds__(256) probe(float* out, float s) {
             for (int i = 0; i < 8; ++i) { p[i] = fma2(p[i], ss, cc); }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { p[i] = fma2(p[i], ss, cc); }
+        } else if (MODE == 6) {   // 16 scalar FFMA + 16 integer ALU ops
+            unsigned q = __float_as_uint(m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = fmaf(a[i], s, 0.25f); q = (q ^ (q >> 3)) + i; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = fmaf(a[i], s, 0.125f); }
+            m = __uint_as_float(q);
+        } else if (MODE == 7) {   // 8 FFMA2 + the same 16 integer ALU ops
+            unsigned q = __float_as_uint(m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p[i] = fma2(p[i], ss, cc); q = (q ^ (q >> 3)) + i; }
+            m = __uint_as_float(q);
+        } else if (MODE == 8) {   // 16 scalar FFMA + 2 approximate MUFU
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = fmaf(a[i], s, 0.25f); }
+            m = __fdividef(1.0f, m); a[7] = rsqrtf(a[7]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = fmaf(a[i], s, 0.125f); }
+        } else if (MODE == 9) {   // 8 FFMA2 + 2 approximate MUFU
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p[i] = fma2(p[i], ss, cc); }
+            m = __fdividef(1.0f, m); a[7] = rsqrtf(a[7]);
+        } else if (MODE == 10) {  // 8 packed mul + 8 packed add
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ss)); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(cc)); }
         } else if (MODE == 5) {   // 2 approximate MUFU (rcp + rsqrt), independent chains
             m = __fdividef(1.0f, m) + 1.0f; a[0] = rsqrtf(a[0]) + 1.0f; a[1] = __fdividef(1.0f, a[1]) + 1.0f; a[2] = rsqrtf(a[2]) + 1.0f;
         }
@@ -69,5 +96,10 @@ int main() {
     run<2>("16 FFMA + 2 MUFU", 16, out);
     run<3>("8 FFMA2 + 2 MUFU", 16, out);
     run<5>("4 MUFU (approx)", 0, out);
+    run<6>("16 FFMA + 16 int ALU", 16, out);
+    run<7>("8 FFMA2 + 16 int ALU", 16, out);
+    run<8>("16 FFMA + 2 MUFU approx", 16, out);
+    run<9>("8 FFMA2 + 2 MUFU approx", 16, out);
+    run<10>("8 FMUL2 + 8 FADD2", 16, out);
     return 0;
 }
