@@ -86,6 +86,10 @@ int SKY_FN(set_gbuffer)(SkyContext* ctx, const void* albedo_dev, const void* nor
  * v = latitude (EarthRender.frag:22-26).  width or height 0 removes it (the ground pass then writes albedo 0). */
 int SKY_FN(set_earth_albedo)(SkyContext* ctx, const uint8_t* host_srgb8, int width, int height);
 
+/* Clear(const GBuffer&) (src/Base/include/GBuffer.h:28-34; AppWindow::Render, AppWindow.cpp:168): the three colour targets to 0, the depth
+ * plane to 1.0 -- what a frame starts from before the ground pass (and the meshes, which are outside the path) fill the G-buffer. */
+int SKY_FN(gbuffer_clear)(SkyContext* ctx, float* depth_dev, void* albedo_dev, void* normal_dev, void* orm_dev, int width, int height);
+
 /* Earth::RenderToGBuffer (src/SkyRendering/Earth.cpp:46-65, shaders/SkyRendering/EarthRender.frag, K7): the analytic ground pass.  For every pixel
  * whose view ray meets the ground sphere in front of what the depth buffer already holds it writes gl_FragDepth (quantised to
  * the D24 of GBuffer.cpp:22) and the three G-buffer targets in the formats of GBuffer.cpp:19-21 -- albedo GL_RGBA8 from the earth

@@ -104,6 +104,14 @@ int orc_set_earth_albedo(SkyContext* ctx, const uint8_t* srgb8, int width, int h
     return 0;
 }
 
+int orc_gbuffer_clear(SkyContext* ctx, float* depth, void* albedo, void* normal, void* orm, int width, int height) {
+    if (!depth || !albedo || !normal || !orm || width <= 0 || height <= 0) return fail(ctx, "gbuffer_clear: bad arguments");
+    const size_t n = size_t(width) * height;   // Clear(const GBuffer&), GBuffer.h:28-34
+    std::fill(depth, depth + n, 1.0f);
+    std::memset(albedo, 0, n * 4); std::memset(normal, 0, n * 8); std::memset(orm, 0, n * 8);
+    return 0;
+}
+
 int orc_earth_gbuffer(SkyContext* ctx, const SkyEarthBufferData* earth, float* depth, void* albedo, void* normal, void* orm, int width, int height) {
     if (!earth || !depth || !albedo || !normal || !orm || width <= 0 || height <= 0) return fail(ctx, "earth_gbuffer: bad arguments");
     EarthGBuffer(ctx->scene.atm, *earth, ctx->earth_albedo, depth, static_cast<uint8_t*>(albedo), static_cast<int16_t*>(normal), static_cast<uint16_t*>(orm), width, height);

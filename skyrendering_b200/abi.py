@@ -199,6 +199,7 @@ KERNEL_API = {
     "pt_set_tracking": ([I], I),
     "set_star_map": ([_VOIDP, I, I], I),
     "set_earth_albedo": ([_VOIDP, I, I], I),
+    "gbuffer_clear": ([_VOIDP, _VOIDP, _VOIDP, _VOIDP, I, I], I),
     "earth_gbuffer": ([P(EarthBufferData), _VOIDP, _VOIDP, _VOIDP, _VOIDP, I, I], I),
     "tonemap": ([_VOIDP, I, I, C.POINTER(ToneMapParams), _VOIDP], I),
     "pt_samples_host": ([P(CloudCommonBufferData), U, U, P(I * 4), _VOIDP], I),
@@ -401,6 +402,10 @@ class Context:
             out.append(flat[o:o + w * h].reshape(h, w, 4))
             o += w * h
         return out
+
+    def gbuffer_clear(self, depth, albedo, normal, orm, width, height):
+        """Clear(const GBuffer&) (GBuffer.h:28-34): colour targets 0, depth 1."""
+        self._call("gbuffer_clear", _ptr(depth), _ptr(albedo), _ptr(normal), _ptr(orm), width, height)
 
     def earth_gbuffer(self, earth, depth, albedo, normal, orm, width, height):
         """K7 (Earth::RenderToGBuffer): depth float32 [H][W] in/out; albedo uint8, normal int16, orm uint16 [H][W][4] written where the ground is hit."""

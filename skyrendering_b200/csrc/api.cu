@@ -132,6 +132,7 @@ static int alloc_bake_luts(SkyContext* ctx) {
     rc |= sky_alloc(ctx, ctx->multiscattering, 32, 32);  // Atmosphere.cpp:17-18
     rc |= sky_alloc(ctx, ctx->transmittance_h, 256, 64);
     rc |= sky_alloc(ctx, ctx->multiscattering_h, 32, 32);
+    rc |= sky_alloc(ctx, ctx->density_h, kDensityLutSize, 1);
     if (rc) return rc;
     // GL_LINEAR + CLAMP_TO_EDGE texture views (Samplers.cpp linear_clamp_no_mipmap) over the RGBA16F copies
     auto make_tex = [](const Lut<half4>& l, cudaTextureObject_t* out) {
@@ -151,6 +152,7 @@ static int alloc_bake_luts(SkyContext* ctx) {
     };
     rc |= make_tex(ctx->transmittance_h, &ctx->transmittance_tex);
     rc |= make_tex(ctx->multiscattering_h, &ctx->multiscattering_tex);
+    rc |= make_tex(ctx->density_h, &ctx->density_tex);
     return rc;
 }
 
@@ -161,6 +163,7 @@ static void swap_lut_sets(SkyContext* ctx) {
     std::swap(ctx->sky_lum, a.sky_lum); std::swap(ctx->sky_trans, a.sky_trans);
     std::swap(ctx->ap_lum, a.ap_lum); std::swap(ctx->ap_trans, a.ap_trans);
     std::swap(ctx->env, a.env); std::swap(ctx->transmittance_h, a.transmittance_h); std::swap(ctx->multiscattering_h, a.multiscattering_h);
+    std::swap(ctx->density_h, a.density_h); std::swap(ctx->density_tex, a.density_tex);
     std::swap(ctx->transmittance_tex, a.transmittance_tex); std::swap(ctx->multiscattering_tex, a.multiscattering_tex);
     std::swap(ctx->sky_lum_tex, a.sky_lum_tex); std::swap(ctx->sky_trans_tex, a.sky_trans_tex);
     std::swap(ctx->ap_lum_tex, a.ap_lum_tex); std::swap(ctx->ap_trans_tex, a.ap_trans_tex);
@@ -212,7 +215,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h);
+    free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->density_h);
     free_lut(ctx->transmittance); free_lut(ctx->multiscattering); free_lut(ctx->sky_lum); free_lut(ctx->sky_trans);
     free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
     for (auto& m : ctx->shadow_maps) free_lut(m);
@@ -234,9 +237,9 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->alt.shadow_froxel);
     if (ctx->lut_stream) { cudaStreamSynchronize(ctx->lut_stream); cudaStreamDestroy(ctx->lut_stream); }
     swap_lut_sets(ctx);  // free the alternate set through the same path
-    free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->transmittance); free_lut(ctx->multiscattering);
+    free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->density_h); free_lut(ctx->transmittance); free_lut(ctx->multiscattering);
     free_lut(ctx->sky_lum); free_lut(ctx->sky_trans); free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
-    for (cudaTextureObject_t t : {ctx->transmittance_tex, ctx->multiscattering_tex, ctx->sky_lum_tex, ctx->sky_trans_tex, ctx->ap_lum_tex, ctx->ap_trans_tex}) if (t) cudaDestroyTextureObject(t);
+    for (cudaTextureObject_t t : {ctx->density_tex, ctx->transmittance_tex, ctx->multiscattering_tex, ctx->sky_lum_tex, ctx->sky_trans_tex, ctx->ap_lum_tex, ctx->ap_trans_tex}) if (t) cudaDestroyTextureObject(t);
     swap_lut_sets(ctx);
     if (ctx->transmittance_tex) cudaDestroyTextureObject(ctx->transmittance_tex);
     if (ctx->multiscattering_tex) cudaDestroyTextureObject(ctx->multiscattering_tex);
@@ -416,6 +419,14 @@ int sky_set_earth_albedo(SkyContext* ctx, const uint8_t* host_srgb8, int width, 
     cudaStreamSynchronize(ctx->stream);
     cudaFree(thr_dev);
     return rc;
+}
+
+int sky_gbuffer_clear(SkyContext* ctx, float* depth, void* albedo, void* normal, void* orm, int width, int height) {
+    if (!depth || !albedo || !normal || !orm || width <= 0 || height <= 0) return sky_fail(ctx, "gbuffer_clear: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(depth) & 7) || (reinterpret_cast<uintptr_t>(albedo) & 7) || (reinterpret_cast<uintptr_t>(normal) & 15) || (reinterpret_cast<uintptr_t>(orm) & 15))
+        return sky_fail(ctx, "gbuffer_clear: targets must be 16-byte aligned");
+    if (int e = lanes_join(ctx)) return e;  // a frame in flight on the second lane may still read the depth plane
+    return launch_gbuffer_clear(ctx, depth, albedo, normal, orm, width, height);
 }
 
 int sky_earth_gbuffer(SkyContext* ctx, const SkyEarthBufferData* earth, float* depth, void* albedo, void* normal, void* orm, int width, int height) {

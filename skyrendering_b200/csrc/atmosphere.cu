@@ -227,7 +227,7 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
 // (tests/test_gpu_parity.py: C2 / C3 at 1920x1080, C4 at 3840x2160).
 template <bool EXTRA>
 SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const LutView& transmittance_texture, const LutView& multiscattering_texture,
-                                           float start_i, float3 earth_center, float3 start_position, float3 view_direction, float3 sun_direction,
+                                           cudaTextureObject_t density_texture, float start_i, float3 earth_center, float3 start_position, float3 view_direction, float3 sun_direction,
                                            float marching_distance, float steps, float3& transmittance, const ScatterExtras* extras) {
     const SkyAtmosphereBufferData& u = atm.u;
     const float kLog2e = 1.4426950408889634f;
@@ -247,7 +247,7 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
     const float3 Rs = f3(u.rayleigh_scattering), Ms = f3(u.mie_scattering), Ma = f3(u.mie_absorption), Oz = f3(u.ozone_absorption);
     const float3 RsP = Rs * rayleigh_phase * solar, MsP = Ms * mie_phase * solar;   // single scattering, phase and illuminance folded
     const float3 Qms = solar * u.multiscattering_mask;                                // multiple scattering: x scattering_i x LUT
-    const float k_r = -u.inv_rayleigh_exponential_distribution * kLog2e, k_m = -u.inv_mie_exponential_distribution * kLog2e;
+    const float dn_a = (1.0f - 1.0f / float(kDensityLutSize)) / (u.top_radius - u.bottom_radius), dn_b = 0.5f / float(kDensityLutSize);
     const float k_t = -dx * kLog2e;
     // ray constants of the (r, mu_s) -> transmittance-LUT mapping (Atmosphere.glsl:90-108)
     const float bottom = u.bottom_radius, top = u.top_radius;
@@ -264,7 +264,16 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
     const float mv_a = (1.0f - 1.0f / mh) / (top - bottom), mv_b = 0.5f / mh;
 
     float3 T = f3(1.0f), L = f3(0.0f);
-    for (float i = start_i; i < steps; ++i) {
+    // the shader's `for (float i = start_i; i < SAMPLE_COUNT; ++i)` with an integer trip count (start_i is in [0, 1): the number of
+    // i = start_i + k below `steps` is ceil(steps - start_i)), so that the compiler may unroll it
+    const int trip = max(int(ceilf(steps - start_i)), 0);
+    float i = start_i;
+#ifndef SKY_K6_UNROLL
+#define SKY_K6_UNROLL 4   // measured at 4K, scene c3: 1 -> 693 us, 2 -> 716 us, 4 -> 683 us (profiles/k6_variants_r02l.log)
+#endif
+    constexpr int kUnroll = SKY_K6_UNROLL;
+#pragma unroll kUnroll
+    for (int k = 0; k < trip; ++k, i += 1.0f) {
         const float d = i * dx;
         const float dd = d * (d + two_rmu);
         const float ri2 = dd + r2;
@@ -273,9 +282,9 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
         const float altitude = r_i - bottom;
         const float rms = a_s + b_s * d;            // r_i mu_s_i
         const float mu_s = rms * inv_r;
-        // densities (GetScattering / GetExtinction, :119-132,156-159)
-        const float dR = __saturatef(exp2f(altitude * k_r)), dM = __saturatef(exp2f(altitude * k_m));
-        const float dO = fmaxf(0.0f, 1.0f - fabsf(altitude - u.ozone_center_altitude) * u.inv_ozone_width);
+        // densities (GetScattering / GetExtinction, :119-132,156-159): one fetch of the altitude table
+        const float4 dens = tex2D<float4>(density_texture, dn_b + altitude * dn_a, 0.5f);
+        const float dR = dens.x, dM = dens.y, dO = dens.z;
         const float3 scattering = Rs * dR + Ms * dM;
         const float3 extinction = scattering + Ma * dM + Oz * dO;
         const float3 T_i = f3(exp2f(extinction.x * k_t), exp2f(extinction.y * k_t), exp2f(extinction.z * k_t));
@@ -299,7 +308,12 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
         if (EXTRA && extras->moon_shadow)  // :281-284
             L_i *= GetVisibilityFromMoonShadow(f3(extras->moon_position) - position_i, extras->moon_radius, sun_direction, u.sun_angular_radius);
         // analytic integral over the segment (:288): (L_i - L_i T_i) / extinction, attenuated by the transmittance so far
-        L += T * (L_i - L_i * T_i) * f3(1.0f / extinction.x, 1.0f / extinction.y, 1.0f / extinction.z);
+        // (one MUFU.RCP for the three channels: 1 / x = y z / (x y z); the products stay far inside the fp32 range for extinction
+        // coefficients per km, and a vanishing extinction gives the same 0 x inf = NaN the shader's own division produces)
+        const float xy = extinction.x * extinction.y;
+        const float inv_xyz = 1.0f / (xy * extinction.z);
+        const float inv_z = xy * inv_xyz, inv_xy_z = extinction.z * inv_xyz;
+        L += T * (L_i - L_i * T_i) * f3(extinction.y * inv_xy_z, extinction.x * inv_xy_z, inv_z);
         T *= T_i;
     }
     transmittance = T;
@@ -410,11 +424,23 @@ __global__ void __launch_bounds__(64) k2_multiscattering(const __grid_constant__
     }
 }
 
+// RGBA16F copies of the two bake LUTs + the density table of K6's march (context.h): texel i of the table is the altitude
+// i / (nd - 1) x (top - bottom) and holds (rayleigh density, mie density, ozone density, 0) -- GetScattering / GetExtinction's three
+// altitude profiles (Atmosphere.glsl:119-132,156-159), with the same clamps
 __global__ void __launch_bounds__(256) k_luts_to_half(const float4* __restrict__ a, half4* __restrict__ ah, int na, const float4* __restrict__ b,
-                                                      half4* __restrict__ bh, int nb) {
+                                                      half4* __restrict__ bh, int nb, half4* __restrict__ density, int nd, SkyAtmosphereBufferData u) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < na) ah[i] = to_half4(a[i]);
     else if (i - na < nb) bh[i - na] = to_half4(b[i - na]);
+    else if (i - na - nb < nd) {
+        const int k = i - na - nb;
+        const float altitude = float(k) / float(nd - 1) * (u.top_radius - u.bottom_radius);
+        const float dR = clampf(LUT_EXP(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
+        const float dM = clampf(LUT_EXP(-altitude * u.inv_mie_exponential_distribution), 0.0f, 1.0f);
+        const float dO = fmaxf(0.0f, altitude < u.ozone_center_altitude ? 1.0f + (altitude - u.ozone_center_altitude) * u.inv_ozone_width
+                                                                        : 1.0f - (altitude - u.ozone_center_altitude) * u.inv_ozone_width);
+        density[k] = to_half4(f4(dR, dM, dO, 0.0f));
+    }
 }
 
 // ------------------------------------------------------------------------------------------- K3 / K4 / K5 / K6
@@ -438,6 +464,7 @@ struct RenderParams {
     SkyAtmosphereRenderBufferData r;  // AtmosphereRenderer.glsl:25-50
     SkyLutConfig cfg;
     LutView transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
+    cudaTextureObject_t density_tex;  // 1-D altitude -> (rayleigh, mie, ozone) density table, kDensityLutSize texels (context.h)
     FroxelView froxel;  // p == nullptr: no cloud shadow froxel yet (visibility 1)
     ScatterExtras extras;
     const uchar4* star_map;      // GL_SRGB8 codes (RGBX), nullptr: no star term
@@ -841,8 +868,16 @@ SKY_D float3 ComputeObjectLuminance(const RenderParams& P, float3 position, floa
 // shaded by ComputeObjectLuminance when a G-buffer is bound (template flag OBJECT); without one they carry the in-scatter alone,
 // which is what the reference's program computes on a cleared (all-zero) G-buffer.  Alpha is 1 everywhere (:431).
 // HBM-bound: 4 B depth in + 8 B hdr out per pixel; LUTs and froxels are L2-resident.
-template <bool EXTRA, bool OBJECT, bool PCSS_ON = false>
-__global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : 3) k6_composite(const __grid_constant__ RenderParams P) {
+#ifndef SKY_K6_OCC
+#define SKY_K6_OCC 3   // resident 256-thread blocks per SM of the plain composite (80 registers)
+#endif
+#ifndef SKY_K6_LUT_OCC
+#define SKY_K6_LUT_OCC 6
+#endif
+// LUTONLY: the launch's configuration has both USE_SKY_VIEW_LUT and USE_AERIAL_PERSPECTIVE_LUT (scenes c1 / c2): no pixel marches, so the
+// march is compiled out and the kernel -- a latency-bound chain of depth load, LUT and froxel fetches -- runs at twice the occupancy
+template <bool EXTRA, bool OBJECT, bool PCSS_ON = false, bool LUTONLY = false>
+__global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : LUTONLY ? SKY_K6_LUT_OCC : SKY_K6_OCC) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
     if (P.band_count > 1) py = ((py / P.band_rows) * P.band_count + P.band_index) * P.band_rows + py % P.band_rows;
     if (px >= P.width || py >= P.height) return;
@@ -874,10 +909,10 @@ __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : 3) k6_composit
             float3 uvw = aerial_perspective_uvw(vTexCoord, marching_distance, P.r.aerial_perspective_lut_max_distance, P.ap_lum.w, P.ap_lum.h, P.ap_lum.d);
             luminance = xyz(sample_lut3d_sel<kCompositeTexLut>(P.ap_lum, uvw.x, uvw.y, uvw.z));
             transmittance = xyz(sample_lut3d_sel<kCompositeTexLut>(P.ap_trans, uvw.x, uvw.y, uvw.z));
-        } else {
+        } else if (!LUTONLY) {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
 #if defined(SKY_COMPOSITE_TU) && !defined(SKY_STRICT_TU) && !defined(SKY_K6_REFERENCE_ORDER_MARCH)
-            luminance = ComputeScatteredLuminanceFast<EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position, view_direction,
+            luminance = ComputeScatteredLuminanceFast<EXTRA>(P.atm, P.transmittance, P.multiscattering, P.density_tex, start_i, f3(P.r.earth_center), start_position, view_direction,
                                                              sun_direction, marching_distance, P.r.raymarching_steps, transmittance, &P.extras);
 #else
             luminance = ComputeScatteredLuminance<false, kCompositeTexLut, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
@@ -935,6 +970,7 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.sky_trans = LutView{ctx->sky_trans.p, ctx->sky_trans.w, ctx->sky_trans.h, 1, ctx->sky_trans_tex};
     P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d, ctx->ap_lum_tex};
     P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, ctx->ap_trans_tex};
+    P.density_tex = ctx->density_tex;
     P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
     P.blue_noise = ctx->blue_noise;
     P.star_map = ctx->star_map.p; P.srgb_decode = ctx->srgb_decode; P.star_w = ctx->star_map.w; P.star_h = ctx->star_map.h;
@@ -970,9 +1006,9 @@ RenderParams make_render_params(SkyContext* ctx) {
 #ifndef SKY_COMPOSITE_TU
 // RGBA16F copies of the two bake LUTs for K6's texture fetches (context.h)
 int launch_lut_half_copies(SkyContext* ctx) {
-    const int na = ctx->transmittance.w * ctx->transmittance.h, nb = ctx->multiscattering.w * ctx->multiscattering.h;
-    k_luts_to_half<<<ceil_div(na + nb, 256), 256, 0, ctx->stream>>>(ctx->transmittance.p, ctx->transmittance_h.p, na, ctx->multiscattering.p,
-                                                                     ctx->multiscattering_h.p, nb);
+    const int na = ctx->transmittance.w * ctx->transmittance.h, nb = ctx->multiscattering.w * ctx->multiscattering.h, nd = ctx->density_h.w;
+    k_luts_to_half<<<ceil_div(na + nb + nd, 256), 256, 0, ctx->stream>>>(ctx->transmittance.p, ctx->transmittance_h.p, na, ctx->multiscattering.p,
+                                                                          ctx->multiscattering_h.p, nb, ctx->density_h.p, nd, ctx->atm);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1080,6 +1116,7 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
         } else if (extra) k6_composite<true, true><<<grid, 256, 0, ctx->stream>>>(P);
         else k6_composite<false, true><<<grid, 256, 0, ctx->stream>>>(P);
     } else if (extra) k6_composite<true, false><<<grid, 256, 0, ctx->stream>>>(P);
+    else if (P.cfg.use_sky_view_lut && P.cfg.use_aerial_perspective_lut) k6_composite<false, false, false, true><<<grid, 256, 0, ctx->stream>>>(P);
     else k6_composite<false, false><<<grid, 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;

@@ -616,17 +616,25 @@ struct K16Taps {
     float mid[kK16MaxTaps], weight[kK16MaxTaps];
 };
 
+#ifdef SKY_K16_WAVE_STATS   // experiment builds only (tools/k16_stats.py): where the lane slots of the wavefront kernel go
+__device__ unsigned long long g_k16_stats[8];
+#define K16_STAT(slot, value) do { const unsigned long long v__ = (unsigned long long)(value); if (lane == 0) atomicAdd(&g_k16_stats[slot], v__); } while (0)
+#else
+#define K16_STAT(slot, value) do { } while (0)
+#endif
 template <int MAT, bool HW>
 __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block) k16_render_wave(const __grid_constant__ CloudParams P, const __grid_constant__ K16Taps taps) {
     const SkyCloudCommonBufferData& c = P.c;
     const SkyCloudBufferData& b = P.b;
     __shared__ K16WaveScratch scratch[kK16Block / 32];
     __shared__ float tap_mid[kK16MaxTaps], tap_weight[kK16MaxTaps];   // indexed per lane: shared memory, not the constant bank
+    __shared__ unsigned int recip[33];   // ceil(2^16 / n): floor(t / n) = (t * recip[n]) >> 16 exactly for t < 256, n <= 32 (task -> (tap, step) without I2F / F2I)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
     K16WaveScratch& W = scratch[threadIdx.x >> 5];
     const int n_taps = taps.count;
     if (threadIdx.x < unsigned(kK16MaxTaps)) { tap_mid[threadIdx.x] = taps.mid[threadIdx.x]; tap_weight[threadIdx.x] = taps.weight[threadIdx.x]; }
+    if (threadIdx.x < 33u) recip[threadIdx.x] = threadIdx.x ? (65536u + threadIdx.x - 1u) / threadIdx.x : 0u;
     __syncthreads();
     const float3 camera = f3(c.uCameraPos);
     const float3 sample_vector = b.uShadowDistance * f3(c.uSunDirection);
@@ -685,7 +693,7 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
         }
         __syncwarp();
         // ---- stage 1: lane -> (group ray j, look-ahead step k), step-major ------------------------------------------------------
-        const int k = __float2int_rd((float(lane) + 0.5f) * (1.0f / float(A)));
+        const int k = int((lane * recip[A]) >> 16);
         const int j = int(lane) - k * A;
         const bool has_task = k < K;
         float4 rd = f4(0.0f, 0.0f, 0.0f, 0.0f), rs = rd;
@@ -699,6 +707,7 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
             sigma_t = SampleSigmaT<MAT, HW>(P.mat, pos, height01);               // :117
         }
         const bool cloud = valid && !(sigma_t < 1e-5f);                           // :118-119
+        K16_STAT(0, 1); K16_STAT(1, A); K16_STAT(2, __popc(__ballot_sync(0xffffffffu, valid)));
         // ---- stage 2: the shadow marches of the steps with cloud in them (:98-114), all lanes --------------------------------------
         const unsigned dmask = __ballot_sync(0xffffffffu, cloud);
         unsigned cloud_rays = 0;                                                  // group rays with cloud in one of their K steps
@@ -709,10 +718,11 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
             if (cloud) W.pos[d] = f4(pos, 0.0f);
             __syncwarp();
             const int total = D * n_taps;
-            const float inv_D = 1.0f / float(D);
+            const unsigned int recip_D = recip[D];
+            K16_STAT(3, D); K16_STAT(4, (total + 31) / 32);
 #pragma unroll 1
             for (int task = int(lane); task < total; task += 32) {
-                const int tap = __float2int_rd((float(task) + 0.5f) * inv_D);
+                const int tap = int((unsigned(task) * recip_D) >> 16);
                 const float4 p = W.pos[task - tap * D];
                 const float3 sample_pos = f3(p.x, p.y, p.z) + sample_vector * tap_mid[tap];
                 const float sample_height01 = CalHeight01(P, sample_pos);
@@ -721,8 +731,13 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
             __syncwarp();
             float4 o = f4(1.0f, 0.0f, 0.0f, valid ? 0.0f : -1.0f);
             if (cloud) {
-                float optical_depth = 0.0f;
-                for (int tap = 0; tap < n_taps; ++tap) optical_depth += W.res[tap * D + d];   // the shader's order
+                float optical_depth;
+                if (n_taps == 5) {   // uShadowSteps = 5 in every shipped configuration: no loop
+                    optical_depth = (((W.res[d] + W.res[D + d]) + W.res[2 * D + d]) + W.res[3 * D + d]) + W.res[4 * D + d];
+                } else {
+                    optical_depth = 0.0f;
+                    for (int tap = 0; tap < n_taps; ++tap) optical_depth += W.res[tap * D + d];   // the shader's order
+                }
                 const float transmittance_to_sun = expf(-optical_depth);
                 // the step-local part of RayMarchStep, :120-133
                 const float tr = expf(-rs.y * sigma_t);
@@ -740,6 +755,9 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
         // ---- stage 3: each group ray consumes its steps in order: the loop body of :170-177 / :182-187 ------------------------------
         if (selected) {
             const uint32_t n = min(cnt, uint32_t(K));            // steps of this ray that were evaluated
+#ifdef SKY_K16_WAVE_STATS
+            atomicAdd(&g_k16_stats[5], (unsigned long long)n);
+#endif
             if (!((cloud_rays >> rank) & 1u)) {
                 // clear air all the way: the transmittance does not change, so `break` fires after the first step or never
                 if (ctx.transmittance < kMinTransmittance) cnt = 0;
@@ -1213,3 +1231,11 @@ int launch_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
     return 0;
 }
 #endif  // SKY_STRICT_TU
+
+#if defined(SKY_K16_WAVE_STATS) && !defined(SKY_STRICT_TU)
+extern "C" __attribute__((visibility("default"))) int sky_debug_k16_stats(unsigned long long* out, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_k16_stats, sizeof(g_k16_stats)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[8] = {}; if (cudaMemcpyToSymbol(g_k16_stats, z, sizeof(z)) != cudaSuccess) return 1; }
+    return 0;
+}
+#endif

@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 constexpr int kMaxMipLevels = 13;
+constexpr int kDensityLutSize = 2048;  // 49 m per texel for a 100 km atmosphere: interpolation error of exp(-h / 1.2 km) 2e-4 relative
 constexpr int kEarthMaxLevels = 15;  // earth albedo map: up to 16384 texels per axis
 constexpr int SKY_PEER_TIMEOUT_SLOT = 16, SKY_PEER_FLAG_SLOTS = 32;  // see k_peer_flags (cloud.cu)  // up to 4096 texels per axis
 
@@ -86,10 +87,11 @@ struct SkyContext {
     cudaEvent_t ev_main_to_lut = nullptr;
     struct LutSet {                    // the alternate copy of everything sky_atmosphere_bake / sky_atmosphere_luts write
         Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
-        Lut<half4> env, transmittance_h, multiscattering_h;
+        Lut<half4> env, transmittance_h, multiscattering_h, density_h;
         Lut<uint16_t> shadow_froxel;   // second froxel volume: the shadow chain of frame N+1 also runs on lut_stream
         Lut<float2> shadow_blurred;    // second blurred cloud shadow map (shadow_maps[2]): the object branch of frame N's K6 samples
                                        // it on the caller's stream while K12 of frame N+1 writes the other one on lut_stream
+        cudaTextureObject_t density_tex = 0;
         cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0, sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
         const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
         int lut_tex_dims[4][3] = {};
@@ -125,6 +127,11 @@ struct SkyContext {
     // fp16 rounding (2^-11 relative) is far inside the frame tolerance; the strict objects filter the fp32 LUTs in software.
     Lut<half4> transmittance_h, multiscattering_h;
     cudaTextureObject_t transmittance_tex = 0, multiscattering_tex = 0;  // LINEAR views of those copies
+    // K6's march also reads the three density profiles of the atmosphere model -- exp(-h / H_rayleigh), exp(-h / H_mie) and the ozone tent
+    // (Atmosphere.glsl:119-132,156-159) -- from a 1-D RGBA16F table over the altitude (kDensityLutSize texels from the ground to the top
+    // boundary, LINEAR + CLAMP): one TEX instead of two MUFU.EX2 and eight ALU instructions per step.  Rebuilt with every bake.
+    Lut<half4> density_h;
+    cudaTextureObject_t density_tex = 0;
     // LINEAR views of the per-frame LUTs for K6's look-ups: sky view as 2-D, aerial perspective as a 32 x (32 D) atlas of its slices
     cudaTextureObject_t sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
     const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -240,6 +247,7 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
 int launch_env_brdf_lut(SkyContext* ctx);                                      // ibl.cu         K22
 int launch_ibl_precompute(SkyContext* ctx);                                    // ibl.cu         cube mips, K23, K24
 int launch_earth_albedo_mips(SkyContext* ctx, const float* thresholds_dev);    // earth.cu       glGenerateTextureMipmap (GL_SRGB8)
+int launch_gbuffer_clear(SkyContext* ctx, float* depth, void* albedo, void* normal, void* orm, int width, int height);  // earth.cu
 int launch_earth_gbuffer(SkyContext* ctx, const SkyEarthBufferData& e, float* depth, void* albedo, void* normal, void* orm, int width, int height);  // earth.cu K7
 int launch_tonemap(SkyContext* ctx, const half4* hdr, int w, int h, const SkyToneMapParams& p, void* out);  // atmosphere.cu K21
 int launch_noise(SkyContext* ctx, int kind, const SkyNoiseCreateInfo* info);   // noise.cu       K8-K10

@@ -2,10 +2,9 @@
 // (src/SkyRendering/Earth.cpp:46-65), and the earth albedo map it samples (Textures::Textures, src/Base/src/Textures.cpp:52-58:
 // GL_SRGB8 upload + glGenerateTextureMipmap; sampler Earth.cpp:34-42: REPEAT x CLAMP_TO_EDGE, LINEAR_MIPMAP_LINEAR, maximum anisotropy).
 //
-// Compiled with -fmad=false like the LUT bake: IEEE division / sqrt, acos / atan from include/sky_detmath.h, the shader's operation
-// order, and the textureGrad rule of include/sky_texgrad.h (shared with the oracle and the reference-shader shim), so depth, normal,
-// ORM and the albedo are bit-identical to the oracle -- except where the LOD goes through log2f (CUDA's vs libm's last ulp: a
-// different blend fraction at the 1e-7 level, i.e. at most one RGBA8 code; tests/test_gpu_earth.py states the tolerance).
+// Compiled with -fmad=false like the LUT bake: IEEE division / sqrt, acos / atan / log2 from include/sky_detmath.h, the shader's
+// operation order, and the textureGrad rule of include/sky_texgrad.h (shared with the oracle and the reference-shader shim), so depth,
+// normal, ORM, albedo and every mip level of the map are bit-identical to the oracle (tests/test_gpu_earth.py).
 //
 // Mapping:
 //   * k7_earth_gbuffer: a fragment program takes screen-space derivatives inside 2x2 pixel quads, so a thread block is 16x8 pixels
@@ -136,7 +135,33 @@ __global__ void k7_albedo_mip(const uchar4* src, int sw, int sh, uchar4* dst, in
     dst[i] = make_uchar4(box(t00.x, t10.x, t01.x, t11.x), box(t00.y, t10.y, t01.y, t11.y), box(t00.z, t10.z, t01.z, t11.z), 255);
 }
 
+// Clear(const GBuffer&), GBuffer.h:28-34: one thread per pixel pair, 16-byte stores
+__global__ void __launch_bounds__(256) k_gbuffer_clear(float2* depth, uint2* albedo, uint4* normal, uint4* orm, size_t pairs, float* depth_tail, unsigned* albedo_tail,
+                                                       uint2* normal_tail, uint2* orm_tail) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < pairs) {
+        depth[i] = make_float2(1.0f, 1.0f);
+        albedo[i] = make_uint2(0u, 0u);
+        normal[i] = make_uint4(0u, 0u, 0u, 0u);
+        orm[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (i == pairs && depth_tail) {   // odd pixel count
+        *depth_tail = 1.0f; *albedo_tail = 0u; *normal_tail = make_uint2(0u, 0u); *orm_tail = make_uint2(0u, 0u);
+    }
+}
+
 }  // namespace
+
+int launch_gbuffer_clear(SkyContext* ctx, float* depth, void* albedo, void* normal, void* orm, int width, int height) {
+    const size_t n = size_t(width) * height, pairs = n / 2;
+    const bool odd = (n & 1) != 0;
+    SKY_PERF_MARKER("Clear GBuffer");
+    k_gbuffer_clear<<<unsigned((pairs + 1 + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<float2*>(depth), static_cast<uint2*>(albedo), static_cast<uint4*>(normal), static_cast<uint4*>(orm), pairs,
+        odd ? depth + (n - 1) : nullptr, odd ? static_cast<unsigned*>(albedo) + (n - 1) : nullptr, odd ? static_cast<uint2*>(normal) + (n - 1) : nullptr,
+        odd ? static_cast<uint2*>(orm) + (n - 1) : nullptr);
+    SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 int launch_earth_albedo_mips(SkyContext* ctx, const float* thresholds_dev) {
     int w = ctx->earth_w, h = ctx->earth_h;

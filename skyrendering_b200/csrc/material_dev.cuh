@@ -64,6 +64,17 @@ SKY_D int level_from_log2(float log2_d2, float lod_h, int levels) {
     return !(x < 0.0f) ? -1 : min(d, levels - 1);
 }
 
+// Hardware path: the same decision without the integer level -- `mag` (x >= 0: LINEAR on level 0) and the LOD as the float -floor(x),
+// which the POINT-mip texture object clamps to its last level (maxMipmapLevelClamp, noise.cu) -- 4 instructions instead of 8 + I2F.
+struct HwLod { bool mag; float lod; };
+SKY_D HwLod hw_lod_from_log2(float log2_d2, float lod_h) {
+    const float x = lod_h - 0.5f * log2_d2;
+    HwLod r;
+    r.mag = !(x < 0.0f);
+    r.lod = kFloorMagic - __fadd_rd(x, kFloorMagic);   // -floor(x), exact for |x| < 2^22
+    return r;
+}
+
 // ---- unified fetches ------------------------------------------------------------------------------------
 // One fetch = one tap: cell index + weights.  `level` < 0: LINEAR on level 0 (GL magnification); otherwise NEAREST
 // on that mip level, expressed as the same cell load with zero weights (corner 0 of cell (i,j,k) is texel (i,j,k)),
@@ -175,6 +186,19 @@ SKY_D float4 sample2d_hw(const MipView& t, float u, float v, int level) {
 SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, int level) {
     return level < 0 ? tex3DLod<float>(t.tex_linear, u, v, w, 0.0f) : tex3DLod<float>(t.tex_point, u, v, w, float(level));
 }
+SKY_D float4 sample2d_hw(const MipView& t, float u, float v, HwLod l) {
+    return l.mag ? tex2DLod<float4>(t.tex_linear, u, v, 0.0f) : tex2DLod<float4>(t.tex_point, u, v, l.lod);
+}
+SKY_D float sample3d_hw(const MipView& t, float u, float v, float w, HwLod l) {
+    return l.mag ? tex3DLod<float>(t.tex_linear, u, v, w, 0.0f) : tex3DLod<float>(t.tex_point, u, v, w, l.lod);
+}
+// Production objects, DEFAULT0: fetch the two displacement taps only for evaluations that pass the weather-map early-out (one more
+// dependent texture round trip, ~35 fewer instructions for every evaluation in clear air).  The kernels that run this material are
+// bound by instruction issue as much as by latency; measured, the eager fetch (0) wins.
+#ifndef SKY_M0_LATE_DISPLACEMENT
+#define SKY_M0_LATE_DISPLACEMENT 0   // measured at 4K, scene c3 (profiles/k16_variants_r02n.log): late 383 us, eager 367 us -- the round trip costs more than the instructions
+#endif
+constexpr bool kLateDisplacement = SKY_M0_LATE_DISPLACEMENT != 0;
 
 // ---- SampleSigmaT ------------------------------------------------------------------------------------
 // VolumetricCloudDefaultMaterial0.glsl:9-16
@@ -217,26 +241,27 @@ struct SigmaEval {
             const SkyMaterialCommonBufferData& mc = M.m.common;
             log2_d2 = SKY_LOG2(distance2(pos, M.camera_pos));
             const SkySampleInfo& ci = mc.uCloudMapSampleInfo;
-            int lc = level_from_log2(log2_d2, M.lod_h_cloud_map, M.cloud_map.levels);
             float cu = pos.x * ci.frequency + ci.bias[0], cv = pos.y * ci.frequency + ci.bias[1];
             if (HW) {
-                float4 c = sample2d_hw(M.cloud_map, cu, cv, lc);
+                float4 c = sample2d_hw(M.cloud_map, cu, cv, hw_lod_from_log2(log2_d2, M.lod_h_cloud_map));
                 cloud_type[0] = c.x; cloud_type[1] = c.y;
             } else {
+                int lc = level_from_log2(log2_d2, M.lod_h_cloud_map, M.cloud_map.levels);
                 t_cm = tap2_repeat(M.cloud_map, cu, cv, lc);
                 c_cm = load_cell8(M.cloud_map, t_cm.cell);
             }
-            if (MAT == SKY_MATERIAL_DEFAULT0) {
+            if (MAT == SKY_MATERIAL_DEFAULT0 && !(HW && kLateDisplacement)) {
                 // the displacement fetches do not depend on the weather map: issued with it (one latency, not two),
                 // even though an evaluation that ends at the early-out below drops them
                 const SkySampleInfo& di = mc.uDisplacementSampleInfo;
-                int ld = level_from_log2(log2_d2, M.lod_h_displacement, M.displacement.levels);
                 float du = pos.x * di.frequency + di.bias[0], dv = pos.y * di.frequency + di.bias[1], dw = pos.z * di.frequency;
                 if (HW) {
+                    const HwLod ld = hw_lod_from_log2(log2_d2, M.lod_h_displacement);
                     float4 a = sample2d_hw(M.displacement, du, dv, ld);
                     float4 b = sample2d_hw(M.displacement, du, dw, ld);
                     disp[0] = a.x; disp[1] = a.y; disp[2] = b.z; disp[3] = b.w;
                 } else {
+                    int ld = level_from_log2(log2_d2, M.lod_h_displacement, M.displacement.levels);
                     t_d0 = tap2_repeat(M.displacement, du, dv, ld);
                     t_d1 = tap2_repeat(M.displacement, du, dw, ld);
                     c_d0 = load_cell16(M.displacement, t_d0.cell);
@@ -247,10 +272,10 @@ struct SigmaEval {
             const SkyMaterialVoxelBufferData& m = M.m.u.voxel;
             float u = pos.x * m.uSampleFrequency[0] + m.uSampleBias[0];
             float v = pos.y * m.uSampleFrequency[1] + m.uSampleBias[1];
-            int level = level_from_log2(SKY_LOG2(distance2(pos, M.camera_pos)), M.lod_h_voxel, M.voxel.levels);
             if (HW) {
-                detail = sample3d_hw(M.voxel, u, v, height01, level);
+                detail = sample3d_hw(M.voxel, u, v, height01, hw_lod_from_log2(SKY_LOG2(distance2(pos, M.camera_pos)), M.lod_h_voxel));
             } else {
+                int level = level_from_log2(SKY_LOG2(distance2(pos, M.camera_pos)), M.lod_h_voxel, M.voxel.levels);
                 t_vx = tapb_border(M.voxel, u, v, height01, level);
                 c_vx = load_cellb(M.voxel, t_vx);
             }
@@ -268,18 +293,29 @@ struct SigmaEval {
             need = false;
 #endif
             if (need) {
+                if (HW && kLateDisplacement) {
+                    const SkySampleInfo& di = mc.uDisplacementSampleInfo;
+                    const float du = pos.x * di.frequency + di.bias[0], dv = pos.y * di.frequency + di.bias[1], dw = pos.z * di.frequency;
+                    const HwLod ld = hw_lod_from_log2(log2_d2, M.lod_h_displacement);
+                    const float4 a = sample2d_hw(M.displacement, du, dv, ld), b = sample2d_hw(M.displacement, du, dw, ld);
+                    disp[0] = a.x; disp[1] = a.y; disp[2] = b.z; disp[3] = b.w;
+                }
                 if (!HW) {
                     disp[0] = blend_rgba8(c_d0, 0, t_d0.a, t_d0.b); disp[1] = blend_rgba8(c_d0, 1, t_d0.a, t_d0.b);
                     disp[2] = blend_rgba8(c_d1, 2, t_d1.a, t_d1.b); disp[3] = blend_rgba8(c_d1, 3, t_d1.a, t_d1.b);
                 }
+#ifdef SKY_STRICT_TU   // the shader's literal sum (:24-26), signed zeros included
                 float3 displace_vector = f3(0.0f + disp[0] + disp[2], 0.0f + disp[1], 0.0f + disp[3]);
+#else
+                float3 displace_vector = f3(disp[0] + disp[2], disp[1], disp[3]);
+#endif
                 float3 p = pos + m.uDisplacementScale * displace_vector;
                 const SkySampleInfo& ti = mc.uDetailSampleInfo;
-                int lt = level_from_log2(SKY_LOG2(distance2(p, M.camera_pos)), M.lod_h_detail, M.detail.levels);
                 float tu = p.x * ti.frequency + ti.bias[0], tv = p.y * ti.frequency + ti.bias[1], tw = p.z * ti.frequency;
                 if (HW) {
-                    detail = sample3d_hw(M.detail, tu, tv, tw, lt);
+                    detail = sample3d_hw(M.detail, tu, tv, tw, hw_lod_from_log2(SKY_LOG2(distance2(p, M.camera_pos)), M.lod_h_detail));
                 } else {
+                    int lt = level_from_log2(SKY_LOG2(distance2(p, M.camera_pos)), M.lod_h_detail, M.detail.levels);
                     t_dt = tap3_repeat(M.detail, tu, tv, tw, lt);
                     c_dt = load_cell8(M.detail, t_dt.cell);
                 }
@@ -293,11 +329,11 @@ struct SigmaEval {
             need = !(density == 0);  // :22 returns before the detail fetch
             if (need) {
                 const SkySampleInfo& ti = mc.uDetailSampleInfo;
-                int lt = level_from_log2(log2_d2, M.lod_h_detail, M.detail.levels);
                 float tu = pos.x * ti.frequency + ti.bias[0], tv = pos.y * ti.frequency + ti.bias[1], tw = pos.z * ti.frequency;
                 if (HW) {
-                    detail = sample3d_hw(M.detail, tu, tv, tw, lt);
+                    detail = sample3d_hw(M.detail, tu, tv, tw, hw_lod_from_log2(log2_d2, M.lod_h_detail));
                 } else {
+                    int lt = level_from_log2(log2_d2, M.lod_h_detail, M.detail.levels);
                     t_dt = tap3_repeat(M.detail, tu, tv, tw, lt);
                     c_dt = load_cell8(M.detail, t_dt.cell);
                 }

@@ -189,9 +189,12 @@ class Renderer:
             self._env_brdf_baked = True
         self.ibl = bool(on)
 
-    def ground_pass(self, depth, albedo, normal, orm):
+    def ground_pass(self, depth, albedo, normal, orm, clear=False):
         """Earth::RenderToGBuffer (Earth.cpp:46-65, K7): the analytic ground into the depth plane and the three G-buffer targets
-        (uint8 / int16 / uint16 [H][W][4] in the library's memory space), which it then binds for the composite's object branch."""
+        (uint8 / int16 / uint16 [H][W][4] in the library's memory space), which it then binds for the composite's object branch.
+        clear=True starts from Clear(gbuffer) like AppWindow::RenderGBuffer (AppWindow.cpp:192-200)."""
+        if clear:
+            self.ctx.gbuffer_clear(depth, albedo, normal, orm, self.width, self.height)
         self.earth_buffer = self.scene.earth_buffer()
         self.ctx.earth_gbuffer(self.earth_buffer, depth, albedo, normal, orm, self.width, self.height)
         self.ctx.set_gbuffer(albedo, normal, orm)

@@ -20,6 +20,6 @@ for m in re.finditer(r"Function properties for (\S+)\n\s+(\d+) bytes stack frame
         out.append(f"{tag}: {m.group(4)} regs, {m.group(3)} B spill")
 print(sys.argv[1], "|", "; ".join(out))
 PY
-objs="atmosphere.o composite.o noise.o ibl.o cloud.o pathtrace.o api.o cloud_strict.o pathtrace_strict.o composite_strict.o"
+objs="atmosphere.o composite.o noise.o ibl.o earth.o cloud.o pathtrace.o api.o cloud_strict.o pathtrace_strict.o composite_strict.o"
 objs=${objs/ $tu.o/ /tmp/${tu}_$name.o}
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variant_$name.so $objs -cudart static -ldl
