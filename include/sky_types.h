@@ -207,6 +207,9 @@ typedef struct SkyLutConfig {
                                            (PCSS_ENABLE, AtmosphereRenderer.cpp:99; Shadow.glsl:85-99); needs a G-buffer (sky_set_gbuffer) */
 } SkyLutConfig;
 
+/* Where the row bands of a tile-sharded frame's target go (sky_set_output_gather) */
+enum SkyOutputGather { SKY_GATHER_OFF = 0, SKY_GATHER_ALL = 1, SKY_GATHER_ROOT = 2 };
+
 /* Collision sampling of the path tracer (sky_pt_set_tracking) */
 enum SkyPtTracking {
     SKY_PT_TRACKING_REFERENCE = 0,     /* the reference's global majorant kSigmaTMax: identical random streams (default) */
@@ -299,6 +302,8 @@ enum SkyResource {
     SKY_RES_EARTH_ALBEDO = 31,        /* u8x4   GL_SRGB8 codes (RGBX) of the earth albedo map, ALL levels concatenated (level l =
                                          [max(H >> l, 1)][max(W >> l, 1)]): the upload of sky_set_earth_albedo + glGenerateTextureMipmap
                                          src/Base/src/Textures.cpp:52-58 */
+    SKY_RES_FRAME_HDR = 32,           /* half4  [H][W] the context-owned frame target of a tile-sharded frame (sky_peer_export allocates it,
+                                         sky_set_output_gather): pass its pointer as hdr_dev */
     SKY_RES_COUNT_
 };
 

@@ -151,12 +151,21 @@ int SKY_FN(set_output_bands)(SkyContext* ctx, int band_rows, int band_index, int
 typedef struct SkyPeerHandles {
     unsigned char render[64];    /* cudaIpcMemHandle_t of half4[H/4][W/4] */
     unsigned char distance[64];  /* cudaIpcMemHandle_t of float[H/4][W/4] */
-    unsigned char flags[64];     /* cudaIpcMemHandle_t of unsigned int[SKY_MAX_PEERS] */
+    unsigned char flags[64];     /* cudaIpcMemHandle_t of the arrival / done flag words */
+    unsigned char hdr[64];       /* cudaIpcMemHandle_t of SKY_RES_FRAME_HDR, half4[H][W] (sky_set_output_gather) */
 } SkyPeerHandles;
 #define SKY_MAX_PEERS 8
 int SKY_FN(peer_export)(SkyContext* ctx, SkyPeerHandles* out);
 int SKY_FN(peer_attach)(SkyContext* ctx, int rank, int world_size, const SkyPeerHandles* all_ranks);
 int SKY_FN(peer_detach)(SkyContext* ctx);
+/* The frame target of a tile-sharded frame whose FULL-RES passes are sharded too (sky_set_output_bands): with peers attached and
+ * `hdr_dev` of sky_composite / sky_cloud_frame_end == the context's own SKY_RES_FRAME_HDR (allocated and exported by sky_peer_export),
+ * K18 -- the last writer of a frame -- stores every texel of its row bands straight into the frame targets of the receiving ranks over
+ * NVLink, and cloud_frame_end ends with the same device-side arrival barrier as the K16 exchange: no NCCL all-gather, no host
+ * synchronisation.  mode: SKY_GATHER_OFF (default), SKY_GATHER_ALL (every rank ends with the whole frame), SKY_GATHER_ROOT (rank 0 -- the
+ * rank that displays -- does).  A rank's next frame releases the previous frame's target when its cloud_frame_begin is reached in stream
+ * order: whatever reads the frame must be queued on the caller's stream before that. */
+int SKY_FN(set_output_gather)(SkyContext* ctx, int mode);
 
 /* cloud_frame with HOST buffers: copies depth and hdr in, runs the frame, copies hdr out and
  * synchronises -- the call a host application without device pointers makes. */

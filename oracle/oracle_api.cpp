@@ -470,6 +470,7 @@ int orc_counters_enable(SkyContext* ctx, int enable) {
 int orc_peer_export(SkyContext* ctx, SkyPeerHandles*) { return fail(ctx, "peer memory is a CUDA feature"); }
 int orc_peer_attach(SkyContext* ctx, int, int, const SkyPeerHandles*) { return fail(ctx, "peer memory is a CUDA feature"); }
 int orc_peer_detach(SkyContext*) { return 0; }
+int orc_set_output_gather(SkyContext* ctx, int mode) { return mode == SKY_GATHER_OFF ? 0 : fail(ctx, "peer memory is a CUDA feature"); }
 int orc_pt_set_tracking(SkyContext* ctx, int mode) { return mode == SKY_PT_TRACKING_REFERENCE ? 0 : fail(ctx, "the oracle only implements the reference's tracking"); }
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
 int orc_set_strict_arithmetic(SkyContext*, int) { return 0; }  // the oracle IS the strict arithmetic

@@ -159,7 +159,8 @@ ENV_OFF, ENV_CONST_ENVIRONMENT_MAP, ENV_GROUND_SINGLE_BOUNCE, ENV_GROUND_MULTI_B
  RES_SHADOW_MAP, RES_SHADOW_FROXEL, RES_CHECKERBOARD_DEPTH, RES_INDEX_LINEAR_DEPTH, RES_CLOUD_RENDER,
  RES_CLOUD_DISTANCE, RES_RECONSTRUCT, RES_PT_ACCUM, RES_PT_MASK, RES_VOXEL, RES_CLOUD_MAP_MIPS, RES_DETAIL_MIPS,
  RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS, RES_MESH_SHADOW_MAP, RES_ENV_BRDF_LUT, RES_ENVIRONMENT_MIPS,
- RES_ENV_RADIANCE_SH, RES_PREFILTERED_RADIANCE, RES_EARTH_ALBEDO) = range(32)
+ RES_ENV_RADIANCE_SH, RES_PREFILTERED_RADIANCE, RES_EARTH_ALBEDO, RES_FRAME_HDR) = range(33)
+GATHER_OFF, GATHER_ALL, GATHER_ROOT = range(3)   # SkyOutputGather
 IBL_PREFILTERED_RESOLUTION, IBL_ROUGHNESS_COUNT, ENV_BRDF_LUT_SIZE = 128, 5, 512  # IBL.h:10-11, Textures.cpp:61-62
 FMT_F32, FMT_F16, FMT_U8, FMT_U16, FMT_U64 = range(5)
 _FMT_DTYPE = {FMT_F32: np.float32, FMT_F16: np.float16, FMT_U8: np.uint8, FMT_U16: np.uint16, FMT_U64: np.uint64}
@@ -193,6 +194,7 @@ KERNEL_API = {
     "peer_export": ([_VOIDP], I),
     "peer_attach": ([I, I, _VOIDP], I),
     "peer_detach": ([], I),
+    "set_output_gather": ([I], I),
     "pt_begin": ([P(PathTracingInit)], I),
     "pt_samples": ([P(CloudCommonBufferData), U, U, P(I * 4)], I),
     "pt_resolve": ([U, _VOIDP], I),
@@ -352,17 +354,18 @@ class Context:
     def cloud_frame_end(self, depth, hdr): self._call("cloud_frame_end", _ptr(depth), _ptr(hdr))
     def cloud_frame_host(self, common, cloud, depth, hdr): self._call("cloud_frame_host", C.byref(common), C.byref(cloud), _ptr(depth), _ptr(hdr))
     def peer_export(self):
-        """192 bytes: the CUDA IPC handles of this context's K16 outputs and arrival flags (SkyPeerHandles)."""
-        buf = C.create_string_buffer(192)
+        """256 bytes: the CUDA IPC handles of this context's K16 outputs, arrival flags and frame target (SkyPeerHandles)."""
+        buf = C.create_string_buffer(256)
         self._call("peer_export", buf)
         return buf.raw
 
     def peer_attach(self, rank, world_size, all_handles):
         blob = b"".join(all_handles)
-        assert len(blob) == 192 * world_size
+        assert len(blob) == 256 * world_size
         self._call("peer_attach", rank, world_size, C.c_char_p(blob))
 
     def peer_detach(self): self._call("peer_detach")
+    def set_output_gather(self, mode): self._call("set_output_gather", int(mode))
     def pt_begin(self, init): self._call("pt_begin", C.byref(init))
 
     def pt_samples(self, common, frame_begin, count, region):

@@ -98,6 +98,7 @@ bool resolve(SkyContext* ctx, int resource, ResView& v) {
         case SKY_RES_RECONSTRUCT: v = view_of(ctx->reconstruct[1], 4, SKY_FMT_F16); return true;  // newest after the swap
         case SKY_RES_PT_ACCUM: v = view_of(ctx->pt_accum, 4, SKY_FMT_F32); return true;
         case SKY_RES_PT_MASK: v = view_of(ctx->pt_mask, 1, SKY_FMT_U8); return true;
+        case SKY_RES_FRAME_HDR: v = view_of(ctx->frame_hdr, 4, SKY_FMT_F16); return true;
         case SKY_RES_EARTH_ALBEDO:
             if (!ctx->earth_albedo) return true;
             v.ptr = ctx->earth_albedo; v.w = int(ctx->earth_texels); v.h = 1; v.d = 1; v.ch = 4; v.fmt = SKY_FMT_U8; v.bytes = ctx->earth_texels * 4;
@@ -192,7 +193,8 @@ int sky_ctx_create(int device, void* cuda_stream, SkyContext** out) {
     SkyContext* ctx = new SkyContext();
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
-    if (const char* lit = std::getenv("SKYB200_K16_LITERAL")) ctx->k16_literal = lit[0] == '1';   // A/B switch for measurements (tools/)
+    if (const char* lit = std::getenv("SKYB200_K16_LITERAL")) ctx->k16_literal = lit[0] == '1';
+    if (const char* grp = std::getenv("SKYB200_K16_GROUP")) ctx->k16_group = grp[0] == '4' ? 4 : grp[0] == '8' ? 8 : 0;   // A/B switch for measurements (tools/)
     int rc = 0;
     rc |= alloc_bake_luts(ctx);
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);  // VolumetricCloud.cpp:52,102-105
@@ -236,6 +238,8 @@ void sky_ctx_destroy(SkyContext* ctx) {
     for (cudaEvent_t ev : {ctx->ev_fork, ctx->ev_shadow, ctx->ev_pre_composite, ctx->ev_lane2, ctx->ev_frame_mark[0], ctx->ev_frame_mark[1], ctx->ev_luts_ready, ctx->ev_main_to_lut}) if (ev) cudaEventDestroy(ev);
     free_lut(ctx->alt.shadow_froxel);
     if (ctx->lut_stream) { cudaStreamSynchronize(ctx->lut_stream); cudaStreamDestroy(ctx->lut_stream); }
+    if (ctx->shadow_stream) { cudaStreamSynchronize(ctx->shadow_stream); cudaStreamDestroy(ctx->shadow_stream); }
+    if (ctx->ev_shadow_ready) cudaEventDestroy(ctx->ev_shadow_ready);
     swap_lut_sets(ctx);  // free the alternate set through the same path
     free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->density_h); free_lut(ctx->transmittance); free_lut(ctx->multiscattering);
     free_lut(ctx->sky_lum); free_lut(ctx->sky_trans); free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
@@ -256,6 +260,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     free_lut(ctx->alt.shadow_blurred);
     sky_peer_detach(ctx);
     if (ctx->my_flags) cudaFree(ctx->my_flags);
+    free_lut(ctx->frame_hdr);
     delete ctx;
 }
 
@@ -271,6 +276,11 @@ struct LaneScope {  // launchers issue on ctx->stream: point it at lane2 for the
     ~LaneScope() { ctx->stream = saved; }
 };
 int luts_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lut_stream (frame pipelining)
+    if (ctx->shadow_stream_pending) {
+        SKY_CUDA(ctx, cudaEventRecord(ctx->ev_shadow_ready, ctx->shadow_stream));
+        SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_shadow_ready, 0));
+        ctx->shadow_stream_pending = false;
+    }
     if (!ctx->luts_pending) return 0;
     SKY_CUDA(ctx, cudaEventRecord(ctx->ev_luts_ready, ctx->lut_stream));
     SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_luts_ready, 0));
@@ -281,6 +291,7 @@ int lut_stream_follow_main(SkyContext* ctx) {  // lut_stream is ordered after ev
     if (!ctx->pipelining) return 0;
     SKY_CUDA(ctx, cudaEventRecord(ctx->ev_main_to_lut, ctx->stream));
     SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->ev_main_to_lut, 0));
+    if (ctx->shadow_stream) SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->shadow_stream, ctx->ev_main_to_lut, 0));
     return 0;
 }
 int lanes_join(SkyContext* ctx) {  // the caller's stream is ordered after everything queued on lane2 (and on lut_stream)
@@ -322,7 +333,8 @@ int sky_set_frame_pipelining(SkyContext* ctx, int enable) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         SKY_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->lut_stream, cudaStreamNonBlocking, hi));
-        for (cudaEvent_t* ev : {&ctx->ev_frame_mark[0], &ctx->ev_frame_mark[1], &ctx->ev_luts_ready, &ctx->ev_main_to_lut})
+        SKY_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->shadow_stream, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t* ev : {&ctx->ev_frame_mark[0], &ctx->ev_frame_mark[1], &ctx->ev_luts_ready, &ctx->ev_main_to_lut, &ctx->ev_shadow_ready})
             SKY_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         swap_lut_sets(ctx);                       // allocate the bake LUTs of the second set
         int rc = alloc_bake_luts(ctx);
@@ -454,6 +466,7 @@ int sky_set_viewport(SkyContext* ctx, int w, int h) {
     if (w < 12 || h < 12) return sky_fail(ctx, "viewport too small");
     if (int e = lanes_join(ctx)) return e;
     sky_peer_detach(ctx);  // the exported buffers are about to be reallocated
+    free_lut(ctx->frame_hdr);
     ctx->width = w; ctx->height = h;
     int rc = 0;  // VolumetricCloud.cpp:120-136; histories zero-filled
     rc |= sky_alloc(ctx, ctx->checkerboard_depth, w / 2, h / 2);
@@ -479,8 +492,8 @@ int sky_atmosphere_bake(SkyContext* ctx, const SkyAtmosphereBufferData* a) {
         const int n = ctx->mark_count & 1;
         SKY_CUDA(ctx, cudaEventRecord(ctx->ev_frame_mark[n], ctx->stream));
         swap_lut_sets(ctx);
-        if (ctx->mark_count >= 1) SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->ev_frame_mark[n ^ 1], 0));
-        else SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->ev_frame_mark[n], 0));
+        ctx->frame_gate = ctx->ev_frame_mark[ctx->mark_count >= 1 ? n ^ 1 : n];
+        SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->lut_stream, ctx->frame_gate, 0));
         ++ctx->mark_count;
         ctx->atm = *a;
         ctx->luts_pending = true;
@@ -638,14 +651,23 @@ int sky_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData* common) {
             if (int e = sky_alloc(ctx, other_map, ctx->shadow_maps[2].w, ctx->shadow_maps[2].h)) return e;
             ctx->bake_since_shadow = false;
         }
-        if (!ctx->bake_since_shadow) {  // out-of-protocol call (no bake since the last shadow pass): order conservatively
+        // sharded frame: the chain runs on its own stream (context.h); switching between the two streams orders conservatively once
+        const bool own_stream = ctx->out_band_count > 1 && ctx->shadow_stream != nullptr;
+        if (!ctx->bake_since_shadow || own_stream != ctx->shadow_stream_last) {  // out-of-protocol call (no bake since the last shadow pass) / stream switch
             if (int e = lanes_join(ctx)) return e;
             if (int e = lut_stream_follow_main(ctx)) return e;
         }
+        ctx->shadow_stream_last = own_stream;
         ctx->bake_since_shadow = false;
         std::swap(ctx->shadow_froxel, other);
         std::swap(ctx->shadow_maps[2], other_map);
         ctx->pre_composite_recorded = false;  // a new frame
+        if (own_stream) {
+            if (ctx->frame_gate) SKY_CUDA(ctx, cudaStreamWaitEvent(ctx->shadow_stream, ctx->frame_gate, 0));   // the write set was last read before it
+            ctx->shadow_stream_pending = true;
+            LaneScope lane(ctx, ctx->shadow_stream);
+            return (ctx->strict_arithmetic ? launch_cloud_shadow_strict : launch_cloud_shadow)(ctx, *common);
+        }
         ctx->luts_pending = true;
         LaneScope lane(ctx, ctx->lut_stream);
         return (ctx->strict_arithmetic ? launch_cloud_shadow_strict : launch_cloud_shadow)(ctx, *common);
@@ -709,8 +731,9 @@ int sky_peer_detach(SkyContext* ctx) {
         if (ctx->peer_render[k]) cudaIpcCloseMemHandle(ctx->peer_render[k]);
         if (ctx->peer_distance[k]) cudaIpcCloseMemHandle(ctx->peer_distance[k]);
         if (ctx->peer_flags[k]) cudaIpcCloseMemHandle(ctx->peer_flags[k]);
+        if (ctx->peer_hdr[k]) cudaIpcCloseMemHandle(ctx->peer_hdr[k]);
     }
-    for (int k = 0; k < SKY_MAX_PEERS; ++k) { ctx->peer_render[k] = nullptr; ctx->peer_distance[k] = nullptr; ctx->peer_flags[k] = nullptr; }
+    for (int k = 0; k < SKY_MAX_PEERS; ++k) { ctx->peer_render[k] = nullptr; ctx->peer_distance[k] = nullptr; ctx->peer_flags[k] = nullptr; ctx->peer_hdr[k] = nullptr; }
     ctx->peer_rank = 0; ctx->peer_world = 1; ctx->peer_band_frame = false;
     return 0;
 }
@@ -736,6 +759,10 @@ int sky_peer_export(SkyContext* ctx, SkyPeerHandles* out) {
     std::memcpy(out->distance, &h, 64);
     SKY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->my_flags));
     std::memcpy(out->flags, &h, 64);
+    if (int e = sky_alloc(ctx, ctx->frame_hdr, ctx->width, ctx->height)) return e;   // the frame target peers store their row bands into
+    SKY_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SKY_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->frame_hdr.p));
+    std::memcpy(out->hdr, &h, 64);
     return 0;
 }
 
@@ -750,6 +777,7 @@ int sky_peer_attach(SkyContext* ctx, int rank, int world_size, const SkyPeerHand
             ctx->peer_render[k] = ctx->render_texture.p;
             ctx->peer_distance[k] = ctx->cloud_distance.p;
             ctx->peer_flags[k] = ctx->my_flags;
+            ctx->peer_hdr[k] = ctx->frame_hdr.p;
             continue;
         }
         cudaIpcMemHandle_t h;
@@ -763,6 +791,9 @@ int sky_peer_attach(SkyContext* ctx, int rank, int world_size, const SkyPeerHand
         std::memcpy(&h, all[k].flags, 64);
         SKY_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         ctx->peer_flags[k] = static_cast<unsigned int*>(p);
+        std::memcpy(&h, all[k].hdr, 64);
+        SKY_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_hdr[k] = static_cast<half4*>(p);
     }
     return 0;
 }
@@ -875,6 +906,13 @@ int sky_set_output_bands(SkyContext* ctx, int band_rows, int band_index, int ban
     if (band_count <= 1) { ctx->out_band_rows = 0; ctx->out_band_index = 0; ctx->out_band_count = 1; return 0; }
     if (band_rows < 8 || band_rows % 8 != 0 || band_index < 0 || band_index >= band_count) return sky_fail(ctx, "set_output_bands: band_rows must be a positive multiple of 8 and 0 <= band_index < band_count");
     ctx->out_band_rows = band_rows; ctx->out_band_index = band_index; ctx->out_band_count = band_count;
+    return 0;
+}
+
+int sky_set_output_gather(SkyContext* ctx, int mode) {
+    if (!ctx) return 1;
+    if (mode != SKY_GATHER_OFF && mode != SKY_GATHER_ALL && mode != SKY_GATHER_ROOT) return sky_fail(ctx, "set_output_gather: unknown mode");
+    ctx->out_gather = mode;
     return 0;
 }
 

@@ -68,6 +68,9 @@ struct CloudParams {
     half4* peer_render[8];
     float* peer_distance[8];
     int peer_count;
+    // K18: frame targets of the ranks that receive this rank's row bands (sky_set_output_gather); hdr_peer_count == 0: local only
+    half4* hdr_peers[8];
+    int hdr_peer_count;
 };
 
 SKY_D float DepthToLinearDepth(const SkyCloudCommonBufferData& c, float depth) {  // VolumetricCloudCommon.glsl:32-34
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
 //   stage 3: each group ray's own lane consumes its K steps IN ORDER exactly like the shader's loop body (:134-137, :170-188): running
 //            transmittance, sums, the `break` at kMinTransmittance (steps evaluated past it are discarded: the only speculation,
 //            at most K - 1 steps once per segment), step count and t.
-// A ray's operations are the shader's in the shader's order; only the look-ahead positions are formed as t + k * step with one FMA.
+// A ray's operations are the shader's in the shader's order, the look-ahead t included (k additions of step_size).
 // The critical path of a ray drops from 12 texture round trips per step to <= 3, and lanes are full while rays of a group remain.
 // The strict objects and the counting variant keep k16_render, whose lanes follow the shader's loop literally.
 #ifndef SKY_K16_LOOKAHEAD
@@ -589,11 +592,15 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_OCC * 128 / kK16Block) k16_
 #ifndef SKY_K16_WAVE_OCC
 #define SKY_K16_WAVE_OCC 8    // resident 128-thread blocks per SM: 5 -> 480 us, 8 -> 408 us (64 registers, 20 bytes of spill)
 #endif
+// GR x LA = 32: a warp owns GR rays and looks LA steps ahead.  8 x 4 is the throughput shape (4K on one GPU: instruction issue
+// bounds the kernel); 4 x 8 halves a ray's critical path -- twice the warps, half the round trips per ray -- and is the latency shape,
+// chosen at launch when the rays of the launch cannot fill the machine twice over (a rank's bands of a sharded 4K frame).
 constexpr int kK16MaxTaps = 8, kK16LookAhead = SKY_K16_LOOKAHEAD, kK16GroupRays = 8;
+template <int GR, int LA>
 struct K16WaveScratch {
-    float4 dir[kK16GroupRays];                 // group ray: view_dir.xyz, back lobe
-    float4 state[kK16GroupRays];               // group ray: t, step_size, steps evaluated this round (uint bits), forward lobe
-    float4 out[kK16GroupRays][kK16LookAhead];  // per group ray and look-ahead step: (tr, sun, env, state); state 0 clear, 1 cloud
+    float4 dir[GR];                            // group ray: view_dir.xyz, back lobe
+    float4 state[GR];                          // group ray: t, step_size, steps evaluated this round (uint bits), forward lobe
+    float4 out[GR][LA];                        // per group ray and look-ahead step: (tr, sun, env, state); state 0 clear, 1 cloud
     float4 pos[32];                            // steps with cloud in them, by rank: position
     float res[32 * kK16MaxTaps];               // optical-depth terms of the shadow taps [tap * D + rank]
 };
@@ -622,16 +629,16 @@ __device__ unsigned long long g_k16_stats[8];
 #else
 #define K16_STAT(slot, value) do { } while (0)
 #endif
-template <int MAT, bool HW>
+template <int MAT, bool HW, int GR = kK16GroupRays, int LA = kK16LookAhead>
 __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block) k16_render_wave(const __grid_constant__ CloudParams P, const __grid_constant__ K16Taps taps) {
     const SkyCloudCommonBufferData& c = P.c;
     const SkyCloudBufferData& b = P.b;
-    __shared__ K16WaveScratch scratch[kK16Block / 32];
+    __shared__ K16WaveScratch<GR, LA> scratch[kK16Block / 32];
     __shared__ float tap_mid[kK16MaxTaps], tap_weight[kK16MaxTaps];   // indexed per lane: shared memory, not the constant bank
     __shared__ unsigned int recip[33];   // ceil(2^16 / n): floor(t / n) = (t * recip[n]) >> 16 exactly for t < 256, n <= 32 (task -> (tap, step) without I2F / F2I)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
-    K16WaveScratch& W = scratch[threadIdx.x >> 5];
+    K16WaveScratch<GR, LA>& W = scratch[threadIdx.x >> 5];
     const int n_taps = taps.count;
     if (threadIdx.x < unsigned(kK16MaxTaps)) { tap_mid[threadIdx.x] = taps.mid[threadIdx.x]; tap_weight[threadIdx.x] = taps.weight[threadIdx.x]; }
     if (threadIdx.x < 33u) recip[threadIdx.x] = threadIdx.x ? (65536u + threadIdx.x - 1u) / threadIdx.x : 0u;
@@ -649,7 +656,7 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
     // ---- a warp owns ONE group: 8 rays (a row of 8 quarter-res texels, the block's warps are consecutive rows), held by lanes 0..7.
     //      What a warp does one after the other is what decides the kernel's critical path, so it is one group, not four.
     RaySetup S{};
-    if (lane < unsigned(kK16GroupRays)) S = k16_ray_setup(P, int(blockIdx.x) * kK16GroupRays + int(lane), int(blockIdx.y) * (kK16Block / 32) + warp_in_block);
+    if (lane < unsigned(GR)) S = k16_ray_setup(P, int(blockIdx.x) * GR + int(lane), int(blockIdx.y) * (kK16Block / 32) + warp_in_block);
 #endif
     RayMarchContext ctx;
     ctx.cos_sun_view = S.cos_sun_view;
@@ -684,9 +691,9 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
         const unsigned amask = __ballot_sync(0xffffffffu, marching);
         if (amask == 0) break;
         const int rank = __popc(amask & lt);
-        const bool selected = marching && rank < kK16GroupRays;
-        const int A = min(__popc(amask), kK16GroupRays);
-        const int K = min(32 / A, kK16LookAhead);
+        const bool selected = marching && rank < GR;
+        const int A = min(__popc(amask), GR);
+        const int K = min(32 / A, LA);
         if (selected) {
             W.dir[rank] = f4(S.view_dir, hg_back);
             W.state[rank] = f4(ctx.t, ctx.step_size, __uint_as_float(min(cnt, uint32_t(K))), hg_forward);
@@ -702,7 +709,12 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
         float sigma_t = 0.0f, height01 = 0.0f;
         float3 pos = camera;
         if (valid) {
-            pos = camera + f3(rd.x, rd.y, rd.z) * fmaf(float(k), rs.y, rs.x);   // UpdateContext, :90-93
+            // t of look-ahead step k: the shader's k additions `t += step_size` (:176 / :187), not t + k * step_size -- the positions, and with
+            // them every texel, are then the same whatever (rays per warp, look-ahead) shape the launch uses
+            float tk = rs.x;
+#pragma unroll
+            for (int q = 1; q < LA; ++q) tk += q <= k ? rs.y : 0.0f;
+            pos = camera + f3(rd.x, rd.y, rd.z) * tk;   // UpdateContext, :90-93
             height01 = CalHeight01(P, pos);
             sigma_t = SampleSigmaT<MAT, HW>(P.mat, pos, height01);               // :117
         }
@@ -761,7 +773,11 @@ __global__ void __launch_bounds__(kK16Block, SKY_K16_WAVE_OCC * 128 / kK16Block)
             if (!((cloud_rays >> rank) & 1u)) {
                 // clear air all the way: the transmittance does not change, so `break` fires after the first step or never
                 if (ctx.transmittance < kMinTransmittance) cnt = 0;
-                else { cnt -= n; ctx.t = fmaf(float(n), ctx.step_size, ctx.t); }
+                else {
+                    cnt -= n;
+#pragma unroll
+                    for (int q = 0; q < LA; ++q) ctx.t += uint32_t(q) < n ? ctx.step_size : 0.0f;   // n times `t += step_size`
+                }
             } else {
 #pragma unroll 1
                 for (uint32_t kk = 0; kk < n; ++kk) {
@@ -915,7 +931,9 @@ __global__ void __launch_bounds__(256) k18_upscale(const __grid_constant__ Cloud
     color.x = color.x * k + upscaled.x;
     color.y = color.y * k + upscaled.y;
     color.z = color.z * k + upscaled.z;
-    *dst = to_half4(color);
+    const half4 texel = to_half4(color);
+    *dst = texel;
+    for (int k = 0; k < P.hdr_peer_count; ++k) P.hdr_peers[k][size_t(y) * P.width + x] = texel;   // 8 B per pixel and receiving rank over NVLink
 }
 
 // ------------------------------------------------------------------------------------------------ tex peak
@@ -955,18 +973,21 @@ struct PeerBarrierParams {
     unsigned int* my_flags;
     int rank, world;
     unsigned int epoch;
-    int offset;      // 0: arrival flags, 8: done flags
+    int offset;      // 0: K16 rows arrived, 8: K17 done reading them, 32: frame-target rows arrived, 40: previous frame target released
     int signal, wait;
+    unsigned int signal_mask, wait_mask;   // ranks to signal / to wait for (bit k); 0 = all
 };
 __global__ void __launch_bounds__(32) k_peer_flags(const __grid_constant__ PeerBarrierParams P) {
     int k = threadIdx.x;
     if (k < P.world) {
-        if (P.signal) {
+        const bool do_signal = P.signal && (P.signal_mask == 0u || ((P.signal_mask >> k) & 1u));
+        const bool do_wait = P.wait && (P.wait_mask == 0u || ((P.wait_mask >> k) & 1u));
+        if (do_signal) {
             __threadfence_system();  // this stream's earlier kernels (K16's peer stores / K17's reads) first
             volatile unsigned int* theirs = P.peer_flags[k] + P.offset + P.rank;
             *theirs = P.epoch;
         }
-        if (P.wait) {
+        if (do_wait) {
             volatile unsigned int* mine = P.my_flags + P.offset + k;
             // bounded: a rank that died, skipped a frame or attached out of step must not hang this GPU's stream for ever.
             // After kPeerWaitTimeoutNs the frame goes on with whatever rows arrived and slot SKY_PEER_TIMEOUT_SLOT records the
@@ -1138,6 +1159,13 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
                 B.offset = 8; B.signal = 0; B.wait = 1;
                 k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
                 SKY_LAUNCH_CHECK(ctx);
+                if (ctx->out_gather != SKY_GATHER_OFF) {
+                    // this point follows, in stream order, everything the caller queued to read the previous frame's target: peers may
+                    // overwrite their row bands in it from now on
+                    B.offset = 40; B.signal = 1; B.wait = 0;
+                    k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+                    SKY_LAUNCH_CHECK(ctx);
+                }
             }
             ++ctx->peer_epoch;
         }
@@ -1153,11 +1181,19 @@ int launch_cloud_begin(SkyContext* ctx, const SkyCloudCommonBufferData& c, const
     taps.count = k16_shadow_taps(b.uShadowSteps, taps.mid, taps.weight, kK16MaxTaps);
     // the ray-group wavefront kernel: production object, not counting, a shadow march it can deal out (1..8 taps)
     const bool wave = !count && !ctx->k16_literal && taps.count >= 1 && taps.count <= kK16MaxTaps;
-    const dim3 wave_grid = SKY_K16_WAVE_RAYS == 32 ? grid : dim3(ceil_div(QW, kK16GroupRays), ceil_div(rows, kK16Block / 32));
+    // the latency shape (4 rays x 8 steps per warp) when the launch has fewer 8-ray groups than twice the warps the machine holds (measured,
+    // profiles/k16_group_r02r.log: a rank's bands of an 8-way sharded 4K frame 126 -> 104 us; a whole 1080p frame 135 -> 152 us, so not there)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long groups8 = long(ceil_div(QW, 8)) * rows;
+    const bool narrow = SKY_K16_WAVE_RAYS != 32 && (ctx->k16_group == 4 || (ctx->k16_group == 0 && groups8 < 2l * sms * SKY_K16_WAVE_OCC * (128 / 32)));
+    const int group_rays = narrow ? 4 : kK16GroupRays;
+    const dim3 wave_grid = SKY_K16_WAVE_RAYS == 32 ? grid : dim3(ceil_div(QW, group_rays), ceil_div(rows, kK16Block / 32));
 #endif
     int rc = dispatch_material(ctx->material.type, ctx->hw_filtering, [&]<int MAT, bool HW>() {
         if (count) k16_render<MAT, HW, true><<<grid, kK16Block, 0, ctx->stream>>>(P);
 #ifndef SKY_STRICT_TU
+        else if (wave && narrow) k16_render_wave<MAT, HW, 4, 8><<<wave_grid, kK16Block, 0, ctx->stream>>>(P, taps);
         else if (wave) k16_render_wave<MAT, HW><<<wave_grid, kK16Block, 0, ctx->stream>>>(P, taps);
 #endif
         else k16_render<MAT, HW, false><<<grid, kK16Block, 0, ctx->stream>>>(P);
@@ -1200,8 +1236,34 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
         SKY_PERF_MARKER("Upscale");  // VolumetricCloud.cpp:407
         P.out_band_rows = ctx->out_band_rows; P.out_band_index = ctx->out_band_index; P.out_band_count = ctx->out_band_count;
         const int rows = owned_rows(ctx, P.height);
+        // frame target in peer memory (sky_set_output_gather): K18 is the last writer of a frame, its stores go to the receiving ranks too
+        const bool gather = ctx->out_gather != SKY_GATHER_OFF && ctx->peer_world > 1 && ctx->out_band_count == ctx->peer_world && ctx->out_band_index == ctx->peer_rank &&
+                            ctx->frame_hdr.p && hdr == ctx->frame_hdr.p && ctx->my_flags && ctx->peer_epoch > 0;
+        PeerBarrierParams B{};
+        if (gather) {
+            const bool to_all = ctx->out_gather == SKY_GATHER_ALL;
+            for (int k = 0; k < ctx->peer_world; ++k) {
+                B.peer_flags[k] = ctx->peer_flags[k];
+                if (k != ctx->peer_rank && (to_all || k == 0)) P.hdr_peers[P.hdr_peer_count++] = ctx->peer_hdr[k];
+            }
+            B.my_flags = ctx->my_flags; B.rank = ctx->peer_rank; B.world = ctx->peer_world;
+            const unsigned int receivers = to_all ? 0u : 1u;   // mask of the ranks that receive (0 = all)
+            if (P.hdr_peer_count > 0 && ctx->peer_epoch > 1) {
+                // the receivers must have released the previous frame's target (flag value: the last frame they are done with)
+                B.epoch = ctx->peer_epoch - 1; B.offset = 40; B.signal = 0; B.wait = 1; B.wait_mask = receivers;
+                k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
+                SKY_LAUNCH_CHECK(ctx);
+            }
+        }
         if (rows > 0) k18_upscale<<<dim3(ceil_div(P.width, 32), ceil_div(rows, 8)), 256, 0, ctx->stream>>>(P);
         SKY_LAUNCH_CHECK(ctx);
+        if (gather) {
+            const bool to_all = ctx->out_gather == SKY_GATHER_ALL;
+            const bool receive = to_all || ctx->peer_rank == 0;
+            B.epoch = ctx->peer_epoch; B.offset = 32; B.signal = 1; B.signal_mask = to_all ? 0u : 1u; B.wait = receive ? 1 : 0; B.wait_mask = 0u;
+            k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);   // my rows are in every receiver's target; a receiver waits for everybody's
+            SKY_LAUNCH_CHECK(ctx);
+        }
         std::swap(ctx->reconstruct[0], ctx->reconstruct[1]);  // VolumetricCloud.cpp:421-422
     }
     return 0;

@@ -11,7 +11,7 @@
 constexpr int kMaxMipLevels = 13;
 constexpr int kDensityLutSize = 2048;  // 49 m per texel for a 100 km atmosphere: interpolation error of exp(-h / 1.2 km) 2e-4 relative
 constexpr int kEarthMaxLevels = 15;  // earth albedo map: up to 16384 texels per axis
-constexpr int SKY_PEER_TIMEOUT_SLOT = 16, SKY_PEER_FLAG_SLOTS = 32;  // see k_peer_flags (cloud.cu)  // up to 4096 texels per axis
+constexpr int SKY_PEER_TIMEOUT_SLOT = 16, SKY_PEER_FLAG_SLOTS = 64;  // see k_peer_flags (cloud.cu)  // up to 4096 texels per axis
 
 // A UNORM8 texture with its full mip chain, kept twice: as linear device memory (exact fp32
 // software filtering, the default) and as a CUDA mip-mapped array behind two texture objects
@@ -63,6 +63,7 @@ struct SkyContext {
     bool hw_filtering = false;
     bool strict_arithmetic = false;  // sky_set_strict_arithmetic: route K6, K11-K18, K19/K20 to the *_strict objects
     bool counting = false;
+    int k16_group = 0;               // SKYB200_K16_GROUP=4|8: force the wavefront kernel's rays per warp (0: chosen per launch, cloud.cu)
     bool k16_literal = false;        // SKYB200_K16_LITERAL=1: the production object launches k16_render (one lane = one ray, the shader's loop) instead of k16_render_coop
     int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: rows K6 / K18 own
 
@@ -85,6 +86,12 @@ struct SkyContext {
     bool luts_pending = false;         // lut_stream holds work the caller's stream has not been ordered after
     bool bake_since_shadow = false;    // this frame's bake already ordered lut_stream after the frame before last
     cudaEvent_t ev_main_to_lut = nullptr;
+    // Sharded frames (sky_set_output_bands, band_count > 1): a rank's share of K6 / K16 / K18 is short, so the serial chain on lut_stream --
+    // K1, K2, shadow chain, K3-K5, ~0.4 ms of latency-bound kernels -- becomes the frame time; there the shadow chain gets a stream of its
+    // own (same gate event, same double-buffered outputs), which takes ~0.1 ms off that chain.  On one GPU this was measured to be worse.
+    cudaStream_t shadow_stream = nullptr;
+    cudaEvent_t ev_shadow_ready = nullptr, frame_gate = nullptr;   // frame_gate: the frame mark lut_stream waited for at this frame's bake (borrowed)
+    bool shadow_stream_pending = false, shadow_stream_last = false;
     struct LutSet {                    // the alternate copy of everything sky_atmosphere_bake / sky_atmosphere_luts write
         Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
         Lut<half4> env, transmittance_h, multiscattering_h, density_h;
@@ -183,7 +190,11 @@ struct SkyContext {
     half4* peer_render[8] = {};      // [rank] -> that rank's render_texture (own entry = local pointer)
     float* peer_distance[8] = {};
     unsigned int* peer_flags[8] = {};  // [rank] -> that rank's arrival flags
-    unsigned int* my_flags = nullptr;  // unsigned int[SKY_PEER_FLAG_SLOTS]: [0,8) arrival epochs, [8,16) done epochs (written by peers), [16] timeout
+    unsigned int* my_flags = nullptr;  // unsigned int[SKY_PEER_FLAG_SLOTS]: [0,8) arrival epochs, [8,16) done epochs (written by peers), [16] timeout,
+                                       // [32,40) frame-target rows arrived, [40,48) frame target of the previous frame released
+    Lut<half4> frame_hdr;              // SKY_RES_FRAME_HDR: the exported frame target (sky_set_output_gather)
+    half4* peer_hdr[8] = {};           // [rank] -> that rank's frame_hdr (own entry = local pointer)
+    int out_gather = 0;                // SkyOutputGather
     unsigned int peer_epoch = 0;
     bool peer_band_frame = false;      // the open frame rendered bands into peer memory
 

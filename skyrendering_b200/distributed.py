@@ -94,10 +94,13 @@ class ShardedPathTracer:
 class ShardedCloudFrame:
     """Tile-sharded K16 with an all-gather of its two outputs; everything else replicated."""
 
-    def __init__(self, renderer, rank, world_size, band_rows=8, group=None, fused=None, shard_output=False, output_band_rows=8):
+    def __init__(self, renderer, rank, world_size, band_rows=8, group=None, fused=None, shard_output=False, output_band_rows=8, gather=abi.GATHER_ALL):
         """shard_output: the two FULL-RES passes are sharded too -- K6 (through `composite`) and K18 only touch this rank's
-        row bands (sky_set_output_bands) and `frame` ends with an all-gather of the HDR rows, so every rank ends with the
-        complete frame.  K6 is the largest kernel of a frame; without this only K16 shrinks with the number of GPUs."""
+        row bands (sky_set_output_bands) and `frame` ends with the HDR rows of every rank in the frame target of the receiving
+        ranks (`gather`: GATHER_ALL every rank, GATHER_ROOT rank 0).  K6 is the largest kernel of a frame; without this only K16
+        shrinks with the number of GPUs.  With CUDA contexts the frame target is the context's own SKY_RES_FRAME_HDR in peer
+        memory (sky_set_output_gather): K18 stores its rows into it on every receiver, no collective -- read the frame from
+        `target(hdr)`.  Other bindings (CPU tests) all-gather the rows of the caller's `hdr`."""
         self.r, self.rank, self.world, self.band_rows, self.group = renderer, rank, world_size, band_rows, group
         self.shard_output = bool(shard_output) and world_size > 1
         self.output_band_rows = output_band_rows
@@ -119,10 +122,19 @@ class ShardedCloudFrame:
             dist.all_gather_object(everyone, mine, group=group)
             renderer.ctx.peer_attach(rank, world_size, everyone)
             dist.barrier(group=group)
+        self.gather = gather
+        self._target = None
+        if self.fused and self.shard_output:
+            renderer.ctx.set_output_gather(gather)
+            self._target = resource_tensor(renderer.ctx, abi.RES_FRAME_HDR)[0][0]   # half4 [H][W] alias of the exported frame target
+
+    def target(self, hdr):
+        """The tensor a sharded frame is rendered into: the context's exported frame target (fused peer exchange) or the caller's."""
+        return hdr if self._target is None else self._target
 
     def composite(self, depth, hdr):
         """K6 over this rank's row bands (all rows unless shard_output)."""
-        self.r.ctx.composite(depth, hdr, self.r.width, self.r.height)
+        self.r.ctx.composite(depth, self.target(hdr), self.r.width, self.r.height)
 
     def gather_output(self, hdr):
         """all-gather of the HDR row bands: every rank ends with the whole frame.  hdr: half4 [H][W] (torch tensor on the
@@ -161,9 +173,9 @@ class ShardedCloudFrame:
             return
         ctx.cloud_frame_begin(common, cloud, depth, self.band_rows, self.rank, self.world)
         if self.fused:
-            ctx.cloud_frame_end(depth, hdr)  # waits on the device for every rank's rows, then K17 / K18
-            if self.shard_output:
-                self.gather_output(hdr)
+            # waits on the device for every rank's K16 rows, then K17 / K18; with shard_output K18 stores its row bands into the
+            # receivers' frame targets and the call ends with the device-side arrival barrier (no collective, no host sync)
+            ctx.cloud_frame_end(depth, self.target(hdr))
             return
         for res in (abi.RES_CLOUD_RENDER, abi.RES_CLOUD_DISTANCE):
             t, zc = resource_tensor(ctx, res)

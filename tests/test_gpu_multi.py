@@ -49,8 +49,8 @@ def _worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, f"hdr_{rank}.npy"), hdr.cpu().numpy())
         np.save(os.path.join(out_dir, f"render_{rank}.npy"), r.ctx.read(abi.RES_CLOUD_RENDER))
         dist.barrier()
-        # the same frames with the full-res passes sharded too (K6 + K18 on this rank's row bands, all-gather of the HDR rows),
-        # frames in flight (overlap + pipelining), no host synchronisation inside the loop
+        # the same frames with the full-res passes sharded too (K6 + K18 on this rank's row bands; K18 stores them into every rank's frame
+        # target over peer memory, sky_set_output_gather), frames in flight (overlap + pipelining), no host synchronisation inside the loop
         r2 = Renderer("c3", w, h, library=cuda, device=rank)
         r2.prime()
         r2.ctx.set_frame_overlap(True)
@@ -66,10 +66,30 @@ def _worker(rank, world, port, out_dir):
             scf2.frame(common, cloud, depth, hdr)
         r2.ctx.sync()
         torch.cuda.synchronize()
-        np.save(os.path.join(out_dir, f"hdr_sharded_{rank}.npy"), hdr.cpu().numpy())
+        assert scf2.target(hdr) is not hdr     # the context's exported frame target
+        np.save(os.path.join(out_dir, f"hdr_sharded_{rank}.npy"), scf2.target(hdr).cpu().numpy())
         r2.ctx.set_frame_pipelining(False)
         r2.ctx.set_frame_overlap(False)
         dist.barrier()
+        # ... gathered on rank 0 only (the rank that displays), and through the portable collective path (NCCL all-gather of the rows)
+        for tag, kwargs in (("root", dict(gather=abi.GATHER_ROOT)), ("collective", dict(fused=False))):
+            r3 = Renderer("c3", w, h, library=cuda, device=rank)
+            r3.prime()
+            scf3 = ShardedCloudFrame(r3, rank, world, band_rows=8, shard_output=True, **kwargs)
+            for _ in range(4):
+                hdr.zero_()
+                r3.earth_update()
+                common, cloud, _ = r3.cloud_update(0.0)
+                r3.ctx.cloud_shadow(common)
+                r3.atmosphere_render_luts()
+                scf3.composite(depth, hdr)
+                scf3.frame(common, cloud, depth, hdr)
+            r3.ctx.sync()
+            torch.cuda.synchronize()
+            np.save(os.path.join(out_dir, f"hdr_{tag}_{rank}.npy"), scf3.target(hdr).cpu().numpy())
+            dist.barrier()
+            r3.ctx.peer_detach()
+            dist.barrier()
         # path tracer: split kFrameId range + one all-reduce
         rp = Renderer("c5", 256, 144, library=cuda, device=rank)
         rp.upload_voxels(synthetic_voxel_grid(63, 77, 43))
@@ -100,6 +120,10 @@ def test_two_gpu_sharding_matches_single_gpu(tmp_path):
         assert np.array_equal(np.load(tmp_path / f"render_{k}.npy").astype(np.float32), ref["render"])  # rays are independent
         assert np.array_equal(np.load(tmp_path / f"hdr_{k}.npy").astype(np.float32), ref["hdr"])
         assert np.array_equal(np.load(tmp_path / f"hdr_sharded_{k}.npy").astype(np.float32), ref["hdr"])
+        assert np.array_equal(np.load(tmp_path / f"hdr_collective_{k}.npy").astype(np.float32), ref["hdr"])
+    assert np.array_equal(np.load(tmp_path / "hdr_root_0.npy").astype(np.float32), ref["hdr"])   # rank 0 holds the whole frame
+    own = (np.arange(432) // 8) % 2 == 1                                                              # rank 1 only its own row bands
+    assert np.array_equal(np.load(tmp_path / "hdr_root_1.npy").astype(np.float32)[own], ref["hdr"][own])
     _, _, whole = run_path_trace("c5", 256, 144, abi.cuda_library(), 8, grid=synthetic_voxel_grid(63, 77, 43), max_bounces=8,
                                  region_box_half_width=8.0)
     pts = [np.load(tmp_path / f"pt_{k}.npy")[0] for k in range(world)]

@@ -817,6 +817,23 @@ def test_c5_path_tracer_160x90x64spp_reference_defaults(libs, data):
     assert np.mean(np.all(as_[0] == ao[1], axis=-1)) > 0.5
 
 
+
+def test_k16_wave_shapes_are_bit_identical(libs, monkeypatch):
+    """The wavefront kernel's two launch shapes -- 8 rays x 4 look-ahead steps per warp (throughput) and 4 x 8 (latency: a rank's bands
+    of a sharded frame) -- render the same texels bit for bit: every ray performs the shader's operations in the shader's order, the
+    k additions of step_size behind a look-ahead position included.  (What makes a sharded frame equal the single-GPU frame.)"""
+    cuda, _ = libs
+    outs = {}
+    for group in ("8", "4"):
+        monkeypatch.setenv("SKYB200_K16_GROUP", group)
+        for hw in (False, True):
+            outs[(group, hw)] = run_cloud_frames("c3", 768, 432, cuda, frames=3, device="cuda", hw=hw, move=(0.05, 0.0, 0.02))
+    monkeypatch.delenv("SKYB200_K16_GROUP")
+    for hw in (False, True):
+        a, b = outs[("8", hw)], outs[("4", hw)]
+        for key in ("render", "distance", "reconstruct", "hdr"):
+            assert np.array_equal(a[key], b[key]), (hw, key, float(np.mean(np.all(a[key] == b[key], axis=-1))) if a[key].ndim == 3 else 0)
+
 def test_full_size_frame_determinism_and_layout(libs):
     """4K with the library defaults (exact filtering, one stream): layout, ranges, work bounds and run-to-run determinism."""
     cuda, _ = libs
