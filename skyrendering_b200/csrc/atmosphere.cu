@@ -187,6 +187,12 @@ SKY_D MarchStep march_step(const AtmosphereModel& atm, const LutView& transmitta
     return s;
 }
 
+// Steps evaluated side by side per loop trip (bit-identical for any value, see the loop).  Measured on B200 (profiles/lut_variants_r02t.log,
+// scene c1 / c3, K3-K5): 1 -> 137 / 167 us, 2 -> 163 / 247 us, 4 -> 200 / 277 us -- the extra independent work does not pay for the
+// predicated tail evaluations and the registers, so the shader's own one-step loop stays.
+#ifndef SKY_MARCH_STEPS
+#define SKY_MARCH_STEPS 1
+#endif
 // Atmosphere.glsl:220-295, one thread per march.  MS = MULTISCATTERING_COMPUTE_PROGRAM permutation.
 template <bool MS, bool TEXLUT = false, bool EXTRA = false>
 SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture,
@@ -199,6 +205,36 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
     transmittance = f3(1.0f);
     float3 luminance = f3(0.0f);
     if (MS) { L_f = f3(0.0f); start_i = 0.5f; }
+#if SKY_MARCH_STEPS > 1
+    // SKY_MARCH_STEPS steps per trip.  A step's evaluation (march_step: the exp / sqrt / LUT-fetch chain, ~95 % of the work) depends on
+    // nothing the loop carries -- only the three accumulations below do -- so evaluating steps i, i + 1, ... side by side multiplies the
+    // independent instructions a thread can have in flight.  The LUT kernels are a few warps per SM working through long dependent marches
+    // (K2: two warps per texel, 30 steps), so this is what they are short of.  Same operations on the same operands in the same order:
+    // the same bits.
+    for (float i = start_i; i < SAMPLE_COUNT;) {
+        float idx[SKY_MARCH_STEPS];
+        bool live[SKY_MARCH_STEPS];
+        MarchStep st[SKY_MARCH_STEPS];
+#pragma unroll
+        for (int q = 0; q < SKY_MARCH_STEPS; ++q) {
+            idx[q] = q == 0 ? i : idx[q - 1] + 1.0f;    // the loop's own `++i`
+            live[q] = idx[q] < SAMPLE_COUNT;
+        }
+#pragma unroll
+        for (int q = 0; q < SKY_MARCH_STEPS; ++q)
+            st[q] = march_step<MS, TEXLUT, EXTRA>(atm, transmittance_texture, multiscattering_texture, m, live[q] ? idx[q] : i, earth_center, start_position,
+                                                  view_direction, sun_direction, extras);
+#pragma unroll
+        for (int q = 0; q < SKY_MARCH_STEPS; ++q) {
+            if (live[q]) {
+                luminance += transmittance * st[q].A / st[q].extinction;
+                if (MS) L_f += transmittance * st[q].B / st[q].extinction;
+                transmittance *= st[q].transmittance;
+            }
+        }
+        i = idx[SKY_MARCH_STEPS - 1] + 1.0f;
+    }
+#else
     for (float i = start_i; i < SAMPLE_COUNT; ++i) {
         const MarchStep s = march_step<MS, TEXLUT, EXTRA>(atm, transmittance_texture, multiscattering_texture, m, i, earth_center, start_position,
                                                           view_direction, sun_direction, extras);
@@ -206,6 +242,7 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
         if (MS) L_f += transmittance * s.B / s.extinction;
         transmittance *= s.transmittance;
     }
+#endif
     return luminance;
 }
 
