@@ -676,18 +676,31 @@ def main():
             lk = int(cn[abi.CNT_PT_LOOKUPS])
             free_b, total_b = torch.cuda.mem_get_info()
             traffic = ncu_traffic("k19_path_trace_" + key)
+            # the same launch with the grid read as a plain R8 3-D array through the texture unit (1 B per voxel instead of the 9 B of the
+            # corner-packed cells; 8-bit interpolation weights, so not stream-exact -- a layout comparison, not the headline mode)
+            rl.ctx.set_hw_filtering(True)
+            ms_tex = kernel_ms(lambda: rl.ctx.pt_samples(cl_, 1, spp_l, [0, 0, PT_W, PT_H]), reps=2)
+            rl.ctx.set_hw_filtering(False)
+            traffic_tex = ncu_traffic("k19_path_trace_" + key + "_tex")
             configs[key] = {
                 "workload": f"c5 path tracer {PT_W}x{PT_H}, synthetic {grid_l.shape[2]}x{grid_l.shape[1]}x{grid_l.shape[0]} R8 grid ({grid_l.nbytes / 1e9:.2f} GB of voxels), "
                             f"reference defaults, one launch of {spp_l} kFrameIds",
                 "ms_per_launch": ms_l, "gsamples_per_s": PT_W * PT_H * spp_l / (ms_l * 1e-3) / 1e9,
                 "lookups_per_launch": lk, "lookups_per_path": lk / max(1, int(cn[abi.CNT_PT_PATHS])),
                 "device_memory_in_use_gb": (total_b - free_b) / 1e9, "grid_generate_s": t_gen, "upload_and_pack_s": t_up,
+                # achieved = the MEASURED DRAM bytes of the committed ncu capture of this launch shape over this run's launch time when the capture
+                # exists (profiles/traffic_r02.json), else the 32-byte-sector upper bound
                 "roofline": {"kernel": "k19_path_trace", "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peak_kind,
-                             "achieved": lk * 32 / (ms_l * 1e-3) / 1e9, "frac": lk * 32 / (ms_l * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "achieved": (traffic if traffic is not None else lk * 32) / (ms_l * 1e-3) / 1e9,
+                             "frac": (traffic if traffic is not None else lk * 32) / (ms_l * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "achieved_upper_bound_32B_sectors": lk * 32 / (ms_l * 1e-3) / 1e9,
                              "achieved_algorithmic_8B": lk * 8 / (ms_l * 1e-3) / 1e9, "traffic": traffic,
                              "wasted_traffic_ratio": None if traffic is None else traffic / (lk * 8.0),
                              "note": "upper bound of the DRAM bytes: lookups x one 32-byte sector (the corner-packed cell of a trilinear tap lies in one "
-                                     "sector); lookups that hit L2 (mip levels, coherent primary rays) never reach DRAM -- `traffic` is the measured figure"}}
+                                     "sector); lookups that hit L2 (mip levels, coherent primary rays) never reach DRAM -- `traffic` is the measured figure"},
+                "texture_unit_variant": {"ms_per_launch": ms_tex, "gsamples_per_s": PT_W * PT_H * spp_l / (ms_tex * 1e-3) / 1e9, "traffic": traffic_tex,
+                                         "wasted_traffic_ratio": None if traffic_tex is None else traffic_tex / (lk * 8.0),
+                                         "layout": "R8 3-D CUDA array + mip chain behind two texture objects (1.14 B per voxel)"}}
             del rl, grid_l
             torch.cuda.empty_cache()
 
