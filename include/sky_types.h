@@ -207,6 +207,16 @@ typedef struct SkyLutConfig {
                                            (PCSS_ENABLE, AtmosphereRenderer.cpp:99; Shadow.glsl:85-99); needs a G-buffer (sky_set_gbuffer) */
 } SkyLutConfig;
 
+/* Launch shapes a caller may pin (sky_set_launch_shape) -- the counterpart of GLReloadableComputeProgram's run-time workgroup-size
+ * candidates (src/Base/include/GLReloadableProgram.h:43-59, GUI AppWindow.cpp:529-531).  Results do not depend on the shape. */
+enum SkyKernelId { SKY_KERNEL_K16 = 0 };
+enum SkyK16Shape {
+    SKY_K16_AUTO = 0,       /* chosen per launch from the number of rays (cloud.cu) */
+    SKY_K16_WAVE_8x4 = 1,   /* ray-group wavefront, 8 rays x 4 look-ahead steps per warp: the throughput shape */
+    SKY_K16_WAVE_4x8 = 2,   /* 4 rays x 8 steps: the latency shape (a rank's bands of a sharded frame) */
+    SKY_K16_LITERAL = 3     /* one lane = one ray, the shader's loop (what the strict objects and the counting variant always run) */
+};
+
 /* Where the row bands of a tile-sharded frame's target go (sky_set_output_gather) */
 enum SkyOutputGather { SKY_GATHER_OFF = 0, SKY_GATHER_ALL = 1, SKY_GATHER_ROOT = 2 };
 

@@ -213,6 +213,9 @@ int SKY_FN(write_resource)(SkyContext* ctx, int resource, const void* host_src, 
  * variants; counters live in SKY_RES_COUNTERS and are reset here. */
 int SKY_FN(counters_enable)(SkyContext* ctx, int enable);
 
+/* Pin the launch shape of a kernel that has several (SkyKernelId / SkyK16Shape, sky_types.h); SKY_K16_AUTO restores the per-launch choice. */
+int SKY_FN(set_launch_shape)(SkyContext* ctx, int kernel, int shape);
+
 /* Which filtering the material textures use: 0 = exact fp32 software filtering on gathered
  * texels (default; matches the oracle), 1 = hardware linear filtering (8-bit weights). */
 int SKY_FN(set_hw_filtering)(SkyContext* ctx, int enable);

@@ -161,6 +161,8 @@ ENV_OFF, ENV_CONST_ENVIRONMENT_MAP, ENV_GROUND_SINGLE_BOUNCE, ENV_GROUND_MULTI_B
  RES_DISPLACEMENT_MIPS, RES_VOXEL_MIPS, RES_COUNTERS, RES_MESH_SHADOW_MAP, RES_ENV_BRDF_LUT, RES_ENVIRONMENT_MIPS,
  RES_ENV_RADIANCE_SH, RES_PREFILTERED_RADIANCE, RES_EARTH_ALBEDO, RES_FRAME_HDR) = range(33)
 GATHER_OFF, GATHER_ALL, GATHER_ROOT = range(3)   # SkyOutputGather
+KERNEL_K16 = 0                                    # SkyKernelId
+K16_AUTO, K16_WAVE_8x4, K16_WAVE_4x8, K16_LITERAL = range(4)   # SkyK16Shape
 IBL_PREFILTERED_RESOLUTION, IBL_ROUGHNESS_COUNT, ENV_BRDF_LUT_SIZE = 128, 5, 512  # IBL.h:10-11, Textures.cpp:61-62
 FMT_F32, FMT_F16, FMT_U8, FMT_U16, FMT_U64 = range(5)
 _FMT_DTYPE = {FMT_F32: np.float32, FMT_F16: np.float16, FMT_U8: np.uint8, FMT_U16: np.uint16, FMT_U64: np.uint64}
@@ -195,6 +197,7 @@ KERNEL_API = {
     "peer_attach": ([I, I, _VOIDP], I),
     "peer_detach": ([], I),
     "set_output_gather": ([I], I),
+    "set_launch_shape": ([I, I], I),
     "pt_begin": ([P(PathTracingInit)], I),
     "pt_samples": ([P(CloudCommonBufferData), U, U, P(I * 4)], I),
     "pt_resolve": ([U, _VOIDP], I),
@@ -366,6 +369,7 @@ class Context:
 
     def peer_detach(self): self._call("peer_detach")
     def set_output_gather(self, mode): self._call("set_output_gather", int(mode))
+    def set_launch_shape(self, kernel, shape): self._call("set_launch_shape", int(kernel), int(shape))
     def pt_begin(self, init): self._call("pt_begin", C.byref(init))
 
     def pt_samples(self, common, frame_begin, count, region):

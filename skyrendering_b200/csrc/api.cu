@@ -909,6 +909,14 @@ int sky_set_output_bands(SkyContext* ctx, int band_rows, int band_index, int ban
     return 0;
 }
 
+int sky_set_launch_shape(SkyContext* ctx, int kernel, int shape) {
+    if (!ctx) return 1;
+    if (kernel != SKY_KERNEL_K16 || shape < SKY_K16_AUTO || shape > SKY_K16_LITERAL) return sky_fail(ctx, "set_launch_shape: unknown kernel or shape");
+    ctx->k16_group = shape == SKY_K16_WAVE_8x4 ? 8 : shape == SKY_K16_WAVE_4x8 ? 4 : 0;
+    ctx->k16_literal = shape == SKY_K16_LITERAL;
+    return 0;
+}
+
 int sky_set_output_gather(SkyContext* ctx, int mode) {
     if (!ctx) return 1;
     if (mode != SKY_GATHER_OFF && mode != SKY_GATHER_ALL && mode != SKY_GATHER_ROOT) return sky_fail(ctx, "set_output_gather: unknown mode");

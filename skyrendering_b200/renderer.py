@@ -259,6 +259,25 @@ class Renderer:
         self._pt_frame_cnt = 0
         self._pt_tile = 0
 
+    def path_trace_save(self, path):
+        """Checkpoint of a progressive path-tracing job (the reference keeps the accumulation in a GL texture and loses it
+        on resize / exit): the RGBA32F sum, the number of kFrameIds in it and the PathTracing parameters.  The job is a plain sum over
+        kFrameIds in order, so a resumed job continues bit-identically."""
+        np.savez(path, accum=self.ctx.read(abi.RES_PT_ACCUM), frames=np.int64(self._pt_frame_cnt), size=np.int64([self.width, self.height]),
+                 init=np.frombuffer(bytes(self.pt_init), np.uint8))
+
+    def path_trace_resume(self, path):
+        """Restart from `path_trace_save`: same viewport, same PathTracing parameters, the saved sum and frame count."""
+        d = np.load(path)
+        if tuple(int(v) for v in d["size"]) != (self.width, self.height):
+            raise ValueError(f"checkpoint is {tuple(d['size'])}, renderer is {(self.width, self.height)}")
+        self.pt_init = abi.PathTracingInit.from_buffer_copy(d["init"].tobytes())
+        self.ctx.pt_begin(self.pt_init)
+        self.ctx.write(abi.RES_PT_ACCUM, np.ascontiguousarray(d["accum"], np.float32))
+        self._pt_frame_cnt = int(d["frames"])
+        self._pt_tile = 0
+        return self._pt_frame_cnt
+
     def path_trace_frames(self, common, count, frame_begin=None):
         """`count` full-screen PathTracing::Render calls with sqrt_tile_count == 1."""
         begin = self._pt_frame_cnt + 1 if frame_begin is None else frame_begin

@@ -59,7 +59,7 @@ def to_numpy(x):
 
 
 def run_cloud_frames(scene, width, height, library, frames, device, composite=True, move=None, hw=False, count=False, strict=False,
-                     overlap=False, pipelining=False):
+                     overlap=False, pipelining=False, k16_shape=None):
     """Bake, zero histories, run `frames` HandleDisplayEvent iterations (static camera unless `move`
     gives a per-frame camera delta), return the final HDR and the intermediate buffers.
     overlap / pipelining: the production frame mode bench.py times (sky_set_frame_overlap, sky_set_frame_pipelining)."""
@@ -68,6 +68,8 @@ def run_cloud_frames(scene, width, height, library, frames, device, composite=Tr
         r.ctx.set_hw_filtering(True)
     if strict:
         r.ctx.set_strict_arithmetic(True)
+    if k16_shape is not None:
+        r.ctx.set_launch_shape(abi.KERNEL_K16, k16_shape)
     r.prime()
     if overlap:
         r.ctx.set_frame_overlap(True)

@@ -818,19 +818,19 @@ def test_c5_path_tracer_160x90x64spp_reference_defaults(libs, data):
 
 
 
-def test_k16_wave_shapes_are_bit_identical(libs, monkeypatch):
+def test_k16_wave_shapes_are_bit_identical(libs):
     """The wavefront kernel's two launch shapes -- 8 rays x 4 look-ahead steps per warp (throughput) and 4 x 8 (latency: a rank's bands
     of a sharded frame) -- render the same texels bit for bit: every ray performs the shader's operations in the shader's order, the
     k additions of step_size behind a look-ahead position included.  (What makes a sharded frame equal the single-GPU frame.)"""
     cuda, _ = libs
     outs = {}
-    for group in ("8", "4"):
-        monkeypatch.setenv("SKYB200_K16_GROUP", group)
+    for shape in (abi.K16_WAVE_8x4, abi.K16_WAVE_4x8):   # sky_set_launch_shape: the run-time workgroup-size choice of GLReloadableProgram.h:43-59
         for hw in (False, True):
-            outs[(group, hw)] = run_cloud_frames("c3", 768, 432, cuda, frames=3, device="cuda", hw=hw, move=(0.05, 0.0, 0.02))
-    monkeypatch.delenv("SKYB200_K16_GROUP")
+            outs[(shape, hw)] = run_cloud_frames("c3", 768, 432, cuda, frames=3, device="cuda", hw=hw, move=(0.05, 0.0, 0.02), k16_shape=shape)
+    with pytest.raises(abi.SkyError):
+        outs[(abi.K16_WAVE_8x4, False)]["renderer"].ctx.set_launch_shape(abi.KERNEL_K16, 9)
     for hw in (False, True):
-        a, b = outs[("8", hw)], outs[("4", hw)]
+        a, b = outs[(abi.K16_WAVE_8x4, hw)], outs[(abi.K16_WAVE_4x8, hw)]
         for key in ("render", "distance", "reconstruct", "hdr"):
             assert np.array_equal(a[key], b[key]), (hw, key, float(np.mean(np.all(a[key] == b[key], axis=-1))) if a[key].ndim == 3 else 0)
 

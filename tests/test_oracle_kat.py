@@ -300,3 +300,35 @@ def test_tonemap_known_answers():
         assert np.all(np.abs(out[0, :, 0].astype(np.float64) - want) <= 1), (mode, out[0, :, 0], want)
         assert np.all(out[..., 3] == 255) and out[0, 0, 0] == 0 and out[0, -1, 0] == 255
         assert np.array_equal(out[..., 0], out[..., 1]) and np.array_equal(out[..., 0], out[..., 2])
+
+
+def test_path_tracing_checkpoint_resumes_bit_identically(tmp_path):
+    """Renderer.path_trace_save / path_trace_resume (the reference loses its accumulation texture on resize / exit): a
+    job interrupted after 3 of 6 kFrameIds and resumed in a NEW renderer ends with the accumulator of the uninterrupted job, bit for bit."""
+    from skyrendering_b200.renderer import synthetic_voxel_grid
+    grid = synthetic_voxel_grid(31, 39, 21)
+
+    def start():
+        r = Renderer("c5", 48, 30, library=oracle_library())
+        r.upload_voxels(grid)
+        r.prime()
+        common, _, _ = r.cloud_update(0.0)
+        r.ctx.cloud_shadow(common)
+        r.atmosphere_render_luts()
+        return r, common
+    a, common = start()
+    a.path_trace_begin(max_bounces=4, region_box_half_width=4.0)
+    a.path_trace_frames(common, 6)
+    whole = a.ctx.read(abi.RES_PT_ACCUM)
+    b, common = start()
+    b.path_trace_begin(max_bounces=4, region_box_half_width=4.0)
+    b.path_trace_frames(common, 3)
+    b.path_trace_save(tmp_path / "job.npz")
+    c, common = start()
+    assert c.path_trace_resume(tmp_path / "job.npz") == 3
+    assert c.pt_init.max_bounces == 4
+    assert c.path_trace_frames(common, 3) == 6
+    assert np.array_equal(c.ctx.read(abi.RES_PT_ACCUM), whole) and whole[..., :3].sum() > 0
+    d = Renderer("c5", 64, 30, library=oracle_library())
+    with pytest.raises(ValueError):
+        d.path_trace_resume(tmp_path / "job.npz")
