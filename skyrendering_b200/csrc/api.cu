@@ -162,6 +162,7 @@ static void swap_lut_sets(SkyContext* ctx) {
     SkyContext::LutSet& a = ctx->alt;
     std::swap(ctx->transmittance, a.transmittance); std::swap(ctx->multiscattering, a.multiscattering);
     std::swap(ctx->sky_lum, a.sky_lum); std::swap(ctx->sky_trans, a.sky_trans);
+    std::swap(ctx->sky_lum_h, a.sky_lum_h); std::swap(ctx->sky_trans_h, a.sky_trans_h); std::swap(ctx->ap_lum_h, a.ap_lum_h); std::swap(ctx->ap_trans_h, a.ap_trans_h);
     std::swap(ctx->ap_lum, a.ap_lum); std::swap(ctx->ap_trans, a.ap_trans);
     std::swap(ctx->env, a.env); std::swap(ctx->transmittance_h, a.transmittance_h); std::swap(ctx->multiscattering_h, a.multiscattering_h);
     std::swap(ctx->density_h, a.density_h); std::swap(ctx->density_tex, a.density_tex);
@@ -223,6 +224,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     for (auto& m : ctx->shadow_maps) free_lut(m);
     free_lut(ctx->star_map); if (ctx->srgb_decode) cudaFree(ctx->srgb_decode);
     if (ctx->earth_albedo) cudaFree(ctx->earth_albedo);
+    for (auto& e : ctx->froxel_tex) if (e.tex) cudaDestroyTextureObject(e.tex);
     free_lut(ctx->mesh_shadow_map); free_lut(ctx->shadow_froxel); free_lut(ctx->checkerboard_depth); free_lut(ctx->cloud_distance);
     free_lut(ctx->index_linear_depth); free_lut(ctx->render_texture); free_lut(ctx->reconstruct[0]); free_lut(ctx->reconstruct[1]);
     free_lut(ctx->pt_accum); free_lut(ctx->pt_mask);
@@ -243,6 +245,7 @@ void sky_ctx_destroy(SkyContext* ctx) {
     swap_lut_sets(ctx);  // free the alternate set through the same path
     free_lut(ctx->transmittance_h); free_lut(ctx->multiscattering_h); free_lut(ctx->density_h); free_lut(ctx->transmittance); free_lut(ctx->multiscattering);
     free_lut(ctx->sky_lum); free_lut(ctx->sky_trans); free_lut(ctx->ap_lum); free_lut(ctx->ap_trans); free_lut(ctx->env);
+    free_lut(ctx->sky_lum_h); free_lut(ctx->sky_trans_h); free_lut(ctx->ap_lum_h); free_lut(ctx->ap_trans_h);
     for (cudaTextureObject_t t : {ctx->density_tex, ctx->transmittance_tex, ctx->multiscattering_tex, ctx->sky_lum_tex, ctx->sky_trans_tex, ctx->ap_lum_tex, ctx->ap_trans_tex}) if (t) cudaDestroyTextureObject(t);
     swap_lut_sets(ctx);
     if (ctx->transmittance_tex) cudaDestroyTextureObject(ctx->transmittance_tex);
@@ -475,6 +478,7 @@ int sky_set_viewport(SkyContext* ctx, int w, int h) {
     rc |= sky_alloc(ctx, ctx->cloud_distance, w / 4, h / 4);
     rc |= sky_alloc(ctx, ctx->reconstruct[0], w / 2, h / 2);
     rc |= sky_alloc(ctx, ctx->reconstruct[1], w / 2, h / 2);
+    for (auto& e : ctx->froxel_tex) if (e.tex) { cudaDestroyTextureObject(e.tex); e = SkyContext::FroxelTex{}; }
     rc |= sky_alloc(ctx, ctx->shadow_froxel, w / 12, h / 12, 128);
     for (auto& m : ctx->shadow_maps) rc |= sky_alloc(ctx, m, 512, 512);
     if (ctx->alt.shadow_blurred.p) rc |= sky_alloc(ctx, ctx->alt.shadow_blurred, 512, 512);
@@ -518,22 +522,26 @@ int sky_atmosphere_luts(SkyContext* ctx, const SkyAtmosphereRenderBufferData* r,
     rc |= sky_alloc(ctx, ctx->ap_lum, 32, 32, cfg->aerial_perspective_depth, false);  // AtmosphereRenderer.cpp:19-20
     rc |= sky_alloc(ctx, ctx->ap_trans, 32, 32, cfg->aerial_perspective_depth, false);
     rc |= sky_alloc(ctx, ctx->env, cfg->environment_size, cfg->environment_size, 6, false);
+    rc |= sky_alloc(ctx, ctx->sky_lum_h, cfg->sky_view_width, cfg->sky_view_height, 1, false);
+    rc |= sky_alloc(ctx, ctx->sky_trans_h, cfg->sky_view_width, cfg->sky_view_height, 1, false);
+    rc |= sky_alloc(ctx, ctx->ap_lum_h, 32, 32, cfg->aerial_perspective_depth, false);
+    rc |= sky_alloc(ctx, ctx->ap_trans_h, 32, 32, cfg->aerial_perspective_depth, false);
     if (rc) return rc;
     // texture views for K6 (production object): recreated when sky_alloc moved or resized a LUT
     {
-        Lut<float4>* luts[4] = {&ctx->sky_lum, &ctx->sky_trans, &ctx->ap_lum, &ctx->ap_trans};
+        Lut<half4>* luts[4] = {&ctx->sky_lum_h, &ctx->sky_trans_h, &ctx->ap_lum_h, &ctx->ap_trans_h};   // the RGBA16F copies K3 / K4 write (context.h)
         cudaTextureObject_t* tex[4] = {&ctx->sky_lum_tex, &ctx->sky_trans_tex, &ctx->ap_lum_tex, &ctx->ap_trans_tex};
         for (int i = 0; i < 4; ++i) {
-            const Lut<float4>& l = *luts[i];
+            const Lut<half4>& l = *luts[i];
             if (*tex[i] && ctx->lut_tex_key[i] == l.p && ctx->lut_tex_dims[i][0] == l.w && ctx->lut_tex_dims[i][1] == l.h && ctx->lut_tex_dims[i][2] == l.d) continue;
             if (*tex[i]) { cudaDestroyTextureObject(*tex[i]); *tex[i] = 0; }
             cudaResourceDesc res{};
             res.resType = cudaResourceTypePitch2D;
             res.res.pitch2D.devPtr = l.p;
-            res.res.pitch2D.desc = cudaCreateChannelDesc<float4>();
+            res.res.pitch2D.desc = cudaCreateChannelDescHalf4();
             res.res.pitch2D.width = size_t(l.w);
             res.res.pitch2D.height = size_t(l.h) * size_t(l.d);   // 3-D LUT: its slices stacked
-            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(float4);
+            res.res.pitch2D.pitchInBytes = size_t(l.w) * sizeof(half4);
             cudaTextureDesc td{};
             td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
             td.filterMode = cudaFilterModeLinear;
@@ -887,6 +895,9 @@ int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint
     if (bytes != d.bytes) return sky_fail(ctx, "write_resource: size mismatch, expected " + std::to_string(d.bytes));
     SKY_CUDA(ctx, cudaMemcpyAsync(d.ptr, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (resource == SKY_RES_TRANSMITTANCE || resource == SKY_RES_MULTISCATTERING) { if (int e = launch_lut_half_copies(ctx)) return e; }
+    if (resource == SKY_RES_SKY_VIEW_LUMINANCE || resource == SKY_RES_SKY_VIEW_TRANSMITTANCE || resource == SKY_RES_AERIAL_LUMINANCE || resource == SKY_RES_AERIAL_TRANSMITTANCE) {
+        if (int e = launch_frame_lut_half_copies(ctx)) return e;
+    }
     if (resource == SKY_RES_CLOUD_MAP) { if (int e = launch_mip_chain(ctx, ctx->cloud_map)) return e; }
     if (resource == SKY_RES_DETAIL) { if (int e = launch_mip_chain(ctx, ctx->detail)) return e; }
     if (resource == SKY_RES_DISPLACEMENT) { if (int e = launch_mip_chain(ctx, ctx->displacement)) return e; }

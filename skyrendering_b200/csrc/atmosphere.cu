@@ -509,6 +509,7 @@ struct RenderParams {
     int star_w, star_h;
     const uint16_t* blue_noise;
     float4 *sky_lum_out, *sky_trans_out, *ap_lum_out, *ap_trans_out;
+    half4 *sky_lum_h_out, *sky_trans_h_out, *ap_lum_h_out, *ap_trans_h_out;   // RGBA16F copies for K6's texture fetches (context.h)
     half4* env_out;
     const float* depth;
     half4* hdr;
@@ -617,6 +618,8 @@ SKY_D void k3_sky_view_texel(const RenderParams& P, int x, int y) {
     }
     P.sky_lum_out[y * W + x] = f4(luminance, 0.0f);
     P.sky_trans_out[y * W + x] = f4(transmittance, 0.0f);
+    P.sky_lum_h_out[y * W + x] = to_half4(f4(luminance, 0.0f));
+    P.sky_trans_h_out[y * W + x] = to_half4(f4(transmittance, 0.0f));
 }
 
 // K4 -- AtmosphereRenderer.glsl:191-243
@@ -645,6 +648,8 @@ SKY_D void k4_aerial_perspective_froxel(const RenderParams& P, int x, int y, int
     size_t o = (size_t(z) * H + y) * W + x;
     P.ap_lum_out[o] = f4(luminance, 0.0f);
     P.ap_trans_out[o] = f4(transmittance, 0.0f);
+    P.ap_lum_h_out[o] = to_half4(f4(luminance, 0.0f));
+    P.ap_trans_h_out[o] = to_half4(f4(transmittance, 0.0f));
 }
 
 // K3 and K4 are independent (both read only the bake LUTs) and each is a few hundred 64-thread blocks of long dependent
@@ -958,7 +963,7 @@ __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : LUTONLY ? SKY_
 #endif
         }
     }
-    if (P.froxel.p) luminance *= SampleRayScatterVisibility(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);
+    if (P.froxel.p) luminance *= SampleRayScatterVisibilitySel<kCompositeTexLut>(P.froxel, vTexCoord, marching_distance, P.r.uInvShadowFroxelMaxDistance);
 
     if (intersect_object) {
         if (OBJECT) {  // :404-410
@@ -996,6 +1001,36 @@ __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : LUTONLY ? SKY_
     P.hdr[size_t(py) * P.width + px] = to_half4(f4(luminance, 1.0f));   // FragColor = vec4(luminance, 1.0), :431
 }
 
+// R16-unorm LINEAR view of the current froxel volume (its slices stacked), for K6's production object.  The volume is double-buffered under
+// frame pipelining: two cached views keyed by pointer.  0 when the row pitch does not meet the texture alignment (odd viewports): software path.
+cudaTextureObject_t froxel_texture(SkyContext* ctx) {
+    const Lut<uint16_t>& f = ctx->shadow_froxel;
+    if (!f.p || (size_t(f.w) * sizeof(uint16_t)) % 32 != 0 || size_t(f.h) * f.d > 65536) return 0;
+    for (auto& e : ctx->froxel_tex)
+        if (e.tex && e.key == f.p && e.w == f.w && e.h == f.h && e.d == f.d) return e.tex;
+    SkyContext::FroxelTex* slot = &ctx->froxel_tex[0];
+    for (auto& e : ctx->froxel_tex) if (!e.tex) { slot = &e; break; }
+    if (slot->tex) {   // both slots hold other volumes (a resize): rebuild both lazily
+        for (auto& e : ctx->froxel_tex) { cudaDestroyTextureObject(e.tex); e = SkyContext::FroxelTex{}; }
+        slot = &ctx->froxel_tex[0];
+    }
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypePitch2D;
+    res.res.pitch2D.devPtr = f.p;
+    res.res.pitch2D.desc = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    res.res.pitch2D.width = size_t(f.w);
+    res.res.pitch2D.height = size_t(f.h) * size_t(f.d);
+    res.res.pitch2D.pitchInBytes = size_t(f.w) * sizeof(uint16_t);
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    if (cudaCreateTextureObject(&slot->tex, &res, &td, nullptr) != cudaSuccess) { cudaGetLastError(); slot->tex = 0; return 0; }
+    slot->key = f.p; slot->w = f.w; slot->h = f.h; slot->d = f.d;
+    return slot->tex;
+}
+
 RenderParams make_render_params(SkyContext* ctx) {
     RenderParams P{};
     P.atm.u = ctx->atm;
@@ -1008,11 +1043,12 @@ RenderParams make_render_params(SkyContext* ctx) {
     P.ap_lum = LutView{ctx->ap_lum.p, ctx->ap_lum.w, ctx->ap_lum.h, ctx->ap_lum.d, ctx->ap_lum_tex};
     P.ap_trans = LutView{ctx->ap_trans.p, ctx->ap_trans.w, ctx->ap_trans.h, ctx->ap_trans.d, ctx->ap_trans_tex};
     P.density_tex = ctx->density_tex;
-    P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d};
+    P.froxel = FroxelView{ctx->shadow_froxel.p, ctx->shadow_froxel.w, ctx->shadow_froxel.h, ctx->shadow_froxel.d, froxel_texture(ctx)};
     P.blue_noise = ctx->blue_noise;
     P.star_map = ctx->star_map.p; P.srgb_decode = ctx->srgb_decode; P.star_w = ctx->star_map.w; P.star_h = ctx->star_map.h;
     P.sky_lum_out = ctx->sky_lum.p; P.sky_trans_out = ctx->sky_trans.p;
     P.ap_lum_out = ctx->ap_lum.p; P.ap_trans_out = ctx->ap_trans.p;
+    P.sky_lum_h_out = ctx->sky_lum_h.p; P.sky_trans_h_out = ctx->sky_trans_h.p; P.ap_lum_h_out = ctx->ap_lum_h.p; P.ap_trans_h_out = ctx->ap_trans_h.p;
     P.env_out = ctx->env.p;
     P.extras.moon_shadow = P.cfg.moon_shadow;
     P.extras.moon_radius = P.r.moon_radius;
@@ -1047,6 +1083,19 @@ int launch_lut_half_copies(SkyContext* ctx) {
     k_luts_to_half<<<ceil_div(na + nb + nd, 256), 256, 0, ctx->stream>>>(ctx->transmittance.p, ctx->transmittance_h.p, na, ctx->multiscattering.p,
                                                                           ctx->multiscattering_h.p, nb, ctx->density_h.p, nd, ctx->atm);
     SKY_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ... and of the four per-frame LUTs after sky_write_resource replaced one of them (K3 / K4 write their copies themselves)
+int launch_frame_lut_half_copies(SkyContext* ctx) {
+    struct { const Lut<float4>* src; const Lut<half4>* dst; } pairs[4] = {{&ctx->sky_lum, &ctx->sky_lum_h}, {&ctx->sky_trans, &ctx->sky_trans_h},
+                                                                           {&ctx->ap_lum, &ctx->ap_lum_h}, {&ctx->ap_trans, &ctx->ap_trans_h}};
+    for (auto& pr : pairs) {
+        if (!pr.src->p || !pr.dst->p) continue;
+        const int n = pr.src->w * pr.src->h * pr.src->d;
+        k_luts_to_half<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(pr.src->p, pr.dst->p, n, nullptr, nullptr, 0, nullptr, 0, ctx->atm);
+        SKY_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 

@@ -138,7 +138,20 @@ SKY_D float3 aerial_perspective_uvw(float2 uv, float marching_distance, float ma
 struct FroxelView {
     const uint16_t* p;
     int w, h, d;
+    cudaTextureObject_t tex;   // optional (K6, production object): the slices stacked in one R16 2-D texture over the same memory, 0 = none
 };
+// The same fetch through the texture unit: two bilinear R16-unorm fetches (8-bit weights) + the slice blend in fp32, instead of eight loads,
+// eight conversions and their weights.  v is clamped to the texel centres of its slice (CLAMP_TO_EDGE; keeps the footprint out of the next slice).
+SKY_D float sample_froxel_atlas(const FroxelView& t, float u, float v, float w) {
+    const float z = fminf(fmaxf(w * float(t.d) - 0.5f, -1.0f), float(t.d));   // dist >> froxel range: clamp before the floor
+    const float fz = floorf(z), c = z - fz;
+    const int k0 = clampi(int(fz), 0, t.d - 1), k1 = clampi(int(fz) + 1, 0, t.d - 1);
+    const float hv = 0.5f / float(t.h);
+    const float vc = fminf(fmaxf(v, hv), 1.0f - hv);
+    const float inv_d = 1.0f / float(t.d);
+    const float a = tex2D<float>(t.tex, u, (float(k0) + vc) * inv_d), b = tex2D<float>(t.tex, u, (float(k1) + vc) * inv_d);
+    return a + c * (b - a);
+}
 SKY_D float sample_froxel(const FroxelView& t, float u, float v, float w) {
     float x = u * float(t.w) - 0.5f, y = v * float(t.h) - 0.5f, z = w * float(t.d) - 0.5f;
     float fx = floorf(x), fy = floorf(y), fz = floorf(z);
@@ -165,6 +178,12 @@ SKY_D float sample_froxel(const FroxelView& t, float u, float v, float w) {
 SKY_D float SampleRayScatterVisibility(const FroxelView& froxel, float2 uv, float dist, float inv_max_dist) {
     float w = dist * inv_max_dist;
     return mixf(1.0f, sample_froxel(froxel, uv.x, uv.y, w), clampf(1.0f / w, 0.0f, 1.0f));
+}
+template <bool TEXLUT>
+SKY_D float SampleRayScatterVisibilitySel(const FroxelView& froxel, float2 uv, float dist, float inv_max_dist) {
+    if (!TEXLUT || !froxel.tex) return SampleRayScatterVisibility(froxel, uv, dist, inv_max_dist);
+    float w = dist * inv_max_dist;
+    return mixf(1.0f, sample_froxel_atlas(froxel, uv.x, uv.y, w), clampf(1.0f / w, 0.0f, 1.0f));
 }
 
 template <bool TEXLUT>

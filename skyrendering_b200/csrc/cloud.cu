@@ -195,39 +195,51 @@ __global__ void __launch_bounds__(128) k12_blur(const float2* __restrict__ in, f
 }
 
 // ------------------------------------------------------------------------------------------------ K13
-// VolumetricCloudShadowFroxel.comp:10-27: running mean of cloud-shadow transmittance along each view
-// ray.  The sum stays sequential per column (reference order); the shadow-map taps do not depend on
-// it, so the loop is unrolled to keep 8 taps in flight.
-__global__ void __launch_bounds__(64) k13_shadow_froxel(const __grid_constant__ CloudParams P) {
+// VolumetricCloudShadowFroxel.comp:10-27: running mean of cloud-shadow transmittance along each view ray.
+// Only the sum is sequential; the shadow-map taps (a projection + a bilinear RG32F fetch each, all of the work) depend on the slice index
+// alone.  One thread per column walking its 128 slices -- the shader's mapping -- is a handful of warps per SM in a long dependent loop
+// (ncu profiles/k13_r02v.md: 76 us at 4K, occupancy 15 %, 0.59 eligible warps; 1080p is a quarter of the columns and takes as long).
+// So a block takes 32 columns x kK13Slabs slabs of slices: warp g evaluates the taps of slab g for the block's 32 columns into shared
+// memory (its t is the shader's running `t += step_size`, advanced to the slab's first slice), then warp 0 -- one lane per column --
+// adds them in slice order, and every warp turns its slab's sums into means and stores them.  Same operations on the same operands in the same order as the serial loop: bit-identical.
+constexpr int kK13Slabs = 8, kK13Columns = 32, kK13MaxDepth = 128;
+__global__ void __launch_bounds__(kK13Slabs * kK13Columns, 3) k13_shadow_froxel(const __grid_constant__ CloudParams P) {
     const SkyCloudCommonBufferData& c = P.c;
     const int FW = P.froxel.w, FH = P.froxel.h, FD = P.froxel.d;
-    int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
-    if (gx >= FW || gy >= FH) return;
-    float2 uv = f2((float(gx) + 0.5f) / float(FW), (float(gy) + 0.5f) / float(FH));
-    float3 camera = f3(c.uCameraPos);
-    float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 0.0f));
-    float step_size = c.uShadowFroxelMaxDistance / float(FD);
-    float3 dir = normalize(frag_pos - camera);
-    float t = 0.5f * step_size;
-    float transmittance_sum = 0.0f;
-    for (int z0 = 0; z0 < FD; z0 += 8) {
-        float tap[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
+    __shared__ float taps[kK13MaxDepth][kK13Columns];
+    const int col = threadIdx.x & (kK13Columns - 1), slab = threadIdx.x / kK13Columns;
+    const int gx = blockIdx.x * kK13Columns + col, gy = blockIdx.y;
+    const int per_slab = (FD + kK13Slabs - 1) / kK13Slabs, z_begin = slab * per_slab, z_end = min(z_begin + per_slab, FD);
+    if (gx < FW) {
+        float2 uv = f2((float(gx) + 0.5f) / float(FW), (float(gy) + 0.5f) / float(FH));
+        float3 camera = f3(c.uCameraPos);
+        float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, 0.0f));
+        float step_size = c.uShadowFroxelMaxDistance / float(FD);
+        float3 dir = normalize(frag_pos - camera);
+        float t = 0.5f * step_size;
+        for (int z = 0; z < z_begin; ++z) t += step_size;   // the serial loop's t at this slab's first slice
+#pragma unroll 4
+        for (int z = z_begin; z < z_end; ++z) {
             float3 pos = camera + t * dir;
             t += step_size;
             float3 light_ndc = projective_mul(c.uLightVP, pos);
-            tap[k] = (z0 + k < FD) ? SampleCloudShadowTransmittance(P.shadow_blurred, P.shadow_w, P.shadow_h, light_ndc) : 0.0f;
+            taps[z][col] = SampleCloudShadowTransmittance(P.shadow_blurred, P.shadow_w, P.shadow_h, light_ndc);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int z = z0 + k;
-            if (z < FD) {
-                transmittance_sum += tap[k];
-                float ray_scatter_visibility = transmittance_sum / float(z + 1);
-                P.froxel_out[(size_t(z) * FH + gy) * FW + gx] = uint16_t(__float2int_rn(clampf(ray_scatter_visibility, 0.0f, 1.0f) * 65535.0f));
-            }
+    }
+    __syncthreads();
+    if (slab == 0) {   // the running sum, in slice order, one lane per column; the sums replace the taps
+        float transmittance_sum = 0.0f;
+#pragma unroll 8
+        for (int z = 0; z < FD; ++z) {
+            transmittance_sum += taps[z][col];
+            taps[z][col] = transmittance_sum;
         }
+    }
+    __syncthreads();
+    if (gx >= FW) return;
+    for (int z = z_begin; z < z_end; ++z) {   // mean, quantisation and store of this slab's slices: independent again
+        float ray_scatter_visibility = taps[z][col] / float(z + 1);
+        P.froxel_out[(size_t(z) * FH + gy) * FW + gx] = uint16_t(__float2int_rn(clampf(ray_scatter_visibility, 0.0f, 1.0f) * 65535.0f));
     }
 }
 
@@ -1118,7 +1130,8 @@ int launch_cloud_shadow(SkyContext* ctx, const SkyCloudCommonBufferData& c) {
     nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
     SKY_PERF_MARKER("VolumetricCloudShadowFroxel");  // :316
-    k13_shadow_froxel<<<dim3(ceil_div(P.froxel.w, 64), P.froxel.h), 64, 0, ctx->stream>>>(P);
+    if (P.froxel.d > kK13MaxDepth) return sky_fail(ctx, "shadow froxel volume deeper than 128 slices");
+    k13_shadow_froxel<<<dim3(ceil_div(P.froxel.w, kK13Columns), P.froxel.h), kK13Slabs * kK13Columns, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;
 }

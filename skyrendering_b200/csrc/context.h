@@ -94,7 +94,7 @@ struct SkyContext {
     bool shadow_stream_pending = false, shadow_stream_last = false;
     struct LutSet {                    // the alternate copy of everything sky_atmosphere_bake / sky_atmosphere_luts write
         Lut<float4> transmittance, multiscattering, sky_lum, sky_trans, ap_lum, ap_trans;
-        Lut<half4> env, transmittance_h, multiscattering_h, density_h;
+        Lut<half4> env, transmittance_h, multiscattering_h, density_h, sky_lum_h, sky_trans_h, ap_lum_h, ap_trans_h;
         Lut<uint16_t> shadow_froxel;   // second froxel volume: the shadow chain of frame N+1 also runs on lut_stream
         Lut<float2> shadow_blurred;    // second blurred cloud shadow map (shadow_maps[2]): the object branch of frame N's K6 samples
                                        // it on the caller's stream while K12 of frame N+1 writes the other one on lut_stream
@@ -139,10 +139,15 @@ struct SkyContext {
     // boundary, LINEAR + CLAMP): one TEX instead of two MUFU.EX2 and eight ALU instructions per step.  Rebuilt with every bake.
     Lut<half4> density_h;
     cudaTextureObject_t density_tex = 0;
-    // LINEAR views of the per-frame LUTs for K6's look-ups: sky view as 2-D, aerial perspective as a 32 x (32 D) atlas of its slices
+    // LINEAR views of the per-frame LUTs for K6's look-ups: sky view as 2-D, aerial perspective as a 32 x (32 D) atlas of its slices.  They sit
+    // over RGBA16F copies that K3 / K4 write beside the RGBA32F LUTs: a LUT-only composite (scenes c1 / c2) is bound by the L1/TEX pipe on 128-bit
+    // texels (ncu profiles/k6c2_r02v.md: 78.6 % of its peak), 64-bit texels filter at twice the rate; K6's output is RGBA16F anyway
+    Lut<half4> sky_lum_h, sky_trans_h, ap_lum_h, ap_trans_h;
     cudaTextureObject_t sky_lum_tex = 0, sky_trans_tex = 0, ap_lum_tex = 0, ap_trans_tex = 0;
     const void* lut_tex_key[4] = {nullptr, nullptr, nullptr, nullptr};
     int lut_tex_dims[4][3] = {};
+    struct FroxelTex { cudaTextureObject_t tex = 0; const void* key = nullptr; int w = 0, h = 0, d = 0; };
+    FroxelTex froxel_tex[2];         // LINEAR R16 views of the (double-buffered) froxel volume for K6, see froxel_texture (atmosphere.cu)
     uint16_t* blue_noise = nullptr;  // 64x64 u16
 
     // materials
@@ -252,6 +257,7 @@ inline int owned_rows(const SkyContext* ctx, int h) {
     return n;
 }
 int launch_lut_half_copies(SkyContext* ctx);                                  // atmosphere.cu
+int launch_frame_lut_half_copies(SkyContext* ctx);                            // atmosphere.cu
 int launch_atmosphere_bake(SkyContext* ctx);                                   // atmosphere.cu  K1,K2
 int launch_atmosphere_luts(SkyContext* ctx);                                   // atmosphere.cu  K3,K4,K5
 int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int h);  // atmosphere.cu K6
