@@ -182,6 +182,9 @@ enum : int {
 #ifndef SKY_K19_TRACK_ROUNDS
 #define SKY_K19_TRACK_ROUNDS 8
 #endif
+#ifndef SKY_K19_MIN_TRACKING
+#define SKY_K19_MIN_TRACKING 1
+#endif
 #ifndef SKY_K19_BATCH
 #define SKY_K19_BATCH 4
 #endif
@@ -366,7 +369,13 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
         // without a lookup.  Divisions by the constant majorant are multiplications by its reciprocal.
 #pragma unroll 1
         for (int round = 0; round < kTrackRounds; ++round) {
+#if SKY_K19_MIN_TRACKING > 1
+            // leave the hot block once fewer than SKY_K19_MIN_TRACKING lanes still track: the others idle here until the state
+            // transitions below run (results do not depend on it: every path consumes its own stream)
+            if (__popc(__ballot_sync(0xffffffffu, state == ST_TRACK)) < (round == 0 ? 1 : SKY_K19_MIN_TRACKING)) break;
+#else
             if (!__any_sync(0xffffffffu, state == ST_TRACK)) break;
+#endif
             if (state == ST_TRACK) {
                 const float3 dir = in_shadow ? sun : rd;
                 // (1) branch-free: the next kBatch collision distances and stream positions.  Entries past the end of

@@ -22,4 +22,6 @@ for spp in [int(x) for x in os.environ.get("SPP", "2,8,32").split(",")]:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); r.ctx.pt_samples(common, 1, spp, [0, 0, 1280, 720]); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"grid x{scale} {os.environ.get('SKYB200_LIB','default').split('/')[-1]} HW={os.environ.get('HW','0')} spp={spp}: {ms:.1f} ms  {1280*720*spp/ms/1e3:.2f} Msamples/s", flush=True)
+    import hashlib
+    digest = hashlib.sha256(r.ctx.read(abi.RES_PT_ACCUM).tobytes()).hexdigest()[:12] if os.environ.get("DIGEST") else ""
+    print(f"grid x{scale} {os.environ.get('SKYB200_LIB','default').split('/')[-1]} HW={os.environ.get('HW','0')} spp={spp}: {ms:.1f} ms  {1280*720*spp/ms/1e3:.2f} Msamples/s {digest}", flush=True)
