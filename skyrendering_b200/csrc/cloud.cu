@@ -830,74 +830,83 @@ SKY_D float4 sample_half4_linear_clamp(const half4* p, int w, int h, float u, fl
     return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
 }
 
+// One thread per QUARTER-res cell = the 2x2 half-res pixels that share it: the nine-texel neighbourhood of the quarter-res render (loads,
+// Reinhard), its nine linear depths, the cell's cloud distance and shading index are the same for all four pixels, which the shader's
+// one-invocation-per-pixel mapping fetches and tone-maps four times (ncu profiles/k17_r02v.md: 663 instructions per pixel, ALU pipe 50 %,
+// XU 32 %, 96 registers).  Every pixel still performs the shader's operations on the same operands in the same order.
 __global__ void __launch_bounds__(128) k17_reconstruct(const __grid_constant__ CloudParams P) {
     const SkyCloudCommonBufferData& c = P.c;
     const int QW = P.width / 4, QH = P.height / 4, HW_ = P.width / 2, HH = P.height / 2;
-    int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 8 + (threadIdx.x >> 4);
-    if (x >= HW_ || y >= HH) return;
-    int qx = x >> 1, qy = y >> 1;
-    float2 uv = f2((float(x) + 0.5f) / float(HW_), (float(y) + 0.5f) / float(HH));
-    float depth = __ldg(P.checkerboard + size_t(y) * HW_ + x);
-    float linear_depth = DepthToLinearDepth(c, depth);
+    const int qx = blockIdx.x * 16 + (threadIdx.x & 15), qy = blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (2 * qx >= HW_ || 2 * qy >= HH) return;
     // kOffsets, :35
     const int ox[9] = {0, 0, 1, 1, 1, 0, -1, -1, -1}, oy[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1};
-    float rendered_linear_depths[9], delta_linear_depths[9];
-    float min_delta_linear_depth = 1e10f;
-    int nearest_i = 0;
+    float rendered_linear_depths[9];
+    float4 taps[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         // the two textureGathers + two texelFetchClamps of :37-49 read exactly these clamped texels
         int tx = clampi(qx + ox[i], 0, QW - 1), ty = clampi(qy + oy[i], 0, QH - 1);
         rendered_linear_depths[i] = __ldg(P.index_linear + size_t(ty) * QW + tx).y;
-        delta_linear_depths[i] = fabsf(rendered_linear_depths[i] - linear_depth);
-        if (delta_linear_depths[i] < min_delta_linear_depth) {
-            min_delta_linear_depth = delta_linear_depths[i];
-            nearest_i = i;
-        }
-    }
-    float4 taps[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        int tx = clampi(qx + ox[i], 0, QW - 1), ty = clampi(qy + oy[i], 0, QH - 1);
         taps[i] = Reinhard(load_half4(P.render + size_t(ty) * QW + tx));
     }
-    float4 rendered_nearest = taps[0];
+    const int cqx = clampi(qx, 0, QW - 1), cqy = clampi(qy, 0, QH - 1);
+    const float rendered_distance = __ldg(P.cloud_distance + size_t(cqy) * QW + cqx);
+    const int rendered_index = int(__ldg(P.index_linear + size_t(cqy) * QW + cqx).x);
+    const int2 roff = IndexToOffset(uint32_t(rendered_index));
+    const float3 camera = f3(c.uCameraPos);
+#pragma unroll 1
+    for (int sub = 0; sub < 4; ++sub) {
+        const int x = 2 * qx + (sub & 1), y = 2 * qy + (sub >> 1);
+        if (x >= HW_ || y >= HH) continue;
+        float2 uv = f2((float(x) + 0.5f) / float(HW_), (float(y) + 0.5f) / float(HH));
+        float depth = __ldg(P.checkerboard + size_t(y) * HW_ + x);
+        float linear_depth = DepthToLinearDepth(c, depth);
+        float delta_linear_depths[9];
+        float min_delta_linear_depth = 1e10f;
+        int nearest_i = 0;
 #pragma unroll
-    for (int i = 1; i < 9; ++i) if (i == nearest_i) rendered_nearest = taps[i];
-    float4 aabb_min = rendered_nearest, aabb_max = rendered_nearest;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        float4 rendered = taps[i];
-        if (delta_linear_depths[i] < rendered_linear_depths[i] * 0.3f ||
-            fabsf(rendered.w - rendered_nearest.w) / fmaxf(1e-6f, 1 - fmaxf(rendered.w, rendered_nearest.w)) < 0.2f) {
-            aabb_min = min4(aabb_min, rendered);
-            aabb_max = max4(aabb_max, rendered);
+        for (int i = 0; i < 9; ++i) {
+            delta_linear_depths[i] = fabsf(rendered_linear_depths[i] - linear_depth);
+            if (delta_linear_depths[i] < min_delta_linear_depth) {
+                min_delta_linear_depth = delta_linear_depths[i];
+                nearest_i = i;
+            }
         }
-    }
-    float4 rendered = taps[0];
-    float3 camera = f3(c.uCameraPos);
-    float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
-    float3 view_dir = normalize(frag_pos - camera);
-    int cqx = clampi(qx, 0, QW - 1), cqy = clampi(qy, 0, QH - 1);
-    float rendered_distance = __ldg(P.cloud_distance + size_t(cqy) * QW + cqx);
-    float3 cloud_pos = camera + view_dir * rendered_distance;
-    float3 pre = projective_mul(c.uReprojectMat, cloud_pos);
-    float2 pre_uv = f2(pre.x * 0.5f + 0.5f, pre.y * 0.5f + 0.5f);
-    float4 pre_frame = Reinhard(sample_half4_linear_clamp(P.reconstruct_prev, HW_, HH, pre_uv.x, pre_uv.y));
-    pre_frame = min4(max4(pre_frame, aabb_min), aabb_max);
+        float4 rendered_nearest = taps[0];
+#pragma unroll
+        for (int i = 1; i < 9; ++i) if (i == nearest_i) rendered_nearest = taps[i];
+        float4 aabb_min = rendered_nearest, aabb_max = rendered_nearest;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            float4 rendered = taps[i];
+            if (delta_linear_depths[i] < rendered_linear_depths[i] * 0.3f ||
+                fabsf(rendered.w - rendered_nearest.w) / fmaxf(1e-6f, 1 - fmaxf(rendered.w, rendered_nearest.w)) < 0.2f) {
+                aabb_min = min4(aabb_min, rendered);
+                aabb_max = max4(aabb_max, rendered);
+            }
+        }
+        float4 rendered = taps[0];
+        float3 frag_pos = projective_mul(c.uInvMVP, f3(uv.x * 2.0f - 1.0f, uv.y * 2.0f - 1.0f, depth * 2.0f - 1.0f));
+        float3 view_dir = normalize(frag_pos - camera);
+        float3 cloud_pos = camera + view_dir * rendered_distance;
+        float3 pre = projective_mul(c.uReprojectMat, cloud_pos);
+        float2 pre_uv = f2(pre.x * 0.5f + 0.5f, pre.y * 0.5f + 0.5f);
+        float4 pre_frame = Reinhard(sample_half4_linear_clamp(P.reconstruct_prev, HW_, HH, pre_uv.x, pre_uv.y));
+        pre_frame = min4(max4(pre_frame, aabb_min), aabb_max);
 
-    bool is_pre_out_of_screen = fmaxf(fabsf(pre.x), fabsf(pre.y)) > 1.0f;
-    int rendered_index = int(__ldg(P.index_linear + size_t(cqy) * QW + cqx).x);
-    int2 roff = IndexToOffset(uint32_t(rendered_index));
-    bool is_rendered = ((x & 1) == roff.x) && ((y & 1) == roff.y);
-    float rendered_weight = is_pre_out_of_screen ? 1.0f : is_rendered ? 0.2f : 0.0f;
-    float4 reconstructed = InverseReinhard(mix4(pre_frame, rendered, rendered_weight));
-    P.reconstruct_out[size_t(y) * HW_ + x] = to_half4(reconstructed);
+        bool is_pre_out_of_screen = fmaxf(fabsf(pre.x), fabsf(pre.y)) > 1.0f;
+        bool is_rendered = ((x & 1) == roff.x) && ((y & 1) == roff.y);
+        float rendered_weight = is_pre_out_of_screen ? 1.0f : is_rendered ? 0.2f : 0.0f;
+        float4 reconstructed = InverseReinhard(mix4(pre_frame, rendered, rendered_weight));
+        P.reconstruct_out[size_t(y) * HW_ + x] = to_half4(reconstructed);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K18
 // VolumetricCloudUpscale.comp:11-55: depth-aware 4-tap upscale and composite over the HDR target.
-// HBM-bound: 4 B depth + 8 B hdr read + 8 B hdr write per full-res pixel.
+// HBM-bound: 4 B depth + 8 B hdr read + 8 B hdr write per full-res pixel.  (One thread per 2x2 pixel block -- 9 shared half-res texels
+// instead of 16, 16-byte HDR accesses -- was measured and is slower, 65 vs 57 us at 4K: a quarter of the threads in flight.)
 __global__ void __launch_bounds__(256) k18_upscale(const __grid_constant__ CloudParams P) {
     const SkyCloudCommonBufferData& c = P.c;
     const int HW_ = P.width / 2, HH = P.height / 2;
@@ -1237,7 +1246,7 @@ int launch_cloud_end(SkyContext* ctx, const SkyCloudCommonBufferData& c, const f
             SKY_LAUNCH_CHECK(ctx);
             ctx->peer_band_frame = false;
         }
-        k17_reconstruct<<<dim3(ceil_div(HW_, 16), ceil_div(HH, 8)), 128, 0, ctx->stream>>>(P);
+        k17_reconstruct<<<dim3(ceil_div(ceil_div(HW_, 2), 16), ceil_div(ceil_div(HH, 2), 8)), 128, 0, ctx->stream>>>(P);
         if (peer_frame) {
             B.offset = 8; B.signal = 1; B.wait = 0;  // K17 was the last reader of the exchanged buffers
             k_peer_flags<<<1, 32, 0, ctx->stream>>>(B);
