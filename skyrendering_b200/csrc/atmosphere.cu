@@ -262,7 +262,10 @@ SKY_D float3 ComputeScatteredLuminance(const AtmosphereModel& atm, const LutView
 //   * every uniform-only factor (phase x scattering x solar illuminance, log2(e) / scale height, LUT texel insets) is folded once per ray.
 // The strict object keeps the shader's statement order (bit-level parity); this one is checked against the oracle at frame tolerance
 // (tests/test_gpu_parity.py: C2 / C3 at 1920x1080, C4 at 3840x2160).
-template <bool EXTRA>
+//   * the solar illuminance multiplies every term of a step: it is applied once to the finished sum; the multiscattering mask is folded
+//     into the RGBA16F copy of the multiscattering LUT when the copy is made (k_luts_to_half); a grey Mie term (rgb-equal scattering and
+//     absorption coefficients, as in every shipped scene -- checked per launch, template flag GREY) is one scalar per step, not three.
+template <bool EXTRA, bool GREY>
 SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const LutView& transmittance_texture, const LutView& multiscattering_texture,
                                            cudaTextureObject_t density_texture, float start_i, float3 earth_center, float3 start_position, float3 view_direction, float3 sun_direction,
                                            float marching_distance, float steps, float3& transmittance, const ScatterExtras* extras) {
@@ -282,9 +285,10 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
     const float mie_phase = mie_k * (1.0f + cos_sun_view * cos_sun_view) / (mie_b * sqrtf(mie_b));
     const float3 solar = f3(u.solar_illuminance);
     const float3 Rs = f3(u.rayleigh_scattering), Ms = f3(u.mie_scattering), Ma = f3(u.mie_absorption), Oz = f3(u.ozone_absorption);
-    const float3 RsP = Rs * rayleigh_phase * solar, MsP = Ms * mie_phase * solar;   // single scattering, phase and illuminance folded
-    const float3 Qms = solar * u.multiscattering_mask;                                // multiple scattering: x scattering_i x LUT
-    const float dn_a = (1.0f - 1.0f / float(kDensityLutSize)) / (u.top_radius - u.bottom_radius), dn_b = 0.5f / float(kDensityLutSize);
+    const float3 RsP = Rs * rayleigh_phase, MsP = Ms * mie_phase;   // single scattering with the phase folded (x solar at the end)
+    const float3 Me = Ms + Ma;                                          // Mie extinction
+    // both altitude tables are addressed with r_i directly: the `- bottom` of the altitude sits in the offsets
+    const float dn_a = (1.0f - 1.0f / float(kDensityLutSize)) / (u.top_radius - u.bottom_radius), dn_b = 0.5f / float(kDensityLutSize) - u.bottom_radius * dn_a;
     const float k_t = -dx * kLog2e;
     // ray constants of the (r, mu_s) -> transmittance-LUT mapping (Atmosphere.glsl:90-108)
     const float bottom = u.bottom_radius, top = u.top_radius;
@@ -298,7 +302,7 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
     // multiscattering LUT (Atmosphere.glsl:169-178): u from mu_s, v from the altitude
     const float mw = float(multiscattering_texture.w), mh = float(multiscattering_texture.h);
     const float mu_a = 0.5f * (1.0f - 1.0f / mw), mu_b = 0.5f / mw + mu_a;
-    const float mv_a = (1.0f - 1.0f / mh) / (top - bottom), mv_b = 0.5f / mh;
+    const float mv_a = (1.0f - 1.0f / mh) / (top - bottom), mv_b = 0.5f / mh - bottom * mv_a;
 
     float3 T = f3(1.0f), L = f3(0.0f);
     // the shader's `for (float i = start_i; i < SAMPLE_COUNT; ++i)` with an integer trip count (start_i is in [0, 1): the number of
@@ -306,7 +310,7 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
     const int trip = max(int(ceilf(steps - start_i)), 0);
     float i = start_i;
 #ifndef SKY_K6_UNROLL
-#define SKY_K6_UNROLL 4   // measured at 4K, scene c3: 1 -> 693 us, 2 -> 716 us, 4 -> 683 us (profiles/k6_variants_r02l.log)
+#define SKY_K6_UNROLL 4   // measured at 4K, scene c3 (profiles/k6_variants_r02A.log): 1 -> 642 us, 2 -> 613 us, 4 -> 600 us; 4 blocks/SM (64 registers): 629-669 us
 #endif
     constexpr int kUnroll = SKY_K6_UNROLL;
 #pragma unroll kUnroll
@@ -316,14 +320,22 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
         const float ri2 = dd + r2;
         const float inv_r = rsqrtf(ri2);
         const float r_i = ri2 * inv_r;
-        const float altitude = r_i - bottom;
         const float rms = a_s + b_s * d;            // r_i mu_s_i
         const float mu_s = rms * inv_r;
         // densities (GetScattering / GetExtinction, :119-132,156-159): one fetch of the altitude table
-        const float4 dens = tex2D<float4>(density_texture, dn_b + altitude * dn_a, 0.5f);
+        const float4 dens = tex2D<float4>(density_texture, dn_b + r_i * dn_a, 0.5f);
         const float dR = dens.x, dM = dens.y, dO = dens.z;
-        const float3 scattering = Rs * dR + Ms * dM;
-        const float3 extinction = scattering + Ma * dM + Oz * dO;
+        float3 scattering, extinction, single;
+        if (GREY) {
+            const float sM = Ms.x * dM, eM = Me.x * dM, pM = MsP.x * dM;
+            scattering = f3(Rs.x * dR + sM, Rs.y * dR + sM, Rs.z * dR + sM);
+            extinction = f3(Rs.x * dR + eM, Rs.y * dR + eM, Rs.z * dR + eM) + Oz * dO;
+            single = f3(RsP.x * dR + pM, RsP.y * dR + pM, RsP.z * dR + pM);
+        } else {
+            scattering = Rs * dR + Ms * dM;
+            extinction = scattering + Ma * dM + Oz * dO;
+            single = f3(RsP.x * dR + MsP.x * dM, RsP.y * dR + MsP.y * dM, RsP.z * dR + MsP.z * dM);
+        }
         const float3 T_i = f3(exp2f(extinction.x * k_t), exp2f(extinction.y * k_t), exp2f(extinction.z * k_t));
         // GetSunVisibility (:110-117) = LUT(r_i, mu_s) x smoothstep around the geometric horizon
         const float rho = sqrtf(fmaxf(dd + r2_minus_b2, 0.0f));
@@ -332,7 +344,7 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
         const float d_min = top - r_i;
         const float x_mu = (d_top - d_min) / (rho + r_i + H_minus_top);   // (d - d_min) / (d_max - d_min)
         const float4 t_sun = tex2D<float4>(transmittance_texture.tex, uu_b + x_mu * uu_a, vv_b + rho * vv_a);
-        const float4 ms = tex2D<float4>(multiscattering_texture.tex, mu_b + mu_s * mu_a, mv_b + altitude * mv_a);
+        const float4 ms = tex2D<float4>(multiscattering_texture.tex, mu_b + mu_s * mu_a, mv_b + r_i * mv_a);   // x multiscattering_mask already
         const float e = __saturatef((rms + rho) * edge_k + 0.5f);
         float vis = e * e * (3.0f - 2.0f * e);
         float3 position_i;
@@ -340,21 +352,24 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
             position_i = start_position + view_direction * d;
             if (extras->shadow_size > 0) vis *= GetVisibilityFromShadowMap(*extras, position_i);  // :274-277 (single scattering only)
         }
-        float3 L_i = f3(RsP.x * dR + MsP.x * dM, RsP.y * dR + MsP.y * dM, RsP.z * dR + MsP.z * dM) * (f3(t_sun.x, t_sun.y, t_sun.z) * vis) +
-                     f3(ms.x, ms.y, ms.z) * scattering * Qms;
+        float3 L_i = single * (f3(t_sun.x, t_sun.y, t_sun.z) * vis) + f3(ms.x, ms.y, ms.z) * scattering;
         if (EXTRA && extras->moon_shadow)  // :281-284
             L_i *= GetVisibilityFromMoonShadow(f3(extras->moon_position) - position_i, extras->moon_radius, sun_direction, u.sun_angular_radius);
         // analytic integral over the segment (:288): (L_i - L_i T_i) / extinction, attenuated by the transmittance so far
         // (one MUFU.RCP for the three channels: 1 / x = y z / (x y z); the products stay far inside the fp32 range for extinction
         // coefficients per km, and a vanishing extinction gives the same 0 x inf = NaN the shader's own division produces)
+#ifdef SKY_K6_RCP3   // experiment: three MUFU.RCP instead of one + six multiplications
+        L += T * (L_i - L_i * T_i) * f3(1.0f / extinction.x, 1.0f / extinction.y, 1.0f / extinction.z);
+#else
         const float xy = extinction.x * extinction.y;
         const float inv_xyz = 1.0f / (xy * extinction.z);
         const float inv_z = xy * inv_xyz, inv_xy_z = extinction.z * inv_xyz;
         L += T * (L_i - L_i * T_i) * f3(extinction.y * inv_xy_z, extinction.x * inv_xy_z, inv_z);
+#endif
         T *= T_i;
     }
     transmittance = T;
-    return L;
+    return L * solar;
 }
 #endif
 
@@ -468,8 +483,10 @@ __global__ void __launch_bounds__(256) k_luts_to_half(const float4* __restrict__
                                                       half4* __restrict__ bh, int nb, half4* __restrict__ density, int nd, SkyAtmosphereBufferData u) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < na) ah[i] = to_half4(a[i]);
-    else if (i - na < nb) bh[i - na] = to_half4(b[i - na]);
-    else if (i - na - nb < nd) {
+    else if (i - na < nb) {   // (K6's march takes the multiscattering mask from here: one multiplication per texel instead of three per step)
+        const float4 v = b[i - na];
+        bh[i - na] = to_half4(f4(v.x * u.multiscattering_mask, v.y * u.multiscattering_mask, v.z * u.multiscattering_mask, v.w));
+    } else if (i - na - nb < nd) {
         const int k = i - na - nb;
         const float altitude = float(k) / float(nd - 1) * (u.top_radius - u.bottom_radius);
         const float dR = clampf(LUT_EXP(-altitude * u.inv_rayleigh_exponential_distribution), 0.0f, 1.0f);
@@ -918,7 +935,7 @@ SKY_D float3 ComputeObjectLuminance(const RenderParams& P, float3 position, floa
 #endif
 // LUTONLY: the launch's configuration has both USE_SKY_VIEW_LUT and USE_AERIAL_PERSPECTIVE_LUT (scenes c1 / c2): no pixel marches, so the
 // march is compiled out and the kernel -- a latency-bound chain of depth load, LUT and froxel fetches -- runs at twice the occupancy
-template <bool EXTRA, bool OBJECT, bool PCSS_ON = false, bool LUTONLY = false>
+template <bool EXTRA, bool OBJECT, bool PCSS_ON = false, bool LUTONLY = false, bool GREY = false>
 __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : LUTONLY ? SKY_K6_LUT_OCC : SKY_K6_OCC) k6_composite(const __grid_constant__ RenderParams P) {
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
     if (P.band_count > 1) py = ((py / P.band_rows) * P.band_count + P.band_index) * P.band_rows + py % P.band_rows;
@@ -953,8 +970,8 @@ __global__ void __launch_bounds__(256, PCSS_ON ? 1 : OBJECT ? 2 : LUTONLY ? SKY_
             transmittance = xyz(sample_lut3d_sel<kCompositeTexLut>(P.ap_trans, uvw.x, uvw.y, uvw.z));
         } else if (!LUTONLY) {
             float start_i = DitherStart(P, P.cfg.raymarching_dither, px, py);
-#if defined(SKY_COMPOSITE_TU) && !defined(SKY_STRICT_TU) && !defined(SKY_K6_REFERENCE_ORDER_MARCH)
-            luminance = ComputeScatteredLuminanceFast<EXTRA>(P.atm, P.transmittance, P.multiscattering, P.density_tex, start_i, f3(P.r.earth_center), start_position, view_direction,
+#if defined(SKY_COMPOSITE_TU) && !defined(SKY_STRICT_TU)
+            luminance = ComputeScatteredLuminanceFast<EXTRA, GREY>(P.atm, P.transmittance, P.multiscattering, P.density_tex, start_i, f3(P.r.earth_center), start_position, view_direction,
                                                              sun_direction, marching_distance, P.r.raymarching_steps, transmittance, &P.extras);
 #else
             luminance = ComputeScatteredLuminance<false, kCompositeTexLut, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
@@ -1193,6 +1210,9 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
     const int rows = owned_rows(ctx, h);
     if (rows <= 0) return 0;
     const bool extra = P.cfg.moon_shadow || P.cfg.volumetric_light;
+    const SkyAtmosphereBufferData& a = ctx->atm;   // grey Mie term (all shipped scenes): the march's scalar-Mie instantiation
+    const bool grey = a.mie_scattering[0] == a.mie_scattering[1] && a.mie_scattering[1] == a.mie_scattering[2] &&
+                      a.mie_absorption[0] == a.mie_absorption[1] && a.mie_absorption[1] == a.mie_absorption[2];
     SKY_PERF_MARKER("Render");  // AtmosphereRenderer.cpp:247
     const dim3 grid(ceil_div(w, 256), rows);
     if (ctx->gbuffer_albedo) {  // object branch (sky_set_gbuffer); api.cu has checked that the IBL chain exists
@@ -1200,9 +1220,11 @@ int launch_composite(SkyContext* ctx, const float* depth, half4* hdr, int w, int
             if (extra) k6_composite<true, true, true><<<grid, 256, 0, ctx->stream>>>(P);
             else k6_composite<false, true, true><<<grid, 256, 0, ctx->stream>>>(P);
         } else if (extra) k6_composite<true, true><<<grid, 256, 0, ctx->stream>>>(P);
+        else if (grey) k6_composite<false, true, false, false, true><<<grid, 256, 0, ctx->stream>>>(P);
         else k6_composite<false, true><<<grid, 256, 0, ctx->stream>>>(P);
     } else if (extra) k6_composite<true, false><<<grid, 256, 0, ctx->stream>>>(P);
     else if (P.cfg.use_sky_view_lut && P.cfg.use_aerial_perspective_lut) k6_composite<false, false, false, true><<<grid, 256, 0, ctx->stream>>>(P);
+    else if (grey) k6_composite<false, false, false, false, true><<<grid, 256, 0, ctx->stream>>>(P);
     else k6_composite<false, false><<<grid, 256, 0, ctx->stream>>>(P);
     SKY_LAUNCH_CHECK(ctx);
     return 0;

@@ -14,10 +14,10 @@ txt = open(sys.argv[2]).read()
 out = []
 for m in re.finditer(r"Function properties for (\S+)\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores.*\n.*Used (\d+) registers", txt):
     n = m.group(1)
-    k = re.search(r"(k19_path_traceILi3ELb0ELi1ELb0|k16_render(_coop)?ILi([01])ELb([01])E|k6_compositeILb0ELb0ELb0E)", n)
+    k = re.search(r"(k19_path_traceILi3ELb0ELi1ELb0|k16_render(_coop)?ILi([01])ELb([01])E|k6_compositeILb0ELb0ELb0ELb0ELb1E)", n)
     if k:
         if k.group(1).startswith("k19"): tag = "k19"
-        elif k.group(1).startswith("k6"): tag = "k6"
+        elif k.group(1).startswith("k6"): tag = "k6grey"
         else: tag = f"k16{'coop' if k.group(2) else ''}<M{k.group(3)},{'hw' if k.group(4) == '1' else 'exact'}>"
         out.append(f"{tag}: {m.group(4)} regs, {m.group(3)} B spill")
 print(sys.argv[1], "|", "; ".join(out))
