@@ -100,6 +100,12 @@ int skyhost_ground_depth(SkyScene* scene, float* depth, int width, int height);
  * textureGrad that is not shipped) -- and 0 (the cleared value) elsewhere.  Host arrays [height][width][4]. */
 int skyhost_ground_gbuffer(SkyScene* scene, const float albedo_rgb[3], uint8_t* albedo, int16_t* normal, uint16_t* orm, int width, int height);
 
+/* stbi_load / stbi_load_16 of a PNG file with stbi_set_flip_vertically_on_load (src/Base/src/StbImage.cpp:12-17; Textures.cpp:19-26 loads the
+ * 64x64 16-bit blue-noise tile this way).  Two calls: with out == NULL it returns the dimensions, channel count and bits per sample (8 / 16);
+ * with a buffer of width * height * channels * (bits / 8) bytes it writes the samples in host byte order, row 0 = the BOTTOM row of the
+ * image when flip_vertically != 0 (the GL texel order the reference uploads).  Non-interlaced grey / RGB / grey+alpha / RGBA, 8 or 16 bit. */
+int skyhost_png_load(const char* path, int flip_vertically, int32_t* width, int32_t* height, int32_t* channels, int32_t* bits, void* out, int64_t out_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,9 @@
 
 #include "scene.h"
 #include "vdb.h"
+#include "png.h"
+#include <cstring>
+#include <stdexcept>
 
 using namespace skyhost;
 
@@ -190,6 +193,30 @@ int skyhost_ground_depth(SkyScene* s, float* depth, int width, int height) {
 
 int skyhost_ground_gbuffer(SkyScene* s, const float albedo_rgb[3], uint8_t* albedo, int16_t* normal, uint16_t* orm, int width, int height) {
     return guarded([&] { s->scene.GroundGBuffer(albedo_rgb, albedo, normal, orm, width, height); });
+}
+
+int skyhost_png_load(const char* path, int flip_vertically, int32_t* width, int32_t* height, int32_t* channels, int32_t* bits, void* out, int64_t out_bytes) {
+    try {
+        const skyhost::PngImage im = skyhost::load_png(path ? path : "");
+        if (width) *width = im.width;
+        if (height) *height = im.height;
+        if (channels) *channels = im.channels;
+        if (bits) *bits = im.bits;
+        if (!out) return 0;
+        const size_t bytes_per_sample = size_t(im.bits / 8), stride = size_t(im.width) * im.channels * bytes_per_sample;
+        if (out_bytes != int64_t(stride * im.height)) throw std::runtime_error("png_load: the buffer must hold width * height * channels * (bits / 8) bytes");
+        uint8_t* dst = static_cast<uint8_t*>(out);
+        for (int y = 0; y < im.height; ++y) {
+            const uint8_t* src = im.samples.data() + size_t(flip_vertically ? im.height - 1 - y : y) * stride;
+            uint8_t* row = dst + size_t(y) * stride;
+            if (bytes_per_sample == 1) std::memcpy(row, src, stride);
+            else for (size_t i = 0; i < stride; i += 2) { row[i] = src[i + 1]; row[i + 1] = src[i]; }   // big-endian file -> little-endian host
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    }
 }
 
 }  // extern "C"

@@ -27,8 +27,15 @@ SCENE_FILES = {
 }
 
 
-def load_blue_noise():
-    """64x64 R16 blue noise in GL texel order (Textures.cpp:19-26 after StbImage.cpp:12-17's flip)."""
+def load_blue_noise(path=None):
+    """64x64 R16 blue noise in GL texel order (Textures.cpp:19-26 after StbImage.cpp:12-17's flip): the shipped tile, or a PNG like the
+    reference's data/BlueNoise/64_64/HDR_L_0.png read by the host library's own PNG reader (host/png.cpp)."""
+    if path is not None:
+        from .host import load_png
+        tile = load_png(path, flip_vertically=True)
+        if tile.shape != (64, 64) or tile.dtype != np.uint16:
+            raise ValueError(f"blue noise must be a 64x64 16-bit grey PNG, got {tile.shape} {tile.dtype}")
+        return np.ascontiguousarray(tile)
     return np.fromfile(os.path.join(_DATA, "blue_noise_64x64.u16"), dtype="<u2").reshape(64, 64)
 
 
