@@ -2,9 +2,12 @@
 // AppWindow::HandleDisplayEvent / Render do per frame (src/SkyRendering/AppWindow.cpp:139-181), without a window.
 //
 //   skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file.vdb] [--raw8 file dx dy dz]
-//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--out image.ppm] [--dump-rgba8 file]
+//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]
 // --objects shades object pixels like the reference (AtmosphereRenderer.glsl:284-343): the environment-BRDF LUT once, the IBL tail
 // of the LUT phase every frame, and the G-buffer of the analytic ground pass (skyhost_ground_gbuffer) bound with sky_set_gbuffer.
+// With --earth-map (an 8-bit RGB PNG, equirectangular, read by the host library's PNG reader with the reference's vertical flip) the frame
+// runs the reference's own order instead: Clear(gbuffer), Earth::RenderToGBuffer as the kernel K7 (sky_gbuffer_clear, sky_earth_gbuffer) into
+// the depth plane and the G-buffer, then the composite with the object branch on what K7 wrote.
 //
 // The scene JSON is the reference's own config format (bin/config*.json); the host library deserialises it with the
 // reference's defaults and computes every uniform block; the CUDA library renders.  There is no Python and no CPU fallback in
@@ -63,6 +66,8 @@ struct Driver {
     SkyCloudBufferData cloud{};
     SkyMaterialBlock material{};
     bool objects = false;  // --objects: the object branch of the composite on the ground pass's G-buffer
+    bool ground_pass = false;  // --earth-map: Clear(gbuffer) + Earth::RenderToGBuffer (K7) every frame
+    float* gdepth = nullptr; void *gb_albedo = nullptr, *gb_normal = nullptr, *gb_orm = nullptr;
 
     void earth_update() {  // Earth::Update (Earth.cpp:42-44)
         SkyAtmosphereBufferData a;
@@ -97,6 +102,13 @@ struct Driver {
         earth_update();
         cloud_update(0.0f);
         sky_ok(sky_cloud_shadow(ctx, &common), "cloud_shadow");
+        if (ground_pass) {  // AppWindow::Render: Clear(*gbuffer_), RenderGBuffer -> earth_.RenderToGBuffer (AppWindow.cpp:168-171,192-200)
+            SkyEarthBufferData earth;
+            host_ok(skyhost_earth_buffer(scene, &earth), "earth_buffer");
+            sky_ok(sky_gbuffer_clear(ctx, gdepth, gb_albedo, gb_normal, gb_orm, width, height), "gbuffer_clear");
+            sky_ok(sky_earth_gbuffer(ctx, &earth, gdepth, gb_albedo, gb_normal, gb_orm, width, height), "earth_gbuffer");
+            depth = gdepth;
+        }
         atmosphere_luts();
         sky_ok(sky_composite(ctx, depth, hdr, width, height), "composite");
         sky_ok(sky_cloud_frame(ctx, &common, &cloud, depth, hdr), "cloud_frame");
@@ -107,14 +119,14 @@ struct Driver {
 
 int main(int argc, char** argv) {
     if (argc < 4) die("usage: skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file] [--raw8 file dx dy dz] "
-                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--out image.ppm] [--dump-rgba8 file]");
+                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]");
     const std::string scene_path = argv[1];
     Driver d;
     d.width = std::atoi(argv[2]);
     d.height = std::atoi(argv[3]);
     int frames = 8, warmup = 8, spp = 0, raw_dim[3] = {0, 0, 0};
     bool hw = false, strict = false, overlap = false, pipeline = false;
-    std::string out_ppm, dump_rgba8, vdb_path, raw8_path, data_dir;
+    std::string out_ppm, dump_rgba8, vdb_path, raw8_path, data_dir, earth_map;
     for (int i = 4; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) die("missing value after " + a); return argv[++i]; };
@@ -128,6 +140,7 @@ int main(int argc, char** argv) {
         else if (a == "--overlap") overlap = true;
         else if (a == "--pipeline") pipeline = true;
         else if (a == "--objects") d.objects = true;
+        else if (a == "--earth-map") { earth_map = next(); d.objects = true; }
         else if (a == "--out") out_ppm = next();
         else if (a == "--dump-rgba8") dump_rgba8 = next();
         else if (a == "--data") data_dir = next();
@@ -189,7 +202,22 @@ int main(int argc, char** argv) {
     cuda_ok(cudaMemset(hdr, 0, npix * 8), "cudaMemset");
 
     void *gb_albedo = nullptr, *gb_normal = nullptr, *gb_orm = nullptr;
-    if (d.objects) {  // Textures::Textures bakes the environment-BRDF LUT once (Textures.cpp:60-75); Earth::RenderToGBuffer's targets are inputs
+    if (d.objects && !earth_map.empty()) {  // Textures::Textures: the earth albedo map (Textures.cpp:52-58), then K7 fills the G-buffer every frame
+        sky_ok(sky_env_brdf_lut(d.ctx), "env_brdf_lut");
+        int32_t mw = 0, mh = 0, mc = 0, mb = 0;
+        host_ok(skyhost_png_load(earth_map.c_str(), 1, &mw, &mh, &mc, &mb, nullptr, 0), "png_load");
+        if (mc != 3 || mb != 8) die("--earth-map: an 8-bit RGB PNG is expected");
+        std::vector<uint8_t> texels(size_t(mw) * mh * 3);
+        host_ok(skyhost_png_load(earth_map.c_str(), 1, nullptr, nullptr, nullptr, nullptr, texels.data(), int64_t(texels.size())), "png_load");
+        sky_ok(sky_set_earth_albedo(d.ctx, texels.data(), mw, mh), "set_earth_albedo");
+        cuda_ok(cudaMalloc(&d.gdepth, npix * 4), "cudaMalloc");
+        cuda_ok(cudaMalloc(&gb_albedo, npix * 4), "cudaMalloc");
+        cuda_ok(cudaMalloc(&gb_normal, npix * 8), "cudaMalloc");
+        cuda_ok(cudaMalloc(&gb_orm, npix * 8), "cudaMalloc");
+        d.gb_albedo = gb_albedo; d.gb_normal = gb_normal; d.gb_orm = gb_orm;
+        d.ground_pass = true;
+        sky_ok(sky_set_gbuffer(d.ctx, gb_albedo, gb_normal, gb_orm), "set_gbuffer");
+    } else if (d.objects) {  // Textures::Textures bakes the environment-BRDF LUT once (Textures.cpp:60-75); Earth::RenderToGBuffer's targets are inputs
         sky_ok(sky_env_brdf_lut(d.ctx), "env_brdf_lut");
         std::vector<uint8_t> albedo(npix * 4);
         std::vector<int16_t> normal(npix * 4);

@@ -274,3 +274,40 @@ def test_cpp_frame_driver_objects_match_the_python_driver(libs, tmp_path):
         imgs.append(img.cpu().numpy())
     got = np.fromfile(dump, np.uint8).reshape(h, w, 4)
     assert np.array_equal(got, imgs[0]) and not np.array_equal(got, imgs[1])
+
+
+def test_cpp_frame_driver_ground_pass_matches_the_python_driver(libs, tmp_path):
+    """skyrender --earth-map (C++ over the two C ABIs): the reference's whole frame order -- Clear(gbuffer), Earth::RenderToGBuffer as the kernel
+    K7 on an earth map read by the host library's PNG reader, IBL tail, composite with the object branch on what K7 wrote, cloud chain -- renders
+    the same RGBA8 image, byte for byte, as the Python frame driver, and a different one from the constant-albedo stand-in."""
+    import os
+    import subprocess
+    from skyrendering_b200.host import load_png
+    from skyrendering_b200.renderer import scene_path, synthetic_earth_albedo
+    from tests.parity import make_buffers
+    from tests.test_png import write_png
+    cuda, _ = libs
+    exe = os.path.join(abi.REPO_ROOT, "skyrendering_b200", "host", "skyrender")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    w, h = 384, 216
+    png = str(tmp_path / "earth.png")
+    write_png(png, synthetic_earth_albedo(512, 256, seed=4)[::-1])   # file rows run top to bottom; the loaders flip them back into GL order
+    dump = str(tmp_path / "frame.rgba8")
+    out = subprocess.run([exe, scene_path("c3"), str(w), str(h), "--warmup", "3", "--frames", "0", "--earth-map", png, "--dump-rgba8", dump], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    r = Renderer("c3", w, h, library=cuda)
+    r.enable_ibl()
+    r.ctx.set_earth_albedo(load_png(png, flip_vertically=True))
+    r.prime()
+    depth, hdr = make_buffers(w, h, np.ones((h, w), np.float32), "cuda")
+    t = [torch.zeros((h, w, 4), dtype=dt, device="cuda") for dt in (torch.uint8, torch.int16, torch.uint16)]
+    for _ in range(3):
+        hdr.zero_()
+        r.ground_pass(depth, *t, clear=True)
+        r.frame(depth, hdr, 0.0)
+    img = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    r.ctx.tonemap(hdr, w, h, img)
+    r.ctx.sync()
+    got = np.fromfile(dump, np.uint8).reshape(h, w, 4)
+    assert np.array_equal(got, img.cpu().numpy())
+    assert (t[0].cpu().numpy()[..., 3] == 255).mean() > 0.2 and len(np.unique(t[0].cpu().numpy()[..., :3].reshape(-1, 3), axis=0)) > 50
