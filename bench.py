@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--frame-exact-filtering", action="store_true",
                     help="4K frame: exact fp32 software filtering of the material textures instead of the texture unit (the production setting: "
                          "its frame error against the oracle equals exact filtering's to three digits, DESIGN.md section 6)")
+    ap.add_argument("--frame-exact-luts", action="store_true", help="4K frame: the bit-exact one-thread-per-march LUT kernels instead of the cooperative production march (sky_set_lut_arithmetic)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-frame", action="store_true")
     ap.add_argument("--skip-configs", action="store_true", help="skip the single-GPU configurations C1-C3")
@@ -403,6 +404,11 @@ def main():
     frame_hw = not args.frame_exact_filtering
     fname = lambda hw: "hardware" if hw else "exact_fp32"
     rf.ctx.set_hw_filtering(frame_hw)
+    # the LUT phase of a production frame: the lane-cooperative march of K2-K4 (tolerance stated in tests/test_gpu_parity.py; the frame is
+    # unchanged to 4 digits); the bit-exact kernels are timed as the variant
+    frame_luts = abi.LUT_EXACT if args.frame_exact_luts else abi.LUT_COOPERATIVE
+    lname = lambda m: "cooperative" if m == abi.LUT_COOPERATIVE else "exact"
+    rf.ctx.set_lut_arithmetic(frame_luts)
     rf.prime()
     rf.cloud_update(0.0)
     tex_peak = rf.ctx.tex_peak(0)      # trilinear R8 3-D fetches / s (coherent)
@@ -461,6 +467,10 @@ def main():
         rf.ctx.set_frame_pipelining(True)
         frame_ms = timed_frames(max(args.steps, 3), 1)
         frame_host_submit_ms = host_timing["ms_per_step"] / FRAME_BATCH   # if this approaches ms_per_frame the loop is host-bound, not GPU-bound
+        other_luts = abi.LUT_EXACT if frame_luts == abi.LUT_COOPERATIVE else abi.LUT_COOPERATIVE
+        rf.ctx.set_lut_arithmetic(other_luts)
+        frame_other_luts_ms = timed_frames(max(args.steps, 3), 1)
+        rf.ctx.set_lut_arithmetic(frame_luts)
         # the same frame with the reference's object shading: the IBL tail of the LUT phase every frame (cube mips +
         # K23 + K24, AtmosphereRenderer.cpp:242-244) and K6's object branch on a synthetic G-buffer (ground pixels get sun + ambient)
         object_variant = None
@@ -505,6 +515,11 @@ def main():
             "K14_K16": kernel_ms(lambda: rf.ctx.cloud_frame_begin(common, cloud, depth)),
             "K17_K18": kernel_ms(lambda: rf.ctx.cloud_frame_end(depth, hdr)),
         }
+        rf.ctx.set_lut_arithmetic(other_luts)
+        lut_variant = {"lut_arithmetic": lname(other_luts), "ms_per_frame": frame_other_luts_ms, "bake_K1_K2_ms": kernel_ms(rf.earth_update),
+                       "luts_K3_K5_ms": kernel_ms(rf.atmosphere_render_luts)}
+        rf.ctx.set_lut_arithmetic(frame_luts)
+        rf.prime()
         if object_variant is not None:  # single stream, like parts_ms
             object_variant["ibl_mips_K23_K24_ms"] = kernel_ms(rf.ctx.ibl_precompute)
             rf.ctx.set_gbuffer(*gb)
@@ -547,7 +562,7 @@ def main():
         depth_host = torch.from_numpy(depth_np).pin_memory()
         e2e_frame_ms = timed_steps(lambda: rf.ctx.cloud_frame_host(common, cloud, depth_host.numpy(), hdr_host.numpy()), 3, 1) if world == 1 else None
         frame = {
-            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "host_submit_ms_per_frame": frame_host_submit_ms, "ms_per_frame_overlap_only": frame_overlap_ms, "ms_per_frame_single_stream": frame_serial_ms, "filtering": fname(frame_hw), "unit": "ms", "higher_is_better": False,
+            "metric": "cloud_frame_4k_ms", "ms_per_frame": frame_ms, "host_submit_ms_per_frame": frame_host_submit_ms, "ms_per_frame_overlap_only": frame_overlap_ms, "ms_per_frame_single_stream": frame_serial_ms, "filtering": fname(frame_hw), "lut_arithmetic": lname(frame_luts), "unit": "ms", "higher_is_better": False,
             "frame_definition": "one AppWindow::HandleDisplayEvent: K1,K2 bake, K11-K13 shadow chain, K3-K5 LUTs, K6 composite, K14-K18 cloud chain; "
                                 "ms_per_frame = consecutive frames with sky_set_frame_overlap (shadow + cloud chain beside LUTs + composite on a second stream) and "
                                 "sky_set_frame_pipelining (the LUT phase of frame N+1 beside frame N's K6 / K16, two LUT sets), "
@@ -566,6 +581,7 @@ def main():
             "frame_fraction_of_floor": ((fetches / mix_peak) + (hbm_bytes + k6_bytes + (FRAME_W // 2) * (FRAME_H // 2) * 4 + FRAME_W * FRAME_H * 4) / (peaks["hbm_gbs"] * 1e9)) / (frame_ms * 1e-3),
             "mpixels_per_s": FRAME_W * FRAME_H / (frame_ms * 1e-3) / 1e6,
             "filtering_variant": other_variant,
+            "lut_arithmetic_variant": lut_variant,
             "object_shading_variant": object_variant,
             "e2e_host_buffers_ms": e2e_frame_ms,
             "e2e_h2d_bytes": FRAME_W * FRAME_H * 12, "e2e_d2h_bytes": FRAME_W * FRAME_H * 8,
@@ -589,7 +605,11 @@ def main():
         r1.prime()
         c1 = {"workload": "c1 LUT bake: transmittance 256x64, multiscattering 32x32, sky-view 128x128, aerial perspective 32^3, environment cube",
               "bake_K1_K2_us": kernel_ms(r1.earth_update) * 1e3, "luts_K3_K5_us": kernel_ms(r1.atmosphere_render_luts) * 1e3,
-              "bound": "latency / launch (5 M march steps, < 2 MB written)", "parity": "bit-exact (tests/test_gpu_parity.py)"}
+              "bound": "latency / launch (5 M march steps, < 2 MB written)", "parity": "bit-exact (tests/test_gpu_parity.py)", "lut_arithmetic": "exact"}
+        r1.ctx.set_lut_arithmetic(abi.LUT_COOPERATIVE)
+        r1.prime()
+        c1["cooperative"] = {"bake_K1_K2_us": kernel_ms(r1.earth_update) * 1e3, "luts_K3_K5_us": kernel_ms(r1.atmosphere_render_luts) * 1e3,
+                             "parity": "stated tolerance (tests/test_gpu_parity.py::test_cooperative_lut_bake_within_tolerance)"}
         if cpu is not None:
             o1 = Renderer("c1", 1920, 1080, library=cpu)
             o1.prime()
@@ -601,6 +621,7 @@ def main():
             W, H = 1920, 1080
             r = Renderer(scene, W, H, library=cuda, device=local_rank)
             r.ctx.set_hw_filtering(frame_hw)
+            r.ctx.set_lut_arithmetic(frame_luts)
             r.prime()
             dnp = r.scene.ground_depth(W, H)
             d = torch.from_numpy(dnp).cuda()
@@ -764,6 +785,7 @@ def main():
                 return h if sharder is None else sharder.target(h).clone()   # (fused peer exchange: the frame is in the context's exported target)
             rs = Renderer("c3", FRAME_W, FRAME_H, library=cuda, device=local_rank)
             rs.ctx.set_hw_filtering(frame_hw)
+            rs.ctx.set_lut_arithmetic(frame_luts)
             rs.prime()
             rs.ctx.set_frame_overlap(True); rs.ctx.set_frame_pipelining(True)
             hdr_sharded = frames_of(rs, ShardedCloudFrame(rs, rank, world, band_rows=8, shard_output=True))
@@ -772,6 +794,7 @@ def main():
             if rank == 0:
                 r1 = Renderer("c3", FRAME_W, FRAME_H, library=cuda, device=local_rank)
                 r1.ctx.set_hw_filtering(frame_hw)
+                r1.ctx.set_lut_arithmetic(frame_luts)
                 r1.prime()
                 hdr_single = frames_of(r1, None)
                 sharded_checks["frame_4k"] = {"frames": 3, "bit_identical": bool(torch.equal(hdr_sharded, hdr_single)),

@@ -226,6 +226,18 @@ int SKY_FN(set_hw_filtering)(SkyContext* ctx, int enable);
  * relative RMS 1e-2 because the altitude |p| - R of VolumetricCloudCommon.glsl:36-39 cancels four digits, which makes any
  * frame sensitive to contraction at the 1e-3 level).  The LUT bake and the noise kernels are always strict. */
 int SKY_FN(set_strict_arithmetic)(SkyContext* ctx, int enable);
+/* Arithmetic of the per-frame LUT marches K2, K3 and K4 (Atmosphere.glsl:220-295 as dispatched by Atmosphere.cpp:116 and
+ * AtmosphereRenderer.cpp:222-233).  SKY_LUT_EXACT (default): one thread per march, the shader's unfused fp32 operation order with IEEE division /
+ * square root and the deterministic elementary functions -- bit-identical to the oracle.  SKY_LUT_COOPERATIVE: the production march --
+ * four lanes fold contiguous chunks of a march's steps into affine maps (L, T) -> (L + T A, T T_i) and compose them in order; fused
+ * multiply-adds and the hardware ex2 / rcp / sqrt where the result is well conditioned, the shader's own expression for r_i.  Same quadrature,
+ * same ray set-up; the LUTs agree with the exact ones to the tolerance stated in tests/test_gpu_parity.py
+ * (test_cooperative_lut_bake_within_tolerance).  K1 and K5 are unaffected; with MOON_SHADOW_ENABLE or VOLUMETRIC_LIGHT_ENABLE K3 / K4 stay
+ * on the exact kernel. */
+#define SKY_LUT_EXACT 0
+#define SKY_LUT_COOPERATIVE 1
+int SKY_FN(set_lut_arithmetic)(SkyContext* ctx, int mode);
+
 /* Opt-in overlap of the two independent halves of a frame (AppWindow::Render, AppWindow.cpp:148-175) on a second,
  * internal stream: {cloud shadow chain K11-K13, K14-K17} run beside {K3-K5, composite K6}; K18 joins them.  Results are
  * bit-identical.  While enabled, the work of cloud_shadow / cloud_frame_begin is ordered on the caller's stream at

@@ -163,6 +163,7 @@ ENV_OFF, ENV_CONST_ENVIRONMENT_MAP, ENV_GROUND_SINGLE_BOUNCE, ENV_GROUND_MULTI_B
 GATHER_OFF, GATHER_ALL, GATHER_ROOT = range(3)   # SkyOutputGather
 KERNEL_K16 = 0                                    # SkyKernelId
 K16_AUTO, K16_WAVE_8x4, K16_WAVE_4x8, K16_LITERAL = range(4)   # SkyK16Shape
+LUT_EXACT, LUT_COOPERATIVE = 0, 1   # sky_set_lut_arithmetic
 IBL_PREFILTERED_RESOLUTION, IBL_ROUGHNESS_COUNT, ENV_BRDF_LUT_SIZE = 128, 5, 512  # IBL.h:10-11, Textures.cpp:61-62
 FMT_F32, FMT_F16, FMT_U8, FMT_U16, FMT_U64 = range(5)
 _FMT_DTYPE = {FMT_F32: np.float32, FMT_F16: np.float16, FMT_U8: np.uint8, FMT_U16: np.uint16, FMT_U64: np.uint64}
@@ -214,6 +215,7 @@ KERNEL_API = {
     "counters_enable": ([I], I),
     "set_hw_filtering": ([I], I),
     "set_strict_arithmetic": ([I], I),
+    "set_lut_arithmetic": ([I], I),
     "set_frame_overlap": ([I], I),
     "set_frame_pipelining": ([I], I),
     "set_output_bands": ([I, I, I], I),
@@ -428,6 +430,7 @@ class Context:
     def counters_enable(self, on): self._call("counters_enable", int(on))
     def set_hw_filtering(self, on): self._call("set_hw_filtering", int(on))
     def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))
+    def set_lut_arithmetic(self, mode): self._call("set_lut_arithmetic", int(mode))
     def set_frame_overlap(self, on): self._call("set_frame_overlap", int(on))
     def set_frame_pipelining(self, on): self._call("set_frame_pipelining", int(on))
     def set_output_bands(self, band_rows, band_index, band_count): self._call("set_output_bands", int(band_rows), int(band_index), int(band_count))

@@ -954,6 +954,13 @@ int sky_set_strict_arithmetic(SkyContext* ctx, int enable) {
     return 0;
 }
 
+int sky_set_lut_arithmetic(SkyContext* ctx, int mode) {
+    if (!ctx) return 1;
+    if (mode != SKY_LUT_EXACT && mode != SKY_LUT_COOPERATIVE) return sky_fail(ctx, "set_lut_arithmetic: unknown mode");
+    ctx->lut_arithmetic = mode;
+    return 0;
+}
+
 int sky_set_hw_filtering(SkyContext* ctx, int enable) {
     ctx->hw_filtering = enable != 0;
     return 0;

@@ -3,7 +3,9 @@
 // each function).  Compiled with -fmad=false: these kernels are microsecond-scale and
 // latency-bound, and the altitude r_i - bottom_radius (Atmosphere.glsl:258-260) cancels ~7 digits,
 // so keeping the reference's unfused fp32 operation order is worth more than the FMAs.
+#include <cstdlib>
 #include "../../include/sky_detmath.h"
+#include "../../include/skyb200.h"
 #include "atmosphere_dev.cuh"
 #include "ibl_dev.cuh"
 #include "context.h"
@@ -378,6 +380,125 @@ SKY_D float3 ComputeScatteredLuminanceFast(const AtmosphereModel& atm, const Lut
 // bit-identical, but K2 went 78 -> 520 us and K3-K5 230 -> 470 us: these kernels already issue at ~50 % of the machine with one
 // thread per march, and the replicated serial part costs 5x the instructions.)
 
+#ifndef SKY_COMPOSITE_TU
+// ---- the production LUT march (sky_set_lut_arithmetic(ctx, SKY_LUT_COOPERATIVE)) ----------------------------------------------
+// What differs from the march above, and why it may.  The bit-exact kernels are one thread per march: a serial chain of 30-51 steps
+// of ~450 instructions each (IEEE division / square root, the deterministic exp), i.e. the LATENCY of one thread, which no
+// amount of sharding shortens (K2 78 us, K3+K4 80 us on B200).  Only two things in a march are sequential, though: the running
+// transmittance product and the sum it weights.  A step is the affine map (L, T) -> (L + T A_i, T T_i), affine maps compose
+// associatively, so LANES lanes each fold a contiguous chunk of the steps into one map and a shuffle tree composes the chunks in
+// order.  The per-step arithmetic uses FMAs and the hardware ex2 / rcp / sqrt approximations where the result is well conditioned,
+// and keeps the shader's own unfused expression for the one quantity that is not: r_i (Atmosphere.glsl:258), whose altitude
+// r_i - bottom_radius cancels seven digits (one ulp of r_i is 0.5 m, 4e-4 of the Mie density).  The ray set-up (directions,
+// boundary distances, phase functions) is the exact code above, so every lane group marches the reference's own segment.
+// Tolerance instead of bit-exactness: tests/test_gpu_parity.py::test_cooperative_lut_bake_within_tolerance.
+#ifndef SKY_LUT_COOP_THREADS   // resident threads per SM the cooperative kernels are compiled for (register budget = 65536 / this)
+#define SKY_LUT_COOP_THREADS 768
+#endif
+#ifndef SKY_LUT_COOP_UNROLL
+#define SKY_LUT_COOP_UNROLL 1
+#endif
+SKY_D float ap_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+SKY_D float ap_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+SKY_D float ap_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+SKY_D float3 fma3(float3 a, float3 b, float3 c) { return f3(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z)); }
+SKY_D float3 fma3(float3 a, float s, float3 c) { return f3(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z)); }
+SKY_D float3 shfl_down3(unsigned mask, float3 v, int offset, int width) {
+    return f3(__shfl_down_sync(mask, v.x, offset, width), __shfl_down_sync(mask, v.y, offset, width), __shfl_down_sync(mask, v.z, offset, width));
+}
+// (1 - exp(-x)) / sigma with x = sigma dx: the segment weight of Atmosphere.glsl:288.  For x < 1/32 the alternating series
+// dx (1 - x/2 + x^2/6 - x^3/24 + x^4/120) instead of the cancelling difference (truncation < 5e-11): measured against the oracle
+// (profiles/lut_coop_r02D.log, mode 2 vs mode 1) it halves the count of texels beyond 1e-4 at the same speed.
+SKY_D float segment_weight(float sigma, float x, float T_i, float dx) {
+    const float w = (1.0f - T_i) * ap_rcp(sigma);
+    const float p = fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 120.0f, -1.0f / 24.0f), 1.0f / 6.0f), -0.5f), 1.0f);
+    return x < 0.03125f ? dx * p : w;
+}
+
+// Atmosphere.glsl:220-295 for the lane group `group_mask` (LANES consecutive lanes, this lane is number `lane` of it); the result is
+// valid in lane 0 of the group.  Every lane of the group must call it with the same ray.
+template <bool MS, int LANES>
+SKY_D float3 ComputeScatteredLuminanceCooperative(const AtmosphereModel& atm, const LutView& transmittance_texture, const LutView& multiscattering_texture,
+                                                  float start_i, float3 earth_center, float3 start_position, float3 view_direction, float3 sun_direction,
+                                                  float marching_distance, float steps, int lane, unsigned group_mask, float3& transmittance, float3& L_f) {
+    const SkyAtmosphereBufferData& u = atm.u;
+    const MarchSetup m = march_setup<MS>(atm, earth_center, start_position, view_direction, sun_direction, marching_distance, steps);
+    if (MS) start_i = 0.5f;
+    // the shader's `for (float i = start_i; i < SAMPLE_COUNT; ++i)`: start_i is in [0, 1), so it runs ceil(steps - start_i) times
+    const int trip = max(int(ceilf(steps - start_i)), 0);
+    const int per = (trip + LANES - 1) / LANES;
+    const int k_begin = lane * per, k_end = min(k_begin + per, trip);
+
+    const float kLog2e = 1.4426950408889634f;
+    const float bottom = u.bottom_radius, top = u.top_radius;
+    const float dx = m.dx, r2 = m.r * m.r, two_rmu = 2.0f * m.r * m.mu;      // the shader's own terms of r_i
+    const float3 rel = start_position - earth_center;
+    const float a_s = dot(sun_direction, rel), b_s = dot(sun_direction, view_direction);   // r_i mu_s_i = a_s + b_s d_i
+    const float kR = -u.inv_rayleigh_exponential_distribution * kLog2e, kM = -u.inv_mie_exponential_distribution * kLog2e;
+    const float3 Rs = f3(u.rayleigh_scattering), Ms = f3(u.mie_scattering), Ma = f3(u.mie_absorption), Oz = f3(u.ozone_absorption);
+    const float3 RsP = Rs * m.rayleigh_phase, MsP = Ms * m.mie_phase;
+    const float k_t = -dx * kLog2e;
+    // (r, mu_s) -> transmittance LUT coordinates (Atmosphere.glsl:90-108), ray-invariant factors
+    const float H = sqrtf((top - bottom) * (top + bottom));
+    const float tw = float(transmittance_texture.w), th = float(transmittance_texture.h);
+    const float uu_a = 1.0f - 1.0f / tw, uu_b = 0.5f / tw, vv_a = (1.0f - 1.0f / th) / H, vv_b = 0.5f / th;
+    const float edge_k = 0.5f / (bottom * u.sun_angular_radius);
+    // multiscattering LUT coordinates (:169-178)
+    const float mw = float(multiscattering_texture.w), mh = float(multiscattering_texture.h);
+    const float mu_a = 0.5f * (1.0f - 1.0f / mw), mu_b = 0.5f / mw + mu_a;
+    const float mv_a = (1.0f - 1.0f / mh) / (top - bottom), mv_b = 0.5f / mh;
+
+    float3 T = f3(1.0f), L = f3(0.0f), Lf = f3(0.0f);
+    constexpr int kCoopUnroll = SKY_LUT_COOP_UNROLL;
+#pragma unroll kCoopUnroll
+    for (int k = k_begin; k < k_end; ++k) {
+        const float d = (start_i + float(k)) * dx;
+        const float r_i = sqrtf(d * d + two_rmu * d + r2);          // unfused, IEEE: the shader's expression (:258)
+        const float altitude = r_i - bottom;
+        const float dR = __saturatef(ap_ex2(altitude * kR)), dM = __saturatef(ap_ex2(altitude * kM));
+        const float dO = fmaxf(0.0f, fmaf(-fabsf(altitude - u.ozone_center_altitude), u.inv_ozone_width, 1.0f));
+        const float3 scattering = fma3(Ms, dM, Rs * dR);
+        const float3 extinction = fma3(Oz, dO, fma3(Ma, dM, scattering));
+        const float3 x = extinction * dx;
+        const float3 T_i = f3(ap_ex2(extinction.x * k_t), ap_ex2(extinction.y * k_t), ap_ex2(extinction.z * k_t));
+        // GetSunVisibility (:110-117): rho^2 = r_i^2 - bottom^2 = altitude (r_i + bottom), the top-boundary discriminant
+        // r_i^2 (mu_s^2 - 1) + top^2 = (r_i mu_s)^2 + (top - r_i)(top + r_i): no cancelling squares
+        const float rms = fmaf(b_s, d, a_s);
+        const float rho = ap_sqrt(fmaxf(altitude * (r_i + bottom), 0.0f));
+        const float d_min = top - r_i;
+        const float d_top = fmaxf(ap_sqrt(fmaxf(fmaf(rms, rms, d_min * (top + r_i)), 0.0f)) - rms, 0.0f);
+        const float x_mu = (d_top - d_min) * ap_rcp(rho + H - d_min);
+        const float3 t_sun = xyz(sample_lut2d(transmittance_texture, fmaf(x_mu, uu_a, uu_b), fmaf(rho, vv_a, vv_b)));
+        const float e = __saturatef(fmaf(rms + rho, edge_k, 0.5f));   // the smoothstep around the geometric horizon, cos_theta_h = -rho / r_i
+        const float vis = e * e * fmaf(-2.0f, e, 3.0f);
+        float3 L_i;
+        if (MS) {
+            L_i = scattering * (t_sun * (vis * m.rayleigh_phase));     // isotropic phase for both species (:134-136)
+        } else {
+            const float mu_s = rms * ap_rcp(r_i);
+            const float3 ms = xyz(sample_lut2d(multiscattering_texture, fmaf(mu_s, mu_a, mu_b), fmaf(altitude, mv_a, mv_b)));
+            L_i = fma3(fma3(MsP, dM, RsP * dR), t_sun * vis, (ms * u.multiscattering_mask) * scattering);
+        }
+        const float3 w = f3(segment_weight(extinction.x, x.x, T_i.x, dx), segment_weight(extinction.y, x.y, T_i.y, dx),
+                            segment_weight(extinction.z, x.z, T_i.z, dx));
+        L = fma3(T, L_i * w, L);
+        if (MS) Lf = fma3(T, scattering * w, Lf);
+        T = T * T_i;
+    }
+    // compose the chunks in order: lane l takes (L, T) o (L', T') = (L + T L', T T') with the map `offset` lanes up
+#pragma unroll
+    for (int offset = 1; offset < LANES; offset <<= 1) {
+        const float3 Lr = shfl_down3(group_mask, L, offset, LANES), Tr = shfl_down3(group_mask, T, offset, LANES);
+        L = fma3(T, Lr, L);
+        if (MS) Lf = fma3(T, shfl_down3(group_mask, Lf, offset, LANES), Lf);
+        T = T * Tr;
+    }
+    transmittance = T;
+    L_f = Lf;
+    return MS ? L : L * f3(u.solar_illuminance);
+}
+#endif  // !SKY_COMPOSITE_TU
+
 // Atmosphere.glsl:297-306
 template <bool MS>
 SKY_D float3 ComputeGroundLuminance(const AtmosphereModel& atm, const LutView& transmittance_texture, float3 earth_center,
@@ -475,6 +596,63 @@ __global__ void __launch_bounds__(64) k2_multiscattering(const __grid_constant__
         P.multiscattering_out[gy * P.ms_w + gx] = f4(L_2nd_order * F_ms, 1.0f);
     }
 }
+
+#ifndef SKY_COMPOSITE_TU
+// K2, production arithmetic: one block per texel as above, but LANES lanes per sphere direction (64 x LANES threads), each folding a
+// chunk of the direction's 30 steps (ComputeScatteredLuminanceCooperative); the 64 directions are then added in the reference's
+// pairwise order like above.
+template <int LANES>
+__global__ void __launch_bounds__(64 * LANES, (SKY_LUT_COOP_THREADS / (64 * LANES)) > 0 ? SKY_LUT_COOP_THREADS / (64 * LANES) : 1) k2_multiscattering_cooperative(const __grid_constant__ BakeParams P) {
+    const SkyAtmosphereBufferData& u = P.atm.u;
+    const int gx = blockIdx.x, gy = blockIdx.y;
+    const int local_index = int(threadIdx.x) / LANES, lane = int(threadIdx.x) % LANES;
+    const unsigned group_mask = (LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31u) / LANES * LANES);
+    float x_mu_s = float(gx) / float(P.ms_w - 1), x_altitude = float(gy) / float(P.ms_h - 1);
+    float altitude = x_altitude * (u.top_radius - u.bottom_radius);
+    float mu_s = x_mu_s * 2.0f - 1.0f;
+    float3 earth_center = f3(0.0f, -u.bottom_radius, 0.0f);
+    float3 start_position = f3(0.0f, altitude, 0.0f);
+    float3 sun_direction = f3(0.0f, mu_s, sqrtf(1 - mu_s * mu_s));
+    float unit_theta = (0.5f + float(local_index / 8)) / 8.0f;
+    float unit_phi = (0.5f + float(local_index % 8)) / 8.0f;
+    float cos_theta = 1.0f - 2.0f * unit_theta;
+    float sin_theta = sqrtf(clampf(1.0f - cos_theta * cos_theta, 0.0f, 1.0f));
+    float phi = 2 * kPi * unit_phi;
+    float3 view_direction = f3(LUT_COS(phi) * sin_theta, cos_theta, LUT_SIN(phi) * sin_theta);
+    float r = altitude + u.bottom_radius;
+    float mu = view_direction.y;
+    bool intersect_bottom = P.atm.RayIntersectsGround(r, mu);
+    float marching_distance = intersect_bottom ? P.atm.DistanceToBottomAtmosphereBoundary(r, mu) : P.atm.DistanceToTopAtmosphereBoundary(r, mu);
+    float3 transmittance, L_f;
+    float3 luminance = ComputeScatteredLuminanceCooperative<true, LANES>(P.atm, P.transmittance, P.transmittance, 0.5f, earth_center, start_position,
+                                                                                  view_direction, sun_direction, marching_distance, u.multiscattering_steps,
+                                                                                  lane, group_mask, transmittance, L_f);
+    __shared__ float sh[64][6];
+    if (lane == 0) {
+        if (intersect_bottom) {
+            float3 ground_position = start_position + view_direction * marching_distance;
+            luminance += transmittance * ComputeGroundLuminance<true>(P.atm, P.transmittance, earth_center, ground_position, sun_direction);
+        }
+        float* s = sh[local_index];
+        s[0] = luminance.x; s[1] = luminance.y; s[2] = luminance.z; s[3] = L_f.x; s[4] = L_f.y; s[5] = L_f.z;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = sh[threadIdx.x][k] + sh[threadIdx.x + 32][k];
+#pragma unroll
+    for (int stride = 16; stride >= 1; stride >>= 1)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] += __shfl_down_sync(0xffffffffu, v[k], stride);
+    if (threadIdx.x == 0) {
+        float3 L_2nd_order = f3(v[0], v[1], v[2]) / 64.0f;
+        float3 f_ms = f3(v[3], v[4], v[5]) / 64.0f;
+        float3 F_ms = 1.0f / (f3(1.0f) - f_ms);
+        P.multiscattering_out[gy * P.ms_w + gx] = f4(L_2nd_order * F_ms, 1.0f);
+    }
+}
+#endif
 
 // RGBA16F copies of the two bake LUTs + the density table of K6's march (context.h): texel i of the table is the altitude
 // i / (nd - 1) x (top - bottom) and holds (rayleigh density, mie density, ozone density, 0) -- GetScattering / GetExtinction's three
@@ -596,8 +774,9 @@ SKY_D float DitherStart(const RenderParams& P, int enable, int x, int y) {
 }
 
 // K3 -- AtmosphereRenderer.glsl:153-186 (+ :81-111)
-template <bool EXTRA>
-SKY_D void k3_sky_view_texel(const RenderParams& P, int x, int y) {
+// LANES > 1: the production arithmetic -- LANES consecutive lanes share the texel's march (lane `lane` of the group `group_mask`)
+template <bool EXTRA, int LANES = 1>
+SKY_D void k3_sky_view_texel(const RenderParams& P, int x, int y, int lane = 0, unsigned group_mask = 0) {
     const int W = P.cfg.sky_view_width, H = P.cfg.sky_view_height;
     if (x >= W || y >= H) return;
     float r = P.r.camera_earth_center_distance;
@@ -629,10 +808,18 @@ SKY_D void k3_sky_view_texel(const RenderParams& P, int x, int y) {
     float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
     if (marching_distance > 0) {
         float start_i = DitherStart(P, P.cfg.sky_view_dither, x, y);
+#ifndef SKY_COMPOSITE_TU
+        if constexpr (LANES > 1)
+            luminance = ComputeScatteredLuminanceCooperative<false, LANES>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center),
+                                                                                    start_position, view_direction, f3(P.r.sun_direction), marching_distance,
+                                                                                    P.r.sky_view_lut_steps, lane, group_mask, transmittance, unused);
+        else
+#endif
         luminance = ComputeScatteredLuminance<false, false, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
                                                                    view_direction, f3(P.r.sun_direction), marching_distance, P.r.sky_view_lut_steps,
                                                                    transmittance, unused, &P.extras);
     }
+    if (lane != 0) return;
     P.sky_lum_out[y * W + x] = f4(luminance, 0.0f);
     P.sky_trans_out[y * W + x] = f4(transmittance, 0.0f);
     P.sky_lum_h_out[y * W + x] = to_half4(f4(luminance, 0.0f));
@@ -640,10 +827,10 @@ SKY_D void k3_sky_view_texel(const RenderParams& P, int x, int y) {
 }
 
 // K4 -- AtmosphereRenderer.glsl:191-243
-template <bool EXTRA>
-SKY_D void k4_aerial_perspective_froxel(const RenderParams& P, int x, int y, int z) {
+template <bool EXTRA, int LANES = 1>
+SKY_D void k4_aerial_perspective_froxel(const RenderParams& P, int x, int y, int z, int lane = 0, unsigned group_mask = 0) {
     const int W = P.ap_lum.w, H = P.ap_lum.h, D = P.ap_lum.d;
-    if (y >= H || z >= D) return;
+    if (x >= W || y >= H || z >= D) return;
     float3 uvw = f3(float(x) / float(W - 1), float(y) / float(H - 1), float(z) / float(D - 1));
     float3 position = projective_mul(P.r.inv_view_projection, f3(uvw.x * 2.0f - 1.0f, uvw.y * 2.0f - 1.0f, 0.0f));
     float3 view_direction = normalize(position - f3(P.r.camera_position));
@@ -658,10 +845,18 @@ SKY_D void k4_aerial_perspective_froxel(const RenderParams& P, int x, int y, int
     float3 transmittance = f3(1.0f), luminance = f3(0.0f), unused;
     if (marching_distance > 0) {
         float start_i = DitherStart(P, P.cfg.aerial_perspective_dither, x, y);
+#ifndef SKY_COMPOSITE_TU
+        if constexpr (LANES > 1)
+            luminance = ComputeScatteredLuminanceCooperative<false, LANES>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center),
+                                                                                    start_position, view_direction, f3(P.r.sun_direction), marching_distance,
+                                                                                    P.r.aerial_perspective_lut_steps, lane, group_mask, transmittance, unused);
+        else
+#endif
         luminance = ComputeScatteredLuminance<false, false, EXTRA>(P.atm, P.transmittance, P.multiscattering, start_i, f3(P.r.earth_center), start_position,
                                                                    view_direction, f3(P.r.sun_direction), marching_distance,
                                                                    P.r.aerial_perspective_lut_steps, transmittance, unused, &P.extras);
     }
+    if (lane != 0) return;
     size_t o = (size_t(z) * H + y) * W + x;
     P.ap_lum_out[o] = f4(luminance, 0.0f);
     P.ap_trans_out[o] = f4(transmittance, 0.0f);
@@ -681,6 +876,23 @@ __global__ void __launch_bounds__(64) k34_sky_view_and_aerial_perspective(const 
         k4_aerial_perspective_froxel<EXTRA>(P, int(threadIdx.x) % W, (b % g4x) * (64 / W) + int(threadIdx.x) / W, b / g4x);
     }
 }
+
+#ifndef SKY_COMPOSITE_TU
+// K3 + K4, production arithmetic: the same shared launch, 256-thread blocks = 256 / LANES marches x LANES lanes.  K3 blocks take a run of
+// texels of a sky-view row, K4 blocks a run of froxels of a row of a slice.
+template <int LANES>
+__global__ void __launch_bounds__(256, SKY_LUT_COOP_THREADS / 256) k34_cooperative(const __grid_constant__ RenderParams P, int n3, int g3x, int g4x) {
+    constexpr int kMarches = 256 / LANES;
+    const int march = int(threadIdx.x) / LANES, lane = int(threadIdx.x) % LANES;
+    const unsigned group_mask = (LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31u) / LANES * LANES);
+    if (int(blockIdx.x) < n3) {
+        k3_sky_view_texel<false, LANES>(P, int(blockIdx.x % g3x) * kMarches + march, int(blockIdx.x / g3x), lane, group_mask);
+    } else {
+        const int b = int(blockIdx.x) - n3, H = P.ap_lum.h;
+        k4_aerial_perspective_froxel<false, LANES>(P, (b % g4x) * kMarches + march, (b / g4x) % H, b / (g4x * H), lane, group_mask);
+    }
+}
+#endif
 
 // shaders/Base/Common.glsl:13-30
 SKY_D float3 ConvertCubUvToDir(int index, float u, float v) {
@@ -1116,6 +1328,16 @@ int launch_frame_lut_half_copies(SkyContext* ctx) {
     return 0;
 }
 
+// lanes per march of the cooperative kernels: 4 unless SKYB200_LUT_LANES says 2, 8 or 16.  Measured on B200, scene c3, back-to-back launches
+// (profiles/lut_coop_variants_r02E.log): K1 + K2 + copies 153 us exact -> 46.5 / 46.5 / 61 / 77 us with 2 / 4 / 8 / 16 lanes, K3 + K4 + K5
+// 158 us -> 66 / 60 / 70 / 86 us.  Few lanes win: the exact ray set-up is replicated per lane, and 4 lanes already fill the machine 1.7 times over.
+// 64 instead of 80 registers, and the step loop unrolled by two, are within 2 us of this either way (same log).
+static int lut_lanes() {
+    const char* e = getenv("SKYB200_LUT_LANES");
+    const int n = e ? atoi(e) : 4;
+    return n == 2 || n == 8 || n == 16 ? n : 4;
+}
+
 int launch_atmosphere_bake(SkyContext* ctx) {
     BakeParams P{};
     P.atm.u = ctx->atm;
@@ -1129,7 +1351,14 @@ int launch_atmosphere_bake(SkyContext* ctx) {
     nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
     nvtxRangePushA("Multiscattering");  // :116
-    k2_multiscattering<<<dim3(P.ms_w, P.ms_h), 64, 0, ctx->stream>>>(P);
+    if (ctx->lut_arithmetic == SKY_LUT_COOPERATIVE) {
+        switch (lut_lanes()) {
+            case 2: k2_multiscattering_cooperative<2><<<dim3(P.ms_w, P.ms_h), 128, 0, ctx->stream>>>(P); break;
+            case 8: k2_multiscattering_cooperative<8><<<dim3(P.ms_w, P.ms_h), 512, 0, ctx->stream>>>(P); break;
+            case 16: k2_multiscattering_cooperative<16><<<dim3(P.ms_w, P.ms_h), 1024, 0, ctx->stream>>>(P); break;
+            default: k2_multiscattering_cooperative<4><<<dim3(P.ms_w, P.ms_h), 256, 0, ctx->stream>>>(P); break;
+        }
+    } else k2_multiscattering<<<dim3(P.ms_w, P.ms_h), 64, 0, ctx->stream>>>(P);
     nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);
     return launch_lut_half_copies(ctx);
@@ -1146,7 +1375,17 @@ int launch_atmosphere_luts(SkyContext* ctx) {
     const int g3x = ceil_div(P.cfg.sky_view_width, 64), n3 = g3x * P.cfg.sky_view_height;
     const int g4x = ceil_div(P.ap_lum.h, 64 / P.ap_lum.w), n4 = g4x * P.ap_lum.d;
     nvtxRangePushA("SkyViewLut + AerialPerspective");  // AtmosphereRenderer.cpp:222,229 (one launch here)
-    if (extra) k34_sky_view_and_aerial_perspective<true><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
+    if (!extra && ctx->lut_arithmetic != SKY_LUT_EXACT) {   // (the two optional march terms stay on the exact kernel)
+        const int lanes = lut_lanes(), marches = 256 / lanes;
+        const int c3x = ceil_div(P.cfg.sky_view_width, marches), c3 = c3x * P.cfg.sky_view_height;
+        const int c4x = ceil_div(P.ap_lum.w, marches), c4 = c4x * P.ap_lum.h * P.ap_lum.d;
+        switch (lanes) {
+            case 2: k34_cooperative<2><<<c3 + c4, 256, 0, ctx->stream>>>(P, c3, c3x, c4x); break;
+            case 8: k34_cooperative<8><<<c3 + c4, 256, 0, ctx->stream>>>(P, c3, c3x, c4x); break;
+            case 16: k34_cooperative<16><<<c3 + c4, 256, 0, ctx->stream>>>(P, c3, c3x, c4x); break;
+            default: k34_cooperative<4><<<c3 + c4, 256, 0, ctx->stream>>>(P, c3, c3x, c4x); break;
+        }
+    } else if (extra) k34_sky_view_and_aerial_perspective<true><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
     else k34_sky_view_and_aerial_perspective<false><<<n3 + n4, 64, 0, ctx->stream>>>(P, n3, g3x, g4x);
     nvtxRangePop();
     SKY_LAUNCH_CHECK(ctx);

@@ -62,6 +62,7 @@ struct SkyContext {
     std::string error;
     bool hw_filtering = false;
     bool strict_arithmetic = false;  // sky_set_strict_arithmetic: route K6, K11-K18, K19/K20 to the *_strict objects
+    int lut_arithmetic = 0;          // sky_set_lut_arithmetic: SKY_LUT_EXACT (bit-faithful K2-K4) or the lane-cooperative production march
     bool counting = false;
     int k16_group = 0;               // SKYB200_K16_GROUP=4|8: force the wavefront kernel's rays per warp (0: chosen per launch, cloud.cu)
     bool k16_literal = false;        // SKYB200_K16_LITERAL=1: the production object launches k16_render (one lane = one ray, the shader's loop) instead of k16_render_coop

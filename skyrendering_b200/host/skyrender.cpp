@@ -2,7 +2,7 @@
 // AppWindow::HandleDisplayEvent / Render do per frame (src/SkyRendering/AppWindow.cpp:139-181), without a window.
 //
 //   skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file.vdb] [--raw8 file dx dy dz]
-//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]
+//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--coop-luts] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]
 // --objects shades object pixels like the reference (AtmosphereRenderer.glsl:284-343): the environment-BRDF LUT once, the IBL tail
 // of the LUT phase every frame, and the G-buffer of the analytic ground pass (skyhost_ground_gbuffer) bound with sky_set_gbuffer.
 // With --earth-map (an 8-bit RGB PNG, equirectangular, read by the host library's PNG reader with the reference's vertical flip) the frame
@@ -119,13 +119,13 @@ struct Driver {
 
 int main(int argc, char** argv) {
     if (argc < 4) die("usage: skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file] [--raw8 file dx dy dz] "
-                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]");
+                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--coop-luts] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]");
     const std::string scene_path = argv[1];
     Driver d;
     d.width = std::atoi(argv[2]);
     d.height = std::atoi(argv[3]);
     int frames = 8, warmup = 8, spp = 0, raw_dim[3] = {0, 0, 0};
-    bool hw = false, strict = false, overlap = false, pipeline = false;
+    bool hw = false, strict = false, overlap = false, pipeline = false, coop_luts = false;
     std::string out_ppm, dump_rgba8, vdb_path, raw8_path, data_dir, earth_map;
     for (int i = 4; i < argc; ++i) {
         std::string a = argv[i];
@@ -139,6 +139,7 @@ int main(int argc, char** argv) {
         else if (a == "--strict") strict = true;
         else if (a == "--overlap") overlap = true;
         else if (a == "--pipeline") pipeline = true;
+        else if (a == "--coop-luts") coop_luts = true;
         else if (a == "--objects") d.objects = true;
         else if (a == "--earth-map") { earth_map = next(); d.objects = true; }
         else if (a == "--out") out_ppm = next();
@@ -160,6 +161,7 @@ int main(int argc, char** argv) {
     sky_ok(sky_set_blue_noise(d.ctx, reinterpret_cast<const uint16_t*>(bn.data())), "set_blue_noise");
     sky_ok(sky_set_viewport(d.ctx, d.width, d.height), "set_viewport");
     sky_ok(sky_set_hw_filtering(d.ctx, hw), "set_hw_filtering");
+    sky_ok(sky_set_lut_arithmetic(d.ctx, coop_luts ? SKY_LUT_COOPERATIVE : SKY_LUT_EXACT), "set_lut_arithmetic");
     sky_ok(sky_set_strict_arithmetic(d.ctx, strict), "set_strict_arithmetic");
 
     int material_type = -1;

@@ -59,10 +59,11 @@ def to_numpy(x):
 
 
 def run_cloud_frames(scene, width, height, library, frames, device, composite=True, move=None, hw=False, count=False, strict=False,
-                     overlap=False, pipelining=False, k16_shape=None):
+                     overlap=False, pipelining=False, k16_shape=None, coop_luts=False):
     """Bake, zero histories, run `frames` HandleDisplayEvent iterations (static camera unless `move`
     gives a per-frame camera delta), return the final HDR and the intermediate buffers.
-    overlap / pipelining: the production frame mode bench.py times (sky_set_frame_overlap, sky_set_frame_pipelining)."""
+    overlap / pipelining / coop_luts: the production frame mode bench.py times (sky_set_frame_overlap, sky_set_frame_pipelining,
+    sky_set_lut_arithmetic)."""
     r = Renderer(scene, width, height, library=library)
     if hw:
         r.ctx.set_hw_filtering(True)
@@ -70,6 +71,8 @@ def run_cloud_frames(scene, width, height, library, frames, device, composite=Tr
         r.ctx.set_strict_arithmetic(True)
     if k16_shape is not None:
         r.ctx.set_launch_shape(abi.KERNEL_K16, k16_shape)
+    if coop_luts:
+        r.ctx.set_lut_arithmetic(abi.LUT_COOPERATIVE)
     r.prime()
     if overlap:
         r.ctx.set_frame_overlap(True)
