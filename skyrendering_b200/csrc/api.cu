@@ -315,7 +315,14 @@ int lane2_fork(SkyContext* ctx, cudaEvent_t after) {  // lane2 is ordered after 
 int sky_set_frame_overlap(SkyContext* ctx, int enable) {
     if (int e = lanes_join(ctx)) return e;
     if (enable && !ctx->lane2) {
-        SKY_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane2, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        // lane2 (shadow chain, K14-K17) runs ABOVE the caller's stream: its kernels are the short ones of a frame, and behind K6's 32 400 queued
+        // blocks they only got SM slots as those drained.  Measured at 4K, scene c3 (profiles/k16_persist_r02F.log): 1197 -> 1165 us per frame.
+        // (Same log: a persistent K16 holding a fixed 3-6 blocks of every SM beside K6 -- the two instruction streams interleaved instead of
+        // one kernel after the other -- is bit-identical and no faster, 1158 us: K6 already fills 89 % of the issue slots.  Removed again.)
+        const char* pr = std::getenv("SKYB200_LANE2_PRIORITY");   // 0: the caller's priority (A/B measurements)
+        SKY_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->lane2, cudaStreamNonBlocking, pr && pr[0] == '0' ? lo : hi));
         for (cudaEvent_t* ev : {&ctx->ev_fork, &ctx->ev_shadow, &ctx->ev_pre_composite, &ctx->ev_lane2})
             SKY_CUDA(ctx, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
