@@ -427,6 +427,15 @@ def main():
         "lookups_per_launch": lookups, "tentative_collisions_per_launch": collisions, "paths_per_launch": int(cnt[abi.CNT_PT_PATHS]),
         "ms_per_launch": k19_ms,
     }
+    # what actually bounds K19 (ncu: 81 % issue-active, L2 hit rate 99.7 %): the instruction-issue roof, like K6's -- warp instructions of the
+    # committed ncu capture of this launch shape over this run's launch time, against 148 SMs x 4 schedulers x the SM clock under load
+    k19_entry = ncu_entry("k19_path_trace")
+    if k19_entry and k19_entry.get("warp_instructions"):
+        sm_hz_pt = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        pt_roofline["issue"] = {"bound": "issue", "unit": "Gwarp-inst/s", "peak": 148 * 4 * sm_hz_pt / 1e9,
+                                "achieved": k19_entry["warp_instructions"] / (k19_ms * 1e-3) / 1e9,
+                                "frac": k19_entry["warp_instructions"] / (k19_ms * 1e-3) / (148 * 4 * sm_hz_pt),
+                                "warp_instructions_per_launch": k19_entry["warp_instructions"], "capture": k19_entry.get("capture")}
 
     # ---- 4K cloud frame ---------------------------------------------------------------------------------
     frame = None

@@ -1,5 +1,5 @@
 """Every kernel of the library once, at smoke size, with no oracle in the process: the workload compute-sanitizer runs
-(tools/sanitize.sh: memcheck + racecheck + initcheck; logs under profiles/).  Covers the LUT bake (K1-K5), the IBL chain (K22-K24), the
+(tools/sanitize.sh: memcheck + racecheck + initcheck; logs under profiles/).  Covers the LUT bake (K1-K5, exact and cooperative marches), the IBL chain (K22-K24), the
 ground pass (K7 + the sRGB mip kernel), noise generation (K8-K10), the shadow chain (K11-K13), both K16 kernels (wavefront and
 the literal / counting variant), K17 / K18, the composite with the object branch and PCSS, the tone map, the strict objects, the
 frame overlap + pipelining lanes, and the path tracer (K19 / K19b / K20) in both tracking modes."""
@@ -18,6 +18,7 @@ for scene, strict, hw in (("c3", False, False), ("c3", False, True), ("c1", True
     r = Renderer(scene, w, h)
     r.ctx.set_strict_arithmetic(strict)
     r.ctx.set_hw_filtering(hw)
+    r.ctx.set_lut_arithmetic(abi.LUT_COOPERATIVE if hw or scene == "c2" else abi.LUT_EXACT)   # both LUT marches
     r.enable_ibl()
     r.prime()
     r.ctx.set_earth_albedo(synthetic_earth_albedo(128, 64))
