@@ -158,12 +158,28 @@ SKY_D float blend_cell(uint2 cell, float a, float b, float c) {
     return (y0 + c * (y1 - y0)) * (1.0f / 255.0f);
 }
 
+SKY_D float blend_cell_raw(uint2 cell, float a, float b, float c) {  // the same blend on the byte scale (0..255): the caller folds 1/255 into its own factor
+    float x00 = lerp_biased(byte_biased(cell.x, 0), byte_biased(cell.x, 1), a), x10 = lerp_biased(byte_biased(cell.x, 2), byte_biased(cell.x, 3), a);
+    float x01 = lerp_biased(byte_biased(cell.y, 0), byte_biased(cell.y, 1), a), x11 = lerp_biased(byte_biased(cell.y, 2), byte_biased(cell.y, 3), a);
+    float y0 = x00 + b * (x10 - x00), y1 = x01 + b * (x11 - x01);
+    return y0 + c * (y1 - y0);
+}
+
 // K19's fast path: level-0 LINEAR lookup of the voxel grid for a position the caller has already bounded to the
 // footprint apron (u, v at most a quarter texel outside [-1/2w, 1 + 1/2w], w_ in [0, 1]): the padded cell layout needs
 // no range test.  Same arithmetic as tapb_border.
 struct VoxelTap { unsigned int xy; int k; float a, b, c; };
 SKY_D VoxelTap voxel_tap(const MipView& t, float u, float v, float w_) {
     float x = u * float(t.w[0]) - 0.5f, y = v * float(t.h[0]) - 0.5f, z = w_ * float(t.d[0]) - 0.5f;
+    int i0, j0, k0;
+    float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
+    VoxelTap tap;
+    tap.a = x - fx; tap.b = y - fy; tap.c = z - fz;
+    tap.xy = (unsigned int)((j0 + 2) * t.cell_w[0] + (i0 + 2));
+    tap.k = k0 + 1;
+    return tap;
+}
+SKY_D VoxelTap voxel_tap_texel(const MipView& t, float x, float y, float z) {  // the same tap from level-0 texel coordinates (u * w - 0.5, ...)
     int i0, j0, k0;
     float fx = floor_small(x, i0), fy = floor_small(y, j0), fz = floor_small(z, k0);
     VoxelTap tap;
