@@ -279,8 +279,9 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-frame", action="store_true")
     ap.add_argument("--skip-configs", action="store_true", help="skip the single-GPU configurations C1-C3")
-    ap.add_argument("--full-grid", action="store_true", help="configs: also run C5 on the 1987x2449x1351 grid (6.6 GB of voxels, ~80 GB on the device, "
-                                                              "minutes of grid generation + upload: not part of the default run)")
+    ap.add_argument("--no-full-grid", dest="full_grid", action="store_false",
+                    help="configs: skip C5 on the 1987x2449x1351 grid (6.6 GB of voxels, 78 GB on the device with its corner-packed cells, mips and texture copy; "
+                         "about 20 s of the default run; skipped by itself when the device has less than 100 GB free)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -685,6 +686,9 @@ def main():
         for key, scale, spp_l in large:
             from skyrendering_b200.renderer import synthetic_voxel_grid_large
             torch.cuda.empty_cache()
+            if key == "c5_full" and torch.cuda.mem_get_info()[0] < 100e9:
+                configs[key] = {"skipped": f"{torch.cuda.mem_get_info()[0] / 1e9:.0f} GB of device memory free, the full-resolution grid needs 78 GB"}
+                continue
             t0 = time.perf_counter()
             grid_l = synthetic_voxel_grid_large(scale)
             t_gen = time.perf_counter() - t0
@@ -726,8 +730,10 @@ def main():
                              "achieved_upper_bound_32B_sectors": lk * 32 / (ms_l * 1e-3) / 1e9,
                              "achieved_algorithmic_8B": lk * 8 / (ms_l * 1e-3) / 1e9, "traffic": traffic,
                              "wasted_traffic_ratio": None if traffic is None else traffic / (lk * 8.0),
-                             "note": "upper bound of the DRAM bytes: lookups x one 32-byte sector (the corner-packed cell of a trilinear tap lies in one "
-                                     "sector); lookups that hit L2 (mip levels, coherent primary rays) never reach DRAM -- `traffic` is the measured figure"},
+                             "note": "`traffic` is the MEASURED DRAM byte count of this launch shape (single-pass ncu capture, profiles/traffic_r02.json): on the full-resolution "
+                                     "grid 93 B per algorithmic lookup -- every lookup misses L2 and DRAM answers a miss with more than the one 32-byte sector that holds the "
+                                     "8-byte cell (cudaLimitMaxL2FetchGranularity = 32 changes nothing on B200, profiles/l2_fetch_granularity_r02I.log) -- so this is the one "
+                                     "regime in which K19 is HBM-bound; on the quarter grid most lookups still hit L2 (9 B per lookup) and the kernel is issue-bound"},
                 "texture_unit_variant": {"ms_per_launch": ms_tex, "gsamples_per_s": PT_W * PT_H * spp_l / (ms_tex * 1e-3) / 1e9, "traffic": traffic_tex,
                                          "wasted_traffic_ratio": None if traffic_tex is None else traffic_tex / (lk * 8.0),
                                          "layout": "R8 3-D CUDA array + mip chain behind two texture objects (1.14 B per voxel)"}}

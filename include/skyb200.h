@@ -219,12 +219,6 @@ int SKY_FN(set_launch_shape)(SkyContext* ctx, int kernel, int shape);
 /* Which filtering the material textures use: 0 = exact fp32 software filtering on gathered
  * texels (default; matches the oracle), 1 = hardware linear filtering (8-bit weights). */
 int SKY_FN(set_hw_filtering)(SkyContext* ctx, int enable);
-/* DRAM fetch granularity of L2 misses on this context's device (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes; a device-wide hint).
- * The path tracer's lookups into a voxel grid far beyond L2 (VolumetricCloudVoxelMaterial.cpp:39-75 with the full-resolution
- * wdas_cloud: 60 GB of corner-packed cells) are independent 8-byte reads, one per 32-byte sector; with the default granularity every miss
- * drags a second sector along and K19 becomes HBM-bound on bytes it never uses.  bytes == 0 only queries;
- * *in_effect (may be NULL) receives the value the device reports afterwards. */
-int SKY_FN(set_l2_fetch_granularity)(SkyContext* ctx, int bytes, int* in_effect);
 /* Validation mode: 1 routes the frame kernels (K6, K11-K18) and the path tracer (K19/K20) to objects compiled from the
  * same sources WITHOUT FMA contraction and with IEEE division / square root / elementary functions, i.e. the unfused
  * fp32 arithmetic the oracle (and a GLSL compiler honouring `precise`) performs, operation by operation.  The default

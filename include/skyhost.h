@@ -106,6 +106,14 @@ int skyhost_ground_gbuffer(SkyScene* scene, const float albedo_rgb[3], uint8_t* 
  * image when flip_vertically != 0 (the GL texel order the reference uploads).  Non-interlaced grey / RGB / grey+alpha / RGBA, 8 or 16 bit. */
 int skyhost_png_load(const char* path, int flip_vertically, int32_t* width, int32_t* height, int32_t* channels, int32_t* bits, void* out, int64_t out_bytes);
 
+/* stbi_load of a JPEG file with stbi_set_flip_vertically_on_load (src/Base/src/StbImage.cpp:12-17; Textures.cpp:27-58 loads the earth albedo, the star
+ * map and the two moon maps of data/NASA this way: progressive 4:4:4 YCbCr files).  Same two-call protocol as skyhost_png_load: out == NULL returns
+ * width, height and channels (1 = grey, 3 = RGB); with a buffer of width * height * channels bytes it writes the 8-bit samples, row 0 = the BOTTOM
+ * row of the image when flip_vertically != 0.  Baseline, extended-sequential and progressive Huffman DCT, restart intervals, sampling factors 1 and 2;
+ * the inverse DCT, chroma upsampling and YCbCr -> RGB use stb_image's integer arithmetic, so the bytes are the ones the reference uploads
+ * (host/jpeg.cpp; pinned against external/stb/stb_image.h in tests/test_jpeg.py).  The result feeds sky_set_star_map / sky_set_earth_albedo. */
+int skyhost_jpeg_load(const char* path, int flip_vertically, int32_t* width, int32_t* height, int32_t* channels, void* out, int64_t out_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -473,7 +473,6 @@ int orc_peer_detach(SkyContext*) { return 0; }
 int orc_set_output_gather(SkyContext* ctx, int mode) { return mode == SKY_GATHER_OFF ? 0 : fail(ctx, "peer memory is a CUDA feature"); }
 int orc_pt_set_tracking(SkyContext* ctx, int mode) { return mode == SKY_PT_TRACKING_REFERENCE ? 0 : fail(ctx, "the oracle only implements the reference's tracking"); }
 int orc_set_hw_filtering(SkyContext*, int) { return 0; }
-int orc_set_l2_fetch_granularity(SkyContext*, int, int* in_effect) { if (in_effect) *in_effect = 0; return 0; }  // no L2 to configure
 int orc_set_launch_shape(SkyContext* ctx, int kernel, int shape) { return kernel == SKY_KERNEL_K16 && shape >= SKY_K16_AUTO && shape <= SKY_K16_LITERAL ? 0 : fail(ctx, "set_launch_shape: unknown kernel or shape"); }
 int orc_set_lut_arithmetic(SkyContext*, int) { return 0; }     // ... and the exact LUT march
 int orc_set_strict_arithmetic(SkyContext*, int) { return 0; }  // the oracle IS the strict arithmetic

@@ -214,7 +214,6 @@ KERNEL_API = {
     "write_resource": ([I, _VOIDP, C.c_uint64], I),
     "counters_enable": ([I], I),
     "set_hw_filtering": ([I], I),
-    "set_l2_fetch_granularity": ([I, P(I)], I),
     "set_strict_arithmetic": ([I], I),
     "set_lut_arithmetic": ([I], I),
     "set_frame_overlap": ([I], I),
@@ -431,11 +430,6 @@ class Context:
     def counters_enable(self, on): self._call("counters_enable", int(on))
     def set_hw_filtering(self, on): self._call("set_hw_filtering", int(on))
 
-    def set_l2_fetch_granularity(self, nbytes=0):
-        """cudaLimitMaxL2FetchGranularity of the context's device (32 / 64 / 128; 0 only queries); returns the value in effect."""
-        now = C.c_int(0)
-        self._call("set_l2_fetch_granularity", int(nbytes), C.byref(now))
-        return now.value
     def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))
     def set_lut_arithmetic(self, mode): self._call("set_lut_arithmetic", int(mode))
     def set_frame_overlap(self, on): self._call("set_frame_overlap", int(on))

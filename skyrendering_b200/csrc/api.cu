@@ -973,19 +973,6 @@ int sky_set_hw_filtering(SkyContext* ctx, int enable) {
     return 0;
 }
 
-int sky_set_l2_fetch_granularity(SkyContext* ctx, int bytes, int* in_effect) {
-    if (!ctx) return 1;
-    if (bytes != 0 && bytes != 32 && bytes != 64 && bytes != 128) return sky_fail(ctx, "set_l2_fetch_granularity: 0 (query), 32, 64 or 128 bytes");
-    SKY_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (bytes) SKY_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(bytes)));
-    if (in_effect) {
-        size_t now = 0;
-        SKY_CUDA(ctx, cudaDeviceGetLimit(&now, cudaLimitMaxL2FetchGranularity));
-        *in_effect = int(now);
-    }
-    return 0;
-}
-
 int sky_tex_peak(SkyContext* ctx, int mode, double* fetches_per_second) {
     if (int e = lanes_join(ctx)) return e;
     return launch_tex_peak(ctx, mode, fetches_per_second);

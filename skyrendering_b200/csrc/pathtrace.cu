@@ -202,8 +202,12 @@ enum : int {
 #undef SKY_K19_FOLD
 #define SKY_K19_FOLD 0
 #endif
-#ifndef SKY_K19_OCC
+#ifndef SKY_K19_OCC   // resident 128-thread blocks per SM.  With the folded hot block the production kernel fits 80 registers without spilling:
+#ifdef SKY_STRICT_TU  // measured (profiles/k19_occ_r02J.log, 64 kFrameIds): 4 -> 82.4, 5 -> 89.8, 6 -> 91.6 Msamples/s
 #define SKY_K19_OCC 5
+#else
+#define SKY_K19_OCC 6
+#endif
 #endif
 constexpr int kTrackRounds = SKY_K19_TRACK_ROUNDS, kBatch = SKY_K19_BATCH;
 // free-flight logarithm: logf (<= 1 ulp) or the MUFU.LG2-based __logf (what GLSL's log() compiles to on this hardware)

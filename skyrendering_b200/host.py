@@ -51,6 +51,7 @@ def _host():
             "skyhost_ground_depth": ([V, C.c_void_p, I, I], I),
             "skyhost_ground_gbuffer": ([V, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, I, I], I),
             "skyhost_png_load": ([C.c_char_p, I, P(I), P(I), P(I), P(I), C.c_void_p, C.c_int64], I),
+            "skyhost_jpeg_load": ([C.c_char_p, I, P(I), P(I), P(I), C.c_void_p, C.c_int64], I),
             "skyhost_vdb_open": ([C.c_char_p, P(V)], I),
             "skyhost_vdb_parse": ([C.c_void_p, C.c_int64, P(V)], I),
             "skyhost_vdb_close": ([V], None),
@@ -70,7 +71,7 @@ HOST_SYMBOLS = [
     "skyhost_atmosphere_buffer", "skyhost_lut_config", "skyhost_atmosphere_render_buffer", "skyhost_set_viewport",
     "skyhost_cloud_update", "skyhost_noise_info", "skyhost_set_voxel_dim", "skyhost_material_type", "skyhost_pt_params",
     "skyhost_pt_init", "skyhost_pt_region", "skyhost_camera_get", "skyhost_camera_move", "skyhost_view_projection",
-    "skyhost_earth_buffer", "skyhost_png_load", "skyhost_ground_depth", "skyhost_ground_gbuffer", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
+    "skyhost_earth_buffer", "skyhost_png_load", "skyhost_jpeg_load", "skyhost_ground_depth", "skyhost_ground_gbuffer", "skyhost_vdb_open", "skyhost_vdb_parse", "skyhost_vdb_close", "skyhost_vdb_info", "skyhost_vdb_fill_r8",
     "skyhost_vdb_fill_float",
 ]
 
@@ -211,6 +212,19 @@ def load_png(path, flip_vertically=True):
         raise RuntimeError(L.skyhost_last_error().decode())
     out = np.empty((h.value, w.value, c.value), np.uint16 if b.value == 16 else np.uint8)
     if L.skyhost_png_load(os.fsencode(path), int(flip_vertically), None, None, None, None, out.ctypes.data, out.nbytes) != 0:
+        raise RuntimeError(L.skyhost_last_error().decode())
+    return out[..., 0] if c.value == 1 else out
+
+
+def load_jpeg(path, flip_vertically=True):
+    """stbi_load of a JPEG with the reference's vertical flip (StbImage.cpp:12-17; Textures.cpp:27-58: the NASA earth / star / moon maps): uint8
+    [H][W][3] (or [H][W] for a grey file), row 0 = the bottom row of the image when `flip_vertically` -- the GL texel order the reference uploads."""
+    L = _host()
+    w, h, c = I(), I(), I()
+    if L.skyhost_jpeg_load(os.fsencode(path), int(flip_vertically), C.byref(w), C.byref(h), C.byref(c), None, 0) != 0:
+        raise RuntimeError(L.skyhost_last_error().decode())
+    out = np.empty((h.value, w.value, c.value), np.uint8)
+    if L.skyhost_jpeg_load(os.fsencode(path), int(flip_vertically), None, None, None, out.ctypes.data, out.nbytes) != 0:
         raise RuntimeError(L.skyhost_last_error().decode())
     return out[..., 0] if c.value == 1 else out
 

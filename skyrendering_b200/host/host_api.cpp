@@ -6,6 +6,7 @@
 #include "scene.h"
 #include "vdb.h"
 #include "png.h"
+#include "jpeg.h"
 #include <cstring>
 #include <stdexcept>
 
@@ -212,6 +213,29 @@ int skyhost_png_load(const char* path, int flip_vertically, int32_t* width, int3
             if (bytes_per_sample == 1) std::memcpy(row, src, stride);
             else for (size_t i = 0; i < stride; i += 2) { row[i] = src[i + 1]; row[i + 1] = src[i]; }   // big-endian file -> little-endian host
         }
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+int skyhost_jpeg_load(const char* path, int flip_vertically, int32_t* width, int32_t* height, int32_t* channels, void* out, int64_t out_bytes) {
+    try {
+        static thread_local std::string cached_path;          // the two-call protocol decodes a (progressive, multi-megapixel) file once
+        static thread_local skyhost::JpegImage cached;
+        const std::string name = path ? path : "";
+        if (name != cached_path || cached.samples.empty()) { cached = skyhost::JpegImage{}; cached_path.clear(); cached = skyhost::load_jpeg(name); cached_path = name; }
+        const skyhost::JpegImage& im = cached;
+        if (width) *width = im.width;
+        if (height) *height = im.height;
+        if (channels) *channels = im.channels;
+        if (!out) return 0;
+        const size_t stride = size_t(im.width) * im.channels;
+        if (out_bytes != int64_t(stride * im.height)) throw std::runtime_error("jpeg_load: the buffer must hold width * height * channels bytes");
+        uint8_t* dst = static_cast<uint8_t*>(out);
+        for (int y = 0; y < im.height; ++y) std::memcpy(dst + size_t(y) * stride, im.samples.data() + size_t(flip_vertically ? im.height - 1 - y : y) * stride, stride);
+        cached = skyhost::JpegImage{}; cached_path.clear();
         return 0;
     } catch (const std::exception& e) {
         g_error = e.what();

@@ -2,10 +2,10 @@
 // AppWindow::HandleDisplayEvent / Render do per frame (src/SkyRendering/AppWindow.cpp:139-181), without a window.
 //
 //   skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file.vdb] [--raw8 file dx dy dz]
-//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--coop-luts] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]
+//             [--hw-filtering] [--strict] [--overlap] [--pipeline] [--coop-luts] [--objects] [--earth-map file.png|file.jpg] [--out image.ppm] [--dump-rgba8 file]
 // --objects shades object pixels like the reference (AtmosphereRenderer.glsl:284-343): the environment-BRDF LUT once, the IBL tail
 // of the LUT phase every frame, and the G-buffer of the analytic ground pass (skyhost_ground_gbuffer) bound with sky_set_gbuffer.
-// With --earth-map (an 8-bit RGB PNG, equirectangular, read by the host library's PNG reader with the reference's vertical flip) the frame
+// With --earth-map (an 8-bit RGB PNG or JPEG, equirectangular, read by the host library's own readers with the reference's vertical flip) the frame
 // runs the reference's own order instead: Clear(gbuffer), Earth::RenderToGBuffer as the kernel K7 (sky_gbuffer_clear, sky_earth_gbuffer) into
 // the depth plane and the G-buffer, then the composite with the object branch on what K7 wrote.
 //
@@ -119,7 +119,7 @@ struct Driver {
 
 int main(int argc, char** argv) {
     if (argc < 4) die("usage: skyrender <scene.json> <width> <height> [--frames N] [--warmup N] [--spp N] [--vdb file] [--raw8 file dx dy dz] "
-                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--coop-luts] [--objects] [--earth-map file.png] [--out image.ppm] [--dump-rgba8 file]");
+                      "[--hw-filtering] [--strict] [--overlap] [--pipeline] [--coop-luts] [--objects] [--earth-map file.png|file.jpg] [--out image.ppm] [--dump-rgba8 file]");
     const std::string scene_path = argv[1];
     Driver d;
     d.width = std::atoi(argv[2]);
@@ -206,11 +206,16 @@ int main(int argc, char** argv) {
     void *gb_albedo = nullptr, *gb_normal = nullptr, *gb_orm = nullptr;
     if (d.objects && !earth_map.empty()) {  // Textures::Textures: the earth albedo map (Textures.cpp:52-58), then K7 fills the G-buffer every frame
         sky_ok(sky_env_brdf_lut(d.ctx), "env_brdf_lut");
-        int32_t mw = 0, mh = 0, mc = 0, mb = 0;
-        host_ok(skyhost_png_load(earth_map.c_str(), 1, &mw, &mh, &mc, &mb, nullptr, 0), "png_load");
-        if (mc != 3 || mb != 8) die("--earth-map: an 8-bit RGB PNG is expected");
+        int32_t mw = 0, mh = 0, mc = 0, mb = 8;
+        unsigned char magic[2] = {0, 0};
+        if (FILE* f = std::fopen(earth_map.c_str(), "rb")) { if (std::fread(magic, 1, 2, f) != 2) magic[0] = 0; std::fclose(f); }
+        const bool jpeg = magic[0] == 0xff && magic[1] == 0xd8;   // the reference's own map (data/NASA/world.topo.bathy...jpg) is a progressive JPEG
+        if (jpeg) host_ok(skyhost_jpeg_load(earth_map.c_str(), 1, &mw, &mh, &mc, nullptr, 0), "jpeg_load");
+        else host_ok(skyhost_png_load(earth_map.c_str(), 1, &mw, &mh, &mc, &mb, nullptr, 0), "png_load");
+        if (mc != 3 || mb != 8) die("--earth-map: an 8-bit RGB PNG or JPEG is expected");
         std::vector<uint8_t> texels(size_t(mw) * mh * 3);
-        host_ok(skyhost_png_load(earth_map.c_str(), 1, nullptr, nullptr, nullptr, nullptr, texels.data(), int64_t(texels.size())), "png_load");
+        if (jpeg) host_ok(skyhost_jpeg_load(earth_map.c_str(), 1, nullptr, nullptr, nullptr, texels.data(), int64_t(texels.size())), "jpeg_load");
+        else host_ok(skyhost_png_load(earth_map.c_str(), 1, nullptr, nullptr, nullptr, nullptr, texels.data(), int64_t(texels.size())), "png_load");
         sky_ok(sky_set_earth_albedo(d.ctx, texels.data(), mw, mh), "set_earth_albedo");
         cuda_ok(cudaMalloc(&d.gdepth, npix * 4), "cudaMalloc");
         cuda_ok(cudaMalloc(&gb_albedo, npix * 4), "cudaMalloc");

@@ -39,6 +39,20 @@ def load_blue_noise(path=None):
     return np.fromfile(os.path.join(_DATA, "blue_noise_64x64.u16"), dtype="<u2").reshape(64, 64)
 
 
+def load_srgb_map(path):
+    """An 8-bit RGB image in GL texel order for sky_set_star_map / sky_set_earth_albedo, as Textures::Textures loads the reference's NASA maps
+    (Textures.cpp:27-58: stbi_load with the vertical flip, uploaded as GL_SRGB8): a JPEG (host/jpeg.cpp, byte-identical to stb_image) or an 8-bit PNG."""
+    from .host import load_jpeg, load_png
+    with open(path, "rb") as f:
+        magic = f.read(4)
+    image = load_png(path, flip_vertically=True) if magic == b"\x89PNG" else load_jpeg(path, flip_vertically=True)
+    if image.dtype != np.uint8:
+        raise ValueError(f"{path}: an 8-bit image is needed, got {image.dtype}")
+    if image.ndim == 2:
+        image = np.repeat(image[..., None], 3, axis=2)
+    return np.ascontiguousarray(image[..., :3])
+
+
 def scene_path(name):
     return os.path.join(SCENES_DIR, SCENE_FILES.get(name, name))
 

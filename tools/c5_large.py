@@ -34,7 +34,6 @@ print(f"grid {grid.shape[2]}x{grid.shape[1]}x{grid.shape[0]} {grid.nbytes / 1e9:
 region = [0, 0, W, H]
 
 if mode == "launch":
-    if os.environ.get("FINAL_GRANULARITY"): print("granularity in effect", r.ctx.set_l2_fetch_granularity(int(os.environ["FINAL_GRANULARITY"])), flush=True)
     r.ctx.set_hw_filtering(bool(int(os.environ.get("HW", "0"))))
     r.ctx.pt_samples(common, 1, spp, region)
     torch.cuda.synchronize()
@@ -54,17 +53,6 @@ def launch_ms(reps=3):
     return float(np.mean(out)), out
 
 
-gran_default = r.ctx.set_l2_fetch_granularity(0)
-sweep = {}
-for g in [int(x) for x in os.environ.get("GRANULARITY", "").split(",") if x]:
-    eff = r.ctx.set_l2_fetch_granularity(g)
-    m, each = launch_ms()
-    r.ctx.set_hw_filtering(True)
-    mt, _ = launch_ms()
-    r.ctx.set_hw_filtering(False)
-    sweep[str(g)] = {"in_effect": eff, "cells_ms_per_launch": m, "cells_ms_each": each, "cells_gsamples_per_s": W * H * spp / (m * 1e-3) / 1e9, "texture_ms_per_launch": mt}
-    print(f"L2 fetch granularity {g} (in effect {eff}): cells {m:.1f} ms = {W * H * spp / m / 1e3:.1f} Msamples/s, texture array {mt:.1f} ms", flush=True)
-r.ctx.set_l2_fetch_granularity(int(os.environ.get("FINAL_GRANULARITY", str(gran_default))))
 ms_cells, all_cells = launch_ms()
 r.ctx.counters_enable(True)
 r.ctx.pt_samples(common, 1, spp, region); r.ctx.sync()
@@ -76,7 +64,7 @@ ms_tex, all_tex = launch_ms()
 r.ctx.set_hw_filtering(False)
 out = {"workload": f"c5 path tracer {W}x{H}, synthetic {grid.shape[2]}x{grid.shape[1]}x{grid.shape[0]} R8 grid ({grid.nbytes / 1e9:.2f} GB of voxels), reference defaults, "
                    f"one launch of {spp} kFrameIds, L2 flushed between launches",
-       "l2_fetch_granularity_default": gran_default, "l2_fetch_granularity": r.ctx.set_l2_fetch_granularity(0), "granularity_sweep": sweep, "grid_generate_s": t_gen, "upload_and_pack_s": t_up, "device_memory_in_use_gb": (total_b - free_b) / 1e9,
+       "grid_generate_s": t_gen, "upload_and_pack_s": t_up, "device_memory_in_use_gb": (total_b - free_b) / 1e9,
        "lookups_per_launch": lookups, "tentative_collisions_per_launch": coll, "paths_per_launch": paths, "lookups_per_path": lookups / max(1, paths),
        "corner_packed_cells": {"ms_per_launch": ms_cells, "ms_each": all_cells, "gsamples_per_s": W * H * spp / (ms_cells * 1e-3) / 1e9,
                                "algorithmic_8B_gbs": lookups * 8 / (ms_cells * 1e-3) / 1e9, "sector_32B_upper_bound_gbs": lookups * 32 / (ms_cells * 1e-3) / 1e9},
