@@ -202,6 +202,13 @@ enum : int {
 #undef SKY_K19_FOLD
 #define SKY_K19_FOLD 0
 #endif
+#ifndef SKY_K19_BRANCHLESS   // 1: resolution of a batch as selects; 2: the blends of a batch too
+#define SKY_K19_BRANCHLESS 2   // measured (profiles/k19_branchless_r02K.log, 64 kFrameIds): 0 -> 91.9, 1 -> 98.7, 2 -> 100.0 Msamples/s, accumulators byte-identical
+#endif
+#if defined(SKY_STRICT_TU) && SKY_K19_BRANCHLESS
+#undef SKY_K19_BRANCHLESS
+#define SKY_K19_BRANCHLESS 0
+#endif
 #ifndef SKY_K19_OCC   // resident 128-thread blocks per SM.  With the folded hot block the production kernel fits 80 registers without spilling:
 #ifdef SKY_STRICT_TU  // measured (profiles/k19_occ_r02J.log, 64 kFrameIds): 4 -> 82.4, 5 -> 89.8, 6 -> 91.6 Msamples/s
 #define SKY_K19_OCC 5
@@ -445,7 +452,17 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                     for (int k = 0; k < kBatch; ++k) cell[k] = voxel_tap_load(P.mat.voxel, tap[k], live[k]);
 #pragma unroll
 #if SKY_K19_FOLD >= 2   // sig[] holds sigma_t / sigma_t_max directly: one multiplication for (1/255) * uDensity / sigma_t_max
+#if SKY_K19_BRANCHLESS >= 2
+                    // every lane blends the cell it loaded (a lane that is not live loaded cell 0) and the result is selected: four reconvergence
+                    // regions fewer per batch; a warp in which NO lane is live at position k is rare once paths have desynchronised
+                    for (int k = 0; k < kBatch; ++k) {
+                        float blended = blend_cell_raw(cell[k], tap[k].a, tap[k].b, tap[k].c) * P.v_collision_scale;
+                        asm volatile("" : "+f"(blended));   // keep the blend out of a conditional arm
+                        sig[k] = live[k] ? blended : 0.0f;
+                    }
+#else
                     for (int k = 0; k < kBatch; ++k) sig[k] = live[k] ? blend_cell_raw(cell[k], tap[k].a, tap[k].b, tap[k].c) * P.v_collision_scale : 0.0f;
+#endif
 #else
                     for (int k = 0; k < kBatch; ++k) sig[k] = live[k] ? blend_cell(cell[k], tap[k].a, tap[k].b, tap[k].c) * vm.uDensity : 0.0f;
 #endif
@@ -467,6 +484,43 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
 #endif
                 const float to_probability = kSigIsProbability ? 1.0f : inv_sigma_t_max;
                 // (3) in-order resolution
+#if SKY_K19_BRANCHLESS && !defined(SKY_K19_PROBE)
+                // Lanes of a warp are a mix of shadow rays and free flights almost all the time, so the nested `if`s below cost a warp BOTH arms for
+                // every collision (~30 instructions and four reconvergence regions per collision).  The same decisions as selects: every collision
+                // updates the running product under a predicate and remembers the first event (box exit or real collision) of the batch; the one
+                // divergent block that acts on the event runs once per batch.  Same operations on the same operands: the accumulator is bit-identical.
+                if (!COUNT) {
+                    bool alive = true, event_seen = false, event_is_exit = false;
+                    uint32_t event_s = s;
+                    float event_t = tk[kBatch - 1];
+#pragma unroll
+                    for (int k = 0; k < kBatch; ++k) {
+                        const float pk = kSigIsProbability ? sig[k] : sig[k] * to_probability;
+                        const bool out = tk[k] > t_max;
+                        const bool hit = float(sk[k]) * (1.0f / 4294967296.0f) < pk;                      // :191-195
+                        const float factor = 1.0f - fmaxf(0.0f, pk);                                     // :148
+                        // (bitwise, not short-circuit, operators: the compiler must not turn the tests back into branches)
+                        transmittance = (alive & !out & in_shadow) ? transmittance * factor : transmittance;
+                        const bool event = alive & (out | (!in_shadow & hit));
+                        event_is_exit = event ? out : event_is_exit;
+                        event_s = event ? sk[k] : event_s;
+                        event_t = event ? tk[k] : event_t;
+                        event_seen = event_seen | event;
+                        alive = alive & !event;
+                    }
+                    if (!event_seen) {
+                        t = tk[kBatch - 1]; seed = s;
+                    } else if (event_is_exit) {   // the ray left the box; the stream stands after this step's draw
+                        state = in_shadow ? ST_SHADOW_END : ST_EXIT_PRIMARY;
+                        seed = event_s;
+                    } else {
+                        state = ST_SCATTER;
+                        t = event_t;
+                        seed = PRNG<PRNG_KIND>(event_s);
+                    }
+                } else
+#endif
+                {
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k) {
                     if (state == ST_TRACK) {
@@ -489,6 +543,7 @@ __global__ void __launch_bounds__(128, SKY_K19_OCC) k19_path_trace(const __grid_
                     }
                 }
                 if (state == ST_TRACK) { t = tk[kBatch - 1]; seed = s; }
+                }
 #ifndef SKY_K19_NO_ZERO_CUT
                 // Zero-transmittance cut (exact): once the running product of a shadow ray is exactly 0 -- a texel at the
                 // majorant, or the underflow of ~10^2 collisions deep inside the cloud -- every further factor multiplies
