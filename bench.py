@@ -373,6 +373,11 @@ def main():
     sampler.start()
     pt_ms = timed_steps(pt_step, args.steps, args.warmup)
     clocks = sampler.stop()
+    launches_before = rp.ctx.launch_count()       # the library's own count (sky_launch_count) over K more steps like the timed ones
+    for _ in range(args.steps):
+        pt_step()
+    rp.ctx.sync()
+    pt_launches = rp.ctx.launch_count() - launches_before
     pt_value = PT_W * PT_H * args.spp / (pt_ms * 1e-3) / 1e9
 
     # end to end through the C-ABI call with HOST buffers (pinned), per rank its share + host-side sum on rank 0
@@ -476,6 +481,10 @@ def main():
         frame_overlap_ms = timed_frames(max(args.steps, 3), 1)
         rf.ctx.set_frame_pipelining(True)
         frame_ms = timed_frames(max(args.steps, 3), 1)
+        launches_before = rf.ctx.launch_count()       # the library's own count (sky_launch_count) over one more batch of frames
+        frame_batch()
+        rf.ctx.sync()
+        frame_launches = (rf.ctx.launch_count() - launches_before) / FRAME_BATCH
         frame_host_submit_ms = host_timing["ms_per_step"] / FRAME_BATCH   # if this approaches ms_per_frame the loop is host-bound, not GPU-bound
         other_luts = abi.LUT_EXACT if frame_luts == abi.LUT_COOPERATIVE else abi.LUT_COOPERATIVE
         rf.ctx.set_lut_arithmetic(other_luts)
@@ -577,7 +586,7 @@ def main():
                                 "ms_per_frame = consecutive frames with sky_set_frame_overlap (shadow + cloud chain beside LUTs + composite on a second stream) and "
                                 "sky_set_frame_pipelining (the LUT phase of frame N+1 beside frame N's K6 / K16, two LUT sets), "
                                 "parts_ms each kernel group alone",
-            "parts_ms": parts, "gpu_launches": 15, "frames_per_timed_iteration": FRAME_BATCH,
+            "parts_ms": parts, "gpu_launches": frame_launches, "frames_per_timed_iteration": FRAME_BATCH,
             "sigma_evals_per_frame": evals, "tex_fetches_per_frame": fetches,
             "roofline": {"kernel": "k16_render (+K14,K15)", "bound": "tex", "achieved": fetches / k16_s / 1e9, "peak": mix_peak / 1e9,
                          "unit": "Gfetch/s", "frac": fetches / k16_s / mix_peak, "traffic": ncu_traffic("k16_render_hw" if frame_hw else "k16_render"),
@@ -825,8 +834,9 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
-            # per step and rank: K19 (persistent state machine) + K19b (ordered accumulate) per chunk of <= 291 kFrameIds (4 GiB of sample slots)
-            "gpu_launches": args.steps * 2 * max(1, -(-my_count // 291)),
+            # counted by the library (sky_launch_count) over K steps on this rank: per step K19 (persistent state machine) + K19b (ordered accumulate)
+            # per chunk of <= 291 kFrameIds (4 GiB of sample slots)
+            "gpu_launches": pt_launches,
             "roofline": pt_roofline, "cpu_baseline": cpu_baseline,
             # short top-level keys for the driver's SCALE capture: the N-rank 4K frame time and the sharded-vs-single verdict
             "frame_4k_ms": None if frame is None else frame["ms_per_frame"], "sharded_equals_single": sharded_equals_single,

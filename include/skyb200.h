@@ -212,6 +212,9 @@ int SKY_FN(write_resource)(SkyContext* ctx, int resource, const void* host_src, 
 /* Work counters for the roofline: enable != 0 switches kernels to their counting
  * variants; counters live in SKY_RES_COUNTERS and are reset here. */
 int SKY_FN(counters_enable)(SkyContext* ctx, int enable);
+/* Number of kernel launches this context has issued since it was created (host-side count, one per launch; memsets and copies are not
+ * kernels).  bench.py reports the difference across its timed region as `gpu_launches`. */
+int SKY_FN(launch_count)(SkyContext* ctx, uint64_t* launches);
 
 /* Pin the launch shape of a kernel that has several (SkyKernelId / SkyK16Shape, sky_types.h); SKY_K16_AUTO restores the per-launch choice. */
 int SKY_FN(set_launch_shape)(SkyContext* ctx, int kernel, int shape);

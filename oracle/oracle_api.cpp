@@ -461,6 +461,7 @@ int orc_write_resource(SkyContext* ctx, int resource, const void* src, uint64_t 
     return fail(ctx, "write_resource: resource is not writable");
 }
 
+int orc_launch_count(SkyContext*, uint64_t* launches) { if (launches) *launches = 0; return 0; }  // the oracle launches nothing
 int orc_counters_enable(SkyContext* ctx, int enable) {
     ctx->scene.counting = enable != 0;
     for (auto& c : ctx->scene.counters) c = 0;

@@ -213,6 +213,7 @@ KERNEL_API = {
     "read_resource": ([I, _VOIDP, C.c_uint64], I),
     "write_resource": ([I, _VOIDP, C.c_uint64], I),
     "counters_enable": ([I], I),
+    "launch_count": ([P(C.c_uint64)], I),
     "set_hw_filtering": ([I], I),
     "set_strict_arithmetic": ([I], I),
     "set_lut_arithmetic": ([I], I),
@@ -428,6 +429,12 @@ class Context:
         self._call("tonemap", _ptr(hdr), width, height, C.byref(p), _ptr(out))
 
     def counters_enable(self, on): self._call("counters_enable", int(on))
+
+    def launch_count(self):
+        """kernel launches issued for this context so far (sky_launch_count)"""
+        n = C.c_uint64(0)
+        self._call("launch_count", C.byref(n))
+        return int(n.value)
     def set_hw_filtering(self, on): self._call("set_hw_filtering", int(on))
 
     def set_strict_arithmetic(self, on): self._call("set_strict_arithmetic", int(on))

@@ -912,6 +912,12 @@ int sky_write_resource(SkyContext* ctx, int resource, const void* host_src, uint
     return 0;
 }
 
+int sky_launch_count(SkyContext* ctx, uint64_t* launches) {
+    if (!ctx || !launches) return 1;
+    *launches = ctx->launch_count;
+    return 0;
+}
+
 int sky_counters_enable(SkyContext* ctx, int enable) {
     if (int e = lanes_join(ctx)) return e;
     ctx->counting = enable != 0;

@@ -64,6 +64,7 @@ struct SkyContext {
     bool strict_arithmetic = false;  // sky_set_strict_arithmetic: route K6, K11-K18, K19/K20 to the *_strict objects
     int lut_arithmetic = 0;          // sky_set_lut_arithmetic: SKY_LUT_EXACT (bit-faithful K2-K4) or the lane-cooperative production march
     bool counting = false;
+    unsigned long long launch_count = 0;   // kernel launches issued for this context (SKY_LAUNCH_CHECK follows every launch); sky_launch_count
     int k16_group = 0;               // SKYB200_K16_GROUP=4|8: force the wavefront kernel's rays per warp (0: chosen per launch, cloud.cu)
     bool k16_literal = false;        // SKYB200_K16_LITERAL=1: the production object launches k16_render (one lane = one ray, the shader's loop) instead of k16_render_coop
     int out_band_rows = 0, out_band_index = 0, out_band_count = 1;  // sky_set_output_bands: rows K6 / K18 own
@@ -231,7 +232,11 @@ int sky_fail(SkyContext* ctx, const std::string& msg);
         if (e__ != cudaSuccess)                                                                     \
             return sky_fail(ctx, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
     } while (0)
-#define SKY_LAUNCH_CHECK(ctx) SKY_CUDA(ctx, cudaGetLastError())
+#define SKY_LAUNCH_CHECK(ctx)                 \
+    do {                                      \
+        ++(ctx)->launch_count;                \
+        SKY_CUDA(ctx, cudaGetLastError());    \
+    } while (0)
 
 template <class T>
 int sky_alloc(SkyContext* ctx, Lut<T>& l, int w, int h, int d = 1, bool zero = true) {

@@ -715,6 +715,23 @@ def test_cpp_frame_driver_matches_the_python_driver(libs, tmp_path):
     assert np.array_equal(np.fromfile(dump, np.uint8).reshape(h, w, 4), img.cpu().numpy())
 
 
+def test_launch_count_counts_kernel_launches(libs):
+    """sky_launch_count: the host-side count bench.py reports as `gpu_launches` -- one path-tracing call on a small region is K19 + the ordered
+    accumulate (two launches; the job-counter memset is not a kernel), and the oracle, which launches nothing, reports 0."""
+    cuda, orc = libs
+    grid = synthetic_voxel_grid(63, 77, 43)
+    r, common, _ = run_path_trace("c5", 64, 36, cuda, 2, grid=grid, max_bounces=4, region_box_half_width=10.0)
+    before = r.ctx.launch_count()
+    assert before > 0                                   # the LUT bake, the shadow chain and the first path-tracing call
+    r.ctx.pt_samples(common, 3, 2, [0, 0, 64, 36])
+    r.ctx.sync()
+    assert r.ctx.launch_count() - before == 2
+    r.ctx.pt_samples(common, 5, 2, [64, 36, 64, 36])    # an empty region launches nothing
+    assert r.ctx.launch_count() - before == 2
+    ro, _, _ = run_path_trace("c5", 64, 36, orc, 1, grid=grid, max_bounces=2, region_box_half_width=10.0)
+    assert ro.ctx.launch_count() == 0
+
+
 def test_error_behaviour(libs):
     cuda, _ = libs
     ctx = abi.Context(cuda)
