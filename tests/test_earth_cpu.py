@@ -140,3 +140,30 @@ def test_detmath_against_double_precision():
     x, _, o = run(2, rng.uniform(-20, 20, n)); assert np.abs(o - np.cos(x)).max() < 2e-7
     _, _, o = run(5, [0.0, 0.0, 1.0, -1.0], [1.0, -1.0, 0.0, 0.0])
     assert np.allclose(o, [0.0, np.pi, np.pi / 2, -np.pi / 2], atol=1e-6)
+
+
+REF_EARTH_MAP = "/root/reference/data/NASA/world.topo.bathy.200401.3x5400x2700.jpg"
+
+
+@pytest.mark.skipif(not (refpin.reference_present() and __import__("os").path.exists(REF_EARTH_MAP)), reason="needs the reference tree (build container only)")
+def test_ground_pass_on_the_reference_earth_map():
+    """The whole input chain on the reference's own asset: the 5400 x 2700 progressive JPEG Textures.cpp:52-58 loads, decoded by the host library's
+    JPEG reader (byte-identical to stb_image, tests/test_jpeg.py), uploaded as GL_SRGB8 with its mip chain, sampled by K7 -- the oracle against the
+    reference's fragment shader text, bit for bit in all four targets (odd mip sizes: 2700 -> 1350 -> 675 -> 337 ...)."""
+    from skyrendering_b200.renderer import load_srgb_map
+    earth = load_srgb_map(REF_EARTH_MAP)
+    assert earth.shape == (2700, 5400, 3)
+    w, h = 160, 90
+    r = Renderer("c2", w, h, library=oracle_library())
+    r.prime()
+    r.ctx.set_earth_albedo(earth)
+    depth = np.ones((h, w), np.float32)
+    targets = [np.zeros((h, w, 4), dt) for dt in (np.uint8, np.int16, np.uint16)]
+    r.ground_pass(depth, *targets)
+    levels = r.ctx.earth_albedo_levels()
+    assert [l.shape[:2] for l in levels[:4]] == [(2700, 5400), (1350, 2700), (675, 1350), (337, 675)]
+    d, A, N, O = refpin.ref_earth_gbuffer(refpin.ref_library(), r, np.ones((h, w), np.float32), w, h, levels)
+    a, n, o = refpin.quantise_gbuffer(A, N, O)
+    assert np.array_equal(d, depth) and np.array_equal(a, targets[0]) and np.array_equal(n, targets[1]) and np.array_equal(o, targets[2])
+    kept = depth != 1
+    assert 0.2 < kept.mean() < 0.8 and len(np.unique(targets[0][kept][:, :3], axis=0)) > 10   # the map is sampled (this camera sees open ocean: dark blues)
