@@ -6,6 +6,7 @@
   * where /root/reference is present (this container): the same comparison live against oracle/_ref, so the fixture
     cannot go stale.
 The GPU half (CUDA path against the same digests) is tests/test_gpu_parity.py::test_cuda_matches_reference_shader_digests."""
+import os
 import numpy as np
 import pytest
 
@@ -314,3 +315,38 @@ def test_oracle_star_term_is_the_reference_fragment_program():
     r.ctx.set_star_map(None)
     r.ctx.composite(depth, hdr, w, h)
     assert np.array_equal(hdr.astype(np.float32), plain)
+
+
+REF_STAR_MAP = "/root/reference/data/NASA/starmap_2020_4k.jpg"
+
+
+@pytest.mark.skipif(not (refpin.reference_present() and os.path.exists(REF_STAR_MAP)), reason="the reference tree is only mounted in the build container")
+def test_oracle_star_term_on_the_reference_star_map():
+    """The same term on the reference's own asset: the 4096 x 2048 progressive JPEG Textures.cpp:43-50 loads, decoded by the host library's JPEG
+    reader (byte-identical to stb_image, tests/test_jpeg.py) and uploaded as GL_SRGB8 -- the oracle's composite against the reference's fragment program."""
+    from skyrendering_b200.renderer import load_blue_noise, load_srgb_map
+    from tests.parity import make_buffers
+    from tests import permutations
+    ref, orc = refpin.ref_library(), oracle_library()
+    w, h = 160, 90
+    stars = load_srgb_map(REF_STAR_MAP)
+    assert stars.shape == (2048, 4096, 3)
+    r = Renderer("c2", w, h, library=orc)
+    r.prime()
+    depth_np = r.scene.ground_depth(w, h)
+    depth, hdr = make_buffers(w, h, depth_np, "cpu")
+    r.frame(depth, hdr, 0.0)
+    froxel = r.ctx.read(abi.RES_SHADOW_FROXEL)
+    r.ctx.set_star_map(stars)
+    hdr[...] = 0
+    r.ctx.composite(depth, hdr, w, h)
+    got = hdr.astype(np.float32)
+    want = refpin.ref_composite(ref, r, depth_np, w, h, load_blue_noise(), froxel=froxel, star_linear=permutations.srgb_decode(stars))
+    want16 = want.astype(np.float16).astype(np.float32)
+    # at 160 x 90 one pixel column of this camera leaves the GLSL domain in the shader text (an inverse trigonometric function a few ulp outside
+    # [-1, 1]: undefined in GLSL, NaN in the shim, clamped by the oracle and the kernels -- DESIGN.md section 5, "Oracle"): excluded, and rare
+    defined = np.all(np.isfinite(want16[..., :3]), axis=-1)
+    assert defined.mean() > 0.999 and np.all(np.isfinite(got))
+    assert np.array_equal(got[..., :3][defined], want16[..., :3][defined])
+    sky = depth_np == 1
+    assert len(np.unique(got[sky][:, :3], axis=0)) > 100   # the Milky Way, not a constant
